@@ -1,0 +1,83 @@
+"""ctypes binding of libhoic_b200.so (include/hoic.h).  There is no CPU fallback: a missing library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhoic_b200.so")
+_lib = None
+
+OBS_DIM, ACT_DIM, FRAME_DIM, INFO_DIM, NQ, NV, MAX_CONTACTS = 617, 32, 212, 9, 33, 32, 32
+
+EXPORTS = [
+    "hoic_last_error", "hoic_version", "hoic_model_create", "hoic_model_destroy", "hoic_batch_create",
+    "hoic_batch_destroy", "hoic_batch_size", "hoic_set_motions", "hoic_set_reward_weights", "hoic_set_mode",
+    "hoic_reset", "hoic_step", "hoic_get_state", "hoic_set_state", "hoic_set_cur_t", "hoic_get_warmstart",
+    "hoic_set_warmstart", "hoic_get_contacts", "hoic_substep_debug", "hoic_get_derived", "hoic_get_rfc",
+    "hoic_get_counters", "hoic_launch_count",
+]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_ulonglong) for n in (
+        "env_steps", "substeps", "ncon", "nefc", "newton_iters", "ls_evals", "mpr_calls", "mpr_iters", "qp_iters",
+        "fail_physics", "fail_overflow", "chol_calls")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class HoicError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (python -m hoic_b200.build / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HoicError(f"{LIB_PATH} not found: build it with `python -m hoic_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        vp, ip, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.hoic_last_error.restype = C.c_char_p
+        L.hoic_version.restype = ip
+        L.hoic_model_create.restype = vp
+        L.hoic_model_create.argtypes = [C.c_char_p, sz, ip]
+        L.hoic_model_destroy.argtypes = [vp]
+        L.hoic_batch_create.restype = vp
+        L.hoic_batch_create.argtypes = [C.POINTER(vp), ip, vp, ip, ip]
+        L.hoic_batch_destroy.argtypes = [vp]
+        L.hoic_batch_size.argtypes = [vp]
+        L.hoic_set_motions.argtypes = [vp, vp, vp, vp, ip]
+        L.hoic_set_reward_weights.argtypes = [vp, vp]
+        L.hoic_set_mode.argtypes = [vp, ip]
+        L.hoic_reset.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.hoic_step.argtypes = [vp] + [vp] * 8 + [vp]
+        L.hoic_get_state.argtypes = [vp, vp, vp, vp]
+        L.hoic_set_state.argtypes = [vp, vp, vp, vp]
+        L.hoic_set_cur_t.argtypes = [vp, vp, vp]
+        L.hoic_get_warmstart.argtypes = [vp, vp, vp]
+        L.hoic_set_warmstart.argtypes = [vp, vp, vp]
+        L.hoic_get_contacts.argtypes = [vp, vp, vp, vp, vp]
+        L.hoic_substep_debug.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.hoic_get_derived.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.hoic_get_rfc.argtypes = [vp, vp, vp]
+        L.hoic_get_counters.argtypes = [vp, C.POINTER(Counters)]
+        L.hoic_launch_count.restype = C.c_ulonglong
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise HoicError(f"{what}: {lib().hoic_last_error().decode()}")
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)

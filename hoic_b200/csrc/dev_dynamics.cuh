@@ -1,0 +1,243 @@
+// dev_dynamics.cuh -- forward kinematics, CoM quantities, composite-rigid-body mass matrix, bias forces (RNE),
+// Jacobian transposes and semi-implicit Euler.  One warp per environment: lane = body / dof / geom index.
+// Restates MuJoCo 2.1 mj_kinematics / mj_comPos / mj_crb / mj_comVel / mj_rne / mj_jac / mj_Euler for this model
+// class; reference call site uhc/envs/ho_im4.py:545 (sim.step()).
+// Positions are stored relative to S_ORG (the hand root translation at forward time) to keep float32 cancellation
+// out of contact depths and relative poses.
+#pragma once
+#include "dev_math.cuh"
+
+// ---------------------------------------------------------------------------------------------- position stage
+__device__ void pos_stage(float* s, const DevModel& m, int lane) {
+  const float* q = s + S_QPOS;
+  const int nbody = m.nbody;
+  // origin
+  if (lane < 3) s[S_ORG + lane] = q[m.org_qadr + lane];
+  __syncwarp();
+  const V3 org = ld3(s + S_ORG);
+  if (lane == 0) {
+    st3(s + S_XPOS, -org);
+    stq(s + S_XQUAT, q4(1.f, 0.f, 0.f, 0.f));
+    M3 I = q2m(q4(1.f, 0.f, 0.f, 0.f));
+    stm(s + U_XMAT, I);
+  }
+  __syncwarp();
+  const int b = lane;
+  const int lvl = b < nbody ? m.body_level[b] : -1;
+  for (int L = 1; L <= m.nlevel; L++) {
+    if (lvl == L) {
+      const int p = m.body_parent[b], ja = m.body_jntadr[b], jn = m.body_jntnum[b];
+      V3 pos;
+      Q4 quat;
+      if (jn == 1 && m.jnt_type[ja] == J_FREE) {
+        const int a = m.jnt_qposadr[ja];
+        pos = ld3(q + a) - org;
+        quat = qnormalize(ldq(q + a + 3));
+        stq(s + S_QPOS + a + 3, quat);  // mj_kinematics normalises qpos in place
+        st3(s + U_XANCH + 3 * ja, pos);
+        st3(s + U_XAXIS + 3 * ja, ld3(m.jnt_axis[ja]));
+      } else {
+        const M3 Rp = ldm(s + U_XMAT + 9 * p);
+        pos = ld3(s + S_XPOS + 3 * p) + mulv(Rp, ld3(m.body_pos[b]));
+        quat = qmul(ldq(s + S_XQUAT + 4 * p), ldq(m.body_quat[b]));
+        for (int j = ja; j < ja + jn; j++) {
+          const M3 R = q2m(quat);
+          const V3 ax = mulv(R, ld3(m.jnt_axis[j]));
+          const V3 jp = ld3(m.jnt_pos[j]);
+          const V3 anchor = pos + mulv(R, jp);
+          st3(s + U_XAXIS + 3 * j, ax);
+          st3(s + U_XANCH + 3 * j, anchor);
+          const float qq = q[m.jnt_qposadr[j]] - m.qpos0[m.jnt_qposadr[j]];
+          if (m.jnt_type[j] == J_SLIDE) {
+            pos = pos + ax * qq;
+          } else {
+            quat = qmul(quat, aa2q(ld3(m.jnt_axis[j]), qq));
+            pos = anchor - rotq(quat, jp);
+          }
+        }
+      }
+      quat = qnormalize(quat);
+      st3(s + S_XPOS + 3 * b, pos);
+      stq(s + S_XQUAT + 4 * b, quat);
+      stm(s + U_XMAT + 9 * b, q2m(quat));
+    }
+    __syncwarp();
+  }
+  // geoms
+  if (lane < m.ngeom) {
+    const int gb = m.geom_body[lane];
+    const M3 R = ldm(s + U_XMAT + 9 * gb);
+    st3(s + S_GPOS + 3 * lane, ld3(s + S_XPOS + 3 * gb) + mulv(R, ld3(m.geom_pos[lane])));
+    stm(s + S_GMAT + 9 * lane, mulm(R, ldm(m.geom_mat[lane])));
+  }
+  // inertial frames, subtree CoM of each moving tree, cinert
+  V3 xipos = v3(0, 0, 0);
+  M3 ximat;
+  float mass = 0.f;
+  int slot = -1;
+  if (b < nbody && b > 0) {
+    const M3 R = ldm(s + U_XMAT + 9 * b);
+    xipos = ld3(s + S_XPOS + 3 * b) + mulv(R, ld3(m.body_ipos[b]));
+    ximat = mulm(R, ldm(m.body_imat[b]));
+    mass = m.body_mass[b];
+    slot = m.body_rootslot[b];
+  }
+  for (int r = 0; r < m.nroot; r++) {
+    const float w = slot == r ? mass : 0.f;
+    const float cx = wsum(w * xipos.x), cy = wsum(w * xipos.y), cz = wsum(w * xipos.z);
+    if (lane == 0) st3(s + S_COM + 3 * r, v3(cx, cy, cz) * m.root_invmass[r]);
+  }
+  __syncwarp();
+  if (b < nbody) {
+    float ci[10];
+    if (b > 0 && slot >= 0) inert_com(ci, m.body_inertia[b], ximat, xipos - ld3(s + S_COM + 3 * slot), mass);
+    else
+      for (int k = 0; k < 10; k++) ci[k] = 0.f;
+    for (int k = 0; k < 10; k++) { s[U_CINERT + 10 * b + k] = ci[k]; s[U_CRB + 10 * b + k] = ci[k]; }
+  }
+  // cdof, lane = dof
+  if (lane < m.nv) {
+    const int j = m.dof_jnt[lane], jb = m.jnt_body[j], t = m.jnt_type[j];
+    const V3 off = ld3(s + S_COM + 3 * m.dof_rootslot[lane]) - ld3(s + U_XANCH + 3 * j);
+    V3 rot = v3(0, 0, 0), lin = v3(0, 0, 0);
+    if (t == J_FREE) {
+      const int k = lane - m.jnt_dofadr[j];
+      if (k < 3) { setcomp(lin, k, 1.f); }
+      else { rot = col(ldm(s + U_XMAT + 9 * jb), k - 3); lin = cross(rot, off); }
+    } else if (t == J_SLIDE) {
+      lin = ld3(s + U_XAXIS + 3 * j);
+    } else {
+      rot = ld3(s + U_XAXIS + 3 * j);
+      lin = cross(rot, off);
+    }
+    st3(s + S_CDOF + 6 * lane, rot);
+    st3(s + S_CDOF + 6 * lane + 3, lin);
+  }
+  __syncwarp();
+  // composite inertias: parents gather their children, deepest level first
+  for (int L = m.nlevel - 1; L >= 1; L--) {
+    if (lvl == L) {
+      for (int c = m.body_firstchild[b]; c >= 0; c = m.body_nextsib[c])
+        for (int k = 0; k < 10; k++) s[U_CRB + 10 * b + k] += s[U_CRB + 10 * c + k];
+    }
+    __syncwarp();
+  }
+  // mass matrix, lane = dof i: row i entries for i and its ancestors
+#pragma unroll 4
+  for (int j = 0; j < 32; j++) s[S_M + lane * 33 + j] = (j == lane && lane >= m.nv) ? 1.f : 0.f;
+  __syncwarp();
+  if (lane < m.nv) {
+    float buf[6];
+    mul_inert_vec(buf, s + U_CRB + 10 * m.dof_body[lane], s + S_CDOF + 6 * lane);
+    for (int j = lane; j >= 0; j = m.dof_parent[j]) {
+      const float* c = s + S_CDOF + 6 * j;
+      float v = c[0] * buf[0] + c[1] * buf[1] + c[2] * buf[2] + c[3] * buf[3] + c[4] * buf[4] + c[5] * buf[5];
+      if (j == lane) v += m.dof_armature[lane];
+      s[S_M + lane * 33 + j] = v;
+      s[S_M + j * 33 + lane] = v;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------- velocity stage
+// cvel / cdof_dot, then bias forces by recursive Newton-Euler.  Needs U_CINERT from pos_stage (same substep).
+__device__ void vel_stage(float* s, const DevModel& m, int lane) {
+  const float* qv = s + S_QVEL;
+  const int b = lane;
+  const int lvl = b < m.nbody ? m.body_level[b] : -1;
+  if (lane == 0) {
+    for (int k = 0; k < 6; k++) { s[U_CVEL + k] = 0.f; s[U_CACC + k] = k < 3 ? 0.f : -m.gravity[k - 3]; s[U_CFRC + k] = 0.f; }
+  }
+  __syncwarp();
+  for (int L = 1; L <= m.nlevel; L++) {
+    if (lvl == L) {
+      const int p = m.body_parent[b], da = m.body_dofadr[b], dn = m.body_dofnum[b];
+      float cv[6], ca[6], t1[6], t2[6], t3[6];
+      for (int k = 0; k < 6; k++) { cv[k] = s[U_CVEL + 6 * p + k]; ca[k] = s[U_CACC + 6 * p + k]; }
+      for (int j = 0; j < dn; j++) {
+        const int d = da + j;
+        if (m.jnt_type[m.dof_jnt[d]] == J_FREE) {
+          for (int k3 = 0; k3 < 3; k3++) {
+            for (int k = 0; k < 6; k++) { s[U_CDOFDOT + 6 * (d + k3) + k] = 0.f; cv[k] += s[S_CDOF + 6 * (d + k3) + k] * qv[d + k3]; }
+          }
+          for (int k3 = 3; k3 < 6; k3++) {
+            cross_motion(t1, cv, s + S_CDOF + 6 * (d + k3));
+            for (int k = 0; k < 6; k++) s[U_CDOFDOT + 6 * (d + k3) + k] = t1[k];
+          }
+          for (int k3 = 3; k3 < 6; k3++)
+            for (int k = 0; k < 6; k++) cv[k] += s[S_CDOF + 6 * (d + k3) + k] * qv[d + k3];
+          j += 5;
+        } else {
+          cross_motion(t1, cv, s + S_CDOF + 6 * d);
+          for (int k = 0; k < 6; k++) { s[U_CDOFDOT + 6 * d + k] = t1[k]; cv[k] += s[S_CDOF + 6 * d + k] * qv[d]; }
+        }
+      }
+      for (int j = 0; j < dn; j++)
+        for (int k = 0; k < 6; k++) ca[k] += s[U_CDOFDOT + 6 * (da + j) + k] * qv[da + j];
+      mul_inert_vec(t1, s + U_CINERT + 10 * b, ca);
+      mul_inert_vec(t2, s + U_CINERT + 10 * b, cv);
+      cross_force(t3, cv, t2);
+      for (int k = 0; k < 6; k++) { s[U_CVEL + 6 * b + k] = cv[k]; s[U_CACC + 6 * b + k] = ca[k]; s[U_CFRC + 6 * b + k] = t1[k] + t3[k]; }
+    }
+    __syncwarp();
+  }
+  for (int L = m.nlevel - 1; L >= 1; L--) {
+    if (lvl == L) {
+      for (int c = m.body_firstchild[b]; c >= 0; c = m.body_nextsib[c])
+        for (int k = 0; k < 6; k++) s[U_CFRC + 6 * b + k] += s[U_CFRC + 6 * c + k];
+    }
+    __syncwarp();
+  }
+  if (lane < m.nv) {
+    const float* c = s + S_CDOF + 6 * lane;
+    const float* f = s + U_CFRC + 6 * m.dof_body[lane];
+    s[S_BIAS + lane] = c[0] * f[0] + c[1] * f[1] + c[2] * f[2] + c[3] * f[3] + c[4] * f[4] + c[5] * f[5];
+  } else {
+    s[S_BIAS + lane] = 0.f;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------- J^T wrench
+// mj_applyFT: qfrc[lane] contribution of (force, torque) at `point` (relative to S_ORG of the stored kinematics)
+__device__ __forceinline__ float apply_ft(const float* s, const DevModel& m, int lane, V3 force, V3 torque, V3 point, int body) {
+  if (lane >= m.nv || !((m.body_chain[body] >> lane) & 1u)) return 0.f;
+  const V3 off = point - ld3(s + S_COM + 3 * m.dof_rootslot[lane]);
+  const V3 rot = ld3(s + S_CDOF + 6 * lane), lin = ld3(s + S_CDOF + 6 * lane + 3);
+  const V3 jp = lin + cross(rot, off);
+  return dot(jp, force) + dot(rot, torque);
+}
+
+// ---------------------------------------------------------------------------------------------- Euler
+// mj_Euler with implicit joint damping: (M + h diag(damping)) qacc' = qfrc_smooth + qfrc_constraint.
+// Returns false on a failed factorisation.
+__device__ bool euler_step(float* s, const DevModel& m, int lane, unsigned long long* chol_calls) {
+  const float h = m.timestep;
+#pragma unroll 4
+  for (int j = 0; j < 32; j++) s[S_H + lane * 33 + j] = s[S_M + lane * 33 + j];
+  if (lane < m.nv) s[S_H + lane * 33 + lane] += h * m.dof_damping[lane];
+  __syncwarp();
+  float qa;
+  const float rhs = lane < m.nv ? s[S_SMOOTH + lane] + s[S_FCON + lane] : 0.f;
+  const bool ok = warp_chol_solve(s + S_H, rhs, &qa, lane);
+  (void)chol_calls;
+  __syncwarp();
+  if (lane < m.nv) s[S_QVEL + lane] += h * qa;
+  __syncwarp();
+  if (lane < m.njnt) {
+    const int qa_ = m.jnt_qposadr[lane], da = m.jnt_dofadr[lane];
+    if (m.jnt_type[lane] == J_FREE) {
+      for (int k = 0; k < 3; k++) s[S_QPOS + qa_ + k] += h * s[S_QVEL + da + k];
+      V3 w = ld3(s + S_QVEL + da + 3);
+      const float ang = h * normalize(w);
+      const Q4 qn = qmul(qnormalize(ldq(s + S_QPOS + qa_ + 3)), aa2q(w, ang));
+      stq(s + S_QPOS + qa_ + 3, qn);
+    } else {
+      s[S_QPOS + qa_] += h * s[S_QVEL + da];
+    }
+  }
+  s[S_WARM + lane] = s[S_QACC + lane];
+  __syncwarp();
+  return ok;
+}

@@ -1,0 +1,216 @@
+// dev_math.cuh -- float32 vector / quaternion / spatial-algebra helpers and warp-level linear algebra.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "dev_model.h"
+
+#define FULLMASK 0xffffffffu
+#define F_MINVAL 1e-15f
+#define F_MAXVAL 1e10f
+#define F_PI 3.14159265358979323846f
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st3(float* p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float norm(V3 a) { return sqrtf(dot(a, a)); }
+// mju_normalize3 semantics: returns the norm, tiny vectors become (1,0,0)
+__device__ __forceinline__ float normalize(V3& a) {
+  float n = norm(a);
+  if (n < F_MINVAL) { a = v3(1.f, 0.f, 0.f); }
+  else { float s = 1.0f / n; a = a * s; }
+  return n;
+}
+__device__ __forceinline__ float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+__device__ __forceinline__ void setcomp(V3& a, int i, float v) { if (i == 0) a.x = v; else if (i == 1) a.y = v; else a.z = v; }
+
+struct Q4 { float w, x, y, z; };
+__device__ __forceinline__ Q4 q4(float w, float x, float y, float z) { Q4 q; q.w = w; q.x = x; q.y = y; q.z = z; return q; }
+__device__ __forceinline__ Q4 ldq(const float* p) { return q4(p[0], p[1], p[2], p[3]); }
+__device__ __forceinline__ void stq(float* p, Q4 q) { p[0] = q.w; p[1] = q.x; p[2] = q.y; p[3] = q.z; }
+__device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
+  return q4(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+            a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w);
+}
+__device__ __forceinline__ Q4 qconj(Q4 a) { return q4(a.w, -a.x, -a.y, -a.z); }
+__device__ __forceinline__ Q4 qnormalize(Q4 q) {
+  float n = sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  if (n < F_MINVAL) return q4(1.f, 0.f, 0.f, 0.f);
+  float s = 1.0f / n;
+  return q4(q.w * s, q.x * s, q.y * s, q.z * s);
+}
+// row-major 3x3 in registers
+struct M3 { float m[9]; };
+__device__ __forceinline__ M3 q2m(Q4 q) {
+  M3 r;
+  float w = q.w, x = q.x, y = q.y, z = q.z;
+  r.m[0] = w * w + x * x - y * y - z * z; r.m[1] = 2 * (x * y - w * z); r.m[2] = 2 * (x * z + w * y);
+  r.m[3] = 2 * (x * y + w * z); r.m[4] = w * w - x * x + y * y - z * z; r.m[5] = 2 * (y * z - w * x);
+  r.m[6] = 2 * (x * z - w * y); r.m[7] = 2 * (y * z + w * x); r.m[8] = w * w - x * x - y * y + z * z;
+  return r;
+}
+__device__ __forceinline__ M3 ldm(const float* p) { M3 r; for (int i = 0; i < 9; i++) r.m[i] = p[i]; return r; }
+__device__ __forceinline__ void stm(float* p, const M3& a) { for (int i = 0; i < 9; i++) p[i] = a.m[i]; }
+__device__ __forceinline__ V3 mulv(const M3& a, V3 v) {
+  return v3(a.m[0] * v.x + a.m[1] * v.y + a.m[2] * v.z, a.m[3] * v.x + a.m[4] * v.y + a.m[5] * v.z,
+            a.m[6] * v.x + a.m[7] * v.y + a.m[8] * v.z);
+}
+__device__ __forceinline__ V3 mulTv(const M3& a, V3 v) {
+  return v3(a.m[0] * v.x + a.m[3] * v.y + a.m[6] * v.z, a.m[1] * v.x + a.m[4] * v.y + a.m[7] * v.z,
+            a.m[2] * v.x + a.m[5] * v.y + a.m[8] * v.z);
+}
+__device__ __forceinline__ M3 mulm(const M3& a, const M3& b) {
+  M3 r;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
+  return r;
+}
+__device__ __forceinline__ M3 mulmT(const M3& a, const M3& b) {  // a * b^T
+  M3 r;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r.m[3 * i + j] = a.m[3 * i] * b.m[3 * j] + a.m[3 * i + 1] * b.m[3 * j + 1] + a.m[3 * i + 2] * b.m[3 * j + 2];
+  return r;
+}
+__device__ __forceinline__ V3 col(const M3& a, int k) { return v3(a.m[k], a.m[3 + k], a.m[6 + k]); }
+__device__ __forceinline__ V3 rotq(Q4 q, V3 v) { return mulv(q2m(q), v); }
+__device__ __forceinline__ Q4 aa2q(V3 axis, float angle) {
+  float s, c;
+  sincosf(0.5f * angle, &s, &c);
+  return q4(c, axis.x * s, axis.y * s, axis.z * s);
+}
+
+// ---- warp reductions (all lanes receive the result)
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULLMASK, v, o));
+  return v;
+}
+__device__ __forceinline__ double wsumd(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+__device__ __forceinline__ int wsumi(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+// exclusive prefix sum of small ints across the warp
+__device__ __forceinline__ int wexscan(int v, int lane) {
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(FULLMASK, x, o);
+    if (lane >= o) x += y;
+  }
+  return x - v;
+}
+
+// ---- spatial algebra: 6-vectors (rot; lin) at the tree root's CoM, 10-vector inertia
+__device__ __forceinline__ void inert_com(float* res, const float* inert, const M3& mat, V3 d, float mass) {
+  float I[6];  // xx yy zz xy xz yz of mat * diag(inert) * mat^T
+  const float* m = mat.m;
+  I[0] = m[0] * m[0] * inert[0] + m[1] * m[1] * inert[1] + m[2] * m[2] * inert[2];
+  I[1] = m[3] * m[3] * inert[0] + m[4] * m[4] * inert[1] + m[5] * m[5] * inert[2];
+  I[2] = m[6] * m[6] * inert[0] + m[7] * m[7] * inert[1] + m[8] * m[8] * inert[2];
+  I[3] = m[0] * m[3] * inert[0] + m[1] * m[4] * inert[1] + m[2] * m[5] * inert[2];
+  I[4] = m[0] * m[6] * inert[0] + m[1] * m[7] * inert[1] + m[2] * m[8] * inert[2];
+  I[5] = m[3] * m[6] * inert[0] + m[4] * m[7] * inert[1] + m[5] * m[8] * inert[2];
+  res[0] = I[0] + mass * (d.y * d.y + d.z * d.z);
+  res[1] = I[1] + mass * (d.x * d.x + d.z * d.z);
+  res[2] = I[2] + mass * (d.x * d.x + d.y * d.y);
+  res[3] = I[3] - mass * d.x * d.y;
+  res[4] = I[4] - mass * d.x * d.z;
+  res[5] = I[5] - mass * d.y * d.z;
+  res[6] = mass * d.x; res[7] = mass * d.y; res[8] = mass * d.z; res[9] = mass;
+}
+__device__ __forceinline__ void mul_inert_vec(float* res, const float* i, const float* v) {
+  res[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  res[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  res[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  res[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  res[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  res[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+__device__ __forceinline__ void cross_motion(float* res, const float* vel, const float* v) {
+  V3 w = ld3(vel), u = ld3(vel + 3), a = ld3(v), b = ld3(v + 3);
+  st3(res, cross(w, a));
+  st3(res + 3, cross(w, b) + cross(u, a));
+}
+__device__ __forceinline__ void cross_force(float* res, const float* vel, const float* f) {
+  V3 w = ld3(vel), u = ld3(vel + 3), a = ld3(f), b = ld3(f + 3);
+  st3(res, cross(w, a) + cross(u, b));
+  st3(res + 3, cross(w, b));
+}
+
+// ---- 32x32 SPD solve, one warp.  A: shared, row stride 33, lane i owns row i; on exit the lower triangle of A
+// holds the Cholesky factor L and x[lane] the solution of A x = b.  Factorisation runs in registers (row per lane,
+// column pivots broadcast by shuffle), the back-substitution reads L^T from shared memory.  Returns false if a
+// pivot is not positive.  Rows/cols >= n must be identity (callers pad).
+__device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int lane) {
+  float h[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) h[j] = A[lane * 33 + j];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    float dkk = __shfl_sync(FULLMASK, h[k], k);
+    ok = ok && (dkk > F_MINVAL);
+    float inv = 1.0f / sqrtf(fmaxf(dkk, F_MINVAL));
+    float lik = h[k] * inv;
+    h[k] = lik;
+#pragma unroll
+    for (int j = k + 1; j < 32; j++) {
+      float ljk = __shfl_sync(FULLMASK, lik, j);
+      h[j] = fmaf(-lik, ljk, h[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j++) A[lane * 33 + j] = h[j];
+  // forward: L y = b (column oriented, from registers)
+  float y = b;
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    float yk = __shfl_sync(FULLMASK, y, k) / __shfl_sync(FULLMASK, h[k], k);
+    if (lane == k) y = yk;
+    else if (lane > k) y = fmaf(-h[k], yk, y);
+  }
+  __syncwarp();
+  // backward: L^T x = y; lane j needs L[k][j] -> shared row k
+  float x = y;
+#pragma unroll 4
+  for (int k = 31; k >= 0; k--) {
+    float xk = __shfl_sync(FULLMASK, x, k) / A[k * 33 + k];
+    if (lane == k) x = xk;
+    else if (lane < k) x = fmaf(-A[k * 33 + lane], xk, x);
+  }
+  *xout = x;
+  return ok;
+}
+// solve with an existing factor in A (lower triangle), e.g. second right-hand side
+__device__ __noinline__ float warp_chol_resolve(const float* A, float b, int lane) {
+  float y = b;
+  for (int k = 0; k < 32; k++) {
+    float yk = __shfl_sync(FULLMASK, y, k) / A[k * 33 + k];
+    if (lane == k) y = yk;
+    else if (lane > k) y = fmaf(-A[lane * 33 + k], yk, y);
+  }
+  float x = y;
+  for (int k = 31; k >= 0; k--) {
+    float xk = __shfl_sync(FULLMASK, x, k) / A[k * 33 + k];
+    if (lane == k) x = xk;
+    else if (lane < k) x = fmaf(-A[k * 33 + lane], xk, x);
+  }
+  return x;
+}

@@ -1,0 +1,435 @@
+// dev_solver.cuh -- constraint rows and the Newton solver of MuJoCo 2.1's soft-constraint model, one warp per env.
+// Row classes: [0,32) dof friction loss (J = e_i, implicit), [32,64) joint limits (J = +-e_dof, implicit),
+// [64, ...) pyramidal contact edges, stored as per-contact BASIS rows (normal, 2 tangents, torsion) so that
+// edge row = basis_0 +- mu_k * basis_k.  Restates mj_makeConstraint / mj_makeImpedance / mj_referenceConstraint /
+// mj_fwdConstraint(Newton) for this model class; reference call site ho_im4.py:545.
+#pragma once
+#include "dev_math.cuh"
+
+#define U_BINFO (U_MPRQ)   // basis row -> contact | k<<8 (the MPR queue is dead once contacts exist)
+#define U_CW (U_CON)       // per-contact Hessian weights reuse the contact records' slots 14..15 + CINFO pad
+
+__device__ __forceinline__ float impedance(const float* si, float pos, float margin) {
+  float s0 = fminf(0.9999f, fmaxf(0.0001f, si[0])), s1 = fminf(0.9999f, fmaxf(0.0001f, si[1]));
+  float s2 = fmaxf(0.f, si[2]), s3 = fminf(0.9999f, fmaxf(0.0001f, si[3])), s4 = fmaxf(1.f, si[4]);
+  if (s0 == s1 || s2 <= F_MINVAL) return 0.5f * (s0 + s1);
+  float x = fabsf((pos - margin) / s2), y;
+  if (x >= 1.f || x <= 0.f) return x >= 1.f ? s1 : s0;
+  if (s4 == 1.f) y = x;
+  else if (x <= s3) y = powf(x, s4) / powf(s3, s4 - 1.f);
+  else y = 1.f - powf(1.f - x, s4) / powf(1.f - s3, s4 - 1.f);
+  return s0 + y * (s1 - s0);
+}
+__device__ __forceinline__ void kb_from_solref(const float* sr, const float* si, float timestep, float& K, float& B) {
+  const float dmax = fminf(0.9999f, fmaxf(0.0001f, si[1]));
+  if (sr[0] > 0.f) {
+    const float tc = fmaxf(sr[0], 2.f * timestep), dr = sr[1];
+    B = 2.f / (dmax * tc);
+    K = 1.f / (dmax * dmax * tc * tc * dr * dr);
+  } else {
+    K = -sr[0] / (dmax * dmax);
+    B = -sr[1] / dmax;
+  }
+}
+
+// Builds all rows from the contacts in U_CON and the current qpos / qvel.  Sets MI_NLIM / MI_NBASIS / MI_NEDGE.
+__device__ void build_rows(float* s, const DevModel& m, int lane) {
+  int* misc = (int*)(s + S_MISC);
+  int* rinfo = (int*)(s + U_RINFO);
+  int* binfo = (int*)(s + U_BINFO);
+  const float* qv = s + S_QVEL;
+  // friction-loss rows
+  {
+    const bool on = lane < m.nv && m.dof_frictionloss[lane] > 0.f;
+    s[U_D + H_RFR + lane] = on ? m.fr_D[lane] : 0.f;
+    s[U_AREF + H_RFR + lane] = on ? -m.fr_B[lane] * qv[lane] : 0.f;
+  }
+  // joint-limit rows: lower sides first, then upper sides (order does not affect the solution)
+  int nlim = 0;
+  s[U_D + H_RLIM + lane] = 0.f;
+  s[U_AREF + H_RLIM + lane] = 0.f;
+  rinfo[H_RLIM + lane] = 0;
+  __syncwarp();
+  for (int side = -1; side <= 1; side += 2) {
+    bool on = false;
+    float dist = 0.f;
+    if (lane < m.njnt && m.jnt_limited[lane] && m.jnt_type[lane] != J_FREE) {
+      const float value = s[S_QPOS + m.jnt_qposadr[lane]];
+      dist = side * (m.jnt_range[lane][(side + 1) / 2] - value);
+      on = dist < m.jnt_margin[lane];
+    }
+    const unsigned bal = __ballot_sync(FULLMASK, on);
+    const int idx = nlim + __popc(bal & ((1u << lane) - 1u));
+    if (on && idx < 32) {
+      const int dof = m.jnt_dofadr[lane];
+      const float margin = m.jnt_margin[lane];
+      const float imp = impedance(m.jnt_solimp[lane], dist, margin);
+      float K, B;
+      kb_from_solref(m.jnt_solref[lane], m.jnt_solimp[lane], m.timestep, K, B);
+      const float R = fmaxf(F_MINVAL, (1.f - imp) * m.jnt_invweight[lane] / imp);
+      const float sgn = (float)(-side);
+      s[U_D + H_RLIM + idx] = 1.0f / R;
+      s[U_AREF + H_RLIM + idx] = -B * (sgn * qv[dof]) - K * imp * (dist - margin);
+      rinfo[H_RLIM + idx] = dof | ((side < 0 ? 1 : 0) << 8);   // bit 8: J = +1 (lower side), else -1
+    }
+    nlim += __popc(bal);
+  }
+  if (nlim > 32) { nlim = 32; if (lane == 0) misc[MI_FLAGS] |= 2; }
+  // contacts
+  const int ncon = misc[MI_NCON];
+  int nbasis = 0, nedge = 0;
+  bool overflow = false;
+  for (int c = 0; c < ncon; c++) {
+    const float* cr = s + U_CON + 16 * c;
+    const DevCand& cd = m.cand[__float_as_int(cr[13])];
+    const int dim = cd.condim, nb = dim == 1 ? 1 : dim, ne = dim == 1 ? 1 : 2 * (dim - 1);
+    float* ci = s + U_CINFO + 8 * c;
+    if (nbasis + nb > H_NBASIS || nedge + ne > H_NEDGE) {
+      overflow = true;
+      if (lane == 0) { ((int*)ci)[0] = 0; ((int*)ci)[1] = 0; ((int*)ci)[2] = 0; ((int*)ci)[3] = 0; ci[6] = 0.f; }
+      continue;
+    }
+    const int b1 = m.geom_body[cd.g1], b2 = m.geom_body[cd.g2];
+    const V3 pos = ld3(cr), f0 = ld3(cr + 3), f1 = ld3(cr + 6), f2 = ld3(cr + 9);
+    const float dist = cr[12];
+    // jacobian difference column for dof = lane
+    float sg = 0.f;
+    if (lane < m.nv) sg = (float)((m.body_chain[b2] >> lane) & 1u) - (float)((m.body_chain[b1] >> lane) & 1u);
+    V3 jp = v3(0, 0, 0), jr = v3(0, 0, 0);
+    if (sg != 0.f) {
+      const V3 off = pos - ld3(s + S_COM + 3 * m.dof_rootslot[lane]);
+      const V3 rot = ld3(s + S_CDOF + 6 * lane), lin = ld3(s + S_CDOF + 6 * lane + 3);
+      jp = (lin + cross(rot, off)) * sg;
+      jr = rot * sg;
+    }
+    float bcol[4];
+    bcol[0] = dot(f0, jp); bcol[1] = dot(f1, jp); bcol[2] = dot(f2, jp); bcol[3] = dot(f0, jr);
+    float bvel[4];
+    const float qvl = lane < m.nv ? qv[lane] : 0.f;
+    for (int a = 0; a < nb; a++) {
+      s[U_B + (nbasis + a) * 33 + lane] = bcol[a];
+      bvel[a] = wsum(bcol[a] * qvl);
+      if (lane == 0) binfo[nbasis + a] = c | (a << 8);
+    }
+    // impedance / reference (identical on all lanes)
+    const float imp = impedance(cd.solimp, dist, cd.includemargin);
+    float K, B;
+    kb_from_solref(cd.solref, cd.solimp, m.timestep, K, B);
+    const float mu0 = cd.friction[0], mu1 = cd.friction[1];
+    float D;
+    if (dim == 1) {
+      D = 1.0f / fmaxf(F_MINVAL, (1.f - imp) * cd.dA_tran / imp);
+    } else {
+      const float dA = cd.dA_tran + mu0 * mu0 * cd.dA_tran;
+      const float R0 = fmaxf(F_MINVAL, (1.f - imp) * dA / imp);
+      const float mu = mu0 * sqrtf(1.0f / fmaxf(F_MINVAL, m.impratio));
+      D = 1.0f / (2.f * mu * mu * R0);
+    }
+    const float posterm = K * imp * (dist - cd.includemargin);
+    if (lane < ne) {
+      float jv;
+      if (dim == 1) jv = bvel[0];
+      else {
+        const int k = lane / 2 + 1;
+        const float mu = k <= 2 ? mu0 : mu1;
+        jv = bvel[0] + ((lane & 1) ? -mu : mu) * bvel[k];
+      }
+      const int r = H_RCON + nedge + lane;
+      s[U_AREF + r] = -B * jv - posterm;
+      s[U_D + r] = D;
+      rinfo[r] = c | (lane << 8);
+    }
+    if (lane == 0) {
+      ((int*)ci)[0] = nbasis; ((int*)ci)[1] = nb; ((int*)ci)[2] = nedge; ((int*)ci)[3] = ne;
+      ci[4] = mu0; ci[5] = mu1; ci[6] = D;
+      ((unsigned*)ci)[7] = m.body_chain[b1] | m.body_chain[b2];
+    }
+    nbasis += nb;
+    nedge += ne;
+  }
+  // clear unused edge rows of the last partially used 32-row group so that generic row loops can run unguarded
+  for (int r = H_RCON + nedge + lane; r < H_RCON + ((nedge + 31) & ~31); r += 32) { s[U_D + r] = 0.f; s[U_AREF + r] = 0.f; rinfo[r] = 0; }
+  if (lane == 0) {
+    misc[MI_NLIM] = nlim; misc[MI_NBASIS] = nbasis; misc[MI_NEDGE] = nedge;
+    if (overflow) misc[MI_FLAGS] |= 2;
+  }
+  __syncwarp();
+}
+
+// ---- row-wise products ----------------------------------------------------------------------------------------
+// out[r] = (J v)[r] for all rows; v in shared (32 floats).  Uses U_BV as scratch.
+__device__ void mul_J(float* s, int lane, int nbasis, int nedge, const float* v, float* out) {
+  const int* rinfo = (const int*)(s + U_RINFO);
+  for (int a = lane; a < nbasis; a += 32) {
+    const float* B = s + U_B + a * 33;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j++) acc = fmaf(B[j], v[j], acc);
+    s[U_BV + a] = acc;
+  }
+  __syncwarp();
+  out[H_RFR + lane] = v[lane];
+  {
+    const int ri = rinfo[H_RLIM + lane];
+    out[H_RLIM + lane] = ((ri >> 8) & 1 ? 1.f : -1.f) * v[ri & 255];
+  }
+  for (int e = lane; e < nedge; e += 32) {
+    const int ri = rinfo[H_RCON + e], c = ri & 255, ed = ri >> 8;
+    const float* ci = s + U_CINFO + 8 * c;
+    const int bo = ((const int*)ci)[0], ne = ((const int*)ci)[3];
+    float val = s[U_BV + bo];
+    if (ne > 1) {
+      const int k = ed / 2 + 1;
+      const float mu = k <= 2 ? ci[4] : ci[5];
+      val += ((ed & 1) ? -mu : mu) * s[U_BV + bo + k];
+    }
+    out[H_RCON + e] = val;
+  }
+  __syncwarp();
+}
+
+// per-row force / cost / curvature at constraint-space residual x
+__device__ __forceinline__ void row_eval(const float* s, const DevModel& m, int r, float x, float& force, float& cost, float& curv) {
+  const float D = s[U_D + r];
+  if (r < H_RLIM) {
+    const float fl = m.dof_frictionloss[r], Rf = m.fr_Rf[r];
+    if (D == 0.f) { force = 0.f; cost = 0.f; curv = 0.f; }
+    else if (x <= -Rf) { force = fl; cost = fl * (-0.5f * Rf - x); curv = 0.f; }
+    else if (x >= Rf) { force = -fl; cost = fl * (-0.5f * Rf + x); curv = 0.f; }
+    else { force = -D * x; cost = 0.5f * D * x * x; curv = D; }
+  } else {
+    if (x < 0.f) { force = -D * x; cost = 0.5f * D * x * x; curv = D; }
+    else { force = 0.f; cost = 0.f; curv = 0.f; }
+  }
+}
+
+// constraint cost at jar (shared array), optionally writing forces; all lanes get the total
+__device__ float rows_update(float* s, const DevModel& m, int lane, int nedge, const float* jar, bool write) {
+  float cost = 0.f;
+  const int nrow = H_RCON + nedge;
+  for (int r = lane; r < nrow; r += 32) {
+    float f, c, k;
+    row_eval(s, m, r, jar[r], f, c, k);
+    cost += c;
+    if (write) s[U_FORCE + r] = f;
+  }
+  cost = wsum(cost);
+  __syncwarp();
+  return cost;
+}
+
+// (M v)[lane]
+__device__ __forceinline__ float mul_M(const float* s, int lane, const float* v) {
+  const float* Mr = s + S_M + lane * 33;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j++) acc = fmaf(Mr[j], v[j], acc);
+  return acc;
+}
+
+// gradient and Newton direction.  grad = Ma - qfrc_smooth - J^T f ; H = M + J^T D_active J ; search = -H^-1 grad
+__device__ bool newton_direction(float* s, const DevModel& m, int lane, int nlim, int ncon, int nbasis, int nedge) {
+  const int* rinfo = (const int*)(s + U_RINFO);
+  const int* binfo = (const int*)(s + U_BINFO);
+  const float* jar = s + U_JAR;
+  // per-basis-row force coefficients g_a and per-contact Hessian weights
+  for (int a = lane; a < nbasis; a += 32) {
+    const int c = binfo[a] & 255, k = binfo[a] >> 8;
+    const float* ci = s + U_CINFO + 8 * c;
+    const int eo = H_RCON + ((const int*)ci)[2], ne = ((const int*)ci)[3];
+    float g;
+    if (k == 0) { g = 0.f; for (int e = 0; e < ne; e++) g += s[U_FORCE + eo + e]; }
+    else { const float mu = k <= 2 ? ci[4] : ci[5]; g = mu * (s[U_FORCE + eo + 2 * (k - 1)] - s[U_FORCE + eo + 2 * (k - 1) + 1]); }
+    s[U_BV + a] = g;
+  }
+  for (int c = lane; c < ncon; c += 32) {
+    // weights: w[0] = C00, w[1..3] = C0k, w[4..6] = Ckk  (stored in the contact record's free slots + CW)
+    float* ci = s + U_CINFO + 8 * c;
+    const int eo = H_RCON + ((const int*)ci)[2], ne = ((const int*)ci)[3];
+    const float D = ci[6];
+    float* w = s + U_CON + 16 * c;   // pos/frame no longer needed once the rows exist: reuse slots 0..6
+    float c00 = 0.f, c0k[3] = {0, 0, 0}, ckk[3] = {0, 0, 0};
+    for (int e = 0; e < ne; e++) {
+      const float act = jar[eo + e] < 0.f ? D : 0.f;
+      c00 += act;
+      if (ne > 1) {
+        const int k = e / 2;
+        const float mu = k < 2 ? ci[4] : ci[5];
+        c0k[k] += ((e & 1) ? -mu : mu) * act;
+        ckk[k] += mu * mu * act;
+      }
+    }
+    w[0] = c00; w[1] = c0k[0]; w[2] = c0k[1]; w[3] = c0k[2]; w[4] = ckk[0]; w[5] = ckk[1]; w[6] = ckk[2];
+  }
+  __syncwarp();
+  // gradient
+  float jtf = s[U_FORCE + H_RFR + lane];
+  for (int r = 0; r < nlim; r++) {
+    const int ri = rinfo[H_RLIM + r];
+    if ((ri & 255) == lane) jtf += ((ri >> 8) & 1 ? 1.f : -1.f) * s[U_FORCE + H_RLIM + r];
+  }
+  for (int a = 0; a < nbasis; a++) jtf = fmaf(s[U_B + a * 33 + lane], s[U_BV + a], jtf);
+  const float grad = s[S_MA + lane] - s[S_SMOOTH + lane] - jtf;
+  s[S_GRAD + lane] = grad;
+  s[S_FCON + lane] = jtf;
+  // Hessian row `lane`
+  float h[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) h[j] = s[S_M + lane * 33 + j];
+  float diag = 0.f;
+  {
+    float f, c, k;
+    row_eval(s, m, H_RFR + lane, jar[H_RFR + lane], f, c, k);
+    diag += k;
+  }
+  for (int r = 0; r < nlim; r++) {
+    const int ri = rinfo[H_RLIM + r];
+    if ((ri & 255) == lane && jar[H_RLIM + r] < 0.f) diag += s[U_D + H_RLIM + r];
+  }
+  for (int c = 0; c < ncon; c++) {
+    const float* ci = s + U_CINFO + 8 * c;
+    const int bo = ((const int*)ci)[0], nb = ((const int*)ci)[1];
+    if (nb == 0) continue;
+    const unsigned mask = ((const unsigned*)ci)[7];
+    const float* w = s + U_CON + 16 * c;
+    if (w[0] == 0.f) continue;   // no active edge
+    const float* B0 = s + U_B + bo * 33;
+    float al[4];
+    {
+      const float b0 = B0[lane];
+      al[0] = w[0] * b0; al[1] = al[2] = al[3] = 0.f;
+      for (int k = 1; k < nb; k++) {
+        const float bk = B0[k * 33 + lane];
+        al[0] = fmaf(w[k], bk, al[0]);
+        al[k] = w[k] * b0 + w[3 + k] * bk;
+      }
+    }
+#pragma unroll
+    for (int jb = 0; jb < 16; jb++) {
+      if ((mask >> (2 * jb)) & 3u) {
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          const int j = 2 * jb + jj;
+          float acc = al[0] * B0[j];
+          if (nb > 1) { acc = fmaf(al[1], B0[33 + j], acc); acc = fmaf(al[2], B0[66 + j], acc); }
+          if (nb > 3) acc = fmaf(al[3], B0[99 + j], acc);
+          h[j] += acc;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j++) s[S_H + lane * 33 + j] = h[j];
+  s[S_H + lane * 33 + lane] += diag;
+  __syncwarp();
+  float dir;
+  const bool ok = warp_chol_solve(s + S_H, -grad, &dir, lane);
+  s[S_SEARCH + lane] = dir;
+  __syncwarp();
+  return ok;
+}
+
+// derivative and curvature of the total cost along the search direction at step alpha
+__device__ __forceinline__ void ls_eval(const float* s, const DevModel& m, int lane, int nedge, float alpha, float qg1,
+                                        float qg2, float& d1, float& d2) {
+  float a1 = 0.f, a2 = 0.f;
+  const int nrow = H_RCON + nedge;
+  for (int r = lane; r < nrow; r += 32) {
+    const float jv = s[U_JV + r];
+    float f, c, k;
+    row_eval(s, m, r, s[U_JAR + r] + alpha * jv, f, c, k);
+    a1 -= f * jv;          // d cost / d alpha = -force * Jv
+    a2 += k * jv * jv;
+  }
+  d1 = qg1 + 2.f * alpha * qg2 + wsum(a1);
+  d2 = 2.f * qg2 + wsum(a2);
+}
+
+// exact minimiser of the piecewise-quadratic cost along `search` by safeguarded Newton on its derivative
+__device__ float line_search(float* s, const DevModel& m, int lane, int nbasis, int nedge, unsigned& evals) {
+  const float sv = s[S_SEARCH + lane];
+  const float mv = mul_M(s, lane, s + S_SEARCH);
+  s[S_MV + lane] = mv;
+  mul_J(s, lane, nbasis, nedge, s + S_SEARCH, s + U_JV);
+  const float qg1 = wsum(sv * (s[S_MA + lane] - s[S_SMOOTH + lane]));
+  const float qg2 = 0.5f * wsum(sv * mv);
+  float d1, d2, lo = 0.f, hi = -1.f, alpha = 0.f, dlo;
+  ls_eval(s, m, lane, nedge, 0.f, qg1, qg2, d1, d2);
+  evals++;
+  if (!(d1 < 0.f) || !(d2 > 0.f)) return 0.f;
+  dlo = d1;
+  const float gtol = 1e-6f * fabsf(d1);
+  alpha = -d1 / d2;
+  for (int it = 0; it < 24; it++) {
+    ls_eval(s, m, lane, nedge, alpha, qg1, qg2, d1, d2);
+    evals++;
+    if (fabsf(d1) <= gtol) break;
+    if (d1 < 0.f) { lo = alpha; dlo = d1; } else hi = alpha;
+    float nxt = alpha - d1 / d2;
+    if (hi >= 0.f) {
+      if (!(nxt > lo && nxt < hi)) nxt = 0.5f * (lo + hi);
+      if (hi - lo <= 1e-7f * hi) { alpha = nxt; break; }
+    } else if (!(nxt > alpha)) {
+      nxt = 2.f * alpha;
+    }
+    alpha = nxt;
+  }
+  (void)dlo;
+  return alpha;
+}
+
+// mj_fwdConstraint with the Newton solver.  Inputs: S_SMOOTH, S_ASMOOTH, S_WARM, rows.  Outputs: S_QACC, S_FCON.
+__device__ bool solve_newton(float* s, const DevModel& m, int lane, unsigned& iters_out, unsigned& ls_evals) {
+  const int* misc = (const int*)(s + S_MISC);
+  const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON], nbasis = misc[MI_NBASIS], nedge = misc[MI_NEDGE];
+  const float scale = 1.0f / (m.meaninertia * (float)(m.nv > 1 ? m.nv : 1));
+  const float asm_ = s[S_ASMOOTH + lane], fsm = s[S_SMOOTH + lane];
+  // warm start selection
+  float qacc = s[S_WARM + lane];
+  s[S_QACC + lane] = qacc;
+  __syncwarp();
+  float ma = mul_M(s, lane, s + S_QACC);
+  mul_J(s, lane, nbasis, nedge, s + S_QACC, s + U_JAR);
+  for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JAR + r] -= s[U_AREF + r];
+  __syncwarp();
+  const float cost_warm = rows_update(s, m, lane, nedge, s + U_JAR, false) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
+  mul_J(s, lane, nbasis, nedge, s + S_ASMOOTH, s + U_JV);
+  for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JV + r] -= s[U_AREF + r];
+  __syncwarp();
+  const float cost_smooth = rows_update(s, m, lane, nedge, s + U_JV, false);
+  if (cost_warm > cost_smooth) {
+    qacc = asm_;
+    s[S_QACC + lane] = qacc;
+    for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JAR + r] = s[U_JV + r];
+    __syncwarp();
+    ma = mul_M(s, lane, s + S_QACC);
+  }
+  s[S_MA + lane] = ma;
+  __syncwarp();
+  float cost = rows_update(s, m, lane, nedge, s + U_JAR, true) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
+  bool ok = newton_direction(s, m, lane, nlim, ncon, nbasis, nedge);
+  unsigned iter = 0;
+  while (ok && iter < (unsigned)m.iterations) {
+    const float alpha = line_search(s, m, lane, nbasis, nedge, ls_evals);
+    if (alpha == 0.f) break;
+    qacc += alpha * s[S_SEARCH + lane];
+    ma += alpha * s[S_MV + lane];
+    s[S_QACC + lane] = qacc;
+    s[S_MA + lane] = ma;
+    for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JAR + r] += alpha * s[U_JV + r];
+    __syncwarp();
+    const float oldcost = cost;
+    cost = rows_update(s, m, lane, nedge, s + U_JAR, true) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
+    ok = newton_direction(s, m, lane, nlim, ncon, nbasis, nedge);
+    const float g = s[S_GRAD + lane];
+    const float gradn = scale * sqrtf(wsum(g * g));
+    const float improvement = scale * (oldcost - cost);
+    iter++;
+    // float32 noise floor on the cost difference replaces MuJoCo's absolute 1e-8 (see DESIGN.md "precision")
+    const float tol = fmaxf(m.tolerance, 2e-7f * scale * fabsf(cost));
+    if (improvement < tol || gradn < m.tolerance) break;
+  }
+  iters_out += iter;
+  // S_FCON holds J^T f of the final forces (written by newton_direction)
+  return ok;
+}

@@ -1,0 +1,898 @@
+// hoic_capi.cu -- kernels and the C ABI of libhoic_b200.so (include/hoic.h).
+// One warp per environment, one 32-thread CTA per warp: an env's whole step (15 substeps of control + physics, the
+// residual-force QP, termination, reward and observation) runs in one kernel with its working set in shared memory.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hoic.h"
+#include "../../include/hoic_blob.h"
+#include "dev_collide.cuh"
+#include "dev_dynamics.cuh"
+#include "dev_env.cuh"
+#include "dev_model.h"
+#include "dev_solver.cuh"
+
+// ================================================================================================ device side
+
+struct BatchDev {
+  int n_envs;
+  const DevModel* const* env_model;   // [N]
+  float* state;                       // [N][ST_STRIDE]
+  float* old_geom;                    // [N][HN*12 + 4] geom poses (+origin) of the forward that preceded the step
+  const float* frames;                // all motions
+  const int* motion_offset;
+  const int* motion_len;
+  int n_motions;
+  const float* reward_w;              // [24]
+  int mode_train;
+  unsigned long long* counters;       // hoic_counters as 12 x u64
+};
+
+struct StepOut {
+  float* obs; float* reward; float* info; uint8_t* done; uint8_t* fail; uint8_t* end; float* percent;
+};
+
+struct Cnt { unsigned substeps, ncon, nefc, newton, ls, mpr_calls, mpr_iters, qp, fail_phys, fail_over; };
+
+__device__ __forceinline__ bool bad(float v) { return !(fabsf(v) <= F_MAXVAL); }
+
+// forward dynamics of the state in S_QPOS/S_QVEL with S_CTRL/S_QAPP/S_WARM, then Euler.  `record`: add the contacts
+// of this forward to the contact sums (they are what record_contact sees before the NEXT sim.step()).
+__device__ bool substep_core(float* s, const DevModel& m, int lane, bool record, Cnt& cnt, bool integrate = true) {
+  int* misc = (int*)(s + S_MISC);
+  bool fail = __any_sync(FULLMASK, bad(s[S_QPOS + lane]) || bad(s[S_QVEL + lane]) || (lane == 0 && bad(s[S_QPOS + 32])));
+  if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
+  pos_stage(s, m, lane);
+  vel_stage(s, m, lane);
+  collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
+  if (record) record_contacts(s, m, lane);
+  build_rows(s, m, lane);
+  // smooth dynamics
+  {
+    const bool on = lane < m.nv;
+    const float passive = on ? -m.dof_damping[lane] * s[S_QVEL + lane] : 0.f;
+    const float act = lane < m.nu ? s[S_CTRL + lane] : 0.f;   // motors on dofs 0..nu-1, gear 1
+    const float fs = on ? passive - s[S_BIAS + lane] + s[S_QAPP + lane] + act : 0.f;
+    s[S_SMOOTH + lane] = fs;
+#pragma unroll 4
+    for (int j = 0; j < 32; j++) s[S_H + lane * 33 + j] = s[S_M + lane * 33 + j];
+    __syncwarp();
+    float as;
+    if (!warp_chol_solve(s + S_H, fs, &as, lane)) fail = true;
+    s[S_ASMOOTH + lane] = as;
+    __syncwarp();
+  }
+  unsigned it = 0;
+  if (!solve_newton(s, m, lane, it, cnt.ls)) fail = true;
+  cnt.newton += it;
+  cnt.substeps++;
+  cnt.ncon += misc[MI_NCON];
+  cnt.nefc += m.nv + misc[MI_NLIM] + misc[MI_NEDGE];
+  if (lane == 0) misc[MI_ITER] = (int)it;
+  fail = __any_sync(FULLMASK, fail || bad(s[S_QACC + lane]));
+  if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
+  if (misc[MI_FLAGS] & 2) return false;   // capacity overflow: treated like MuJoCo's nconmax / njmax warnings
+  if (integrate && !euler_step(s, m, lane, nullptr)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
+  return true;
+}
+
+__device__ __forceinline__ void load_state(float* s, const float* st, int lane, int qoff, int voff) {
+  s[S_QPOS + lane] = st[qoff + lane];
+  if (lane < 4) s[S_QPOS + 32 + lane] = lane == 0 ? st[qoff + 32] : 0.f;
+  s[S_QVEL + lane] = st[voff + lane];
+}
+
+__device__ void flush_counters(const BatchDev& B, const Cnt& c, int lane, unsigned env_steps) {
+  if (lane != 0) return;
+  unsigned long long* g = B.counters;
+  if (env_steps) atomicAdd(g + 0, (unsigned long long)env_steps);
+  atomicAdd(g + 1, (unsigned long long)c.substeps);
+  atomicAdd(g + 2, (unsigned long long)c.ncon);
+  atomicAdd(g + 3, (unsigned long long)c.nefc);
+  atomicAdd(g + 4, (unsigned long long)c.newton);
+  atomicAdd(g + 5, (unsigned long long)c.ls);
+  atomicAdd(g + 6, (unsigned long long)c.mpr_calls);
+  atomicAdd(g + 7, (unsigned long long)c.mpr_iters);
+  atomicAdd(g + 8, (unsigned long long)c.qp);
+  if (c.fail_phys) atomicAdd(g + 9, (unsigned long long)c.fail_phys);
+  if (c.fail_over) atomicAdd(g + 10, (unsigned long long)c.fail_over);
+}
+
+__device__ __forceinline__ EnvCtx make_ctx(const BatchDev& B, const int* ints) {
+  EnvCtx e;
+  const int mid = ints[1], sidx = ints[2];
+  e.motion = B.frames + (size_t)(B.motion_offset[mid] + sidx) * H_FRAME;
+  e.expert_len = ints[3];
+  e.cur_t = ints[0];
+  e.start_ind = 0;
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------------ step kernel
+__global__ void __launch_bounds__(32) k_step(BatchDev B, const float* __restrict__ actions, StepOut out) {
+  extern __shared__ float s[];
+  const int env = blockIdx.x, lane = threadIdx.x;
+  if (env >= B.n_envs) return;
+  const DevModel& m = *B.env_model[env];
+  float* st = B.state + (size_t)env * ST_STRIDE;
+  int* ints = (int*)(st + ST_INTS);
+  int* misc = (int*)(s + S_MISC);
+  Cnt cnt;
+  memset(&cnt, 0, sizeof cnt);
+  if (lane < 16) misc[lane] = 0;
+  EnvCtx ctx = make_ctx(B, ints);
+  // action: clip, residual wrench
+  {
+    float a = lane < m.nu + (m.residual_force ? 6 : 0) ? actions[(size_t)env * HOIC_ACT_DIM + lane] : 0.f;
+    s[S_ACT + lane] = fminf(fmaxf(a, -1.f), 1.f);
+  }
+  // current state in registers while the previous forward is recomputed
+  const float cq = st[ST_QPOS + lane], cq32 = st[ST_QPOS + 32], cv = st[ST_QVEL + lane], cw = st[ST_WARM + lane];
+  load_state(s, st, lane, ST_PQPOS, ST_PQVEL);
+  s[S_CSUM + lane] = 0.f;
+  for (int i = lane; i < 240; i += 32) s[S_CSUM + i] = 0.f;
+  s[S_CCNT + lane] = 0.f;
+  __syncwarp();
+  pos_stage(s, m, lane);
+  vel_stage(s, m, lane);
+  collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
+  record_contacts(s, m, lane);
+  // snapshot of geom poses for the averaged velocities (ho_im4.py:508-511)
+  {
+    float* og = B.old_geom + (size_t)env * (HN * 12 + 4);
+    for (int i = lane; i < m.ngeom * 3; i += 32) og[i] = s[S_GPOS + i];
+    for (int i = lane; i < m.ngeom * 9; i += 32) og[HN * 3 + i] = s[S_GMAT + i];
+    if (lane < 3) og[HN * 12 + lane] = s[S_ORG + lane];
+  }
+  const float old_obj_vel = (lane >= m.nv - 6 && lane < m.nv) ? cv : 0.f;
+  // restore the current state
+  s[S_QPOS + lane] = cq;
+  if (lane == 0) s[S_QPOS + 32] = cq32;
+  s[S_QVEL + lane] = cv;
+  s[S_WARM + lane] = cw;
+  if (lane == 0) misc[MI_FLAGS] = 0;   // a capacity overflow in the stale forward was already reported last step
+  __syncwarp();
+  const V3 vf = m.residual_force ? ld3(s + S_ACT + m.nu) * m.rf_scale : v3(0, 0, 0);
+  const V3 vt = m.residual_force ? ld3(s + S_ACT + m.nu + 3) * m.rt_scale : v3(0, 0, 0);
+  float pq = cq, pq32 = cq32, pv = cv;
+  bool fail = false;
+  for (int k = 0; k < m.sim_step; k++) {
+    if (!pd_torque(s, m, lane, ctx)) { fail = true; break; }
+    {
+      // J^T wrenches with the previous forward's Jacobians (stale cdof / com / geom_xpos)
+      const V3 org = ld3(s + S_ORG);
+      float qf = apply_ft(s, m, lane, v3(0.f, 0.f, m.hand_mass * 9.8f), v3(0, 0, 0), ld3(s + S_GPOS + 3 * m.hand_geom0), m.palm_body);
+      if (m.residual_force) qf += apply_ft(s, m, lane, vf, vt, ld3(s + S_QPOS + m.nhand_q) - org, m.obj_body);
+      __syncwarp();
+      s[S_QAPP + lane] = qf;
+    }
+    pq = s[S_QPOS + lane]; pq32 = s[S_QPOS + 32]; pv = s[S_QVEL + lane];
+    __syncwarp();
+    if (!substep_core(s, m, lane, k + 1 < m.sim_step, cnt)) { fail = true; break; }
+  }
+  const int flags = misc[MI_FLAGS];
+  if (flags & 1) cnt.fail_phys++;
+  if (flags & 2) cnt.fail_over++;
+  // ---- tail: averages, contact classification, residual-force QP
+  float rfc_score = 0.f, rest[6] = {0, 0, 0, 0, 0, 0};
+  int ncg = 0;
+  const int nhg = m.hand_geom1 - m.hand_geom0 + 1;
+  if (!fail) {
+    const float* og = B.old_geom + (size_t)env * (HN * 12 + 4);
+    const float inv_dt = 1.0f / (m.sim_step * m.timestep);
+    const V3 org = ld3(s + S_ORG), oorg = ld3(og + HN * 12);
+    const float acc = (s[S_QVEL + lane] - old_obj_vel) * inv_dt;   // lanes nv-6..nv-1: obj_avg_acc
+    const V3 obj_a = v3(__shfl_sync(FULLMASK, acc, m.nv - 6), __shfl_sync(FULLMASK, acc, m.nv - 5), __shfl_sync(FULLMASK, acc, m.nv - 4));
+    const V3 obj_oa = v3(__shfl_sync(FULLMASK, acc, m.nv - 3), __shfl_sync(FULLMASK, acc, m.nv - 2), __shfl_sync(FULLMASK, acc, m.nv - 1));
+    // classify_contact: lane = hand geom slot
+    bool has = lane < nhg && s[S_CCNT + lane] > 0.f;
+    float fr[12];
+    if (has) {
+      const float ic = 1.0f / s[S_CCNT + lane];
+      for (int k = 0; k < 12; k++) fr[k] = s[S_CSUM + 12 * lane + k] * ic;
+      V3 n = ld3(fr + 3);
+      n = n * (1.0f / norm(n));
+      V3 t = fabsf(n.x) >= 1e-5f ? cross(n, v3(1.f, 0.f, 0.f)) : cross(n, v3(0.f, 1.f, 0.f));
+      t = t * (1.0f / norm(t));
+      V3 b = cross(n, t);
+      b = b * (1.0f / norm(b));
+      st3(fr + 3, n); st3(fr + 6, t); st3(fr + 9, b);
+    }
+    const float ts = has ? s[S_CCNT + lane] / (float)m.sim_step : 0.f;
+    const unsigned bal = __ballot_sync(FULLMASK, has);
+    ncg = __popc(bal);
+    __syncwarp();
+    // geom average velocities: contact geoms (lane = slot) and the last geom (object visual mesh)
+    auto geom_vel = [&](int g, V3& lin, V3& ang) {
+      const V3 pn = ld3(s + S_GPOS + 3 * g) , po = ld3(og + 3 * g);
+      lin = ((pn - po) + (org - oorg)) * inv_dt;
+      const M3 Rd = mulmT(ldm(s + S_GMAT + 9 * g), ldm(og + HN * 3 + 9 * g));
+      ang = matrix_to_axis_angle(Rd) * inv_dt;
+    };
+    V3 obj_v, obj_w;
+    geom_vel(m.last_geom, obj_v, obj_w);
+    if (has) {
+      const int idx = __popc(bal & ((1u << lane) - 1u));
+      for (int k = 0; k < 12; k++) s[QP_CF + 12 * idx + k] = fr[k];
+      s[QP_TS + idx] = ts;
+      ((int*)(s + QP_G1))[idx] = m.hand_geom0 + lane;
+      V3 gl, ga;
+      geom_vel(m.hand_geom0 + lane, gl, ga);
+      st3(s + QP_GV + 6 * idx, gl); st3(s + QP_GV + 6 * idx + 3, ga);
+    }
+    __syncwarp();
+    if (m.residual_force) {
+      if (!m.explain_force) {
+        rfc_score = norm(vf) + 1e4f * norm(vt);
+      } else {
+        const V3 obj_p = ld3(s + S_QPOS + m.nhand_q);
+        const M3 R = q2m(qnormalize(ldq(s + S_QPOS + m.nhand_q + 3)));
+        M3 RI;
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) RI.m[3 * i + j] = R.m[3 * i + j] * m.obj_inertia[j];
+        const M3 I = mulmT(RI, R);
+        const V3 F = (obj_a + v3(0.f, 0.f, 9.8f)) * m.obj_mass;
+        const V3 T = mulv(I, obj_oa) + cross(obj_w, mulv(I, obj_w));
+        if (ncg == 0) {
+          rfc_score = norm(F) + 1e4f * norm(T);
+          rest[0] = F.x; rest[1] = F.y; rest[2] = F.z; rest[3] = T.x; rest[4] = T.y; rest[5] = T.z;
+        } else {
+          rfc_score = rfc_qp(s, lane, ncg, m.surface_contact ? 5 : 1, F, T, obj_p, obj_v, obj_w, s + S_GPOS, org, rest, cnt.qp);
+        }
+      }
+    }
+  }
+  // ---- bookkeeping, termination, reward, observation (ho_im4.py:641-662)
+  ctx.cur_t += 1;
+  float reward = 0.f;
+  const bool body_fail = diff_and_reward(s, m, lane, ctx, B.reward_w, rfc_score, &reward, out.info ? out.info + (size_t)env * HOIC_INFO_DIM : nullptr);
+  if (B.mode_train) fail = fail || body_fail;
+  const bool end = ctx.cur_t + ctx.start_ind >= ctx.expert_len - m.w_size - 1;
+  if (out.obs) write_obs(s, m, lane, ctx, out.obs + (size_t)env * HOIC_OBS_DIM);
+  if (lane == 0) {
+    if (out.reward) out.reward[env] = reward;
+    if (out.done) out.done[env] = fail || end;
+    if (out.fail) out.fail[env] = fail;
+    if (out.end) out.end[env] = end;
+    if (out.percent) out.percent[env] = (float)ctx.cur_t / (float)(ctx.expert_len - 1);
+    ints[0] = ctx.cur_t;
+    st[ST_RFC] = rfc_score;
+    for (int k = 0; k < 6; k++) st[ST_RFC + 1 + k] = rest[k];
+    st[ST_RFC + 7] = (float)ncg;
+  }
+  // ---- write state back
+  st[ST_QPOS + lane] = s[S_QPOS + lane];
+  st[ST_QVEL + lane] = s[S_QVEL + lane];
+  st[ST_WARM + lane] = s[S_WARM + lane];
+  st[ST_PQPOS + lane] = pq;
+  st[ST_PQVEL + lane] = pv;
+  if (lane == 0) { st[ST_QPOS + 32] = s[S_QPOS + 32]; st[ST_PQPOS + 32] = pq32; }
+  flush_counters(B, cnt, lane, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ reset kernel
+__global__ void __launch_bounds__(32) k_reset(BatchDev B, const uint8_t* __restrict__ mask, const int* __restrict__ motion_id,
+                                              const int* __restrict__ start_idx, float* obs_out) {
+  extern __shared__ float s[];
+  const int env = blockIdx.x, lane = threadIdx.x;
+  if (env >= B.n_envs) return;
+  if (mask && !mask[env]) return;
+  const DevModel& m = *B.env_model[env];
+  float* st = B.state + (size_t)env * ST_STRIDE;
+  int* ints = (int*)(st + ST_INTS);
+  int* misc = (int*)(s + S_MISC);
+  if (lane < 16) misc[lane] = 0;
+  int mid = ints[1], sidx = ints[2];
+  if (motion_id) mid = min(max(motion_id[env], 0), B.n_motions - 1);
+  if (start_idx) sidx = start_idx[env];
+  const int mlen = B.motion_len[mid];
+  sidx = min(max(sidx, 0), mlen - 1);
+  __syncwarp();
+  if (lane == 0) { ints[0] = 0; ints[1] = mid; ints[2] = sidx; ints[3] = mlen - sidx; }
+  EnvCtx ctx;
+  ctx.motion = B.frames + (size_t)(B.motion_offset[mid] + sidx) * H_FRAME;
+  ctx.expert_len = mlen - sidx; ctx.cur_t = 0; ctx.start_ind = 0;
+  const float* f = ctx.motion;
+  const int nh = m.nhand_q, nhv = m.nhand_v;
+  // reset_model (ho_im4.py:690-716): frame 0
+  if (lane < nh) s[S_QPOS + lane] = f[F_DOF + lane];
+  else if (lane < 32) s[S_QPOS + lane] = f[F_OBJPOSE + lane - nh];
+  if (lane == 0) s[S_QPOS + 32] = f[F_OBJPOSE + 32 - nh];
+  if (lane < nhv) s[S_QVEL + lane] = f[F_DOFVEL + lane];
+  else if (lane < nhv + 3) s[S_QVEL + lane] = f[F_OBJVEL + lane - nhv];
+  else s[S_QVEL + lane] = f[F_OBJANGVEL + lane - nhv - 3];
+  __syncwarp();
+  pos_stage(s, m, lane);   // sim.forward() of set_state: poses for the observation (and normalised quaternion)
+  if (obs_out) write_obs(s, m, lane, ctx, obs_out + (size_t)env * HOIC_OBS_DIM);
+  st[ST_QPOS + lane] = s[S_QPOS + lane];
+  st[ST_QVEL + lane] = s[S_QVEL + lane];
+  st[ST_WARM + lane] = 0.f;   // mj_resetData
+  st[ST_PQPOS + lane] = s[S_QPOS + lane];
+  st[ST_PQVEL + lane] = s[S_QVEL + lane];
+  if (lane == 0) { st[ST_QPOS + 32] = s[S_QPOS + 32]; st[ST_PQPOS + 32] = s[S_QPOS + 32]; }
+  if (lane < 8) st[ST_RFC + lane] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+__global__ void k_get_state(BatchDev B, float* qpos, float* qvel, float* warm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n_envs * 33) return;
+  const int env = i / 33, k = i % 33;
+  const float* st = B.state + (size_t)env * ST_STRIDE;
+  if (qpos) qpos[i] = st[ST_QPOS + k];
+  if (k < 32) {
+    if (qvel) qvel[env * 32 + k] = st[ST_QVEL + k];
+    if (warm) warm[env * 32 + k] = st[ST_WARM + k];
+  }
+}
+__global__ void k_set_state(BatchDev B, const float* qpos, const float* qvel, const float* warm, const int* cur_t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n_envs * 33) return;
+  const int env = i / 33, k = i % 33;
+  float* st = B.state + (size_t)env * ST_STRIDE;
+  if (qpos) { st[ST_QPOS + k] = qpos[i]; st[ST_PQPOS + k] = qpos[i]; }
+  if (k < 32) {
+    if (qvel) { st[ST_QVEL + k] = qvel[env * 32 + k]; st[ST_PQVEL + k] = qvel[env * 32 + k]; }
+    if (warm) st[ST_WARM + k] = warm[env * 32 + k];
+  }
+  if (cur_t && k == 0) ((int*)(st + ST_INTS))[0] = cur_t[env];
+}
+__global__ void k_get_rfc(BatchDev B, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n_envs * 8) return;
+  out[i] = B.state[(size_t)(i / 8) * ST_STRIDE + ST_RFC + i % 8];
+}
+
+// forward of the state the last forward was computed from; exports derived quantities / contacts
+__global__ void __launch_bounds__(32) k_forward_debug(BatchDev B, float* xpos, float* xquat, float* qM, float* bias, int* ncon_out,
+                                                      int* pairs, float* cdata) {
+  extern __shared__ float s[];
+  const int env = blockIdx.x, lane = threadIdx.x;
+  if (env >= B.n_envs) return;
+  const DevModel& m = *B.env_model[env];
+  const float* st = B.state + (size_t)env * ST_STRIDE;
+  int* misc = (int*)(s + S_MISC);
+  if (lane < 16) misc[lane] = 0;
+  load_state(s, st, lane, ST_PQPOS, ST_PQVEL);
+  __syncwarp();
+  pos_stage(s, m, lane);
+  vel_stage(s, m, lane);
+  const V3 org = ld3(s + S_ORG);
+  if (xpos) for (int i = lane; i < m.nbody * 3; i += 32) xpos[(size_t)env * m.nbody * 3 + i] = s[S_XPOS + i] + comp(org, i % 3);
+  if (xquat) for (int i = lane; i < m.nbody * 4; i += 32) xquat[(size_t)env * m.nbody * 4 + i] = s[S_XQUAT + i];
+  if (qM) for (int i = lane; i < 1024; i += 32) qM[(size_t)env * 1024 + i] = s[S_M + (i / 32) * 33 + i % 32];
+  if (bias) bias[(size_t)env * 32 + lane] = s[S_BIAS + lane];
+  if (ncon_out) {
+    unsigned a = 0, b = 0;
+    collide(s, m, lane, a, b);
+    const int ncon = misc[MI_NCON];
+    if (lane == 0) ncon_out[env] = ncon;
+    for (int c = 0; c < HOIC_MAX_CONTACTS; c++) {
+      const float* cr = s + U_CON + 16 * c;
+      const bool on = c < ncon;
+      if (pairs && lane < 2) {
+        const DevCand& cd = m.cand[on ? __float_as_int(cr[13]) : 0];
+        pairs[((size_t)env * HOIC_MAX_CONTACTS + c) * 2 + lane] = on ? (lane == 0 ? cd.g1 : cd.g2) : -1;
+      }
+      if (cdata && lane < 13) {
+        float v = 0.f;
+        if (on) { v = lane == 0 ? cr[12] : cr[lane - 1]; if (lane >= 1 && lane <= 3) v += comp(org, lane - 1); }
+        cdata[((size_t)env * HOIC_MAX_CONTACTS + c) * 13 + lane] = v;
+      }
+    }
+  }
+}
+
+// one mj_step with explicit ctrl / qfrc_applied (single-substep parity entry)
+__global__ void __launch_bounds__(32) k_substep_debug(BatchDev B, const float* ctrl, const float* qfrc_applied, float* qacc,
+                                                      float* fcon, int* stats) {
+  extern __shared__ float s[];
+  const int env = blockIdx.x, lane = threadIdx.x;
+  if (env >= B.n_envs) return;
+  const DevModel& m = *B.env_model[env];
+  float* st = B.state + (size_t)env * ST_STRIDE;
+  int* misc = (int*)(s + S_MISC);
+  if (lane < 16) misc[lane] = 0;
+  Cnt cnt;
+  memset(&cnt, 0, sizeof cnt);
+  load_state(s, st, lane, ST_QPOS, ST_QVEL);
+  s[S_WARM + lane] = st[ST_WARM + lane];
+  s[S_CTRL + lane] = lane < m.nu ? ctrl[(size_t)env * m.nu + lane] : 0.f;
+  s[S_QAPP + lane] = qfrc_applied[(size_t)env * 32 + lane];
+  for (int i = lane; i < 240; i += 32) s[S_CSUM + i] = 0.f;
+  s[S_CCNT + lane] = 0.f;
+  const float pq = s[S_QPOS + lane], pv = s[S_QVEL + lane], pq32 = st[ST_QPOS + 32];
+  __syncwarp();
+  const bool ok = substep_core(s, m, lane, false, cnt);
+  if (qacc) qacc[(size_t)env * 32 + lane] = s[S_QACC + lane];
+  if (fcon) fcon[(size_t)env * 32 + lane] = s[S_FCON + lane];
+  if (stats && lane == 0) {
+    stats[env * 4 + 0] = m.nv + misc[MI_NLIM] + misc[MI_NEDGE];
+    stats[env * 4 + 1] = misc[MI_NCON];
+    stats[env * 4 + 2] = misc[MI_ITER];
+    stats[env * 4 + 3] = ok ? 0 : misc[MI_FLAGS] | 4;
+  }
+  st[ST_QPOS + lane] = s[S_QPOS + lane];
+  st[ST_QVEL + lane] = s[S_QVEL + lane];
+  st[ST_WARM + lane] = s[S_WARM + lane];
+  st[ST_PQPOS + lane] = pq;
+  st[ST_PQVEL + lane] = pv;
+  if (lane == 0) { st[ST_QPOS + 32] = s[S_QPOS + 32]; st[ST_PQPOS + 32] = pq32; }
+  flush_counters(B, cnt, lane, 0);
+}
+
+// ================================================================================================ host side
+
+static thread_local std::string g_err;
+static unsigned long long g_launches = 0;
+static int set_err(const std::string& e) { g_err = e; return -1; }
+#define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+#define CUDA_OKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return nullptr; } } while (0)
+
+struct hoic_model {
+  int device;
+  DevModel* dev;
+  float4* mesh_vert;
+  DevModel host;
+};
+
+struct hoic_batch {
+  int device, n_envs;
+  BatchDev b;
+  std::vector<const DevModel*> env_model_host;
+  const DevModel** env_model_dev;
+  float *frames, *reward_w;
+  int *motion_offset, *motion_len;
+  size_t smem_bytes;
+};
+
+extern "C" const char* hoic_last_error(void) { return g_err.c_str(); }
+extern "C" int hoic_version(void) { return 1; }
+extern "C" unsigned long long hoic_launch_count(void) { return g_launches; }
+
+namespace {
+
+struct Blob {
+  hoic_blob_view v;
+  bool ok = true;
+  std::vector<double> f(const char* name, size_t expect = 0) {
+    int dt; size_t n;
+    const void* p = hoic_blob_find(&v, name, &dt, &n);
+    if (!p || dt != HOIC_BLOB_F64 || (expect && n != expect)) { ok = false; g_err = std::string("blob field ") + name; return std::vector<double>(expect ? expect : 1, 0.0); }
+    std::vector<double> out(n);
+    memcpy(out.data(), p, n * sizeof(double));
+    return out;
+  }
+  std::vector<int> i(const char* name, size_t expect = 0) {
+    int dt; size_t n;
+    const void* p = hoic_blob_find(&v, name, &dt, &n);
+    if (!p || dt != HOIC_BLOB_I32 || (expect && n != expect)) { ok = false; g_err = std::string("blob field ") + name; return std::vector<int>(expect ? expect : 1, 0); }
+    std::vector<int> out(n);
+    memcpy(out.data(), p, n * sizeof(int));
+    return out;
+  }
+};
+
+void quat2mat_h(const double* q, float* m) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = (float)(w * w + x * x - y * y - z * z); m[1] = (float)(2 * (x * y - w * z)); m[2] = (float)(2 * (x * z + w * y));
+  m[3] = (float)(2 * (x * y + w * z)); m[4] = (float)(w * w - x * x + y * y - z * z); m[5] = (float)(2 * (y * z - w * x));
+  m[6] = (float)(2 * (x * z - w * y)); m[7] = (float)(2 * (y * z + w * x)); m[8] = (float)(w * w - x * x - y * y + z * z);
+}
+
+double impedance_h(const double* si, double pos, double margin) {
+  auto clip = [](double x, double a, double b) { return x < a ? a : (x > b ? b : x); };
+  double s0 = clip(si[0], 1e-4, 0.9999), s1 = clip(si[1], 1e-4, 0.9999), s2 = si[2] > 0 ? si[2] : 0, s3 = clip(si[3], 1e-4, 0.9999), s4 = si[4] > 1 ? si[4] : 1;
+  if (s0 == s1 || s2 <= 1e-15) return 0.5 * (s0 + s1);
+  double x = fabs((pos - margin) / s2), y;
+  if (x >= 1 || x <= 0) return x >= 1 ? s1 : s0;
+  if (s4 == 1) y = x; else if (x <= s3) y = pow(x, s4) / pow(s3, s4 - 1); else y = 1 - pow(1 - x, s4) / pow(1 - s3, s4 - 1);
+  return s0 + y * (s1 - s0);
+}
+
+bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<float4>& verts) {
+  Blob B;
+  if (hoic_blob_open(&B.v, blob, nbytes) != 0) { g_err = "not a HOIC model blob"; return false; }
+  memset(&D, 0, sizeof D);
+  D.nq = B.i("nq", 1)[0]; D.nv = B.i("nv", 1)[0]; D.nbody = B.i("nbody", 1)[0]; D.ngeom = B.i("ngeom", 1)[0];
+  D.njnt = B.i("njnt", 1)[0]; D.nu = B.i("nu", 1)[0];
+  if (!B.ok) return false;
+  if (D.nq > H_NQ - 3 || D.nv > HN || D.nbody > HN || D.ngeom > HN || D.njnt > HN) { g_err = "model exceeds kernel maxima (32 bodies/dofs/geoms/joints)"; return false; }
+  const int nb = D.nbody, nv = D.nv, ng = D.ngeom, nj = D.njnt;
+  D.timestep = (float)B.f("opt_timestep", 1)[0];
+  D.tolerance = (float)B.f("opt_tolerance", 1)[0];
+  D.impratio = (float)B.f("opt_impratio", 1)[0];
+  D.mpr_tolerance = (float)B.f("opt_mpr_tolerance", 1)[0];
+  D.meaninertia = (float)B.f("stat_meaninertia", 1)[0];
+  { auto g = B.f("opt_gravity", 3); for (int k = 0; k < 3; k++) D.gravity[k] = (float)g[k]; }
+  D.iterations = B.i("opt_iterations", 1)[0];
+  D.mpr_iterations = B.i("opt_mpr_iterations", 1)[0];
+  auto parent = B.i("body_parentid", nb), rootid = B.i("body_rootid", nb), weld = B.i("body_weldid", nb);
+  auto dofadr = B.i("body_dofadr", nb), dofnum = B.i("body_dofnum", nb), jntadr = B.i("body_jntadr", nb), jntnum = B.i("body_jntnum", nb);
+  auto geomadr = B.i("body_geomadr", nb), geomnum = B.i("body_geomnum", nb);
+  auto bpos = B.f("body_pos", nb * 3), bquat = B.f("body_quat", nb * 4), bipos = B.f("body_ipos", nb * 3), biquat = B.f("body_iquat", nb * 4);
+  auto bmass = B.f("body_mass", nb), binertia = B.f("body_inertia", nb * 3), bsub = B.f("body_subtreemass", nb), binvw = B.f("body_invweight0", nb * 2);
+  auto jtype = B.i("jnt_type", nj), jbody = B.i("jnt_bodyid", nj), jqadr = B.i("jnt_qposadr", nj), jdadr = B.i("jnt_dofadr", nj), jlim = B.i("jnt_limited", nj);
+  auto jpos = B.f("jnt_pos", nj * 3), jaxis = B.f("jnt_axis", nj * 3), jrange = B.f("jnt_range", nj * 2), jmargin = B.f("jnt_margin", nj);
+  auto jsolref = B.f("jnt_solref", nj * 2), jsolimp = B.f("jnt_solimp", nj * 5);
+  auto dbody = B.i("dof_bodyid", nv), djnt = B.i("dof_jntid", nv), dparent = B.i("dof_parentid", nv);
+  auto darm = B.f("dof_armature", nv), ddamp = B.f("dof_damping", nv), dfl = B.f("dof_frictionloss", nv), dinvw = B.f("dof_invweight0", nv);
+  auto dsolref = B.f("dof_solref", nv * 2), dsolimp = B.f("dof_solimp", nv * 5);
+  auto qpos0 = B.f("qpos0", D.nq);
+  auto gtype = B.i("geom_type", ng), gbody = B.i("geom_bodyid", ng), gcontype = B.i("geom_contype", ng), gconaff = B.i("geom_conaffinity", ng);
+  auto gcondim = B.i("geom_condim", ng), gvadr = B.i("geom_vertadr", ng), gvnum = B.i("geom_vertnum", ng);
+  auto gpos = B.f("geom_pos", ng * 3), gquat = B.f("geom_quat", ng * 4), gsize = B.f("geom_size", ng * 3), grbound = B.f("geom_rbound", ng);
+  auto gfri = B.f("geom_friction", ng * 3), gsolref = B.f("geom_solref", ng * 2), gsolimp = B.f("geom_solimp", ng * 5), gsolmix = B.f("geom_solmix", ng);
+  auto gmargin = B.f("geom_margin", ng), ggap = B.f("geom_gap", ng);
+  std::vector<double> mv;
+  { int dt; size_t n; const void* p = hoic_blob_find(&B.v, "mesh_vert", &dt, &n); if (!p || dt != HOIC_BLOB_F64) { g_err = "blob field mesh_vert"; return false; } mv.resize(n); memcpy(mv.data(), p, n * 8); }
+  auto actdof = B.i("actuator_dofid", D.nu);
+  std::vector<int> pg1, pg2, pdim, psig;
+  std::vector<double> pfri, psolref, psolimp, pmargin, pgap;
+  { int dt; size_t n; const void* p = hoic_blob_find(&B.v, "pair_geom1", &dt, &n);
+    if (p && n > 0) { pg1 = B.i("pair_geom1"); pg2 = B.i("pair_geom2"); pdim = B.i("pair_dim"); psig = B.i("pair_signature");
+      pfri = B.f("pair_friction"); psolref = B.f("pair_solref"); psolimp = B.f("pair_solimp"); pmargin = B.f("pair_margin"); pgap = B.f("pair_gap"); } }
+  auto hbi = B.i("env_hand_body_idx");
+  auto ids = B.i("env_ids", 11);
+  auto base_pose = B.f("env_base_pose", D.nu), ctrl_scale = B.f("env_ctrl_scale", D.nu), jkp = B.f("env_jkp", D.nu), jkd = B.f("env_jkd", D.nu), tlim = B.f("env_torque_lim", D.nu);
+  auto sc = B.f("env_scalars", 8);
+  if (!B.ok) return false;
+  for (int u = 0; u < D.nu; u++) if (actdof[u] != u) { g_err = "actuators must drive dofs 0..nu-1 in order"; return false; }
+
+  D.obj_body = ids[0]; D.palm_body = ids[1]; D.hand_geom0 = ids[2]; D.hand_geom1 = ids[3]; D.obj_geom0 = ids[4]; D.obj_geom1 = ids[5];
+  D.sim_step = ids[6]; D.w_size = ids[7]; D.residual_force = ids[8]; D.surface_contact = ids[9]; D.explain_force = ids[10];
+  D.last_geom = ng - 1;
+  D.nhand_q = D.nq - 7; D.nhand_v = nv - 6; D.n_hand_body = (int)hbi.size();
+  if (D.hand_geom1 - D.hand_geom0 + 1 > H_NHG || D.n_hand_body > HN) { g_err = "too many hand geoms/bodies"; return false; }
+  D.hand_mass = (float)sc[0]; D.rf_scale = (float)sc[1]; D.rt_scale = (float)sc[2]; D.pos_thresh = (float)sc[3]; D.rot_thresh = (float)sc[4];
+  D.jpos_thresh = (float)sc[5]; D.obj_pos_thresh = (float)sc[6]; D.obj_rot_thresh = (float)sc[7];
+  D.obj_mass = (float)bmass[nb - 1];
+  for (int k = 0; k < 3; k++) D.obj_inertia[k] = (float)binertia[(nb - 1) * 3 + k];
+  for (int i = 0; i < D.n_hand_body; i++) D.hand_body_idx[i] = hbi[i];
+  for (int i = 0; i < D.nu; i++) { D.base_pose[i] = (float)base_pose[i]; D.ctrl_scale[i] = (float)ctrl_scale[i]; D.jkp[i] = (float)jkp[i]; D.jkd[i] = (float)jkd[i]; D.torque_lim[i] = (float)tlim[i]; }
+  // origin: the first three qpos must be the slides of the hand root (world-aligned translation)
+  D.org_qadr = 0;
+  // bodies
+  D.nroot = 0;
+  std::vector<int> rootslot_of_body(nb, -1);
+  for (int b = 1; b < nb; b++) {
+    if (rootid[b] == b) {
+      bool moving = false;
+      for (int c = b; c < nb; c++) if (rootid[c] == b && dofnum[c] > 0) moving = true;
+      if (moving) {
+        if (D.nroot >= 4) { g_err = "more than 4 moving kinematic trees"; return false; }
+        D.root_body[D.nroot] = b;
+        D.root_invmass[D.nroot] = bsub[b] > 1e-15 ? (float)(1.0 / bsub[b]) : 0.f;
+        rootslot_of_body[b] = D.nroot++;
+      }
+    }
+  }
+  int maxlevel = 0;
+  for (int b = 0; b < nb; b++) {
+    D.body_parent[b] = parent[b];
+    int lvl = 0;
+    for (int c = b; c != 0; c = parent[c]) lvl++;
+    D.body_level[b] = lvl;
+    if (lvl > maxlevel) maxlevel = lvl;
+    D.body_rootslot[b] = b ? rootslot_of_body[rootid[b]] : -1;
+    D.body_dofadr[b] = dofadr[b]; D.body_dofnum[b] = dofnum[b]; D.body_jntadr[b] = jntadr[b]; D.body_jntnum[b] = jntnum[b];
+    D.body_weld[b] = weld[b];
+    D.body_firstchild[b] = -1; D.body_nextsib[b] = -1;
+    for (int k = 0; k < 3; k++) { D.body_pos[b][k] = (float)bpos[3 * b + k]; D.body_ipos[b][k] = (float)bipos[3 * b + k]; D.body_inertia[b][k] = (float)binertia[3 * b + k]; }
+    for (int k = 0; k < 4; k++) D.body_quat[b][k] = (float)bquat[4 * b + k];
+    quat2mat_h(&biquat[4 * b], D.body_imat[b]);
+    D.body_mass[b] = (float)bmass[b];
+  }
+  D.nlevel = maxlevel;
+  for (int b = nb - 1; b >= 1; b--) { int p = parent[b]; D.body_nextsib[b] = D.body_firstchild[p]; D.body_firstchild[p] = b; }
+  for (int b = 0; b < nb; b++) {
+    unsigned mask = 0;
+    int bb = b;
+    while (bb && !dofnum[bb]) bb = parent[bb];
+    if (bb) for (int d = dofadr[bb] + dofnum[bb] - 1; d >= 0; d = dparent[d]) mask |= 1u << d;
+    D.body_chain[b] = mask;
+  }
+  for (int j = 0; j < nj; j++) {
+    D.jnt_type[j] = jtype[j]; D.jnt_body[j] = jbody[j]; D.jnt_qposadr[j] = jqadr[j]; D.jnt_dofadr[j] = jdadr[j]; D.jnt_limited[j] = jlim[j];
+    for (int k = 0; k < 3; k++) { D.jnt_pos[j][k] = (float)jpos[3 * j + k]; D.jnt_axis[j][k] = (float)jaxis[3 * j + k]; }
+    D.jnt_range[j][0] = (float)jrange[2 * j]; D.jnt_range[j][1] = (float)jrange[2 * j + 1];
+    D.jnt_margin[j] = (float)jmargin[j];
+    for (int k = 0; k < 2; k++) D.jnt_solref[j][k] = (float)jsolref[2 * j + k];
+    for (int k = 0; k < 5; k++) D.jnt_solimp[j][k] = (float)jsolimp[5 * j + k];
+    D.jnt_invweight[j] = (float)dinvw[jdadr[j]];
+  }
+  for (int k = 0; k < D.nq; k++) D.qpos0[k] = (float)qpos0[k];
+  for (int d = 0; d < nv; d++) {
+    D.dof_body[d] = dbody[d]; D.dof_jnt[d] = djnt[d]; D.dof_parent[d] = dparent[d];
+    D.dof_rootslot[d] = rootslot_of_body[rootid[dbody[d]]];
+    D.dof_armature[d] = (float)darm[d]; D.dof_damping[d] = (float)ddamp[d]; D.dof_frictionloss[d] = (float)dfl[d];
+    // friction-loss row constants: pos = margin = 0 -> impedance solimp[0]; K = 0
+    const double* si = &dsolimp[5 * d];
+    const double* sr = &dsolref[2 * d];
+    double imp = impedance_h(si, 0, 0), dmax = si[1] < 1e-4 ? 1e-4 : (si[1] > 0.9999 ? 0.9999 : si[1]);
+    double R = (1 - imp) * dinvw[d] / imp;
+    if (R < 1e-15) R = 1e-15;
+    double Bc;
+    if (sr[0] > 0) { double tc = sr[0] > 2 * D.timestep ? sr[0] : 2 * (double)D.timestep; Bc = 2 / (dmax * tc); } else Bc = -sr[1] / dmax;
+    D.fr_D[d] = (float)(1.0 / R); D.fr_B[d] = (float)Bc; D.fr_Rf[d] = (float)(R * dfl[d]);
+  }
+  for (int g = 0; g < ng; g++) {
+    D.geom_type[g] = gtype[g]; D.geom_body[g] = gbody[g]; D.geom_vertadr[g] = gvadr[g]; D.geom_vertnum[g] = gvnum[g];
+    for (int k = 0; k < 3; k++) { D.geom_pos[g][k] = (float)gpos[3 * g + k]; D.geom_size[g][k] = (float)gsize[3 * g + k]; }
+    quat2mat_h(&gquat[4 * g], D.geom_mat[g]);
+    D.geom_rbound[g] = (float)grbound[g];
+  }
+  verts.resize(mv.size() / 3 + 1);
+  for (size_t i = 0; i < mv.size() / 3; i++) verts[i] = make_float4((float)mv[3 * i], (float)mv[3 * i + 1], (float)mv[3 * i + 2], 0.f);
+  // collision candidates in signature order (explicit pairs merged; mj_collision driver)
+  int ncand = 0;
+  bool too_many = false;
+  auto add_cand = [&](int g1, int g2, int pair) {
+    if (gtype[g1] > gtype[g2]) { int t = g1; g1 = g2; g2 = t; }
+    const int t1 = gtype[g1], t2 = gtype[g2];
+    double margin, gap, solref[2], solimp[5], fr[3];
+    int condim;
+    if (pair < 0) {
+      if (gbody[g1] == gbody[g2]) return;
+      if (!((gcontype[g1] & gconaff[g2]) || (gcontype[g2] & gconaff[g1]))) return;
+      margin = gmargin[g1] > gmargin[g2] ? gmargin[g1] : gmargin[g2];
+      gap = ggap[g1] > ggap[g2] ? ggap[g1] : ggap[g2];
+      double s1 = gsolmix[g1], s2 = gsolmix[g2], mix = (s1 + s2 > 0) ? s1 / (s1 + s2) : 0.5;
+      condim = gcondim[g1] > gcondim[g2] ? gcondim[g1] : gcondim[g2];
+      for (int k = 0; k < 3; k++) fr[k] = gfri[3 * g1 + k] > gfri[3 * g2 + k] ? gfri[3 * g1 + k] : gfri[3 * g2 + k];
+      if (gsolref[2 * g1] > 0 && gsolref[2 * g2] > 0) for (int k = 0; k < 2; k++) solref[k] = mix * gsolref[2 * g1 + k] + (1 - mix) * gsolref[2 * g2 + k];
+      else for (int k = 0; k < 2; k++) solref[k] = gsolref[2 * g1 + k] < gsolref[2 * g2 + k] ? gsolref[2 * g1 + k] : gsolref[2 * g2 + k];
+      for (int k = 0; k < 5; k++) solimp[k] = mix * gsolimp[5 * g1 + k] + (1 - mix) * gsolimp[5 * g2 + k];
+    } else {
+      margin = pmargin[pair]; gap = pgap[pair]; condim = pdim[pair];
+      fr[0] = pfri[5 * pair]; fr[1] = pfri[5 * pair + 2]; fr[2] = pfri[5 * pair + 3];
+      for (int k = 0; k < 2; k++) solref[k] = psolref[2 * pair + k];
+      for (int k = 0; k < 5; k++) solimp[k] = psolimp[5 * pair + k];
+    }
+    int kind;
+    if (t1 == G_PLANE && t2 == G_CAPSULE) kind = K_PLANE_CAPSULE;
+    else if (t1 == G_PLANE && t2 == G_BOX) kind = K_PLANE_BOX;
+    else if (t1 == G_PLANE && t2 == G_MESH) kind = K_PLANE_MESH;
+    else if (t1 == G_CAPSULE && t2 == G_CAPSULE) kind = K_CAP_CAP;
+    else if (t1 == G_CAPSULE && t2 == G_BOX) kind = K_CAP_BOX;
+    else if (t1 == G_BOX && t2 == G_BOX) kind = K_BOX_BOX;
+    else if (t2 == G_MESH && t1 != G_PLANE) kind = K_CONVEX;
+    else return;
+    if (condim != 1 && condim != 3 && condim != 4) { too_many = true; g_err = "unsupported condim"; return; }
+    if (ncand >= H_MAXCAND) { too_many = true; g_err = "too many collision candidates"; return; }
+    DevCand& c = D.cand[ncand++];
+    c.g1 = g1; c.g2 = g2; c.kind = kind; c.condim = condim;
+    c.margin = (float)margin; c.includemargin = (float)(margin - gap);
+    for (int k = 0; k < 3; k++) c.friction[k] = (float)fr[k];
+    for (int k = 0; k < 2; k++) c.solref[k] = (float)solref[k];
+    for (int k = 0; k < 5; k++) c.solimp[k] = (float)solimp[k];
+    c.dA_tran = (float)(binvw[2 * gbody[g1]] + binvw[2 * gbody[g2]]);
+    c.dA_rot = (float)(binvw[2 * gbody[g1] + 1] + binvw[2 * gbody[g2] + 1]);
+    c.hand_slot = (g1 >= D.hand_geom0 && g1 <= D.hand_geom1 && g2 >= D.obj_geom0 && g2 <= D.obj_geom1) ? g1 - D.hand_geom0 : -1;
+  };
+  {
+    size_t pairadr = 0;
+    for (int b1 = 0; b1 < nb; b1++)
+      for (int b2 = b1 + 1; b2 < nb; b2++) {
+        const int sig = (b1 << 16) + b2;
+        bool merged = false;
+        while (pairadr < pg1.size() && psig[pairadr] <= sig) { if (psig[pairadr] == sig) merged = true; add_cand(pg1[pairadr], pg2[pairadr], (int)pairadr); pairadr++; }
+        if (merged) continue;
+        if (!geomnum[b1] || !geomnum[b2]) continue;
+        if (weld[b1] == 0 && weld[b2] == 0) continue;
+        if (weld[b1] == weld[b2]) continue;
+        const int w1 = weld[b1], w2 = weld[b2], pw1 = weld[parent[w1]], pw2 = weld[parent[w2]];
+        if ((w1 != 0 && w2 != 0) && (pw1 == w2 || pw2 == w1)) continue;
+        for (int g1 = geomadr[b1]; g1 < geomadr[b1] + geomnum[b1]; g1++)
+          for (int g2 = geomadr[b2]; g2 < geomadr[b2] + geomnum[b2]; g2++) add_cand(g1, g2, -1);
+      }
+    while (pairadr < pg1.size()) { add_cand(pg1[pairadr], pg2[pairadr], (int)pairadr); pairadr++; }
+  }
+  if (too_many) return false;
+  D.ncand = ncand;
+  return true;
+}
+
+}  // namespace
+
+extern "C" hoic_model* hoic_model_create(const void* blob_host, size_t nbytes, int device) {
+  hoic_model* M = new hoic_model();
+  std::vector<float4> verts;
+  if (!build_dev_model(blob_host, nbytes, M->host, verts)) { delete M; return nullptr; }
+  M->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&M->mesh_vert, verts.size() * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMemcpy(M->mesh_vert, verts.data(), verts.size() * sizeof(float4), cudaMemcpyHostToDevice);
+  M->host.mesh_vert = M->mesh_vert;
+  if (e == cudaSuccess) e = cudaMalloc(&M->dev, sizeof(DevModel));
+  if (e == cudaSuccess) e = cudaMemcpy(M->dev, &M->host, sizeof(DevModel), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { set_err(std::string("hoic_model_create: ") + cudaGetErrorString(e)); delete M; return nullptr; }
+  return M;
+}
+
+extern "C" void hoic_model_destroy(hoic_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaFree(m->dev);
+  cudaFree(m->mesh_vert);
+  delete m;
+}
+
+extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_models, const int* env_model_id_host, int n_envs, int device) {
+  if (!models || n_models < 1 || n_envs < 1) { set_err("hoic_batch_create: bad arguments"); return nullptr; }
+  hoic_batch* b = new hoic_batch();
+  memset(&b->b, 0, sizeof b->b);
+  b->device = device; b->n_envs = n_envs;
+  b->env_model_host.resize(n_envs);
+  for (int i = 0; i < n_envs; i++) {
+    int id = env_model_id_host ? env_model_id_host[i] : 0;
+    if (id < 0 || id >= n_models || models[id]->device != device) { set_err("hoic_batch_create: bad model id / device"); delete b; return nullptr; }
+    b->env_model_host[i] = models[id]->dev;
+  }
+  CUDA_OKP(cudaSetDevice(device));
+  CUDA_OKP(cudaMalloc(&b->env_model_dev, n_envs * sizeof(DevModel*)));
+  CUDA_OKP(cudaMemcpy(b->env_model_dev, b->env_model_host.data(), n_envs * sizeof(DevModel*), cudaMemcpyHostToDevice));
+  CUDA_OKP(cudaMalloc(&b->b.state, (size_t)n_envs * ST_STRIDE * sizeof(float)));
+  CUDA_OKP(cudaMemset(b->b.state, 0, (size_t)n_envs * ST_STRIDE * sizeof(float)));
+  CUDA_OKP(cudaMalloc(&b->b.old_geom, (size_t)n_envs * (HN * 12 + 4) * sizeof(float)));
+  CUDA_OKP(cudaMalloc(&b->b.counters, 16 * sizeof(unsigned long long)));
+  CUDA_OKP(cudaMemset(b->b.counters, 0, 16 * sizeof(unsigned long long)));
+  CUDA_OKP(cudaMalloc(&b->reward_w, 24 * sizeof(float)));
+  CUDA_OKP(cudaMemset(b->reward_w, 0, 24 * sizeof(float)));
+  b->b.n_envs = n_envs;
+  b->b.env_model = b->env_model_dev;
+  b->b.reward_w = b->reward_w;
+  b->b.mode_train = 1;
+  b->smem_bytes = (size_t)S_TOTAL * sizeof(float);
+  CUDA_OKP(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
+  CUDA_OKP(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
+  CUDA_OKP(cudaFuncSetAttribute(k_forward_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
+  CUDA_OKP(cudaFuncSetAttribute(k_substep_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
+  return b;
+}
+
+extern "C" void hoic_batch_destroy(hoic_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  cudaFree(b->env_model_dev); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters);
+  cudaFree(b->reward_w); cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
+  delete b;
+}
+
+extern "C" int hoic_batch_size(const hoic_batch* b) { return b ? b->n_envs : -1; }
+
+extern "C" int hoic_set_motions(hoic_batch* b, const float* frames_host, const int* motion_offset_host, const int* motion_len_host, int n_motions) {
+  if (!b || !frames_host || n_motions < 1) return set_err("hoic_set_motions: bad arguments");
+  size_t total = 0;
+  for (int i = 0; i < n_motions; i++) {
+    if (motion_len_host[i] < 2) return set_err("hoic_set_motions: motion shorter than 2 frames");
+    size_t e = (size_t)motion_offset_host[i] + motion_len_host[i];
+    if (e > total) total = e;
+  }
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
+  CUDA_OK(cudaMalloc(&b->frames, total * H_FRAME * sizeof(float)));
+  CUDA_OK(cudaMalloc(&b->motion_offset, n_motions * sizeof(int)));
+  CUDA_OK(cudaMalloc(&b->motion_len, n_motions * sizeof(int)));
+  CUDA_OK(cudaMemcpy(b->frames, frames_host, total * H_FRAME * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(b->motion_offset, motion_offset_host, n_motions * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(b->motion_len, motion_len_host, n_motions * sizeof(int), cudaMemcpyHostToDevice));
+  b->b.frames = b->frames; b->b.motion_offset = b->motion_offset; b->b.motion_len = b->motion_len; b->b.n_motions = n_motions;
+  return 0;
+}
+
+extern "C" int hoic_set_reward_weights(hoic_batch* b, const float* w_host) {
+  if (!b || !w_host) return set_err("hoic_set_reward_weights: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaMemcpy(b->reward_w, w_host, 24 * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int hoic_set_mode(hoic_batch* b, int train) {
+  if (!b) return set_err("hoic_set_mode: null batch");
+  b->b.mode_train = train ? 1 : 0;
+  return 0;
+}
+
+#define LAUNCH_CHECK() do { g_launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return set_err(std::string("kernel launch: ") + cudaGetErrorString(e_)); } while (0)
+
+extern "C" int hoic_reset(hoic_batch* b, const uint8_t* mask, const int* motion_id, const int* start_idx, float* obs_out, void* stream) {
+  if (!b) return set_err("hoic_reset: null batch");
+  if (!b->b.frames) return set_err("hoic_reset: call hoic_set_motions first");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_reset<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, mask, motion_id, start_idx, obs_out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float* reward, float* reward_info, uint8_t* done,
+                         uint8_t* fail, uint8_t* end, float* percent, void* stream) {
+  if (!b || !actions) return set_err("hoic_step: bad arguments");
+  if (!b->b.frames) return set_err("hoic_step: call hoic_set_motions first");
+  CUDA_OK(cudaSetDevice(b->device));
+  StepOut o = {obs, reward, reward_info, done, fail, end, percent};
+  k_step<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, actions, o);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int hoic_get_state(hoic_batch* b, float* qpos, float* qvel, void* stream) {
+  if (!b) return set_err("hoic_get_state: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_get_state<<<(b->n_envs * 33 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, qpos, qvel, nullptr);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_set_state(hoic_batch* b, const float* qpos, const float* qvel, void* stream) {
+  if (!b) return set_err("hoic_set_state: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_set_state<<<(b->n_envs * 33 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, qpos, qvel, nullptr, nullptr);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_set_cur_t(hoic_batch* b, const int* cur_t, void* stream) {
+  if (!b || !cur_t) return set_err("hoic_set_cur_t: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_set_state<<<(b->n_envs * 33 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, nullptr, nullptr, nullptr, cur_t);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_get_warmstart(hoic_batch* b, float* warm, void* stream) {
+  if (!b || !warm) return set_err("hoic_get_warmstart: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_get_state<<<(b->n_envs * 33 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, nullptr, nullptr, warm);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_set_warmstart(hoic_batch* b, const float* warm, void* stream) {
+  if (!b || !warm) return set_err("hoic_set_warmstart: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_set_state<<<(b->n_envs * 33 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, nullptr, nullptr, warm, nullptr);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_get_contacts(hoic_batch* b, int* ncon, int* geom_pairs, float* dist_pos_frame, void* stream) {
+  if (!b || !ncon) return set_err("hoic_get_contacts: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_forward_debug<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, nullptr, nullptr, nullptr, nullptr, ncon, geom_pairs, dist_pos_frame);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_get_derived(hoic_batch* b, float* xpos, float* xquat, float* qM, float* qfrc_bias, void* stream) {
+  if (!b) return set_err("hoic_get_derived: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_forward_debug<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, xpos, xquat, qM, qfrc_bias, nullptr, nullptr, nullptr);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_substep_debug(hoic_batch* b, const float* ctrl, const float* qfrc_applied, float* qacc, float* qfrc_constraint,
+                                  int* stats, void* stream) {
+  if (!b || !ctrl || !qfrc_applied) return set_err("hoic_substep_debug: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_substep_debug<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, ctrl, qfrc_applied, qacc, qfrc_constraint, stats);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_get_rfc(hoic_batch* b, float* out, void* stream) {
+  if (!b || !out) return set_err("hoic_get_rfc: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_get_rfc<<<(b->n_envs * 8 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_get_counters(hoic_batch* b, hoic_counters* out_host) {
+  if (!b || !out_host) return set_err("hoic_get_counters: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  unsigned long long h[16];
+  CUDA_OK(cudaMemcpy(h, b->b.counters, sizeof h, cudaMemcpyDeviceToHost));
+  out_host->env_steps = h[0]; out_host->substeps = h[1]; out_host->ncon = h[2]; out_host->nefc = h[3]; out_host->newton_iters = h[4];
+  out_host->ls_evals = h[5]; out_host->mpr_calls = h[6]; out_host->mpr_iters = h[7]; out_host->qp_iters = h[8];
+  out_host->fail_physics = h[9]; out_host->fail_overflow = h[10]; out_host->chol_calls = h[11];
+  return 0;
+}

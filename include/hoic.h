@@ -1,0 +1,113 @@
+/* hoic.h -- C ABI of libhoic_b200.so: batched HandMimic environments on one B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the reference's native layer on the rollout hot path.  The reference has no
+ * plugin registry: its env (uhc/envs/ho_im4.py) drives MuJoCo 2.1 through mujoco_py objects.  Each entry point below
+ * names the reference interface it replaces (paths relative to the reference root).  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions: every function returns 0 on success and <0 on error (`hoic_last_error()` gives the message);
+ * all array pointers are DEVICE pointers owned by the caller unless the name ends in `_host`; launches are
+ * asynchronous on the caller-supplied stream (a `cudaStream_t` passed as void*; NULL = legacy default stream);
+ * one host thread per batch, no internal threads, no global state besides the handles and the error string.
+ * Floating-point I/O is float32; the arithmetic type of the kernels is float32 (float64 only inside the
+ * residual-force QP).
+ */
+#ifndef HOIC_H
+#define HOIC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOIC_OBS_DIM 617     /* get_full_obs_v5, ho_im4.py:280-356 */
+#define HOIC_ACT_DIM 32      /* 26 PD targets + 6 residual force/torque, ho_im4.py:139-161 */
+#define HOIC_FRAME_DIM 212   /* one expert frame, dataset_singledepth.py:239-288 (layout: hoic_b200/motion.py) */
+#define HOIC_INFO_DIM 9      /* ho_mimic_reward_9 info vector, ho_reward.py:1043-1046 */
+#define HOIC_NQ 33
+#define HOIC_NV 32
+#define HOIC_MAX_CONTACTS 32 /* per-env contact capacity of the kernels (the MJCF's nconmax is 100) */
+
+typedef struct hoic_model hoic_model;
+typedef struct hoic_batch hoic_batch;
+
+typedef struct hoic_counters {
+  unsigned long long env_steps, substeps, ncon, nefc, newton_iters, ls_evals, mpr_calls, mpr_iters, qp_iters;
+  unsigned long long fail_physics, fail_overflow, chol_calls;
+} hoic_counters;
+
+const char* hoic_last_error(void);
+int hoic_version(void);
+
+/* replaces mujoco_py.load_model_from_path (uhc/khrylib/rl/envs/common/mujoco_env.py:15-34): the MJCF is compiled on
+ * the host by hoic_b200.mjcf into a flat blob (include/hoic_blob.h); this uploads it. `blob_host` is host memory. */
+hoic_model* hoic_model_create(const void* blob_host, size_t nbytes, int device);
+void hoic_model_destroy(hoic_model* m);
+
+/* replaces one mujoco_py.MjSim per forked sampler process (uhc/agents/agent_handmimic.py:421-428, 503-535):
+ * n_envs environments on `device`, env i using models[env_model_id_host[i]] (NULL = all model 0). */
+hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_models, const int* env_model_id_host, int n_envs,
+                              int device);
+void hoic_batch_destroy(hoic_batch* b);
+int hoic_batch_size(const hoic_batch* b);
+
+/* replaces env.set_expert(load_seq(...)) (ho_im4.py:135-137, agent_handmimic.py:450-452): all motions, concatenated
+ * frames_host[n_frames_total][212] (float32, host), motion m = frames [offset[m], offset[m]+len[m]). */
+int hoic_set_motions(hoic_batch* b, const float* frames_host, const int* motion_offset_host, const int* motion_len_host,
+                     int n_motions);
+
+/* replaces cfg.reward_weights after cfg.update_adaptive_params (uhc/utils/config_utils/handmimic_config.py:157-195):
+ * w_host[24] = w_p w_wp w_v w_j w_op w_or w_ov w_orfc k_p k_wp k_v k_j k_op k_or k_ov k_orfc, rest reserved. */
+int hoic_set_reward_weights(hoic_batch* b, const float* w_host);
+
+/* replaces env.set_mode (ho_im4.py:132): train=1 applies the tracking-error termination of ho_im4.py:655-656 */
+int hoic_set_mode(hoic_batch* b, int train);
+
+/* replaces env.reset() (mujoco_env.py:95-105 + ho_im4.py:690-716): for every env with mask[i]!=0 (mask NULL = all)
+ * take expert = motion[motion_id[i]][start_idx[i]:], state <- its frame 0, mj_resetData + forward, cur_t = 0,
+ * obs_out[i] <- observation.  motion_id/start_idx NULL = keep the env's current assignment. */
+int hoic_reset(hoic_batch* b, const uint8_t* mask, const int* motion_id, const int* start_idx, float* obs_out,
+               void* stream);
+
+/* replaces env.step(a) + custom_reward (ho_im4.py:611-662, ho_reward.py:943-1046, agent_handmimic.py:467-473):
+ * 15 x [stable PD, gravity compensation + residual wrench, contact recording, mj_step], residual-force QP,
+ * termination, reward 9, observation.  Any output pointer may be NULL. */
+int hoic_step(hoic_batch* b, const float* actions /*[N][32]*/, float* obs /*[N][617]*/, float* reward /*[N]*/,
+              float* reward_info /*[N][9]*/, uint8_t* done /*[N]*/, uint8_t* fail /*[N]*/, uint8_t* end /*[N]*/,
+              float* percent /*[N]*/, void* stream);
+
+/* replaces sim.get_state() / data.qpos, data.qvel reads (mujoco_env.py:109, ho_im4.py:794-804) */
+int hoic_get_state(hoic_batch* b, float* qpos /*[N][33]*/, float* qvel /*[N][32]*/, void* stream);
+/* replaces env.set_state(qpos, qvel) = sim.set_state + sim.forward (mujoco_env.py:107-114); keeps cur_t */
+int hoic_set_state(hoic_batch* b, const float* qpos, const float* qvel, void* stream);
+/* sets env.cur_t (parity tests start from arbitrary expert frames) */
+int hoic_set_cur_t(hoic_batch* b, const int* cur_t, void* stream);
+/* qacc_warmstart in/out (data.qacc_warmstart); parity entry */
+int hoic_get_warmstart(hoic_batch* b, float* warm /*[N][32]*/, void* stream);
+int hoic_set_warmstart(hoic_batch* b, const float* warm, void* stream);
+
+/* replaces reading data.contact[:ncon] (ho_im4.py:883-889) after the LAST forward: ncon[N], geom pairs [N][32][2],
+ * and [N][32][13] = dist, pos[3], frame[9] */
+int hoic_get_contacts(hoic_batch* b, int* ncon, int* geom_pairs, float* dist_pos_frame, void* stream);
+
+/* one mj_step (sim.step(), ho_im4.py:545) from the current state with explicit ctrl[N][26] and qfrc_applied[N][32];
+ * optional outputs qacc[N][32], qfrc_constraint[N][32], stats[N][4] = nefc, ncon, newton iterations, fail */
+int hoic_substep_debug(hoic_batch* b, const float* ctrl, const float* qfrc_applied, float* qacc, float* qfrc_constraint,
+                       int* stats, void* stream);
+/* derived quantities of the last forward (data.body_xpos / body_xquat / qM / qfrc_bias), any pointer may be NULL:
+ * xpos[N][25][3], xquat[N][25][4], qM[N][32][32], qfrc_bias[N][32] */
+int hoic_get_derived(hoic_batch* b, float* xpos, float* xquat, float* qM, float* qfrc_bias, void* stream);
+/* per-step scalars of the last hoic_step: [N][8] = rfc_score, rest_force[3], rest_torque[3], n contact geoms */
+int hoic_get_rfc(hoic_batch* b, float* out, void* stream);
+
+/* integer work counters accumulated by the kernels since creation (synchronises the device) */
+int hoic_get_counters(hoic_batch* b, hoic_counters* out_host);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+unsigned long long hoic_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOIC_H */

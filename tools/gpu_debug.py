@@ -1,0 +1,125 @@
+"""GPU bring-up script: parity of the CUDA path against the oracle + a quick throughput number.
+Run on a GPU box:  python tools/gpu_debug.py [box|bottle|banana] [n_envs]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import model, oracle_env  # noqa: E402
+from hoic_b200.vecenv import HandMimicVecEnv  # noqa: E402
+
+np.set_printoptions(precision=5, suppress=True, linewidth=200)
+obj = sys.argv[1] if len(sys.argv) > 1 else "box"
+NB = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+mdl = model(obj)
+ex = mdl.motion(1)
+print("model", obj, "blob", len(mdl.blob))
+
+# ---------------------------------------------------------------- 1. reset + derived quantities
+orc = oracle_env(obj)
+o_obs = orc.reset()
+env = HandMimicVecEnv(mdl, 4, [ex], auto_reset=False, random_start=False)
+g_obs = env.reset(motion_id=[0] * 4, start_idx=[0] * 4).cpu().numpy()
+print("reset obs maxabs err", np.abs(g_obs[0] - o_obs).max(), "argmax", np.abs(g_obs[0] - o_obs).argmax())
+xpos, xquat, qM, bias = [t.cpu().numpy() for t in env.get_derived()]
+print("xpos err", np.abs(xpos[0].ravel() - orc.get("xpos")).max(), "xquat err", np.abs(xquat[0].ravel() - orc.get("xquat")).max())
+print("qM err", np.abs(qM[0] - orc.get("qM").reshape(32, 32)).max(), "bias err", np.abs(bias[0] - orc.get("qfrc_bias")).max(), "bias max", np.abs(orc.get("qfrc_bias")).max())
+ncon, pairs, cdata = [t.cpu().numpy() for t in env.get_contacts()]
+oc = orc.contacts()
+print("contacts gpu", ncon[0], pairs[0, :ncon[0]].tolist(), "oracle", len(oc), oc[:, 13:15].astype(int).tolist())
+if len(oc) and ncon[0] == len(oc):
+    print(" dist gpu", cdata[0, :ncon[0], 0], "oracle", oc[:, 0])
+
+# ---------------------------------------------------------------- 2. single-substep parity along an oracle rollout
+rng = np.random.RandomState(0)
+S = []
+orc.reset()
+nstep = 0
+while len(S) < 256 and nstep < 400:
+    a = np.clip(rng.randn(32) * 0.3, -1, 1)
+    # replicate do_simulation by hand to capture per-substep inputs
+    obs, r, done, info = None, None, False, None
+    # use the env-level step for bookkeeping every 15 substeps, but capture substeps through the substep API
+    for k in range(15):
+        q0, v0, w0 = orc.get("qpos"), orc.get("qvel"), orc.get("qacc_warmstart")
+        fail = orc.substep(np.concatenate([a[:26], a[26:]]))
+        ctrl, qapp = orc.get("ctrl"), orc.get("qfrc_applied")
+        cnt = orc.counters()
+        if (k % 5) == 2:
+            S.append(dict(q0=q0, v0=v0, w0=w0, ctrl=ctrl, qapp=qapp, q1=orc.get("qpos"), v1=orc.get("qvel"), qacc=orc.get("qacc"),
+                          fcon=orc.get("qfrc_constraint"), ncon=cnt["ncon"], nefc=cnt["nefc"], it=cnt["solver_iter"],
+                          cons=orc.contacts()))
+        if fail:
+            break
+    orc.cur_t = orc.cur_t + 1
+    nstep += 1
+    d = orc.ho_diff()
+    if fail or d[3] > 0.1 or d[0] > 0.1 or orc.cur_t > 280:
+        orc.reset()
+print("captured", len(S), "substep states; ncon hist", np.bincount([s["ncon"] for s in S]))
+n = len(S)
+env2 = HandMimicVecEnv(mdl, n, [ex], auto_reset=False, random_start=False)
+env2.reset(motion_id=[0] * n, start_idx=[0] * n)
+env2.set_state(np.stack([s["q0"] for s in S]), np.stack([s["v0"] for s in S]))
+env2.set_warmstart(np.stack([s["w0"] for s in S]))
+gncon, gpairs, gcd = [t.cpu().numpy() for t in env2.get_contacts()]
+qacc, fcon, stats = env2.substep_debug(np.stack([s["ctrl"] for s in S]), np.stack([s["qapp"] for s in S]))
+q1, v1 = env2.get_state()
+qacc, fcon, stats, q1, v1 = [t.cpu().numpy() for t in (qacc, fcon, stats, q1, v1)]
+oq1, ov1, oqacc = np.stack([s["q1"] for s in S]), np.stack([s["v1"] for s in S]), np.stack([s["qacc"] for s in S])
+ofcon = np.stack([s["fcon"] for s in S])
+eq = np.abs(q1 - oq1).max(1)
+ev = np.abs(v1 - ov1)
+ea = np.abs(qacc - oqacc)
+rel_v = (ev / (1e-4 * np.abs(ov1) + 1e-5)).max(1)
+print("qpos maxerr", eq.max(), "qvel maxerr", ev.max(), "qacc maxerr", ea.max(), "qacc scale", np.abs(oqacc).max())
+print("qvel err / (1e-4*|v| + 1e-5): median", np.median(rel_v), "max", rel_v.max(), "frac<=1:", (rel_v <= 1).mean())
+print("fcon maxerr", np.abs(fcon - ofcon).max(), "scale", np.abs(ofcon).max())
+ncon_o = np.array([s["ncon"] for s in S])
+print("ncon match", (stats[:, 1] == ncon_o).mean(), "nefc match", (stats[:, 0] == np.array([s["nefc"] for s in S])).mean(),
+      "gpu iters mean", stats[:, 2].mean(), "oracle iters mean", np.mean([s["it"] for s in S]), "gpu fail", (stats[:, 3] != 0).sum())
+bad = np.argsort(-ea.max(1))[:5]
+for i in bad:
+    print("  worst", i, "qacc err", ea[i].max(), "at dof", ea[i].argmax(), "qacc", oqacc[i][ea[i].argmax()], "ncon", ncon_o[i], stats[i].tolist())
+mism = np.where(stats[:, 1] != ncon_o)[0][:5]
+for i in mism:
+    print("  ncon mismatch", i, "gpu", gpairs[i, :gncon[i]].tolist(), gcd[i, :gncon[i], 0], "oracle", S[i]["cons"][:, 13:15].astype(int).tolist(), S[i]["cons"][:, 0])
+
+# ---------------------------------------------------------------- 3. full-step trajectory parity (drift)
+orc.reset()
+env.reset(motion_id=[0] * 4, start_idx=[0] * 4)
+rng = np.random.RandomState(1)
+for t in range(40):
+    a = np.clip(rng.randn(32) * 0.1, -1, 1)
+    oo, orw, od, oi = orc.step(a)
+    go, grw, gd, gi = env.step(torch.as_tensor(np.tile(a, (4, 1)), dtype=torch.float32))
+    go, grw, gd = go.cpu().numpy(), grw.cpu().numpy(), gd.cpu().numpy()
+    rf = env.get_rfc().cpu().numpy()[0]
+    if t % 4 == 0 or od or gd[0]:
+        print("t", t, "obs err", np.abs(go[0] - oo).max(), "reward", orw, grw[0], "rfc", oi["rfc_score"], rf[0], "ncg", rf[7], orc.counters()["n_avg_cp"], "done", od, gd[0])
+    if od or gd[0]:
+        break
+print("counters", env.counters())
+
+# ---------------------------------------------------------------- 4. throughput
+mots = [mdl.motion(s) for s in range(1, 5)]
+big = HandMimicVecEnv(mdl, NB, mots, auto_reset=True)
+big.reset()
+act = torch.randn(NB, 32, device="cuda") * 0.1
+for _ in range(3):
+    big.step(act)
+torch.cuda.synchronize()
+t0 = time.time()
+K = 10
+for _ in range(K):
+    big.step(act)
+torch.cuda.synchronize()
+dt = (time.time() - t0) / K
+print(f"N={NB}: {dt*1e3:.2f} ms/step -> {NB/dt:.0f} env-steps/s")
+c = big.counters()
+print("counters", c, "ncon/substep", c["ncon"] / max(c["substeps"], 1), "newton/substep", c["newton_iters"] / max(c["substeps"], 1))
