@@ -321,7 +321,10 @@ __device__ __forceinline__ void mpr_support(const CObj& o1, const CObj& o2, V3 d
   s.v2 = support_w(o2, -dir, lane);
   s.v = s.v1 - s.v2;
 }
-#define CCDF_EPS FLT_EPSILON
+// libccd's absolute epsilon tests (ccdIsZero on squared lengths / dot products) are kept at the DOUBLE build's value:
+// MuJoCo links libccd in double precision, and with FLT_EPSILON the 'origin on the v0-v1 segment' shortcut of
+// discoverPortal would fire for offsets of several millimetres.
+#define CCDF_EPS 2.220446049250313e-16f
 __device__ __forceinline__ bool ccd_zero(float x) { return fabsf(x) < CCDF_EPS; }
 __device__ __forceinline__ bool ccd_eq(float a, float b) {
   float ab = fabsf(a - b);
@@ -337,7 +340,7 @@ __device__ float point_seg_dist2(V3 P, V3 x0, V3 b, V3& wit) {
   V3 e = wit - P;
   return dot(e, e);
 }
-__device__ float point_tri_dist2(V3 P, V3 x0, V3 B, V3 C, V3& wit) {
+__device__ float point_tri_dist2(V3 P, V3 x0, V3 B, V3 C, V3& wit, bool& inside) {
   V3 d1 = B - x0, d2 = C - x0, a = x0 - P;
   float v = dot(d1, d1), w = dot(d2, d2), p = dot(a, d1), q = dot(a, d2), r = dot(d1, d2);
   float s = (q * r - w * p) / (w * v - r * r), t = (-s * r - q) / w;
@@ -345,8 +348,10 @@ __device__ float point_tri_dist2(V3 P, V3 x0, V3 B, V3 C, V3& wit) {
       (ccd_eq(t + s, 1.f) || t + s < 1.f)) {
     wit = x0 + d1 * s + d2 * t;
     V3 e = wit - P;
+    inside = true;
     return dot(e, e);
   }
+  inside = false;
   V3 w2;
   float dist = point_seg_dist2(P, x0, B, wit), d2_ = point_seg_dist2(P, x0, C, w2);
   if (d2_ < dist) { dist = d2_; wit = w2; }
@@ -429,9 +434,19 @@ __device__ int mpr_penetration(const CObj& o1, const CObj& o2, float tol, int ma
     iters++;
     if (portal_reach_tol(s, v4, d, tol) || it > max_iter) {
       V3 wit;
-      depth = sqrtf(point_tri_dist2(origin, s[1].v, s[2].v, s[3].v, wit));
-      if (ccd_zero(wit.x) && ccd_zero(wit.y) && ccd_zero(wit.z)) wit = d;
-      normalize(wit);
+      bool inside;
+      depth = sqrtf(point_tri_dist2(origin, s[1].v, s[2].v, s[3].v, wit, inside));
+      if (inside) {
+        // the closest point is the orthogonal projection of the origin on the portal: its direction IS the portal
+        // normal and its length n.v1.  Taking both from the normal (cross product of O(size) edges) instead of from
+        // the O(depth) witness vector keeps shallow contacts accurate in float32 (same value in exact arithmetic).
+        float dn = dot(d, s[1].v);
+        wit = dn < 0.f ? -d : d;
+        depth = fabsf(dn);
+      } else {
+        if (ccd_zero(wit.x) && ccd_zero(wit.y) && ccd_zero(wit.z)) wit = d;
+        normalize(wit);
+      }
       dir = wit;
       // barycentric position (findPos)
       float b[4], sum;

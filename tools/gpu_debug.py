@@ -86,10 +86,16 @@ print("ncon match", (stats[:, 1] == ncon_o).mean(), "nefc match", (stats[:, 0] =
 bad = np.argsort(-ea.max(1))[:5]
 for i in bad:
     print("  worst", i, "qacc err", ea[i].max(), "at dof", ea[i].argmax(), "qacc", oqacc[i][ea[i].argmax()], "ncon", ncon_o[i], stats[i].tolist())
+    oc_ = S[i]["cons"]
+    for c in range(len(oc_)):
+        print("     oracle", oc_[c, 13:15].astype(int), "dist %.6f" % oc_[c, 0], "pos", oc_[c, 1:4], "n", oc_[c, 4:7])
+    for c in range(gncon[i]):
+        print("     gpu   ", gpairs[i, c], "dist %.6f" % gcd[i, c, 0], "pos", gcd[i, c, 1:4], "n", gcd[i, c, 4:7])
 mism = np.where(stats[:, 1] != ncon_o)[0][:5]
 for i in mism:
     print("  ncon mismatch", i, "gpu", gpairs[i, :gncon[i]].tolist(), gcd[i, :gncon[i], 0], "oracle", S[i]["cons"][:, 13:15].astype(int).tolist(), S[i]["cons"][:, 0])
 
+if os.environ.get('ONLY2'): sys.exit(0)
 # ---------------------------------------------------------------- 3. full-step trajectory parity (drift)
 orc.reset()
 env.reset(motion_id=[0] * 4, start_idx=[0] * 4)
