@@ -15,7 +15,7 @@ EXPORTS = [
     "hoic_batch_destroy", "hoic_batch_size", "hoic_set_motions", "hoic_set_reward_weights", "hoic_set_mode",
     "hoic_reset", "hoic_step", "hoic_get_state", "hoic_set_state", "hoic_set_cur_t", "hoic_get_warmstart",
     "hoic_set_warmstart", "hoic_get_contacts", "hoic_substep_debug", "hoic_get_derived", "hoic_get_rfc",
-    "hoic_get_counters", "hoic_launch_count",
+    "hoic_get_counters", "hoic_launch_count", "hoic_measure_fp32_peak",
 ]
 
 
@@ -65,6 +65,7 @@ def lib():
         L.hoic_get_rfc.argtypes = [vp, vp, vp]
         L.hoic_get_counters.argtypes = [vp, C.POINTER(Counters)]
         L.hoic_launch_count.restype = C.c_ulonglong
+        L.hoic_measure_fp32_peak.argtypes = [ip, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 

@@ -896,3 +896,45 @@ extern "C" int hoic_get_counters(hoic_batch* b, hoic_counters* out_host) {
   out_host->fail_physics = h[9]; out_host->fail_overflow = h[10]; out_host->chol_calls = h[11];
   return 0;
 }
+
+// ---- FP32 FMA peak micro-benchmark: 16 independent accumulators per thread, full-chip grid
+__global__ void k_fma_peak(float* out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = threadIdx.x * 1e-3f + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = fmaf(x[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += x[i];
+  if (s == 12345.678f) out[0] = s;
+}
+extern "C" int hoic_measure_fp32_peak(int device, double* tflops_host) {
+  if (!tflops_host) return set_err("hoic_measure_fp32_peak: null output");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  float* d;
+  CUDA_OK(cudaMalloc(&d, 4));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    k_fma_peak<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+    g_launches++;
+    cudaEventRecord(e1);
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 16.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops_host = best;
+  return 0;
+}

@@ -1,0 +1,161 @@
+"""Batched PPO pieces around the rollout engine, in plain PyTorch (policy / value MLPs and the update only):
+`MLP` / `PolicyGaussian` / `Value` (uhc/khrylib/models/mlp.py:5-27, rl/core/policy_gaussian.py:9-47, critic.py:5-18,
+state_dict keys kept: net.affine_layers.N.*, action_mean.*, action_log_std, value_head.*), a batched `ZFilter`
+(utils/zfilter.py:7-73), GAE (rl/core/common.py:5-25) as a device-side reverse scan over [T, N], and the clipped
+surrogate update (rl/agents/agent_ppo.py:16-64, agent_pg.py:18-56).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import dist as hdist
+
+
+class MLP(nn.Module):
+    def __init__(self, input_dim, hidden_dims=(2048, 1024, 512), activation="gelu"):
+        super().__init__()
+        self.activation = {"tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid, "gelu": nn.GELU()}[activation]
+        self.out_dim = hidden_dims[-1]
+        self.affine_layers = nn.ModuleList()
+        last = input_dim
+        for nh in hidden_dims:
+            self.affine_layers.append(nn.Linear(last, nh))
+            last = nh
+
+    def forward(self, x):
+        for affine in self.affine_layers:
+            x = self.activation(affine(x))
+        return x
+
+
+class PolicyGaussian(nn.Module):
+    def __init__(self, net, action_dim, log_std=0.0, fix_std=False):
+        super().__init__()
+        self.type = "gaussian"
+        self.net = net
+        self.action_mean = nn.Linear(net.out_dim, action_dim)
+        self.action_mean.weight.data.mul_(0.1)
+        self.action_mean.bias.data.mul_(0.0)
+        self.action_log_std = nn.Parameter(torch.ones(1, action_dim) * log_std, requires_grad=not fix_std)
+
+    def forward(self, x):
+        mean = self.action_mean(self.net(x))
+        log_std = self.action_log_std.expand_as(mean)
+        return mean, log_std
+
+    @torch.no_grad()
+    def select_action(self, x, mean_action=False, generator=None):
+        mean, log_std = self.forward(x)
+        if mean_action:
+            return mean
+        return mean + torch.exp(log_std) * torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
+
+    def get_log_prob(self, x, action):
+        mean, log_std = self.forward(x)
+        var = torch.exp(2 * log_std)
+        lp = -(action - mean) ** 2 / (2 * var) - 0.5 * math.log(2 * math.pi) - log_std
+        return lp.sum(1, keepdim=True)
+
+
+class Value(nn.Module):
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+        self.value_head = nn.Linear(net.out_dim, 1)
+        self.value_head.weight.data.mul_(0.1)
+        self.value_head.bias.data.mul_(0.0)
+
+    def forward(self, x):
+        return self.value_head(self.net(x))
+
+
+class ZFilter:
+    """y = clip((x - mean) / (std + 1e-8), -clip, clip) with running statistics over every env (the reference only
+    keeps worker 0's statistics, SURVEY.md section 5 -- documented difference).  Batched Welford merge."""
+
+    def __init__(self, shape, clip=5.0, device="cpu", dtype=torch.float64):
+        self.n = torch.zeros((), dtype=dtype, device=device)
+        self.mean = torch.zeros(shape, dtype=dtype, device=device)
+        self.m2 = torch.zeros(shape, dtype=dtype, device=device)
+        self.clip = clip
+
+    @property
+    def std(self):
+        var = torch.where(self.n > 1, self.m2 / torch.clamp(self.n - 1, min=1), self.mean ** 2)
+        return torch.sqrt(var)
+
+    def update(self, x):
+        x = x.to(self.mean.dtype)
+        nb = x.shape[0]
+        bmean = x.mean(0)
+        bm2 = ((x - bmean) ** 2).sum(0)
+        tot = self.n + nb
+        delta = bmean - self.mean
+        self.mean = self.mean + delta * (nb / tot)
+        self.m2 = self.m2 + bm2 + delta ** 2 * (self.n * nb / tot)
+        self.n = tot
+
+    def __call__(self, x, update=True):
+        if update:
+            self.update(x)
+        y = (x.to(self.mean.dtype) - self.mean) / (self.std + 1e-8)
+        return torch.clamp(y, -self.clip, self.clip).to(x.dtype)
+
+    def allreduce(self):
+        """Merge statistics across ranks (sum of counts, pooled mean / M2)."""
+        if not hdist._on():
+            return
+        import torch.distributed as dist
+        n, s1, s2 = self.n.clone(), self.mean * self.n, self.m2 + self.mean ** 2 * self.n
+        for t in (n, s1, s2):
+            dist.all_reduce(t)
+        self.n, self.mean = n, s1 / n
+        self.m2 = s2 - self.mean ** 2 * n
+
+
+def estimate_advantages(rewards, masks, values, gamma, tau):
+    """GAE over time-major [T, N] tensors (common.py:5-25 applied per environment column).  `values` has T+1 rows: the
+    last row bootstraps envs whose episode is still running when the fixed-horizon rollout stops (the reference only
+    stores complete episodes; SURVEY.md R21 documents this)."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    last = torch.zeros_like(rewards[0])
+    for t in range(T - 1, -1, -1):
+        delta = rewards[t] + gamma * values[t + 1] * masks[t] - values[t]
+        last = delta + gamma * tau * last * masks[t]
+        adv[t] = last
+    returns = values[:-1] + adv
+    mean, std = hdist.global_mean_std(adv.reshape(-1))
+    return (adv - mean) / std, returns
+
+
+def ppo_update(policy, value, opt_policy, opt_value, states, actions, returns, advantages, fixed_log_probs, clip_epsilon=0.2,
+               num_epoch=5, grad_clip=40.0):
+    """agent_ppo.py:16-51 with full-batch steps; gradients are averaged across ranks before clipping."""
+    stats = {}
+    for _ in range(num_epoch):
+        vloss = (value(states) - returns).pow(2).mean()
+        opt_value.zero_grad(set_to_none=True)
+        vloss.backward()
+        hdist.allreduce_grads(value.parameters())
+        opt_value.step()
+        log_probs = policy.get_log_prob(states, actions)
+        ratio = torch.exp(log_probs - fixed_log_probs)
+        surr = -torch.min(ratio * advantages, torch.clamp(ratio, 1.0 - clip_epsilon, 1.0 + clip_epsilon) * advantages).mean()
+        opt_policy.zero_grad(set_to_none=True)
+        surr.backward()
+        hdist.allreduce_grads(policy.parameters())
+        torch.nn.utils.clip_grad_norm_(policy.parameters(), grad_clip)
+        opt_policy.step()
+        stats = dict(value_loss=float(vloss.detach()), surrogate=float(surr.detach()))
+    return stats
+
+
+def make_policy_value(cfg, obs_dim=617, act_dim=32, device="cuda", dtype=torch.float32, seed=1):
+    torch.manual_seed(seed)
+    policy = PolicyGaussian(MLP(obs_dim, cfg.policy_hsize, cfg.policy_htype), act_dim, log_std=cfg.log_std, fix_std=cfg.fix_std)
+    value = Value(MLP(obs_dim, cfg.value_hsize, cfg.value_htype))
+    return policy.to(device=device, dtype=dtype), value.to(device=device, dtype=dtype)

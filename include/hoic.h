@@ -104,6 +104,8 @@ int hoic_get_rfc(hoic_batch* b, float* out, void* stream);
 
 /* integer work counters accumulated by the kernels since creation (synchronises the device) */
 int hoic_get_counters(hoic_batch* b, hoic_counters* out_host);
+/* FP32 FMA micro-benchmark on `device` (roofline denominator for the non-tensor pipe): 2*FMAs/s in TFLOP/s */
+int hoic_measure_fp32_peak(int device, double* tflops_host);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 unsigned long long hoic_launch_count(void);
 

@@ -602,3 +602,6 @@ void orc_get_counters(orc_env* e, int* out) {
 void orc_get_rfc(orc_env* e, double* out) { /* rest_force3, rest_torque3, rfc_score */
   memcpy(out, e->rest_force, 3 * sizeof(double)); memcpy(out + 3, e->rest_torque, 3 * sizeof(double)); out[6] = e->rfc_score;
 }
+
+/* test hook: the QP solver on caller-supplied data */
+int qp_nonneg_test(int n, const double* Q, const double* p, double* x) { return qp_nonneg(n, Q, p, x); }

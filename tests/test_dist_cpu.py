@@ -1,0 +1,58 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: env sharding and rollout-statistics reduction."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from common import ROOT
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from hoic_b200 import dist as hd
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+sh = hd.shard(10, rank, 2)
+assert sh.tolist() == list(range(rank, 10, 2)), sh
+mid = hd.mixed_model_ids(10, 3, rank, 2)
+assert mid.tolist() == [(i % 3) for i in range(rank, 10, 2)]
+# rollout statistics: sums / min / max / moments must equal the single-process values
+rng = np.random.RandomState(0)
+rew = rng.rand(10); info = rng.rand(10, 9); done = rng.rand(10) < 0.4
+st = hd.RolloutStats(device="cpu")
+st.update(torch.as_tensor(rew[sh]), torch.as_tensor(info[sh]), torch.as_tensor(done[sh]))
+tot = st.allreduce()
+assert abs(tot["reward_sum"] - rew.sum()) < 1e-12 and tot["num_steps"] == 10 and tot["num_episodes"] == int(done.sum())
+assert abs(tot["reward_min"] - rew.min()) < 1e-12 and abs(tot["reward_max"] - rew.max()) < 1e-12
+assert np.allclose(tot["info_sum"], info.sum(0))
+# global advantage normalisation from sharded moments (uhc/khrylib/rl/core/common.py:22)
+adv = rng.randn(10)
+mean, std = hd.global_mean_std(torch.as_tensor(adv[sh]))
+assert abs(mean - adv.mean()) < 1e-12 and abs(std - torch.as_tensor(adv).std().item()) < 1e-12
+# gradient averaging keeps replicas identical
+p = torch.nn.Linear(4, 2)
+torch.manual_seed(rank); 
+for q in p.parameters(): q.grad = torch.randn_like(q)
+ref = [q.grad.clone() for q in p.parameters()]
+hd.allreduce_grads(p.parameters())
+g = [torch.zeros_like(r) for r in ref]
+for q, r in zip(p.parameters(), ref):
+    both = [torch.zeros_like(r), torch.zeros_like(r)]
+    dist.all_gather(both, r)
+    assert torch.allclose(q.grad, (both[0] + both[1]) / 2)
+dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 500)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK {r}" in o, o

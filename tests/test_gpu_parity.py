@@ -1,0 +1,220 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI (hoic_b200.capi / vecenv), against
+the float64 oracle and the committed golden vectors.
+
+Tolerances (float32 kernels vs float64 oracle; north_star: rtol 1e-4 on single-step qpos / qvel / reward, contact sets
+exact): |dq| <= 1e-4*|q| + 2e-6, |dv| <= 1e-4*|v| + 1e-5 with at most 1% of the states allowed up to 10x that (MPR on
+float32 hull data can pick a different but equally valid portal), reward rtol 1e-4, observation atol 2e-4 per step.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import OBJECTS, ROOT, model, oracle_env
+from hoic_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(obj, n, seeds=(1,), **kw):
+    from hoic_b200.vecenv import HandMimicVecEnv
+    mdl = model(obj)
+    kw.setdefault("auto_reset", False)
+    kw.setdefault("random_start", False)
+    return HandMimicVecEnv(mdl, n, [mdl.motion(s) for s in seeds], **kw)
+
+
+def golden(obj):
+    return np.load(os.path.join(ROOT, "tests", "golden", f"{obj}.npz"))
+
+
+def test_library_loaded_and_no_fallback():
+    L = capi.lib()
+    assert L.hoic_version() == 1
+    assert os.path.abspath(capi.LIB_PATH).startswith(ROOT)
+
+
+@pytest.mark.parametrize("obj", OBJECTS)
+def test_reset_and_derived_quantities(obj):
+    G = golden(obj)
+    env = make_env(obj, 3)
+    obs = env.reset(motion_id=[0] * 3, start_idx=[0] * 3).cpu().numpy()
+    assert np.abs(obs - G["reset_obs"][None]).max() < 2e-6
+    orc = oracle_env(obj)
+    orc.reset()
+    xpos, xquat, qM, bias = [t.cpu().numpy() for t in env.get_derived()]
+    assert np.abs(xpos[0].ravel() - orc.get("xpos")).max() < 5e-7
+    assert np.abs(xquat[0].ravel() - orc.get("xquat")).max() < 1e-6
+    assert np.abs(qM[0] - orc.get("qM").reshape(32, 32)).max() < 1e-6 * np.abs(orc.get("qM")).max()
+    assert np.abs(bias[0] - orc.get("qfrc_bias")).max() < 1e-5
+    ncon, pairs, data = [t.cpu().numpy() for t in env.get_contacts()]
+    oc = orc.contacts()
+    assert ncon[0] == len(oc)
+    assert sorted(map(tuple, pairs[0, :ncon[0]].tolist())) == sorted(map(tuple, oc[:, 13:15].astype(int).tolist()))
+    env.close()
+
+
+@pytest.mark.parametrize("obj", OBJECTS)
+def test_single_substep_parity_on_golden_states(obj):
+    """One mj_step from identical (qpos, qvel, ctrl, qfrc_applied, qacc_warmstart): qpos / qvel / contact sets."""
+    G = golden(obj)
+    n = len(G["sub_q0"])
+    env = make_env(obj, n)
+    env.reset(motion_id=[0] * n, start_idx=[0] * n)
+    env.set_state(G["sub_q0"], G["sub_v0"])
+    env.set_warmstart(G["sub_w0"])
+    ncon, pairs, data = [t.cpu().numpy() for t in env.get_contacts()]
+    for i in range(n):   # contact sets: exact multiset of (geom1, geom2)
+        want = sorted(map(tuple, G["sub_pairs"][i][:G["sub_ncon"][i]].tolist()))
+        assert sorted(map(tuple, pairs[i, :ncon[i]].tolist())) == want, (i, want)
+    qacc, fcon, stats = env.substep_debug(G["sub_ctrl"], G["sub_qapp"])
+    q1, v1 = [t.cpu().numpy() for t in env.get_state()]
+    stats = stats.cpu().numpy()
+    assert (stats[:, 3] == 0).all() and (stats[:, 0] == G["sub_nefc"]).all() and (stats[:, 1] == G["sub_ncon"]).all()
+    rq = np.abs(q1 - G["sub_q1"]) / (1e-4 * np.abs(G["sub_q1"]) + 2e-6)
+    rv = np.abs(v1 - G["sub_v1"]) / (1e-4 * np.abs(G["sub_v1"]) + 1e-5)
+    worst = np.maximum(rq.max(1), rv.max(1))
+    assert (worst <= 1).mean() >= 0.99 and worst.max() <= 10, (np.sort(worst)[-5:])
+    env.close()
+
+
+@pytest.mark.parametrize("obj", OBJECTS)
+def test_step_trajectory_vs_golden(obj):
+    """env.step parity over the golden rollout: obs, reward, reward info, rfc score, done flags; drift is printed."""
+    G = golden(obj)
+    env = make_env(obj, 2)
+    env.reset(motion_id=[0, 0], start_idx=[0, 0])
+    drift = []
+    for t in range(len(G["actions"])):
+        a = torch.as_tensor(np.tile(G["actions"][t], (2, 1)), dtype=torch.float32)
+        obs, rew, done, info = env.step(a)
+        obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+        err = np.abs(obs[0] - G["obs"][t]).max()
+        drift.append(err)
+        assert err < 2e-4 * (t + 1), (t, err)
+        assert abs(rew[0] - G["reward"][t]) <= 1e-4 * abs(G["reward"][t]) + 1e-5 * (t + 1)
+        assert np.abs(info["reward_info"].cpu().numpy()[0] - G["info"][t]).max() < 1e-3
+        rf = env.get_rfc().cpu().numpy()[0, 0]
+        assert abs(rf - G["rfc"][t]) <= 2e-3 * abs(G["rfc"][t]) + 1e-3
+        assert [int(done[0]), int(info["fail"][0]), int(info["end"][0])] == G["flags"][t].tolist()
+        assert np.array_equal(obs[0], obs[1])   # identical envs give identical results
+    print(obj, "obs drift per step", ["%.1e" % d for d in drift])
+    env.close()
+
+
+def test_long_horizon_drift_vs_live_oracle():
+    """150-substep (10 env steps) drift against the oracle running on the box's CPU, small actions."""
+    obj = "bottle"
+    env = make_env(obj, 1)
+    orc = oracle_env(obj)
+    env.reset(motion_id=[0], start_idx=[0])
+    orc.reset()
+    rng = np.random.RandomState(11)
+    for t in range(10):
+        a = np.clip(rng.randn(32) * 0.05, -1, 1)
+        oo, orw, od, oi = orc.step(a)
+        go, grw, gd, gi = env.step(torch.as_tensor(a[None], dtype=torch.float32))
+        q, v = [x.cpu().numpy()[0] for x in env.get_state()]
+        dq, dv = np.abs(q - orc.get("qpos")).max(), np.abs(v - orc.get("qvel")).max()
+        print("step", t, "qpos drift %.2e qvel drift %.2e reward %.6f / %.6f" % (dq, dv, orw, float(grw[0])))
+        assert dq < 1e-3 and abs(orw - float(grw[0])) < 2e-3
+        if od:
+            break
+    env.close()
+
+
+def test_edge_cases_clipping_end_and_test_mode():
+    env = make_env("box", 4)
+    mdl = model("box")
+    T = 300
+    # start 8 frames before the end: `end` fires when cur_t >= len - w_size - 1 (ho_im4.py:657)
+    env.reset(motion_id=[0] * 4, start_idx=[T - 8] * 4)
+    a = torch.zeros(4, 32)
+    a[1] = 5.0      # clipped to +1 (ho_im4.py:613)
+    a[2] = 1.0
+    obs, rew, done, info = env.step(a)
+    assert int(info["end"][0]) == 0
+    obs2, rew2, done2, info2 = env.step(a)
+    assert info2["end"].cpu().numpy().tolist() == [1, 1, 1, 1] and done2.cpu().numpy().all()
+    assert np.array_equal(obs2[1].cpu().numpy(), obs2[2].cpu().numpy())
+    assert abs(float(info2["percent"][0]) - 2.0 / 7.0) < 1e-6
+    # test mode: tracking-error termination disabled (ho_im4.py:655-656)
+    env.reset(motion_id=[0] * 4, start_idx=[0] * 4)
+    env.set_mode("test")
+    q, v = env.get_state()
+    q[:, 26] += 0.5    # object far from the expert
+    env.set_state(q, v)
+    _, _, done3, info3 = env.step(torch.zeros(4, 32))
+    assert not info3["fail"].cpu().numpy().any()
+    env.set_mode("train")
+    env.reset(motion_id=[0] * 4, start_idx=[0] * 4)
+    q, v = env.get_state()
+    q[:, 26] += 0.5
+    env.set_state(q, v)
+    _, _, done4, info4 = env.step(torch.zeros(4, 32))
+    assert info4["fail"].cpu().numpy().all()
+    # non-finite state -> physics failure flag, no crash
+    q[:, 0] = float("nan")
+    env.set_state(q, v)
+    _, _, done5, info5 = env.step(torch.zeros(4, 32))
+    assert info5["fail"].cpu().numpy().all()
+    env.close()
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 2 size (4096 envs): determinism across launches, independence of batch position, auto-reset."""
+    N = 4096
+    mdl = model("box")
+    from hoic_b200.vecenv import HandMimicVecEnv
+    mots = [mdl.motion(s) for s in (1, 2, 3, 4)]
+    envA = HandMimicVecEnv(mdl, N, mots, seed=7, auto_reset=True)
+    envB = HandMimicVecEnv(mdl, N, mots, seed=7, auto_reset=True)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    oa, ob = envA.reset().clone(), envB.reset().clone()
+    assert torch.equal(oa, ob)
+    tot_done = 0
+    for t in range(12):
+        act = torch.randn(N, 32, device="cuda", generator=gen) * 0.3
+        o1, r1, d1, _ = envA.step(act)
+        o2, r2, d2, _ = envB.step(act)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)    # bitwise reproducible
+        assert torch.isfinite(o1).all() and torch.isfinite(r1).all() and (r1 >= 0).all() and (r1 <= 1.0 + 1e-6).all()
+        tot_done += int(d1.sum())
+    assert tot_done > 0                                   # some episodes ended and were re-seeded in place
+    c = envA.counters()
+    assert c["env_steps"] == N * 12 and c["fail_overflow"] == 0
+    # batch-position independence: env 0 of a 1-env batch equals env 0 of the big batch from the same start
+    small = HandMimicVecEnv(mdl, 1, mots, seed=7, auto_reset=False)
+    big = HandMimicVecEnv(mdl, 257, mots, seed=7, auto_reset=False)
+    small.reset(motion_id=[2], start_idx=[5])
+    big.reset(motion_id=[2] * 257, start_idx=[5] * 257)
+    a = torch.randn(1, 32, device="cuda", generator=gen) * 0.2
+    os_, rs, _, _ = small.step(a)
+    ob_, rb, _, _ = big.step(a.repeat(257, 1))
+    assert torch.equal(os_[0], ob_[0]) and torch.equal(os_[0], ob_[256])
+    for e in (envA, envB, small, big):
+        e.close()
+
+
+def test_mixed_object_batch():
+    """BASELINE config 5 shape: env_model_id = env_id mod 3, each env draws motions of its own object."""
+    from hoic_b200.vecenv import HandMimicVecEnv
+    mdls = [model(o) for o in OBJECTS]
+    mots = [m.motion(1) for m in mdls]
+    env = HandMimicVecEnv(mdls, 96, mots, motion_model=[0, 1, 2], seed=1, auto_reset=True)
+    obs = env.reset().clone()
+    singles = []
+    for k, m in enumerate(mdls):
+        e = HandMimicVecEnv(m, 1, [mots[k]], auto_reset=False, random_start=False)
+        singles.append(e.reset(motion_id=[0], start_idx=[0]).clone())
+    # random_start draws different start frames, so compare structure only where start_idx==0 is forced
+    env2 = HandMimicVecEnv(mdls, 6, mots, motion_model=[0, 1, 2], auto_reset=False, random_start=False)
+    o2 = env2.reset()
+    for i in range(6):
+        assert torch.equal(o2[i], singles[i % 3][0])
+    a = torch.zeros(96, 32, device="cuda")
+    for _ in range(3):
+        o, r, d, _ = env.step(a)
+    assert torch.isfinite(o).all() and env.counters()["mpr_calls"] > 0
+    env.close(); env2.close()

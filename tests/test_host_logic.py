@@ -1,0 +1,388 @@
+"""CPU tests: host logic (MJCF compiler, blob, config, motion derivations), the C-ABI surface, and the oracle pinned by
+known answers, by a numpy transcription of the reference's pure-Python observation / reward code, and by goldens."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import OBJECTS, ROOT, model, oracle_env
+from hoic_b200 import blob as hblob
+from hoic_b200 import mjcf, motion as hmotion
+from hoic_b200.config import Config, REWARD_KEYS
+import ref_numpy as R
+
+
+# ------------------------------------------------------------------------------------------------ compiler / blob
+@pytest.mark.parametrize("obj,ngeom,nverts", [("box", 23, 0), ("bottle", 24, 388), ("banana", 25, 1877)])
+def test_compile_invariants(obj, ngeom, nverts):
+    """Sizes implied by ho_im4.py:72-107, 139-167 and SURVEY.md section 8."""
+    m = model(obj)
+    A = m.arrays
+    assert (int(A["nq"][0]), int(A["nv"][0]), int(A["nu"][0]), int(A["nbody"][0]), int(A["njnt"][0])) == (33, 32, 26, 25, 27)
+    assert int(A["ngeom"][0]) == ngeom and A["mesh_vert"].shape[0] == nverts
+    ids = A["env_ids"]
+    assert (ids[2], ids[3]) == (2, 20) and ids[4] == 21 and ids[5] == ngeom - 2 and ids[0] == 24 and ids[1] == 3
+    assert abs(A["env_scalars"][0] - 0.635) < 1e-12            # hand mass = sum of <inertial mass>
+    assert len(A["pair_geom1"]) == 19                          # explicit <pair>s (LF1-RF1 listed twice)
+    assert A["opt_timestep"][0] == 0.0022222 and A["opt_iterations"][0] == 20
+    M = m.compiled()
+    # class= overrides childclass: hand geoms keep the default friction / condim 3, conaffinity 0
+    g = M["names_geom"].index("robot0:C_FF1")
+    assert A["geom_condim"][g] == 3 and np.allclose(A["geom_friction"][g], [1, 0.005, 0.0001]) and A["geom_conaffinity"][g] == 0
+    # joint armature overrides the class value
+    assert np.allclose(A["dof_armature"][:26], 0.005) and np.allclose(A["dof_armature"][26:], 0.001)
+    assert np.allclose(A["dof_frictionloss"], 0.001) and np.allclose(A["dof_damping"][:26], 0.01) and np.allclose(A["dof_damping"][26:], 0)
+
+
+def test_object_inertia_box():
+    A = model("box").arrays
+    s = np.array([0.0165, 0.0265, 0.049])
+    mass = 8 * s.prod() * 125
+    assert abs(A["body_mass"][24] - mass) < 1e-12
+    I = mass / 3 * np.array([s[1] ** 2 + s[2] ** 2, s[0] ** 2 + s[2] ** 2, s[0] ** 2 + s[1] ** 2])
+    assert np.allclose(A["body_inertia"][24], I, rtol=1e-12)
+    assert np.allclose(A["body_iquat"][24], [1, 0, 0, 0])
+
+
+def test_mesh_props_closed_form():
+    """mesh_props_legacy on a box mesh reproduces the primitive's volume / CoM / inertia."""
+    s = np.array([0.3, 0.2, 0.1])
+    v = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], dtype=float) * s + np.array([0.5, -0.2, 0.1])
+    from scipy.spatial import ConvexHull
+    h = ConvexHull(v)
+    V, com, I = mjcf.mesh_props_legacy(v[h.simplices])
+    assert abs(V - 8 * s.prod()) < 1e-12 and np.allclose(com, [0.5, -0.2, 0.1])
+    Iref = V / 3 * np.array([s[1] ** 2 + s[2] ** 2, s[0] ** 2 + s[2] ** 2, s[0] ** 2 + s[1] ** 2])
+    assert np.allclose(np.diag(I), Iref) and np.allclose(I - np.diag(np.diag(I)), 0, atol=1e-15)
+
+
+def test_blob_roundtrip_and_json():
+    m = model("box")
+    d = hblob.unpack(m.blob)
+    b2 = hblob.pack(d)
+    d2 = hblob.unpack(b2)
+    assert set(d) == set(d2)
+    for k in d:
+        if isinstance(d[k], bytes):
+            assert d[k] == d2[k]
+        else:
+            assert np.array_equal(d[k], d2[k])
+    assert '"body_pos"' in hblob.dump_json(m.blob)
+    with pytest.raises(ValueError):
+        hblob.unpack(b"garbage" * 10)
+
+
+def test_shipped_blobs_match_reference_compile():
+    """hoic_b200/data/*.hoicmodel (what the GPU box loads) equal a fresh compile when the reference tree is reachable."""
+    from hoic_b200 import assets
+    if assets.reference_root() is None:
+        pytest.skip("reference tree not reachable")
+    for obj in OBJECTS:
+        fresh = assets.compile_from_reference(obj, assets.reference_root())
+        shipped = open(os.path.join(assets.DATA_DIR, f"{obj}.hoicmodel"), "rb").read()
+        a, b = hblob.unpack(fresh.blob), hblob.unpack(shipped)
+        for k in a:
+            if not isinstance(a[k], bytes):
+                assert np.allclose(a[k], b[k], rtol=1e-12, atol=1e-15), k
+
+
+def test_config_adaptive_schedule():
+    """handmimic_config.py:175-195: w_orfc,k_orfc = {0.05,0.1} e^{8e-4 min(i,3000)}, k_p,k_j,k_wp = {6,12,3} e^{-5e-4 ...}."""
+    cfg = model("box").cfg
+    cfg.update_adaptive_params(0)
+    w = cfg.reward_vector()
+    d = dict(zip(REWARD_KEYS, w))
+    assert np.isclose(d["w_orfc"], 0.05) and np.isclose(d["k_orfc"], 0.1) and np.isclose(d["k_p"], 6) and np.isclose(d["k_j"], 12)
+    cfg.update_adaptive_params(5000)
+    d = dict(zip(REWARD_KEYS, cfg.reward_vector()))
+    assert np.isclose(d["w_orfc"], 0.05 * np.exp(8e-4 * 3000)) and np.isclose(d["k_wp"], 3 * np.exp(-5e-4 * 3000))
+    cfg.update_adaptive_params(0)
+    assert cfg.sim_step == 15 and cfg.future_w_size == 5 and cfg.residual_force_scale == 2.5 and cfg.unsupported == []
+
+
+def test_motion_derivations():
+    M = model("box").compiled()
+    ex = model("box").motion(1)
+    T = ex["seq_len"]
+    assert T == 300 and hmotion.pack_frames(ex).shape == (300, 212)
+    hv = ex["hand_dof_vel_seq"]
+    assert np.allclose(hv[1:], (ex["hand_dof_seq"][1:] - ex["hand_dof_seq"][:-1]) * 30) and np.allclose(hv[0], hv[1])
+    lo, hi = M["jnt_range"][:-1, 0], M["jnt_range"][:-1, 1]
+    assert (ex["hand_dof_seq"] >= lo - 1e-12).all() and (ex["hand_dof_seq"] <= hi + 1e-12).all()
+    # FK of the expert equals the oracle's FK at that pose
+    env = oracle_env("box")
+    q = np.concatenate([ex["hand_dof_seq"][150], M["qpos0"][26:]])
+    env.set_state(q, np.zeros(32))
+    idx = M["env"]["hand_body_idx"]
+    assert np.abs(env.get("xpos").reshape(-1, 3)[idx] - ex["body_pos_seq"][150]).max() < 1e-12
+    assert np.abs(env.get("xquat").reshape(-1, 4)[idx] - ex["body_quat_seq"][150]).max() < 1e-12
+    sl = hmotion.load_seq(ex, 37)
+    assert sl["seq_len"] == 263 and np.array_equal(sl["obj_pose_seq"][0], ex["obj_pose_seq"][37])
+    # axis-angle of a known rotation
+    Rz = np.array([[np.cos(0.3), -np.sin(0.3), 0], [np.sin(0.3), np.cos(0.3), 0], [0, 0, 1]])
+    assert np.allclose(hmotion.matrix_to_axis_angle(Rz), [0, 0, 0.3])
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_capi_exports_every_declared_symbol():
+    from hoic_b200 import build, capi
+    so = build.build()
+    lib = ctypes.CDLL(so)
+    hdr = open(os.path.join(ROOT, "include", "hoic.h")).read()
+    declared = set(re.findall(r"\b(hoic_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.hoic_version.restype = ctypes.c_int
+    assert lib.hoic_version() == 1
+
+
+def test_vecenv_refuses_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hoic_b200 import capi
+    from hoic_b200.vecenv import HandMimicVecEnv
+    with pytest.raises(capi.HoicError):
+        HandMimicVecEnv(model("box"), 2, [model("box").motion(1)])
+
+
+# ------------------------------------------------------------------------------------------------ oracle: known answers
+def test_oracle_mass_matrix_vs_jacobian_sum():
+    env = oracle_env("bottle")
+    env.reset()
+    rng = np.random.RandomState(0)
+    M = model("bottle").compiled()
+    for _ in range(3):
+        q = env.get("qpos")
+        q[:26] += rng.randn(26) * 0.2
+        q[29:33] = rng.randn(4)
+        q[29:33] /= np.linalg.norm(q[29:33])
+        env.set_state(q, np.zeros(32))
+        H, _, _, _ = mjcf.mass_matrix(M, env.get("qpos"))
+        assert np.abs(env.qM() - H).max() < 1e-13
+
+
+def test_oracle_bias_is_gravity_gradient_and_coriolis():
+    """qfrc_bias(q, 0) = dV/dq for the hand joints, and the velocity part matches d/dt(M) v - 1/2 d(v'Mv)/dq."""
+    env = oracle_env("box")
+    env.reset()
+    M = model("box").compiled()
+    rng = np.random.RandomState(1)
+    q = env.get("qpos")
+    q[3:26] += rng.randn(23) * 0.2
+    nb = M["nbody"]
+
+    def potential(qq):
+        kin = mjcf.fk(M, qq)
+        z = [kin["xpos"][b][2] + (mjcf.quat2mat(kin["xquat"][b]) @ M["body_ipos"][b])[2] for b in range(nb)]
+        return 9.81 * float(np.dot(M["body_mass"], z))
+
+    env.set_state(q, np.zeros(32))
+    bias0 = env.get("qfrc_bias")
+    g = np.zeros(26)
+    for i in range(26):
+        dq = np.zeros(33); dq[i] = 1e-6
+        g[i] = (potential(q + dq) - potential(q - dq)) / 2e-6
+    assert np.abs(bias0[:26] - g).max() < 2e-6
+    v = np.zeros(32); v[:26] = rng.randn(26)
+    env.set_state(q, v)
+    cor = env.get("qfrc_bias") - bias0
+
+    def Mq(qq):
+        return mjcf.mass_matrix(M, qq)[0]
+    e = 1e-6
+    qd = np.zeros(33); qd[:26] = v[:26]
+    Mdot_v = (Mq(q + e * qd) - Mq(q - e * qd)) @ v / (2 * e)
+    grad = np.array([v @ (Mq(q + e * np.eye(33)[i]) - Mq(q - e * np.eye(33)[i])) @ v / (2 * e) for i in range(26)])
+    assert np.abs(cor[:26] - (Mdot_v[:26] - 0.5 * grad)).max() < 1e-6
+
+
+def test_oracle_free_fall_and_rest():
+    env = oracle_env("box")
+    env.reset()
+    A = model("box").arrays
+    h, m = A["opt_timestep"][0], A["body_mass"][24]
+    q = env.get("qpos"); q[26:29] = [0.5, 0.5, 1.5]; q[29:33] = [1, 0, 0, 0]
+    env.set_state(q, np.zeros(32)); env.set_ctrl_applied(np.zeros(26), np.zeros(32))
+    for _ in range(100):
+        env.mj_step()
+    # weight m g on inertia m + armature, opposed by the 0.001 N friction loss of the free joint
+    a_eff = (m * 9.81 - 0.001) / (m + 0.001)
+    assert abs(env.get("qvel")[28] + a_eff * h * 100) < 1e-9
+    q = env.get("qpos"); q[26:29] = [0.4, 0.4, 0.549 - 1e-4]; q[29:33] = [1, 0, 0, 0]; q[0:3] = [0, 0, 1.0]
+    env.set_state(q, np.zeros(32))
+    for _ in range(600):
+        env.mj_step()
+    assert np.abs(env.get("qvel")[26:]).max() < 1e-10
+    assert abs(env.get("qfrc_constraint")[28] - m * 9.81) < 1e-9          # contact force balances the weight
+    c = env.contacts()
+    tab = c[c[:, 13] == 1]
+    assert len(tab) == 4 and np.allclose(tab[:, 4:7], [0, 0, 1]) and set(tab[:, 15]) == {4.0}
+
+
+def test_oracle_newton_reaches_the_optimum():
+    from scipy.optimize import minimize
+    env = oracle_env("bottle")
+    env.reset()
+    rng = np.random.RandomState(0)
+    for _ in range(40):
+        env.step(rng.randn(32) * 0.1)
+    J, Mq, aref, D = env.efc_J(), env.qM(), env.get("efc_aref"), env.get("efc_D")
+    qacc, qs, force = env.get("qacc"), env.get("qacc_smooth"), env.get("efc_force")
+    Rr, fl = 1 / D, 0.001
+
+    def cost(a):
+        jar = J @ a - aref
+        c = 0.5 * (a - qs) @ Mq @ (a - qs)
+        for r, x in enumerate(jar):
+            if r < 32:
+                Rf = Rr[r] * fl
+                c += 0.5 * D[r] * x * x if abs(x) < Rf else fl * (abs(x) - 0.5 * Rf)
+            elif x < 0:
+                c += 0.5 * D[r] * x * x
+        return c
+    res = minimize(cost, qacc, method="BFGS", options=dict(gtol=1e-12, maxiter=4000))
+    assert cost(qacc) <= res.fun + 1e-9 * abs(res.fun)
+    assert np.linalg.norm(Mq @ (qacc - qs) - J.T @ force) < 1e-9          # KKT stationarity
+
+
+def test_oracle_collision_closed_forms():
+    env = oracle_env("box")
+    env.reset()
+    q = env.get("qpos")
+    # box lying flat 1 mm inside the table, rotated 30 deg about z: 4 corner contacts, dist = -1 mm, pos mid-surface
+    q[0:3] = [0, 0, 1.5]
+    th = np.pi / 6
+    q[26:29] = [0.1, -0.2, 0.5 + 0.049 - 1e-3]; q[29:33] = [np.cos(th / 2), 0, 0, np.sin(th / 2)]
+    env.set_state(q, np.zeros(32))
+    c = env.contacts(); c = c[(c[:, 13] == 1) & (c[:, 14] == 21)]
+    assert len(c) == 4 and np.allclose(c[:, 0], -1e-3, atol=1e-12) and np.allclose(c[:, 3], 0.5 - 0.5e-3, atol=1e-12)
+    corners = np.array([[sx * 0.0165, sy * 0.0265] for sx in (-1, 1) for sy in (-1, 1)])
+    Rz = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    want = corners @ Rz.T + [0.1, -0.2]
+    got = c[:, 1:3]
+    assert all(np.min(np.linalg.norm(want - g, axis=1)) < 1e-12 for g in got)
+    # object dropped to the floor away from the table: plane-box, lowest corners
+    q[26:29] = [2.0, 2.0, 0.049 - 2e-3]; q[29:33] = [1, 0, 0, 0]
+    env.set_state(q, np.zeros(32))
+    c = env.contacts(); c = c[(c[:, 13] == 0) & (c[:, 14] == 21)]
+    assert len(c) == 4 and np.allclose(c[:, 0], -2e-3, atol=1e-12) and np.allclose(c[:, 4:7], [0, 0, 1])
+
+
+def test_oracle_capsule_box_and_mpr_agree_on_a_face_contact():
+    """A finger capsule pressed flat onto a face of the box object: analytic capsule-box gives 2 end contacts with the
+    face normal; the same pose against the convex-mesh bottle bottom checks MPR depth against plane geometry."""
+    env = oracle_env("box")
+    env.reset()
+    M = model("box").compiled()
+    g = M["names_geom"].index("robot0:C_FF1")
+    q = env.get("qpos"); q[0:3] = [0, 0, 1.0]; q[6:26] = 0
+    env.set_state(q, np.zeros(32))
+    gp, gm = env.get("geom_xpos").reshape(-1, 3)[g], env.get("geom_xmat").reshape(-1, 3, 3)[g]
+    r, hl = M["geom_size"][g][0], M["geom_size"][g][1]
+    axis = gm[:, 2]
+    # orthonormal frame with x along the capsule axis; put the box's +z face 0.5 mm into the capsule from "below" (-n)
+    n = np.cross(axis, [0.3, 0.5, 0.8]); n /= np.linalg.norm(n)
+    y = np.cross(n, axis)
+    Rb = np.stack([axis, y, n], axis=1)            # box axes: x along capsule, z along n
+    pen = 5e-4
+    centre = gp - n * (r - pen + 0.049)
+    q[26:29] = centre; q[29:33] = mjcf.mat2quat(Rb)
+    env.set_state(q, np.zeros(32))
+    c = env.contacts(); c = c[(c[:, 13] == g) & (c[:, 14] == 21)]
+    assert len(c) == 2 and np.allclose(c[:, 0], -pen, atol=1e-9)
+    assert np.allclose(c[:, 4:7], -n, atol=1e-9)                      # from capsule (geom1) towards the box
+    ends = np.sort((c[:, 1:4] - gp) @ axis)
+    assert np.allclose(ends, [-min(hl, 0.0165), min(hl, 0.0165)], atol=1e-9)
+
+
+def test_oracle_mpr_depth_on_mesh_face():
+    env = oracle_env("bottle")
+    env.reset()
+    M = model("bottle").compiled()
+    # bottle upright, pushed 0.3 mm into the table: box-mesh MPR contact with normal +z and that depth
+    q = env.get("qpos"); q[0:3] = [0, 0, 1.5]
+    ex = model("bottle").motion(1)
+    q[26:33] = ex["obj_pose_seq"][0]; q[28] -= 3e-4 + 2e-4
+    env.set_state(q, np.zeros(32))
+    c = env.contacts(); c = c[c[:, 13] == 1]
+    assert len(c) >= 1
+    assert np.allclose(c[:, 4:7], [0, 0, 1], atol=1e-6) and np.allclose(c[:, 0], -3e-4, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ oracle vs transcription
+@pytest.mark.parametrize("obj", OBJECTS)
+def test_oracle_obs_reward_vs_numpy_transcription(obj):
+    env = oracle_env(obj)
+    mdl = model(obj)
+    M, ex = mdl.compiled(), mdl.motion(1)
+    ws = dict(mdl.cfg.reward_weights)
+    rng = np.random.RandomState(5)
+    env.reset()
+    t = 0
+    for step in range(12):
+        o, r, done, info = env.step(rng.randn(32) * 0.15)
+        t += 1
+        view = R.EnvView(env.get("qpos"), env.get("qvel"), env.get("xpos").reshape(-1, 3), env.get("xquat").reshape(-1, 4), ex, t,
+                         M["env"]["hand_body_idx"], M["env"]["palm_body"], rfc_score=info["rfc_score"])
+        assert np.abs(R.get_full_obs_v5(view) - o).max() < 1e-12
+        rr, ri = R.ho_mimic_reward_9(view, ws)
+        assert abs(rr - r) < 1e-12 and np.abs(ri - info["reward_info"]).max() < 1e-12
+        d = R.calc_ho_diff(view)
+        assert np.abs(d - env.ho_diff()).max() < 1e-12
+        body_fail = d[0] > 0.1 or d[1] > 1.0 or d[2] > 0.1 or d[3] > 0.1 or d[4] > 1.0
+        assert info["fail"] == (body_fail or env.counters()["warn_bad"] == 1)
+        assert info["end"] == (t >= 300 - 5 - 1)
+        if done:
+            break
+
+
+def test_oracle_rfc_qp_vs_bounded_lbfgs():
+    """The active-set QP of the oracle reaches the optimum of the reference's QP (ho_im4.py:1063-1068)."""
+    rng = np.random.RandomState(3)
+    import ctypes as C
+    from oracle import lib
+    L = lib()
+    for trial in range(4):
+        k = 1 + trial
+        frames = []
+        for i in range(k):
+            n = rng.randn(3); n /= np.linalg.norm(n)
+            t = np.cross(n, [1, 0, 0]); t /= np.linalg.norm(t)
+            frames.append(np.concatenate([rng.randn(3) * 0.03 + [0, 0, 0.6], n, t, np.cross(n, t)]))
+        F, T = rng.randn(3) * 0.3, rng.randn(3) * 0.005
+        ts = rng.randint(1, 30, size=k).astype(float)
+        gx, gv, ga = rng.randn(k, 3) * 0.02 + [0, 0, 0.6], rng.randn(k, 3) * 0.05, rng.randn(k, 3)
+        obj_p, obj_v, obj_w = np.array([0, 0, 0.6]) + rng.randn(3) * 0.01, rng.randn(3) * 0.05, rng.randn(3)
+        score, fval, Q, p = R.solve_rfc_numpy(F, T, frames, ts, gx, gv, ga, obj_p, obj_v, obj_w)
+        n = Q.shape[0]
+        x = np.zeros(n)
+        L.qp_nonneg_test.restype = C.c_int
+        Qc, pc = np.ascontiguousarray(Q), np.ascontiguousarray(p)
+        L.qp_nonneg_test(C.c_int(n), Qc.ctypes.data_as(C.c_void_p), pc.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p))
+        f_or = 0.5 * x @ Q @ x + p @ x
+        assert (x >= 0).all() and f_or <= fval + 1e-9 * (1 + abs(fval))
+        g = Q @ x + p                                         # KKT: g >= 0, g_i x_i = 0
+        assert g.min() > -1e-8 * (1 + np.abs(p).max()) and np.abs(g * x).max() < 1e-7 * (1 + np.abs(p).max())
+
+
+# ------------------------------------------------------------------------------------------------ goldens
+@pytest.mark.parametrize("obj", OBJECTS)
+def test_oracle_reproduces_goldens(obj):
+    G = np.load(os.path.join(ROOT, "tests", "golden", f"{obj}.npz"))
+    env = oracle_env(obj)
+    assert np.abs(env.reset() - G["reset_obs"]).max() < 1e-9
+    for t in range(len(G["actions"])):
+        o, r, d, i = env.step(G["actions"][t])
+        assert np.abs(o - G["obs"][t]).max() < 1e-7 and abs(r - G["reward"][t]) < 1e-8
+        assert [int(d), int(i["fail"]), int(i["end"])] == G["flags"][t].tolist()
+    for k in range(0, len(G["sub_q0"]), 6):
+        env.set_state(G["sub_q0"][k], G["sub_v0"][k])
+        env.set_warmstart(G["sub_w0"][k])
+        env.set_ctrl_applied(G["sub_ctrl"][k], G["sub_qapp"][k])
+        env.clear_warnings()
+        env.mj_step()
+        assert np.abs(env.get("qvel") - G["sub_v1"][k]).max() < 1e-8 and env.counters()["ncon"] == G["sub_ncon"][k]
