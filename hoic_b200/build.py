@@ -12,7 +12,7 @@ DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "cs
     os.path.join(HERE, "..", "include", "hoic.h"), os.path.join(HERE, "..", "include", "hoic_blob.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-         "--fmad=true", "-Xptxas", "-v"]
+         "--fmad=true", "-prec-div=false", "-prec-sqrt=false", "-ftz=true", "-Xptxas", "-v"]
 
 
 def needs_build():

@@ -108,7 +108,7 @@ __device__ int sphere_box_local(RawCon& c, float margin, V3 p, float r, const fl
 
 // capsule (geom1) vs box (geom2): exact minimiser of the segment-box distance, two contacts at the ends of the
 // portion above a face when the closest feature is a face (same construction as the oracle).
-__device__ int capsule_box(RawCon* c, float margin, V3 cp, const M3& cm, const float* cs, V3 bp, const M3& bm, const float* bs) {
+__device__ __noinline__ int capsule_box(RawCon* c, float margin, V3 cp, const M3& cm, const float* cs, V3 bp, const M3& bm, const float* bs) {
   const float h = cs[1], r = cs[0];
   V3 p0 = mulTv(bm, cp - bp), a = mulTv(bm, col(cm, 2));
   float tb[8];
@@ -161,7 +161,7 @@ __device__ int capsule_box(RawCon* c, float margin, V3 cp, const M3& cm, const f
 }
 
 // box (geom1) vs box (geom2): 15-axis separating-axis test, reference/incident face clipping or edge-edge point
-__device__ int box_box(RawCon* c, float margin, V3 p1, const M3& R1, const float* A, V3 p2, const M3& R2, const float* B) {
+__device__ __noinline__ int box_box(RawCon* c, float margin, V3 p1, const M3& R1, const float* A, V3 p2, const M3& R2, const float* B) {
   V3 p = p2 - p1, pp = mulTv(R1, p);
   float R[9], Q[9], s, best = -FLT_MAX;
   V3 nrm = v3(0, 0, 0);
@@ -286,7 +286,7 @@ struct Supp { V3 v, v1, v2; };
 
 // support point of a convex object along world direction `dir`; the whole warp calls this with identical
 // arguments, mesh vertices are scanned cooperatively (lane-strided) and reduced by shuffles.
-__device__ V3 support_w(const CObj& o, V3 dirw, int lane) {
+__device__ __noinline__ V3 support_w(const CObj& o, V3 dirw, int lane) {
   V3 d = mulTv(o.mat, dirw), l;
   if (o.type == G_CAPSULE) {
     float nn = norm(d);
@@ -340,7 +340,7 @@ __device__ float point_seg_dist2(V3 P, V3 x0, V3 b, V3& wit) {
   V3 e = wit - P;
   return dot(e, e);
 }
-__device__ float point_tri_dist2(V3 P, V3 x0, V3 B, V3 C, V3& wit, bool& inside) {
+__device__ __noinline__ float point_tri_dist2(V3 P, V3 x0, V3 B, V3 C, V3& wit, bool& inside) {
   V3 d1 = B - x0, d2 = C - x0, a = x0 - P;
   float v = dot(d1, d1), w = dot(d2, d2), p = dot(a, d1), q = dot(a, d2), r = dot(d1, d2);
   float s = (q * r - w * p) / (w * v - r * r), t = (-s * r - q) / w;
@@ -375,7 +375,7 @@ __device__ __forceinline__ void expand_portal(Supp* s, const Supp& v4) {
   else { if (dot(s[3].v, c) > 0.f) s[2] = v4; else s[1] = v4; }
 }
 // returns 0 when intersecting; all lanes run the same scalar logic (uniform), only support scans are split
-__device__ int mpr_penetration(const CObj& o1, const CObj& o2, float tol, int max_iter, float& depth, V3& dir, V3& pos,
+__device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, float tol, int max_iter, float& depth, V3& dir, V3& pos,
                                int& iters, int lane) {
   Supp s[4], v4;
   V3 d;
@@ -501,7 +501,7 @@ __device__ __forceinline__ void write_contact(float* s, int idx, const RawCon& r
 }
 
 // Fills U_CON / MI_NCON from S_GPOS / S_GMAT.  Counters: mpr calls / support iterations.
-__device__ void collide(float* s, const DevModel& m, int lane, unsigned& mpr_calls, unsigned& mpr_iters) {
+__device__ __noinline__ void collide(float* s, const DevModel& m, int lane, unsigned& mpr_calls, unsigned& mpr_iters) {
   int ncon = 0, nq = 0;
   bool overflow = false;
   int* mprq = (int*)(s + U_MPRQ);

@@ -8,7 +8,7 @@
 #include "dev_math.cuh"
 
 // ---------------------------------------------------------------------------------------------- position stage
-__device__ void pos_stage(float* s, const DevModel& m, int lane) {
+__device__ __noinline__ void pos_stage(float* s, const DevModel& m, int lane) {
   const float* q = s + S_QPOS;
   const int nbody = m.nbody;
   // origin
@@ -142,7 +142,7 @@ __device__ void pos_stage(float* s, const DevModel& m, int lane) {
 
 // ---------------------------------------------------------------------------------------------- velocity stage
 // cvel / cdof_dot, then bias forces by recursive Newton-Euler.  Needs U_CINERT from pos_stage (same substep).
-__device__ void vel_stage(float* s, const DevModel& m, int lane) {
+__device__ __noinline__ void vel_stage(float* s, const DevModel& m, int lane) {
   const float* qv = s + S_QVEL;
   const int b = lane;
   const int lvl = b < m.nbody ? m.body_level[b] : -1;
@@ -212,7 +212,7 @@ __device__ __forceinline__ float apply_ft(const float* s, const DevModel& m, int
 // ---------------------------------------------------------------------------------------------- Euler
 // mj_Euler with implicit joint damping: (M + h diag(damping)) qacc' = qfrc_smooth + qfrc_constraint.
 // Returns false on a failed factorisation.
-__device__ bool euler_step(float* s, const DevModel& m, int lane, unsigned long long* chol_calls) {
+__device__ __noinline__ bool euler_step(float* s, const DevModel& m, int lane, unsigned long long* chol_calls) {
   const float h = m.timestep;
 #pragma unroll 4
   for (int j = 0; j < 32; j++) s[S_H + lane * 33 + j] = s[S_M + lane * 33 + j];
@@ -220,7 +220,7 @@ __device__ bool euler_step(float* s, const DevModel& m, int lane, unsigned long 
   __syncwarp();
   float qa;
   const float rhs = lane < m.nv ? s[S_SMOOTH + lane] + s[S_FCON + lane] : 0.f;
-  const bool ok = warp_chol_solve(s + S_H, rhs, &qa, lane);
+  const bool ok = warp_chol_solve(s + S_H, rhs, &qa, lane, s + S_COL);
   (void)chol_calls;
   __syncwarp();
   if (lane < m.nv) s[S_QVEL + lane] += h * qa;

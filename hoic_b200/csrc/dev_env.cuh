@@ -25,7 +25,7 @@ __device__ __forceinline__ const float* expert_frame(const EnvCtx& e, int delta)
 }
 
 // ---- stable PD with the previous forward's M and bias.  Writes S_CTRL.
-__device__ bool pd_torque(float* s, const DevModel& m, int lane, const EnvCtx& e) {
+__device__ __noinline__ bool pd_torque(float* s, const DevModel& m, int lane, const EnvCtx& e) {
   const int n = m.nhand_v;
   const float dt = m.timestep;
   const float* ref = expert_frame(e, 0) + F_DOF;
@@ -51,7 +51,7 @@ __device__ bool pd_torque(float* s, const DevModel& m, int lane, const EnvCtx& e
   }
   __syncwarp();
   float acc;
-  const bool ok = warp_chol_solve(s + S_H, rhs, &acc, lane);
+  const bool ok = warp_chol_solve(s + S_H, rhs, &acc, lane, s + S_COL);
   float t = 0.f;
   if (lane < n) {
     t = -kp * err - kd * (qv + acc * dt);
@@ -63,7 +63,7 @@ __device__ bool pd_torque(float* s, const DevModel& m, int lane, const EnvCtx& e
 }
 
 // ---- record_contact: add hand-object contacts of the last forward to the per-hand-geom sums (world positions)
-__device__ void record_contacts(float* s, const DevModel& m, int lane) {
+__device__ __noinline__ void record_contacts(float* s, const DevModel& m, int lane) {
   const int ncon = ((const int*)(s + S_MISC))[MI_NCON];
   const V3 org = ld3(s + S_ORG);
   for (int c = 0; c < ncon; c++) {
@@ -82,7 +82,7 @@ __device__ void record_contacts(float* s, const DevModel& m, int lane) {
 }
 
 // pytorch3d-style matrix -> axis-angle (uhc/utils/transforms.py:99-158, 414-490)
-__device__ V3 matrix_to_axis_angle(const M3& R) {
+__device__ __noinline__ V3 matrix_to_axis_angle(const M3& R) {
   const float* r = R.m;
   float qa[4] = {1 + r[0] + r[4] + r[8], 1 + r[0] - r[4] - r[8], 1 - r[0] + r[4] - r[8], 1 - r[0] - r[4] + r[8]};
   float cand[4][4] = {{0, r[7] - r[5], r[2] - r[6], r[3] - r[1]}, {r[7] - r[5], 0, r[3] + r[1], r[2] + r[6]},
@@ -109,7 +109,7 @@ __device__ V3 matrix_to_axis_angle(const M3& R) {
 #define QP_END (QP_GV + H_NHG * 6)
 
 struct QpVar { double g[6]; };
-__device__ __forceinline__ void qp_var(const float* s, int i, int ec, V3 obj_p, float sqw, QpVar& out, V3* pos_out) {
+__device__ __noinline__ void qp_var(const float* s, int i, int ec, V3 obj_p, float sqw, QpVar& out, V3* pos_out) {
   const float dx = 0.0025f, mu = 0.75f;
   const int pt = i >> 2, e = i & 3, k = pt / ec, j = pt % ec;
   const float* cf = s + QP_CF + 12 * k;
@@ -147,7 +147,7 @@ __device__ __forceinline__ bool solve6(double H[6][6], const double* rhs, double
 }
 
 // returns rfc_score; fills rest[6]
-__device__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,
+__device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,
                         V3 org_now, float* rest, unsigned& qp_iters) {
   const double eps = 1e-7, w_t = 1e4, sqw = 100.0;
   const int n = 4 * ec * ncg;
@@ -259,7 +259,7 @@ __device__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_
 __device__ __forceinline__ void put_rot2(float* o, const M3& R) {
   o[0] = R.m[0]; o[1] = R.m[1]; o[2] = R.m[3]; o[3] = R.m[4]; o[4] = R.m[6]; o[5] = R.m[7];
 }
-__device__ void write_obs(const float* s, const DevModel& m, int lane, const EnvCtx& e, float* obs) {
+__device__ __noinline__ void write_obs(const float* s, const DevModel& m, int lane, const EnvCtx& e, float* obs) {
   const float* qpos = s + S_QPOS;
   const float* qvel = s + S_QVEL;
   const V3 org = ld3(s + S_ORG);
@@ -331,7 +331,7 @@ __device__ void write_obs(const float* s, const DevModel& m, int lane, const Env
 }
 
 // ---- calc_ho_diff + reward 9.  Returns body_fail; reward / info written by lane 0.
-__device__ bool diff_and_reward(const float* s, const DevModel& m, int lane, const EnvCtx& e, const float* rw, float rfc_score,
+__device__ __noinline__ bool diff_and_reward(const float* s, const DevModel& m, int lane, const EnvCtx& e, const float* rw, float rfc_score,
                                 float* reward, float* info9) {
   const float* f = expert_frame(e, 0);
   const float* qpos = s + S_QPOS;

@@ -155,62 +155,55 @@ __device__ __forceinline__ void cross_force(float* res, const float* vel, const 
 }
 
 // ---- 32x32 SPD solve, one warp.  A: shared, row stride 33, lane i owns row i; on exit the lower triangle of A
-// holds the Cholesky factor L and x[lane] the solution of A x = b.  Factorisation runs in registers (row per lane,
-// column pivots broadcast by shuffle), the back-substitution reads L^T from shared memory.  Returns false if a
-// pivot is not positive.  Rows/cols >= n must be identity (callers pad).
-__device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int lane) {
+// holds the Cholesky factor L and *xout (per lane) the solution of A x = b.  The factorisation keeps one row per
+// lane in registers; the pivot column is broadcast through a small double-buffered shared array (`col`, 2 x 36
+// floats) instead of shuffles, the forward substitution rides along as a 33rd column, and the back-substitution
+// reads L^T from shared memory.  Returns false if a pivot is not positive.  Rows/cols >= n must be identity.
+__device__ __forceinline__ float rsqrt_nr(float x) {
+  float y = rsqrtf(x);
+  return y * fmaf(-0.5f * x * y, y, 1.5f);   // one Newton step on the MUFU estimate
+}
+__device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int lane, float* col) {
   float h[32];
 #pragma unroll
   for (int j = 0; j < 32; j++) h[j] = A[lane * 33 + j];
   bool ok = true;
+  float yb = b;
 #pragma unroll
   for (int k = 0; k < 32; k++) {
-    float dkk = __shfl_sync(FULLMASK, h[k], k);
+    float* c = col + (k & 1) * 36;
+    c[lane] = h[k];
+    if (lane == k) c[32] = yb;
+    __syncwarp();
+    const float dkk = c[k];
     ok = ok && (dkk > F_MINVAL);
-    float inv = 1.0f / sqrtf(fmaxf(dkk, F_MINVAL));
-    float lik = h[k] * inv;
+    const float inv = rsqrt_nr(fmaxf(dkk, F_MINVAL));
+    const float lik = h[k] * inv;
     h[k] = lik;
+    const float yk = c[32] * inv;
+    yb = lane == k ? yk : (lane > k ? fmaf(-lik, yk, yb) : yb);
+    const float cc = -lik * inv;
+    // trailing update of this lane's row: h[j] -= A[i][k] A[j][k] / d, pivot column read as aligned float4 broadcasts
 #pragma unroll
-    for (int j = k + 1; j < 32; j++) {
-      float ljk = __shfl_sync(FULLMASK, lik, j);
-      h[j] = fmaf(-lik, ljk, h[j]);
+    for (int g = (k + 1) / 4; g < 8; g++) {
+      const float4 c4 = *reinterpret_cast<const float4*>(c + 4 * g);
+      if (4 * g + 0 > k) h[4 * g + 0] = fmaf(cc, c4.x, h[4 * g + 0]);
+      if (4 * g + 1 > k) h[4 * g + 1] = fmaf(cc, c4.y, h[4 * g + 1]);
+      if (4 * g + 2 > k) h[4 * g + 2] = fmaf(cc, c4.z, h[4 * g + 2]);
+      if (4 * g + 3 > k) h[4 * g + 3] = fmaf(cc, c4.w, h[4 * g + 3]);
     }
   }
 #pragma unroll
   for (int j = 0; j < 32; j++) A[lane * 33 + j] = h[j];
-  // forward: L y = b (column oriented, from registers)
-  float y = b;
-#pragma unroll
-  for (int k = 0; k < 32; k++) {
-    float yk = __shfl_sync(FULLMASK, y, k) / __shfl_sync(FULLMASK, h[k], k);
-    if (lane == k) y = yk;
-    else if (lane > k) y = fmaf(-h[k], yk, y);
-  }
   __syncwarp();
-  // backward: L^T x = y; lane j needs L[k][j] -> shared row k
-  float x = y;
-#pragma unroll 4
-  for (int k = 31; k >= 0; k--) {
-    float xk = __shfl_sync(FULLMASK, x, k) / A[k * 33 + k];
-    if (lane == k) x = xk;
-    else if (lane < k) x = fmaf(-A[k * 33 + lane], xk, x);
+  // backward: L^T x = y
+  const float myinv = 1.0f / A[lane * 33 + lane];
+  float x = yb;
+#pragma unroll 8
+  for (int i = 31; i >= 0; i--) {
+    const float xi = __shfl_sync(FULLMASK, x * myinv, i);
+    x = lane == i ? xi : (lane < i ? fmaf(-A[i * 33 + lane], xi, x) : x);
   }
   *xout = x;
   return ok;
-}
-// solve with an existing factor in A (lower triangle), e.g. second right-hand side
-__device__ __noinline__ float warp_chol_resolve(const float* A, float b, int lane) {
-  float y = b;
-  for (int k = 0; k < 32; k++) {
-    float yk = __shfl_sync(FULLMASK, y, k) / A[k * 33 + k];
-    if (lane == k) y = yk;
-    else if (lane > k) y = fmaf(-A[lane * 33 + k], yk, y);
-  }
-  float x = y;
-  for (int k = 31; k >= 0; k--) {
-    float xk = __shfl_sync(FULLMASK, x, k) / A[k * 33 + k];
-    if (lane == k) x = xk;
-    else if (lane < k) x = fmaf(-A[k * 33 + lane], xk, x);
-  }
-  return x;
 }

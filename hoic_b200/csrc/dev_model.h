@@ -96,7 +96,8 @@ struct DevModel {
 #define S_CSUM (S_H + 1056)            // 19*12 contact sums -> 240
 #define S_CCNT (S_CSUM + 240)          // 32 (as float counts)
 #define S_MISC (S_CCNT + HN)           // 16 scalars: ncon, nlim, nbasis, nedge, flags, ...
-#define S_UNION (S_MISC + 16)
+#define S_COL (S_MISC + 16)            // 2 x 36: pivot-column broadcast buffer of warp_chol_solve
+#define S_UNION (S_COL + 72)
 // position / velocity stage temporaries
 #define U_XMAT (S_UNION)               // 32*9
 #define U_XAXIS (U_XMAT + 288)         // 32*3 per joint

@@ -33,7 +33,7 @@ __device__ __forceinline__ void kb_from_solref(const float* sr, const float* si,
 }
 
 // Builds all rows from the contacts in U_CON and the current qpos / qvel.  Sets MI_NLIM / MI_NBASIS / MI_NEDGE.
-__device__ void build_rows(float* s, const DevModel& m, int lane) {
+__device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
   int* misc = (int*)(s + S_MISC);
   int* rinfo = (int*)(s + U_RINFO);
   int* binfo = (int*)(s + U_BINFO);
@@ -158,7 +158,7 @@ __device__ void build_rows(float* s, const DevModel& m, int lane) {
 
 // ---- row-wise products ----------------------------------------------------------------------------------------
 // out[r] = (J v)[r] for all rows; v in shared (32 floats).  Uses U_BV as scratch.
-__device__ void mul_J(float* s, int lane, int nbasis, int nedge, const float* v, float* out) {
+__device__ __noinline__ void mul_J(float* s, int lane, int nbasis, int nedge, const float* v, float* out) {
   const int* rinfo = (const int*)(s + U_RINFO);
   for (int a = lane; a < nbasis; a += 32) {
     const float* B = s + U_B + a * 33;
@@ -204,7 +204,7 @@ __device__ __forceinline__ void row_eval(const float* s, const DevModel& m, int 
 }
 
 // constraint cost at jar (shared array), optionally writing forces; all lanes get the total
-__device__ float rows_update(float* s, const DevModel& m, int lane, int nedge, const float* jar, bool write) {
+__device__ __noinline__ float rows_update(float* s, const DevModel& m, int lane, int nedge, const float* jar, bool write) {
   float cost = 0.f;
   const int nrow = H_RCON + nedge;
   for (int r = lane; r < nrow; r += 32) {
@@ -227,12 +227,12 @@ __device__ __forceinline__ float mul_M(const float* s, int lane, const float* v)
   return acc;
 }
 
-// gradient and Newton direction.  grad = Ma - qfrc_smooth - J^T f ; H = M + J^T D_active J ; search = -H^-1 grad
-__device__ bool newton_direction(float* s, const DevModel& m, int lane, int nlim, int ncon, int nbasis, int nedge) {
+// gradient: grad = Ma - qfrc_smooth - J^T f (forces from the last rows_update).  Writes S_GRAD and S_FCON = J^T f,
+// and the per-basis-row force coefficients in U_BV.  Returns |grad|^2 (all lanes).
+__device__ __noinline__ float newton_gradient(float* s, const DevModel& m, int lane, int nlim, int nbasis) {
   const int* rinfo = (const int*)(s + U_RINFO);
   const int* binfo = (const int*)(s + U_BINFO);
-  const float* jar = s + U_JAR;
-  // per-basis-row force coefficients g_a and per-contact Hessian weights
+  (void)m;
   for (int a = lane; a < nbasis; a += 32) {
     const int c = binfo[a] & 255, k = binfo[a] >> 8;
     const float* ci = s + U_CINFO + 8 * c;
@@ -242,12 +242,32 @@ __device__ bool newton_direction(float* s, const DevModel& m, int lane, int nlim
     else { const float mu = k <= 2 ? ci[4] : ci[5]; g = mu * (s[U_FORCE + eo + 2 * (k - 1)] - s[U_FORCE + eo + 2 * (k - 1) + 1]); }
     s[U_BV + a] = g;
   }
+  __syncwarp();
+  float jtf = s[U_FORCE + H_RFR + lane];
+  for (int r = 0; r < nlim; r++) {
+    const int ri = rinfo[H_RLIM + r];
+    if ((ri & 255) == lane) jtf += ((ri >> 8) & 1 ? 1.f : -1.f) * s[U_FORCE + H_RLIM + r];
+  }
+#pragma unroll 4
+  for (int a = 0; a < nbasis; a++) jtf = fmaf(s[U_B + a * 33 + lane], s[U_BV + a], jtf);
+  const float grad = s[S_MA + lane] - s[S_SMOOTH + lane] - jtf;
+  s[S_GRAD + lane] = grad;
+  s[S_FCON + lane] = jtf;
+  __syncwarp();
+  return wsum(grad * grad);
+}
+
+// Newton direction: H = M + J^T D_active J (row `lane` in registers), Cholesky, search = -H^-1 grad
+__device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int lane, int nlim, int ncon, int nbasis, int nedge) {
+  const int* rinfo = (const int*)(s + U_RINFO);
+  const float* jar = s + U_JAR;
+  (void)nbasis; (void)nedge;
   for (int c = lane; c < ncon; c += 32) {
-    // weights: w[0] = C00, w[1..3] = C0k, w[4..6] = Ckk  (stored in the contact record's free slots + CW)
+    // per-contact Hessian weights: w[0] = C00, w[1..3] = C0k, w[4..6] = Ckk (contact record slots 0..6 are free now)
     float* ci = s + U_CINFO + 8 * c;
     const int eo = H_RCON + ((const int*)ci)[2], ne = ((const int*)ci)[3];
     const float D = ci[6];
-    float* w = s + U_CON + 16 * c;   // pos/frame no longer needed once the rows exist: reuse slots 0..6
+    float* w = s + U_CON + 16 * c;
     float c00 = 0.f, c0k[3] = {0, 0, 0}, ckk[3] = {0, 0, 0};
     for (int e = 0; e < ne; e++) {
       const float act = jar[eo + e] < 0.f ? D : 0.f;
@@ -262,17 +282,6 @@ __device__ bool newton_direction(float* s, const DevModel& m, int lane, int nlim
     w[0] = c00; w[1] = c0k[0]; w[2] = c0k[1]; w[3] = c0k[2]; w[4] = ckk[0]; w[5] = ckk[1]; w[6] = ckk[2];
   }
   __syncwarp();
-  // gradient
-  float jtf = s[U_FORCE + H_RFR + lane];
-  for (int r = 0; r < nlim; r++) {
-    const int ri = rinfo[H_RLIM + r];
-    if ((ri & 255) == lane) jtf += ((ri >> 8) & 1 ? 1.f : -1.f) * s[U_FORCE + H_RLIM + r];
-  }
-  for (int a = 0; a < nbasis; a++) jtf = fmaf(s[U_B + a * 33 + lane], s[U_BV + a], jtf);
-  const float grad = s[S_MA + lane] - s[S_SMOOTH + lane] - jtf;
-  s[S_GRAD + lane] = grad;
-  s[S_FCON + lane] = jtf;
-  // Hessian row `lane`
   float h[32];
 #pragma unroll
   for (int j = 0; j < 32; j++) h[j] = s[S_M + lane * 33 + j];
@@ -323,14 +332,14 @@ __device__ bool newton_direction(float* s, const DevModel& m, int lane, int nlim
   s[S_H + lane * 33 + lane] += diag;
   __syncwarp();
   float dir;
-  const bool ok = warp_chol_solve(s + S_H, -grad, &dir, lane);
+  const bool ok = warp_chol_solve(s + S_H, -s[S_GRAD + lane], &dir, lane, s + S_COL);
   s[S_SEARCH + lane] = dir;
   __syncwarp();
   return ok;
 }
 
 // derivative and curvature of the total cost along the search direction at step alpha
-__device__ __forceinline__ void ls_eval(const float* s, const DevModel& m, int lane, int nedge, float alpha, float qg1,
+__device__ __noinline__ void ls_eval(const float* s, const DevModel& m, int lane, int nedge, float alpha, float qg1,
                                         float qg2, float& d1, float& d2) {
   float a1 = 0.f, a2 = 0.f;
   const int nrow = H_RCON + nedge;
@@ -346,7 +355,7 @@ __device__ __forceinline__ void ls_eval(const float* s, const DevModel& m, int l
 }
 
 // exact minimiser of the piecewise-quadratic cost along `search` by safeguarded Newton on its derivative
-__device__ float line_search(float* s, const DevModel& m, int lane, int nbasis, int nedge, unsigned& evals) {
+__device__ __noinline__ float line_search(float* s, const DevModel& m, int lane, int nbasis, int nedge, unsigned& evals) {
   const float sv = s[S_SEARCH + lane];
   const float mv = mul_M(s, lane, s + S_SEARCH);
   s[S_MV + lane] = mv;
@@ -379,7 +388,7 @@ __device__ float line_search(float* s, const DevModel& m, int lane, int nbasis, 
 }
 
 // mj_fwdConstraint with the Newton solver.  Inputs: S_SMOOTH, S_ASMOOTH, S_WARM, rows.  Outputs: S_QACC, S_FCON.
-__device__ bool solve_newton(float* s, const DevModel& m, int lane, unsigned& iters_out, unsigned& ls_evals) {
+__device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane, unsigned& iters_out, unsigned& ls_evals) {
   const int* misc = (const int*)(s + S_MISC);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON], nbasis = misc[MI_NBASIS], nedge = misc[MI_NEDGE];
   const float scale = 1.0f / (m.meaninertia * (float)(m.nv > 1 ? m.nv : 1));
@@ -407,27 +416,45 @@ __device__ bool solve_newton(float* s, const DevModel& m, int lane, unsigned& it
   s[S_MA + lane] = ma;
   __syncwarp();
   float cost = rows_update(s, m, lane, nedge, s + U_JAR, true) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
-  bool ok = newton_direction(s, m, lane, nlim, ncon, nbasis, nedge);
+  bool ok = true;
   unsigned iter = 0;
-  while (ok && iter < (unsigned)m.iterations) {
+  float oldcost = cost;
+  for (;;) {
+    const float g2 = newton_gradient(s, m, lane, nlim, nbasis);
+    if (iter > 0) {
+      const float improvement = scale * (oldcost - cost), gradn = scale * sqrtf(g2);
+      // float32 noise floor on the cost difference replaces MuJoCo's absolute 1e-8 (see DESIGN.md "precision")
+      const float tol = fmaxf(m.tolerance, 2e-7f * scale * fabsf(cost));
+      if (improvement < tol || gradn < m.tolerance) break;
+    }
+    if (iter >= (unsigned)m.iterations) break;
+    ok = newton_direction(s, m, lane, nlim, ncon, nbasis, nedge);
+    if (!ok) break;
     const float alpha = line_search(s, m, lane, nbasis, nedge, ls_evals);
     if (alpha == 0.f) break;
     qacc += alpha * s[S_SEARCH + lane];
     ma += alpha * s[S_MV + lane];
     s[S_QACC + lane] = qacc;
     s[S_MA + lane] = ma;
-    for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JAR + r] += alpha * s[U_JV + r];
+    // move along the search direction; note whether any row changed state (active set / friction branch)
+    bool changed = false;
+    for (int r = lane; r < H_RCON + nedge; r += 32) {
+      const float x0 = s[U_JAR + r], x1 = x0 + alpha * s[U_JV + r];
+      s[U_JAR + r] = x1;
+      if (r < H_RLIM) { const float Rf = m.fr_Rf[r]; changed |= ((x0 <= -Rf) != (x1 <= -Rf)) || ((x0 >= Rf) != (x1 >= Rf)); }
+      else changed |= (x0 < 0.f) != (x1 < 0.f);
+    }
+    changed = __any_sync(FULLMASK, changed);
     __syncwarp();
-    const float oldcost = cost;
+    oldcost = cost;
     cost = rows_update(s, m, lane, nedge, s + U_JAR, true) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
-    ok = newton_direction(s, m, lane, nlim, ncon, nbasis, nedge);
-    const float g = s[S_GRAD + lane];
-    const float gradn = scale * sqrtf(wsum(g * g));
-    const float improvement = scale * (oldcost - cost);
     iter++;
-    // float32 noise floor on the cost difference replaces MuJoCo's absolute 1e-8 (see DESIGN.md "precision")
-    const float tol = fmaxf(m.tolerance, 2e-7f * scale * fabsf(cost));
-    if (improvement < tol || gradn < m.tolerance) break;
+    if (!changed) {
+      // no row changed state along the step: the cost was exactly quadratic there and the Newton step with the exact
+      // line search landed on its minimiser, which is the optimum of the convex problem.  Refresh J^T f and stop.
+      newton_gradient(s, m, lane, nlim, nbasis);
+      break;
+    }
   }
   iters_out += iter;
   // S_FCON holds J^T f of the final forces (written by newton_direction)

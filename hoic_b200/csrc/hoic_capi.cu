@@ -40,34 +40,35 @@ struct Cnt { unsigned substeps, ncon, nefc, newton, ls, mpr_calls, mpr_iters, qp
 
 __device__ __forceinline__ bool bad(float v) { return !(fabsf(v) <= F_MAXVAL); }
 
-// forward dynamics of the state in S_QPOS/S_QVEL with S_CTRL/S_QAPP/S_WARM, then Euler.  `record`: add the contacts
-// of this forward to the contact sums (they are what record_contact sees before the NEXT sim.step()).
-__device__ bool substep_core(float* s, const DevModel& m, int lane, bool record, Cnt& cnt, bool integrate = true) {
+// Phases of one substep.  Kept as separate noinline calls so that every warp of a CTA runs the same (large) piece of
+// code between two CTA barriers: the step kernel is instruction-fetch bound otherwise (profiles/r01_v1_*).
+__device__ __noinline__ bool phase_forward(float* s, const DevModel& m, int lane) {
   int* misc = (int*)(s + S_MISC);
-  bool fail = __any_sync(FULLMASK, bad(s[S_QPOS + lane]) || bad(s[S_QVEL + lane]) || (lane == 0 && bad(s[S_QPOS + 32])));
+  const bool fail = __any_sync(FULLMASK, bad(s[S_QPOS + lane]) || bad(s[S_QVEL + lane]) || (lane == 0 && bad(s[S_QPOS + 32])));
   if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   pos_stage(s, m, lane);
   vel_stage(s, m, lane);
-  collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
-  if (record) record_contacts(s, m, lane);
-  build_rows(s, m, lane);
-  // smooth dynamics
-  {
-    const bool on = lane < m.nv;
-    const float passive = on ? -m.dof_damping[lane] * s[S_QVEL + lane] : 0.f;
-    const float act = lane < m.nu ? s[S_CTRL + lane] : 0.f;   // motors on dofs 0..nu-1, gear 1
-    const float fs = on ? passive - s[S_BIAS + lane] + s[S_QAPP + lane] + act : 0.f;
-    s[S_SMOOTH + lane] = fs;
+  return true;
+}
+__device__ __noinline__ bool phase_smooth(float* s, const DevModel& m, int lane) {
+  const bool on = lane < m.nv;
+  const float passive = on ? -m.dof_damping[lane] * s[S_QVEL + lane] : 0.f;
+  const float act = lane < m.nu ? s[S_CTRL + lane] : 0.f;   // motors on dofs 0..nu-1, gear 1
+  const float fs = on ? passive - s[S_BIAS + lane] + s[S_QAPP + lane] + act : 0.f;
+  s[S_SMOOTH + lane] = fs;
 #pragma unroll 4
-    for (int j = 0; j < 32; j++) s[S_H + lane * 33 + j] = s[S_M + lane * 33 + j];
-    __syncwarp();
-    float as;
-    if (!warp_chol_solve(s + S_H, fs, &as, lane)) fail = true;
-    s[S_ASMOOTH + lane] = as;
-    __syncwarp();
-  }
+  for (int j = 0; j < 32; j++) s[S_H + lane * 33 + j] = s[S_M + lane * 33 + j];
+  __syncwarp();
+  float as;
+  const bool ok = warp_chol_solve(s + S_H, fs, &as, lane, s + S_COL);
+  s[S_ASMOOTH + lane] = as;
+  __syncwarp();
+  return ok;
+}
+__device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int lane, Cnt& cnt) {
+  int* misc = (int*)(s + S_MISC);
   unsigned it = 0;
-  if (!solve_newton(s, m, lane, it, cnt.ls)) fail = true;
+  bool fail = !solve_newton(s, m, lane, it, cnt.ls);
   cnt.newton += it;
   cnt.substeps++;
   cnt.ncon += misc[MI_NCON];
@@ -75,8 +76,19 @@ __device__ bool substep_core(float* s, const DevModel& m, int lane, bool record,
   if (lane == 0) misc[MI_ITER] = (int)it;
   fail = __any_sync(FULLMASK, fail || bad(s[S_QACC + lane]));
   if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
-  if (misc[MI_FLAGS] & 2) return false;   // capacity overflow: treated like MuJoCo's nconmax / njmax warnings
-  if (integrate && !euler_step(s, m, lane, nullptr)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
+  return !(misc[MI_FLAGS] & 2);   // capacity overflow: treated like MuJoCo's nconmax / njmax warnings
+}
+
+// forward dynamics of the state in S_QPOS/S_QVEL with S_CTRL/S_QAPP/S_WARM, then Euler (single-warp callers)
+__device__ bool substep_core(float* s, const DevModel& m, int lane, bool record, Cnt& cnt) {
+  int* misc = (int*)(s + S_MISC);
+  if (!phase_forward(s, m, lane)) return false;
+  collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
+  if (record) record_contacts(s, m, lane);
+  build_rows(s, m, lane);
+  if (!phase_smooth(s, m, lane)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
+  if (!phase_solve(s, m, lane, cnt)) return false;
+  if (!euler_step(s, m, lane, nullptr)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   return true;
 }
 
@@ -112,140 +124,174 @@ __device__ __forceinline__ EnvCtx make_ctx(const BatchDev& B, const int* ints) {
   return e;
 }
 
+// ---- tail of env.step after the substeps: averages, contact classification, residual-force QP (ho_im4.py:553-565, 631)
+__device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, const float* og, float old_obj_vel, V3 vf, V3 vt,
+                                        float* rest, int& ncg_out, unsigned& qp_iters) {
+  float rfc_score = 0.f;
+  const int nhg = m.hand_geom1 - m.hand_geom0 + 1;
+  const float inv_dt = 1.0f / (m.sim_step * m.timestep);
+  const V3 org = ld3(s + S_ORG), oorg = ld3(og + HN * 12);
+  const float acc = (s[S_QVEL + lane] - old_obj_vel) * inv_dt;   // lanes nv-6..nv-1: obj_avg_acc
+  const V3 obj_a = v3(__shfl_sync(FULLMASK, acc, m.nv - 6), __shfl_sync(FULLMASK, acc, m.nv - 5), __shfl_sync(FULLMASK, acc, m.nv - 4));
+  const V3 obj_oa = v3(__shfl_sync(FULLMASK, acc, m.nv - 3), __shfl_sync(FULLMASK, acc, m.nv - 2), __shfl_sync(FULLMASK, acc, m.nv - 1));
+  // classify_contact: lane = hand geom slot
+  const bool has = lane < nhg && s[S_CCNT + lane] > 0.f;
+  float fr[12];
+  if (has) {
+    const float ic = 1.0f / s[S_CCNT + lane];
+    for (int k = 0; k < 12; k++) fr[k] = s[S_CSUM + 12 * lane + k] * ic;
+    V3 n = ld3(fr + 3);
+    n = n * (1.0f / norm(n));
+    V3 t = fabsf(n.x) >= 1e-5f ? cross(n, v3(1.f, 0.f, 0.f)) : cross(n, v3(0.f, 1.f, 0.f));
+    t = t * (1.0f / norm(t));
+    V3 b = cross(n, t);
+    b = b * (1.0f / norm(b));
+    st3(fr + 3, n); st3(fr + 6, t); st3(fr + 9, b);
+  }
+  const float ts = has ? s[S_CCNT + lane] / (float)m.sim_step : 0.f;
+  const unsigned bal = __ballot_sync(FULLMASK, has);
+  const int ncg = __popc(bal);
+  ncg_out = ncg;
+  __syncwarp();
+  // geom average velocities: contact geoms (lane = slot) and the last geom (object visual mesh)
+  auto geom_vel = [&](int g, V3& lin, V3& ang) {
+    const V3 pn = ld3(s + S_GPOS + 3 * g), po = ld3(og + 3 * g);
+    lin = ((pn - po) + (org - oorg)) * inv_dt;
+    const M3 Rd = mulmT(ldm(s + S_GMAT + 9 * g), ldm(og + HN * 3 + 9 * g));
+    ang = matrix_to_axis_angle(Rd) * inv_dt;
+  };
+  V3 obj_v, obj_w;
+  geom_vel(m.last_geom, obj_v, obj_w);
+  if (has) {
+    const int idx = __popc(bal & ((1u << lane) - 1u));
+    for (int k = 0; k < 12; k++) s[QP_CF + 12 * idx + k] = fr[k];
+    s[QP_TS + idx] = ts;
+    ((int*)(s + QP_G1))[idx] = m.hand_geom0 + lane;
+    V3 gl, ga;
+    geom_vel(m.hand_geom0 + lane, gl, ga);
+    st3(s + QP_GV + 6 * idx, gl); st3(s + QP_GV + 6 * idx + 3, ga);
+  }
+  __syncwarp();
+  if (m.residual_force) {
+    if (!m.explain_force) {
+      rfc_score = norm(vf) + 1e4f * norm(vt);
+    } else {
+      const V3 obj_p = ld3(s + S_QPOS + m.nhand_q);
+      const M3 R = q2m(qnormalize(ldq(s + S_QPOS + m.nhand_q + 3)));
+      M3 RI;
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) RI.m[3 * i + j] = R.m[3 * i + j] * m.obj_inertia[j];
+      const M3 I = mulmT(RI, R);
+      const V3 F = (obj_a + v3(0.f, 0.f, 9.8f)) * m.obj_mass;
+      const V3 T = mulv(I, obj_oa) + cross(obj_w, mulv(I, obj_w));
+      if (ncg == 0) {
+        rfc_score = norm(F) + 1e4f * norm(T);
+        rest[0] = F.x; rest[1] = F.y; rest[2] = F.z; rest[3] = T.x; rest[4] = T.y; rest[5] = T.z;
+      } else {
+        rfc_score = rfc_qp(s, lane, ncg, m.surface_contact ? 5 : 1, F, T, obj_p, obj_v, obj_w, s + S_GPOS, org, rest, qp_iters);
+      }
+    }
+  }
+  return rfc_score;
+}
+
 // ------------------------------------------------------------------------------------------------ step kernel
-__global__ void __launch_bounds__(32) k_step(BatchDev B, const float* __restrict__ actions, StepOut out) {
-  extern __shared__ float s[];
-  const int env = blockIdx.x, lane = threadIdx.x;
-  if (env >= B.n_envs) return;
-  const DevModel& m = *B.env_model[env];
-  float* st = B.state + (size_t)env * ST_STRIDE;
+// H_WPB warps (= environments) per CTA.  The substep loop runs sim_step+1 times: pass -1 recomputes the forward of the
+// state that preceded the step (the "stale" quantities the env logic reads) with the same code as the
+// real substeps.  CTA barriers keep the warps of a CTA inside the same code region (instruction-cache locality).
+#define H_WPB 7
+__global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __restrict__ actions, StepOut out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * H_WPB + warp;
+  float* s = smem + (size_t)warp * S_TOTAL;
+  const bool live = env < B.n_envs;
+  const int envc = live ? env : B.n_envs - 1;
+  const DevModel& m = *B.env_model[envc];
+  float* st = B.state + (size_t)envc * ST_STRIDE;
   int* ints = (int*)(st + ST_INTS);
   int* misc = (int*)(s + S_MISC);
   Cnt cnt;
   memset(&cnt, 0, sizeof cnt);
   if (lane < 16) misc[lane] = 0;
   EnvCtx ctx = make_ctx(B, ints);
-  // action: clip, residual wrench
   {
-    float a = lane < m.nu + (m.residual_force ? 6 : 0) ? actions[(size_t)env * HOIC_ACT_DIM + lane] : 0.f;
+    float a = lane < m.nu + (m.residual_force ? 6 : 0) ? actions[(size_t)envc * HOIC_ACT_DIM + lane] : 0.f;
     s[S_ACT + lane] = fminf(fmaxf(a, -1.f), 1.f);
   }
   // current state in registers while the previous forward is recomputed
   const float cq = st[ST_QPOS + lane], cq32 = st[ST_QPOS + 32], cv = st[ST_QVEL + lane], cw = st[ST_WARM + lane];
   load_state(s, st, lane, ST_PQPOS, ST_PQVEL);
-  s[S_CSUM + lane] = 0.f;
   for (int i = lane; i < 240; i += 32) s[S_CSUM + i] = 0.f;
   s[S_CCNT + lane] = 0.f;
   __syncwarp();
-  pos_stage(s, m, lane);
-  vel_stage(s, m, lane);
-  collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
-  record_contacts(s, m, lane);
-  // snapshot of geom poses for the averaged velocities (ho_im4.py:508-511)
-  {
-    float* og = B.old_geom + (size_t)env * (HN * 12 + 4);
-    for (int i = lane; i < m.ngeom * 3; i += 32) og[i] = s[S_GPOS + i];
-    for (int i = lane; i < m.ngeom * 9; i += 32) og[HN * 3 + i] = s[S_GMAT + i];
-    if (lane < 3) og[HN * 12 + lane] = s[S_ORG + lane];
-  }
   const float old_obj_vel = (lane >= m.nv - 6 && lane < m.nv) ? cv : 0.f;
-  // restore the current state
-  s[S_QPOS + lane] = cq;
-  if (lane == 0) s[S_QPOS + 32] = cq32;
-  s[S_QVEL + lane] = cv;
-  s[S_WARM + lane] = cw;
-  if (lane == 0) misc[MI_FLAGS] = 0;   // a capacity overflow in the stale forward was already reported last step
-  __syncwarp();
-  const V3 vf = m.residual_force ? ld3(s + S_ACT + m.nu) * m.rf_scale : v3(0, 0, 0);
-  const V3 vt = m.residual_force ? ld3(s + S_ACT + m.nu + 3) * m.rt_scale : v3(0, 0, 0);
+  float* og = B.old_geom + (size_t)envc * (HN * 12 + 4);
+  V3 vf = v3(0, 0, 0), vt = v3(0, 0, 0);
   float pq = cq, pq32 = cq32, pv = cv;
-  bool fail = false;
-  for (int k = 0; k < m.sim_step; k++) {
-    if (!pd_torque(s, m, lane, ctx)) { fail = true; break; }
-    {
+  bool ok = live;      // false once this env failed (or the slot is padding): skips work, keeps hitting the barriers
+  const int nsub = m.sim_step;
+  for (int k = -1; k < nsub; k++) {
+    __syncthreads();
+    if (ok && k >= 0) {
+      if (k == 0) {
+        vf = m.residual_force ? ld3(s + S_ACT + m.nu) * m.rf_scale : v3(0, 0, 0);
+        vt = m.residual_force ? ld3(s + S_ACT + m.nu + 3) * m.rt_scale : v3(0, 0, 0);
+      }
+      ok = pd_torque(s, m, lane, ctx);
       // J^T wrenches with the previous forward's Jacobians (stale cdof / com / geom_xpos)
       const V3 org = ld3(s + S_ORG);
       float qf = apply_ft(s, m, lane, v3(0.f, 0.f, m.hand_mass * 9.8f), v3(0, 0, 0), ld3(s + S_GPOS + 3 * m.hand_geom0), m.palm_body);
       if (m.residual_force) qf += apply_ft(s, m, lane, vf, vt, ld3(s + S_QPOS + m.nhand_q) - org, m.obj_body);
       __syncwarp();
       s[S_QAPP + lane] = qf;
+      pq = s[S_QPOS + lane]; pq32 = s[S_QPOS + 32]; pv = s[S_QVEL + lane];
+      __syncwarp();
+      if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
     }
-    pq = s[S_QPOS + lane]; pq32 = s[S_QPOS + 32]; pv = s[S_QVEL + lane];
-    __syncwarp();
-    if (!substep_core(s, m, lane, k + 1 < m.sim_step, cnt)) { fail = true; break; }
+    if (ok) ok = phase_forward(s, m, lane) || k < 0;   // a bad stale state is reported by the previous step already
+    __syncthreads();
+    if (ok) {
+      collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
+      if (k + 1 < nsub) record_contacts(s, m, lane);
+    }
+    if (k < 0) {
+      if (ok) {
+        // snapshot of geom poses for the averaged velocities (ho_im4.py:508-511), then restore the current state
+        for (int i = lane; i < m.ngeom * 3; i += 32) og[i] = s[S_GPOS + i];
+        for (int i = lane; i < m.ngeom * 9; i += 32) og[HN * 3 + i] = s[S_GMAT + i];
+        if (lane < 3) og[HN * 12 + lane] = s[S_ORG + lane];
+        s[S_QPOS + lane] = cq;
+        if (lane == 0) { s[S_QPOS + 32] = cq32; misc[MI_FLAGS] = 0; }
+        s[S_QVEL + lane] = cv;
+        s[S_WARM + lane] = cw;
+        __syncwarp();
+      }
+      continue;
+    }
+    __syncthreads();
+    if (ok) {
+      build_rows(s, m, lane);
+      ok = phase_smooth(s, m, lane);
+      if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
+    }
+    __syncthreads();
+    if (ok) ok = phase_solve(s, m, lane, cnt);
+    __syncthreads();
+    if (ok) {
+      ok = euler_step(s, m, lane, nullptr);
+      if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
+    }
   }
+  __syncthreads();
+  if (!live) return;
+  bool fail = !ok;
   const int flags = misc[MI_FLAGS];
   if (flags & 1) cnt.fail_phys++;
   if (flags & 2) cnt.fail_over++;
-  // ---- tail: averages, contact classification, residual-force QP
   float rfc_score = 0.f, rest[6] = {0, 0, 0, 0, 0, 0};
   int ncg = 0;
-  const int nhg = m.hand_geom1 - m.hand_geom0 + 1;
-  if (!fail) {
-    const float* og = B.old_geom + (size_t)env * (HN * 12 + 4);
-    const float inv_dt = 1.0f / (m.sim_step * m.timestep);
-    const V3 org = ld3(s + S_ORG), oorg = ld3(og + HN * 12);
-    const float acc = (s[S_QVEL + lane] - old_obj_vel) * inv_dt;   // lanes nv-6..nv-1: obj_avg_acc
-    const V3 obj_a = v3(__shfl_sync(FULLMASK, acc, m.nv - 6), __shfl_sync(FULLMASK, acc, m.nv - 5), __shfl_sync(FULLMASK, acc, m.nv - 4));
-    const V3 obj_oa = v3(__shfl_sync(FULLMASK, acc, m.nv - 3), __shfl_sync(FULLMASK, acc, m.nv - 2), __shfl_sync(FULLMASK, acc, m.nv - 1));
-    // classify_contact: lane = hand geom slot
-    bool has = lane < nhg && s[S_CCNT + lane] > 0.f;
-    float fr[12];
-    if (has) {
-      const float ic = 1.0f / s[S_CCNT + lane];
-      for (int k = 0; k < 12; k++) fr[k] = s[S_CSUM + 12 * lane + k] * ic;
-      V3 n = ld3(fr + 3);
-      n = n * (1.0f / norm(n));
-      V3 t = fabsf(n.x) >= 1e-5f ? cross(n, v3(1.f, 0.f, 0.f)) : cross(n, v3(0.f, 1.f, 0.f));
-      t = t * (1.0f / norm(t));
-      V3 b = cross(n, t);
-      b = b * (1.0f / norm(b));
-      st3(fr + 3, n); st3(fr + 6, t); st3(fr + 9, b);
-    }
-    const float ts = has ? s[S_CCNT + lane] / (float)m.sim_step : 0.f;
-    const unsigned bal = __ballot_sync(FULLMASK, has);
-    ncg = __popc(bal);
-    __syncwarp();
-    // geom average velocities: contact geoms (lane = slot) and the last geom (object visual mesh)
-    auto geom_vel = [&](int g, V3& lin, V3& ang) {
-      const V3 pn = ld3(s + S_GPOS + 3 * g) , po = ld3(og + 3 * g);
-      lin = ((pn - po) + (org - oorg)) * inv_dt;
-      const M3 Rd = mulmT(ldm(s + S_GMAT + 9 * g), ldm(og + HN * 3 + 9 * g));
-      ang = matrix_to_axis_angle(Rd) * inv_dt;
-    };
-    V3 obj_v, obj_w;
-    geom_vel(m.last_geom, obj_v, obj_w);
-    if (has) {
-      const int idx = __popc(bal & ((1u << lane) - 1u));
-      for (int k = 0; k < 12; k++) s[QP_CF + 12 * idx + k] = fr[k];
-      s[QP_TS + idx] = ts;
-      ((int*)(s + QP_G1))[idx] = m.hand_geom0 + lane;
-      V3 gl, ga;
-      geom_vel(m.hand_geom0 + lane, gl, ga);
-      st3(s + QP_GV + 6 * idx, gl); st3(s + QP_GV + 6 * idx + 3, ga);
-    }
-    __syncwarp();
-    if (m.residual_force) {
-      if (!m.explain_force) {
-        rfc_score = norm(vf) + 1e4f * norm(vt);
-      } else {
-        const V3 obj_p = ld3(s + S_QPOS + m.nhand_q);
-        const M3 R = q2m(qnormalize(ldq(s + S_QPOS + m.nhand_q + 3)));
-        M3 RI;
-        for (int i = 0; i < 3; i++)
-          for (int j = 0; j < 3; j++) RI.m[3 * i + j] = R.m[3 * i + j] * m.obj_inertia[j];
-        const M3 I = mulmT(RI, R);
-        const V3 F = (obj_a + v3(0.f, 0.f, 9.8f)) * m.obj_mass;
-        const V3 T = mulv(I, obj_oa) + cross(obj_w, mulv(I, obj_w));
-        if (ncg == 0) {
-          rfc_score = norm(F) + 1e4f * norm(T);
-          rest[0] = F.x; rest[1] = F.y; rest[2] = F.z; rest[3] = T.x; rest[4] = T.y; rest[5] = T.z;
-        } else {
-          rfc_score = rfc_qp(s, lane, ncg, m.surface_contact ? 5 : 1, F, T, obj_p, obj_v, obj_w, s + S_GPOS, org, rest, cnt.qp);
-        }
-      }
-    }
-  }
+  if (!fail) rfc_score = step_tail(s, m, lane, og, old_obj_vel, vf, vt, rest, ncg, cnt.qp);
   // ---- bookkeeping, termination, reward, observation (ho_im4.py:641-662)
   ctx.cur_t += 1;
   float reward = 0.f;
@@ -264,7 +310,6 @@ __global__ void __launch_bounds__(32) k_step(BatchDev B, const float* __restrict
     for (int k = 0; k < 6; k++) st[ST_RFC + 1 + k] = rest[k];
     st[ST_RFC + 7] = (float)ncg;
   }
-  // ---- write state back
   st[ST_QPOS + lane] = s[S_QPOS + lane];
   st[ST_QVEL + lane] = s[S_QVEL + lane];
   st[ST_WARM + lane] = s[S_WARM + lane];
@@ -748,7 +793,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   b->b.reward_w = b->reward_w;
   b->b.mode_train = 1;
   b->smem_bytes = (size_t)S_TOTAL * sizeof(float);
-  CUDA_OKP(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
+  CUDA_OKP(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(b->smem_bytes * H_WPB)));
   CUDA_OKP(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
   CUDA_OKP(cudaFuncSetAttribute(k_forward_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
   CUDA_OKP(cudaFuncSetAttribute(k_substep_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
@@ -816,7 +861,7 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
   if (!b->b.frames) return set_err("hoic_step: call hoic_set_motions first");
   CUDA_OK(cudaSetDevice(b->device));
   StepOut o = {obs, reward, reward_info, done, fail, end, percent};
-  k_step<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, actions, o);
+  k_step<<<(b->n_envs + H_WPB - 1) / H_WPB, 32 * H_WPB, b->smem_bytes * H_WPB, (cudaStream_t)stream>>>(b->b, actions, o);
   LAUNCH_CHECK();
   return 0;
 }
