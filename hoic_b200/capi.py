@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhoic_b200.so")
+LIB_PATH = os.environ.get("HOIC_LIB", os.path.join(_HERE, "libhoic_b200.so"))   # HOIC_LIB: alternate build for A/B timing
 _lib = None
 
 OBS_DIM, ACT_DIM, FRAME_DIM, INFO_DIM, NQ, NV, MAX_CONTACTS = 617, 32, 212, 9, 33, 32, 32
@@ -15,7 +15,7 @@ EXPORTS = [
     "hoic_batch_destroy", "hoic_batch_size", "hoic_set_motions", "hoic_set_reward_weights", "hoic_set_mode",
     "hoic_reset", "hoic_step", "hoic_get_state", "hoic_set_state", "hoic_set_cur_t", "hoic_get_warmstart",
     "hoic_set_warmstart", "hoic_get_contacts", "hoic_substep_debug", "hoic_get_derived", "hoic_get_rfc",
-    "hoic_get_counters", "hoic_launch_count", "hoic_measure_fp32_peak",
+    "hoic_get_counters", "hoic_launch_count", "hoic_measure_fp32_peak", "hoic_get_work", "hoic_set_env_order",
 ]
 
 
@@ -65,6 +65,8 @@ def lib():
         L.hoic_get_rfc.argtypes = [vp, vp, vp]
         L.hoic_get_counters.argtypes = [vp, C.POINTER(Counters)]
         L.hoic_launch_count.restype = C.c_ulonglong
+        L.hoic_get_work.argtypes = [vp, vp, vp]
+        L.hoic_set_env_order.argtypes = [vp, vp]
         L.hoic_measure_fp32_peak.argtypes = [ip, C.POINTER(C.c_double)]
         _lib = L
     return _lib

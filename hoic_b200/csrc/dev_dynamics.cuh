@@ -8,60 +8,96 @@
 #include "dev_math.cuh"
 
 // ---------------------------------------------------------------------------------------------- position stage
+// Scratch aliases inside the union (dead before the constraint stage): per-joint local rotation / slide and per-body
+// local transform are computed lane-parallel first, so that the serial walk down the tree is one quaternion product
+// and one rotation per level.
+#define U_JQ (U_CVEL)          // 32*4: hinge rotation quaternion of each joint (slide: displacement in .w)
+#define U_DV (U_CVEL)          // 32*6: cdof * qvel            (velocity stage; U_JQ is dead by then)
+#define U_DA (U_CACC)          // 32*6: cdof_dot * qvel
 __device__ __noinline__ void pos_stage(float* s, const DevModel& m, int lane) {
   const float* q = s + S_QPOS;
   const int nbody = m.nbody;
-  // origin
   if (lane < 3) s[S_ORG + lane] = q[m.org_qadr + lane];
+  // (1) lane = joint: local joint motion
+  if (lane < m.njnt) {
+    const int t = m.jnt_type[lane];
+    const float qq = t == J_FREE ? 0.f : q[m.jnt_qposadr[lane]] - m.qpos0[m.jnt_qposadr[lane]];
+    Q4 dq = q4(qq, 0.f, 0.f, 0.f);
+    if (t == J_HINGE) dq = aa2q(ld3(m.jnt_axis[lane]), qq);
+    stq(s + U_JQ + 4 * lane, dq);
+  }
   __syncwarp();
   const V3 org = ld3(s + S_ORG);
+  // (2) lane = body: transform of the body relative to its parent's frame, joint axes / anchors in the parent frame
+  const int b = lane;
+  const int lvl = b < nbody ? m.body_level[b] : -1;
+  V3 lp = v3(0, 0, 0);
+  Q4 lq = q4(1.f, 0.f, 0.f, 0.f);
+  bool isfree = false;
+  if (b > 0 && b < nbody) {
+    const int ja = m.body_jntadr[b], jn = m.body_jntnum[b];
+    isfree = jn == 1 && m.jnt_type[ja] == J_FREE;
+    if (!isfree) {
+      lp = ld3(m.body_pos[b]);
+      lq = ldq(m.body_quat[b]);
+      for (int j = ja; j < ja + jn; j++) {
+        const M3 R = q2m(lq);
+        const V3 ax = mulv(R, ld3(m.jnt_axis[j]));
+        const V3 jp = ld3(m.jnt_pos[j]);
+        const V3 anchor = lp + mulv(R, jp);
+        st3(s + U_XAXIS + 3 * j, ax);
+        st3(s + U_XANCH + 3 * j, anchor);
+        const Q4 dq = ldq(s + U_JQ + 4 * j);
+        if (m.jnt_type[j] == J_SLIDE) {
+          lp = lp + ax * dq.w;
+        } else {
+          lq = qmul(lq, dq);
+          lp = anchor - rotq(lq, jp);
+        }
+      }
+    }
+  }
   if (lane == 0) {
     st3(s + S_XPOS, -org);
     stq(s + S_XQUAT, q4(1.f, 0.f, 0.f, 0.f));
-    M3 I = q2m(q4(1.f, 0.f, 0.f, 0.f));
-    stm(s + U_XMAT, I);
+    stm(s + U_XMAT, q2m(q4(1.f, 0.f, 0.f, 0.f)));
   }
   __syncwarp();
-  const int b = lane;
-  const int lvl = b < nbody ? m.body_level[b] : -1;
+  // (3) walk down the tree, one level at a time
   for (int L = 1; L <= m.nlevel; L++) {
     if (lvl == L) {
-      const int p = m.body_parent[b], ja = m.body_jntadr[b], jn = m.body_jntnum[b];
       V3 pos;
       Q4 quat;
-      if (jn == 1 && m.jnt_type[ja] == J_FREE) {
-        const int a = m.jnt_qposadr[ja];
+      if (isfree) {
+        const int a = m.jnt_qposadr[m.body_jntadr[b]];
         pos = ld3(q + a) - org;
         quat = qnormalize(ldq(q + a + 3));
         stq(s + S_QPOS + a + 3, quat);  // mj_kinematics normalises qpos in place
-        st3(s + U_XANCH + 3 * ja, pos);
-        st3(s + U_XAXIS + 3 * ja, ld3(m.jnt_axis[ja]));
       } else {
-        const M3 Rp = ldm(s + U_XMAT + 9 * p);
-        pos = ld3(s + S_XPOS + 3 * p) + mulv(Rp, ld3(m.body_pos[b]));
-        quat = qmul(ldq(s + S_XQUAT + 4 * p), ldq(m.body_quat[b]));
-        for (int j = ja; j < ja + jn; j++) {
-          const M3 R = q2m(quat);
-          const V3 ax = mulv(R, ld3(m.jnt_axis[j]));
-          const V3 jp = ld3(m.jnt_pos[j]);
-          const V3 anchor = pos + mulv(R, jp);
-          st3(s + U_XAXIS + 3 * j, ax);
-          st3(s + U_XANCH + 3 * j, anchor);
-          const float qq = q[m.jnt_qposadr[j]] - m.qpos0[m.jnt_qposadr[j]];
-          if (m.jnt_type[j] == J_SLIDE) {
-            pos = pos + ax * qq;
-          } else {
-            quat = qmul(quat, aa2q(ld3(m.jnt_axis[j]), qq));
-            pos = anchor - rotq(quat, jp);
-          }
-        }
+        const int p = m.body_parent[b];
+        pos = ld3(s + S_XPOS + 3 * p) + mulv(ldm(s + U_XMAT + 9 * p), lp);
+        quat = qnormalize(qmul(ldq(s + S_XQUAT + 4 * p), lq));
       }
-      quat = qnormalize(quat);
       st3(s + S_XPOS + 3 * b, pos);
       stq(s + S_XQUAT + 4 * b, quat);
       stm(s + U_XMAT + 9 * b, q2m(quat));
     }
     __syncwarp();
+  }
+  // (4) lane = joint: axis / anchor to world
+  if (lane < m.njnt) {
+    const int jb = m.jnt_body[lane];
+    if (m.jnt_type[lane] == J_FREE) {
+      st3(s + U_XANCH + 3 * lane, ld3(s + S_XPOS + 3 * jb));
+      st3(s + U_XAXIS + 3 * lane, ld3(m.jnt_axis[lane]));
+    } else {
+      const int p = m.body_parent[jb];
+      const M3 Rp = ldm(s + U_XMAT + 9 * p);
+      const V3 ax = mulv(Rp, ld3(s + U_XAXIS + 3 * lane));
+      const V3 an = ld3(s + S_XPOS + 3 * p) + mulv(Rp, ld3(s + U_XANCH + 3 * lane));
+      st3(s + U_XAXIS + 3 * lane, ax);
+      st3(s + U_XANCH + 3 * lane, an);
+    }
   }
   // geoms
   if (lane < m.ngeom) {
@@ -117,19 +153,27 @@ __device__ __noinline__ void pos_stage(float* s, const DevModel& m, int lane) {
   // composite inertias: parents gather their children, deepest level first
   for (int L = m.nlevel - 1; L >= 1; L--) {
     if (lvl == L) {
-      for (int c = m.body_firstchild[b]; c >= 0; c = m.body_nextsib[c])
-        for (int k = 0; k < 10; k++) s[U_CRB + 10 * b + k] += s[U_CRB + 10 * c + k];
+      float acc[10];
+#pragma unroll
+      for (int k = 0; k < 10; k++) acc[k] = s[U_CRB + 10 * b + k];
+      for (int c = m.body_firstchild[b]; c >= 0; c = m.body_nextsib[c]) {
+#pragma unroll
+        for (int k = 0; k < 10; k++) acc[k] += s[U_CRB + 10 * c + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 10; k++) s[U_CRB + 10 * b + k] = acc[k];
     }
     __syncwarp();
   }
   // mass matrix, lane = dof i: row i entries for i and its ancestors
-#pragma unroll 4
+#pragma unroll 8
   for (int j = 0; j < 32; j++) s[S_M + lane * 33 + j] = (j == lane && lane >= m.nv) ? 1.f : 0.f;
   __syncwarp();
   if (lane < m.nv) {
     float buf[6];
     mul_inert_vec(buf, s + U_CRB + 10 * m.dof_body[lane], s + S_CDOF + 6 * lane);
-    for (int j = lane; j >= 0; j = m.dof_parent[j]) {
+    for (unsigned mk = m.dof_anc[lane] | (1u << lane); mk; mk &= mk - 1) {
+      const int j = __ffs(mk) - 1;
       const float* c = s + S_CDOF + 6 * j;
       float v = c[0] * buf[0] + c[1] * buf[1] + c[2] * buf[2] + c[3] * buf[3] + c[4] * buf[4] + c[5] * buf[5];
       if (j == lane) v += m.dof_armature[lane];
@@ -141,58 +185,63 @@ __device__ __noinline__ void pos_stage(float* s, const DevModel& m, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------- velocity stage
-// cvel / cdof_dot, then bias forces by recursive Newton-Euler.  Needs U_CINERT from pos_stage (same substep).
+// Bias forces by recursive Newton-Euler, written as lane-parallel sums over ancestor-dof masks instead of a serial walk:
+//   cvel_b = sum_{e in chain(b)} cdof_e qvel_e ;  cdof_dot_d = cvel(before d) x cdof_d ;  cacc_b = -g + sum cdof_dot_e qvel_e
+// (mj_comVel / mj_rne).  Needs U_CINERT from pos_stage (same substep).
 __device__ __noinline__ void vel_stage(float* s, const DevModel& m, int lane) {
-  const float* qv = s + S_QVEL;
   const int b = lane;
   const int lvl = b < m.nbody ? m.body_level[b] : -1;
-  if (lane == 0) {
-    for (int k = 0; k < 6; k++) { s[U_CVEL + k] = 0.f; s[U_CACC + k] = k < 3 ? 0.f : -m.gravity[k - 3]; s[U_CFRC + k] = 0.f; }
+  const float qv = lane < m.nv ? s[S_QVEL + lane] : 0.f;
+  float cd[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) { cd[k] = lane < m.nv ? s[S_CDOF + 6 * lane + k] : 0.f; s[U_DV + 6 * lane + k] = cd[k] * qv; }
+  __syncwarp();
+  {
+    float vb[6] = {0, 0, 0, 0, 0, 0}, t1[6];
+    if (lane < m.nv) {
+      for (unsigned mk = m.dof_premask[lane]; mk; mk &= mk - 1) {
+        const int e = __ffs(mk) - 1;
+#pragma unroll
+        for (int k = 0; k < 6; k++) vb[k] += s[U_DV + 6 * e + k];
+      }
+    }
+    cross_motion(t1, vb, cd);
+    const float sc = (lane < m.nv && !m.dof_dotzero[lane]) ? qv : 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) s[U_DA + 6 * lane + k] = t1[k] * sc;
   }
   __syncwarp();
-  for (int L = 1; L <= m.nlevel; L++) {
-    if (lvl == L) {
-      const int p = m.body_parent[b], da = m.body_dofadr[b], dn = m.body_dofnum[b];
-      float cv[6], ca[6], t1[6], t2[6], t3[6];
-      for (int k = 0; k < 6; k++) { cv[k] = s[U_CVEL + 6 * p + k]; ca[k] = s[U_CACC + 6 * p + k]; }
-      for (int j = 0; j < dn; j++) {
-        const int d = da + j;
-        if (m.jnt_type[m.dof_jnt[d]] == J_FREE) {
-          for (int k3 = 0; k3 < 3; k3++) {
-            for (int k = 0; k < 6; k++) { s[U_CDOFDOT + 6 * (d + k3) + k] = 0.f; cv[k] += s[S_CDOF + 6 * (d + k3) + k] * qv[d + k3]; }
-          }
-          for (int k3 = 3; k3 < 6; k3++) {
-            cross_motion(t1, cv, s + S_CDOF + 6 * (d + k3));
-            for (int k = 0; k < 6; k++) s[U_CDOFDOT + 6 * (d + k3) + k] = t1[k];
-          }
-          for (int k3 = 3; k3 < 6; k3++)
-            for (int k = 0; k < 6; k++) cv[k] += s[S_CDOF + 6 * (d + k3) + k] * qv[d + k3];
-          j += 5;
-        } else {
-          cross_motion(t1, cv, s + S_CDOF + 6 * d);
-          for (int k = 0; k < 6; k++) { s[U_CDOFDOT + 6 * d + k] = t1[k]; cv[k] += s[S_CDOF + 6 * d + k] * qv[d]; }
-        }
-      }
-      for (int j = 0; j < dn; j++)
-        for (int k = 0; k < 6; k++) ca[k] += s[U_CDOFDOT + 6 * (da + j) + k] * qv[da + j];
-      mul_inert_vec(t1, s + U_CINERT + 10 * b, ca);
-      mul_inert_vec(t2, s + U_CINERT + 10 * b, cv);
-      cross_force(t3, cv, t2);
-      for (int k = 0; k < 6; k++) { s[U_CVEL + 6 * b + k] = cv[k]; s[U_CACC + 6 * b + k] = ca[k]; s[U_CFRC + 6 * b + k] = t1[k] + t3[k]; }
+  if (b < m.nbody) {
+    float cv[6] = {0, 0, 0, 0, 0, 0}, ca[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]}, t1[6], t2[6], t3[6];
+    for (unsigned mk = m.body_chain[b]; mk; mk &= mk - 1) {
+      const int e = __ffs(mk) - 1;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { cv[k] += s[U_DV + 6 * e + k]; ca[k] += s[U_DA + 6 * e + k]; }
     }
-    __syncwarp();
+    mul_inert_vec(t1, s + U_CINERT + 10 * b, ca);
+    mul_inert_vec(t2, s + U_CINERT + 10 * b, cv);
+    cross_force(t3, cv, t2);
+#pragma unroll
+    for (int k = 0; k < 6; k++) s[U_CFRC + 6 * b + k] = b > 0 ? t1[k] + t3[k] : 0.f;
   }
+  __syncwarp();
   for (int L = m.nlevel - 1; L >= 1; L--) {
     if (lvl == L) {
-      for (int c = m.body_firstchild[b]; c >= 0; c = m.body_nextsib[c])
-        for (int k = 0; k < 6; k++) s[U_CFRC + 6 * b + k] += s[U_CFRC + 6 * c + k];
+      float acc[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) acc[k] = s[U_CFRC + 6 * b + k];
+      for (int c = m.body_firstchild[b]; c >= 0; c = m.body_nextsib[c]) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[k] += s[U_CFRC + 6 * c + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) s[U_CFRC + 6 * b + k] = acc[k];
     }
     __syncwarp();
   }
   if (lane < m.nv) {
-    const float* c = s + S_CDOF + 6 * lane;
     const float* f = s + U_CFRC + 6 * m.dof_body[lane];
-    s[S_BIAS + lane] = c[0] * f[0] + c[1] * f[1] + c[2] * f[2] + c[3] * f[3] + c[4] * f[4] + c[5] * f[5];
+    s[S_BIAS + lane] = cd[0] * f[0] + cd[1] * f[1] + cd[2] * f[2] + cd[3] * f[3] + cd[4] * f[4] + cd[5] * f[5];
   } else {
     s[S_BIAS + lane] = 0.f;
   }

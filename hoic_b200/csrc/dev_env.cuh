@@ -146,12 +146,33 @@ __device__ __forceinline__ bool solve6(double H[6][6], const double* rhs, double
   return true;
 }
 
+// sums v[0..31] across the warp by recursive halving: lane L ends with the total of element L (31 shuffles of doubles
+// in 5 dependent steps instead of 5 per element)
+__device__ __forceinline__ double warp_transpose_sum(double (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; j++) {
+      const double send = upper ? v[j] : v[j + off];
+      const double keep = upper ? v[j + off] : v[j];
+      v[j] = keep + __shfl_xor_sync(FULLMASK, send, off);
+    }
+  }
+  return v[0];
+}
+
+#define QP_G (QP_END + 2)                 // [380][6] float: wrench column of each variable (scaled torque rows)
+#define QP_RED (QP_G + 384 * 6)           // 32 doubles: reduced gradient / Hessian entries
+#define QP_NPER 12                        // variables per lane (380 / 32 rounded up)
+
 // returns rfc_score; fills rest[6]
 __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,
                         V3 org_now, float* rest, unsigned& qp_iters) {
-  const double eps = 1e-7, w_t = 1e4, sqw = 100.0;
+  const double eps = 1e-7, sqw = 100.0;
   const int n = 4 * ec * ncg;
-  // penalties c_i
+  double* red = reinterpret_cast<double*>(s + ((QP_RED + 1) & ~1));
+  // per-variable data: penalty c_i and wrench column g_i
   for (int i = lane; i < n; i += 32) {
     QpVar v;
     V3 pos;
@@ -172,56 +193,79 @@ __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, 
     for (int a = 1; a < 4; a++) if (dirs[a] > dirs[mx]) mx = a;
     if (e != mx) c += norm(vt);
     s[QP_C + i] = c;
+    for (int a = 0; a < 6; a++) s[QP_G + 6 * i + a] = (float)v.g[a];
   }
   __syncwarp();
   const double b6[6] = {F.x, F.y, F.z, sqw * T.x, sqw * T.y, sqw * T.z};
+  double bmax = 0;
+  for (int a = 0; a < 6; a++) bmax = fmax(bmax, fabs(b6[a]));
   double lam[6] = {0, 0, 0, 0, 0, 0};
-  (void)w_t;
+  double sv[QP_NPER], gd[QP_NPER];       // per owned variable: s_i = c_i + g_i.lam and g_i.dl
   for (int it = 0; it < 60; it++) {
-    double gp[6] = {0, 0, 0, 0, 0, 0}, hs[21];
-    for (int k = 0; k < 21; k++) hs[k] = 0;
-    for (int i = lane; i < n; i += 32) {
-      QpVar v;
-      qp_var(s, i, ec, obj_p, (float)sqw, v, nullptr);
-      double si = (double)s[QP_C + i];
-      for (int k = 0; k < 6; k++) si += v.g[k] * lam[k];
-      if (si < 0) {
-        int q = 0;
-        for (int a = 0; a < 6; a++) {
-          gp[a] += si * v.g[a];
-          for (int c = 0; c <= a; c++) hs[q++] += v.g[a] * v.g[c];
+    double acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) acc[k] = 0;
+#pragma unroll
+    for (int t = 0; t < QP_NPER; t++) {
+      const int i = lane + 32 * t;
+      sv[t] = 1.0;
+      if (i < n) {
+        double g[6], si = (double)s[QP_C + i];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { g[k] = (double)s[QP_G + 6 * i + k]; si += g[k] * lam[k]; }
+        sv[t] = si;
+        if (si < 0) {
+          int q = 6;
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            acc[a] += si * g[a];
+#pragma unroll
+            for (int c = 0; c <= a; c++) acc[q++] += g[a] * g[c];
+          }
         }
       }
     }
+    const double mine = warp_transpose_sum(acc, lane);
+    if (lane < 27) red[lane] = mine;
+    __syncwarp();
     double H[6][6], grad[6], dl[6];
     {
-      int q = 0;
+      int q = 6;
+#pragma unroll
       for (int a = 0; a < 6; a++) {
-        grad[a] = 0.5 * lam[a] + b6[a] + wsumd(gp[a]) / eps;
-        for (int c = 0; c <= a; c++) { const double hv = wsumd(hs[q++]) / eps; H[a][c] = hv; H[c][a] = hv; }
+        grad[a] = 0.5 * lam[a] + b6[a] + red[a] / eps;
+#pragma unroll
+        for (int c = 0; c <= a; c++) { const double hv = red[q++] / eps; H[a][c] = hv; H[c][a] = hv; }
         H[a][a] += 0.5;
       }
     }
-    double gmax = 0, bmax = 0;
-    for (int a = 0; a < 6; a++) { gmax = fmax(gmax, fabs(grad[a])); bmax = fmax(bmax, fabs(b6[a])); }
+    __syncwarp();
+    double gmax = 0;
+    for (int a = 0; a < 6; a++) gmax = fmax(gmax, fabs(grad[a]));
     qp_iters++;
     if (gmax <= 1e-9 * (1.0 + bmax)) break;
     double ng[6];
     for (int a = 0; a < 6; a++) ng[a] = -grad[a];
     if (!solve6(H, ng, dl)) break;
-    // exact line search on the piecewise quadratic along dl
     double ll = 0, dd = 0, bd = 0;
     for (int a = 0; a < 6; a++) { ll += lam[a] * dl[a]; dd += dl[a] * dl[a]; bd += b6[a] * dl[a]; }
+#pragma unroll
+    for (int t = 0; t < QP_NPER; t++) {
+      const int i = lane + 32 * t;
+      gd[t] = 0;
+      if (i < n) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) gd[t] += (double)s[QP_G + 6 * i + k] * dl[k];
+      }
+    }
+    // exact line search on the piecewise quadratic along dl (safeguarded Newton on the derivative)
     double lo = 0, hi = -1, alpha = 1.0, d1 = 0, d2 = 0;
     for (int ls = 0; ls < 40; ls++) {
       double a1 = 0, a2 = 0;
-      for (int i = lane; i < n; i += 32) {
-        QpVar v;
-        qp_var(s, i, ec, obj_p, (float)sqw, v, nullptr);
-        double si = (double)s[QP_C + i], gd = 0;
-        for (int k = 0; k < 6; k++) { si += v.g[k] * lam[k]; gd += v.g[k] * dl[k]; }
-        const double sa = si + alpha * gd;
-        if (sa < 0) { a1 += sa * gd; a2 += gd * gd; }
+#pragma unroll
+      for (int t = 0; t < QP_NPER; t++) {
+        const double sa = sv[t] + alpha * gd[t];
+        if (sa < 0) { a1 += sa * gd[t]; a2 += gd[t] * gd[t]; }
       }
       d1 = 0.5 * (ll + alpha * dd) + bd + wsumd(a1) / eps;
       d2 = 0.5 * dd + wsumd(a2) / eps;
@@ -234,20 +278,16 @@ __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, 
       } else if (!(nxt > alpha)) nxt = 2 * alpha;
       alpha = nxt;
     }
-    double step = 0;
-    for (int a = 0; a < 6; a++) { lam[a] += alpha * dl[a]; step = fmax(step, fabs(alpha * dl[a])); }
-    double lmax = 0;
-    for (int a = 0; a < 6; a++) lmax = fmax(lmax, fabs(lam[a]));
+    double step = 0, lmax = 0;
+    for (int a = 0; a < 6; a++) { lam[a] += alpha * dl[a]; step = fmax(step, fabs(alpha * dl[a])); lmax = fmax(lmax, fabs(lam[a])); }
     if (step <= 1e-14 * (1.0 + lmax)) break;
   }
   // primal recovery: x_i = max(0, -s_i/eps); residual wrench in the scaled space
   double gx[6] = {0, 0, 0, 0, 0, 0};
   for (int i = lane; i < n; i += 32) {
-    QpVar v;
-    qp_var(s, i, ec, obj_p, (float)sqw, v, nullptr);
-    double si = (double)s[QP_C + i];
-    for (int k = 0; k < 6; k++) si += v.g[k] * lam[k];
-    if (si < 0) { const double x = -si / eps; for (int k = 0; k < 6; k++) gx[k] += v.g[k] * x; }
+    double g[6], si = (double)s[QP_C + i];
+    for (int k = 0; k < 6; k++) { g[k] = (double)s[QP_G + 6 * i + k]; si += g[k] * lam[k]; }
+    if (si < 0) { const double x = -si / eps; for (int k = 0; k < 6; k++) gx[k] += g[k] * x; }
   }
   double r[6];
   for (int k = 0; k < 6; k++) r[k] = b6[k] - wsumd(gx[k]);

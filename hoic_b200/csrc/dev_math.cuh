@@ -207,3 +207,45 @@ __device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int
   *xout = x;
   return ok;
 }
+
+// ---- rank-one update / downdate of a Cholesky factor held in shared memory (lower triangle, stride 33):
+// L L^T <- L L^T + sign * w w^T, lane i carries w_i.  Columns below `kstart` (the first non-zero of w) are untouched.
+// Returns false if a downdate loses positive definiteness (caller refactorises).
+__device__ __noinline__ bool warp_chol_rank1(float* L, float w, float sign, int kstart, int lane) {
+  bool ok = true;
+#pragma unroll 2
+  for (int k = kstart; k < 32; k++) {
+    const float lkk = L[k * 33 + k];
+    const float wk = __shfl_sync(FULLMASK, w, k);
+    const float r2 = fmaf(sign * wk, wk, lkk * lkk);
+    ok = ok && (r2 > 1e-12f * lkk * lkk);
+    const float r = sqrtf(fmaxf(r2, 1e-30f));
+    const float ilkk = 1.0f / lkk;
+    const float c = r * ilkk, sn = wk * ilkk, ic = lkk / r;
+    if (lane == k) L[k * 33 + k] = r;
+    else if (lane > k) {
+      const float lik = (L[lane * 33 + k] + sign * sn * w) * ic;
+      w = fmaf(c, w, -sn * lik);
+      L[lane * 33 + k] = lik;
+    }
+  }
+  __syncwarp();
+  return ok;
+}
+// solve L L^T x = b with an existing factor
+__device__ __noinline__ float warp_chol_resolve(const float* L, float b, int lane) {
+  const float myinv = 1.0f / L[lane * 33 + lane];
+  float y = b;
+#pragma unroll 4
+  for (int k = 0; k < 32; k++) {
+    const float yk = __shfl_sync(FULLMASK, y * myinv, k);
+    y = lane == k ? yk : (lane > k ? fmaf(-L[lane * 33 + k], yk, y) : y);
+  }
+  float x = y;
+#pragma unroll 4
+  for (int i = 31; i >= 0; i--) {
+    const float xi = __shfl_sync(FULLMASK, x * myinv, i);
+    x = lane == i ? xi : (lane < i ? fmaf(-L[i * 33 + lane], xi, x) : x);
+  }
+  return x;
+}

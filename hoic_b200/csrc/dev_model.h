@@ -29,6 +29,7 @@ struct DevCand {
   float solref[2], solimp[5];
   float dA_tran, dA_rot;        // body_invweight0 sums of the two bodies
   int hand_slot;                // >=0: g1 is hand geom hand_geom0+slot and g2 an object collision geom (record_contact)
+  unsigned chain1, chain2;      // ancestor-dof masks of the two geoms' bodies
   int pad;
 };
 
@@ -52,7 +53,9 @@ struct DevModel {
   float jnt_pos[HN][3], jnt_axis[HN][3], jnt_range[HN][2], jnt_margin[HN], jnt_solref[HN][2], jnt_solimp[HN][5];
   float jnt_invweight[HN], qpos0[H_NQ];
   // dofs
-  int dof_body[HN], dof_jnt[HN], dof_parent[HN], dof_rootslot[HN];
+  int dof_body[HN], dof_jnt[HN], dof_parent[HN], dof_rootslot[HN], dof_dotzero[HN];
+  unsigned dof_anc[HN];          // strict ancestor dofs
+  unsigned dof_premask[HN];      // dofs whose velocity is accumulated before cdof_dot of this dof is formed (mj_comVel)
   float dof_armature[HN], dof_damping[HN], dof_frictionloss[HN], fr_D[HN], fr_B[HN], fr_Rf[HN];
   // geoms
   int geom_type[HN], geom_body[HN], geom_vertadr[HN], geom_vertnum[HN];

@@ -6,6 +6,10 @@
 #pragma once
 #include "dev_math.cuh"
 
+#ifdef H_STATS
+__device__ unsigned long long g_stats[8];
+#endif
+#define H_NCHG 3           // state changes handled by rank-one factor updates before a full refactorisation
 #define U_BINFO (U_MPRQ)   // basis row -> contact | k<<8 (the MPR queue is dead once contacts exist)
 #define U_CW (U_CON)       // per-contact Hessian weights reuse the contact records' slots 14..15 + CINFO pad
 
@@ -89,12 +93,11 @@ __device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
       if (lane == 0) { ((int*)ci)[0] = 0; ((int*)ci)[1] = 0; ((int*)ci)[2] = 0; ((int*)ci)[3] = 0; ci[6] = 0.f; }
       continue;
     }
-    const int b1 = m.geom_body[cd.g1], b2 = m.geom_body[cd.g2];
     const V3 pos = ld3(cr), f0 = ld3(cr + 3), f1 = ld3(cr + 6), f2 = ld3(cr + 9);
     const float dist = cr[12];
     // jacobian difference column for dof = lane
     float sg = 0.f;
-    if (lane < m.nv) sg = (float)((m.body_chain[b2] >> lane) & 1u) - (float)((m.body_chain[b1] >> lane) & 1u);
+    if (lane < m.nv) sg = (float)((cd.chain2 >> lane) & 1u) - (float)((cd.chain1 >> lane) & 1u);
     V3 jp = v3(0, 0, 0), jr = v3(0, 0, 0);
     if (sg != 0.f) {
       const V3 off = pos - ld3(s + S_COM + 3 * m.dof_rootslot[lane]);
@@ -142,7 +145,7 @@ __device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
     if (lane == 0) {
       ((int*)ci)[0] = nbasis; ((int*)ci)[1] = nb; ((int*)ci)[2] = nedge; ((int*)ci)[3] = ne;
       ci[4] = mu0; ci[5] = mu1; ci[6] = D;
-      ((unsigned*)ci)[7] = m.body_chain[b1] | m.body_chain[b2];
+      ((unsigned*)ci)[7] = cd.chain1 | cd.chain2;
     }
     nbasis += nb;
     nedge += ne;
@@ -362,18 +365,17 @@ __device__ __noinline__ float line_search(float* s, const DevModel& m, int lane,
   mul_J(s, lane, nbasis, nedge, s + S_SEARCH, s + U_JV);
   const float qg1 = wsum(sv * (s[S_MA + lane] - s[S_SMOOTH + lane]));
   const float qg2 = 0.5f * wsum(sv * mv);
-  float d1, d2, lo = 0.f, hi = -1.f, alpha = 0.f, dlo;
-  ls_eval(s, m, lane, nedge, 0.f, qg1, qg2, d1, d2);
-  evals++;
-  if (!(d1 < 0.f) || !(d2 > 0.f)) return 0.f;
-  dlo = d1;
+  float d1, d2, lo = 0.f, hi = -1.f, alpha = 1.f;
+  // at alpha = 0 the derivative is grad.search and the curvature search'H search = -grad.search (H search = -grad),
+  // so the first trial point is the full Newton step alpha = 1 without evaluating the rows at 0
+  d1 = wsum(sv * s[S_GRAD + lane]);
+  if (!(d1 < 0.f)) return 0.f;
   const float gtol = 1e-6f * fabsf(d1);
-  alpha = -d1 / d2;
   for (int it = 0; it < 24; it++) {
     ls_eval(s, m, lane, nedge, alpha, qg1, qg2, d1, d2);
     evals++;
     if (fabsf(d1) <= gtol) break;
-    if (d1 < 0.f) { lo = alpha; dlo = d1; } else hi = alpha;
+    if (d1 < 0.f) lo = alpha; else hi = alpha;
     float nxt = alpha - d1 / d2;
     if (hi >= 0.f) {
       if (!(nxt > lo && nxt < hi)) nxt = 0.5f * (lo + hi);
@@ -383,7 +385,6 @@ __device__ __noinline__ float line_search(float* s, const DevModel& m, int lane,
     }
     alpha = nxt;
   }
-  (void)dlo;
   return alpha;
 }
 
@@ -419,6 +420,10 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
   bool ok = true;
   unsigned iter = 0;
   float oldcost = cost;
+  // rows whose state changed during the last move (at most H_NCHG are tracked; more -> full refactorisation)
+  int nchg = -1, chrow[H_NCHG];
+  float chsign[H_NCHG];
+  const int* rinfo = (const int*)(s + U_RINFO);
   for (;;) {
     const float g2 = newton_gradient(s, m, lane, nlim, nbasis);
     if (iter > 0) {
@@ -428,8 +433,37 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
       if (improvement < tol || gradn < m.tolerance) break;
     }
     if (iter >= (unsigned)m.iterations) break;
-    ok = newton_direction(s, m, lane, nlim, ncon, nbasis, nedge);
-    if (!ok) break;
+    bool incremental = nchg >= 0 && nchg <= H_NCHG;
+    if (incremental) {
+      // update the factor of the previous Hessian by the rows that entered (+) or left (-) the quadratic set
+      for (int q = 0; q < nchg && incremental; q++) {
+        const int r = chrow[q];
+        const float sd = sqrtf(s[U_D + r]);
+        float w = 0.f;
+        int k0;
+        if (r < H_RLIM) { k0 = r; if (lane == r) w = sd; }
+        else if (r < H_RCON) { k0 = rinfo[r] & 255; if (lane == k0) w = sd; }
+        else {
+          const int ri = rinfo[r], c = ri & 255, ed = ri >> 8;
+          const float* ci = s + U_CINFO + 8 * c;
+          const int bo = ((const int*)ci)[0], ne = ((const int*)ci)[3];
+          w = s[U_B + bo * 33 + lane];
+          if (ne > 1) { const int k = ed / 2 + 1; const float mu = k <= 2 ? ci[4] : ci[5]; w += ((ed & 1) ? -mu : mu) * s[U_B + (bo + k) * 33 + lane]; }
+          w *= sd;
+          k0 = __ffs(((const unsigned*)ci)[7]) - 1;
+        }
+        incremental = warp_chol_rank1(s + S_H, w, chsign[q], k0, lane);
+      }
+      if (incremental) {
+        const float dir = warp_chol_resolve(s + S_H, -s[S_GRAD + lane], lane);
+        s[S_SEARCH + lane] = dir;
+        __syncwarp();
+      }
+    }
+    if (!incremental) {
+      ok = newton_direction(s, m, lane, nlim, ncon, nbasis, nedge);
+      if (!ok) break;
+    }
     const float alpha = line_search(s, m, lane, nbasis, nedge, ls_evals);
     if (alpha == 0.f) break;
     qacc += alpha * s[S_SEARCH + lane];
@@ -438,11 +472,30 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
     s[S_MA + lane] = ma;
     // move along the search direction; note whether any row changed state (active set / friction branch)
     bool changed = false;
-    for (int r = lane; r < H_RCON + nedge; r += 32) {
-      const float x0 = s[U_JAR + r], x1 = x0 + alpha * s[U_JV + r];
-      s[U_JAR + r] = x1;
-      if (r < H_RLIM) { const float Rf = m.fr_Rf[r]; changed |= ((x0 <= -Rf) != (x1 <= -Rf)) || ((x0 >= Rf) != (x1 >= Rf)); }
-      else changed |= (x0 < 0.f) != (x1 < 0.f);
+    nchg = 0;
+    for (int r0 = 0; r0 < H_RCON + nedge; r0 += 32) {
+      const int r = r0 + lane;
+      bool ch = false, enter = false;
+      if (r < H_RCON + nedge) {
+        const float x0 = s[U_JAR + r], x1 = x0 + alpha * s[U_JV + r];
+        s[U_JAR + r] = x1;
+        if (s[U_D + r] != 0.f) {
+          bool q0, q1;
+          if (r < H_RLIM) { const float Rf = m.fr_Rf[r]; q0 = fabsf(x0) < Rf; q1 = fabsf(x1) < Rf; ch = ((x0 <= -Rf) != (x1 <= -Rf)) || ((x0 >= Rf) != (x1 >= Rf)); }
+          else { q0 = x0 < 0.f; q1 = x1 < 0.f; ch = q0 != q1; }
+          enter = q1 && !q0;
+          // a friction row jumping from one linear branch to the other changes the forces but not the Hessian
+          if (ch && q0 == q1) { changed = true; ch = false; }
+        }
+      }
+      unsigned bal = __ballot_sync(FULLMASK, ch);
+      const unsigned ent = __ballot_sync(FULLMASK, enter);
+      if (bal) changed = true;
+      for (; bal; bal &= bal - 1) {
+        const int bit = __ffs(bal) - 1;
+        if (nchg < H_NCHG) { chrow[nchg] = r0 + bit; chsign[nchg] = (ent >> bit) & 1u ? 1.f : -1.f; }
+        nchg++;
+      }
     }
     changed = __any_sync(FULLMASK, changed);
     __syncwarp();

@@ -30,6 +30,7 @@ struct BatchDev {
   const float* reward_w;              // [24]
   int mode_train;
   unsigned long long* counters;       // hoic_counters as 12 x u64
+  const int* perm;                    // optional env order (load balancing), NULL = identity
 };
 
 struct StepOut {
@@ -47,7 +48,6 @@ __device__ __noinline__ bool phase_forward(float* s, const DevModel& m, int lane
   const bool fail = __any_sync(FULLMASK, bad(s[S_QPOS + lane]) || bad(s[S_QVEL + lane]) || (lane == 0 && bad(s[S_QPOS + 32])));
   if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   pos_stage(s, m, lane);
-  vel_stage(s, m, lane);
   return true;
 }
 __device__ __noinline__ bool phase_smooth(float* s, const DevModel& m, int lane) {
@@ -83,6 +83,7 @@ __device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int lane, 
 __device__ bool substep_core(float* s, const DevModel& m, int lane, bool record, Cnt& cnt) {
   int* misc = (int*)(s + S_MISC);
   if (!phase_forward(s, m, lane)) return false;
+  vel_stage(s, m, lane);
   collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
   if (record) record_contacts(s, m, lane);
   build_rows(s, m, lane);
@@ -200,13 +201,18 @@ __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, c
 // state that preceded the step (the "stale" quantities the env logic reads) with the same code as the
 // real substeps.  CTA barriers keep the warps of a CTA inside the same code region (instruction-cache locality).
 #define H_WPB 7
+#ifndef H_BARRIERS
+#define H_BARRIERS 0xff
+#endif
+#define HB(n) do { if (H_BARRIERS & (1 << (n))) __syncthreads(); } while (0)
 __global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __restrict__ actions, StepOut out) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * H_WPB + warp;
+  const int slot = blockIdx.x * H_WPB + warp;
   float* s = smem + (size_t)warp * S_TOTAL;
-  const bool live = env < B.n_envs;
-  const int envc = live ? env : B.n_envs - 1;
+  const bool live = slot < B.n_envs;
+  const int env = live ? (B.perm ? B.perm[slot] : slot) : B.n_envs - 1;
+  const int envc = env;
   const DevModel& m = *B.env_model[envc];
   float* st = B.state + (size_t)envc * ST_STRIDE;
   int* ints = (int*)(st + ST_INTS);
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __
   bool ok = live;      // false once this env failed (or the slot is padding): skips work, keeps hitting the barriers
   const int nsub = m.sim_step;
   for (int k = -1; k < nsub; k++) {
-    __syncthreads();
+    HB(0);
     if (ok && k >= 0) {
       if (k == 0) {
         vf = m.residual_force ? ld3(s + S_ACT + m.nu) * m.rf_scale : v3(0, 0, 0);
@@ -249,8 +255,11 @@ __global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __
       __syncwarp();
       if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
     }
+    HB(6);
     if (ok) ok = phase_forward(s, m, lane) || k < 0;   // a bad stale state is reported by the previous step already
-    __syncthreads();
+    HB(5);
+    if (ok) vel_stage(s, m, lane);
+    HB(1);
     if (ok) {
       collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
       if (k + 1 < nsub) record_contacts(s, m, lane);
@@ -269,15 +278,18 @@ __global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __
       }
       continue;
     }
-    __syncthreads();
+    HB(2);
     if (ok) {
       build_rows(s, m, lane);
+    }
+    HB(7);
+    if (ok) {
       ok = phase_smooth(s, m, lane);
       if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
     }
-    __syncthreads();
+    HB(3);
     if (ok) ok = phase_solve(s, m, lane, cnt);
-    __syncthreads();
+    HB(4);
     if (ok) {
       ok = euler_step(s, m, lane, nullptr);
       if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
@@ -306,6 +318,7 @@ __global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __
     if (out.end) out.end[env] = end;
     if (out.percent) out.percent[env] = (float)ctx.cur_t / (float)(ctx.expert_len - 1);
     ints[0] = ctx.cur_t;
+    ints[5] = (int)(cnt.newton * 8 + cnt.ncon * 2 + cnt.mpr_iters + (ncg ? 40 + 8 * ncg : 0));
     st[ST_RFC] = rfc_score;
     for (int k = 0; k < 6; k++) st[ST_RFC + 1 + k] = rest[k];
     st[ST_RFC + 7] = (float)ncg;
@@ -654,6 +667,22 @@ bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<f
   for (int d = 0; d < nv; d++) {
     D.dof_body[d] = dbody[d]; D.dof_jnt[d] = djnt[d]; D.dof_parent[d] = dparent[d];
     D.dof_rootslot[d] = rootslot_of_body[rootid[dbody[d]]];
+    {
+      unsigned anc = 0;
+      for (int e = dparent[d]; e >= 0; e = dparent[e]) anc |= 1u << e;
+      D.dof_anc[d] = anc;
+      const int j = djnt[d];
+      if (jtype[j] == J_FREE) {
+        const int k = d - jdadr[j];
+        unsigned base = 0;
+        for (int e = dparent[jdadr[j]]; e >= 0; e = dparent[e]) base |= 1u << e;
+        D.dof_dotzero[d] = k < 3;
+        D.dof_premask[d] = k < 3 ? 0u : (base | (7u << jdadr[j]));
+      } else {
+        D.dof_dotzero[d] = 0;
+        D.dof_premask[d] = anc;
+      }
+    }
     D.dof_armature[d] = (float)darm[d]; D.dof_damping[d] = (float)ddamp[d]; D.dof_frictionloss[d] = (float)dfl[d];
     // friction-loss row constants: pos = margin = 0 -> impedance solimp[0]; K = 0
     const double* si = &dsolimp[5 * d];
@@ -717,6 +746,7 @@ bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<f
     for (int k = 0; k < 5; k++) c.solimp[k] = (float)solimp[k];
     c.dA_tran = (float)(binvw[2 * gbody[g1]] + binvw[2 * gbody[g2]]);
     c.dA_rot = (float)(binvw[2 * gbody[g1] + 1] + binvw[2 * gbody[g2] + 1]);
+    c.chain1 = D.body_chain[gbody[g1]]; c.chain2 = D.body_chain[gbody[g2]];
     c.hand_slot = (g1 >= D.hand_geom0 && g1 <= D.hand_geom1 && g2 >= D.obj_geom0 && g2 <= D.obj_geom1) ? g1 - D.hand_geom0 : -1;
   };
   {
@@ -930,6 +960,22 @@ extern "C" int hoic_get_rfc(hoic_batch* b, float* out, void* stream) {
   LAUNCH_CHECK();
   return 0;
 }
+__global__ void k_get_work(BatchDev B, int* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B.n_envs) out[i] = ((const int*)(B.state + (size_t)i * ST_STRIDE + ST_INTS))[5];
+}
+extern "C" int hoic_get_work(hoic_batch* b, int* work, void* stream) {
+  if (!b || !work) return set_err("hoic_get_work: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_get_work<<<(b->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, work);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_set_env_order(hoic_batch* b, const int* perm) {
+  if (!b) return set_err("hoic_set_env_order: null batch");
+  b->b.perm = perm;
+  return 0;
+}
 extern "C" int hoic_get_counters(hoic_batch* b, hoic_counters* out_host) {
   if (!b || !out_host) return set_err("hoic_get_counters: bad arguments");
   CUDA_OK(cudaSetDevice(b->device));
@@ -939,6 +985,9 @@ extern "C" int hoic_get_counters(hoic_batch* b, hoic_counters* out_host) {
   out_host->env_steps = h[0]; out_host->substeps = h[1]; out_host->ncon = h[2]; out_host->nefc = h[3]; out_host->newton_iters = h[4];
   out_host->ls_evals = h[5]; out_host->mpr_calls = h[6]; out_host->mpr_iters = h[7]; out_host->qp_iters = h[8];
   out_host->fail_physics = h[9]; out_host->fail_overflow = h[10]; out_host->chol_calls = h[11];
+#ifdef H_STATS
+  { unsigned long long st[8]; cudaMemcpyFromSymbol(st, g_stats, sizeof st); fprintf(stderr, "H_STATS iters_with_change=%llu changed_fric=%llu changed_con=%llu le4=%llu only_fric=%llu\n", st[0], st[1], st[2], st[3], st[4]); }
+#endif
   return 0;
 }
 

@@ -26,7 +26,7 @@ class HandMimicVecEnv:
     obs_dim, act_dim = capi.OBS_DIM, capi.ACT_DIM
 
     def __init__(self, models, n_envs, motions, motion_model=None, env_model_id=None, device=0, seed=1,
-                 auto_reset=True, random_start=True, min_episode=200):
+                 auto_reset=True, random_start=True, min_episode=200, balance=True):
         if isinstance(models, Model):
             models = [models]
         if not torch.cuda.is_available():
@@ -63,6 +63,9 @@ class HandMimicVecEnv:
         self.end = torch.zeros(N, dtype=torch.uint8, device=self.device)
         self.set_motions(motions, motion_model)
         self.set_reward_weights(models[0].cfg.reward_vector())
+        self.balance = balance
+        self._work = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self._perm = None
 
     # ------------------------------------------------------------------ configuration
     def set_motions(self, motions, motion_model=None):
@@ -131,6 +134,11 @@ class HandMimicVecEnv:
     def step(self, actions):
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         assert a.shape == (self.n_envs, capi.ACT_DIM)
+        if self.balance and self.n_envs > 7:
+            # group envs of similar cost (last step's solver iterations / contacts) into the same CTA
+            capi.check(self.L.hoic_get_work(self._hb, capi.ptr(self._work), self._stream()), "hoic_get_work")
+            self._perm = torch.argsort(self._work, stable=True).to(torch.int32)
+            capi.check(self.L.hoic_set_env_order(self._hb, capi.ptr(self._perm)), "hoic_set_env_order")
         capi.check(self.L.hoic_step(self._hb, capi.ptr(a), capi.ptr(self.obs), capi.ptr(self.reward), capi.ptr(self.reward_info),
                                     capi.ptr(self.done), capi.ptr(self.fail), capi.ptr(self.end), capi.ptr(self.percent),
                                     self._stream()), "hoic_step")

@@ -102,6 +102,12 @@ int hoic_get_derived(hoic_batch* b, float* xpos, float* xquat, float* qM, float*
 /* per-step scalars of the last hoic_step: [N][8] = rfc_score, rest_force[3], rest_torque[3], n contact geoms */
 int hoic_get_rfc(hoic_batch* b, float* out, void* stream);
 
+/* load balancing across CTAs: work[N] = cost proxy of each env's last step (solver iterations, contacts, QP size);
+ * hoic_set_env_order installs a device permutation (NULL = identity) so that a CTA steps envs of similar cost.
+ * Results do not depend on the order. */
+int hoic_get_work(hoic_batch* b, int* work /*[N]*/, void* stream);
+int hoic_set_env_order(hoic_batch* b, const int* perm /*[N] device, kept by reference*/);
+
 /* integer work counters accumulated by the kernels since creation (synchronises the device) */
 int hoic_get_counters(hoic_batch* b, hoic_counters* out_host);
 /* FP32 FMA micro-benchmark on `device` (roofline denominator for the non-tensor pipe): 2*FMAs/s in TFLOP/s */
