@@ -1,0 +1,148 @@
+"""One PPO iteration on the batched rollout engine: the host-side mirror of `AgentHandMimic`
+(uhc/agents/agent_handmimic.py:26-74, 264-337, 430-535) + `AgentPPO.update_params` (uhc/khrylib/rl/agents/agent_pg.py:40-56,
+agent_ppo.py:16-64) with the same method names (`per_epoch_update`, `sample`, `update_params`, `optimize_policy`).
+
+What differs from the reference, by construction of a batched collector:
+* N environments step in lockstep for a fixed horizon T = ceil(min_batch_size / (N * world)) instead of forked workers
+  running whole episodes until `min_batch_size` samples exist; an episode that is still running at the horizon is
+  bootstrapped with V(s_T) in the GAE (the reference only stores complete episodes, so its last mask is always 0);
+* the observation normaliser sees every environment (the reference keeps worker 0's statistics);
+* float32 networks (the reference runs torch.float64), Adam steps are full-batch over the rank's shard with gradients
+  averaged across ranks (NCCL) before the grad-norm clip, which equals the single-process full-batch step.
+PyTorch does the MLPs and the update only; every env number comes from libhoic_b200.so through `HandMimicVecEnv`.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import torch
+
+from . import dist as hdist
+from . import ppo
+from .vecenv import HandMimicVecEnv
+
+
+class TrajBatch:
+    """Time-major rollout storage on the device (uhc/khrylib/rl/core/trajbatch.py:5-15 fields, [T, N, ...])."""
+
+    def __init__(self, T, N, obs_dim, act_dim, device):
+        f = dict(dtype=torch.float32, device=device)
+        self.states = torch.empty(T, N, obs_dim, **f)
+        self.actions = torch.empty(T, N, act_dim, **f)
+        self.rewards = torch.empty(T, N, **f)
+        self.masks = torch.empty(T, N, **f)
+        self.exps = torch.empty(T, N, **f)
+        self.last_state = torch.empty(N, obs_dim, **f)   # normalised s_T of the envs (bootstrap)
+        self.T, self.N = T, N
+
+
+class AgentHandMimic:
+    def __init__(self, models, n_envs, motions=None, motion_model=None, env_model_id=None, device=0, seed=None, cfg=None,
+                 policy_grad_clip=40.0):
+        models = [models] if not isinstance(models, (list, tuple)) else list(models)
+        self.cfg = cfg or models[0].cfg
+        cfg = self.cfg
+        self.device = torch.device("cuda", device)
+        self.rank = torch.distributed.get_rank() if hdist._on() else 0
+        self.world = torch.distributed.get_world_size() if hdist._on() else 1
+        seed = cfg.seed if seed is None else seed
+        if motions is None:
+            motions, motion_model = [], []
+            for i, m in enumerate(models):
+                for s in range(1, 9):
+                    motions.append(m.motion(s))
+                    motion_model.append(i)
+        self.env = HandMimicVecEnv(models, n_envs, motions, motion_model=motion_model, env_model_id=env_model_id, device=device,
+                                   seed=seed + 1000 * self.rank, auto_reset=True, random_start=True)
+        self.n_envs = n_envs
+        # identical initial weights on every rank (same seed), as a forked worker would inherit them
+        self.policy_net, self.value_net = ppo.make_policy_value(cfg, self.env.obs_dim, self.env.act_dim, device=self.device,
+                                                                dtype=torch.float32, seed=seed)
+        self.running_state = ppo.ZFilter((self.env.obs_dim,), clip=5.0, device=self.device, dtype=torch.float32)
+        self.optimizer_policy = torch.optim.Adam(self.policy_net.parameters(), lr=cfg.policy_lr, weight_decay=cfg.policy_weightdecay)
+        self.optimizer_value = torch.optim.Adam(self.value_net.parameters(), lr=cfg.value_lr, weight_decay=cfg.value_weightdecay)
+        self.policy_grad_clip = policy_grad_clip
+        self.gen = torch.Generator(device=self.device).manual_seed(seed + 7919 * (self.rank + 1))
+        self.noise_rate = 1.0
+        self.epoch = 0
+        self._obs = None
+
+    # ------------------------------------------------------------------ agent_handmimic.py:264-282
+    def per_epoch_update(self, epoch):
+        cfg = self.cfg
+        cfg.update_adaptive_params(epoch)
+        self.noise_rate = float(cfg.adp_noise_rate)
+        for g in self.optimizer_policy.param_groups:
+            g["lr"] = float(cfg.adp_policy_lr)
+        if cfg.fix_std:
+            with torch.no_grad():
+                self.policy_net.action_log_std.fill_(float(cfg.adp_log_std))
+        self.env.set_reward_weights(cfg.reward_vector())   # epoch-adaptive reward weights (handmimic_config.py:175-195)
+
+    # ------------------------------------------------------------------ agent_handmimic.py:430-535
+    @torch.no_grad()
+    def sample(self, min_batch_size):
+        env, N = self.env, self.n_envs
+        env.set_mode("train")
+        T = max(1, math.ceil(min_batch_size / (N * self.world)))
+        batch = TrajBatch(T, N, env.obs_dim, env.act_dim, self.device)
+        stats = hdist.RolloutStats(self.device)
+        if self._obs is None:
+            self._obs = env.reset()
+        obs = self._obs
+        for t in range(T):
+            x = self.running_state(obs)
+            mean, log_std = self.policy_net(x)
+            noise = torch.randn(mean.shape, device=self.device, dtype=mean.dtype, generator=self.gen)
+            if self.noise_rate < 1.0:
+                # mean_action = binomial(1, 1 - noise_rate) per (env, step); exp = 1 - mean_action (:464-465, :484)
+                exp = (torch.rand(N, device=self.device, generator=self.gen) < self.noise_rate).to(torch.float32)
+            else:
+                exp = torch.ones(N, device=self.device)
+            act = mean + torch.exp(log_std) * noise * exp[:, None]
+            batch.states[t] = x
+            batch.actions[t] = act
+            batch.exps[t] = exp
+            obs, r, done, info = env.step(act)
+            batch.rewards[t] = r
+            batch.masks[t] = 1.0 - done.to(torch.float32)
+            stats.update(r, info["reward_info"], done)
+        self._obs = obs
+        batch.last_state = self.running_state(obs, update=False)
+        self.running_state.allreduce()
+        return batch, stats
+
+    # ------------------------------------------------------------------ agent_pg.py:40-56 + agent_ppo.py:16-64
+    def update_params(self, batch):
+        cfg = self.cfg
+        T, N = batch.T, batch.N
+        states = batch.states.reshape(T * N, -1)
+        actions = batch.actions.reshape(T * N, -1)
+        with torch.no_grad():
+            values = self.value_net(torch.cat([states, batch.last_state], 0)).reshape(T + 1, N)
+            adv, ret = ppo.estimate_advantages(batch.rewards, batch.masks, values, cfg.gamma, cfg.tau)
+            fixed_log_probs = self.policy_net.get_log_prob(states, actions)
+        ind = batch.exps.reshape(-1).nonzero().squeeze(1)
+        return ppo.ppo_update(self.policy_net, self.value_net, self.optimizer_policy, self.optimizer_value, states, actions,
+                              ret.reshape(-1, 1), adv.reshape(-1, 1), fixed_log_probs, clip_epsilon=cfg.clip_epsilon,
+                              num_epoch=cfg.num_optim_epoch, grad_clip=self.policy_grad_clip, ind=ind)
+
+    # ------------------------------------------------------------------ agent_handmimic.py:311-337
+    def optimize_policy(self, epoch):
+        self.epoch = epoch
+        torch.cuda.synchronize(self.device)
+        t0 = time.perf_counter()
+        self.per_epoch_update(epoch)
+        batch, stats = self.sample(self.cfg.min_batch_size)
+        torch.cuda.synchronize(self.device)
+        t1 = time.perf_counter()
+        upd = self.update_params(batch)
+        torch.cuda.synchronize(self.device)
+        t2 = time.perf_counter()
+        log = stats.allreduce()
+        return dict(log=log, T_sample=t1 - t0, T_update=t2 - t1, T_total=t2 - t0, samples=batch.T * batch.N * self.world,
+                    horizon=batch.T, **upd)
+
+    def close(self):
+        self.env.close()

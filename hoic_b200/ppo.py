@@ -133,25 +133,36 @@ def estimate_advantages(rewards, masks, values, gamma, tau):
 
 
 def ppo_update(policy, value, opt_policy, opt_value, states, actions, returns, advantages, fixed_log_probs, clip_epsilon=0.2,
-               num_epoch=5, grad_clip=40.0):
-    """agent_ppo.py:16-51 with full-batch steps; gradients are averaged across ranks before clipping."""
-    stats = {}
+               num_epoch=5, grad_clip=40.0, ind=None):
+    """agent_ppo.py:16-64 with full-batch steps (use_mini_batch=False, agent_handmimic.py:66); `ind` = indices of the
+    exploratory samples (exps.nonzero(), :44) the surrogate is taken over.  Gradients are averaged across ranks before
+    the grad-norm clip, so N ranks with equal shards take the single-process full-batch step."""
+    vloss = surr = None
+    if ind is not None and ind.numel() == states.shape[0]:
+        ind = None
     for _ in range(num_epoch):
         vloss = (value(states) - returns).pow(2).mean()
         opt_value.zero_grad(set_to_none=True)
         vloss.backward()
         hdist.allreduce_grads(value.parameters())
         opt_value.step()
-        log_probs = policy.get_log_prob(states, actions)
-        ratio = torch.exp(log_probs - fixed_log_probs)
-        surr = -torch.min(ratio * advantages, torch.clamp(ratio, 1.0 - clip_epsilon, 1.0 + clip_epsilon) * advantages).mean()
+        if ind is None:
+            log_probs = policy.get_log_prob(states, actions)
+            ratio = torch.exp(log_probs - fixed_log_probs)
+            adv = advantages
+        else:
+            log_probs = policy.get_log_prob(states[ind], actions[ind])
+            ratio = torch.exp(log_probs - fixed_log_probs[ind])
+            adv = advantages[ind]
+        surr = -torch.min(ratio * adv, torch.clamp(ratio, 1.0 - clip_epsilon, 1.0 + clip_epsilon) * adv).mean()
         opt_policy.zero_grad(set_to_none=True)
         surr.backward()
         hdist.allreduce_grads(policy.parameters())
         torch.nn.utils.clip_grad_norm_(policy.parameters(), grad_clip)
         opt_policy.step()
-        stats = dict(value_loss=float(vloss.detach()), surrogate=float(surr.detach()))
-    return stats
+    if vloss is None:
+        return {}
+    return dict(value_loss=float(vloss.detach()), surrogate=float(surr.detach()))
 
 
 def make_policy_value(cfg, obs_dim=617, act_dim=32, device="cuda", dtype=torch.float32, seed=1):

@@ -1,0 +1,117 @@
+"""CPU tests of the PPO host logic against literal transcriptions of the reference's pure-Python code:
+GAE (uhc/khrylib/rl/core/common.py:5-25), ZFilter / RunningStat (uhc/khrylib/utils/zfilter.py:7-73), the clipped
+surrogate step (uhc/khrylib/rl/agents/agent_ppo.py:16-64) and the network layout (models/mlp.py, policy_gaussian.py)."""
+import numpy as np
+import torch
+
+from common import model
+from hoic_b200 import ppo
+
+
+def ref_estimate_advantages(rewards, masks, values, gamma, tau):
+    """common.py:5-25 on one concatenated [n, 1] batch (float64)."""
+    n = rewards.shape[0]
+    deltas, adv = np.zeros((n, 1)), np.zeros((n, 1))
+    prev_value = prev_adv = 0.0
+    for i in reversed(range(n)):
+        deltas[i] = rewards[i] + gamma * prev_value * masks[i] - values[i]
+        adv[i] = deltas[i] + gamma * tau * prev_adv * masks[i]
+        prev_value, prev_adv = values[i, 0], adv[i, 0]
+    returns = values + adv
+    a = torch.as_tensor(adv)
+    return ((a - a.mean()) / a.std()).numpy(), returns
+
+
+def test_gae_matches_reference_on_complete_episodes():
+    rng = np.random.RandomState(0)
+    T, N = 40, 6
+    rewards, values = rng.rand(T, N), rng.randn(T + 1, N)
+    masks = (rng.rand(T, N) > 0.15).astype(float)
+    masks[-1] = 0.0      # the reference only stores complete episodes: every column ends with mask 0
+    adv, ret = ppo.estimate_advantages(torch.as_tensor(rewards), torch.as_tensor(masks), torch.as_tensor(values), 0.95, 0.95)
+    # reference layout: episodes concatenated env after env
+    r = rewards.T.reshape(-1, 1); m = masks.T.reshape(-1, 1); v = values[:-1].T.reshape(-1, 1)
+    radv, rret = ref_estimate_advantages(r, m, v, 0.95, 0.95)
+    assert np.allclose(adv.numpy().T.reshape(-1, 1), radv, atol=1e-12)
+    assert np.allclose(ret.numpy().T.reshape(-1, 1), rret, atol=1e-12)
+
+
+def test_gae_bootstraps_truncated_tails():
+    # an episode still running at the horizon uses V(s_T); with tau = 1 the return is the discounted sum + gamma^k V
+    T = 5
+    rewards = torch.ones(T, 1, dtype=torch.float64)
+    masks = torch.ones(T, 1, dtype=torch.float64)
+    values = torch.zeros(T + 1, 1, dtype=torch.float64)
+    values[-1] = 10.0
+    _, ret = ppo.estimate_advantages(rewards, masks, values, 0.9, 1.0)
+    expect = sum(0.9 ** k for k in range(T)) + 0.9 ** T * 10.0
+    assert abs(float(ret[0, 0]) - expect) < 1e-12
+
+
+def test_zfilter_batched_equals_sequential_welford():
+    from_ref_n, M, S = 0, np.zeros(5), np.zeros(5)
+    rng = np.random.RandomState(1)
+    xs = rng.randn(7, 4, 5) * 3 + 1
+    zf = ppo.ZFilter((5,), clip=5.0, dtype=torch.float64)
+    for b in xs:
+        for x in b:             # RunningStat.push, zfilter.py:14-24
+            from_ref_n += 1
+            if from_ref_n == 1:
+                M[...] = x
+            else:
+                old = M.copy()
+                M[...] = old + (x - old) / from_ref_n
+                S[...] = S + (x - old) * (x - M)
+        y = zf(torch.as_tensor(b))
+    std = np.sqrt(S / (from_ref_n - 1))
+    assert np.allclose(zf.mean.numpy(), M, atol=1e-12) and np.allclose(zf.std.numpy(), std, atol=1e-12)
+    expect = np.clip((xs[-1] - M) / (std + 1e-8), -5, 5)
+    assert np.allclose(y.numpy(), expect, atol=1e-12)
+    # update=False leaves the statistics alone
+    n = float(zf.n)
+    zf(torch.as_tensor(xs[0]), update=False)
+    assert float(zf.n) == n
+
+
+def test_network_layout_and_state_dict_keys():
+    cfg = model("box").cfg
+    pol, val = ppo.make_policy_value(cfg, device="cpu", dtype=torch.float64, seed=1)
+    assert [l.out_features for l in pol.net.affine_layers] == [2048, 1024, 512] and pol.action_mean.out_features == 32
+    keys = set(pol.state_dict().keys())
+    assert {"net.affine_layers.0.weight", "action_mean.weight", "action_mean.bias", "action_log_std"} <= keys
+    assert {"net.affine_layers.2.bias", "value_head.weight"} <= set(val.state_dict().keys())
+    assert torch.allclose(pol.action_log_std, torch.tensor(cfg.log_std, dtype=torch.float64), atol=1e-6) and torch.all(pol.action_mean.bias == 0)
+    x = torch.randn(3, 617, dtype=torch.float64)
+    a = pol.select_action(x, mean_action=True)
+    lp = pol.get_log_prob(x, a)     # log-density of the mean: -sum(log_std) - d/2 log(2 pi)
+    assert np.allclose(lp.detach().numpy(), -32 * cfg.log_std - 16 * np.log(2 * np.pi), atol=1e-4)
+
+
+def test_ppo_update_is_the_reference_step():
+    """One epoch of ppo_update == value MSE Adam step then clipped-surrogate Adam step with grad-norm clip (agent_ppo.py:44-64)."""
+    torch.manual_seed(0)
+    mk = lambda: (ppo.PolicyGaussian(ppo.MLP(8, (16, 8), "gelu"), 3, log_std=-1.0).double(), ppo.Value(ppo.MLP(8, (16, 8), "gelu")).double())
+    pol, val = mk()
+    pol2, val2 = mk()
+    pol2.load_state_dict(pol.state_dict()); val2.load_state_dict(val.state_dict())
+    n = 64
+    s, a = torch.randn(n, 8, dtype=torch.float64), torch.randn(n, 3, dtype=torch.float64) * 0.3
+    ret, adv = torch.randn(n, 1, dtype=torch.float64), torch.randn(n, 1, dtype=torch.float64)
+    exps = (torch.rand(n) < 0.8).double()
+    ind = exps.nonzero().squeeze(1)
+    with torch.no_grad():
+        flp = pol.get_log_prob(s, a)
+    op, ov = torch.optim.Adam(pol.parameters(), lr=5e-3), torch.optim.Adam(val.parameters(), lr=3e-3)
+    st = ppo.ppo_update(pol, val, op, ov, s, a, ret, adv, flp, clip_epsilon=0.2, num_epoch=1, grad_clip=0.05, ind=ind)
+    # transcription
+    op2, ov2 = torch.optim.Adam(pol2.parameters(), lr=5e-3), torch.optim.Adam(val2.parameters(), lr=3e-3)
+    vl = (val2(s) - ret).pow(2).mean(); ov2.zero_grad(); vl.backward(); ov2.step()
+    lp = pol2.get_log_prob(s[ind], a[ind]); ratio = torch.exp(lp - flp[ind])
+    sl = -torch.min(ratio * adv[ind], torch.clamp(ratio, 0.8, 1.2) * adv[ind]).mean()
+    op2.zero_grad(); sl.backward(); torch.nn.utils.clip_grad_norm_(pol2.parameters(), 0.05); op2.step()
+    for p, q in zip(list(pol.parameters()) + list(val.parameters()), list(pol2.parameters()) + list(val2.parameters())):
+        assert torch.allclose(p, q, atol=1e-14)
+    assert abs(st["value_loss"] - float(vl)) < 1e-12 and abs(st["surrogate"] - float(sl)) < 1e-12
+    # more epochs reduce the value loss
+    st5 = ppo.ppo_update(pol, val, op, ov, s, a, ret, adv, flp, num_epoch=20, ind=ind)
+    assert st5["value_loss"] < st["value_loss"]

@@ -1,0 +1,55 @@
+"""Train HandMimic with PPO on the batched B200 engine (mirrors scripts/train_hand_mimic.py:60-82 of the reference).
+
+  python train.py --obj box --envs 4096 --iters 10
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 train.py --obj banana --envs 2048
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--obj", default="box", help="box | bottle | banana | mixed")
+    ap.add_argument("--envs", type=int, default=2048, help="environments per GPU")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--epoch", type=int, default=0, help="first epoch (adaptive schedules start here)")
+    ap.add_argument("--min-batch-size", type=int, default=0, help="override cfg.min_batch_size (total over all GPUs)")
+    a = ap.parse_args()
+    import torch.distributed as dist
+    from hoic_b200.agent import AgentHandMimic
+    from hoic_b200.assets import load_model
+    from hoic_b200 import dist as hdist
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    if a.obj == "mixed":
+        models = [load_model(o) for o in ("box", "bottle", "banana")]
+        ids = hdist.mixed_model_ids(a.envs * world, 3, rank, world)
+    else:
+        models, ids = [load_model(a.obj)], None
+    agent = AgentHandMimic(models, a.envs, env_model_id=ids, device=local)
+    if a.min_batch_size:
+        agent.cfg.min_batch_size = a.min_batch_size
+    for i in range(a.epoch, a.epoch + a.iters):
+        info = agent.optimize_policy(i)
+        if rank == 0:
+            log = info.pop("log")
+            print(json.dumps(dict(iter=i, avg_reward=log["avg_reward"], episodes=log["num_episodes"],
+                                  samples_per_s=info["samples"] / info["T_total"], **{k: v for k, v in info.items()})))
+    agent.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
