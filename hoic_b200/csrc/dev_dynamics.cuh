@@ -165,20 +165,21 @@ __device__ __noinline__ void pos_stage(float* s, const DevModel& m, int lane) {
     }
     __syncwarp();
   }
-  // mass matrix, lane = dof i: row i entries for i and its ancestors
-#pragma unroll 8
-  for (int j = 0; j < 32; j++) s[S_M + lane * 33 + j] = (j == lane && lane >= m.nv) ? 1.f : 0.f;
-  __syncwarp();
+  // mass matrix, lane = dof i: entries of row i for its ancestors (by depth) and itself; the rest of the row stays zero
+  {
+    float4* z = reinterpret_cast<float4*>(s + S_MS + lane * MS_STRIDE);
+    z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (lane < m.nv) {
     float buf[6];
     mul_inert_vec(buf, s + U_CRB + 10 * m.dof_body[lane], s + S_CDOF + 6 * lane);
-    for (unsigned mk = m.dof_anc[lane] | (1u << lane); mk; mk &= mk - 1) {
+    int d = 0;   // ancestors come in increasing index = increasing depth
+    for (unsigned mk = m.dof_anc[lane] | (1u << lane); mk; mk &= mk - 1, d++) {
       const int j = __ffs(mk) - 1;
       const float* c = s + S_CDOF + 6 * j;
       float v = c[0] * buf[0] + c[1] * buf[1] + c[2] * buf[2] + c[3] * buf[3] + c[4] * buf[4] + c[5] * buf[5];
       if (j == lane) v += m.dof_armature[lane];
-      s[S_M + lane * 33 + j] = v;
-      s[S_M + j * 33 + lane] = v;
+      s[S_MS + lane * MS_STRIDE + d] = v;
     }
   }
   __syncwarp();
@@ -263,13 +264,9 @@ __device__ __forceinline__ float apply_ft(const float* s, const DevModel& m, int
 // Returns false on a failed factorisation.
 __device__ __noinline__ bool euler_step(float* s, const DevModel& m, int lane, unsigned long long* chol_calls) {
   const float h = m.timestep;
-#pragma unroll 4
-  for (int j = 0; j < 32; j++) s[S_H + lane * 33 + j] = s[S_M + lane * 33 + j];
-  if (lane < m.nv) s[S_H + lane * 33 + lane] += h * m.dof_damping[lane];
-  __syncwarp();
   float qa;
   const float rhs = lane < m.nv ? s[S_SMOOTH + lane] + s[S_FCON + lane] : 0.f;
-  const bool ok = warp_chol_solve(s + S_H, rhs, &qa, lane, s + S_COL);
+  const bool ok = tree_solve(s, m, lane, lane < m.nv ? h * m.dof_damping[lane] : 0.f, rhs, &qa);
   (void)chol_calls;
   __syncwarp();
   if (lane < m.nv) s[S_QVEL + lane] += h * qa;

@@ -43,15 +43,9 @@ __device__ __noinline__ bool pd_torque(float* s, const DevModel& m, int lane, co
     kp = m.jkp[lane]; kd = m.jkd[lane];
     rhs = -s[S_BIAS + lane] - kp * err - kd * qv;
   }
-#pragma unroll 4
-  for (int j = 0; j < 32; j++) {
-    float v = (lane < n && j < n) ? s[S_M + lane * 33 + j] : 0.f;
-    if (j == lane) v = lane < n ? v + kd * dt : 1.f;
-    s[S_H + lane * 33 + j] = v;
-  }
-  __syncwarp();
+  // (M_hand + Kd dt) acc = rhs: the object's dofs are a separate tree, their part of the solve is ignored
   float acc;
-  const bool ok = warp_chol_solve(s + S_H, rhs, &acc, lane, s + S_COL);
+  const bool ok = tree_solve(s, m, lane, lane < n ? kd * dt : 0.f, rhs, &acc);
   float t = 0.f;
   if (lane < n) {
     t = -kp * err - kd * (qv + acc * dt);

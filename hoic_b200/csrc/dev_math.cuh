@@ -154,19 +154,18 @@ __device__ __forceinline__ void cross_force(float* res, const float* vel, const 
   st3(res + 3, cross(w, b));
 }
 
-// ---- 32x32 SPD solve, one warp.  A: shared, row stride 33, lane i owns row i; on exit the lower triangle of A
-// holds the Cholesky factor L and *xout (per lane) the solution of A x = b.  The factorisation keeps one row per
-// lane in registers; the pivot column is broadcast through a small double-buffered shared array (`col`, 2 x 36
-// floats) instead of shuffles, the forward substitution rides along as a 33rd column, and the back-substitution
-// reads L^T from shared memory.  Returns false if a pivot is not positive.  Rows/cols >= n must be identity.
+// ---- 32x32 SPD solve, one warp.  The matrix arrives in registers: lane i holds row i (only columns j <= i are used).
+// On exit the packed lower triangle Lp (row i at i(i+1)/2; conflict-free for lane-indexed rows because the triangular
+// numbers are distinct mod 32) holds the Cholesky factor L and *xout the solution of A x = b.  The pivot column is
+// broadcast through a small double-buffered shared array (`col`, 2 x 36 floats) instead of shuffles, the forward
+// substitution rides along as a 33rd column, and the back-substitution reads L^T from shared memory.  Returns false if
+// a pivot is not positive.  Rows/cols >= n must be identity.
+#define TRI(i) (((i) * ((i) + 1)) >> 1)
 __device__ __forceinline__ float rsqrt_nr(float x) {
   float y = rsqrtf(x);
   return y * fmaf(-0.5f * x * y, y, 1.5f);   // one Newton step on the MUFU estimate
 }
-__device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int lane, float* col) {
-  float h[32];
-#pragma unroll
-  for (int j = 0; j < 32; j++) h[j] = A[lane * 33 + j];
+__device__ __forceinline__ bool warp_chol_solve(float (&h)[32], float* Lp, float b, float* xout, int lane, float* col) {
   bool ok = true;
   float yb = b;
 #pragma unroll
@@ -193,40 +192,44 @@ __device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int
       if (4 * g + 3 > k) h[4 * g + 3] = fmaf(cc, c4.w, h[4 * g + 3]);
     }
   }
+  const int tl = TRI(lane);
 #pragma unroll
-  for (int j = 0; j < 32; j++) A[lane * 33 + j] = h[j];
+  for (int j = 0; j < 32; j++)
+    if (j <= lane) Lp[tl + j] = h[j];
   __syncwarp();
   // backward: L^T x = y
-  const float myinv = 1.0f / A[lane * 33 + lane];
+  const float myinv = 1.0f / Lp[tl + lane];
   float x = yb;
 #pragma unroll 8
   for (int i = 31; i >= 0; i--) {
     const float xi = __shfl_sync(FULLMASK, x * myinv, i);
-    x = lane == i ? xi : (lane < i ? fmaf(-A[i * 33 + lane], xi, x) : x);
+    x = lane == i ? xi : (lane < i ? fmaf(-Lp[TRI(i) + lane], xi, x) : x);
   }
   *xout = x;
   return ok;
 }
 
-// ---- rank-one update / downdate of a Cholesky factor held in shared memory (lower triangle, stride 33):
+// ---- rank-one update / downdate of a Cholesky factor held in shared memory (packed lower triangle):
 // L L^T <- L L^T + sign * w w^T, lane i carries w_i.  Columns below `kstart` (the first non-zero of w) are untouched.
 // Returns false if a downdate loses positive definiteness (caller refactorises).
 __device__ __noinline__ bool warp_chol_rank1(float* L, float w, float sign, int kstart, int lane) {
   bool ok = true;
+  const int tl = TRI(lane);
 #pragma unroll 2
   for (int k = kstart; k < 32; k++) {
-    const float lkk = L[k * 33 + k];
+    const float lkk = L[TRI(k) + k];
     const float wk = __shfl_sync(FULLMASK, w, k);
     const float r2 = fmaf(sign * wk, wk, lkk * lkk);
     ok = ok && (r2 > 1e-12f * lkk * lkk);
     const float r = sqrtf(fmaxf(r2, 1e-30f));
     const float ilkk = 1.0f / lkk;
     const float c = r * ilkk, sn = wk * ilkk, ic = lkk / r;
-    if (lane == k) L[k * 33 + k] = r;
+    __syncwarp();
+    if (lane == k) L[tl + k] = r;
     else if (lane > k) {
-      const float lik = (L[lane * 33 + k] + sign * sn * w) * ic;
+      const float lik = (L[tl + k] + sign * sn * w) * ic;
       w = fmaf(c, w, -sn * lik);
-      L[lane * 33 + k] = lik;
+      L[tl + k] = lik;
     }
   }
   __syncwarp();
@@ -234,18 +237,162 @@ __device__ __noinline__ bool warp_chol_rank1(float* L, float w, float sign, int 
 }
 // solve L L^T x = b with an existing factor
 __device__ __noinline__ float warp_chol_resolve(const float* L, float b, int lane) {
-  const float myinv = 1.0f / L[lane * 33 + lane];
+  const int tl = TRI(lane);
+  const float myinv = 1.0f / L[tl + lane];
   float y = b;
 #pragma unroll 4
   for (int k = 0; k < 32; k++) {
     const float yk = __shfl_sync(FULLMASK, y * myinv, k);
-    y = lane == k ? yk : (lane > k ? fmaf(-L[lane * 33 + k], yk, y) : y);
+    y = lane == k ? yk : (lane > k ? fmaf(-L[tl + k], yk, y) : y);
   }
   float x = y;
 #pragma unroll 4
   for (int i = 31; i >= 0; i--) {
     const float xi = __shfl_sync(FULLMASK, x * myinv, i);
-    x = lane == i ? xi : (lane < i ? fmaf(-L[i * 33 + lane], xi, x) : x);
+    x = lane == i ? xi : (lane < i ? fmaf(-L[TRI(i) + lane], xi, x) : x);
   }
   return x;
+}
+
+// ---- tree-sparse SPD solve (mj_factorM / mj_solveLD of MuJoCo: M = L' D L over the dof tree), one warp.
+// Solves (M + diag(diag_add)) x = b where M is the joint-space inertia stored by (dof, ancestor depth) in S_MS:
+// entry d of row i is M[i, a_i(d)], a_i(d) = ancestor of dof i at depth d, entry depth(i) the diagonal.  Lane = dof.
+// Levels are eliminated deepest first; inside a chain a dof has one descendant per level, so the right-looking update
+// of a row is one scaled subtraction per level.  The only fan-out of the supported topology (the hub: the palm's last
+// dof with the finger chains below it) is handled as a block: the trunk rows receive the Schur complement of all
+// branch dofs at once before the hub level is eliminated.  All level loops are static, the row lives in registers.
+// Scratch (in S_H): scaled rows L[k][d] = M'[k, a_k(d)] / D_k, pivots D, published solution entries, trunk block.
+#define T_MAXD 10
+#define T_HUBD 5     // depth of the hub dof when there is one (compile-time so that the block step is emitted once)
+#define TS_LS (S_H)                 // 32 x MS_STRIDE scaled rows
+#define TS_D (TS_LS + 32 * MS_STRIDE)
+#define TS_X (TS_D + 32)
+#define TS_T (TS_X + 32)            // 21 trunk-block sums
+#define TS_P (S_UNION)              // 32 x 21 products of the branch dofs (callers run while the union region is free)
+__device__ __forceinline__ float rcp_nr(float x) {
+  const float y = 1.0f / x;
+  return y * fmaf(-x, y, 2.0f);
+}
+__device__ __forceinline__ int tbyte(unsigned w0, unsigned w1, unsigned w2, int i) {   // i is a compile-time constant
+  const unsigned w = i < 4 ? w0 : (i < 8 ? w1 : w2);
+  return (int)((w >> (8 * (i & 3))) & 0xffu);
+}
+__device__ __forceinline__ void ld_row12(float (&r)[12], const float* p) {
+  const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4), v2 = *reinterpret_cast<const float4*>(p + 8);
+  r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
+  r[8] = v2.x; r[9] = v2.y; r[10] = v2.z; r[11] = v2.w;
+}
+__device__ __noinline__ bool tree_solve(float* s, const DevModel& m, int lane, float diag_add, float b, float* xout) {
+  const int dep = lane < m.nv ? m.dof_depth[lane] : -1;
+  const int hd = m.hub_depth, maxd = m.tree_maxdepth;
+  const bool trunk = lane < m.nv && m.dof_is_trunk[lane];
+  const bool branch = (m.branch_mask >> lane) & 1u;
+  const int blo = m.branch_lo, bn = m.branch_n;
+  const unsigned a0 = m.dof_anc_at[lane][0], a1 = m.dof_anc_at[lane][1], a2 = m.dof_anc_at[lane][2];
+  const unsigned c0 = m.dof_desc_at[lane][0], c1 = m.dof_desc_at[lane][1], c2 = m.dof_desc_at[lane][2];
+  float* Ls = s + TS_LS;
+  float r[12];
+  ld_row12(r, s + S_MS + lane * MS_STRIDE);
+#pragma unroll
+  for (int d = 0; d < T_MAXD; d++) r[d] += d == dep ? diag_add : 0.f;
+  bool ok = true;
+  float dk = 1.f, dinv = 1.f;
+  // ---- factorisation, deepest level first.  Entries of r beyond the lane's depth are never used.
+#pragma unroll
+  for (int l = T_MAXD - 1; l >= 1; l--) {
+    if (l > maxd) continue;
+    if (l == T_HUBD && hd == T_HUBD) {
+      // Schur complement of the (already eliminated) branch dofs on the trunk block: each branch lane forms its 21
+      // products L[k][ti] D_k L[k][td] from registers, 21 lanes add them up, trunk lanes subtract their row.
+      if (branch) {
+        float w[T_HUBD + 1];
+#pragma unroll
+        for (int t = 0; t <= T_HUBD; t++) w[t] = r[t] * dk;
+        int e = 0;
+#pragma unroll
+        for (int ti = 0; ti <= T_HUBD; ti++)
+#pragma unroll
+          for (int td = 0; td <= ti; td++) s[TS_P + lane * 21 + e++] = w[ti] * r[td];
+      }
+      __syncwarp();
+      if (lane < 21) {
+        float acc0 = 0.f, acc1 = 0.f;
+        const float* P = s + TS_P + blo * 21 + lane;
+        int q = 0;
+#pragma unroll 4
+        for (; q + 1 < bn; q += 2) { acc0 += P[q * 21]; acc1 += P[(q + 1) * 21]; }
+        if (q < bn) acc0 += P[q * 21];
+        s[TS_T + lane] = acc0 + acc1;
+      }
+      __syncwarp();
+      if (trunk) {
+        const float* T = s + TS_T + dep * (dep + 1) / 2;
+#pragma unroll
+        for (int d = 0; d <= T_HUBD; d++)
+          if (d <= dep) r[d] -= T[d];
+      }
+    }
+    if (dep == l) {
+      dk = r[l];
+      ok = dk > F_MINVAL;
+      dinv = rcp_nr(fmaxf(dk, F_MINVAL));
+#pragma unroll
+      for (int d = 0; d < l; d++) r[d] *= dinv;
+      float4* o = reinterpret_cast<float4*>(Ls + lane * MS_STRIDE);
+      o[0] = make_float4(r[0], r[1], r[2], r[3]);
+      if (l > 4) o[1] = make_float4(r[4], r[5], r[6], r[7]);
+      if (l > 8) o[2] = make_float4(r[8], r[9], r[10], r[11]);
+      s[TS_D + lane] = dk;
+    }
+    __syncwarp();
+    const int k = tbyte(c0, c1, c2, l);
+    if (k != 0xff) {
+      float kr[12];
+      const float* kp = Ls + k * MS_STRIDE;
+      {
+        const float4 v0 = *reinterpret_cast<const float4*>(kp);
+        kr[0] = v0.x; kr[1] = v0.y; kr[2] = v0.z; kr[3] = v0.w;
+        if (l > 4) { const float4 v1 = *reinterpret_cast<const float4*>(kp + 4); kr[4] = v1.x; kr[5] = v1.y; kr[6] = v1.z; kr[7] = v1.w; }
+        if (l > 8) { const float4 v2 = *reinterpret_cast<const float4*>(kp + 8); kr[8] = v2.x; kr[9] = v2.y; kr[10] = v2.z; kr[11] = v2.w; }
+      }
+      const float t = kp[dep] * s[TS_D + k];
+#pragma unroll
+      for (int d = 0; d < l; d++) r[d] = fmaf(-t, kr[d], r[d]);
+    }
+  }
+  if (dep == 0) {
+    ok = r[0] > F_MINVAL;
+    dinv = rcp_nr(fmaxf(r[0], F_MINVAL));
+  }
+  // ---- x <- inv(L') x, deepest level first
+  float x = b;
+#pragma unroll
+  for (int l = T_MAXD - 1; l >= 1; l--) {
+    if (l == T_HUBD) {   // static; without a hub there are no branch lanes and the correction is zero
+      float corr = 0.f;
+#pragma unroll
+      for (int t = 0; t <= T_HUBD; t++) {
+        const float q = wsum(branch ? r[t] * x : 0.f);
+        if (t == dep) corr = q;
+      }
+      if (trunk) x -= corr;
+    }
+    if (l > maxd) continue;
+    if (dep == l) s[TS_X + lane] = x;
+    __syncwarp();
+    const int k = tbyte(c0, c1, c2, l);
+    if (k != 0xff) x = fmaf(-Ls[k * MS_STRIDE + dep], s[TS_X + k], x);
+  }
+  // ---- x <- inv(D) x ; x <- inv(L) x, root level first
+  x *= dinv;
+#pragma unroll
+  for (int l = 0; l < T_MAXD - 1; l++) {
+    if (l >= maxd) continue;
+    if (dep == l) s[TS_X + lane] = x;
+    __syncwarp();
+    if (dep > l) x = fmaf(-r[l], s[TS_X + tbyte(a0, a1, a2, l)], x);
+  }
+  __syncwarp();
+  *xout = x;
+  return __all_sync(FULLMASK, ok);
 }

@@ -57,6 +57,16 @@ struct DevModel {
   unsigned dof_anc[HN];          // strict ancestor dofs
   unsigned dof_premask[HN];      // dofs whose velocity is accumulated before cdof_dot of this dof is formed (mj_comVel)
   float dof_armature[HN], dof_damping[HN], dof_frictionloss[HN], fr_D[HN], fr_B[HN], fr_Rf[HN];
+  // dof-tree tables of the tree-sparse L'DL solver (dev_math.cuh: tree_solve).  Supported topology: chains plus at most one
+  // "hub" dof with several child chains (the palm's last dof); checked in build_dev_model.
+  int dof_depth[HN];             // number of ancestor dofs
+  unsigned dof_anc_at[HN][3];    // byte d: ancestor dof at depth d (d < depth), 0xff otherwise
+  unsigned dof_desc_at[HN][3];   // byte l: the unique descendant dof at depth l inside this dof's chain, 0xff if none / hub fan-out
+  int dof_is_trunk[HN];          // hub dof or one of its ancestors
+  unsigned dof_desc[HN];         // all descendant dofs
+  unsigned branch_mask;          // dofs below the hub
+  unsigned dof_depth_nib[4];     // 4-bit depth of dof j at bit 4*(j%8) of word j/8
+  int hub_depth, tree_maxdepth, branch_lo, branch_n;   // branch dofs are the contiguous range [branch_lo, branch_lo + branch_n)
   // geoms
   int geom_type[HN], geom_body[HN], geom_vertadr[HN], geom_vertnum[HN];
   float geom_pos[HN][3], geom_mat[HN][9], geom_size[HN][3], geom_rbound[HN];
@@ -94,9 +104,11 @@ struct DevModel {
 #define S_SEARCH (S_GRAD + HN)
 #define S_TMP (S_SEARCH + HN)          // 32
 #define S_FCON (S_TMP + HN)            // qfrc_constraint
-#define S_M (S_FCON + HN)              // 32*33
-#define S_H (S_M + 1056)               // 32*33 factorisation scratch
-#define S_CSUM (S_H + 1056)            // 19*12 contact sums -> 240
+#define MS_STRIDE 12                   // row stride of S_MS (16-byte aligned rows; entries beyond the depth stay zero)
+#define S_MS (S_FCON + HN)             // 32*12: M by (dof, ancestor depth): entry d of row i = M[i, ancestor of i at depth d]
+#define S_H (S_MS + 384)               // 528: packed lower triangle (row i at i(i+1)/2) of the Newton Hessian / its Cholesky factor;
+                                       //      scratch of tree_solve outside the Newton iterations
+#define S_CSUM (S_H + 528)             // 19*12 contact sums -> 240
 #define S_CCNT (S_CSUM + 240)          // 32 (as float counts)
 #define S_MISC (S_CCNT + HN)           // 16 scalars: ncon, nlim, nbasis, nedge, flags, ...
 #define S_COL (S_MISC + 16)            // 2 x 36: pivot-column broadcast buffer of warp_chol_solve

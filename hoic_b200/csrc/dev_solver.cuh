@@ -221,13 +221,40 @@ __device__ __noinline__ float rows_update(float* s, const DevModel& m, int lane,
   return cost;
 }
 
-// (M v)[lane]
-__device__ __forceinline__ float mul_M(const float* s, int lane, const float* v) {
-  const float* Mr = s + S_M + lane * 33;
-  float acc = 0.f;
+// (M v)[lane] with M stored by (dof, ancestor depth) (S_MS): own row over the ancestors, the column part from the one
+// descendant per level inside the lane's chain, and for the trunk (hub) dofs the sum over all branch dofs by warp sums.
+__device__ __noinline__ float mul_M(const float* s, const DevModel& m, int lane, const float* v) {
+  const bool on = lane < m.nv;
+  const int dep = on ? m.dof_depth[lane] : 0;
+  const bool trunk = on && m.dof_is_trunk[lane];
+  const bool branch = (m.branch_mask >> lane) & 1u;
+  const unsigned a0 = m.dof_anc_at[lane][0], a1 = m.dof_anc_at[lane][1], a2 = m.dof_anc_at[lane][2];
+  const unsigned c0 = m.dof_desc_at[lane][0], c1 = m.dof_desc_at[lane][1], c2 = m.dof_desc_at[lane][2];
+  float r[12];
+  ld_row12(r, s + S_MS + lane * MS_STRIDE);
+  const float vl = v[lane];
+  float acc0 = on ? s[S_MS + lane * MS_STRIDE + dep] * vl : vl, acc1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; j++) acc = fmaf(Mr[j], v[j], acc);
-  return acc;
+  for (int d = 0; d < T_MAXD - 1; d++) {
+    const int j = tbyte(a0, a1, a2, d);
+    if (j != 0xff) acc0 = fmaf(r[d], v[j], acc0);
+  }
+#pragma unroll
+  for (int l = 1; l < T_MAXD; l++) {
+    const int k = tbyte(c0, c1, c2, l);
+    if (k != 0xff) acc1 = fmaf(s[S_MS + k * MS_STRIDE + dep], v[k], acc1);
+  }
+  {
+    // unconditional (uniform control flow keeps the shuffles free of convergence barriers); no hub -> no branch lanes
+    float corr = 0.f;
+#pragma unroll
+    for (int t = 0; t <= T_HUBD; t++) {
+      const float q = wsum(branch ? r[t] * vl : 0.f);
+      if (t == dep) corr = q;
+    }
+    if (trunk) acc1 += corr;
+  }
+  return acc0 + acc1;
 }
 
 // gradient: grad = Ma - qfrc_smooth - J^T f (forces from the last rows_update).  Writes S_GRAD and S_FCON = J^T f,
@@ -285,9 +312,6 @@ __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int l
     w[0] = c00; w[1] = c0k[0]; w[2] = c0k[1]; w[3] = c0k[2]; w[4] = ckk[0]; w[5] = ckk[1]; w[6] = ckk[2];
   }
   __syncwarp();
-  float h[32];
-#pragma unroll
-  for (int j = 0; j < 32; j++) h[j] = s[S_M + lane * 33 + j];
   float diag = 0.f;
   {
     float f, c, k;
@@ -297,6 +321,22 @@ __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int l
   for (int r = 0; r < nlim; r++) {
     const int ri = rinfo[H_RLIM + r];
     if ((ri & 255) == lane && jar[H_RLIM + r] < 0.f) diag += s[U_D + H_RLIM + r];
+  }
+  // H starts as M + diag: lane i pulls row i (columns j <= i) out of the (dof, depth) storage
+  float* Hp = s + S_H;
+  float h[32];
+  {
+    const unsigned am = lane < m.nv ? (m.dof_anc[lane] | (1u << lane)) : 0u;
+    const unsigned n0 = m.dof_depth_nib[0], n1 = m.dof_depth_nib[1], n2 = m.dof_depth_nib[2], n3 = m.dof_depth_nib[3];
+    const float* Mr = s + S_MS + lane * MS_STRIDE;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const unsigned nw = j < 8 ? n0 : (j < 16 ? n1 : (j < 24 ? n2 : n3));
+      const int dj = (nw >> (4 * (j & 7))) & 15u;
+      float val = (am >> j) & 1u ? Mr[dj] : 0.f;
+      if (j == lane) val = lane < m.nv ? val + diag : 1.f;
+      h[j] = val;
+    }
   }
   for (int c = 0; c < ncon; c++) {
     const float* ci = s + U_CINFO + 8 * c;
@@ -330,12 +370,8 @@ __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int l
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 32; j++) s[S_H + lane * 33 + j] = h[j];
-  s[S_H + lane * 33 + lane] += diag;
-  __syncwarp();
   float dir;
-  const bool ok = warp_chol_solve(s + S_H, -s[S_GRAD + lane], &dir, lane, s + S_COL);
+  const bool ok = warp_chol_solve(h, Hp, -s[S_GRAD + lane], &dir, lane, s + S_COL);
   s[S_SEARCH + lane] = dir;
   __syncwarp();
   return ok;
@@ -360,7 +396,7 @@ __device__ __noinline__ void ls_eval(const float* s, const DevModel& m, int lane
 // exact minimiser of the piecewise-quadratic cost along `search` by safeguarded Newton on its derivative
 __device__ __noinline__ float line_search(float* s, const DevModel& m, int lane, int nbasis, int nedge, unsigned& evals) {
   const float sv = s[S_SEARCH + lane];
-  const float mv = mul_M(s, lane, s + S_SEARCH);
+  const float mv = mul_M(s, m, lane, s + S_SEARCH);
   s[S_MV + lane] = mv;
   mul_J(s, lane, nbasis, nedge, s + S_SEARCH, s + U_JV);
   const float qg1 = wsum(sv * (s[S_MA + lane] - s[S_SMOOTH + lane]));
@@ -398,7 +434,7 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
   float qacc = s[S_WARM + lane];
   s[S_QACC + lane] = qacc;
   __syncwarp();
-  float ma = mul_M(s, lane, s + S_QACC);
+  float ma = mul_M(s, m, lane, s + S_QACC);
   mul_J(s, lane, nbasis, nedge, s + S_QACC, s + U_JAR);
   for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JAR + r] -= s[U_AREF + r];
   __syncwarp();
@@ -412,7 +448,7 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
     s[S_QACC + lane] = qacc;
     for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JAR + r] = s[U_JV + r];
     __syncwarp();
-    ma = mul_M(s, lane, s + S_QACC);
+    ma = mul_M(s, m, lane, s + S_QACC);
   }
   s[S_MA + lane] = ma;
   __syncwarp();

@@ -56,11 +56,8 @@ __device__ __noinline__ bool phase_smooth(float* s, const DevModel& m, int lane)
   const float act = lane < m.nu ? s[S_CTRL + lane] : 0.f;   // motors on dofs 0..nu-1, gear 1
   const float fs = on ? passive - s[S_BIAS + lane] + s[S_QAPP + lane] + act : 0.f;
   s[S_SMOOTH + lane] = fs;
-#pragma unroll 4
-  for (int j = 0; j < 32; j++) s[S_H + lane * 33 + j] = s[S_M + lane * 33 + j];
-  __syncwarp();
   float as;
-  const bool ok = warp_chol_solve(s + S_H, fs, &as, lane, s + S_COL);
+  const bool ok = tree_solve(s, m, lane, 0.f, fs, &as);
   s[S_ASMOOTH + lane] = as;
   __syncwarp();
   return ok;
@@ -84,10 +81,10 @@ __device__ bool substep_core(float* s, const DevModel& m, int lane, bool record,
   int* misc = (int*)(s + S_MISC);
   if (!phase_forward(s, m, lane)) return false;
   vel_stage(s, m, lane);
+  if (!phase_smooth(s, m, lane)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
   if (record) record_contacts(s, m, lane);
   build_rows(s, m, lane);
-  if (!phase_smooth(s, m, lane)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   if (!phase_solve(s, m, lane, cnt)) return false;
   if (!euler_step(s, m, lane, nullptr)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   return true;
@@ -200,7 +197,9 @@ __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, c
 // H_WPB warps (= environments) per CTA.  The substep loop runs sim_step+1 times: pass -1 recomputes the forward of the
 // state that preceded the step (the "stale" quantities the env logic reads) with the same code as the
 // real substeps.  CTA barriers keep the warps of a CTA inside the same code region (instruction-cache locality).
-#define H_WPB 7
+#ifndef H_WPB
+#define H_WPB 8
+#endif
 #ifndef H_BARRIERS
 #define H_BARRIERS 0xff
 #endif
@@ -260,6 +259,12 @@ __global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __
     HB(5);
     if (ok) vel_stage(s, m, lane);
     HB(1);
+    if (ok && k >= 0) {
+      // qacc_smooth first: tree_solve borrows the union region, which the contacts occupy from collide() on
+      ok = phase_smooth(s, m, lane);
+      if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
+    }
+    HB(3);
     if (ok) {
       collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
       if (k + 1 < nsub) record_contacts(s, m, lane);
@@ -283,11 +288,6 @@ __global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __
       build_rows(s, m, lane);
     }
     HB(7);
-    if (ok) {
-      ok = phase_smooth(s, m, lane);
-      if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
-    }
-    HB(3);
     if (ok) ok = phase_solve(s, m, lane, cnt);
     HB(4);
     if (ok) {
@@ -422,7 +422,19 @@ __global__ void __launch_bounds__(32) k_forward_debug(BatchDev B, float* xpos, f
   const V3 org = ld3(s + S_ORG);
   if (xpos) for (int i = lane; i < m.nbody * 3; i += 32) xpos[(size_t)env * m.nbody * 3 + i] = s[S_XPOS + i] + comp(org, i % 3);
   if (xquat) for (int i = lane; i < m.nbody * 4; i += 32) xquat[(size_t)env * m.nbody * 4 + i] = s[S_XQUAT + i];
-  if (qM) for (int i = lane; i < 1024; i += 32) qM[(size_t)env * 1024 + i] = s[S_M + (i / 32) * 33 + i % 32];
+  if (qM) {
+    float* out = qM + (size_t)env * 1024;
+    for (int i = lane; i < 1024; i += 32) out[i] = (i / 32 == i % 32 && i / 32 >= m.nv) ? 1.f : 0.f;
+    __syncwarp();
+    if (lane < m.nv) {
+      int d = 0;
+      for (unsigned mk = m.dof_anc[lane] | (1u << lane); mk; mk &= mk - 1, d++) {
+        const int j = __ffs(mk) - 1;
+        out[lane * 32 + j] = s[S_MS + lane * MS_STRIDE + d];
+        out[j * 32 + lane] = s[S_MS + lane * MS_STRIDE + d];
+      }
+    }
+  }
   if (bias) bias[(size_t)env * 32 + lane] = s[S_BIAS + lane];
   if (ncon_out) {
     unsigned a = 0, b = 0;
@@ -693,6 +705,55 @@ bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<f
     double Bc;
     if (sr[0] > 0) { double tc = sr[0] > 2 * D.timestep ? sr[0] : 2 * (double)D.timestep; Bc = 2 / (dmax * tc); } else Bc = -sr[1] / dmax;
     D.fr_D[d] = (float)(1.0 / R); D.fr_B[d] = (float)Bc; D.fr_Rf[d] = (float)(R * dfl[d]);
+  }
+  // dof-tree tables for tree_solve (dev_math.cuh)
+  {
+    std::vector<int> depth(HN, -1);
+    std::vector<std::vector<int>> kids(nv);
+    int maxd = 0, hub = -1;
+    for (int d = 0; d < nv; d++) {
+      depth[d] = dparent[d] < 0 ? 0 : depth[dparent[d]] + 1;
+      if (dparent[d] >= d) { g_err = "dof parents must precede their children"; return false; }
+      if (dparent[d] >= 0) kids[dparent[d]].push_back(d);
+      if (depth[d] > maxd) maxd = depth[d];
+    }
+    for (int d = 0; d < nv; d++)
+      if (kids[d].size() > 1) {
+        if (hub >= 0) { g_err = "unsupported dof tree: more than one branching dof"; return false; }
+        hub = d;
+      }
+    if (maxd >= 10) { g_err = "unsupported dof tree: deeper than 10 dofs"; return false; }
+    D.tree_maxdepth = maxd;
+    D.hub_depth = hub >= 0 ? depth[hub] : -1;
+    if (hub >= 0 && depth[hub] != T_HUBD) { g_err = "unsupported dof tree: the branching dof must have 5 ancestors"; return false; }
+    D.branch_mask = 0;
+    for (int w = 0; w < 4; w++) D.dof_depth_nib[w] = 0;
+    for (int d = 0; d < nv; d++) D.dof_depth_nib[d / 8] |= (unsigned)depth[d] << (4 * (d % 8));
+    for (int i = 0; i < HN; i++) {
+      D.dof_depth[i] = i < nv ? depth[i] : -1;
+      D.dof_is_trunk[i] = 0;
+      D.dof_desc[i] = 0;
+      for (int w = 0; w < 3; w++) { D.dof_anc_at[i][w] = 0xffffffffu; D.dof_desc_at[i][w] = 0xffffffffu; }
+    }
+    auto setbyte = [](unsigned* w, int i, int v) { w[i / 4] = (w[i / 4] & ~(0xffu << (8 * (i % 4)))) | ((unsigned)v << (8 * (i % 4))); };
+    for (int d = hub; d >= 0; d = dparent[d]) D.dof_is_trunk[d] = 1;
+    for (int k = 0; k < nv; k++) {
+      bool below_hub = false;
+      for (int a = dparent[k]; a >= 0; a = dparent[a]) {
+        setbyte(D.dof_anc_at[k], depth[a], a);
+        D.dof_desc[a] |= 1u << k;
+        if (a == hub) below_hub = true;
+      }
+      if (below_hub) D.branch_mask |= 1u << k;
+      // k is the unique descendant at depth[k] of every ancestor up to (excluding) the hub
+      for (int a = dparent[k]; a >= 0 && !(below_hub && D.dof_is_trunk[a]); a = dparent[a]) setbyte(D.dof_desc_at[a], depth[k], k);
+    }
+    D.branch_lo = 0; D.branch_n = 0;
+    if (D.branch_mask) {
+      D.branch_lo = __builtin_ctz(D.branch_mask);
+      D.branch_n = __builtin_popcount(D.branch_mask);
+      if (D.branch_mask != (((D.branch_n < 32 ? (1u << D.branch_n) : 0u) - 1u) << D.branch_lo)) { g_err = "unsupported dof tree: dofs below the branching dof must be contiguous"; return false; }
+    }
   }
   for (int g = 0; g < ng; g++) {
     D.geom_type[g] = gtype[g]; D.geom_body[g] = gbody[g]; D.geom_vertadr[g] = gvadr[g]; D.geom_vertnum[g] = gvnum[g];
