@@ -159,6 +159,7 @@ __device__ __forceinline__ double warp_transpose_sum(double (&v)[32], int lane) 
 #define QP_G (QP_END + 2)                 // [380][6] float: wrench column of each variable (scaled torque rows)
 #define QP_RED (QP_G + 384 * 6)           // 32 doubles: reduced gradient / Hessian entries
 #define QP_NPER 12                        // variables per lane (380 / 32 rounded up)
+static_assert(((QP_RED + 1) & ~1) + 64 <= U_QP_END, "QP scratch exceeds the union region reserved for it");
 
 // returns rfc_score; fills rest[6]
 __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,

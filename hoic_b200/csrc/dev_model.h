@@ -126,18 +126,24 @@ struct DevModel {
 #define U_POS_END (U_CFRC + 192)
 // constraint stage (aliases the above; built after the velocity stage)
 #define U_CON (S_UNION)                // H_NCON * 16: pos3 frame9 dist cand(int) 2 pad
-#define U_B (U_CON + H_NCON * 16)      // H_NBASIS * 33 basis rows
-#define U_AREF (U_B + H_NBASIS * 33)   // H_NROW each:
+#define B_STRIDE 17                    // a contact Jacobian row touches <= 16 dofs (one hand chain + the object, or two
+                                       // finger chains): columns are stored compacted in dof order, see build_rows
+#define U_B (U_CON + H_NCON * 16)      // H_NBASIS * B_STRIDE basis rows
+#define U_AREF (U_B + H_NBASIS * B_STRIDE)   // H_NROW each:
 #define U_D (U_AREF + H_NROW)
 #define U_JAR (U_D + H_NROW)
 #define U_JV (U_JAR + H_NROW)
 #define U_FORCE (U_JV + H_NROW)
 #define U_RINFO (U_FORCE + H_NROW)     // int per row: limit rows dof | sign<<8 ; edge rows contact | edge<<8
 #define U_BV (U_RINFO + H_NROW)        // H_NBASIS: basis . v products
-#define U_CINFO (U_BV + H_NBASIS)      // H_NCON * 8: basis offset, nbasis, edge offset, nedge, mu0, mu1, D, pad
+#define U_BMASK (U_BV + H_NBASIS)      // H_NBASIS: dof mask of each basis row (bit i: dof i has a column)
+#define U_CINFO (U_BMASK + H_NBASIS)      // H_NCON * 8: basis offset, nbasis, edge offset, nedge, mu0, mu1, D, pad
 #define U_MPRQ (U_CINFO + H_NCON * 8)  // H_MAXCAND ints: queued MPR candidates
 #define U_CON_END (U_MPRQ + H_MAXCAND)
-#define S_TOTAL (U_CON_END > U_POS_END ? U_CON_END : U_POS_END)
+#define U_QP_END (S_UNION + 3168)      // residual-force QP scratch (dev_env.cuh: QP_*; static_assert there)
+#define U_TS_END (S_UNION + 32 * 21)   // tree_solve's branch products (dev_math.cuh: TS_P)
+#define S_MAX2(a, b) ((a) > (b) ? (a) : (b))
+#define S_TOTAL ((S_MAX2(S_MAX2(U_CON_END, U_POS_END), S_MAX2(U_QP_END, U_TS_END)) + 3) & ~3)
 
 // misc slots
 #define MI_NCON 0

@@ -98,6 +98,8 @@ __device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
     // jacobian difference column for dof = lane
     float sg = 0.f;
     if (lane < m.nv) sg = (float)((cd.chain2 >> lane) & 1u) - (float)((cd.chain1 >> lane) & 1u);
+    const unsigned cmask = cd.chain1 ^ cd.chain2;                       // dofs with a non-zero column
+    const int tcol = __popc(cmask & ((1u << lane) - 1u));               // compact column of this lane's dof
     V3 jp = v3(0, 0, 0), jr = v3(0, 0, 0);
     if (sg != 0.f) {
       const V3 off = pos - ld3(s + S_COM + 3 * m.dof_rootslot[lane]);
@@ -110,9 +112,9 @@ __device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
     float bvel[4];
     const float qvl = lane < m.nv ? qv[lane] : 0.f;
     for (int a = 0; a < nb; a++) {
-      s[U_B + (nbasis + a) * 33 + lane] = bcol[a];
+      if (sg != 0.f) s[U_B + (nbasis + a) * B_STRIDE + tcol] = bcol[a];
       bvel[a] = wsum(bcol[a] * qvl);
-      if (lane == 0) binfo[nbasis + a] = c | (a << 8);
+      if (lane == 0) { binfo[nbasis + a] = c | (a << 8); ((unsigned*)(s + U_BMASK))[nbasis + a] = cmask; }
     }
     // impedance / reference (identical on all lanes)
     const float imp = impedance(cd.solimp, dist, cd.includemargin);
@@ -145,7 +147,7 @@ __device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
     if (lane == 0) {
       ((int*)ci)[0] = nbasis; ((int*)ci)[1] = nb; ((int*)ci)[2] = nedge; ((int*)ci)[3] = ne;
       ci[4] = mu0; ci[5] = mu1; ci[6] = D;
-      ((unsigned*)ci)[7] = cd.chain1 | cd.chain2;
+      ((unsigned*)ci)[7] = cmask;
     }
     nbasis += nb;
     nedge += ne;
@@ -164,11 +166,20 @@ __device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
 __device__ __noinline__ void mul_J(float* s, int lane, int nbasis, int nedge, const float* v, float* out) {
   const int* rinfo = (const int*)(s + U_RINFO);
   for (int a = lane; a < nbasis; a += 32) {
-    const float* B = s + U_B + a * 33;
-    float acc = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; j++) acc = fmaf(B[j], v[j], acc);
-    s[U_BV + a] = acc;
+    const float* B = s + U_B + a * B_STRIDE;
+    float acc0 = 0.f, acc1 = 0.f;
+    unsigned mk = ((const unsigned*)(s + U_BMASK))[a];
+    for (int t = 0; mk; t += 2) {
+      const int j0 = __ffs(mk) - 1;
+      mk &= mk - 1;
+      acc0 = fmaf(B[t], v[j0], acc0);
+      if (mk) {
+        const int j1 = __ffs(mk) - 1;
+        mk &= mk - 1;
+        acc1 = fmaf(B[t + 1], v[j1], acc1);
+      }
+    }
+    s[U_BV + a] = acc0 + acc1;
   }
   __syncwarp();
   out[H_RFR + lane] = v[lane];
@@ -279,7 +290,10 @@ __device__ __noinline__ float newton_gradient(float* s, const DevModel& m, int l
     if ((ri & 255) == lane) jtf += ((ri >> 8) & 1 ? 1.f : -1.f) * s[U_FORCE + H_RLIM + r];
   }
 #pragma unroll 4
-  for (int a = 0; a < nbasis; a++) jtf = fmaf(s[U_B + a * 33 + lane], s[U_BV + a], jtf);
+  for (int a = 0; a < nbasis; a++) {
+    const unsigned mk = ((const unsigned*)(s + U_BMASK))[a];
+    if ((mk >> lane) & 1u) jtf = fmaf(s[U_B + a * B_STRIDE + __popc(mk & ((1u << lane) - 1u))], s[U_BV + a], jtf);
+  }
   const float grad = s[S_MA + lane] - s[S_SMOOTH + lane] - jtf;
   s[S_GRAD + lane] = grad;
   s[S_FCON + lane] = jtf;
@@ -345,28 +359,28 @@ __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int l
     const unsigned mask = ((const unsigned*)ci)[7];
     const float* w = s + U_CON + 16 * c;
     if (w[0] == 0.f) continue;   // no active edge
-    const float* B0 = s + U_B + bo * 33;
+    const float* B0 = s + U_B + bo * B_STRIDE;
+    const bool inm = (mask >> lane) & 1u;
+    const int tl = __popc(mask & ((1u << lane) - 1u));
     float al[4];
     {
-      const float b0 = B0[lane];
+      const float b0 = inm ? B0[tl] : 0.f;
       al[0] = w[0] * b0; al[1] = al[2] = al[3] = 0.f;
       for (int k = 1; k < nb; k++) {
-        const float bk = B0[k * 33 + lane];
+        const float bk = inm ? B0[k * B_STRIDE + tl] : 0.f;
         al[0] = fmaf(w[k], bk, al[0]);
         al[k] = w[k] * b0 + w[3 + k] * bk;
       }
     }
+    // columns of the contact's dofs only (the mask is uniform across the warp; rows outside it have al = 0)
 #pragma unroll
-    for (int jb = 0; jb < 16; jb++) {
-      if ((mask >> (2 * jb)) & 3u) {
-#pragma unroll
-        for (int jj = 0; jj < 2; jj++) {
-          const int j = 2 * jb + jj;
-          float acc = al[0] * B0[j];
-          if (nb > 1) { acc = fmaf(al[1], B0[33 + j], acc); acc = fmaf(al[2], B0[66 + j], acc); }
-          if (nb > 3) acc = fmaf(al[3], B0[99 + j], acc);
-          h[j] += acc;
-        }
+    for (int j = 0; j < 32; j++) {
+      if ((mask >> j) & 1u) {
+        const int tj = __popc(mask & ((1u << j) - 1u));
+        float acc = al[0] * B0[tj];
+        if (nb > 1) { acc = fmaf(al[1], B0[B_STRIDE + tj], acc); acc = fmaf(al[2], B0[2 * B_STRIDE + tj], acc); }
+        if (nb > 3) acc = fmaf(al[3], B0[3 * B_STRIDE + tj], acc);
+        h[j] += acc;
       }
     }
   }
@@ -483,8 +497,12 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
           const int ri = rinfo[r], c = ri & 255, ed = ri >> 8;
           const float* ci = s + U_CINFO + 8 * c;
           const int bo = ((const int*)ci)[0], ne = ((const int*)ci)[3];
-          w = s[U_B + bo * 33 + lane];
-          if (ne > 1) { const int k = ed / 2 + 1; const float mu = k <= 2 ? ci[4] : ci[5]; w += ((ed & 1) ? -mu : mu) * s[U_B + (bo + k) * 33 + lane]; }
+          const unsigned mask = ((const unsigned*)ci)[7];
+          if ((mask >> lane) & 1u) {
+            const int tl = __popc(mask & ((1u << lane) - 1u));
+            w = s[U_B + bo * B_STRIDE + tl];
+            if (ne > 1) { const int k = ed / 2 + 1; const float mu = k <= 2 ? ci[4] : ci[5]; w += ((ed & 1) ? -mu : mu) * s[U_B + (bo + k) * B_STRIDE + tl]; }
+          }
           w *= sd;
           k0 = __ffs(((const unsigned*)ci)[7]) - 1;
         }

@@ -198,7 +198,7 @@ __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, c
 // state that preceded the step (the "stale" quantities the env logic reads) with the same code as the
 // real substeps.  CTA barriers keep the warps of a CTA inside the same code region (instruction-cache locality).
 #ifndef H_WPB
-#define H_WPB 8
+#define H_WPB 10
 #endif
 #ifndef H_BARRIERS
 #define H_BARRIERS 0xff
@@ -808,6 +808,7 @@ bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<f
     c.dA_tran = (float)(binvw[2 * gbody[g1]] + binvw[2 * gbody[g2]]);
     c.dA_rot = (float)(binvw[2 * gbody[g1] + 1] + binvw[2 * gbody[g2] + 1]);
     c.chain1 = D.body_chain[gbody[g1]]; c.chain2 = D.body_chain[gbody[g2]];
+    if (__builtin_popcount(c.chain1 ^ c.chain2) > B_STRIDE - 1) { too_many = true; g_err = "a contact pair moves more than 16 dofs (compact Jacobian rows)"; return; }
     c.hand_slot = (g1 >= D.hand_geom0 && g1 <= D.hand_geom1 && g2 >= D.obj_geom0 && g2 <= D.obj_geom1) ? g1 - D.hand_geom0 : -1;
   };
   {
