@@ -154,104 +154,101 @@ __device__ __forceinline__ void cross_force(float* res, const float* vel, const 
   st3(res + 3, cross(w, b));
 }
 
-// ---- 32x32 SPD solve, one warp.  The matrix arrives in registers: lane i holds row i (only columns j <= i are used).
-// On exit the packed lower triangle Lp (row i at i(i+1)/2; conflict-free for lane-indexed rows because the triangular
-// numbers are distinct mod 32) holds the Cholesky factor L and *xout the solution of A x = b.  The pivot column is
-// broadcast through a small double-buffered shared array (`col`, 2 x 36 floats) instead of shuffles, the forward
-// substitution rides along as a 33rd column, and the back-substitution reads L^T from shared memory.  Returns false if
-// a pivot is not positive.  Rows/cols >= n must be identity.
-#define TRI(i) (((i) * ((i) + 1)) >> 1)
+// ---- 32x32 SPD solve, one warp, written as rolled loops over 4-wide panels so that the code stays a few hundred
+// instructions (the step kernel is instruction-fetch bound: an unrolled register-resident factorisation costs more in
+// fetch stalls than its arithmetic, profiles/README.md).  Storage: lower triangle in 4x4 blocks, block (I, J), J <= I, at
+// 16 * (I (I + 1) / 2 + J), row-major inside the block: 36 blocks = 576 floats, every row segment a float4.
+// Lane i owns row i.  Per panel p every lane factors the 4x4 diagonal block redundantly in registers (no shuffles on
+// the pivot chain), solves its own row segment against it, and applies the rank-4 update to the rest of its row.
+// The forward substitution rides along; the reciprocals of the diagonal land in the unused upper-triangle slots of
+// the diagonal blocks and feed the blocked back-substitution.  Rows / columns >= n must be identity.
+#define HB_OFF(I, J) (16 * ((((I) * ((I) + 1)) >> 1) + (J)))
+#define H_FLOATS 576
+__device__ __forceinline__ int hidx(int i, int j) { return HB_OFF(i >> 2, j >> 2) + 4 * (i & 3) + (j & 3); }
 __device__ __forceinline__ float rsqrt_nr(float x) {
   float y = rsqrtf(x);
   return y * fmaf(-0.5f * x * y, y, 1.5f);   // one Newton step on the MUFU estimate
 }
-__device__ __forceinline__ bool warp_chol_solve(float (&h)[32], float* Lp, float b, float* xout, int lane, float* col) {
-  bool ok = true;
+__device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int lane) {
+  const int I = lane >> 2, r = lane & 3;
   float yb = b;
-#pragma unroll
-  for (int k = 0; k < 32; k++) {
-    float* c = col + (k & 1) * 36;
-    c[lane] = h[k];
-    if (lane == k) c[32] = yb;
-    __syncwarp();
-    const float dkk = c[k];
-    ok = ok && (dkk > F_MINVAL);
-    const float inv = rsqrt_nr(fmaxf(dkk, F_MINVAL));
-    const float lik = h[k] * inv;
-    h[k] = lik;
-    const float yk = c[32] * inv;
-    yb = lane == k ? yk : (lane > k ? fmaf(-lik, yk, yb) : yb);
-    const float cc = -lik * inv;
-    // trailing update of this lane's row: h[j] -= A[i][k] A[j][k] / d, pivot column read as aligned float4 broadcasts
-#pragma unroll
-    for (int g = (k + 1) / 4; g < 8; g++) {
-      const float4 c4 = *reinterpret_cast<const float4*>(c + 4 * g);
-      if (4 * g + 0 > k) h[4 * g + 0] = fmaf(cc, c4.x, h[4 * g + 0]);
-      if (4 * g + 1 > k) h[4 * g + 1] = fmaf(cc, c4.y, h[4 * g + 1]);
-      if (4 * g + 2 > k) h[4 * g + 2] = fmaf(cc, c4.z, h[4 * g + 2]);
-      if (4 * g + 3 > k) h[4 * g + 3] = fmaf(cc, c4.w, h[4 * g + 3]);
-    }
-  }
-  const int tl = TRI(lane);
-#pragma unroll
-  for (int j = 0; j < 32; j++)
-    if (j <= lane) Lp[tl + j] = h[j];
-  __syncwarp();
-  // backward: L^T x = y
-  const float myinv = 1.0f / Lp[tl + lane];
-  float x = yb;
-#pragma unroll 8
-  for (int i = 31; i >= 0; i--) {
-    const float xi = __shfl_sync(FULLMASK, x * myinv, i);
-    x = lane == i ? xi : (lane < i ? fmaf(-Lp[TRI(i) + lane], xi, x) : x);
-  }
-  *xout = x;
-  return ok;
-}
-
-// ---- rank-one update / downdate of a Cholesky factor held in shared memory (packed lower triangle):
-// L L^T <- L L^T + sign * w w^T, lane i carries w_i.  Columns below `kstart` (the first non-zero of w) are untouched.
-// Returns false if a downdate loses positive definiteness (caller refactorises).
-__device__ __noinline__ bool warp_chol_rank1(float* L, float w, float sign, int kstart, int lane) {
   bool ok = true;
-  const int tl = TRI(lane);
-#pragma unroll 2
-  for (int k = kstart; k < 32; k++) {
-    const float lkk = L[TRI(k) + k];
-    const float wk = __shfl_sync(FULLMASK, w, k);
-    const float r2 = fmaf(sign * wk, wk, lkk * lkk);
-    ok = ok && (r2 > 1e-12f * lkk * lkk);
-    const float r = sqrtf(fmaxf(r2, 1e-30f));
-    const float ilkk = 1.0f / lkk;
-    const float c = r * ilkk, sn = wk * ilkk, ic = lkk / r;
+#pragma unroll 1
+  for (int p = 0; p < 8; p++) {
+    const float4* Dp = reinterpret_cast<const float4*>(A + HB_OFF(p, p));
+    const float4 r0 = Dp[0], r1 = Dp[1], r2 = Dp[2], r3 = Dp[3];
+    const float z0 = __shfl_sync(FULLMASK, yb, 4 * p), z1 = __shfl_sync(FULLMASK, yb, 4 * p + 1),
+                z2 = __shfl_sync(FULLMASK, yb, 4 * p + 2), z3 = __shfl_sync(FULLMASK, yb, 4 * p + 3);
+    const float d0 = r0.x;
+    const float i0 = rsqrt_nr(fmaxf(d0, F_MINVAL));
+    const float l10 = r1.x * i0, l20 = r2.x * i0, l30 = r3.x * i0;
+    const float d1 = fmaf(-l10, l10, r1.y);
+    const float i1 = rsqrt_nr(fmaxf(d1, F_MINVAL));
+    const float l21 = fmaf(-l20, l10, r2.y) * i1, l31 = fmaf(-l30, l10, r3.y) * i1;
+    const float d2 = fmaf(-l21, l21, fmaf(-l20, l20, r2.z));
+    const float i2 = rsqrt_nr(fmaxf(d2, F_MINVAL));
+    const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, r3.z)) * i2;
+    const float d3 = fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, r3.w)));
+    const float i3 = rsqrt_nr(fmaxf(d3, F_MINVAL));
+    ok = ok && d0 > F_MINVAL && d1 > F_MINVAL && d2 > F_MINVAL && d3 > F_MINVAL;
+    const float t0 = z0 * i0, t1 = fmaf(-l10, t0, z1) * i1, t2 = fmaf(-l21, t1, fmaf(-l20, t0, z2)) * i2,
+                t3 = fmaf(-l32, t2, fmaf(-l31, t1, fmaf(-l30, t0, z3))) * i3;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+    if (I >= p) {
+      float4* own = reinterpret_cast<float4*>(A + HB_OFF(I, p) + 4 * r);
+      const float4 a = *own;
+      x0 = a.x * i0;
+      x1 = fmaf(-x0, l10, a.y) * i1;
+      x2 = fmaf(-x1, l21, fmaf(-x0, l20, a.z)) * i2;
+      x3 = fmaf(-x2, l32, fmaf(-x1, l31, fmaf(-x0, l30, a.w))) * i3;
+      if (I == p) {
+        // rows of the diagonal block: entries right of the diagonal carry 1 / L_cc for the back-substitution
+        yb = r == 0 ? t0 : (r == 1 ? t1 : (r == 2 ? t2 : t3));
+        if (r == 0) { x1 = i1; x2 = i2; x3 = i3; }
+        else if (r == 1) { x2 = i0; x3 = 0.f; }
+        else if (r == 2) { x3 = 0.f; }
+      } else {
+        yb = fmaf(-x3, t3, fmaf(-x2, t2, fmaf(-x1, t1, fmaf(-x0, t0, yb))));
+      }
+      *own = make_float4(x0, x1, x2, x3);
+    }
     __syncwarp();
-    if (lane == k) L[tl + k] = r;
-    else if (lane > k) {
-      const float lik = (L[tl + k] + sign * sn * w) * ic;
-      w = fmaf(c, w, -sn * lik);
-      L[tl + k] = lik;
+    // rank-4 update of the row segments right of the panel: A[i][4 Jb + c] -= sum_k L[i][4p + k] L[4 Jb + c][4p + k]
+#pragma unroll 1
+    for (int Jb = p + 1; Jb <= I; Jb++) {
+      const float4* Lr = reinterpret_cast<const float4*>(A + HB_OFF(Jb, p));
+      float4* o = reinterpret_cast<float4*>(A + HB_OFF(I, Jb) + 4 * r);
+      float4 v = *o;
+      const float4 q0 = Lr[0], q1 = Lr[1], q2 = Lr[2], q3 = Lr[3];
+      v.x = fmaf(-x3, q0.w, fmaf(-x2, q0.z, fmaf(-x1, q0.y, fmaf(-x0, q0.x, v.x))));
+      v.y = fmaf(-x3, q1.w, fmaf(-x2, q1.z, fmaf(-x1, q1.y, fmaf(-x0, q1.x, v.y))));
+      v.z = fmaf(-x3, q2.w, fmaf(-x2, q2.z, fmaf(-x1, q2.y, fmaf(-x0, q2.x, v.z))));
+      v.w = fmaf(-x3, q3.w, fmaf(-x2, q3.z, fmaf(-x1, q3.y, fmaf(-x0, q3.x, v.w))));
+      *o = v;
+    }
+    __syncwarp();
+  }
+  // backward: L^T x = y, panel by panel from the bottom
+  float xb = yb;
+#pragma unroll 1
+  for (int p = 7; p >= 0; p--) {
+    const float4* Dp = reinterpret_cast<const float4*>(A + HB_OFF(p, p));
+    const float4 r0 = Dp[0], r1 = Dp[1], r2 = Dp[2], r3 = Dp[3];   // r0 = (L00, 1/L11, 1/L22, 1/L33), r1 = (L10, L11, 1/L00, 0)
+    const float z0 = __shfl_sync(FULLMASK, xb, 4 * p), z1 = __shfl_sync(FULLMASK, xb, 4 * p + 1),
+                z2 = __shfl_sync(FULLMASK, xb, 4 * p + 2), z3 = __shfl_sync(FULLMASK, xb, 4 * p + 3);
+    const float s3 = z3 * r0.w;
+    const float s2 = fmaf(-r3.z, s3, z2) * r0.z;
+    const float s1 = fmaf(-r3.y, s3, fmaf(-r2.y, s2, z1)) * r0.y;
+    const float s0 = fmaf(-r3.x, s3, fmaf(-r2.x, s2, fmaf(-r1.x, s1, z0))) * r1.z;
+    if (I == p) {
+      xb = r == 0 ? s0 : (r == 1 ? s1 : (r == 2 ? s2 : s3));
+    } else if (I < p) {
+      const float* cb = A + HB_OFF(p, I) + r;   // column r of block (p, I)
+      xb = fmaf(-cb[12], s3, fmaf(-cb[8], s2, fmaf(-cb[4], s1, fmaf(-cb[0], s0, xb))));
     }
   }
-  __syncwarp();
+  *xout = xb;
   return ok;
-}
-// solve L L^T x = b with an existing factor
-__device__ __noinline__ float warp_chol_resolve(const float* L, float b, int lane) {
-  const int tl = TRI(lane);
-  const float myinv = 1.0f / L[tl + lane];
-  float y = b;
-#pragma unroll 4
-  for (int k = 0; k < 32; k++) {
-    const float yk = __shfl_sync(FULLMASK, y * myinv, k);
-    y = lane == k ? yk : (lane > k ? fmaf(-L[tl + k], yk, y) : y);
-  }
-  float x = y;
-#pragma unroll 4
-  for (int i = 31; i >= 0; i--) {
-    const float xi = __shfl_sync(FULLMASK, x * myinv, i);
-    x = lane == i ? xi : (lane < i ? fmaf(-L[TRI(i) + lane], xi, x) : x);
-  }
-  return x;
 }
 
 // ---- tree-sparse SPD solve (mj_factorM / mj_solveLD of MuJoCo: M = L' D L over the dof tree), one warp.
@@ -267,8 +264,8 @@ __device__ __noinline__ float warp_chol_resolve(const float* L, float b, int lan
 #define TS_LS (S_H)                 // 32 x MS_STRIDE scaled rows
 #define TS_D (TS_LS + 32 * MS_STRIDE)
 #define TS_X (TS_D + 32)
-#define TS_T (TS_X + 32)            // 21 trunk-block sums
-#define TS_P (S_UNION)              // 32 x 21 products of the branch dofs (callers run while the union region is free)
+#define TS_T (TS_X + 32)            // 21 trunk-block sums (TS_T + 21 <= S_H + H_FLOATS)
+#define TS_P (S_UNION)              // 32 x 21 products of the branch dofs (default scratch: callers run while the union region is free)
 __device__ __forceinline__ float rcp_nr(float x) {
   const float y = 1.0f / x;
   return y * fmaf(-x, y, 2.0f);
@@ -282,7 +279,10 @@ __device__ __forceinline__ void ld_row12(float (&r)[12], const float* p) {
   r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
   r[8] = v2.x; r[9] = v2.y; r[10] = v2.z; r[11] = v2.w;
 }
-__device__ __noinline__ bool tree_solve(float* s, const DevModel& m, int lane, float diag_add, float b, float* xout) {
+// `rows` = row storage to factorise (S_MS layout; may alias TS_LS: every lane reads only its own row before anything is
+// written), `tsp` = 32 x 21 floats of scratch for the hub block.
+__device__ __noinline__ bool tree_solve_at(float* s, const DevModel& m, int lane, const float* rows, float* tsp, float diag_add, float b,
+                                           float* xout) {
   const int dep = lane < m.nv ? m.dof_depth[lane] : -1;
   const int hd = m.hub_depth, maxd = m.tree_maxdepth;
   const bool trunk = lane < m.nv && m.dof_is_trunk[lane];
@@ -292,9 +292,10 @@ __device__ __noinline__ bool tree_solve(float* s, const DevModel& m, int lane, f
   const unsigned c0 = m.dof_desc_at[lane][0], c1 = m.dof_desc_at[lane][1], c2 = m.dof_desc_at[lane][2];
   float* Ls = s + TS_LS;
   float r[12];
-  ld_row12(r, s + S_MS + lane * MS_STRIDE);
+  ld_row12(r, rows + lane * MS_STRIDE);
 #pragma unroll
   for (int d = 0; d < T_MAXD; d++) r[d] += d == dep ? diag_add : 0.f;
+  __syncwarp();
   bool ok = true;
   float dk = 1.f, dinv = 1.f;
   // ---- factorisation, deepest level first.  Entries of r beyond the lane's depth are never used.
@@ -312,12 +313,12 @@ __device__ __noinline__ bool tree_solve(float* s, const DevModel& m, int lane, f
 #pragma unroll
         for (int ti = 0; ti <= T_HUBD; ti++)
 #pragma unroll
-          for (int td = 0; td <= ti; td++) s[TS_P + lane * 21 + e++] = w[ti] * r[td];
+          for (int td = 0; td <= ti; td++) tsp[lane * 21 + e++] = w[ti] * r[td];
       }
       __syncwarp();
       if (lane < 21) {
         float acc0 = 0.f, acc1 = 0.f;
-        const float* P = s + TS_P + blo * 21 + lane;
+        const float* P = tsp + blo * 21 + lane;
         int q = 0;
 #pragma unroll 4
         for (; q + 1 < bn; q += 2) { acc0 += P[q * 21]; acc1 += P[(q + 1) * 21]; }
@@ -395,4 +396,7 @@ __device__ __noinline__ bool tree_solve(float* s, const DevModel& m, int lane, f
   __syncwarp();
   *xout = x;
   return __all_sync(FULLMASK, ok);
+}
+__device__ __forceinline__ bool tree_solve(float* s, const DevModel& m, int lane, float diag_add, float b, float* xout) {
+  return tree_solve_at(s, m, lane, s + S_MS, s + TS_P, diag_add, b, xout);
 }

@@ -106,13 +106,12 @@ struct DevModel {
 #define S_FCON (S_TMP + HN)            // qfrc_constraint
 #define MS_STRIDE 12                   // row stride of S_MS (16-byte aligned rows; entries beyond the depth stay zero)
 #define S_MS (S_FCON + HN)             // 32*12: M by (dof, ancestor depth): entry d of row i = M[i, ancestor of i at depth d]
-#define S_H (S_MS + 384)               // 528: packed lower triangle (row i at i(i+1)/2) of the Newton Hessian / its Cholesky factor;
-                                       //      scratch of tree_solve outside the Newton iterations
-#define S_CSUM (S_H + 528)             // 19*12 contact sums -> 240
+#define S_H (S_MS + 384)               // 576: lower triangle of the Newton Hessian / its Cholesky factor in 4x4 blocks
+                                       //      (dev_math.cuh: warp_chol_solve); scratch of tree_solve outside the Newton iterations
+#define S_CSUM (S_H + 576)             // 19*12 contact sums -> 240
 #define S_CCNT (S_CSUM + 240)          // 32 (as float counts)
 #define S_MISC (S_CCNT + HN)           // 16 scalars: ncon, nlim, nbasis, nedge, flags, ...
-#define S_COL (S_MISC + 16)            // 2 x 36: pivot-column broadcast buffer of warp_chol_solve
-#define S_UNION (S_COL + 72)
+#define S_UNION (S_MISC + 16)
 // position / velocity stage temporaries
 #define U_XMAT (S_UNION)               // 32*9
 #define U_XAXIS (U_XMAT + 288)         // 32*3 per joint

@@ -8,11 +8,19 @@
 
 #ifdef H_STATS
 __device__ unsigned long long g_stats[8];
+__device__ unsigned long long g_nst[64];   // [0..7] solves by iteration count, [8..15] their cycles, [16..] cycles by part
+#define NST_T(i) do { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_nst[16 + (i)], (unsigned long long)(t_ - nst_t)); nst_t = t_; } while (0)
+#else
+#define NST_T(i) do { } while (0)
 #endif
-#define H_NCHG 3           // state changes handled by rank-one factor updates before a full refactorisation
 #define U_BINFO (U_MPRQ)   // basis row -> contact | k<<8 (the MPR queue is dead once contacts exist)
 #define U_CW (U_CON)       // per-contact Hessian weights reuse the contact records' slots 14..15 + CINFO pad
 
+// general power-law sigmoid of mj_makeImpedance; out of line: powf is large and the models here all use power 2
+__device__ __noinline__ float impedance_pow(float x, float s3, float s4) {
+  if (x <= s3) return powf(x, s4) / powf(s3, s4 - 1.f);
+  return 1.f - powf(1.f - x, s4) / powf(1.f - s3, s4 - 1.f);
+}
 __device__ __forceinline__ float impedance(const float* si, float pos, float margin) {
   float s0 = fminf(0.9999f, fmaxf(0.0001f, si[0])), s1 = fminf(0.9999f, fmaxf(0.0001f, si[1]));
   float s2 = fmaxf(0.f, si[2]), s3 = fminf(0.9999f, fmaxf(0.0001f, si[3])), s4 = fmaxf(1.f, si[4]);
@@ -20,8 +28,8 @@ __device__ __forceinline__ float impedance(const float* si, float pos, float mar
   float x = fabsf((pos - margin) / s2), y;
   if (x >= 1.f || x <= 0.f) return x >= 1.f ? s1 : s0;
   if (s4 == 1.f) y = x;
-  else if (x <= s3) y = powf(x, s4) / powf(s3, s4 - 1.f);
-  else y = 1.f - powf(1.f - x, s4) / powf(1.f - s3, s4 - 1.f);
+  else if (s4 == 2.f) y = x <= s3 ? x * x / s3 : 1.f - (1.f - x) * (1.f - x) / (1.f - s3);
+  else y = impedance_pow(x, s3, s4);
   return s0 + y * (s1 - s0);
 }
 __device__ __forceinline__ void kb_from_solref(const float* sr, const float* si, float timestep, float& K, float& B) {
@@ -301,13 +309,13 @@ __device__ __noinline__ float newton_gradient(float* s, const DevModel& m, int l
   return wsum(grad * grad);
 }
 
-// Newton direction: H = M + J^T D_active J (row `lane` in registers), Cholesky, search = -H^-1 grad
-__device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int lane, int nlim, int ncon, int nbasis, int nedge) {
+// Per-contact Hessian weights of the currently quadratic edge rows (written over contact record slots 0..6) and the
+// diagonal contribution of the friction-loss / limit rows (returned, lane = dof).
+__device__ __noinline__ float newton_weights(float* s, const DevModel& m, int lane, int nlim, int ncon) {
   const int* rinfo = (const int*)(s + U_RINFO);
   const float* jar = s + U_JAR;
-  (void)nbasis; (void)nedge;
   for (int c = lane; c < ncon; c += 32) {
-    // per-contact Hessian weights: w[0] = C00, w[1..3] = C0k, w[4..6] = Ckk (contact record slots 0..6 are free now)
+    // w[0] = C00, w[1..3] = C0k, w[4..6] = Ckk
     float* ci = s + U_CINFO + 8 * c;
     const int eo = H_RCON + ((const int*)ci)[2], ne = ((const int*)ci)[3];
     const float D = ci[6];
@@ -325,7 +333,6 @@ __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int l
     }
     w[0] = c00; w[1] = c0k[0]; w[2] = c0k[1]; w[3] = c0k[2]; w[4] = ckk[0]; w[5] = ckk[1]; w[6] = ckk[2];
   }
-  __syncwarp();
   float diag = 0.f;
   {
     float f, c, k;
@@ -336,56 +343,65 @@ __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int l
     const int ri = rinfo[H_RLIM + r];
     if ((ri & 255) == lane && jar[H_RLIM + r] < 0.f) diag += s[U_D + H_RLIM + r];
   }
-  // H starts as M + diag: lane i pulls row i (columns j <= i) out of the (dof, depth) storage
-  float* Hp = s + S_H;
-  float h[32];
+  __syncwarp();
+  return diag;
+}
+
+// Newton direction: H = M + J^T D_active J assembled in shared memory (lane i owns row i, columns j <= i, blocked
+// layout of warp_chol_solve), Cholesky, search = -H^-1 grad.  All loops are rolled: see warp_chol_solve.
+__device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int lane, int ncon, float diag) {
+  float* A = s + S_H;
   {
-    const unsigned am = lane < m.nv ? (m.dof_anc[lane] | (1u << lane)) : 0u;
-    const unsigned n0 = m.dof_depth_nib[0], n1 = m.dof_depth_nib[1], n2 = m.dof_depth_nib[2], n3 = m.dof_depth_nib[3];
-    const float* Mr = s + S_MS + lane * MS_STRIDE;
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      const unsigned nw = j < 8 ? n0 : (j < 16 ? n1 : (j < 24 ? n2 : n3));
-      const int dj = (nw >> (4 * (j & 7))) & 15u;
-      float val = (am >> j) & 1u ? Mr[dj] : 0.f;
-      if (j == lane) val = lane < m.nv ? val + diag : 1.f;
-      h[j] = val;
-    }
+    const int I = lane >> 2, r = lane & 3;
+#pragma unroll 1
+    for (int J = 0; J <= I; J++) *reinterpret_cast<float4*>(A + HB_OFF(I, J) + 4 * r) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  // M + diag: entry d of the (dof, depth) row is M[lane, ancestor at depth d]; ancestors come in increasing index
+  if (lane < m.nv) {
+    const float* Mr = s + S_MS + lane * MS_STRIDE;
+    int d = 0;
+#pragma unroll 1
+    for (unsigned mk = m.dof_anc[lane]; mk; mk &= mk - 1, d++) A[hidx(lane, __ffs(mk) - 1)] = Mr[d];
+    A[hidx(lane, lane)] = Mr[d] + diag;
+  } else {
+    A[hidx(lane, lane)] = 1.f;
+  }
+#pragma unroll 1
   for (int c = 0; c < ncon; c++) {
     const float* ci = s + U_CINFO + 8 * c;
     const int bo = ((const int*)ci)[0], nb = ((const int*)ci)[1];
-    if (nb == 0) continue;
-    const unsigned mask = ((const unsigned*)ci)[7];
     const float* w = s + U_CON + 16 * c;
-    if (w[0] == 0.f) continue;   // no active edge
+    if (nb == 0 || w[0] == 0.f) continue;   // overflowed contact / no active edge
+    const unsigned mask = ((const unsigned*)ci)[7];
+    if (!((mask >> lane) & 1u)) continue;
     const float* B0 = s + U_B + bo * B_STRIDE;
-    const bool inm = (mask >> lane) & 1u;
     const int tl = __popc(mask & ((1u << lane) - 1u));
-    float al[4];
-    {
-      const float b0 = inm ? B0[tl] : 0.f;
-      al[0] = w[0] * b0; al[1] = al[2] = al[3] = 0.f;
-      for (int k = 1; k < nb; k++) {
-        const float bk = inm ? B0[k * B_STRIDE + tl] : 0.f;
-        al[0] = fmaf(w[k], bk, al[0]);
-        al[k] = w[k] * b0 + w[3 + k] * bk;
+    const float b0 = B0[tl];
+    float al0 = w[0] * b0, al1 = 0.f, al2 = 0.f, al3 = 0.f;
+    if (nb > 1) {
+      const float b1 = B0[B_STRIDE + tl], b2 = B0[2 * B_STRIDE + tl];
+      al0 = fmaf(w[1], b1, fmaf(w[2], b2, al0));
+      al1 = fmaf(w[4], b1, w[1] * b0);
+      al2 = fmaf(w[5], b2, w[2] * b0);
+      if (nb > 3) {
+        const float b3 = B0[3 * B_STRIDE + tl];
+        al0 = fmaf(w[3], b3, al0);
+        al3 = fmaf(w[6], b3, w[3] * b0);
       }
     }
-    // columns of the contact's dofs only (the mask is uniform across the warp; rows outside it have al = 0)
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      if ((mask >> j) & 1u) {
-        const int tj = __popc(mask & ((1u << j) - 1u));
-        float acc = al[0] * B0[tj];
-        if (nb > 1) { acc = fmaf(al[1], B0[B_STRIDE + tj], acc); acc = fmaf(al[2], B0[2 * B_STRIDE + tj], acc); }
-        if (nb > 3) acc = fmaf(al[3], B0[3 * B_STRIDE + tj], acc);
-        h[j] += acc;
-      }
+    // columns j <= lane of the contact's dofs; the compact column index runs with the set bits
+    int tj = 0;
+#pragma unroll 1
+    for (unsigned mk = mask & (0xffffffffu >> (31 - lane)); mk; mk &= mk - 1, tj++) {
+      float acc = al0 * B0[tj];
+      if (nb > 1) { acc = fmaf(al1, B0[B_STRIDE + tj], acc); acc = fmaf(al2, B0[2 * B_STRIDE + tj], acc); }
+      if (nb > 3) acc = fmaf(al3, B0[3 * B_STRIDE + tj], acc);
+      A[hidx(lane, __ffs(mk) - 1)] += acc;
     }
   }
+  __syncwarp();
   float dir;
-  const bool ok = warp_chol_solve(h, Hp, -s[S_GRAD + lane], &dir, lane, s + S_COL);
+  const bool ok = warp_chol_solve(A, -s[S_GRAD + lane], &dir, lane);
   s[S_SEARCH + lane] = dir;
   __syncwarp();
   return ok;
@@ -444,6 +460,10 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON], nbasis = misc[MI_NBASIS], nedge = misc[MI_NEDGE];
   const float scale = 1.0f / (m.meaninertia * (float)(m.nv > 1 ? m.nv : 1));
   const float asm_ = s[S_ASMOOTH + lane], fsm = s[S_SMOOTH + lane];
+#ifdef H_STATS
+  long long nst_t = clock64();
+  const long long nst_t0 = nst_t;
+#endif
   // warm start selection
   float qacc = s[S_WARM + lane];
   s[S_QACC + lane] = qacc;
@@ -470,12 +490,10 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
   bool ok = true;
   unsigned iter = 0;
   float oldcost = cost;
-  // rows whose state changed during the last move (at most H_NCHG are tracked; more -> full refactorisation)
-  int nchg = -1, chrow[H_NCHG];
-  float chsign[H_NCHG];
-  const int* rinfo = (const int*)(s + U_RINFO);
+  NST_T(0);   // warm start / initial cost
   for (;;) {
     const float g2 = newton_gradient(s, m, lane, nlim, nbasis);
+    NST_T(1);
     if (iter > 0) {
       const float improvement = scale * (oldcost - cost), gradn = scale * sqrtf(g2);
       // float32 noise floor on the cost difference replaces MuJoCo's absolute 1e-8 (see DESIGN.md "precision")
@@ -483,42 +501,15 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
       if (improvement < tol || gradn < m.tolerance) break;
     }
     if (iter >= (unsigned)m.iterations) break;
-    bool incremental = nchg >= 0 && nchg <= H_NCHG;
-    if (incremental) {
-      // update the factor of the previous Hessian by the rows that entered (+) or left (-) the quadratic set
-      for (int q = 0; q < nchg && incremental; q++) {
-        const int r = chrow[q];
-        const float sd = sqrtf(s[U_D + r]);
-        float w = 0.f;
-        int k0;
-        if (r < H_RLIM) { k0 = r; if (lane == r) w = sd; }
-        else if (r < H_RCON) { k0 = rinfo[r] & 255; if (lane == k0) w = sd; }
-        else {
-          const int ri = rinfo[r], c = ri & 255, ed = ri >> 8;
-          const float* ci = s + U_CINFO + 8 * c;
-          const int bo = ((const int*)ci)[0], ne = ((const int*)ci)[3];
-          const unsigned mask = ((const unsigned*)ci)[7];
-          if ((mask >> lane) & 1u) {
-            const int tl = __popc(mask & ((1u << lane) - 1u));
-            w = s[U_B + bo * B_STRIDE + tl];
-            if (ne > 1) { const int k = ed / 2 + 1; const float mu = k <= 2 ? ci[4] : ci[5]; w += ((ed & 1) ? -mu : mu) * s[U_B + (bo + k) * B_STRIDE + tl]; }
-          }
-          w *= sd;
-          k0 = __ffs(((const unsigned*)ci)[7]) - 1;
-        }
-        incremental = warp_chol_rank1(s + S_H, w, chsign[q], k0, lane);
-      }
-      if (incremental) {
-        const float dir = warp_chol_resolve(s + S_H, -s[S_GRAD + lane], lane);
-        s[S_SEARCH + lane] = dir;
-        __syncwarp();
-      }
-    }
-    if (!incremental) {
-      ok = newton_direction(s, m, lane, nlim, ncon, nbasis, nedge);
+    {
+      // full refactorisation every iteration: the blocked Cholesky is cheaper than tracking rank-one changes
+      const float diag = newton_weights(s, m, lane, nlim, ncon);
+      ok = newton_direction(s, m, lane, ncon, diag);
       if (!ok) break;
+      NST_T(3);
     }
     const float alpha = line_search(s, m, lane, nbasis, nedge, ls_evals);
+    NST_T(4);
     if (alpha == 0.f) break;
     qacc += alpha * s[S_SEARCH + lane];
     ma += alpha * s[S_MV + lane];
@@ -526,29 +517,12 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
     s[S_MA + lane] = ma;
     // move along the search direction; note whether any row changed state (active set / friction branch)
     bool changed = false;
-    nchg = 0;
-    for (int r0 = 0; r0 < H_RCON + nedge; r0 += 32) {
-      const int r = r0 + lane;
-      bool ch = false, enter = false;
-      if (r < H_RCON + nedge) {
-        const float x0 = s[U_JAR + r], x1 = x0 + alpha * s[U_JV + r];
-        s[U_JAR + r] = x1;
-        if (s[U_D + r] != 0.f) {
-          bool q0, q1;
-          if (r < H_RLIM) { const float Rf = m.fr_Rf[r]; q0 = fabsf(x0) < Rf; q1 = fabsf(x1) < Rf; ch = ((x0 <= -Rf) != (x1 <= -Rf)) || ((x0 >= Rf) != (x1 >= Rf)); }
-          else { q0 = x0 < 0.f; q1 = x1 < 0.f; ch = q0 != q1; }
-          enter = q1 && !q0;
-          // a friction row jumping from one linear branch to the other changes the forces but not the Hessian
-          if (ch && q0 == q1) { changed = true; ch = false; }
-        }
-      }
-      unsigned bal = __ballot_sync(FULLMASK, ch);
-      const unsigned ent = __ballot_sync(FULLMASK, enter);
-      if (bal) changed = true;
-      for (; bal; bal &= bal - 1) {
-        const int bit = __ffs(bal) - 1;
-        if (nchg < H_NCHG) { chrow[nchg] = r0 + bit; chsign[nchg] = (ent >> bit) & 1u ? 1.f : -1.f; }
-        nchg++;
+    for (int r = lane; r < H_RCON + nedge; r += 32) {
+      const float x0 = s[U_JAR + r], x1 = x0 + alpha * s[U_JV + r];
+      s[U_JAR + r] = x1;
+      if (s[U_D + r] != 0.f) {
+        if (r < H_RLIM) { const float Rf = m.fr_Rf[r]; changed = changed || ((x0 <= -Rf) != (x1 <= -Rf)) || ((x0 >= Rf) != (x1 >= Rf)); }
+        else changed = changed || ((x0 < 0.f) != (x1 < 0.f));
       }
     }
     changed = __any_sync(FULLMASK, changed);
@@ -556,6 +530,7 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
     oldcost = cost;
     cost = rows_update(s, m, lane, nedge, s + U_JAR, true) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
     iter++;
+    NST_T(5);
     if (!changed) {
       // no row changed state along the step: the cost was exactly quadratic there and the Newton step with the exact
       // line search landed on its minimiser, which is the optimum of the convex problem.  Refresh J^T f and stop.
@@ -563,6 +538,9 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
       break;
     }
   }
+#ifdef H_STATS
+  if (lane == 0) { const int b_ = iter < 7 ? (int)iter : 7; atomicAdd(&g_nst[b_], 1ull); atomicAdd(&g_nst[8 + b_], (unsigned long long)(clock64() - nst_t0)); }
+#endif
   iters_out += iter;
   // S_FCON holds J^T f of the final forces (written by newton_direction)
   return ok;

@@ -200,11 +200,22 @@ __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, c
 #ifndef H_WPB
 #define H_WPB 10
 #endif
+#ifndef H_CPS
+#define H_CPS 1         // resident CTAs per SM the register budget is sized for
+#endif
 #ifndef H_BARRIERS
 #define H_BARRIERS 0xff
 #endif
+#ifdef H_PROF
+// per-phase cycle accounting: own work (phase start -> arrival at the next barrier) and wait (arrival -> release)
+__device__ unsigned long long g_prof[16][2];
+#define HB(n) do { const long long t_arr = clock64(); if (H_BARRIERS & (1 << (n))) __syncthreads(); const long long t_rel = clock64(); \
+    if (lane == 0 && ok) { atomicAdd(&g_prof[prof_phase][0], (unsigned long long)(t_arr - prof_t0)); atomicAdd(&g_prof[prof_phase][1], (unsigned long long)(t_rel - t_arr)); } \
+    prof_phase = (n); prof_t0 = t_rel; } while (0)
+#else
 #define HB(n) do { if (H_BARRIERS & (1 << (n))) __syncthreads(); } while (0)
-__global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __restrict__ actions, StepOut out) {
+#endif
+__global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const float* __restrict__ actions, StepOut out) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * H_WPB + warp;
@@ -235,6 +246,10 @@ __global__ void __launch_bounds__(32 * H_WPB) k_step(BatchDev B, const float* __
   V3 vf = v3(0, 0, 0), vt = v3(0, 0, 0);
   float pq = cq, pq32 = cq32, pv = cv;
   bool ok = live;      // false once this env failed (or the slot is padding): skips work, keeps hitting the barriers
+#ifdef H_PROF
+  int prof_phase = 8;
+  long long prof_t0 = clock64();
+#endif
   const int nsub = m.sim_step;
   for (int k = -1; k < nsub; k++) {
     HB(0);
@@ -1047,8 +1062,19 @@ extern "C" int hoic_get_counters(hoic_batch* b, hoic_counters* out_host) {
   out_host->env_steps = h[0]; out_host->substeps = h[1]; out_host->ncon = h[2]; out_host->nefc = h[3]; out_host->newton_iters = h[4];
   out_host->ls_evals = h[5]; out_host->mpr_calls = h[6]; out_host->mpr_iters = h[7]; out_host->qp_iters = h[8];
   out_host->fail_physics = h[9]; out_host->fail_overflow = h[10]; out_host->chol_calls = h[11];
+#ifdef H_PROF
+  { unsigned long long pr[16][2]; cudaMemcpyFromSymbol(pr, g_prof, sizeof pr);
+    static const char* nm[16] = {"0:pd+applyft", "1:smooth", "2:build_rows", "3:collide", "4:euler", "5:vel", "6:pos", "7:solve", "8:prologue/tail-k-1"};
+    double tot = 0; for (int i = 0; i < 9; i++) tot += (double)pr[i][0] + (double)pr[i][1];
+    for (int i = 0; i < 9; i++) fprintf(stderr, "H_PROF after-barrier %-20s work %5.1f%%  wait %5.1f%%\n", nm[i], 100.0 * pr[i][0] / tot, 100.0 * pr[i][1] / tot); }
+#endif
 #ifdef H_STATS
-  { unsigned long long st[8]; cudaMemcpyFromSymbol(st, g_stats, sizeof st); fprintf(stderr, "H_STATS iters_with_change=%llu changed_fric=%llu changed_con=%llu le4=%llu only_fric=%llu\n", st[0], st[1], st[2], st[3], st[4]); }
+  { unsigned long long ns[64]; cudaMemcpyFromSymbol(ns, g_nst, sizeof ns);
+    for (int i = 0; i < 8; i++) fprintf(stderr, "H_STATS solves with %d iters: %llu  avg cycles %.0f\n", i, ns[i], ns[i] ? (double)ns[8 + i] / ns[i] : 0.0);
+    static const char* pn[6] = {"init", "gradient", "incremental", "full direction", "line search", "move+cost"};
+    double tot = 0; for (int i = 0; i < 6; i++) tot += (double)ns[16 + i];
+    for (int i = 0; i < 6; i++) fprintf(stderr, "H_STATS newton part %-16s %5.1f%%\n", pn[i], 100.0 * ns[16 + i] / tot); }
+  { unsigned long long st[8]; cudaMemcpyFromSymbol(st, g_stats, sizeof st); fprintf(stderr, "H_STATS iters_with_change=%llu changed_fric=%llu changed_con=%llu le4=%llu only_fric=%llu dir_tree=%llu dir_dense=%llu dir_incremental=%llu\n", st[0], st[1], st[2], st[3], st[4], st[5], st[6], st[7]); }
 #endif
   return 0;
 }
