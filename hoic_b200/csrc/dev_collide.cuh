@@ -281,7 +281,7 @@ __device__ __noinline__ int box_box(RawCon* c, float margin, V3 p1, const M3& R1
 }
 
 // ---------------------------------------------------------------------------------------------- MPR (libccd)
-struct CObj { int type, nvert; V3 pos; M3 mat; float size[3]; const float4* vert; };
+struct CObj { int type, nvert, ncl; V3 pos; M3 mat; float size[3]; const float4* vert; const float4* cl; };
 struct Supp { V3 v, v1, v2; };
 
 // support point of a convex object along world direction `dir`; the whole warp calls this with identical
@@ -298,21 +298,40 @@ __device__ __noinline__ V3 support_w(const CObj& o, V3 dirw, int lane) {
     float nn = norm(d);
     l = nn < F_MINVAL ? v3(0, 0, 0) : d * (o.size[0] / nn);
   } else {
-    float best = -FLT_MAX;
-    int bi = 0x7fffffff;
-    for (int i = lane; i < o.nvert; i += 32) {
-      float4 v = __ldg(o.vert + i);
-      float sc = v.x * d.x + v.y * d.y + v.z * d.z;
-      if (sc > best) { best = sc; bi = i; }
+    // mesh: clusters of 32 vertices with a local AABB each (model build).  Upper bound of a cluster = AABB support, lower
+    // bound of the answer = best cluster representative; only clusters whose upper bound reaches it are scanned.
+    // The dot products and the tie rule (lowest ORIGINAL index) are those of a serial scan over all vertices.
+    float ub = -FLT_MAX, lb = -FLT_MAX;
+    if (lane < o.ncl) {
+      const float4 lo = __ldg(o.cl + 2 * lane), hi = __ldg(o.cl + 2 * lane + 1), rp = __ldg(o.vert + 32 * lane);
+      ub = (d.x >= 0.f ? hi.x : lo.x) * d.x + (d.y >= 0.f ? hi.y : lo.y) * d.y + (d.z >= 0.f ? hi.z : lo.z) * d.z;
+      lb = rp.x * d.x + rp.y * d.y + rp.z * d.z;
     }
+    const float best0 = wmax(lb);
+    const float slack = 1e-6f * (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));   // >> rounding of a 3-term dot of |v| < 1 m
+    unsigned surv = __ballot_sync(FULLMASK, ub >= best0 - slack);
+    float best = -FLT_MAX, bx = 0.f, by = 0.f, bz = 0.f;
+    int bi = 0x7fffffff;
+    auto scan = [&](int i) {
+      if (i < o.nvert) {
+        const float4 v = __ldg(o.vert + i);
+        const float sc = v.x * d.x + v.y * d.y + v.z * d.z;
+        const int oi = __float_as_int(v.w);
+        if (sc > best || (sc == best && oi < bi)) { best = sc; bi = oi; bx = v.x; by = v.y; bz = v.z; }
+      }
+    };
+    for (; surv; surv &= surv - 1) scan(32 * (__ffs(surv) - 1) + lane);
+    for (int k = 32; k < o.ncl; k++) scan(32 * k + lane);   // meshes beyond 1024 vertices: the tail is scanned unpruned
+    float wb = best;
+    int wi = bi;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      float ob = __shfl_xor_sync(FULLMASK, best, off);
-      int oi = __shfl_xor_sync(FULLMASK, bi, off);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }  // ties -> lowest index, as a serial scan
+      const float ob = __shfl_xor_sync(FULLMASK, wb, off);
+      const int oi = __shfl_xor_sync(FULLMASK, wi, off);
+      if (ob > wb || (ob == wb && oi < wi)) { wb = ob; wi = oi; }
     }
-    float4 v = __ldg(o.vert + bi);
-    l = v3(v.x, v.y, v.z);
+    const int src = __ffs(__ballot_sync(FULLMASK, bi == wi && best == wb)) - 1;
+    l = v3(__shfl_sync(FULLMASK, bx, src), __shfl_sync(FULLMASK, by, src), __shfl_sync(FULLMASK, bz, src));
   }
   return mulv(o.mat, l) + o.pos;
 }
@@ -480,6 +499,8 @@ __device__ __forceinline__ void make_cobj(const float* s, const DevModel& m, int
   o.size[0] = m.geom_size[g][0]; o.size[1] = m.geom_size[g][1]; o.size[2] = m.geom_size[g][2];
   o.nvert = m.geom_vertnum[g];
   o.vert = m.mesh_vert + (m.geom_vertadr[g] >= 0 ? m.geom_vertadr[g] : 0);
+  o.ncl = m.geom_ncl[g];
+  o.cl = m.mesh_cl + m.geom_cladr[g];   // float4 units
 }
 
 // mju_makeFrame
@@ -522,6 +543,25 @@ __device__ __noinline__ void collide(float* s, const DevModel& m, int lane, unsi
       } else if (m.geom_type[g1] == G_PLANE && rb2 > 0.f) {
         const M3 pm = ldm(s + S_GMAT + 9 * g1);
         if (dot(p2 - p1, col(pm, 2)) > cd.margin + rb2) active = false;
+      }
+      if (active && kind == K_CONVEX && m.geom_type[g2] == G_MESH && (m.geom_type[g1] == G_CAPSULE || m.geom_type[g1] == G_BOX)) {
+        // conservative cull before MPR: 6 separating-axis tests between g1's bounding box and the mesh's local AABB.
+        // A separated pair cannot penetrate, so MPR would report no contact as well.
+        const M3 R1 = ldm(s + S_GMAT + 9 * g1), R2 = ldm(s + S_GMAT + 9 * g2);
+        const float* sz = m.geom_size[g1];
+        const bool cap = m.geom_type[g1] == G_CAPSULE;
+        const float e1[3] = {sz[0], cap ? sz[0] : sz[1], cap ? sz[1] + sz[0] : sz[2]};
+        const float* h2 = m.geom_aabb_h[g2];
+        const V3 dw = p2 + mulv(R2, ld3(m.geom_aabb_c[g2])) - p1;
+        const V3 d1 = mulTv(R1, dw), d2 = mulTv(R2, dw);
+        float R[9];   // R[3i+j] = axis i of g1 . axis j of the mesh
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) R[3 * i + j] = fabsf(dot(col(R1, i), col(R2, j)));
+        const float tol = cd.margin + 1e-6f;
+        for (int i = 0; i < 3; i++) {
+          if (fabsf(comp(d1, i)) > e1[i] + R[3 * i] * h2[0] + R[3 * i + 1] * h2[1] + R[3 * i + 2] * h2[2] + tol) active = false;
+          if (fabsf(comp(d2, i)) > h2[i] + R[i] * e1[0] + R[3 + i] * e1[1] + R[6 + i] * e1[2] + tol) active = false;
+        }
       }
       if (active && kind != K_CONVEX && kind != K_PLANE_MESH) {
         const M3 m1 = ldm(s + S_GMAT + 9 * g1), m2 = ldm(s + S_GMAT + 9 * g2);

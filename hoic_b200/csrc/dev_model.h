@@ -70,7 +70,11 @@ struct DevModel {
   // geoms
   int geom_type[HN], geom_body[HN], geom_vertadr[HN], geom_vertnum[HN];
   float geom_pos[HN][3], geom_mat[HN][9], geom_size[HN][3], geom_rbound[HN];
-  const float4* mesh_vert;       // device pointer, xyz + pad
+  const float4* mesh_vert;       // device pointer: xyz + original vertex index (int bits); every mesh is stored as clusters of 32
+                                 // spatially close vertices (kd split at model build), cluster k of geom g = vertices [32k, 32k+32)
+  const float4* mesh_cl;         // device pointer: per cluster the local AABB (lo, hi) -> support-function pruning
+  int geom_cladr[HN], geom_ncl[HN];
+  float geom_aabb_c[HN][3], geom_aabb_h[HN][3];   // mesh geoms: local AABB centre / half sizes (conservative pair culling)
   // collision candidates in MuJoCo's signature order
   DevCand cand[H_MAXCAND];
   // env

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "../../include/hoic.h"
@@ -579,7 +581,8 @@ double impedance_h(const double* si, double pos, double margin) {
   return s0 + y * (s1 - s0);
 }
 
-bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<float4>& verts) {
+static inline float __int_as_float_h(int i) { float f; memcpy(&f, &i, 4); return f; }
+bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<float4>& verts, size_t& cl_base) {
   Blob B;
   if (hoic_blob_open(&B.v, blob, nbytes) != 0) { g_err = "not a HOIC model blob"; return false; }
   memset(&D, 0, sizeof D);
@@ -776,8 +779,52 @@ bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<f
     quat2mat_h(&gquat[4 * g], D.geom_mat[g]);
     D.geom_rbound[g] = (float)grbound[g];
   }
-  verts.resize(mv.size() / 3 + 1);
-  for (size_t i = 0; i < mv.size() / 3; i++) verts[i] = make_float4((float)mv[3 * i], (float)mv[3 * i + 1], (float)mv[3 * i + 2], 0.f);
+  // mesh vertices: per mesh geom, reorder into clusters of 32 spatially close vertices (recursive median split along the
+  // widest axis, split points on multiples of 32) and record each cluster's AABB; .w keeps the original index, which
+  // breaks ties in the support function exactly like a serial scan in the original order.
+  verts.assign(mv.size() / 3 + 1, make_float4(0.f, 0.f, 0.f, 0.f));
+  cl_base = verts.size();
+  for (int g = 0; g < ng; g++) {
+    D.geom_cladr[g] = 0; D.geom_ncl[g] = 0;
+    for (int k = 0; k < 3; k++) { D.geom_aabb_c[g][k] = 0.f; D.geom_aabb_h[g][k] = 0.f; }
+    const int n = gvnum[g], adr = gvadr[g];
+    if (gtype[g] != G_MESH || n <= 0 || adr < 0) continue;
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; i++) idx[i] = i;
+    auto coord = [&](int i, int ax) { return mv[3 * (size_t)(adr + i) + ax]; };
+    std::vector<std::pair<int, int>> stack{{0, n}};
+    while (!stack.empty()) {
+      const auto [lo, hi] = stack.back();
+      stack.pop_back();
+      if (hi - lo <= 32) continue;
+      double mn[3] = {1e30, 1e30, 1e30}, mx[3] = {-1e30, -1e30, -1e30};
+      for (int i = lo; i < hi; i++)
+        for (int ax = 0; ax < 3; ax++) { mn[ax] = std::min(mn[ax], coord(idx[i], ax)); mx[ax] = std::max(mx[ax], coord(idx[i], ax)); }
+      int ax = 0;
+      for (int k = 1; k < 3; k++) if (mx[k] - mn[k] > mx[ax] - mn[ax]) ax = k;
+      const int ncl = (hi - lo + 31) / 32, mid = lo + 32 * ((ncl + 1) / 2);
+      std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) { return coord(a, ax) < coord(b, ax); });
+      stack.push_back({lo, mid});
+      stack.push_back({mid, hi});
+    }
+    const int ncl = (n + 31) / 32;
+    D.geom_cladr[g] = (int)(verts.size() - cl_base);
+    D.geom_ncl[g] = ncl;
+    float glo[3] = {1e30f, 1e30f, 1e30f}, ghi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int c = 0; c < ncl; c++) {
+      float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+      for (int i = 32 * c; i < std::min(n, 32 * c + 32); i++) {
+        float4 v = make_float4((float)coord(idx[i], 0), (float)coord(idx[i], 1), (float)coord(idx[i], 2), __int_as_float_h(idx[i]));
+        verts[adr + i] = v;
+        const float xyz[3] = {v.x, v.y, v.z};
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], xyz[k]); hi[k] = std::max(hi[k], xyz[k]); }
+      }
+      verts.push_back(make_float4(lo[0], lo[1], lo[2], 0.f));
+      verts.push_back(make_float4(hi[0], hi[1], hi[2], 0.f));
+      for (int k = 0; k < 3; k++) { glo[k] = std::min(glo[k], lo[k]); ghi[k] = std::max(ghi[k], hi[k]); }
+    }
+    for (int k = 0; k < 3; k++) { D.geom_aabb_c[g][k] = 0.5f * (glo[k] + ghi[k]); D.geom_aabb_h[g][k] = 0.5f * (ghi[k] - glo[k]); }
+  }
   // collision candidates in signature order (explicit pairs merged; mj_collision driver)
   int ncand = 0;
   bool too_many = false;
@@ -854,12 +901,14 @@ bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<f
 extern "C" hoic_model* hoic_model_create(const void* blob_host, size_t nbytes, int device) {
   hoic_model* M = new hoic_model();
   std::vector<float4> verts;
-  if (!build_dev_model(blob_host, nbytes, M->host, verts)) { delete M; return nullptr; }
+  size_t cl_base = 0;
+  if (!build_dev_model(blob_host, nbytes, M->host, verts, cl_base)) { delete M; return nullptr; }
   M->device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaMalloc(&M->mesh_vert, verts.size() * sizeof(float4));
   if (e == cudaSuccess) e = cudaMemcpy(M->mesh_vert, verts.data(), verts.size() * sizeof(float4), cudaMemcpyHostToDevice);
   M->host.mesh_vert = M->mesh_vert;
+  M->host.mesh_cl = M->mesh_vert + cl_base;
   if (e == cudaSuccess) e = cudaMalloc(&M->dev, sizeof(DevModel));
   if (e == cudaSuccess) e = cudaMemcpy(M->dev, &M->host, sizeof(DevModel), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { set_err(std::string("hoic_model_create: ") + cudaGetErrorString(e)); delete M; return nullptr; }

@@ -17,6 +17,8 @@ ithr = hdr.index("Thread Instructions Executed")
 base = int(rows[2][ia], 16)
 main = [s for s in syms if "$" not in s[2] and s[0] == 0]
 agg = collections.defaultdict(lambda: [0, 0, 0])
+stall_cols = [(i, n[6:]) for i, n in enumerate(hdr) if n.startswith("stall_") and "Not Issued" not in n]
+stalls = collections.defaultdict(collections.Counter)
 for r in rows[2:]:
     if len(r) <= ithr: continue
     off = int(r[ia], 16) - base
@@ -25,8 +27,11 @@ for r in rows[2:]:
         if a != 0 and a <= off < a + sz:
             name = n; break
     agg[name][0] += int(r[ii]); agg[name][1] += int(r[isamp]); agg[name][2] += int(r[ithr])
+    for i, n in stall_cols:
+        if r[i] not in ("", "0"): stalls[name][n] += int(r[i])
 ti = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values())
-print(f"{'function':45s} {'inst %':>7s} {'samples %':>9s} {'lanes':>6s}")
+print(f"{'function':45s} {'inst %':>7s} {'samples %':>9s} {'lanes':>6s}  top stall reasons (% of the function's samples)")
 for k, v in sorted(agg.items(), key=lambda x: -x[1][0]):
-    print(f"{re.sub(r'^_Z[0-9]+', '', k)[:45]:45s} {100*v[0]/ti:7.2f} {100*v[1]/max(ts,1):9.2f} {v[2]/max(v[0],1):6.1f}")
+    print(f"{re.sub(r'^_Z[0-9]+', '', k)[:45]:45s} {100*v[0]/ti:7.2f} {100*v[1]/max(ts,1):9.2f} {v[2]/max(v[0],1):6.1f}  " +
+          " ".join(f"{n}:{100*c/max(sum(stalls[k].values()),1):.0f}" for n, c in stalls[k].most_common(5)))
 print("total inst", ti, "samples", ts)
