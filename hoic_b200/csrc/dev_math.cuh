@@ -170,6 +170,8 @@ __device__ __forceinline__ float rsqrt_nr(float x) {
   return y * fmaf(-0.5f * x * y, y, 1.5f);   // one Newton step on the MUFU estimate
 }
 __device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int lane) {
+  // Branch-free on purpose: lanes outside the active part of a panel read clamped (valid, irrelevant) addresses and
+  // only their stores are predicated, so the warp never diverges and nothing waits on a reconvergence barrier.
   const int I = lane >> 2, r = lane & 3;
   float yb = b;
   bool ok = true;
@@ -177,6 +179,8 @@ __device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int
   for (int p = 0; p < 8; p++) {
     const float4* Dp = reinterpret_cast<const float4*>(A + HB_OFF(p, p));
     const float4 r0 = Dp[0], r1 = Dp[1], r2 = Dp[2], r3 = Dp[3];
+    float4* own = reinterpret_cast<float4*>(A + HB_OFF(max(I, p), p) + 4 * r);
+    const float4 a = *own;
     const float z0 = __shfl_sync(FULLMASK, yb, 4 * p), z1 = __shfl_sync(FULLMASK, yb, 4 * p + 1),
                 z2 = __shfl_sync(FULLMASK, yb, 4 * p + 2), z3 = __shfl_sync(FULLMASK, yb, 4 * p + 3);
     const float d0 = r0.x;
@@ -190,41 +194,35 @@ __device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int
     const float l32 = fmaf(-l31, l21, fmaf(-l30, l20, r3.z)) * i2;
     const float d3 = fmaf(-l32, l32, fmaf(-l31, l31, fmaf(-l30, l30, r3.w)));
     const float i3 = rsqrt_nr(fmaxf(d3, F_MINVAL));
-    ok = ok && d0 > F_MINVAL && d1 > F_MINVAL && d2 > F_MINVAL && d3 > F_MINVAL;
+    ok = ok && fminf(fminf(d0, d1), fminf(d2, d3)) > F_MINVAL;
     const float t0 = z0 * i0, t1 = fmaf(-l10, t0, z1) * i1, t2 = fmaf(-l21, t1, fmaf(-l20, t0, z2)) * i2,
                 t3 = fmaf(-l32, t2, fmaf(-l31, t1, fmaf(-l30, t0, z3))) * i3;
-    float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-    if (I >= p) {
-      float4* own = reinterpret_cast<float4*>(A + HB_OFF(I, p) + 4 * r);
-      const float4 a = *own;
-      x0 = a.x * i0;
-      x1 = fmaf(-x0, l10, a.y) * i1;
-      x2 = fmaf(-x1, l21, fmaf(-x0, l20, a.z)) * i2;
-      x3 = fmaf(-x2, l32, fmaf(-x1, l31, fmaf(-x0, l30, a.w))) * i3;
-      if (I == p) {
-        // rows of the diagonal block: entries right of the diagonal carry 1 / L_cc for the back-substitution
-        yb = r == 0 ? t0 : (r == 1 ? t1 : (r == 2 ? t2 : t3));
-        if (r == 0) { x1 = i1; x2 = i2; x3 = i3; }
-        else if (r == 1) { x2 = i0; x3 = 0.f; }
-        else if (r == 2) { x3 = 0.f; }
-      } else {
-        yb = fmaf(-x3, t3, fmaf(-x2, t2, fmaf(-x1, t1, fmaf(-x0, t0, yb))));
-      }
-      *own = make_float4(x0, x1, x2, x3);
-    }
+    const float x0 = a.x * i0;
+    const float x1 = fmaf(-x0, l10, a.y) * i1;
+    const float x2 = fmaf(-x1, l21, fmaf(-x0, l20, a.z)) * i2;
+    const float x3 = fmaf(-x2, l32, fmaf(-x1, l31, fmaf(-x0, l30, a.w))) * i3;
+    const bool inblk = I == p, below = I > p;
+    // rows of the diagonal block: entries right of the diagonal carry 1 / L_cc for the back-substitution
+    const float s1 = inblk && r == 0 ? i1 : x1;
+    const float s2 = inblk && r < 2 ? (r == 0 ? i2 : i0) : x2;
+    const float s3 = inblk && r < 3 ? (r == 0 ? i3 : 0.f) : x3;
+    const float tr = r == 0 ? t0 : (r == 1 ? t1 : (r == 2 ? t2 : t3));
+    const float yd = fmaf(-x3, t3, fmaf(-x2, t2, fmaf(-x1, t1, fmaf(-x0, t0, yb))));
+    yb = inblk ? tr : (below ? yd : yb);
+    if (I >= p) *own = make_float4(x0, s1, s2, s3);
     __syncwarp();
     // rank-4 update of the row segments right of the panel: A[i][4 Jb + c] -= sum_k L[i][4p + k] L[4 Jb + c][4p + k]
-#pragma unroll 1
-    for (int Jb = p + 1; Jb <= I; Jb++) {
+#pragma unroll 2
+    for (int Jb = p + 1; Jb < 8; Jb++) {
       const float4* Lr = reinterpret_cast<const float4*>(A + HB_OFF(Jb, p));
-      float4* o = reinterpret_cast<float4*>(A + HB_OFF(I, Jb) + 4 * r);
+      float4* o = reinterpret_cast<float4*>(A + HB_OFF(I, min(Jb, I)) + 4 * r);
       float4 v = *o;
       const float4 q0 = Lr[0], q1 = Lr[1], q2 = Lr[2], q3 = Lr[3];
       v.x = fmaf(-x3, q0.w, fmaf(-x2, q0.z, fmaf(-x1, q0.y, fmaf(-x0, q0.x, v.x))));
       v.y = fmaf(-x3, q1.w, fmaf(-x2, q1.z, fmaf(-x1, q1.y, fmaf(-x0, q1.x, v.y))));
       v.z = fmaf(-x3, q2.w, fmaf(-x2, q2.z, fmaf(-x1, q2.y, fmaf(-x0, q2.x, v.z))));
       v.w = fmaf(-x3, q3.w, fmaf(-x2, q3.z, fmaf(-x1, q3.y, fmaf(-x0, q3.x, v.w))));
-      *o = v;
+      if (Jb <= I) *o = v;
     }
     __syncwarp();
   }
@@ -234,18 +232,17 @@ __device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int
   for (int p = 7; p >= 0; p--) {
     const float4* Dp = reinterpret_cast<const float4*>(A + HB_OFF(p, p));
     const float4 r0 = Dp[0], r1 = Dp[1], r2 = Dp[2], r3 = Dp[3];   // r0 = (L00, 1/L11, 1/L22, 1/L33), r1 = (L10, L11, 1/L00, 0)
+    const float* cb = A + HB_OFF(p, min(I, p)) + r;               // column r of block (p, I)
+    const float c0 = cb[0], c1 = cb[4], c2 = cb[8], c3 = cb[12];
     const float z0 = __shfl_sync(FULLMASK, xb, 4 * p), z1 = __shfl_sync(FULLMASK, xb, 4 * p + 1),
                 z2 = __shfl_sync(FULLMASK, xb, 4 * p + 2), z3 = __shfl_sync(FULLMASK, xb, 4 * p + 3);
     const float s3 = z3 * r0.w;
     const float s2 = fmaf(-r3.z, s3, z2) * r0.z;
     const float s1 = fmaf(-r3.y, s3, fmaf(-r2.y, s2, z1)) * r0.y;
     const float s0 = fmaf(-r3.x, s3, fmaf(-r2.x, s2, fmaf(-r1.x, s1, z0))) * r1.z;
-    if (I == p) {
-      xb = r == 0 ? s0 : (r == 1 ? s1 : (r == 2 ? s2 : s3));
-    } else if (I < p) {
-      const float* cb = A + HB_OFF(p, I) + r;   // column r of block (p, I)
-      xb = fmaf(-cb[12], s3, fmaf(-cb[8], s2, fmaf(-cb[4], s1, fmaf(-cb[0], s0, xb))));
-    }
+    const float sr = r == 0 ? s0 : (r == 1 ? s1 : (r == 2 ? s2 : s3));
+    const float xu = fmaf(-c3, s3, fmaf(-c2, s2, fmaf(-c1, s1, fmaf(-c0, s0, xb))));
+    xb = I == p ? sr : (I < p ? xu : xb);
   }
   *xout = xb;
   return ok;

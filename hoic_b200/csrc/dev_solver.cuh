@@ -351,6 +351,9 @@ __device__ __noinline__ float newton_weights(float* s, const DevModel& m, int la
 // layout of warp_chol_solve), Cholesky, search = -H^-1 grad.  All loops are rolled: see warp_chol_solve.
 __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int lane, int ncon, float diag) {
   float* A = s + S_H;
+#ifdef H_STATS
+  long long nst_t = clock64();
+#endif
   {
     const int I = lane >> 2, r = lane & 3;
 #pragma unroll 1
@@ -400,10 +403,12 @@ __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int l
     }
   }
   __syncwarp();
+  NST_T(8);    // Hessian assembly
   float dir;
   const bool ok = warp_chol_solve(A, -s[S_GRAD + lane], &dir, lane);
   s[S_SEARCH + lane] = dir;
   __syncwarp();
+  NST_T(9);    // Cholesky + substitutions
   return ok;
 }
 
@@ -454,17 +459,11 @@ __device__ __noinline__ float line_search(float* s, const DevModel& m, int lane,
   return alpha;
 }
 
-// mj_fwdConstraint with the Newton solver.  Inputs: S_SMOOTH, S_ASMOOTH, S_WARM, rows.  Outputs: S_QACC, S_FCON.
-__device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane, unsigned& iters_out, unsigned& ls_evals) {
-  const int* misc = (const int*)(s + S_MISC);
-  const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON], nbasis = misc[MI_NBASIS], nedge = misc[MI_NEDGE];
-  const float scale = 1.0f / (m.meaninertia * (float)(m.nv > 1 ? m.nv : 1));
+// ---- mj_fwdConstraint with the Newton solver, split into sub-phases that every warp of a CTA runs in lockstep.
+// Inputs: S_SMOOTH, S_ASMOOTH, S_WARM, rows.  Outputs: S_QACC, S_FCON.
+// warm start selection and initial cost; leaves S_QACC, S_MA, U_JAR, U_FORCE consistent
+__device__ __noinline__ float newton_init(float* s, const DevModel& m, int lane, int nbasis, int nedge) {
   const float asm_ = s[S_ASMOOTH + lane], fsm = s[S_SMOOTH + lane];
-#ifdef H_STATS
-  long long nst_t = clock64();
-  const long long nst_t0 = nst_t;
-#endif
-  // warm start selection
   float qacc = s[S_WARM + lane];
   s[S_QACC + lane] = qacc;
   __syncwarp();
@@ -486,62 +485,86 @@ __device__ __noinline__ bool solve_newton(float* s, const DevModel& m, int lane,
   }
   s[S_MA + lane] = ma;
   __syncwarp();
-  float cost = rows_update(s, m, lane, nedge, s + U_JAR, true) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
-  bool ok = true;
-  unsigned iter = 0;
-  float oldcost = cost;
-  NST_T(0);   // warm start / initial cost
-  for (;;) {
-    const float g2 = newton_gradient(s, m, lane, nlim, nbasis);
-    NST_T(1);
-    if (iter > 0) {
-      const float improvement = scale * (oldcost - cost), gradn = scale * sqrtf(g2);
-      // float32 noise floor on the cost difference replaces MuJoCo's absolute 1e-8 (see DESIGN.md "precision")
-      const float tol = fmaxf(m.tolerance, 2e-7f * scale * fabsf(cost));
-      if (improvement < tol || gradn < m.tolerance) break;
+  return rows_update(s, m, lane, nedge, s + U_JAR, true) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
+}
+
+// line search along S_SEARCH, move, new cost.  Returns 0: zero step (nothing moved), 1: moved and some row changed
+// state (active set / friction branch), 2: moved and no row changed state.
+__device__ __noinline__ int newton_move(float* s, const DevModel& m, int lane, int nbasis, int nedge, float& cost, unsigned& ls_evals) {
+  const float alpha = line_search(s, m, lane, nbasis, nedge, ls_evals);
+  if (alpha == 0.f) return 0;
+  const float qacc = s[S_QACC + lane] + alpha * s[S_SEARCH + lane];
+  const float ma = s[S_MA + lane] + alpha * s[S_MV + lane];
+  s[S_QACC + lane] = qacc;
+  s[S_MA + lane] = ma;
+  bool changed = false;
+  for (int r = lane; r < H_RCON + nedge; r += 32) {
+    const float x0 = s[U_JAR + r], x1 = x0 + alpha * s[U_JV + r];
+    s[U_JAR + r] = x1;
+    if (s[U_D + r] != 0.f) {
+      if (r < H_RLIM) { const float Rf = m.fr_Rf[r]; changed = changed || ((x0 <= -Rf) != (x1 <= -Rf)) || ((x0 >= Rf) != (x1 >= Rf)); }
+      else changed = changed || ((x0 < 0.f) != (x1 < 0.f));
     }
-    if (iter >= (unsigned)m.iterations) break;
-    {
+  }
+  changed = __any_sync(FULLMASK, changed);
+  __syncwarp();
+  cost = rows_update(s, m, lane, nedge, s + U_JAR, true) + wsum(0.5f * (ma - s[S_SMOOTH + lane]) * (qacc - s[S_ASMOOTH + lane]));
+  return changed ? 1 : 2;
+}
+
+// Driver.  With H_NEWTON_LOCKSTEP the sub-phases of an iteration are separated by CTA barriers (every warp of the CTA
+// must then call it, warps without work pass active = false); measured slower than free-running warps (box 4096 envs:
+// 6.98 vs 6.84 ms), so it is off: the imbalance of the solve is the iteration COUNT, not fetch sharing inside it.
+#ifdef H_NEWTON_LOCKSTEP
+#define NEWTON_ANY(run) __syncthreads_or(run)
+#define NEWTON_SYNC() __syncthreads()
+#else
+#define NEWTON_ANY(run) (run)
+#define NEWTON_SYNC() do { } while (0)
+#endif
+__device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int lane, bool active, unsigned& iters_out, unsigned& ls_evals) {
+  const int* misc = (const int*)(s + S_MISC);
+  const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON], nbasis = misc[MI_NBASIS], nedge = misc[MI_NEDGE];
+  const float scale = 1.0f / (m.meaninertia * (float)(m.nv > 1 ? m.nv : 1));
+  bool run = active, ok = true;
+  unsigned iter = 0;
+  float cost = 0.f, oldcost = 0.f;
+  if (run) { cost = newton_init(s, m, lane, nbasis, nedge); oldcost = cost; }
+  for (;;) {
+    if (run) {
+      const float g2 = newton_gradient(s, m, lane, nlim, nbasis);
+      if (iter > 0) {
+        const float improvement = scale * (oldcost - cost), gradn = scale * sqrtf(g2);
+        // float32 noise floor on the cost difference replaces MuJoCo's absolute 1e-8 (see DESIGN.md "precision")
+        const float tol = fmaxf(m.tolerance, 2e-7f * scale * fabsf(cost));
+        if (improvement < tol || gradn < m.tolerance) run = false;
+      }
+      if (iter >= (unsigned)m.iterations) run = false;
+    }
+    if (!NEWTON_ANY(run)) break;
+    if (run) {
       // full refactorisation every iteration: the blocked Cholesky is cheaper than tracking rank-one changes
       const float diag = newton_weights(s, m, lane, nlim, ncon);
       ok = newton_direction(s, m, lane, ncon, diag);
-      if (!ok) break;
-      NST_T(3);
+      if (!ok) run = false;
     }
-    const float alpha = line_search(s, m, lane, nbasis, nedge, ls_evals);
-    NST_T(4);
-    if (alpha == 0.f) break;
-    qacc += alpha * s[S_SEARCH + lane];
-    ma += alpha * s[S_MV + lane];
-    s[S_QACC + lane] = qacc;
-    s[S_MA + lane] = ma;
-    // move along the search direction; note whether any row changed state (active set / friction branch)
-    bool changed = false;
-    for (int r = lane; r < H_RCON + nedge; r += 32) {
-      const float x0 = s[U_JAR + r], x1 = x0 + alpha * s[U_JV + r];
-      s[U_JAR + r] = x1;
-      if (s[U_D + r] != 0.f) {
-        if (r < H_RLIM) { const float Rf = m.fr_Rf[r]; changed = changed || ((x0 <= -Rf) != (x1 <= -Rf)) || ((x0 >= Rf) != (x1 >= Rf)); }
-        else changed = changed || ((x0 < 0.f) != (x1 < 0.f));
+    NEWTON_SYNC();
+    if (run) {
+      oldcost = cost;
+      const int mv = newton_move(s, m, lane, nbasis, nedge, cost, ls_evals);
+      if (mv == 0) run = false;
+      else {
+        iter++;
+        if (mv == 2) {
+          // no row changed state along the step: the cost was exactly quadratic there and the Newton step with the
+          // exact line search landed on its minimiser, the optimum of the convex problem.  Refresh J^T f and stop.
+          newton_gradient(s, m, lane, nlim, nbasis);
+          run = false;
+        }
       }
     }
-    changed = __any_sync(FULLMASK, changed);
-    __syncwarp();
-    oldcost = cost;
-    cost = rows_update(s, m, lane, nedge, s + U_JAR, true) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
-    iter++;
-    NST_T(5);
-    if (!changed) {
-      // no row changed state along the step: the cost was exactly quadratic there and the Newton step with the exact
-      // line search landed on its minimiser, which is the optimum of the convex problem.  Refresh J^T f and stop.
-      newton_gradient(s, m, lane, nlim, nbasis);
-      break;
-    }
   }
-#ifdef H_STATS
-  if (lane == 0) { const int b_ = iter < 7 ? (int)iter : 7; atomicAdd(&g_nst[b_], 1ull); atomicAdd(&g_nst[8 + b_], (unsigned long long)(clock64() - nst_t0)); }
-#endif
   iters_out += iter;
-  // S_FCON holds J^T f of the final forces (written by newton_direction)
+  // S_FCON holds J^T f of the final forces (written by newton_gradient)
   return ok;
 }

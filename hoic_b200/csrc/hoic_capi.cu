@@ -64,10 +64,12 @@ __device__ __noinline__ bool phase_smooth(float* s, const DevModel& m, int lane)
   __syncwarp();
   return ok;
 }
-__device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int lane, Cnt& cnt) {
+// Every warp of the CTA calls this (active = false: only the CTA barriers inside the solver are taken).
+__device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int lane, Cnt& cnt, bool active) {
   int* misc = (int*)(s + S_MISC);
   unsigned it = 0;
-  bool fail = !solve_newton(s, m, lane, it, cnt.ls);
+  bool fail = !solve_newton(s, m, lane, active, it, cnt.ls);
+  if (!active) return false;
   cnt.newton += it;
   cnt.substeps++;
   cnt.ncon += misc[MI_NCON];
@@ -87,7 +89,7 @@ __device__ bool substep_core(float* s, const DevModel& m, int lane, bool record,
   collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
   if (record) record_contacts(s, m, lane);
   build_rows(s, m, lane);
-  if (!phase_solve(s, m, lane, cnt)) return false;
+  if (!phase_solve(s, m, lane, cnt, true)) return false;
   if (!euler_step(s, m, lane, nullptr)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   return true;
 }
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const fl
       build_rows(s, m, lane);
     }
     HB(7);
-    if (ok) ok = phase_solve(s, m, lane, cnt);
+    ok = phase_solve(s, m, lane, cnt, ok);
     HB(4);
     if (ok) {
       ok = euler_step(s, m, lane, nullptr);
@@ -1122,7 +1124,9 @@ extern "C" int hoic_get_counters(hoic_batch* b, hoic_counters* out_host) {
     for (int i = 0; i < 8; i++) fprintf(stderr, "H_STATS solves with %d iters: %llu  avg cycles %.0f\n", i, ns[i], ns[i] ? (double)ns[8 + i] / ns[i] : 0.0);
     static const char* pn[6] = {"init", "gradient", "incremental", "full direction", "line search", "move+cost"};
     double tot = 0; for (int i = 0; i < 6; i++) tot += (double)ns[16 + i];
-    for (int i = 0; i < 6; i++) fprintf(stderr, "H_STATS newton part %-16s %5.1f%%\n", pn[i], 100.0 * ns[16 + i] / tot); }
+    for (int i = 0; i < 6; i++) fprintf(stderr, "H_STATS newton part %-16s %5.1f%%\n", pn[i], 100.0 * ns[16 + i] / tot);
+    unsigned long long nsolve = 0, niter = 0; for (int i = 0; i < 8; i++) { nsolve += ns[i]; niter += ns[i] * i; }
+    fprintf(stderr, "H_STATS per direction call: assembly %.0f cycles, cholesky %.0f cycles (%llu calls)\n", (double)ns[24] / niter, (double)ns[25] / niter, niter); }
   { unsigned long long st[8]; cudaMemcpyFromSymbol(st, g_stats, sizeof st); fprintf(stderr, "H_STATS iters_with_change=%llu changed_fric=%llu changed_con=%llu le4=%llu only_fric=%llu dir_tree=%llu dir_dense=%llu dir_incremental=%llu\n", st[0], st[1], st[2], st[3], st[4], st[5], st[6], st[7]); }
 #endif
   return 0;
