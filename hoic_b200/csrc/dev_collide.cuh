@@ -281,12 +281,45 @@ __device__ __noinline__ int box_box(RawCon* c, float margin, V3 p1, const M3& R1
 }
 
 // ---------------------------------------------------------------------------------------------- MPR (libccd)
-struct CObj { int type, nvert, ncl; V3 pos; M3 mat; float size[3]; const float4* vert; const float4* cl; };
+// The two objects of the pair being solved live in shared memory (U_COBJ): mpr_penetration / support_w are out of line and
+// would otherwise read them from the local-memory stack.
+struct CObj { int type, nvert, ncl, pad; V3 pos; M3 mat; float size[3]; float pad2; const float4* vert; const float4* cl; };
+#define U_COBJ (U_CON_END)   // 2 x 24 words, inside the union's slack below the residual-force QP's extent
+static_assert(sizeof(CObj) == 96 && U_CON_END * 4 % 8 == 0 && U_CON_END + 48 <= U_QP_END, "CObj scratch");
 struct Supp { V3 v, v1, v2; };
+// per-lane view of a mesh for the support function: lane k keeps the AABB of vertex cluster k in registers for the whole
+// MPR call, `warm` (uniform) is the last support vertex in local coordinates = a lower bound for the next query
+struct MeshLane { float lox, loy, loz, hix, hiy, hiz; V3 warm; int valid; };
+struct SuppPt { V3 world, local; };
+
+// order-preserving float -> uint key (for redux.sync, one instruction instead of a 5-step shuffle tree)
+__device__ __forceinline__ unsigned fkey(float f) {
+  const unsigned u = __float_as_uint(f + 0.0f);   // -0 -> +0
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ MeshLane mesh_lane(const CObj& o, int lane) {
+  MeshLane ml;
+  ml.lox = ml.loy = ml.loz = ml.hix = ml.hiy = ml.hiz = 0.f;
+  ml.warm = v3(0, 0, 0);
+  ml.valid = 0;
+  if (o.type == G_MESH && o.nvert > 0) {
+    if (lane < o.ncl) {
+      const float4 lo = __ldg(o.cl + 2 * lane), hi = __ldg(o.cl + 2 * lane + 1);
+      ml.lox = lo.x; ml.loy = lo.y; ml.loz = lo.z; ml.hix = hi.x; ml.hiy = hi.y; ml.hiz = hi.z;
+    }
+    const float4 v0 = __ldg(o.vert);
+    ml.warm = v3(v0.x, v0.y, v0.z);
+    ml.valid = 1;
+  }
+  return ml;
+}
 
 // support point of a convex object along world direction `dir`; the whole warp calls this with identical
-// arguments, mesh vertices are scanned cooperatively (lane-strided) and reduced by shuffles.
-__device__ __noinline__ V3 support_w(const CObj& o, V3 dirw, int lane) {
+// arguments.  Meshes: clusters of 32 vertices with a local AABB each (model build).  Upper bound of a cluster = AABB
+// support, lower bound of the answer = the projection of a known vertex (the previous support vertex); only clusters
+// whose upper bound reaches it are scanned, lane-strided, and reduced with redux.sync.  The dot products and the tie
+// rule (lowest ORIGINAL index) are those of a serial scan over all vertices.
+__device__ __noinline__ SuppPt support_w(const CObj& o, V3 dirw, int lane, MeshLane ml) {
   V3 d = mulTv(o.mat, dirw), l;
   if (o.type == G_CAPSULE) {
     float nn = norm(d);
@@ -298,16 +331,11 @@ __device__ __noinline__ V3 support_w(const CObj& o, V3 dirw, int lane) {
     float nn = norm(d);
     l = nn < F_MINVAL ? v3(0, 0, 0) : d * (o.size[0] / nn);
   } else {
-    // mesh: clusters of 32 vertices with a local AABB each (model build).  Upper bound of a cluster = AABB support, lower
-    // bound of the answer = best cluster representative; only clusters whose upper bound reaches it are scanned.
-    // The dot products and the tie rule (lowest ORIGINAL index) are those of a serial scan over all vertices.
-    float ub = -FLT_MAX, lb = -FLT_MAX;
-    if (lane < o.ncl) {
-      const float4 lo = __ldg(o.cl + 2 * lane), hi = __ldg(o.cl + 2 * lane + 1), rp = __ldg(o.vert + 32 * lane);
-      ub = (d.x >= 0.f ? hi.x : lo.x) * d.x + (d.y >= 0.f ? hi.y : lo.y) * d.y + (d.z >= 0.f ? hi.z : lo.z) * d.z;
-      lb = rp.x * d.x + rp.y * d.y + rp.z * d.z;
-    }
-    const float best0 = wmax(lb);
+    if (!ml.valid) ml = mesh_lane(o, lane);
+    float ub = -FLT_MAX;
+    if (lane < o.ncl)
+      ub = (d.x >= 0.f ? ml.hix : ml.lox) * d.x + (d.y >= 0.f ? ml.hiy : ml.loy) * d.y + (d.z >= 0.f ? ml.hiz : ml.loz) * d.z;
+    const float best0 = ml.warm.x * d.x + ml.warm.y * d.y + ml.warm.z * d.z;
     const float slack = 1e-6f * (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));   // >> rounding of a 3-term dot of |v| < 1 m
     unsigned surv = __ballot_sync(FULLMASK, ub >= best0 - slack);
     float best = -FLT_MAX, bx = 0.f, by = 0.f, bz = 0.f;
@@ -322,22 +350,26 @@ __device__ __noinline__ V3 support_w(const CObj& o, V3 dirw, int lane) {
     };
     for (; surv; surv &= surv - 1) scan(32 * (__ffs(surv) - 1) + lane);
     for (int k = 32; k < o.ncl; k++) scan(32 * k + lane);   // meshes beyond 1024 vertices: the tail is scanned unpruned
-    float wb = best;
-    int wi = bi;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float ob = __shfl_xor_sync(FULLMASK, wb, off);
-      const int oi = __shfl_xor_sync(FULLMASK, wi, off);
-      if (ob > wb || (ob == wb && oi < wi)) { wb = ob; wi = oi; }
-    }
-    const int src = __ffs(__ballot_sync(FULLMASK, bi == wi && best == wb)) - 1;
+    const unsigned key = fkey(best);
+    const unsigned kmax = __reduce_max_sync(FULLMASK, key);
+    const bool top = key == kmax;
+    const unsigned imin = __reduce_min_sync(FULLMASK, top ? (unsigned)bi : 0xffffffffu);
+    const int src = __ffs(__ballot_sync(FULLMASK, top && (unsigned)bi == imin)) - 1;
     l = v3(__shfl_sync(FULLMASK, bx, src), __shfl_sync(FULLMASK, by, src), __shfl_sync(FULLMASK, bz, src));
   }
-  return mulv(o.mat, l) + o.pos;
+  SuppPt r;
+  r.local = l;
+  r.world = mulv(o.mat, l) + o.pos;
+  return r;
 }
-__device__ __forceinline__ void mpr_support(const CObj& o1, const CObj& o2, V3 dir, Supp& s, int lane) {
-  s.v1 = support_w(o1, dir, lane);
-  s.v2 = support_w(o2, -dir, lane);
+// o1's mesh view is not cached (no mesh is ever geom1 against a mesh in these models: it would be rebuilt per query)
+__device__ __forceinline__ void mpr_support(const CObj& o1, const CObj& o2, V3 dir, Supp& s, int lane, MeshLane& ml2) {
+  MeshLane none;
+  none.lox = none.loy = none.loz = none.hix = none.hiy = none.hiz = 0.f; none.warm = v3(0, 0, 0); none.valid = 0;
+  s.v1 = support_w(o1, dir, lane, none).world;
+  const SuppPt p2 = support_w(o2, -dir, lane, ml2);
+  ml2.warm = ml2.valid ? p2.local : ml2.warm;
+  s.v2 = p2.world;
   s.v = s.v1 - s.v2;
 }
 // libccd's absolute epsilon tests (ccdIsZero on squared lengths / dot products) are kept at the DOUBLE build's value:
@@ -395,7 +427,7 @@ __device__ __forceinline__ void expand_portal(Supp* s, const Supp& v4) {
 }
 // returns 0 when intersecting; all lanes run the same scalar logic (uniform), only support scans are split
 __device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, float tol, int max_iter, float& depth, V3& dir, V3& pos,
-                               int& iters, int lane) {
+                               int& iters, int lane, MeshLane ml2) {
   Supp s[4], v4;
   V3 d;
   float dt;
@@ -404,7 +436,7 @@ __device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, floa
   s[0].v1 = o1.pos; s[0].v2 = o2.pos; s[0].v = o1.pos - o2.pos;
   if (ccd_eq(s[0].v.x, 0.f) && ccd_eq(s[0].v.y, 0.f) && ccd_eq(s[0].v.z, 0.f)) s[0].v.x += CCDF_EPS * 10.f;
   d = -s[0].v; normalize(d);
-  mpr_support(o1, o2, d, s[1], lane);
+  mpr_support(o1, o2, d, s[1], lane, ml2);
   dt = dot(s[1].v, d);
   if (ccd_zero(dt) || dt < 0.f) return -1;
   d = cross(s[0].v, s[1].v);
@@ -412,7 +444,7 @@ __device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, floa
     res = (ccd_eq(s[1].v.x, 0.f) && ccd_eq(s[1].v.y, 0.f) && ccd_eq(s[1].v.z, 0.f)) ? 1 : 2;
   } else {
     normalize(d);
-    mpr_support(o1, o2, d, s[2], lane);
+    mpr_support(o1, o2, d, s[2], lane, ml2);
     dt = dot(s[2].v, d);
     if (ccd_zero(dt) || dt < 0.f) return -1;
     d = cross(s[1].v - s[0].v, s[2].v - s[0].v); normalize(d);
@@ -420,7 +452,7 @@ __device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, floa
     int size = 3, guard = 0;
     while (size < 4 && guard++ < 64) {
       bool cont = false;
-      mpr_support(o1, o2, d, s[3], lane);
+      mpr_support(o1, o2, d, s[3], lane, ml2);
       iters++;
       dt = dot(s[3].v, d);
       if (ccd_zero(dt) || dt < 0.f) return -1;
@@ -441,7 +473,7 @@ __device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, floa
     d = portal_dir(s);
     dt = dot(d, s[1].v);
     if (ccd_zero(dt) || dt > 0.f) break;
-    mpr_support(o1, o2, d, v4, lane);
+    mpr_support(o1, o2, d, v4, lane, ml2);
     iters++;
     dt = dot(v4.v, d);
     if (!(ccd_zero(dt) || dt > 0.f) || portal_reach_tol(s, v4, d, tol) || guard > 128) return -1;
@@ -449,7 +481,7 @@ __device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, floa
   }
   for (int it = 0;; it++) {
     d = portal_dir(s);
-    mpr_support(o1, o2, d, v4, lane);
+    mpr_support(o1, o2, d, v4, lane, ml2);
     iters++;
     if (portal_reach_tol(s, v4, d, tol) || it > max_iter) {
       V3 wit;
@@ -494,6 +526,7 @@ __device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, floa
 
 __device__ __forceinline__ void make_cobj(const float* s, const DevModel& m, int g, CObj& o) {
   o.type = m.geom_type[g];
+  o.pad = 0; o.pad2 = 0.f;
   o.pos = ld3(s + S_GPOS + 3 * g);
   o.mat = ldm(s + S_GMAT + 9 * g);
   o.size[0] = m.geom_size[g][0]; o.size[1] = m.geom_size[g][1]; o.size[2] = m.geom_size[g][2];
@@ -595,25 +628,26 @@ __device__ __noinline__ void collide(float* s, const DevModel& m, int lane, unsi
     const DevCand& cd = m.cand[ci];
     RawCon rc;
     int n = 0;
+    CObj& o1 = *reinterpret_cast<CObj*>(s + U_COBJ);
+    CObj& o2 = *reinterpret_cast<CObj*>(s + U_COBJ + 24);
+    __syncwarp();
+    if (lane == 0) { if (cd.kind == K_CONVEX) make_cobj(s, m, cd.g1, o1); make_cobj(s, m, cd.g2, o2); }
+    __syncwarp();
+    const MeshLane ml2 = mesh_lane(o2, lane);
     if (cd.kind == K_CONVEX) {
-      CObj o1, o2;
-      make_cobj(s, m, cd.g1, o1);
-      make_cobj(s, m, cd.g2, o2);
       float depth;
       V3 dir, pos;
       int it = 0;
       mpr_calls++;
-      if (mpr_penetration(o1, o2, m.mpr_tolerance, m.mpr_iterations, depth, dir, pos, it, lane) == 0 &&
+      if (mpr_penetration(o1, o2, m.mpr_tolerance, m.mpr_iterations, depth, dir, pos, it, lane, ml2) == 0 &&
           !(dir.x == 0.f && dir.y == 0.f && dir.z == 0.f)) {
         rc.dist = -depth; rc.n = dir; rc.pos = pos; rc.t = v3(0, 0, 0);
         n = 1;
       }
       mpr_iters += it;
     } else {  // plane - mesh: support vertex along -normal
-      CObj o2;
-      make_cobj(s, m, cd.g2, o2);
       const V3 pn = col(ldm(s + S_GMAT + 9 * cd.g1), 2);
-      const V3 v = support_w(o2, -pn, lane);
+      const V3 v = support_w(o2, -pn, lane, ml2).world;
       const float dist = dot(v - ld3(s + S_GPOS + 3 * cd.g1), pn);
       if (dist <= cd.margin) { rc.dist = dist; rc.pos = v - pn * (0.5f * dist); rc.n = pn; rc.t = v3(0, 0, 0); n = 1; }
     }

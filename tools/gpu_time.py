@@ -24,7 +24,7 @@ for a in acts:
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 c1 = env.counters()
-d = {k: (c1[k] - c0[k]) / max(c1["substeps"] - c0["substeps"], 1) for k in ("ncon", "nefc", "newton_iters", "ls_evals", "mpr_iters")}
+d = {k: (c1[k] - c0[k]) / max(c1["substeps"] - c0["substeps"], 1) for k in ("ncon", "nefc", "newton_iters", "ls_evals", "mpr_calls", "mpr_iters")}
 print(f"{os.environ.get('HOIC_LIB','default')} {obj} N={N}: {ms:.3f} ms/step  {N/ms*1e3:.0f} env-steps/s  per-substep {d}")
 # same measurement without load balancing
 env.balance = False
