@@ -280,6 +280,16 @@ __device__ __noinline__ int box_box(RawCon* c, float margin, V3 p1, const M3& R1
   return n;
 }
 
+// unit directions of the mesh 26-DOP used for pair culling (dev_model.h: geom_dop)
+#define H_DOP_TABLE { \
+    {1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}, \
+    {0.70710678f, 0.70710678f, 0.f}, {0.70710678f, -0.70710678f, 0.f}, {0.70710678f, 0.f, 0.70710678f}, {0.70710678f, 0.f, -0.70710678f}, \
+    {0.f, 0.70710678f, 0.70710678f}, {0.f, 0.70710678f, -0.70710678f}, \
+    {0.57735027f, 0.57735027f, 0.57735027f}, {0.57735027f, 0.57735027f, -0.57735027f}, {0.57735027f, -0.57735027f, 0.57735027f}, \
+    {0.57735027f, -0.57735027f, -0.57735027f}}
+__constant__ float c_dop[H_NDOP][3] = H_DOP_TABLE;
+static const float h_dop[H_NDOP][3] = H_DOP_TABLE;   // host copy for the model build
+
 // ---------------------------------------------------------------------------------------------- MPR (libccd)
 // The two objects of the pair being solved live in shared memory (U_COBJ): mpr_penetration / support_w are out of line and
 // would otherwise read them from the local-memory stack.
@@ -289,7 +299,7 @@ static_assert(sizeof(CObj) == 96 && U_CON_END * 4 % 8 == 0 && U_CON_END + 48 <= 
 struct Supp { V3 v, v1, v2; };
 // per-lane view of a mesh for the support function: lane k keeps the AABB of vertex cluster k in registers for the whole
 // MPR call, `warm` (uniform) is the last support vertex in local coordinates = a lower bound for the next query
-struct MeshLane { float lox, loy, loz, hix, hiy, hiz; V3 warm; int valid; };
+struct MeshLane { float lox, loy, loz, hix, hiy, hiz, rx, ry, rz; V3 warm; int valid; };
 struct SuppPt { V3 world, local; };
 
 // order-preserving float -> uint key (for redux.sync, one instruction instead of a 5-step shuffle tree)
@@ -299,13 +309,14 @@ __device__ __forceinline__ unsigned fkey(float f) {
 }
 __device__ __forceinline__ MeshLane mesh_lane(const CObj& o, int lane) {
   MeshLane ml;
-  ml.lox = ml.loy = ml.loz = ml.hix = ml.hiy = ml.hiz = 0.f;
+  ml.lox = ml.loy = ml.loz = ml.hix = ml.hiy = ml.hiz = ml.rx = ml.ry = ml.rz = 0.f;
   ml.warm = v3(0, 0, 0);
   ml.valid = 0;
   if (o.type == G_MESH && o.nvert > 0) {
     if (lane < o.ncl) {
-      const float4 lo = __ldg(o.cl + 2 * lane), hi = __ldg(o.cl + 2 * lane + 1);
+      const float4 lo = __ldg(o.cl + 2 * lane), hi = __ldg(o.cl + 2 * lane + 1), rp = __ldg(o.vert + 32 * lane);
       ml.lox = lo.x; ml.loy = lo.y; ml.loz = lo.z; ml.hix = hi.x; ml.hiy = hi.y; ml.hiz = hi.z;
+      ml.rx = rp.x; ml.ry = rp.y; ml.rz = rp.z;
     }
     const float4 v0 = __ldg(o.vert);
     ml.warm = v3(v0.x, v0.y, v0.z);
@@ -316,7 +327,7 @@ __device__ __forceinline__ MeshLane mesh_lane(const CObj& o, int lane) {
 
 // support point of a convex object along world direction `dir`; the whole warp calls this with identical
 // arguments.  Meshes: clusters of 32 vertices with a local AABB each (model build).  Upper bound of a cluster = AABB
-// support, lower bound of the answer = the projection of a known vertex (the previous support vertex); only clusters
+// support, lower bound of the answer = the best projection of a few known vertices; only clusters
 // whose upper bound reaches it are scanned, lane-strided, and reduced with redux.sync.  The dot products and the tie
 // rule (lowest ORIGINAL index) are those of a serial scan over all vertices.
 __device__ __noinline__ SuppPt support_w(const CObj& o, V3 dirw, int lane, MeshLane ml) {
@@ -332,10 +343,14 @@ __device__ __noinline__ SuppPt support_w(const CObj& o, V3 dirw, int lane, MeshL
     l = nn < F_MINVAL ? v3(0, 0, 0) : d * (o.size[0] / nn);
   } else {
     if (!ml.valid) ml = mesh_lane(o, lane);
-    float ub = -FLT_MAX;
-    if (lane < o.ncl)
+    // lower bound of the answer: the best of the previous support vertex and every cluster's first vertex
+    float ub = -FLT_MAX, lb = ml.warm.x * d.x + ml.warm.y * d.y + ml.warm.z * d.z;
+    if (lane < o.ncl) {
       ub = (d.x >= 0.f ? ml.hix : ml.lox) * d.x + (d.y >= 0.f ? ml.hiy : ml.loy) * d.y + (d.z >= 0.f ? ml.hiz : ml.loz) * d.z;
-    const float best0 = ml.warm.x * d.x + ml.warm.y * d.y + ml.warm.z * d.z;
+      lb = fmaxf(lb, ml.rx * d.x + ml.ry * d.y + ml.rz * d.z);
+    }
+    const unsigned k0 = __reduce_max_sync(FULLMASK, fkey(lb));
+    const float best0 = __uint_as_float((k0 & 0x80000000u) ? (k0 & 0x7fffffffu) : ~k0);
     const float slack = 1e-6f * (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));   // >> rounding of a 3-term dot of |v| < 1 m
     unsigned surv = __ballot_sync(FULLMASK, ub >= best0 - slack);
     float best = -FLT_MAX, bx = 0.f, by = 0.f, bz = 0.f;
@@ -365,7 +380,7 @@ __device__ __noinline__ SuppPt support_w(const CObj& o, V3 dirw, int lane, MeshL
 // o1's mesh view is not cached (no mesh is ever geom1 against a mesh in these models: it would be rebuilt per query)
 __device__ __forceinline__ void mpr_support(const CObj& o1, const CObj& o2, V3 dir, Supp& s, int lane, MeshLane& ml2) {
   MeshLane none;
-  none.lox = none.loy = none.loz = none.hix = none.hiy = none.hiz = 0.f; none.warm = v3(0, 0, 0); none.valid = 0;
+  none.lox = none.loy = none.loz = none.hix = none.hiy = none.hiz = none.rx = none.ry = none.rz = 0.f; none.warm = v3(0, 0, 0); none.valid = 0;
   s.v1 = support_w(o1, dir, lane, none).world;
   const SuppPt p2 = support_w(o2, -dir, lane, ml2);
   ml2.warm = ml2.valid ? p2.local : ml2.warm;
@@ -578,22 +593,32 @@ __device__ __noinline__ void collide(float* s, const DevModel& m, int lane, unsi
         if (dot(p2 - p1, col(pm, 2)) > cd.margin + rb2) active = false;
       }
       if (active && kind == K_CONVEX && m.geom_type[g2] == G_MESH && (m.geom_type[g1] == G_CAPSULE || m.geom_type[g1] == G_BOX)) {
-        // conservative cull before MPR: 6 separating-axis tests between g1's bounding box and the mesh's local AABB.
-        // A separated pair cannot penetrate, so MPR would report no contact as well.
+        // conservative cull before MPR: separating-axis tests along g1's own axes (against the mesh's local AABB) and
+        // along 13 fixed mesh-local directions whose vertex extents were tabulated at model build (a 26-DOP of the
+        // mesh).  A separated pair cannot penetrate, so MPR would report no contact as well.
         const M3 R1 = ldm(s + S_GMAT + 9 * g1), R2 = ldm(s + S_GMAT + 9 * g2);
         const float* sz = m.geom_size[g1];
         const bool cap = m.geom_type[g1] == G_CAPSULE;
         const float e1[3] = {sz[0], cap ? sz[0] : sz[1], cap ? sz[1] + sz[0] : sz[2]};
         const float* h2 = m.geom_aabb_h[g2];
-        const V3 dw = p2 + mulv(R2, ld3(m.geom_aabb_c[g2])) - p1;
-        const V3 d1 = mulTv(R1, dw), d2 = mulTv(R2, dw);
-        float R[9];   // R[3i+j] = axis i of g1 . axis j of the mesh
-        for (int i = 0; i < 3; i++)
-          for (int j = 0; j < 3; j++) R[3 * i + j] = fabsf(dot(col(R1, i), col(R2, j)));
         const float tol = cd.margin + 1e-6f;
-        for (int i = 0; i < 3; i++) {
-          if (fabsf(comp(d1, i)) > e1[i] + R[3 * i] * h2[0] + R[3 * i + 1] * h2[1] + R[3 * i + 2] * h2[2] + tol) active = false;
-          if (fabsf(comp(d2, i)) > h2[i] + R[i] * e1[0] + R[3 + i] * e1[1] + R[6 + i] * e1[2] + tol) active = false;
+        {
+          const V3 d1 = mulTv(R1, p2 + mulv(R2, ld3(m.geom_aabb_c[g2])) - p1);
+          for (int i = 0; i < 3; i++) {
+            const V3 a = col(R1, i);
+            const float ext = fabsf(dot(a, col(R2, 0))) * h2[0] + fabsf(dot(a, col(R2, 1))) * h2[1] + fabsf(dot(a, col(R2, 2))) * h2[2];
+            if (fabsf(comp(d1, i)) > e1[i] + ext + tol) active = false;
+          }
+        }
+        const V3 c1 = mulTv(R2, p1 - p2);                       // g1's centre in the mesh frame
+        const V3 a0 = mulTv(R2, col(R1, 0)), a1 = mulTv(R2, col(R1, 1)), a2 = mulTv(R2, col(R1, 2));   // g1's axes there
+#pragma unroll 1
+        for (int k = 0; k < H_NDOP; k++) {
+          const V3 u = v3(c_dop[k][0], c_dop[k][1], c_dop[k][2]);
+          const float ext = cap ? fabsf(dot(a2, u)) * sz[1] + sz[0]
+                                : fabsf(dot(a0, u)) * e1[0] + fabsf(dot(a1, u)) * e1[1] + fabsf(dot(a2, u)) * e1[2];
+          const float c = dot(c1, u);
+          if (c - ext > m.geom_dop[g2][k][1] + tol || c + ext < m.geom_dop[g2][k][0] - tol) active = false;
         }
       }
       if (active && kind != K_CONVEX && kind != K_PLANE_MESH) {

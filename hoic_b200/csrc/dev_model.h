@@ -16,6 +16,7 @@
 #define H_NROW (H_RCON + H_NEDGE)
 #define H_OBS 617
 #define H_FRAME 212
+#define H_NDOP 13      // directions of the mesh 26-DOP (pair culling)
 #define H_NHG 19       // hand collision geoms tracked for contact averaging (ho_im4.py:80-87)
 
 enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_BOX = 6, G_MESH = 7 };
@@ -75,6 +76,7 @@ struct DevModel {
   const float4* mesh_cl;         // device pointer: per cluster the local AABB (lo, hi) -> support-function pruning
   int geom_cladr[HN], geom_ncl[HN];
   float geom_aabb_c[HN][3], geom_aabb_h[HN][3];   // mesh geoms: local AABB centre / half sizes (conservative pair culling)
+  float geom_dop[HN][H_NDOP][2];                  // mesh geoms: [min, max] of the vertices along the c_dop directions
   // collision candidates in MuJoCo's signature order
   DevCand cand[H_MAXCAND];
   // env

@@ -826,6 +826,15 @@ bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<f
       for (int k = 0; k < 3; k++) { glo[k] = std::min(glo[k], lo[k]); ghi[k] = std::max(ghi[k], hi[k]); }
     }
     for (int k = 0; k < 3; k++) { D.geom_aabb_c[g][k] = 0.5f * (glo[k] + ghi[k]); D.geom_aabb_h[g][k] = 0.5f * (ghi[k] - glo[k]); }
+    const float (*dop)[3] = h_dop;
+    for (int k = 0; k < H_NDOP; k++) {
+      double mn = 1e30, mx = -1e30;
+      for (int i = 0; i < n; i++) {
+        const double pr = coord(i, 0) * dop[k][0] + coord(i, 1) * dop[k][1] + coord(i, 2) * dop[k][2];
+        mn = std::min(mn, pr); mx = std::max(mx, pr);
+      }
+      D.geom_dop[g][k][0] = (float)mn - 1e-6f; D.geom_dop[g][k][1] = (float)mx + 1e-6f;
+    }
   }
   // collision candidates in signature order (explicit pairs merged; mj_collision driver)
   int ncand = 0;
