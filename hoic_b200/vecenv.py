@@ -135,9 +135,10 @@ class HandMimicVecEnv:
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         assert a.shape == (self.n_envs, capi.ACT_DIM)
         if self.balance and self.n_envs > 7:
-            # group envs of similar cost (last step's solver iterations / contacts) into the same CTA
+            # group envs of similar cost (last step's solver iterations / contacts) into the same CTA, most expensive
+            # CTAs first (longest-processing-time order: the last wave of the grid is the cheapest one)
             capi.check(self.L.hoic_get_work(self._hb, capi.ptr(self._work), self._stream()), "hoic_get_work")
-            self._perm = torch.argsort(self._work, stable=True).to(torch.int32)
+            self._perm = torch.argsort(self._work, stable=True, descending=True).to(torch.int32)
             capi.check(self.L.hoic_set_env_order(self._hb, capi.ptr(self._perm)), "hoic_set_env_order")
         capi.check(self.L.hoic_step(self._hb, capi.ptr(a), capi.ptr(self.obs), capi.ptr(self.reward), capi.ptr(self.reward_info),
                                     capi.ptr(self.done), capi.ptr(self.fail), capi.ptr(self.end), capi.ptr(self.percent),
