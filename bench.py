@@ -217,20 +217,12 @@ def run_ours(args):
     value = world * N * args.steps / (total_ms_max * 1e-3)
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- e2e: host buffers through the C ABI wrapper, H2D of actions and D2H of obs/reward/done inside the timed region
+    # ---- e2e: the reference-facing call with HOST buffers (HandMimicVecEnv.step_host): H2D of the actions, env ordering,
+    # step kernel, auto-reset and D2H of obs / reward / done / info inside the timed region, one CUDA-graph launch per step
     h_act = torch.randn(N, 32).mul_(0.1).pin_memory()
-    h_obs = torch.empty(N, 617).pin_memory()
-    h_rew = torch.empty(N).pin_memory()
-    h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
-    d_act = torch.empty(N, 32, device=dev)
 
     def e2e_step():
-        d_act.copy_(h_act, non_blocking=True)
-        o, r, d, _ = env.step(d_act)
-        h_obs.copy_(o, non_blocking=True)
-        h_rew.copy_(r, non_blocking=True)
-        h_done.copy_(d, non_blocking=True)
-        torch.cuda.synchronize()
+        env.step_host(h_act)
 
     for _ in range(3):
         e2e_step()
@@ -273,7 +265,8 @@ def run_ours(args):
         "config": {"workload": f"{args.obj}_future5_light_add_geom, {N} batched envs per GPU ({cfg_name}), policy MLP + "
                                "env.step + reward + auto-reset per step", "envs_per_gpu": N, "sim_step": 15,
                    "l2": "flushed between steps (256 MiB write, untimed)", "parallelism": f"env-sharded x{world}"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N * 32 * 4), "d2h_bytes_per_step": int(N * (617 * 4 + 4 + 1))},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(env.h2d_bytes), "d2h_bytes_per_step": int(env.d2h_bytes),
+                "api": "HandMimicVecEnv.step_host (pinned host buffers in and out, CUDA graph of copies + hoic_step + auto-reset)"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,

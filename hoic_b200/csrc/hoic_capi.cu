@@ -934,6 +934,7 @@ extern "C" void hoic_model_destroy(hoic_model* m) {
   delete m;
 }
 
+__global__ void k_get_work(BatchDev B, int* out);
 extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_models, const int* env_model_id_host, int n_envs, int device) {
   if (!models || n_models < 1 || n_envs < 1) { set_err("hoic_batch_create: bad arguments"); return nullptr; }
   hoic_batch* b = new hoic_batch();
@@ -962,6 +963,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   b->smem_bytes = (size_t)S_TOTAL * sizeof(float);
   CUDA_OKP(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(b->smem_bytes * H_WPB)));
   CUDA_OKP(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
+  { cudaFuncAttributes fa; CUDA_OKP(cudaFuncGetAttributes(&fa, k_get_work)); }   // load now: launches may later be graph-captured
   CUDA_OKP(cudaFuncSetAttribute(k_forward_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
   CUDA_OKP(cudaFuncSetAttribute(k_substep_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
   return b;

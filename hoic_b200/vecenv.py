@@ -150,7 +150,73 @@ class HandMimicVecEnv:
         info = {"fail": self.fail, "end": self.end, "percent": self.percent, "reward_info": self.reward_info}
         return self.obs, self.reward, self.done, info
 
-    # ------------------------------------------------------------------ state access (parity / checkpointing)
+    # ------------------------------------------------------------------ host-buffer step (the reference-facing call)
+    def step_host(self, actions_host):
+        """`env.step` for callers that live on the host, like the reference's sampler: `actions_host` is a [N, 32] float32
+        array / CPU tensor; returns (obs, reward, done, info) as pinned CPU tensors that stay valid until the next call.
+        The H2D copy of the actions, env ordering, the step kernel, the in-place auto-reset and the D2H copies of the
+        results are captured once into a CUDA graph and replayed as ONE launch per step."""
+        if getattr(self, "_hs", None) is None:
+            self._build_host_step()
+        hs = self._hs
+        src = torch.as_tensor(actions_host, dtype=torch.float32)
+        if src.data_ptr() != hs["act"].data_ptr():
+            hs["act"].copy_(src.reshape(self.n_envs, capi.ACT_DIM))
+        if hs["graph"] is not None:
+            hs["graph"].replay()
+        else:
+            self._host_step_body()
+        torch.cuda.current_stream(self.device).synchronize()
+        info = {"fail": hs["fail"], "end": hs["end"], "percent": hs["percent"], "reward_info": hs["reward_info"]}
+        return hs["obs"], hs["reward"], hs["done"], info
+
+    def _host_step_body(self):
+        hs = self._hs
+        hs["d_act"].copy_(hs["act"], non_blocking=True)
+        obs, rew, done, info = self.step(hs["d_act"])
+        hs["obs"].copy_(obs, non_blocking=True)
+        hs["reward"].copy_(rew, non_blocking=True)
+        hs["done"].copy_(done, non_blocking=True)
+        hs["fail"].copy_(info["fail"], non_blocking=True)
+        hs["end"].copy_(info["end"], non_blocking=True)
+        hs["percent"].copy_(info["percent"], non_blocking=True)
+        hs["reward_info"].copy_(info["reward_info"], non_blocking=True)
+
+    def _build_host_step(self):
+        N = self.n_envs
+        pin = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype).pin_memory()
+        self._hs = dict(act=pin(N, capi.ACT_DIM), obs=pin(N, capi.OBS_DIM), reward=pin(N), percent=pin(N),
+                        reward_info=pin(N, capi.INFO_DIM), done=pin(N, dtype=torch.uint8), fail=pin(N, dtype=torch.uint8),
+                        end=pin(N, dtype=torch.uint8), d_act=torch.zeros(N, capi.ACT_DIM, device=self.device), graph=None)
+        self._hs["act"].zero_()
+        self.h2d_bytes = N * capi.ACT_DIM * 4
+        self.d2h_bytes = N * (capi.OBS_DIM * 4 + 4 + 4 + capi.INFO_DIM * 4 + 3)
+        try:
+            # warm up the torch ops of the body on a side stream without touching the environments, then capture
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            rng = self.gen.get_state()
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.sample_assignments()
+                    torch.argsort(self._work, stable=True, descending=True).to(torch.int32)
+                    self._hs["d_act"].copy_(self._hs["act"], non_blocking=True)
+                    self._hs["obs"].copy_(self.obs, non_blocking=True)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.gen.set_state(rng)
+            g = torch.cuda.CUDAGraph()
+            g.register_generator_state(self.gen)
+            with torch.cuda.graph(g, stream=side):
+                self._host_step_body()
+            torch.cuda.synchronize(self.device)
+            self._hs["graph"] = g
+        except Exception as e:                     # no graph support for this generator / torch build: plain launches
+            import warnings
+            warnings.warn(f"step_host: CUDA graph capture unavailable ({e}); using eager launches")
+            self._hs["graph"] = None
+
+
     def get_state(self):
         q = torch.empty(self.n_envs, capi.NQ, dtype=torch.float32, device=self.device)
         v = torch.empty(self.n_envs, capi.NV, dtype=torch.float32, device=self.device)

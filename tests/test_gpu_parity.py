@@ -224,3 +224,26 @@ def test_mixed_object_batch():
         o, r, d, _ = env.step(a)
     assert torch.isfinite(o).all() and env.counters()["mpr_calls"] > 0
     env.close(); env2.close()
+
+
+def test_step_host_graph_equals_eager_step():
+    from hoic_b200.vecenv import HandMimicVecEnv
+    """The host-buffer call (CUDA graph of copies + env ordering + hoic_step + auto-reset) returns what `step` returns."""
+    mdl = model("box")
+    motions = [mdl.motion(s) for s in range(1, 4)]
+    envs = [HandMimicVecEnv(mdl, 64, motions, device=0, seed=7, auto_reset=True) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    rng = np.random.RandomState(3)
+    for t in range(12):
+        a = np.clip(rng.randn(64, 32) * 0.3, -1, 1).astype(np.float32)
+        o0, r0, d0, i0 = envs[0].step(torch.as_tensor(a))
+        o1, r1, d1, i1 = envs[1].step_host(a)
+        assert not o1.is_cuda and o1.is_pinned()
+        assert np.array_equal(o0.cpu().numpy(), o1.numpy()), t
+        assert np.array_equal(r0.cpu().numpy(), r1.numpy()) and np.array_equal(d0.cpu().numpy(), d1.numpy())
+        assert np.array_equal(i0["fail"].cpu().numpy(), i1["fail"].numpy())
+        assert np.array_equal(i0["reward_info"].cpu().numpy(), i1["reward_info"].numpy())
+    assert envs[1]._hs["graph"] is not None, "CUDA graph capture fell back to eager launches"
+    for e in envs:
+        e.close()
