@@ -173,10 +173,12 @@ __device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
 // out[r] = (J v)[r] for all rows; v in shared (32 floats).  Uses U_BV as scratch.
 __device__ __noinline__ void mul_J(float* s, int lane, int nbasis, int nedge, const float* v, float* out) {
   const int* rinfo = (const int*)(s + U_RINFO);
+#pragma unroll 1
   for (int a = lane; a < nbasis; a += 32) {
     const float* B = s + U_B + a * B_STRIDE;
     float acc0 = 0.f, acc1 = 0.f;
     unsigned mk = ((const unsigned*)(s + U_BMASK))[a];
+#pragma unroll 1
     for (int t = 0; mk; t += 2) {
       const int j0 = __ffs(mk) - 1;
       mk &= mk - 1;
@@ -195,6 +197,7 @@ __device__ __noinline__ void mul_J(float* s, int lane, int nbasis, int nedge, co
     const int ri = rinfo[H_RLIM + lane];
     out[H_RLIM + lane] = ((ri >> 8) & 1 ? 1.f : -1.f) * v[ri & 255];
   }
+#pragma unroll 1
   for (int e = lane; e < nedge; e += 32) {
     const int ri = rinfo[H_RCON + e], c = ri & 255, ed = ri >> 8;
     const float* ci = s + U_CINFO + 8 * c;
@@ -229,6 +232,7 @@ __device__ __forceinline__ void row_eval(const float* s, const DevModel& m, int 
 __device__ __noinline__ float rows_update(float* s, const DevModel& m, int lane, int nedge, const float* jar, bool write) {
   float cost = 0.f;
   const int nrow = H_RCON + nedge;
+#pragma unroll 1
   for (int r = lane; r < nrow; r += 32) {
     float f, c, k;
     row_eval(s, m, r, jar[r], f, c, k);
@@ -242,33 +246,36 @@ __device__ __noinline__ float rows_update(float* s, const DevModel& m, int lane,
 
 // (M v)[lane] with M stored by (dof, ancestor depth) (S_MS): own row over the ancestors, the column part from the one
 // descendant per level inside the lane's chain, and for the trunk (hub) dofs the sum over all branch dofs by warp sums.
+// Rolled loops throughout: the Newton iteration only runs fast while its code stays resident in the 32 KB instruction
+// cache (profiles/README.md), so code bytes count more than executed instructions here.
 __device__ __noinline__ float mul_M(const float* s, const DevModel& m, int lane, const float* v) {
   const bool on = lane < m.nv;
   const int dep = on ? m.dof_depth[lane] : 0;
   const bool trunk = on && m.dof_is_trunk[lane];
   const bool branch = (m.branch_mask >> lane) & 1u;
-  const unsigned a0 = m.dof_anc_at[lane][0], a1 = m.dof_anc_at[lane][1], a2 = m.dof_anc_at[lane][2];
   const unsigned c0 = m.dof_desc_at[lane][0], c1 = m.dof_desc_at[lane][1], c2 = m.dof_desc_at[lane][2];
-  float r[12];
-  ld_row12(r, s + S_MS + lane * MS_STRIDE);
+  const float* Mr = s + S_MS + lane * MS_STRIDE;
   const float vl = v[lane];
-  float acc0 = on ? s[S_MS + lane * MS_STRIDE + dep] * vl : vl, acc1 = 0.f;
-#pragma unroll
-  for (int d = 0; d < T_MAXD - 1; d++) {
-    const int j = tbyte(a0, a1, a2, d);
-    if (j != 0xff) acc0 = fmaf(r[d], v[j], acc0);
+  float acc0 = vl, acc1 = 0.f;
+  if (on) {
+    acc0 = Mr[dep] * vl;
+    int d = 0;
+#pragma unroll 1
+    for (unsigned mk = m.dof_anc[lane]; mk; mk &= mk - 1, d++) acc0 = fmaf(Mr[d], v[__ffs(mk) - 1], acc0);
   }
-#pragma unroll
+#pragma unroll 1
   for (int l = 1; l < T_MAXD; l++) {
-    const int k = tbyte(c0, c1, c2, l);
+    const unsigned w = l < 4 ? c0 : (l < 8 ? c1 : c2);
+    const int k = (int)((w >> (8 * (l & 3))) & 0xffu);
     if (k != 0xff) acc1 = fmaf(s[S_MS + k * MS_STRIDE + dep], v[k], acc1);
   }
   {
-    // unconditional (uniform control flow keeps the shuffles free of convergence barriers); no hub -> no branch lanes
+    // hub: every trunk dof collects its column over all branch dofs by warp sums (uniform control flow; no hub -> no
+    // branch lanes and the sums are zero)
     float corr = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int t = 0; t <= T_HUBD; t++) {
-      const float q = wsum(branch ? r[t] * vl : 0.f);
+      const float q = wsum(branch ? Mr[t] * vl : 0.f);
       if (t == dep) corr = q;
     }
     if (trunk) acc1 += corr;
@@ -282,22 +289,28 @@ __device__ __noinline__ float newton_gradient(float* s, const DevModel& m, int l
   const int* rinfo = (const int*)(s + U_RINFO);
   const int* binfo = (const int*)(s + U_BINFO);
   (void)m;
+#pragma unroll 1
   for (int a = lane; a < nbasis; a += 32) {
     const int c = binfo[a] & 255, k = binfo[a] >> 8;
     const float* ci = s + U_CINFO + 8 * c;
     const int eo = H_RCON + ((const int*)ci)[2], ne = ((const int*)ci)[3];
     float g;
-    if (k == 0) { g = 0.f; for (int e = 0; e < ne; e++) g += s[U_FORCE + eo + e]; }
+    if (k == 0) {
+      g = 0.f;
+#pragma unroll 1
+      for (int e = 0; e < ne; e++) g += s[U_FORCE + eo + e];
+    }
     else { const float mu = k <= 2 ? ci[4] : ci[5]; g = mu * (s[U_FORCE + eo + 2 * (k - 1)] - s[U_FORCE + eo + 2 * (k - 1) + 1]); }
     s[U_BV + a] = g;
   }
   __syncwarp();
   float jtf = s[U_FORCE + H_RFR + lane];
+#pragma unroll 1
   for (int r = 0; r < nlim; r++) {
     const int ri = rinfo[H_RLIM + r];
     if ((ri & 255) == lane) jtf += ((ri >> 8) & 1 ? 1.f : -1.f) * s[U_FORCE + H_RLIM + r];
   }
-#pragma unroll 4
+#pragma unroll 1
   for (int a = 0; a < nbasis; a++) {
     const unsigned mk = ((const unsigned*)(s + U_BMASK))[a];
     if ((mk >> lane) & 1u) jtf = fmaf(s[U_B + a * B_STRIDE + __popc(mk & ((1u << lane) - 1u))], s[U_BV + a], jtf);
@@ -314,24 +327,25 @@ __device__ __noinline__ float newton_gradient(float* s, const DevModel& m, int l
 __device__ __noinline__ float newton_weights(float* s, const DevModel& m, int lane, int nlim, int ncon) {
   const int* rinfo = (const int*)(s + U_RINFO);
   const float* jar = s + U_JAR;
+#pragma unroll 1
   for (int c = lane; c < ncon; c += 32) {
     // w[0] = C00, w[1..3] = C0k, w[4..6] = Ckk
     float* ci = s + U_CINFO + 8 * c;
     const int eo = H_RCON + ((const int*)ci)[2], ne = ((const int*)ci)[3];
     const float D = ci[6];
     float* w = s + U_CON + 16 * c;
-    float c00 = 0.f, c0k[3] = {0, 0, 0}, ckk[3] = {0, 0, 0};
+    w[0] = 0.f; w[1] = 0.f; w[2] = 0.f; w[3] = 0.f; w[4] = 0.f; w[5] = 0.f; w[6] = 0.f;
+#pragma unroll 1
     for (int e = 0; e < ne; e++) {
       const float act = jar[eo + e] < 0.f ? D : 0.f;
-      c00 += act;
+      w[0] += act;
       if (ne > 1) {
         const int k = e / 2;
         const float mu = k < 2 ? ci[4] : ci[5];
-        c0k[k] += ((e & 1) ? -mu : mu) * act;
-        ckk[k] += mu * mu * act;
+        w[1 + k] += ((e & 1) ? -mu : mu) * act;
+        w[4 + k] += mu * mu * act;
       }
     }
-    w[0] = c00; w[1] = c0k[0]; w[2] = c0k[1]; w[3] = c0k[2]; w[4] = ckk[0]; w[5] = ckk[1]; w[6] = ckk[2];
   }
   float diag = 0.f;
   {
@@ -339,6 +353,7 @@ __device__ __noinline__ float newton_weights(float* s, const DevModel& m, int la
     row_eval(s, m, H_RFR + lane, jar[H_RFR + lane], f, c, k);
     diag += k;
   }
+#pragma unroll 1
   for (int r = 0; r < nlim; r++) {
     const int ri = rinfo[H_RLIM + r];
     if ((ri & 255) == lane && jar[H_RLIM + r] < 0.f) diag += s[U_D + H_RLIM + r];
@@ -417,6 +432,7 @@ __device__ __noinline__ void ls_eval(const float* s, const DevModel& m, int lane
                                         float qg2, float& d1, float& d2) {
   float a1 = 0.f, a2 = 0.f;
   const int nrow = H_RCON + nedge;
+#pragma unroll 1
   for (int r = lane; r < nrow; r += 32) {
     const float jv = s[U_JV + r];
     float f, c, k;
@@ -442,6 +458,7 @@ __device__ __noinline__ float line_search(float* s, const DevModel& m, int lane,
   d1 = wsum(sv * s[S_GRAD + lane]);
   if (!(d1 < 0.f)) return 0.f;
   const float gtol = 1e-6f * fabsf(d1);
+#pragma unroll 1
   for (int it = 0; it < 24; it++) {
     ls_eval(s, m, lane, nedge, alpha, qg1, qg2, d1, d2);
     evals++;
@@ -498,6 +515,7 @@ __device__ __noinline__ int newton_move(float* s, const DevModel& m, int lane, i
   s[S_QACC + lane] = qacc;
   s[S_MA + lane] = ma;
   bool changed = false;
+#pragma unroll 1
   for (int r = lane; r < H_RCON + nedge; r += 32) {
     const float x0 = s[U_JAR + r], x1 = x0 + alpha * s[U_JV + r];
     s[U_JAR + r] = x1;
