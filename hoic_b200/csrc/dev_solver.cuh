@@ -246,36 +246,35 @@ __device__ __noinline__ float rows_update(float* s, const DevModel& m, int lane,
 
 // (M v)[lane] with M stored by (dof, ancestor depth) (S_MS): own row over the ancestors, the column part from the one
 // descendant per level inside the lane's chain, and for the trunk (hub) dofs the sum over all branch dofs by warp sums.
-// Rolled loops throughout: the Newton iteration only runs fast while its code stays resident in the 32 KB instruction
-// cache (profiles/README.md), so code bytes count more than executed instructions here.
+// The helpers of the Newton iteration below use rolled loops (code bytes cost instruction fetches, profiles/README.md);
+// mul_M is the exception: its unrolled form measured 4 % faster on the whole step than a rolled one.
 __device__ __noinline__ float mul_M(const float* s, const DevModel& m, int lane, const float* v) {
   const bool on = lane < m.nv;
   const int dep = on ? m.dof_depth[lane] : 0;
   const bool trunk = on && m.dof_is_trunk[lane];
   const bool branch = (m.branch_mask >> lane) & 1u;
+  const unsigned a0 = m.dof_anc_at[lane][0], a1 = m.dof_anc_at[lane][1], a2 = m.dof_anc_at[lane][2];
   const unsigned c0 = m.dof_desc_at[lane][0], c1 = m.dof_desc_at[lane][1], c2 = m.dof_desc_at[lane][2];
-  const float* Mr = s + S_MS + lane * MS_STRIDE;
+  float r[12];
+  ld_row12(r, s + S_MS + lane * MS_STRIDE);
   const float vl = v[lane];
-  float acc0 = vl, acc1 = 0.f;
-  if (on) {
-    acc0 = Mr[dep] * vl;
-    int d = 0;
-#pragma unroll 1
-    for (unsigned mk = m.dof_anc[lane]; mk; mk &= mk - 1, d++) acc0 = fmaf(Mr[d], v[__ffs(mk) - 1], acc0);
+  float acc0 = on ? s[S_MS + lane * MS_STRIDE + dep] * vl : vl, acc1 = 0.f;
+#pragma unroll
+  for (int d = 0; d < T_MAXD - 1; d++) {
+    const int j = tbyte(a0, a1, a2, d);
+    if (j != 0xff) acc0 = fmaf(r[d], v[j], acc0);
   }
-#pragma unroll 1
+#pragma unroll
   for (int l = 1; l < T_MAXD; l++) {
-    const unsigned w = l < 4 ? c0 : (l < 8 ? c1 : c2);
-    const int k = (int)((w >> (8 * (l & 3))) & 0xffu);
+    const int k = tbyte(c0, c1, c2, l);
     if (k != 0xff) acc1 = fmaf(s[S_MS + k * MS_STRIDE + dep], v[k], acc1);
   }
   {
-    // hub: every trunk dof collects its column over all branch dofs by warp sums (uniform control flow; no hub -> no
-    // branch lanes and the sums are zero)
+    // unconditional (uniform control flow keeps the shuffles free of convergence barriers); no hub -> no branch lanes
     float corr = 0.f;
-#pragma unroll 1
+#pragma unroll
     for (int t = 0; t <= T_HUBD; t++) {
-      const float q = wsum(branch ? Mr[t] * vl : 0.f);
+      const float q = wsum(branch ? r[t] * vl : 0.f);
       if (t == dep) corr = q;
     }
     if (trunk) acc1 += corr;
