@@ -161,47 +161,24 @@ __device__ __forceinline__ double warp_transpose_sum(double (&v)[32], int lane) 
 #define QP_NPER 12                        // variables per lane (380 / 32 rounded up)
 static_assert(((QP_RED + 1) & ~1) + 64 <= U_QP_END, "QP scratch exceeds the union region reserved for it");
 
-// returns rfc_score; fills rest[6]
-__device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,
-                        V3 org_now, float* rest, unsigned& qp_iters) {
+// Dual Newton iterations of the residual-force QP on the per-variable data left in QP_C / QP_G by rfc_qp.  NPER = variables
+// per lane: the loops over a lane's variables are unrolled (their values live in registers), so small problems (most
+// grasps touch 2-5 hand geoms = 40-100 variables) run a 3- or 6-wide instance instead of the 12-wide one.
+template <int NPER>
+__device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T, float* rest, unsigned& qp_iters) {
   const double eps = 1e-7, sqw = 100.0;
-  const int n = 4 * ec * ncg;
   double* red = reinterpret_cast<double*>(s + ((QP_RED + 1) & ~1));
-  // per-variable data: penalty c_i and wrench column g_i
-  for (int i = lane; i < n; i += 32) {
-    QpVar v;
-    V3 pos;
-    qp_var(s, i, ec, obj_p, (float)sqw, v, &pos);
-    const int pt = i >> 2, e = i & 3, k = pt / ec;
-    const float* cf = s + QP_CF + 12 * k;
-    const V3 nn = ld3(cf + 3), t = ld3(cf + 6), b = ld3(cf + 9);
-    const int g1 = ((const int*)(s + QP_G1))[k];
-    const V3 crh = pos - (ld3(gpos_now + 3 * g1) + org_now), cro = pos - obj_p;
-    const V3 cvh = ld3(s + QP_GV + 6 * k) + cross(ld3(s + QP_GV + 6 * k + 3), crh);
-    const V3 cvo = obj_v + cross(obj_w, cro);
-    const V3 rel = cvo - cvh;
-    const float vnd = dot(nn, rel);
-    const V3 vn = nn * vnd, vt = rel - vn;
-    float c = vnd <= 0.f ? norm(vn) : 0.f;
-    const float dirs[4] = {-dot(vt, t), dot(vt, t), -dot(vt, b), dot(vt, b)};
-    int mx = 0;
-    for (int a = 1; a < 4; a++) if (dirs[a] > dirs[mx]) mx = a;
-    if (e != mx) c += norm(vt);
-    s[QP_C + i] = c;
-    for (int a = 0; a < 6; a++) s[QP_G + 6 * i + a] = (float)v.g[a];
-  }
-  __syncwarp();
   const double b6[6] = {F.x, F.y, F.z, sqw * T.x, sqw * T.y, sqw * T.z};
   double bmax = 0;
   for (int a = 0; a < 6; a++) bmax = fmax(bmax, fabs(b6[a]));
   double lam[6] = {0, 0, 0, 0, 0, 0};
-  double sv[QP_NPER], gd[QP_NPER];       // per owned variable: s_i = c_i + g_i.lam and g_i.dl
+  double sv[NPER], gd[NPER];       // per owned variable: s_i = c_i + g_i.lam and g_i.dl
   for (int it = 0; it < 60; it++) {
     double acc[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) acc[k] = 0;
 #pragma unroll
-    for (int t = 0; t < QP_NPER; t++) {
+    for (int t = 0; t < NPER; t++) {
       const int i = lane + 32 * t;
       sv[t] = 1.0;
       if (i < n) {
@@ -245,7 +222,7 @@ __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, 
     double ll = 0, dd = 0, bd = 0;
     for (int a = 0; a < 6; a++) { ll += lam[a] * dl[a]; dd += dl[a] * dl[a]; bd += b6[a] * dl[a]; }
 #pragma unroll
-    for (int t = 0; t < QP_NPER; t++) {
+    for (int t = 0; t < NPER; t++) {
       const int i = lane + 32 * t;
       gd[t] = 0;
       if (i < n) {
@@ -258,7 +235,7 @@ __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, 
     for (int ls = 0; ls < 40; ls++) {
       double a1 = 0, a2 = 0;
 #pragma unroll
-      for (int t = 0; t < QP_NPER; t++) {
+      for (int t = 0; t < NPER; t++) {
         const double sa = sv[t] + alpha * gd[t];
         if (sa < 0) { a1 += sa * gd[t]; a2 += gd[t] * gd[t]; }
       }
@@ -289,6 +266,41 @@ __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, 
   for (int k = 0; k < 3; k++) { rest[k] = (float)r[k]; rest[3 + k] = (float)(r[3 + k] / sqw); }
   return (float)(sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) + sqrt(r[3] * r[3] + r[4] * r[4] + r[5] * r[5]));
 }
+
+// returns rfc_score; fills rest[6]
+__device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,
+                        V3 org_now, float* rest, unsigned& qp_iters) {
+  const double sqw = 100.0;
+  const int n = 4 * ec * ncg;
+  // per-variable data: penalty c_i and wrench column g_i
+  for (int i = lane; i < n; i += 32) {
+    QpVar v;
+    V3 pos;
+    qp_var(s, i, ec, obj_p, (float)sqw, v, &pos);
+    const int pt = i >> 2, e = i & 3, k = pt / ec;
+    const float* cf = s + QP_CF + 12 * k;
+    const V3 nn = ld3(cf + 3), t = ld3(cf + 6), b = ld3(cf + 9);
+    const int g1 = ((const int*)(s + QP_G1))[k];
+    const V3 crh = pos - (ld3(gpos_now + 3 * g1) + org_now), cro = pos - obj_p;
+    const V3 cvh = ld3(s + QP_GV + 6 * k) + cross(ld3(s + QP_GV + 6 * k + 3), crh);
+    const V3 cvo = obj_v + cross(obj_w, cro);
+    const V3 rel = cvo - cvh;
+    const float vnd = dot(nn, rel);
+    const V3 vn = nn * vnd, vt = rel - vn;
+    float c = vnd <= 0.f ? norm(vn) : 0.f;
+    const float dirs[4] = {-dot(vt, t), dot(vt, t), -dot(vt, b), dot(vt, b)};
+    int mx = 0;
+    for (int a = 1; a < 4; a++) if (dirs[a] > dirs[mx]) mx = a;
+    if (e != mx) c += norm(vt);
+    s[QP_C + i] = c;
+    for (int a = 0; a < 6; a++) s[QP_G + 6 * i + a] = (float)v.g[a];
+  }
+  __syncwarp();
+  if (n <= 96) return rfc_qp_core<3>(s, lane, n, F, T, rest, qp_iters);
+  if (n <= 192) return rfc_qp_core<6>(s, lane, n, F, T, rest, qp_iters);
+  return rfc_qp_core<QP_NPER>(s, lane, n, F, T, rest, qp_iters);
+}
+
 
 // ---- observation v5 (617 floats) from the last forward's poses and the current qpos / qvel
 __device__ __forceinline__ void put_rot2(float* o, const M3& R) {
