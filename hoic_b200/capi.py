@@ -9,13 +9,15 @@ LIB_PATH = os.environ.get("HOIC_LIB", os.path.join(_HERE, "libhoic_b200.so"))   
 _lib = None
 
 OBS_DIM, ACT_DIM, FRAME_DIM, INFO_DIM, NQ, NV, MAX_CONTACTS = 617, 32, 212, 9, 33, 32, 32
+NHG = 19
+REC_MAXCON, REC_CON, REC_STRIDE, SURF_MAXPT, SURF_PT, SURF_STRIDE = 32, 116, 116 + 19 * 32, 95, 8, 8 + 15 * 95 + 3
 
 EXPORTS = [
     "hoic_last_error", "hoic_version", "hoic_model_create", "hoic_model_destroy", "hoic_batch_create",
     "hoic_batch_destroy", "hoic_batch_size", "hoic_set_motions", "hoic_set_reward_weights", "hoic_set_mode",
     "hoic_reset", "hoic_step", "hoic_get_state", "hoic_set_state", "hoic_set_cur_t", "hoic_get_warmstart",
     "hoic_set_warmstart", "hoic_get_contacts", "hoic_substep_debug", "hoic_get_derived", "hoic_get_rfc",
-    "hoic_get_counters", "hoic_launch_count", "hoic_measure_fp32_peak", "hoic_get_work", "hoic_set_env_order",
+    "hoic_get_counters", "hoic_launch_count", "hoic_measure_fp32_peak", "hoic_get_work", "hoic_set_env_order", "hoic_set_record", "hoic_preprocess_seq",
 ]
 
 
@@ -52,6 +54,8 @@ def lib():
         L.hoic_set_motions.argtypes = [vp, vp, vp, vp, ip]
         L.hoic_set_reward_weights.argtypes = [vp, vp]
         L.hoic_set_mode.argtypes = [vp, ip]
+        L.hoic_set_record.argtypes = [vp, vp, vp]
+        L.hoic_preprocess_seq.argtypes = [vp, vp, vp, ip, C.c_float, ip, vp, vp, vp, vp]
         L.hoic_reset.argtypes = [vp, vp, vp, vp, vp, vp]
         L.hoic_step.argtypes = [vp] + [vp] * 8 + [vp]
         L.hoic_get_state.argtypes = [vp, vp, vp, vp]

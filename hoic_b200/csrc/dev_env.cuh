@@ -75,6 +75,64 @@ __device__ __noinline__ void record_contacts(float* s, const DevModel& m, int la
   __syncwarp();
 }
 
+// ---- test-mode recording (compute_data_frame, ho_im4.py:599-609; layout HOIC_REC_* in include/hoic.h).  Like the
+// reference, which records after sim.step(), body positions / contacts / contact forces / qacc are those of the forward
+// that produced the new state.  record_contact_frames runs before the solve (the Newton weights reuse the head of the
+// contact records), record_forward after it (U_FORCE / U_CINFO live), record_state after Euler.
+__device__ __noinline__ void record_contact_frames(const float* s, const DevModel& m, int lane, float* o) {
+  const int ncon = ((const int*)(s + S_MISC))[MI_NCON];
+  const V3 org = ld3(s + S_ORG);
+  int n = 0;
+  for (int c = 0; c < ncon; c++) {
+    const float* cr = s + U_CON + 16 * c;
+    const DevCand& cd = m.cand[__float_as_int(cr[13])];
+    if (cd.hand_slot < 0) continue;
+    if (n < HOIC_REC_MAXCON) {
+      float* q = o + HOIC_REC_CON + 19 * n;
+      if (lane < 12) q[lane] = cr[lane] + (lane < 3 ? comp(org, lane) : 0.f);
+      else if (lane == 18) q[18] = (float)cd.g1;
+    }
+    n++;
+  }
+  if (lane == 0) o[114] = (float)(n < HOIC_REC_MAXCON ? n : HOIC_REC_MAXCON);
+}
+__device__ __noinline__ void record_forward(const float* s, const DevModel& m, int lane, float* o) {
+  const int* misc = (const int*)(s + S_MISC);
+  const V3 org = ld3(s + S_ORG);
+  for (int i = lane; i < 3 * m.n_hand_body; i += 32) {
+    const int b = i / 3, k = i - 3 * b;
+    o[i] = s[S_XPOS + 3 * m.hand_body_idx[b] + k] + comp(org, k);
+  }
+  if (lane < 6) o[108 + lane] = s[S_QACC + m.nv - 6 + lane];
+  const int ncon = misc[MI_NCON];
+  const float* F = s + U_FORCE + H_RCON;
+  int n = 0;
+  for (int c = 0; c < ncon; c++) {
+    const DevCand& cd = m.cand[__float_as_int(s[U_CON + 16 * c + 13])];
+    if (cd.hand_slot < 0) continue;
+    if (n < HOIC_REC_MAXCON && lane < 6) {
+      // mj_contactForce: mju_decodePyramid of the edge forces (frictionless contacts: the single row's force)
+      const float* ci = s + U_CINFO + 8 * c;
+      const int eoff = ((const int*)ci)[2], ne = ((const int*)ci)[3], k = lane;
+      float f = 0.f;
+      if (ne == 1) f = k == 0 ? F[eoff] : 0.f;
+      else if (k == 0) { for (int e = 0; e < ne; e++) f += F[eoff + e]; }
+      else if (2 * k <= ne) f = (F[eoff + 2 * (k - 1)] - F[eoff + 2 * (k - 1) + 1]) * (k <= 2 ? ci[4] : ci[5]);
+      o[HOIC_REC_CON + 19 * n + 12 + lane] = f;
+    }
+    n++;
+  }
+}
+__device__ __noinline__ void record_state(const float* s, const DevModel& m, int lane, V3 vf, V3 vt, float* o) {
+  if (lane < m.nhand_q) o[63 + lane] = s[S_QPOS + lane];
+  if (lane < 7) o[95 + lane] = s[S_QPOS + m.nhand_q + lane];
+  if (lane < 6) {
+    o[102 + lane] = s[S_QVEL + m.nv - 6 + lane];
+    o[89 + lane] = lane < 3 ? comp(vf, lane) : comp(vt, lane - 3);
+  }
+  if (lane == 0) o[115] = 1.f;
+}
+
 // pytorch3d-style matrix -> axis-angle (uhc/utils/transforms.py:99-158, 414-490)
 __device__ __noinline__ V3 matrix_to_axis_angle(const M3& R) {
   const float* r = R.m;
@@ -165,7 +223,7 @@ static_assert(((QP_RED + 1) & ~1) + 64 <= U_QP_END, "QP scratch exceeds the unio
 // per lane: the loops over a lane's variables are unrolled (their values live in registers), so small problems (most
 // grasps touch 2-5 hand geoms = 40-100 variables) run a 3- or 6-wide instance instead of the 12-wide one.
 template <int NPER>
-__device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T, float* rest, unsigned& qp_iters) {
+__device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T, float* rest, unsigned& qp_iters, float* surf) {
   const double eps = 1e-7, sqw = 100.0;
   double* red = reinterpret_cast<double*>(s + ((QP_RED + 1) & ~1));
   const double b6[6] = {F.x, F.y, F.z, sqw * T.x, sqw * T.y, sqw * T.z};
@@ -256,10 +314,23 @@ __device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T,
   }
   // primal recovery: x_i = max(0, -s_i/eps); residual wrench in the scaled space
   double gx[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = lane; i < n; i += 32) {
-    double g[6], si = (double)s[QP_C + i];
-    for (int k = 0; k < 6; k++) { g[k] = (double)s[QP_G + 6 * i + k]; si += g[k] * lam[k]; }
-    if (si < 0) { const double x = -si / eps; for (int k = 0; k < 6; k++) gx[k] += g[k] * x; }
+  for (int i = lane; i < ((n + 31) & ~31); i += 32) {
+    double g[6] = {0, 0, 0, 0, 0, 0}, x = 0;
+    if (i < n) {
+      double si = (double)s[QP_C + i];
+      for (int k = 0; k < 6; k++) { g[k] = (double)s[QP_G + 6 * i + k]; si += g[k] * lam[k]; }
+      if (si < 0) { x = -si / eps; for (int k = 0; k < 6; k++) gx[k] += g[k] * x; }
+    }
+    if (surf) {
+      // test-mode record: surface_contact_force of a point = (ts A) x over its 4 pyramid edges = 4 adjacent lanes
+      double f[3];
+      for (int k = 0; k < 3; k++) {
+        f[k] = g[k] * x;
+        f[k] += __shfl_xor_sync(FULLMASK, f[k], 1);
+        f[k] += __shfl_xor_sync(FULLMASK, f[k], 2);
+      }
+      if (i < n && (i & 3) == 0) { float* q = surf + HOIC_SURF_PT + 15 * (i >> 2) + 12; q[0] = (float)f[0]; q[1] = (float)f[1]; q[2] = (float)f[2]; }
+    }
   }
   double r[6];
   for (int k = 0; k < 6; k++) r[k] = b6[k] - wsumd(gx[k]);
@@ -269,7 +340,7 @@ __device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T,
 
 // returns rfc_score; fills rest[6]
 __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,
-                        V3 org_now, float* rest, unsigned& qp_iters) {
+                        V3 org_now, float* rest, unsigned& qp_iters, float* surf) {
   const double sqw = 100.0;
   const int n = 4 * ec * ncg;
   // per-variable data: penalty c_i and wrench column g_i
@@ -294,11 +365,18 @@ __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, 
     if (e != mx) c += norm(vt);
     s[QP_C + i] = c;
     for (int a = 0; a < 6; a++) s[QP_G + 6 * i + a] = (float)v.g[a];
+    if (surf && e == 0) {   // surface_contact_frames: the expanded point with the averaged frame (ho_im4.py:983-992)
+      float* q = surf + HOIC_SURF_PT + 15 * pt;
+      st3(q, pos); st3(q + 3, nn); st3(q + 6, t); st3(q + 9, b);
+    }
   }
   __syncwarp();
-  if (n <= 96) return rfc_qp_core<3>(s, lane, n, F, T, rest, qp_iters);
-  if (n <= 192) return rfc_qp_core<6>(s, lane, n, F, T, rest, qp_iters);
-  return rfc_qp_core<QP_NPER>(s, lane, n, F, T, rest, qp_iters);
+  float score;
+  if (n <= 96) score = rfc_qp_core<3>(s, lane, n, F, T, rest, qp_iters, surf);
+  else if (n <= 192) score = rfc_qp_core<6>(s, lane, n, F, T, rest, qp_iters, surf);
+  else score = rfc_qp_core<QP_NPER>(s, lane, n, F, T, rest, qp_iters, surf);
+  if (surf && lane < 8) surf[lane] = lane == 0 ? (float)(n >> 2) : (lane == 7 ? 1.f : rest[lane - 1]);
+  return score;
 }
 
 

@@ -33,6 +33,8 @@ struct BatchDev {
   int mode_train;
   unsigned long long* counters;       // hoic_counters as 12 x u64
   const int* perm;                    // optional env order (load balancing), NULL = identity
+  float* rec_frames;                  // test-mode recording (hoic_set_record), NULL = off
+  float* rec_surface;
 };
 
 struct StepOut {
@@ -128,7 +130,7 @@ __device__ __forceinline__ EnvCtx make_ctx(const BatchDev& B, const int* ints) {
 
 // ---- tail of env.step after the substeps: averages, contact classification, residual-force QP (ho_im4.py:553-565, 631)
 __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, const float* og, float old_obj_vel, V3 vf, V3 vt,
-                                        float* rest, int& ncg_out, unsigned& qp_iters) {
+                                        float* rest, int& ncg_out, unsigned& qp_iters, float* surf) {
   float rfc_score = 0.f;
   const int nhg = m.hand_geom1 - m.hand_geom0 + 1;
   const float inv_dt = 1.0f / (m.sim_step * m.timestep);
@@ -190,7 +192,7 @@ __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, c
         rfc_score = norm(F) + 1e4f * norm(T);
         rest[0] = F.x; rest[1] = F.y; rest[2] = F.z; rest[3] = T.x; rest[4] = T.y; rest[5] = T.z;
       } else {
-        rfc_score = rfc_qp(s, lane, ncg, m.surface_contact ? 5 : 1, F, T, obj_p, obj_v, obj_w, s + S_GPOS, org, rest, qp_iters);
+        rfc_score = rfc_qp(s, lane, ncg, m.surface_contact ? 5 : 1, F, T, obj_p, obj_v, obj_w, s + S_GPOS, org, rest, qp_iters, surf);
       }
     }
   }
@@ -250,6 +252,10 @@ __global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const fl
   V3 vf = v3(0, 0, 0), vt = v3(0, 0, 0);
   float pq = cq, pq32 = cq32, pv = cv;
   bool ok = live;      // false once this env failed (or the slot is padding): skips work, keeps hitting the barriers
+  float* recf = (B.rec_frames && live) ? B.rec_frames + (size_t)envc * m.sim_step * HOIC_REC_STRIDE : nullptr;
+  float* surf = (B.rec_surface && live) ? B.rec_surface + (size_t)envc * HOIC_SURF_STRIDE : nullptr;
+  if (recf) for (int i = lane; i < m.sim_step * HOIC_REC_STRIDE; i += 32) recf[i] = 0.f;
+  if (surf) for (int i = lane; i < HOIC_SURF_STRIDE; i += 32) surf[i] = 0.f;
 #ifdef H_PROF
   int prof_phase = 8;
   long long prof_t0 = clock64();
@@ -305,13 +311,16 @@ __global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const fl
     HB(2);
     if (ok) {
       build_rows(s, m, lane);
+      if (recf) record_contact_frames(s, m, lane, recf + (size_t)k * HOIC_REC_STRIDE);
     }
     HB(7);
     ok = phase_solve(s, m, lane, cnt, ok);
     HB(4);
     if (ok) {
+      if (recf) record_forward(s, m, lane, recf + (size_t)k * HOIC_REC_STRIDE);
       ok = euler_step(s, m, lane, nullptr);
       if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
+      if (recf && ok) record_state(s, m, lane, vf, vt, recf + (size_t)k * HOIC_REC_STRIDE);
     }
   }
   __syncthreads();
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const fl
   if (flags & 2) cnt.fail_over++;
   float rfc_score = 0.f, rest[6] = {0, 0, 0, 0, 0, 0};
   int ncg = 0;
-  if (!fail) rfc_score = step_tail(s, m, lane, og, old_obj_vel, vf, vt, rest, ncg, cnt.qp);
+  if (!fail) rfc_score = step_tail(s, m, lane, og, old_obj_vel, vf, vt, rest, ncg, cnt.qp, surf);
   // ---- bookkeeping, termination, reward, observation (ho_im4.py:641-662)
   ctx.cur_t += 1;
   float reward = 0.f;
@@ -512,6 +521,60 @@ __global__ void __launch_bounds__(32) k_substep_debug(BatchDev B, const float* c
   st[ST_PQVEL + lane] = pv;
   if (lane == 0) { st[ST_QPOS + 32] = s[S_QPOS + 32]; st[ST_PQPOS + 32] = pq32; }
   flush_counters(B, cnt, lane, 0);
+}
+
+// dataset preprocessing of one raw sequence, one warp per frame (DatasetSingleDepth.preprocess_seq, dataset_singledepth.py:78-142)
+__global__ void __launch_bounds__(32) k_preprocess(const DevModel* mp, const float* __restrict__ hand, const float* __restrict__ obj, int T,
+                                                   float freq, int clip, float* frames, int* cmask, float* cpos) {
+  extern __shared__ float s[];
+  const int t = blockIdx.x, lane = threadIdx.x;
+  if (t >= T) return;
+  const DevModel& m = *mp;
+  int* misc = (int*)(s + S_MISC);
+  if (lane < 16) misc[lane] = 0;
+  const int nh = m.nhand_q;
+  const int a = t == 0 ? 1 : t, b = a - 1;           // vel[0] = vel[1] (:157-158)
+  float* f = frames + (size_t)t * H_FRAME;
+  float q = 0.f;
+  if (lane < nh) {
+    // np.clip(hand_dof_seq, lower, upper) (:100); the raw sequence is processed unclipped (:109)
+    const float lo = clip ? m.jnt_range[lane][0] : -F_MAXVAL, hi = clip ? m.jnt_range[lane][1] : F_MAXVAL;
+    q = fminf(fmaxf(hand[(size_t)t * nh + lane], lo), hi);
+    float v = fminf(fmaxf(hand[(size_t)a * nh + lane], lo), hi) - fminf(fmaxf(hand[(size_t)b * nh + lane], lo), hi);
+    if (lane >= 3 && lane < 6) { while (v > F_PI) v -= 2.f * F_PI; while (v < -F_PI) v += 2.f * F_PI; }
+    f[F_DOF + lane] = q;
+    f[F_DOFVEL + lane] = v * freq;
+  }
+  if (lane < 7) f[F_OBJPOSE + lane] = obj[(size_t)7 * t + lane];
+  if (lane < 3) f[F_OBJVEL + lane] = (obj[(size_t)7 * a + lane] - obj[(size_t)7 * b + lane]) * freq;
+  {
+    const M3 Rd = mulmT(q2m(qnormalize(ldq(obj + (size_t)7 * a + 3))), q2m(qnormalize(ldq(obj + (size_t)7 * b + 3))));
+    const V3 w = matrix_to_axis_angle(Rd) * freq;
+    if (lane < 3) f[F_OBJANGVEL + lane] = comp(w, lane);
+  }
+  // forward of (hand dofs, object pose): body poses (:222-237) and the contact pre-pass (:187-220)
+  s[S_QPOS + lane] = lane < nh ? q : obj[(size_t)7 * t + lane - nh];
+  if (lane == 0) s[S_QPOS + 32] = obj[(size_t)7 * t + 32 - nh];
+  s[S_QVEL + lane] = 0.f;
+  __syncwarp();
+  pos_stage(s, m, lane);
+  const V3 org = ld3(s + S_ORG);
+  for (int i = lane; i < 3 * m.n_hand_body; i += 32) f[F_BPOS + i] = s[S_XPOS + 3 * m.hand_body_idx[i / 3] + i % 3] + comp(org, i % 3);
+  for (int i = lane; i < 4 * m.n_hand_body; i += 32) f[F_BQUAT + i] = s[S_XQUAT + 4 * m.hand_body_idx[i / 4] + i % 4];
+  if (!cmask || !cpos) return;
+  unsigned c0 = 0, c1 = 0;
+  collide(s, m, lane, c0, c1);
+  if (lane < H_NHG) cmask[(size_t)t * H_NHG + lane] = 0;
+  for (int i = lane; i < 3 * H_NHG; i += 32) cpos[(size_t)t * H_NHG * 3 + i] = 0.f;
+  __syncwarp();
+  const int ncon = misc[MI_NCON];
+  for (int c = 0; c < ncon; c++) {       // contact_info[g1] = contact.pos: the last contact of a hand geom wins
+    const float* cr = s + U_CON + 16 * c;
+    const int slot = m.cand[__float_as_int(cr[13])].hand_slot;
+    if (slot < 0 || slot >= H_NHG) continue;
+    if (lane < 3) cpos[((size_t)t * H_NHG + slot) * 3 + lane] = cr[lane] + comp(org, lane);
+    else if (lane == 3) cmask[(size_t)t * H_NHG + slot] = 1;
+  }
 }
 
 // ================================================================================================ host side
@@ -1007,6 +1070,14 @@ extern "C" int hoic_set_reward_weights(hoic_batch* b, const float* w_host) {
   return 0;
 }
 
+extern "C" int hoic_set_record(hoic_batch* b, float* frames, float* surface) {
+  if (!b) return set_err("hoic_set_record: null batch");
+  if ((frames == nullptr) != (surface == nullptr)) return set_err("hoic_set_record: pass both buffers or neither");
+  b->b.rec_frames = frames;
+  b->b.rec_surface = surface;
+  return 0;
+}
+
 extern "C" int hoic_set_mode(hoic_batch* b, int train) {
   if (!b) return set_err("hoic_set_mode: null batch");
   b->b.mode_train = train ? 1 : 0;
@@ -1157,6 +1228,18 @@ __global__ void k_fma_peak(float* out, int iters, float a, float b) {
   for (int i = 0; i < 16; i++) s += x[i];
   if (s == 12345.678f) out[0] = s;
 }
+extern "C" int hoic_preprocess_seq(const hoic_model* m, const float* hand_pose_seq, const float* obj_pose_seq, int T, float motion_freq,
+                                   int clip, float* frames_out, int* contact_mask, float* contact_pos, void* stream) {
+  if (!m || !hand_pose_seq || !obj_pose_seq || !frames_out) return set_err("hoic_preprocess_seq: bad arguments");
+  if (T < 2) return set_err("hoic_preprocess_seq: a sequence needs at least 2 frames (finite differences)");
+  if ((contact_mask == nullptr) != (contact_pos == nullptr)) return set_err("hoic_preprocess_seq: pass both contact outputs or neither");
+  CUDA_OK(cudaSetDevice(m->device));
+  k_preprocess<<<T, 32, (size_t)S_TOTAL * sizeof(float), (cudaStream_t)stream>>>(m->dev, hand_pose_seq, obj_pose_seq, T, motion_freq, clip,
+                                                                                 frames_out, contact_mask, contact_pos);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int hoic_measure_fp32_peak(int device, double* tflops_host) {
   if (!tflops_host) return set_err("hoic_measure_fp32_peak: null output");
   CUDA_OK(cudaSetDevice(device));

@@ -99,6 +99,33 @@ class HandMimicVecEnv:
     def set_mode(self, mode):
         capi.check(self.L.hoic_set_mode(self._hb, 1 if mode == "train" else 0), "hoic_set_mode")
 
+    def set_record(self, on=True):
+        """Test-mode recording of `MotionData` (ho_im4.py:27-41): with it on, every `step` also fills the per-substep
+        frames of `compute_data_frame` (:599-609) and the surface-contact record of `solve_rfc` (:1072-1081)."""
+        if on:
+            sim_step = int(self.models[0].cfg.sim_step)
+            self._rec_frames = torch.zeros(self.n_envs, sim_step, capi.REC_STRIDE, dtype=torch.float32, device=self.device)
+            self._rec_surface = torch.zeros(self.n_envs, capi.SURF_STRIDE, dtype=torch.float32, device=self.device)
+        else:
+            self._rec_frames = self._rec_surface = None
+        capi.check(self.L.hoic_set_record(self._hb, capi.ptr(self._rec_frames), capi.ptr(self._rec_surface)), "hoic_set_record")
+
+    def motion_data(self):
+        """Record of the last `step` as a dict of device tensors named like the reference's `MotionData` lists; the
+        leading dims are [env, substep].  `valid` marks substeps that ran, `n_contact` / `n_surface` the filled rows."""
+        if getattr(self, "_rec_frames", None) is None:
+            raise capi.HoicError("motion_data: call set_record(True) first")
+        f, u = self._rec_frames, self._rec_surface
+        N, S = f.shape[0], f.shape[1]
+        con = f[:, :, capi.REC_CON:].reshape(N, S, capi.REC_MAXCON, 19)
+        pts = u[:, capi.SURF_PT:capi.SURF_PT + 15 * capi.SURF_MAXPT].reshape(N, capi.SURF_MAXPT, 15)
+        return dict(hand_kps=f[:, :, 0:63].reshape(N, S, 21, 3), hand_qpos=f[:, :, 63:89], compensate_ft=f[:, :, 89:95],
+                    obj_pose=f[:, :, 95:102], obj_vel=f[:, :, 102:108], obj_acc=f[:, :, 108:114],
+                    n_contact=f[:, :, 114].to(torch.int32), valid=f[:, :, 115] > 0,
+                    contact_frames=con[..., 0:12], contact_force=con[..., 12:18], contact_body=con[..., 18].to(torch.int32),
+                    n_surface=u[:, 0].to(torch.int32), rest_obj_ft=u[:, 1:7], surface_valid=u[:, 7] > 0,
+                    surface_contact_frames=pts[..., 0:12], surface_contact_force=pts[..., 12:15])
+
     # ------------------------------------------------------------------ episodes
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

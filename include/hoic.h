@@ -28,7 +28,21 @@ extern "C" {
 #define HOIC_INFO_DIM 9      /* ho_mimic_reward_9 info vector, ho_reward.py:1043-1046 */
 #define HOIC_NQ 33
 #define HOIC_NV 32
+#define HOIC_NHG 19          /* hand collision geoms (hand_geom_range, ho_im4.py:80-87) */
 #define HOIC_MAX_CONTACTS 32 /* per-env contact capacity of the kernels (the MJCF's nconmax is 100) */
+/* test-mode recording (MotionData, ho_im4.py:27-41).  One frame per physics substep (compute_data_frame :599-609):
+ *   [0,63) hand_kps = body_xpos of the 21 hand bodies   [63,89) hand_qpos   [89,95) compensate_ft (obj_vf, obj_vt)
+ *   [95,102) obj_pose   [102,108) obj_vel   [108,114) obj_acc = qacc[-6:]   [114] number of hand-object contacts
+ *   [115] 1 if the substep ran   then per contact 19 floats: pos[3] frame[9] mj_contactForce[6] hand geom id */
+#define HOIC_REC_MAXCON 32
+#define HOIC_REC_CON 116
+#define HOIC_REC_STRIDE (HOIC_REC_CON + 19 * HOIC_REC_MAXCON)
+/* ... and one record per env step from solve_rfc (ho_im4.py:1072-1081):
+ *   [0] number of expanded contact points  [1,7) rest_obj_ft  [7] 1 if the QP ran (there was a contact)
+ *   then per point 15 floats: surface_contact_frames pos[3] frame[9], surface_contact_force[3] */
+#define HOIC_SURF_MAXPT 95
+#define HOIC_SURF_PT 8
+#define HOIC_SURF_STRIDE (HOIC_SURF_PT + 15 * HOIC_SURF_MAXPT + 3)
 
 typedef struct hoic_model hoic_model;
 typedef struct hoic_batch hoic_batch;
@@ -58,12 +72,26 @@ int hoic_batch_size(const hoic_batch* b);
 int hoic_set_motions(hoic_batch* b, const float* frames_host, const int* motion_offset_host, const int* motion_len_host,
                      int n_motions);
 
+/* replaces DatasetSingleDepth.preprocess_seq for one raw sequence (uhc/data_loaders/dataset_singledepth.py:78-142): clips the
+ * hand dofs to the joint ranges when clip != 0 (:100; the raw sequence of :109 is processed with clip = 0), finite-difference velocities (compute_vel_from_seq :152-185), FK of the 21 hand
+ * bodies (compute_body_pos_quat_from_seq :222-237) and, when the contact outputs are given, the per-frame hand-object
+ * contact pre-pass (compute_contact_info :187-220; contact_info[g1] = contact.pos, indexed here by hand geom slot
+ * g1 - hand_geom0).  hand_pose_seq[T][26], obj_pose_seq[T][7] (xyz + wxyz) -> frames_out[T][HOIC_FRAME_DIM],
+ * contact_mask[T][HOIC_NHG], contact_pos[T][HOIC_NHG][3]; all device pointers; one warp per frame. */
+int hoic_preprocess_seq(const hoic_model* m, const float* hand_pose_seq, const float* obj_pose_seq, int T, float motion_freq,
+                        int clip, float* frames_out, int* contact_mask, float* contact_pos, void* stream);
+
 /* replaces cfg.reward_weights after cfg.update_adaptive_params (uhc/utils/config_utils/handmimic_config.py:157-195):
  * w_host[24] = w_p w_wp w_v w_j w_op w_or w_ov w_orfc k_p k_wp k_v k_j k_op k_or k_ov k_orfc, rest reserved. */
 int hoic_set_reward_weights(hoic_batch* b, const float* w_host);
 
 /* replaces env.set_mode (ho_im4.py:132): train=1 applies the tracking-error termination of ho_im4.py:655-656 */
 int hoic_set_mode(hoic_batch* b, int train);
+
+/* replaces the MotionData lists filled in mode == 'test' (ho_im4.py:547-548 compute_data_frame, :1072-1081): every
+ * following hoic_step writes frames[N][sim_step][HOIC_REC_STRIDE] and surface[N][HOIC_SURF_STRIDE] (device buffers kept
+ * by reference; NULL, NULL switches recording off).  Contact forces are mj_contactForce of the pyramidal rows. */
+int hoic_set_record(hoic_batch* b, float* frames, float* surface);
 
 /* replaces env.reset() (mujoco_env.py:95-105 + ho_im4.py:690-716): for every env with mask[i]!=0 (mask NULL = all)
  * take expert = motion[motion_id[i]][start_idx[i]:], state <- its frame 0, mj_resetData + forward, cur_t = 0,

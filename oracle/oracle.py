@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 OBS_DIM, FRAME_DIM = 617, 212
+REC_STRIDE, SURF_STRIDE = 116 + 19 * 32, 8 + 15 * 95 + 3
 
 
 def build(force=False):
@@ -166,6 +167,21 @@ class OracleEnv:
                 "mpr_iters", "qp_n", "qp_iters", "n_avg_cp"]
         return dict(zip(keys, c.tolist()))
 
+    def contact_forces(self):
+        """mj_contactForce of every contact of the last forward: [ncon, 6]."""
+        buf = np.zeros(100 * 6)
+        k = lib().orc_env_ncontact_force(self.env, _p(buf))
+        return buf[:6 * k].reshape(k, 6).copy()
+
+    def set_record(self, on=True):
+        lib().orc_env_set_record(self.env, C.c_int(1 if on else 0))
+
+    def record(self):
+        """(frames [sim_step, REC_STRIDE], surface [SURF_STRIDE]) of the last step (layout: include/hoic.h HOIC_REC_*)."""
+        frames, surface = np.zeros(15 * REC_STRIDE), np.zeros(SURF_STRIDE)
+        k = lib().orc_get_record(self.env, _p(frames), _p(surface))
+        return frames[:k * REC_STRIDE].reshape(k, REC_STRIDE).copy(), surface
+
     def rfc(self):
         r = np.zeros(7)
         lib().orc_get_rfc(self.env, _p(r))
@@ -175,3 +191,19 @@ class OracleEnv:
         r = np.zeros(5)
         lib().orc_env_ho_diff(self.env, _p(r))
         return r
+
+
+def preprocess_seq(blob: bytes, hand_pose_seq, obj_pose_seq, motion_freq=30.0, clip=True):
+    """Oracle of hoic_preprocess_seq: (frames [T,212], contact_mask [T,19], contact_pos [T,19,3])."""
+    L = lib()
+    mdl = L.orc_model_create(blob, len(blob))
+    hand = np.ascontiguousarray(hand_pose_seq, dtype=np.float64)
+    obj = np.ascontiguousarray(obj_pose_seq, dtype=np.float64)
+    T = hand.shape[0]
+    frames, cmask, cpos = np.zeros((T, FRAME_DIM)), np.zeros((T, 24), dtype=np.int32), np.zeros((T, 24, 3))
+    L.orc_preprocess_seq.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.orc_preprocess_seq(C.c_void_p(mdl), _p(hand), _p(obj), T, C.c_double(motion_freq), 1 if clip else 0, _p(frames), _p(cmask), _p(cpos))
+    L.orc_model_destroy(C.c_void_p(mdl))
+    if rc != 0:
+        raise ValueError("orc_preprocess_seq: need at least 2 frames")
+    return frames, cmask[:, :19].copy(), cpos[:, :19].copy()

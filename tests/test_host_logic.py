@@ -221,6 +221,34 @@ def test_oracle_free_fall_and_rest():
     c = env.contacts()
     tab = c[c[:, 13] == 1]
     assert len(tab) == 4 and np.allclose(tab[:, 4:7], [0, 0, 1]) and set(tab[:, 15]) == {4.0}
+    # mj_contactForce (ho_im4.py:876): the four normal forces carry the weight, no friction is needed at rest
+    cf = env.contact_forces()[c[:, 13] == 1]
+    assert abs(cf[:, 0].sum() - m * 9.81) < 1e-9 and (cf[:, 0] > 0).all() and np.abs(cf[:, 1:]).max() < 1e-9
+
+
+def test_oracle_contact_force_decodes_the_pyramid():
+    """The decoded contact forces (mj_contactForce), rotated to the world frame and summed over the object's contacts,
+    reproduce the constraint force on the object's translational dofs up to its 0.001 N friction-loss rows."""
+    env = oracle_env("box")
+    env.reset()
+    rng = np.random.RandomState(3)
+    seen = 0
+    for t in range(40):
+        env.step(np.clip(rng.randn(32) * 0.1, -1, 1))
+        c, cf, f = env.contacts(), env.contact_forces(), env.get("efc_force")
+        adr = len(f) - int(sum(1 if d == 1 else 2 * (d - 1) for d in c[:, 15]))
+        tot = np.zeros(3)
+        for k in range(len(c)):
+            dim = int(c[k, 15])
+            ne = 1 if dim == 1 else 2 * (dim - 1)
+            fe = f[adr:adr + ne]
+            adr += ne
+            assert abs(cf[k, 0] - fe.sum()) < 1e-12 and not cf[k, dim:].any()
+            if c[k, 14] >= 21:                      # geom2 is an object geom: the force acts on the object along +normal
+                tot += cf[k, :3] @ c[k, 4:13].reshape(3, 3)
+                seen += dim > 1
+        assert np.abs(env.get("qfrc_constraint")[26:29] - tot).max() < 0.001 + 1e-9
+    assert seen >= 10
 
 
 def test_oracle_newton_reaches_the_optimum():
@@ -386,3 +414,29 @@ def test_oracle_reproduces_goldens(obj):
         env.clear_warnings()
         env.mj_step()
         assert np.abs(env.get("qvel") - G["sub_v1"][k]).max() < 1e-8 and env.counters()["ncon"] == G["sub_ncon"][k]
+
+
+def test_oracle_preprocess_seq_vs_numpy_derivation():
+    """orc_preprocess_seq (the checker of hoic_preprocess_seq) against the independent numpy restatement of
+    preprocess_seq in hoic_b200/motion.py (dataset_singledepth.py:78-237), with out-of-range dofs and a wrap of a rotation dof."""
+    import oracle
+    mdl = model("bottle")
+    ex = mdl.motion(2)
+    hand, obj = ex["hand_dof_seq"].copy(), ex["obj_pose_seq"].copy()
+    hand[:, 7] += 3.0                      # beyond the joint range: clipped
+    hand[100:, 4] += 2 * np.pi - 0.01      # a jump through +-pi on a rotation dof: wrapped finite difference
+    M = mdl.M if mdl.M else mdl.compiled
+    fr, cm, cp = oracle.preprocess_seq(mdl.blob, hand, obj, 30)
+    ref = hmotion.pack_frames(hmotion.derive_expert(M, hand, obj, 30))
+    assert np.abs(fr - ref).max() < 1e-12
+    lo, hi = mdl.arrays["jnt_range"][:-1, 0], mdl.arrays["jnt_range"][:-1, 1]
+    assert (fr[:, :26] >= lo - 1e-15).all() and (fr[:, :26] <= hi + 1e-15).all()
+    assert np.abs(fr[:, 26 + 4]).max() < 30 * np.pi          # no 2 pi jump in the rotation velocity
+    # contact pre-pass on the unperturbed motion: nothing touches during the approach, several hand geoms in the grasp
+    _, cm, cp = oracle.preprocess_seq(mdl.blob, ex["hand_dof_seq"], obj, 30)
+    assert cm[:10].sum() == 0 and cm[150:].sum(1).min() >= 5
+    assert (np.abs(cp[cm == 0]) == 0).all() and np.abs(cp[cm == 1] - obj[np.nonzero(cm)[0], :3]).max() < 0.25
+    raw, _, _ = oracle.preprocess_seq(mdl.blob, hand, obj, 30, clip=False)
+    assert np.abs(raw[:, 7] - hand[:, 7]).max() == 0
+    with pytest.raises(ValueError):
+        oracle.preprocess_seq(mdl.blob, hand[:1], obj[:1], 30)
