@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 METRIC = "env-steps/sec at 1/2/4/8 B200 vs mujoco_py sampler on N host cores"
 UNIT = "env-steps/s"
 ALGO_BYTES_PER_ENV_STEP = 6000.0          # ~1500 float32 of state / action / obs traffic per env step
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch from the `ncu --set full` capture of this workload
+# (profiles/r01_v12_k_step_raw.csv: 16.76 MB read + 6.20 MB write at box / 4096 envs); other workloads: not captured -> null
+NCU_TRAFFIC_BYTES = {("box", 4096): 16.756480e6 + 6.199808e6}
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline
@@ -95,7 +98,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -269,7 +272,8 @@ def run_ours(args):
                 "api": "HandMimicVecEnv.step_host (pinned host buffers in and out, CUDA graph of copies + hoic_step + auto-reset)"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get((args.obj, N)),
+                     "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * N, "traffic_source": "profiles/r01_v12_k_step_raw.csv (ncu --set full, per launch)",
                      "peak_source": peak_src, "kernel": "k_step", "kernel_ms": kernel_ms,
                      "note": "neither HBM nor tensor cores bind this kernel: it is FP32-pipe / latency bound, see roofline_fp32"},
         "roofline_fp32": {"bound": "fp32", "achieved": fp32_ach, "peak": tf.value, "unit": "TFLOP/s", "frac": fp32_ach / max(tf.value, 1e-9),

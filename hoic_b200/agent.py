@@ -144,5 +144,71 @@ class AgentHandMimic:
         return dict(log=log, T_sample=t1 - t0, T_update=t2 - t1, T_total=t2 - t0, samples=batch.T * batch.N * self.world,
                     horizon=batch.T, **upd)
 
+    # ------------------------------------------------------------------ agent_handmimic.py:339-403
+    @torch.no_grad()
+    def eval_policy(self, motions=None, model_index=0, record=False, max_steps=10000):
+        """`eval_policy` of the reference, batched: every test motion runs in its own environment, all at once, in
+        mode 'test' (no tracking-error termination, ho_im4.py:655-656) from frame 0 with the mean action and the frozen
+        observation normaliser.  Returns the reference's metrics dict averaged over the motions (`per_motion` holds
+        them one by one) and, with `record`, the `MotionData` tensors of every step ([step][env, substep, ...])."""
+        import numpy as np
+        mdl = self.env.models[model_index]
+        if motions is None:
+            motions = [mdl.motion(1)]
+        n = len(motions)
+        env = HandMimicVecEnv(mdl, n, motions, device=self.device.index, seed=0, auto_reset=False, random_start=False, balance=False)
+        env.set_mode("test")
+        env.set_reward_weights(self.cfg.reward_vector())
+        if record:
+            env.set_record(True)
+        hb = torch.as_tensor(np.asarray(mdl.arrays["env_hand_body_idx"]).astype(np.int64), device=self.device)
+        T = max(int(m["seq_len"]) for m in motions)
+        gt = torch.zeros(n, T, 26, device=self.device)
+        gtj = torch.zeros(n, T, len(hb), 3, device=self.device)
+        for i, m in enumerate(motions):
+            L = int(m["seq_len"])
+            gt[i, :L] = torch.as_tensor(m["hand_dof_seq"], dtype=torch.float32)
+            gtj[i, :L] = torch.as_tensor(m["body_pos_seq"], dtype=torch.float32)
+            gt[i, L:], gtj[i, L:] = gt[i, L - 1], gtj[i, L - 1]
+        lens = torch.as_tensor([int(m["seq_len"]) for m in motions], device=self.device)
+        obs = env.reset(motion_id=list(range(n)), start_idx=[0] * n)
+        alive = torch.ones(n, dtype=torch.bool, device=self.device)
+        acc = {k: torch.zeros(n, device=self.device) for k in ("pose_err", "mpjpe", "reward", "steps")}
+        info_sum = torch.zeros(n, 9, device=self.device)
+        percent = torch.zeros(n, device=self.device)
+        frames = []
+        ar = torch.arange(n, device=self.device)
+        for t in range(max_steps):
+            q, _ = env.get_state()
+            xpos = env.get_derived()[0]
+            ti = torch.remainder(torch.full_like(lens, t), lens)
+            w = alive.to(torch.float32)
+            acc["pose_err"] += w * torch.linalg.norm(gt[ar, ti, 6:] - q[:, 6:26], dim=-1)
+            acc["mpjpe"] += w * torch.linalg.norm(gtj[ar, ti] - xpos[:, hb], dim=-1).mean(-1)
+            x = self.running_state(obs, update=False)
+            act = self.policy_net(x)[0]                      # select_action(mean_action=True)
+            obs, r, done, info = env.step(act)
+            acc["reward"] += w * r
+            acc["steps"] += w
+            info_sum += w[:, None] * info["reward_info"]
+            percent = torch.where(alive, info["percent"], percent)
+            if record:
+                frames.append({k: v.clone() for k, v in env.motion_data().items()})
+            alive = alive & ~done.bool()
+            if not bool(alive.any()):
+                break
+        steps = acc["steps"].clamp(min=1)
+        names = ("pose_reward", "wpose_reward", "jpos_reward", "vel_reward", "obj_pos_reward", "obj_rot_reward", "obj_vel_reward",
+                 "obj_rfc_reward")
+        per = dict(pose_err=acc["pose_err"] / steps, mpjpe=acc["mpjpe"] / steps, avg_reward=acc["reward"] / steps,
+                   total_reward=acc["reward"], percent=percent, **{k: info_sum[:, i] / steps for i, k in enumerate(names)})
+        per = {k: v.cpu().numpy() for k, v in per.items()}
+        metrics = {k: float(v.mean()) for k, v in per.items()}
+        metrics["per_motion"] = per
+        if record:
+            metrics["motion_data"] = frames
+        env.close()
+        return metrics
+
     def close(self):
         self.env.close()

@@ -56,3 +56,41 @@ def test_noise_rate_masks_exploration():
     info = agent.update_params(batch)
     assert np.isfinite(info["surrogate"])
     agent.close()
+
+
+def test_eval_policy_batched_test_mode():
+    """eval_policy (agent_handmimic.py:339-403) with every test motion in its own env: metrics of the reference, test mode
+    (no early termination), optional MotionData recording; the oracle replays motion 0 with the same mean actions."""
+    import sys, os
+    from common import oracle_env
+    from hoic_b200.agent import AgentHandMimic
+    mdl = model("box")
+    agent = AgentHandMimic(mdl, 64)
+    agent.per_epoch_update(0)
+    agent.sample(64 * 4)                                      # fills the observation normaliser
+    motions = [mdl.motion(s) for s in (1, 2, 3)]
+    m = agent.eval_policy(motions=motions, record=True, max_steps=12)
+    per = m["per_motion"]
+    assert set(("pose_err", "mpjpe", "avg_reward", "total_reward", "pose_reward", "obj_rfc_reward", "percent")) <= set(m)
+    assert per["pose_err"].shape == (3,) and np.isfinite(per["mpjpe"]).all() and (per["avg_reward"] > 0).all()
+    assert abs(m["percent"] - 12.0 / 299.0) < 1e-6           # 12 steps of a 300-frame motion, nobody terminated early
+    assert len(m["motion_data"]) == 12 and m["motion_data"][0]["hand_kps"].shape == (3, 15, 21, 3)
+    # oracle replay of motion 0: same policy (float64 copy), frozen normaliser, mean action
+    orc = oracle_env("box", seed=1)
+    orc.set_mode("test")
+    orc.set_reward_weights(agent.cfg.reward_vector())
+    obs = orc.reset()
+    pol = copy.deepcopy(agent.policy_net).double().cpu()
+    mean, std = agent.running_state.mean.double().cpu(), agent.running_state.std.double().cpu()
+    pe = mp = rw = 0.0
+    hb = np.asarray(mdl.arrays["env_hand_body_idx"]).astype(int)
+    for t in range(12):
+        pe += np.linalg.norm(motions[0]["hand_dof_seq"][t][6:] - orc.get("qpos")[6:26])
+        mp += np.linalg.norm(motions[0]["body_pos_seq"][t] - orc.get("xpos").reshape(-1, 3)[hb], axis=-1).mean()
+        x = torch.clamp((torch.as_tensor(obs) - mean) / (std + 1e-8), -5, 5)
+        a = pol(x[None])[0][0].detach().numpy()
+        obs, r, d, info = orc.step(a)
+        rw += r
+    assert abs(per["pose_err"][0] - pe / 12) < 1e-3 and abs(per["mpjpe"][0] - mp / 12) < 1e-4
+    assert abs(per["avg_reward"][0] - rw / 12) < 2e-3
+    agent.close()
