@@ -210,5 +210,13 @@ class AgentHandMimic:
         env.close()
         return metrics
 
+    # ------------------------------------------------------------------ agent_handmimic.py:135-186
+    def save_checkpoint(self, path):
+        ppo.save_checkpoint(path, self.policy_net, self.value_net, self.running_state)
+
+    def load_checkpoint(self, path):
+        """Opens a checkpoint written here or a released `iter_XXXX.p` of the reference (same pickle layout)."""
+        return ppo.load_checkpoint(path, self.policy_net, self.value_net, self.running_state)
+
     def close(self):
         self.env.close()

@@ -7,6 +7,7 @@ surrogate update (rl/agents/agent_ppo.py:16-64, agent_pg.py:18-56).
 from __future__ import annotations
 
 import math
+import pickle
 
 import torch
 import torch.nn as nn
@@ -170,3 +171,86 @@ def make_policy_value(cfg, obs_dim=617, act_dim=32, device="cuda", dtype=torch.f
     policy = PolicyGaussian(MLP(obs_dim, cfg.policy_hsize, cfg.policy_htype), act_dim, log_std=cfg.log_std, fix_std=cfg.fix_std)
     value = Value(MLP(obs_dim, cfg.value_hsize, cfg.value_htype))
     return policy.to(device=device, dtype=dtype), value.to(device=device, dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------------ checkpoints
+# The reference pickles {"policy_dict", "value_dict", "running_state"} with `running_state` an instance of
+# uhc.khrylib.utils.zfilter.ZFilter holding a RunningStat (_n, _M, _S) (agent_handmimic.py:175-186; loaded through the
+# CustomUnpickler of uhc/utils/tools.py:7-18).  The two classes below carry the same attribute names and are pickled under
+# the reference's module path, so a file written here opens in the reference and a released `iter_XXXX.p` opens here
+# without the reference being importable.
+class _RefRunningStat:
+    def __init__(self, n, M, S):
+        self._n, self._M, self._S = n, M, S
+
+
+class _RefZFilter:
+    def __init__(self, rs, clip):
+        self.demean, self.destd, self.clip, self.rs = True, True, clip, rs
+
+
+_RefRunningStat.__module__ = _RefZFilter.__module__ = "uhc.khrylib.utils.zfilter"
+_RefRunningStat.__qualname__ = _RefRunningStat.__name__ = "RunningStat"
+_RefZFilter.__qualname__ = _RefZFilter.__name__ = "ZFilter"
+
+
+class _ref_modules:
+    """While saving, the reference's module path resolves to the two stand-ins, so that pickle writes plain class
+    references (`uhc.khrylib.utils.zfilter.ZFilter`) + attribute dicts: exactly what the reference's own dump contains."""
+    NAMES = ("uhc", "uhc.khrylib", "uhc.khrylib.utils", "uhc.khrylib.utils.zfilter")
+
+    def __enter__(self):
+        import sys, types
+        self.saved = {n: sys.modules.get(n) for n in self.NAMES}
+        for n in self.NAMES:
+            if n not in sys.modules:
+                sys.modules[n] = types.ModuleType(n)
+        self.prev = {k: getattr(sys.modules[self.NAMES[-1]], k, None) for k in ("ZFilter", "RunningStat")}
+        sys.modules[self.NAMES[-1]].ZFilter = _RefZFilter
+        sys.modules[self.NAMES[-1]].RunningStat = _RefRunningStat
+
+    def __exit__(self, *exc):
+        import sys
+        for k, v in self.prev.items():
+            if v is not None:
+                setattr(sys.modules[self.NAMES[-1]], k, v)
+        for n, m in self.saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+
+
+class _RefUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if name == "ZFilter" and "zfilter" in module:
+            return _RefZFilter
+        if name == "RunningStat" and "zfilter" in module:
+            return _RefRunningStat
+        return super().find_class(module, name)
+
+
+def save_checkpoint(path, policy_net, value_net, running_state):
+    """`AgentHandMimic.save_checkpoint` (agent_handmimic.py:175-186): state dicts on the CPU + the observation normaliser."""
+    import numpy as np
+    rs = _RefRunningStat(int(running_state.n.item()), running_state.mean.detach().double().cpu().numpy().copy(),
+                         running_state.m2.detach().double().cpu().numpy().copy())
+    cp = {"policy_dict": {k: v.detach().cpu() for k, v in policy_net.state_dict().items()},
+          "value_dict": {k: v.detach().cpu() for k, v in value_net.state_dict().items()},
+          "running_state": _RefZFilter(rs, running_state.clip)}
+    with open(path, "wb") as f, _ref_modules():
+        pickle.dump(cp, f, protocol=2)
+
+
+def load_checkpoint(path, policy_net, value_net, running_state):
+    """`load_checkpoint` (agent_handmimic.py:135-169): restores the networks (cast to their dtype) and the normaliser."""
+    with open(path, "rb") as f:
+        cp = _RefUnpickler(f).load()
+    policy_net.load_state_dict({k: torch.as_tensor(v).to(next(policy_net.parameters())) for k, v in cp["policy_dict"].items()})
+    value_net.load_state_dict({k: torch.as_tensor(v).to(next(value_net.parameters())) for k, v in cp["value_dict"].items()})
+    z = cp["running_state"]
+    dev, dt = running_state.mean.device, running_state.mean.dtype
+    running_state.n = torch.as_tensor(float(z.rs._n), dtype=dt, device=dev)
+    running_state.mean = torch.as_tensor(z.rs._M, dtype=dt, device=dev).clone()
+    running_state.m2 = torch.as_tensor(z.rs._S, dtype=dt, device=dev).clone()
+    if z.clip:
+        running_state.clip = float(z.clip)
+    return cp

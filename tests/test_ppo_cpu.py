@@ -2,6 +2,7 @@
 GAE (uhc/khrylib/rl/core/common.py:5-25), ZFilter / RunningStat (uhc/khrylib/utils/zfilter.py:7-73), the clipped
 surrogate step (uhc/khrylib/rl/agents/agent_ppo.py:16-64) and the network layout (models/mlp.py, policy_gaussian.py)."""
 import numpy as np
+import pytest
 import torch
 
 from common import model
@@ -115,3 +116,36 @@ def test_ppo_update_is_the_reference_step():
     # more epochs reduce the value loss
     st5 = ppo.ppo_update(pol, val, op, ov, s, a, ret, adv, flp, num_epoch=20, ind=ind)
     assert st5["value_loss"] < st["value_loss"]
+
+
+def test_checkpoint_roundtrip_in_the_reference_format(tmp_path):
+    """iter_XXXX.p layout of agent_handmimic.py:175-186: state dicts + a pickled uhc.khrylib.utils.zfilter.ZFilter whose
+    RunningStat carries (_n, _M, _S); readable without the reference through the name-patching unpickler (tools.py:7-18)."""
+    import pickle
+    import pickletools
+    from common import model
+    cfg = model("box").cfg
+    pol, val = ppo.make_policy_value(cfg, device="cpu", dtype=torch.float32, seed=3)
+    zf = ppo.ZFilter((617,), clip=5.0)
+    x = torch.randn(50, 617, dtype=torch.float64) * 3 + 1
+    zf(x)
+    fn = str(tmp_path / "iter_0001.p")
+    ppo.save_checkpoint(fn, pol, val, zf)
+    ops = [(op.name, arg) for op, arg, _ in pickletools.genops(open(fn, "rb").read())]
+    globals_ = {arg for name, arg in ops if name == "GLOBAL"}
+    assert "uhc.khrylib.utils.zfilter ZFilter" in globals_ and "uhc.khrylib.utils.zfilter RunningStat" in globals_
+    assert not any("hoic_b200" in str(arg) for _, arg in ops)          # nothing of this repo is needed to open the file
+    with pytest.raises(ModuleNotFoundError):
+        pickle.load(open(fn, "rb"))                                      # plain pickle needs the reference's module ...
+    pol2, val2 = ppo.make_policy_value(cfg, device="cpu", dtype=torch.float32, seed=4)
+    zf2 = ppo.ZFilter((617,), clip=10.0)
+    cp = ppo.load_checkpoint(fn, pol2, val2, zf2)                        # ... the patched unpickler does not
+    assert set(cp) == {"policy_dict", "value_dict", "running_state"}
+    for a, b in zip(list(pol.parameters()) + list(val.parameters()), list(pol2.parameters()) + list(val2.parameters())):
+        assert torch.equal(a, b)
+    assert float(zf2.n) == 50 and torch.allclose(zf2.mean, zf.mean) and torch.allclose(zf2.std, zf.std) and zf2.clip == 5.0
+    # the reference's RunningStat.var = _S / (_n - 1): same statistic as ours
+    rs = cp["running_state"].rs
+    assert np.allclose(rs._S / (rs._n - 1), x.var(0, unbiased=True).numpy())
+    y = torch.randn(4, 617, dtype=torch.float64)
+    assert torch.equal(zf(y, update=False), zf2(y, update=False))

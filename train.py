@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--epoch", type=int, default=0, help="first epoch (adaptive schedules start here)")
     ap.add_argument("--min-batch-size", type=int, default=0, help="override cfg.min_batch_size (total over all GPUs)")
+    ap.add_argument("--load", default="", help="checkpoint to start from (iter_XXXX.p layout of the reference)")
+    ap.add_argument("--save", default="", help="write the final checkpoint here (rank 0)")
+    ap.add_argument("--eval", action="store_true", help="run eval_policy (test mode, mean action) after training")
     a = ap.parse_args()
     import torch.distributed as dist
     from hoic_b200.agent import AgentHandMimic
@@ -40,12 +43,19 @@ def main():
     agent = AgentHandMimic(models, a.envs, env_model_id=ids, device=local)
     if a.min_batch_size:
         agent.cfg.min_batch_size = a.min_batch_size
+    if a.load:
+        agent.load_checkpoint(a.load)
     for i in range(a.epoch, a.epoch + a.iters):
         info = agent.optimize_policy(i)
         if rank == 0:
             log = info.pop("log")
             print(json.dumps(dict(iter=i, avg_reward=log["avg_reward"], episodes=log["num_episodes"],
                                   samples_per_s=info["samples"] / info["T_total"], **{k: v for k, v in info.items()})))
+    if rank == 0 and a.save:
+        agent.save_checkpoint(a.save)
+    if rank == 0 and a.eval:
+        m = agent.eval_policy()
+        print(json.dumps({"eval": {k: v for k, v in m.items() if k != "per_motion"}}))
     agent.close()
     if world > 1:
         dist.destroy_process_group()
