@@ -86,7 +86,7 @@ class ZFilter:
     @property
     def std(self):
         var = torch.where(self.n > 1, self.m2 / torch.clamp(self.n - 1, min=1), self.mean ** 2)
-        return torch.sqrt(var)
+        return torch.sqrt(torch.clamp(var, min=0))
 
     def update(self, x):
         x = x.to(self.mean.dtype)
@@ -105,16 +105,30 @@ class ZFilter:
         y = (x.to(self.mean.dtype) - self.mean) / (self.std + 1e-8)
         return torch.clamp(y, -self.clip, self.clip).to(x.dtype)
 
+    @staticmethod
+    def merge_moments(parts):
+        """Pooled (n, mean, M2) of per-rank (n, mean, M2) triples: the arithmetic `allreduce` performs with collectives."""
+        n = sum(p[0].double() for p in parts)
+        mean = sum(p[1].double() * p[0].double() for p in parts) / torch.clamp(n, min=1)
+        m2 = sum(p[2].double() + p[0].double() * (p[1].double() - mean) ** 2 for p in parts)
+        return n, mean, torch.clamp(m2, min=0)
+
     def allreduce(self):
-        """Merge statistics across ranks (sum of counts, pooled mean / M2)."""
+        """Merge statistics across ranks: counts add, means pool, and the centred second moments combine as
+        M2 = sum_r [M2_r + n_r (mean_r - mean)^2] (Chan et al.), in float64.  Raw moments (sum of squares minus n mean^2)
+        cancel catastrophically in float32 and turned the std of (near-)constant observation entries into NaN."""
         if not hdist._on():
             return
         import torch.distributed as dist
-        n, s1, s2 = self.n.clone(), self.mean * self.n, self.m2 + self.mean ** 2 * self.n
-        for t in (n, s1, s2):
-            dist.all_reduce(t)
-        self.n, self.mean = n, s1 / n
-        self.m2 = s2 - self.mean ** 2 * n
+        dt = self.mean.dtype
+        n_r, mean_r, m2_r = self.n.double(), self.mean.double(), self.m2.double()
+        head = torch.cat([n_r.reshape(1), (mean_r * n_r).reshape(-1)])
+        dist.all_reduce(head)
+        n = head[0]
+        mean = head[1:].reshape(mean_r.shape) / torch.clamp(n, min=1)
+        m2 = m2_r + n_r * (mean_r - mean) ** 2
+        dist.all_reduce(m2)
+        self.n, self.mean, self.m2 = n.to(dt), mean.to(dt), torch.clamp(m2, min=0).to(dt)
 
 
 def estimate_advantages(rewards, masks, values, gamma, tau):

@@ -42,6 +42,25 @@ for q, r in zip(p.parameters(), ref):
     both = [torch.zeros_like(r), torch.zeros_like(r)]
     dist.all_gather(both, r)
     assert torch.allclose(q.grad, (both[0] + both[1]) / 2)
+# observation normaliser merged across ranks (float32, as the agent runs it): a constant entry, a large-mean / tiny-spread
+# entry and ordinary ones must come out finite and equal to the single-process statistics
+from hoic_b200 import ppo
+x = rng.randn(4000, 6).astype(np.float32)
+x[:, 0] = 1.0
+x[:, 1] = 1000.0 + 1e-3 * x[:, 1]
+x[:, 2] = 0.0
+zf = ppo.ZFilter((6,), clip=5.0, dtype=torch.float32)
+for chunk in np.array_split(x[rank::2], 5):
+    zf(torch.as_tensor(chunk))
+zf.allreduce()
+one = ppo.ZFilter((6,), clip=5.0, dtype=torch.float64)
+one(torch.as_tensor(x, dtype=torch.float64))
+assert float(zf.n) == 4000 and torch.isfinite(zf.std).all() and (zf.m2 >= 0).all()
+assert torch.allclose(zf.mean.double(), one.mean, rtol=1e-6, atol=1e-6)
+assert torch.allclose(zf.std.double()[3:], one.std[3:], rtol=1e-4) and float(zf.std[0]) < 1e-3 and float(zf.std[2]) == 0.0
+assert abs(float(zf.std[1]) - float(one.std[1])) < 1e-3
+y = zf(torch.as_tensor(x[:8]), update=False)
+assert torch.isfinite(y).all()
 dist.destroy_process_group()
 print("OK", rank)
 '''

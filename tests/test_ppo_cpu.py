@@ -149,3 +149,32 @@ def test_checkpoint_roundtrip_in_the_reference_format(tmp_path):
     assert np.allclose(rs._S / (rs._n - 1), x.var(0, unbiased=True).numpy())
     y = torch.randn(4, 617, dtype=torch.float64)
     assert torch.equal(zf(y, update=False), zf2(y, update=False))
+
+
+def test_zfilter_merge_of_eight_float32_ranks_stays_finite():
+    """The pooled second moment is combined from centred moments in float64.  The earlier raw-moment form
+    (sum of squares - n mean^2 in float32) went negative on near-constant observation entries once 8 ranks were merged
+    and turned the normaliser's std, and with it every network input, into NaN."""
+    rng = np.random.RandomState(0)
+    x = rng.randn(8, 96, 5).astype(np.float32)
+    x[..., 0] = 0.8660254
+    x[..., 1] = 0.5 + 1e-6 * x[..., 1]
+    x[..., 2] = 0.0
+    x[..., 3] = 3.0 + 1e-4 * x[..., 3]
+    parts = []
+    for r in range(8):
+        zf = ppo.ZFilter((5,), dtype=torch.float32)
+        for chunk in np.array_split(x[r], 4):
+            zf(torch.as_tensor(chunk))
+        parts.append((zf.n, zf.mean, zf.m2))
+    n, mean, m2 = ppo.ZFilter.merge_moments(parts)
+    std = torch.sqrt(m2 / (n - 1))
+    ref = torch.as_tensor(x.reshape(-1, 5), dtype=torch.float64)
+    assert float(n) == 768 and torch.isfinite(std).all() and (m2 >= 0).all()
+    assert torch.allclose(mean, ref.mean(0), atol=1e-6) and torch.allclose(std[3:], ref.std(0)[3:], rtol=2e-3)
+    assert float(std[0]) < 1e-6 and float(std[2]) == 0.0 and abs(float(std[1]) - float(ref.std(0)[1])) < 1e-6
+    # the raw-moment merge this replaces does fail on the same input
+    nn = sum(p[0] for p in parts)
+    m = sum(p[1] * p[0] for p in parts) / nn
+    raw = sum(p[2] + p[1] ** 2 * p[0] for p in parts) - m ** 2 * nn
+    assert (raw < 0).any()
