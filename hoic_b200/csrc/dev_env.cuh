@@ -179,22 +179,24 @@ __device__ __noinline__ void qp_var(const float* s, int i, int ec, V3 obj_p, flo
   if (pos_out) *pos_out = pos;
 }
 
-// in-register 6x6 SPD solve (all lanes redundantly)
+// in-register 6x6 SPD solve (all lanes redundantly).  One reciprocal per pivot: a float64 division or square root is a
+// ~30-instruction sequence with a slow-path call, and this runs on the critical path of every QP Newton iteration.
 __device__ __forceinline__ bool solve6(double H[6][6], const double* rhs, double* x) {
+  double inv[6];
   for (int j = 0; j < 6; j++) {
     double sd = H[j][j];
     for (int k = 0; k < j; k++) sd -= H[j][k] * H[j][k];
     if (!(sd > 1e-300)) return false;
-    sd = sqrt(sd);
-    H[j][j] = sd;
+    const double r = rsqrt(sd);            // L_jj = sd * r, 1 / L_jj = r
+    inv[j] = r;
     for (int i = j + 1; i < 6; i++) {
       double t = H[i][j];
       for (int k = 0; k < j; k++) t -= H[i][k] * H[j][k];
-      H[i][j] = t / sd;
+      H[i][j] = t * r;
     }
   }
-  for (int i = 0; i < 6; i++) { double t = rhs[i]; for (int k = 0; k < i; k++) t -= H[i][k] * x[k]; x[i] = t / H[i][i]; }
-  for (int i = 5; i >= 0; i--) { double t = x[i]; for (int k = i + 1; k < 6; k++) t -= H[k][i] * x[k]; x[i] = t / H[i][i]; }
+  for (int i = 0; i < 6; i++) { double t = rhs[i]; for (int k = 0; k < i; k++) t -= H[i][k] * x[k]; x[i] = t * inv[i]; }
+  for (int i = 5; i >= 0; i--) { double t = x[i]; for (int k = i + 1; k < 6; k++) t -= H[k][i] * x[k]; x[i] = t * inv[i]; }
   return true;
 }
 
@@ -224,11 +226,13 @@ static_assert(((QP_RED + 1) & ~1) + 64 <= U_QP_END, "QP scratch exceeds the unio
 // grasps touch 2-5 hand geoms = 40-100 variables) run a 3- or 6-wide instance instead of the 12-wide one.
 template <int NPER>
 __device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T, float* rest, unsigned& qp_iters, float* surf) {
-  const double eps = 1e-7, sqw = 100.0;
+  const double eps = 1e-7, inv_eps = 1.0 / eps, sqw = 100.0;
   double* red = reinterpret_cast<double*>(s + ((QP_RED + 1) & ~1));
   const double b6[6] = {F.x, F.y, F.z, sqw * T.x, sqw * T.y, sqw * T.z};
   double bmax = 0;
   for (int a = 0; a < 6; a++) bmax = fmax(bmax, fabs(b6[a]));
+  // (warm-starting lam from the env's previous QP was measured: 7.8 vs 7.4 iterations, no gain -- the target wrench of
+  // consecutive steps comes from averaged accelerations and moves too much)
   double lam[6] = {0, 0, 0, 0, 0, 0};
   double sv[NPER], gd[NPER];       // per owned variable: s_i = c_i + g_i.lam and g_i.dl
   for (int it = 0; it < 60; it++) {
@@ -263,9 +267,9 @@ __device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T,
       int q = 6;
 #pragma unroll
       for (int a = 0; a < 6; a++) {
-        grad[a] = 0.5 * lam[a] + b6[a] + red[a] / eps;
+        grad[a] = 0.5 * lam[a] + b6[a] + red[a] * inv_eps;
 #pragma unroll
-        for (int c = 0; c <= a; c++) { const double hv = red[q++] / eps; H[a][c] = hv; H[c][a] = hv; }
+        for (int c = 0; c <= a; c++) { const double hv = red[q++] * inv_eps; H[a][c] = hv; H[c][a] = hv; }
         H[a][a] += 0.5;
       }
     }
@@ -297,8 +301,8 @@ __device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T,
         const double sa = sv[t] + alpha * gd[t];
         if (sa < 0) { a1 += sa * gd[t]; a2 += gd[t] * gd[t]; }
       }
-      d1 = 0.5 * (ll + alpha * dd) + bd + wsumd(a1) / eps;
-      d2 = 0.5 * dd + wsumd(a2) / eps;
+      d1 = 0.5 * (ll + alpha * dd) + bd + wsumd(a1) * inv_eps;
+      d2 = 0.5 * dd + wsumd(a2) * inv_eps;
       if (fabs(d1) <= 1e-12 * (fabs(bd) + fabs(0.5 * ll) + 1e-30) || !(d2 > 0)) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
       double nxt = alpha - d1 / d2;
@@ -319,7 +323,7 @@ __device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T,
     if (i < n) {
       double si = (double)s[QP_C + i];
       for (int k = 0; k < 6; k++) { g[k] = (double)s[QP_G + 6 * i + k]; si += g[k] * lam[k]; }
-      if (si < 0) { x = -si / eps; for (int k = 0; k < 6; k++) gx[k] += g[k] * x; }
+      if (si < 0) { x = -si * inv_eps; for (int k = 0; k < 6; k++) gx[k] += g[k] * x; }
     }
     if (surf) {
       // test-mode record: surface_contact_force of a point = (ts A) x over its 4 pyramid edges = 4 adjacent lanes

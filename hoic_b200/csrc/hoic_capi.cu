@@ -192,6 +192,9 @@ __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, c
         rfc_score = norm(F) + 1e4f * norm(T);
         rest[0] = F.x; rest[1] = F.y; rest[2] = F.z; rest[3] = T.x; rest[4] = T.y; rest[5] = T.z;
       } else {
+#ifdef H_NOQP   // timing experiment only (tools/ab.sh): what the residual-force QP costs in kernel wall time
+        if (qp_iters > 1000000u)
+#endif
         rfc_score = rfc_qp(s, lane, ncg, m.surface_contact ? 5 : 1, F, T, obj_p, obj_v, obj_w, s + S_GPOS, org, rest, qp_iters, surf);
       }
     }
