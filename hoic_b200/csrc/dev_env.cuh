@@ -161,8 +161,8 @@ __device__ __noinline__ V3 matrix_to_axis_angle(const M3& R) {
 #define QP_END (QP_GV + H_NHG * 6)
 
 struct QpVar { double g[6]; };
-__device__ __noinline__ void qp_var(const float* s, int i, int ec, V3 obj_p, float sqw, QpVar& out, V3* pos_out) {
-  const float dx = 0.0025f, mu = 0.75f;
+__device__ __noinline__ void qp_var(const float* s, int i, int ec, V3 obj_p, float sqw, float mu, QpVar& out, V3* pos_out) {
+  const float dx = 0.0025f;
   const int pt = i >> 2, e = i & 3, k = pt / ec, j = pt % ec;
   const float* cf = s + QP_CF + 12 * k;
   const V3 n = ld3(cf + 3), t = ld3(cf + 6), b = ld3(cf + 9);
@@ -225,8 +225,8 @@ static_assert(((QP_RED + 1) & ~1) + 64 <= U_QP_END, "QP scratch exceeds the unio
 // per lane: the loops over a lane's variables are unrolled (their values live in registers), so small problems (most
 // grasps touch 2-5 hand geoms = 40-100 variables) run a 3- or 6-wide instance instead of the 12-wide one.
 template <int NPER>
-__device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T, float* rest, unsigned& qp_iters, float* surf) {
-  const double eps = 1e-7, inv_eps = 1.0 / eps, sqw = 100.0;
+__device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T, float* rest, unsigned& qp_iters, float* surf, double sqw) {
+  const double eps = 1e-7, inv_eps = 1.0 / eps;
   double* red = reinterpret_cast<double*>(s + ((QP_RED + 1) & ~1));
   const double b6[6] = {F.x, F.y, F.z, sqw * T.x, sqw * T.y, sqw * T.z};
   double bmax = 0;
@@ -342,6 +342,32 @@ __device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T,
   return (float)(sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) + sqrt(r[3] * r[3] + r[4] * r[4] + r[5] * r[5]));
 }
 
+// Standalone wrench QP on caller-supplied contacts (PhysMetrics.solve_force, scripts/metrics.py:156-196, and the QP of
+// solve_rfc with explicit inputs): contact frames in QP_CF, weights in QP_TS, optional penalties c (NULL = 0).
+__device__ __noinline__ float wrench_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 center, float mu, float sqw, const float* pen,
+                                        float* rest, unsigned& qp_iters, float* surf) {
+  const int n = 4 * ec * ncg;
+  for (int i = lane; i < n; i += 32) {
+    QpVar v;
+    V3 pos;
+    qp_var(s, i, ec, center, sqw, mu, v, &pos);
+    s[QP_C + i] = pen ? pen[i] : 0.f;
+    for (int a = 0; a < 6; a++) s[QP_G + 6 * i + a] = (float)v.g[a];
+    if (surf && (i & 3) == 0) {
+      const float* cf = s + QP_CF + 12 * ((i >> 2) / ec);
+      float* q = surf + HOIC_SURF_PT + 15 * (i >> 2);
+      st3(q, pos); st3(q + 3, ld3(cf + 3)); st3(q + 6, ld3(cf + 6)); st3(q + 9, ld3(cf + 9));
+    }
+  }
+  __syncwarp();
+  float score;
+  if (n <= 96) score = rfc_qp_core<3>(s, lane, n, F, T, rest, qp_iters, surf, (double)sqw);
+  else if (n <= 192) score = rfc_qp_core<6>(s, lane, n, F, T, rest, qp_iters, surf, (double)sqw);
+  else score = rfc_qp_core<QP_NPER>(s, lane, n, F, T, rest, qp_iters, surf, (double)sqw);
+  if (surf && lane < 8) surf[lane] = lane == 0 ? (float)(n >> 2) : (lane == 7 ? 1.f : rest[lane - 1]);
+  return score;
+}
+
 // returns rfc_score; fills rest[6]
 __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,
                         V3 org_now, float* rest, unsigned& qp_iters, float* surf) {
@@ -351,7 +377,7 @@ __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, 
   for (int i = lane; i < n; i += 32) {
     QpVar v;
     V3 pos;
-    qp_var(s, i, ec, obj_p, (float)sqw, v, &pos);
+    qp_var(s, i, ec, obj_p, (float)sqw, 0.75f, v, &pos);
     const int pt = i >> 2, e = i & 3, k = pt / ec;
     const float* cf = s + QP_CF + 12 * k;
     const V3 nn = ld3(cf + 3), t = ld3(cf + 6), b = ld3(cf + 9);
@@ -376,9 +402,9 @@ __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, 
   }
   __syncwarp();
   float score;
-  if (n <= 96) score = rfc_qp_core<3>(s, lane, n, F, T, rest, qp_iters, surf);
-  else if (n <= 192) score = rfc_qp_core<6>(s, lane, n, F, T, rest, qp_iters, surf);
-  else score = rfc_qp_core<QP_NPER>(s, lane, n, F, T, rest, qp_iters, surf);
+  if (n <= 96) score = rfc_qp_core<3>(s, lane, n, F, T, rest, qp_iters, surf, sqw);
+  else if (n <= 192) score = rfc_qp_core<6>(s, lane, n, F, T, rest, qp_iters, surf, sqw);
+  else score = rfc_qp_core<QP_NPER>(s, lane, n, F, T, rest, qp_iters, surf, sqw);
   if (surf && lane < 8) surf[lane] = lane == 0 ? (float)(n >> 2) : (lane == 7 ? 1.f : rest[lane - 1]);
   return score;
 }

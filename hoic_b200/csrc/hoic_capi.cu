@@ -526,6 +526,33 @@ __global__ void __launch_bounds__(32) k_substep_debug(BatchDev B, const float* c
   flush_counters(B, cnt, lane, 0);
 }
 
+// standalone batched wrench QP, one warp per problem (hoic_solve_wrench_qp)
+__global__ void __launch_bounds__(32) k_wrench_qp(int B, int K, int ec, const float* __restrict__ contacts, const int* __restrict__ ncontact,
+                                                  const float* __restrict__ weights, const float* __restrict__ penalties,
+                                                  const float* __restrict__ target, const float* __restrict__ center, float mu, float w_t,
+                                                  float* rest_out, float* score_out, float* surface, int* iters_out) {
+  extern __shared__ float s[];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  if (b >= B) return;
+  const int nc = min(max(ncontact[b], 0), K);
+  const V3 F = ld3(target + 6 * (size_t)b), T = ld3(target + 6 * (size_t)b + 3), c = ld3(center + 3 * (size_t)b);
+  float* surf = surface ? surface + (size_t)b * HOIC_SURF_STRIDE : nullptr;
+  if (surf) for (int i = lane; i < HOIC_SURF_STRIDE; i += 32) surf[i] = 0.f;
+  float rest[6] = {F.x, F.y, F.z, T.x, T.y, T.z};
+  unsigned it = 0;
+  float score;
+  if (nc == 0) {
+    score = norm(F) + sqrtf(w_t) * norm(T);     // nothing can be explained: the whole target wrench is left
+  } else {
+    for (int i = lane; i < 12 * nc; i += 32) s[QP_CF + i] = contacts[(size_t)b * K * 12 + i];
+    if (lane < nc) s[QP_TS + lane] = weights ? weights[(size_t)b * K + lane] : 1.f;
+    __syncwarp();
+    score = wrench_qp(s, lane, nc, ec, F, T, c, mu, sqrtf(w_t), penalties ? penalties + (size_t)b * K * ec * 4 : nullptr, rest, it, surf);
+  }
+  if (lane < 6 && rest_out) rest_out[(size_t)b * 6 + lane] = rest[lane];
+  if (lane == 0) { if (score_out) score_out[b] = score; if (iters_out) iters_out[b] = (int)it; }
+}
+
 // dataset preprocessing of one raw sequence, one warp per frame (DatasetSingleDepth.preprocess_seq, dataset_singledepth.py:78-142)
 __global__ void __launch_bounds__(32) k_preprocess(const DevModel* mp, const float* __restrict__ hand, const float* __restrict__ obj, int T,
                                                    float freq, int clip, float* frames, int* cmask, float* cpos) {
@@ -1231,6 +1258,22 @@ __global__ void k_fma_peak(float* out, int iters, float a, float b) {
   for (int i = 0; i < 16; i++) s += x[i];
   if (s == 12345.678f) out[0] = s;
 }
+extern "C" int hoic_solve_wrench_qp(int device, int n_problems, int max_contacts, int surface_contact, const float* contacts,
+                                    const int* n_contacts, const float* weights, const float* penalties, const float* target,
+                                    const float* center, float mu, float w_t, float* rest, float* score, float* surface, int* iters,
+                                    void* stream) {
+  if (n_problems <= 0 || !contacts || !n_contacts || !target || !center) return set_err("hoic_solve_wrench_qp: bad arguments");
+  const int ec = surface_contact ? 5 : 1;
+  if (max_contacts < 1 || max_contacts > H_NHG) return set_err("hoic_solve_wrench_qp: max_contacts must be in [1, 19] (380 QP variables)");
+  if (!(mu > 0.f) || !(w_t > 0.f)) return set_err("hoic_solve_wrench_qp: mu and w_t must be positive");
+  CUDA_OK(cudaSetDevice(device));
+  k_wrench_qp<<<n_problems, 32, (size_t)S_TOTAL * sizeof(float), (cudaStream_t)stream>>>(n_problems, max_contacts, ec, contacts, n_contacts,
+                                                                                         weights, penalties, target, center, mu, w_t, rest,
+                                                                                         score, surface, iters);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int hoic_preprocess_seq(const hoic_model* m, const float* hand_pose_seq, const float* obj_pose_seq, int T, float motion_freq,
                                    int clip, float* frames_out, int* contact_mask, float* contact_pos, void* stream) {
   if (!m || !hand_pose_seq || !obj_pose_seq || !frames_out) return set_err("hoic_preprocess_seq: bad arguments");

@@ -81,6 +81,21 @@ int hoic_set_motions(hoic_batch* b, const float* frames_host, const int* motion_
 int hoic_preprocess_seq(const hoic_model* m, const float* hand_pose_seq, const float* obj_pose_seq, int T, float motion_freq,
                         int clip, float* frames_out, int* contact_mask, float* contact_pos, void* stream);
 
+/* replaces PhysMetrics.solve_force (scripts/metrics.py:156-196) and exposes the QP of solve_rfc (uhc/envs/ho_im4.py:1003-1070) on
+ * caller-supplied contacts, batched, one warp per problem:
+ *   min_x |F - J_f x|^2 + w_t |T - J_t x|^2 + c.x + 0.5e-7 |x|^2,  x >= 0,
+ * x = 4 friction-pyramid edge forces (coefficient mu) at each contact, expanded to 5 points (+-0.0025 along the tangents)
+ * when surface_contact != 0; torques about center[b].  contacts[B][max_contacts][12] = pos[3] frame[9] (rows: normal,
+ * tangent, bitangent), n_contacts[B] <= max_contacts <= 19, weights[B][max_contacts] (NULL = 1: the `ts` factor of
+ * ho_im4.py:1012-1013), penalties[B][max_contacts * points * 4] (NULL = 0: p_n + p_t of :1028-1042), target[B][6] = F, T.
+ * Outputs (any may be NULL): rest[B][6] = F - J_f x, T - J_t x; score[B] = |rest_f| + sqrt(w_t) |rest_t|;
+ * surface[B][HOIC_SURF_STRIDE] (layout above: points, their frames and forces); iters[B] = Newton iterations.
+ * The reference's settings: solve_rfc mu 0.75, w_t 1e4; solve_force mu 1, w_t 1, no weights, no penalties. */
+int hoic_solve_wrench_qp(int device, int n_problems, int max_contacts, int surface_contact, const float* contacts,
+                         const int* n_contacts, const float* weights, const float* penalties, const float* target,
+                         const float* center, float mu, float w_t, float* rest, float* score, float* surface, int* iters,
+                         void* stream);
+
 /* replaces cfg.reward_weights after cfg.update_adaptive_params (uhc/utils/config_utils/handmimic_config.py:157-195):
  * w_host[24] = w_p w_wp w_v w_j w_op w_or w_ov w_orfc k_p k_wp k_v k_j k_op k_or k_ov k_orfc, rest reserved. */
 int hoic_set_reward_weights(hoic_batch* b, const float* w_host);

@@ -207,3 +207,18 @@ def preprocess_seq(blob: bytes, hand_pose_seq, obj_pose_seq, motion_freq=30.0, c
     if rc != 0:
         raise ValueError("orc_preprocess_seq: need at least 2 frames")
     return frames, cmask[:, :19].copy(), cpos[:, :19].copy()
+
+
+def solve_wrench_qp(contacts, target, center, mu=0.75, w_t=1e4, weights=None, penalties=None, surface_contact=True):
+    """Oracle of hoic_solve_wrench_qp for ONE problem: contacts [nc, 12] -> (rest[6], score, point_force [nc * points, 3])."""
+    L = lib()
+    c = np.ascontiguousarray(contacts, dtype=np.float64).reshape(-1, 12)
+    nc, ec = c.shape[0], 5 if surface_contact else 1
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    p = None if penalties is None else np.ascontiguousarray(penalties, dtype=np.float64)
+    t, ce = np.ascontiguousarray(target, dtype=np.float64), np.ascontiguousarray(center, dtype=np.float64)
+    rest, score, pf = np.zeros(6), np.zeros(1), np.zeros((max(nc * ec, 1), 3))
+    L.orc_solve_wrench_qp.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_double, C.c_double] + [C.c_void_p] * 3
+    L.orc_solve_wrench_qp(nc, ec, _p(c), None if w is None else _p(w), None if p is None else _p(p), _p(t), _p(ce),
+                          C.c_double(mu), C.c_double(w_t), _p(rest), _p(score), _p(pf))
+    return rest, float(score[0]), pf[:nc * ec]

@@ -743,3 +743,68 @@ int orc_preprocess_seq(const orc_model* m, const double* hand_pose_seq, const do
   free(d); free(hand);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ standalone wrench QP
+   The QP of solve_rfc (ho_im4.py:1003-1070) / PhysMetrics.solve_force (scripts/metrics.py:156-196) on explicit inputs,
+   solved like solve_rfc above: dense Q, p and the primal active-set.  Checker of hoic_solve_wrench_qp. */
+int orc_solve_wrench_qp(int nc, int ec, const double* contacts, const double* weights, const double* penalties, const double* target,
+                        const double* center, double mu, double w_t, double* rest, double* score, double* point_force) {
+  const double dx = 0.0025, *F = target, *T = target + 3;
+  int n = 4 * ec * nc, iters = 0;
+  if (nc == 0) {
+    memcpy(rest, target, 6 * sizeof(double));
+    *score = norm3(F) + sqrt(w_t) * norm3(T);
+    return 0;
+  }
+  double* Jf = (double*)calloc((size_t)3 * n, sizeof(double));
+  double* Jt = (double*)calloc((size_t)3 * n, sizeof(double));
+  double* pl = (double*)calloc(n, sizeof(double));
+  double* Q = (double*)malloc((size_t)n * n * sizeof(double));
+  double* x = (double*)malloc(n * sizeof(double));
+  double isq = 1.0 / sqrt(1 + mu * mu);
+  for (int ci = 0; ci < nc; ci++) {
+    const double* cf = contacts + 12 * ci;
+    const double *fr0 = cf + 3, *fr1 = cf + 6, *fr2 = cf + 9;
+    double ts = weights ? weights[ci] : 1.0;
+    for (int j = 0; j < ec; j++) {
+      int i = ci * ec + j;
+      double pos[3], r[3], A[4][3];
+      copy3(pos, cf);
+      if (j == 1) addscl3(pos, pos, fr1, dx); else if (j == 2) addscl3(pos, pos, fr1, -dx);
+      else if (j == 3) addscl3(pos, pos, fr2, dx); else if (j == 4) addscl3(pos, pos, fr2, -dx);
+      for (int k = 0; k < 3; k++) {
+        A[0][k] = (fr0[k] + mu * fr1[k]) * isq; A[1][k] = (fr0[k] - mu * fr1[k]) * isq;
+        A[2][k] = (fr0[k] + mu * fr2[k]) * isq; A[3][k] = (fr0[k] - mu * fr2[k]) * isq;
+      }
+      sub3(r, pos, center);
+      for (int a = 0; a < 4; a++) {
+        double rxA[3];
+        cross3(rxA, r, A[a]);
+        for (int k = 0; k < 3; k++) { Jf[k * n + 4 * i + a] = ts * A[a][k]; Jt[k * n + 4 * i + a] = ts * rxA[k]; }
+        if (penalties) pl[4 * i + a] = penalties[4 * i + a];
+      }
+    }
+  }
+  for (int a = 0; a < n; a++) {
+    double s = 0;
+    for (int b = 0; b < n; b++) {
+      double q = 0;
+      for (int k = 0; k < 3; k++) q += Jf[k * n + a] * Jf[k * n + b] + w_t * Jt[k * n + a] * Jt[k * n + b];
+      Q[(size_t)a * n + b] = 2 * q + (a == b ? 1e-7 : 0);
+    }
+    for (int k = 0; k < 3; k++) s += -2 * Jf[k * n + a] * F[k] - 2 * w_t * Jt[k * n + a] * T[k];
+    pl[a] += s;
+  }
+  iters = qp_nonneg(n, Q, pl, x);
+  for (int k = 0; k < 3; k++) {
+    double sf = 0, st = 0;
+    for (int a = 0; a < n; a++) { sf += Jf[k * n + a] * x[a]; st += Jt[k * n + a] * x[a]; }
+    rest[k] = F[k] - sf; rest[3 + k] = T[k] - st;
+  }
+  *score = norm3(rest) + sqrt(w_t) * norm3(rest + 3);
+  if (point_force)
+    for (int i = 0; i < nc * ec; i++)
+      for (int k = 0; k < 3; k++) { point_force[3 * i + k] = 0; for (int a = 0; a < 4; a++) point_force[3 * i + k] += Jf[k * n + 4 * i + a] * x[4 * i + a]; }
+  free(Jf); free(Jt); free(pl); free(Q); free(x);
+  return iters;
+}

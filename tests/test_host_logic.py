@@ -440,3 +440,33 @@ def test_oracle_preprocess_seq_vs_numpy_derivation():
     assert np.abs(raw[:, 7] - hand[:, 7]).max() == 0
     with pytest.raises(ValueError):
         oracle.preprocess_seq(mdl.blob, hand[:1], obj[:1], 30)
+
+
+def test_oracle_wrench_qp_known_answers():
+    """The standalone wrench QP (solve_rfc's QP / PhysMetrics.solve_force): closed-form cases."""
+    import oracle
+
+    def frame(n):
+        n = np.array(n, float) / np.linalg.norm(n)
+        t = np.cross(n, [1.0, 0, 0]) if abs(n[0]) < 0.9 else np.cross(n, [0, 1.0, 0])
+        t /= np.linalg.norm(t)
+        return np.concatenate([n, t, np.cross(n, t)])
+    W = [0, 0, 0.5, 0, 0, 0]                      # hold 0.5 N against gravity, no torque, about the origin
+    pinch = np.array([np.concatenate([[0, -0.02, 0], frame([0, 1, 0])]), np.concatenate([[0, 0.02, 0], frame([0, -1, 0])])])
+    rest, score, pf = oracle.solve_wrench_qp(pinch, W, [0, 0, 0], mu=1.0, w_t=1.0)
+    assert score < 1e-7 and np.allclose(pf.sum(0), [0, 0, 0.5], atol=1e-7)           # friction of the two pads carries it
+    rest, score, _ = oracle.solve_wrench_qp(pinch, W, [0, 0, 0], mu=0.1, w_t=1.0)
+    assert score < 1e-6                                                              # ... at any mu > 0 by squeezing harder
+    below = np.array([np.concatenate([[0, 0, -0.02], frame([0, 0, 1])])])
+    rest, score, pf = oracle.solve_wrench_qp(below, W, [0, 0, 0], mu=0.75, w_t=1e4)
+    assert score < 1e-6 and np.allclose(pf.sum(0), [0, 0, 0.5], atol=1e-6)           # a support from below pushes up
+    above = np.array([np.concatenate([[0, 0, 0.02], frame([0, 0, -1])])])
+    rest, score, pf = oracle.solve_wrench_qp(above, W, [0, 0, 0], mu=0.75, w_t=1e4)
+    assert np.allclose(rest, W, atol=1e-9) and abs(score - 0.5) < 1e-9 and np.abs(pf).max() < 1e-9   # contacts cannot pull
+    rest, score, _ = oracle.solve_wrench_qp(np.zeros((0, 12)), [0.3, 0, 0.4, 0, 0, 0.01], [0, 0, 0], mu=0.75, w_t=1e4)
+    assert abs(score - (0.5 + 100 * 0.01)) < 1e-12                                   # no contact: |F| + sqrt(w_t) |T|
+    # an off-centre support leaves a torque the single pad cannot cancel exactly: the weighted residual trades force for torque
+    off = np.array([np.concatenate([[0.03, 0, -0.02], frame([0, 0, 1])])])
+    r1, s1, _ = oracle.solve_wrench_qp(off, W, [0, 0, 0], mu=0.75, w_t=1.0, surface_contact=False)
+    r2, s2, _ = oracle.solve_wrench_qp(off, W, [0, 0, 0], mu=0.75, w_t=1e4, surface_contact=False)
+    assert np.linalg.norm(r2[3:]) < np.linalg.norm(r1[3:]) and np.linalg.norm(r2[:3]) > np.linalg.norm(r1[:3])
