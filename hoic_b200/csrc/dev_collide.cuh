@@ -123,7 +123,8 @@ __device__ __noinline__ int capsule_box(RawCon* c, float margin, V3 cp, const M3
       }
   }
   for (int i = 1; i < nb; i++) { float x = tb[i]; int j = i - 1; while (j >= 0 && tb[j] > x) { tb[j + 1] = tb[j]; j--; } tb[j + 1] = x; }
-  float best_t = 0.f, best_d2 = FLT_MAX;
+  float best_t = 0.f, best_d2 = FLT_MAX, zlo = 0.f, zhi = 0.f;
+  bool have_z = false;
   for (int k = 0; k + 1 < nb; k++) {
     float t0 = tb[k], t1 = tb[k + 1], tm = 0.5f * (t0 + t1), A = 0.f, B = 0.f, C = 0.f, t, d2;
     for (int i = 0; i < 3; i++) {
@@ -134,7 +135,11 @@ __device__ __noinline__ int capsule_box(RawCon* c, float margin, V3 cp, const M3
     if (A > 0.f) { t = fminf(fmaxf(-B / A, t0), t1); d2 = A * t * t + 2.f * B * t + C; }
     else { t = t0; d2 = C; }
     if (d2 < best_d2) { best_d2 = d2; best_t = t; }
+    if (A == 0.f && C == 0.f) { if (!have_z) { zlo = t0; have_z = true; } zhi = t1; }   // this stretch of the axis is inside the box
   }
+  // axis through the box interior: every point of the inside stretch is at distance zero; take its midpoint (the entry point
+  // lies on a face and whether it counts as inside would be decided by rounding)
+  if (have_z) best_t = 0.5f * (zlo + zhi);
   V3 p = p0 + a * best_t;
   int nout = 0, kface = -1;
   for (int i = 0; i < 3; i++)

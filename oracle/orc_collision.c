@@ -160,8 +160,8 @@ static int sphere_box_local(rawcon* c, double margin, const double* p, double r,
 static int capsule_box(rawcon* c, double margin, const double* cp, const double* cm, const double* cs,
                        const double* bp, const double* bm, const double* bs) {
   double dif[3], p0[3], a[3], ax[3] = {cm[2], cm[5], cm[8]}, h = cs[1], r = cs[0];
-  double tb[8], best_t = 0, best_d2 = DBL_MAX, p[3];
-  int nb = 0, n = 0, nout = 0, kface = -1;
+  double tb[8], best_t = 0, best_d2 = DBL_MAX, p[3], zlo = 0, zhi = 0;
+  int nb = 0, n = 0, nout = 0, kface = -1, have_z = 0;
   sub3(dif, cp, bp);
   mulmatT3(p0, bm, dif);
   mulmatT3(a, bm, ax);
@@ -184,7 +184,11 @@ static int capsule_box(rawcon* c, double margin, const double* cp, const double*
     if (A > 0) { t = -B / A; if (t < t0) t = t0; if (t > t1) t = t1; d2 = A * t * t + 2 * B * t + C; }
     else { t = t0; d2 = C; }
     if (d2 < best_d2) { best_d2 = d2; best_t = t; }
+    if (A == 0 && C == 0) { if (!have_z) { zlo = t0; have_z = 1; } zhi = t1; }   /* this stretch of the axis is inside the box */
   }
+  /* axis through the box interior: every point of the inside stretch is at distance zero; take its midpoint (the entry
+     point lies on a face and whether it counts as inside would be decided by rounding) */
+  if (have_z) best_t = 0.5 * (zlo + zhi);
   addscl3(p, p0, a, best_t);
   for (int i = 0; i < 3; i++)
     if (fabs(p[i]) > bs[i]) { nout++; kface = i; }

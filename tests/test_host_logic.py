@@ -327,6 +327,36 @@ def test_oracle_capsule_box_and_mpr_agree_on_a_face_contact():
     assert np.allclose(ends, [-min(hl, 0.0165), min(hl, 0.0165)], atol=1e-9)
 
 
+def test_oracle_capsule_box_axis_through_the_box():
+    """A finger capsule whose axis passes through the box interior (a kinematic expert pose can do that): one contact at
+    the midpoint of the inside stretch, normal of the face nearest to it, stable under tiny perturbations (the entry
+    point of the axis lies on a face; picking it made the result depend on rounding)."""
+    env = oracle_env("box")
+    env.reset()
+    M = model("box").compiled()
+    g = M["names_geom"].index("robot0:C_FF1")
+    q = env.get("qpos"); q[0:3] = [0, 0, 1.0]; q[6:26] = 0
+    env.set_state(q, np.zeros(32))
+    gp, gm = env.get("geom_xpos").reshape(-1, 3)[g], env.get("geom_xmat").reshape(-1, 3, 3)[g]
+    r = M["geom_size"][g][0]
+    axis = gm[:, 2]
+    n = np.cross(axis, [0.3, 0.5, 0.8]); n /= np.linalg.norm(n)
+    y = np.cross(n, axis)
+    Rb = np.stack([axis, y, n], axis=1)            # box axes: x along the capsule, z along n
+    out = []
+    for eps in (0.0, 1e-9, -1e-9):
+        centre = gp - n * (0.049 - 0.004) + y * (0.003 + eps)     # axis 4 mm below the +z face, 3 mm off the middle in y
+        q[26:29] = centre; q[29:33] = mjcf.mat2quat(Rb)
+        env.set_state(q, np.zeros(32))
+        c = env.contacts(); c = c[(c[:, 13] == g) & (c[:, 14] == 21)]
+        assert len(c) == 1
+        out.append(c[0])
+    c = out[0]
+    assert np.allclose(c[4:7], -n, atol=1e-9) and abs(c[0] + (0.004 + r)) < 1e-9      # nearest face is +z: depth 4 mm + radius
+    assert abs((c[1:4] - gp) @ axis) < 1e-9                                          # at the middle of the inside stretch
+    assert all(np.abs(o - c).max() < 1e-6 for o in out[1:])
+
+
 def test_oracle_mpr_depth_on_mesh_face():
     env = oracle_env("bottle")
     env.reset()
