@@ -24,7 +24,7 @@ EXPORTS = [
 class Counters(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in (
         "env_steps", "substeps", "ncon", "nefc", "newton_iters", "ls_evals", "mpr_calls", "mpr_iters", "qp_iters",
-        "fail_physics", "fail_overflow", "chol_calls")]
+        "fail_physics", "fail_overflow", "chol_calls", "max_ncon", "max_nbasis", "max_nedge")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -299,8 +299,8 @@ static const float h_dop[H_NDOP][3] = H_DOP_TABLE;   // host copy for the model 
 // The two objects of the pair being solved live in shared memory (U_COBJ): mpr_penetration / support_w are out of line and
 // would otherwise read them from the local-memory stack.
 struct CObj { int type, nvert, ncl, pad; V3 pos; M3 mat; float size[3]; float pad2; const float4* vert; const float4* cl; };
-#define U_COBJ (U_CON_END)   // 2 x 24 words, inside the union's slack below the residual-force QP's extent
-static_assert(sizeof(CObj) == 96 && U_CON_END * 4 % 8 == 0 && U_CON_END + 48 <= U_QP_END, "CObj scratch");
+#define U_COBJ (U_AREF)      // 2 x 24 words over the head of the row arrays: build_rows writes those after collide() is done
+static_assert(sizeof(CObj) == 96 && U_COBJ * 4 % 8 == 0 && 48 <= H_NROW, "CObj scratch");
 struct Supp { V3 v, v1, v2; };
 // per-lane view of a mesh for the support function: lane k keeps the AABB of vertex cluster k in registers for the whole
 // MPR call, `warm` (uniform) is the last support vertex in local coordinates = a lower bound for the next query
@@ -578,7 +578,7 @@ __device__ __forceinline__ void write_contact(float* s, int idx, const RawCon& r
 __device__ __noinline__ void collide(float* s, const DevModel& m, int lane, unsigned& mpr_calls, unsigned& mpr_iters) {
   int ncon = 0, nq = 0;
   bool overflow = false;
-  int* mprq = (int*)(s + U_MPRQ);
+  unsigned short* mprq = (unsigned short*)(s + U_MPRQ);   // candidate indices < H_MAXCAND = 128
   for (int base = 0; base < m.ncand; base += 32) {
     const int ci = base + lane;
     int n = 0, kind = -1;
@@ -649,7 +649,7 @@ __device__ __noinline__ void collide(float* s, const DevModel& m, int lane, unsi
     // queue warp-cooperative candidates
     const bool qd = active && (kind == K_CONVEX || kind == K_PLANE_MESH);
     const unsigned bal = __ballot_sync(FULLMASK, qd);
-    if (qd) mprq[nq + __popc(bal & ((1u << lane) - 1u))] = ci;
+    if (qd) mprq[nq + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)ci;
     nq += __popc(bal);
     __syncwarp();
   }

@@ -57,7 +57,7 @@ __device__ __noinline__ bool pd_torque(float* s, const DevModel& m, int lane, co
 }
 
 // ---- record_contact: add hand-object contacts of the last forward to the per-hand-geom sums (world positions)
-__device__ __noinline__ void record_contacts(float* s, const DevModel& m, int lane) {
+__device__ __noinline__ void record_contacts(float* s, const DevModel& m, int lane, float* csum) {
   const int ncon = ((const int*)(s + S_MISC))[MI_NCON];
   const V3 org = ld3(s + S_ORG);
   for (int c = 0; c < ncon; c++) {
@@ -67,9 +67,9 @@ __device__ __noinline__ void record_contacts(float* s, const DevModel& m, int la
     if (lane < 12) {
       float v = cr[lane];
       if (lane < 3) v += comp(org, lane);
-      s[S_CSUM + 12 * slot + lane] += v;
+      csum[12 * slot + lane] += v;
     } else if (lane == 12) {
-      s[S_CCNT + slot] += 1.f;
+      csum[240 + slot] += 1.f;
     }
   }
   __syncwarp();
@@ -153,7 +153,7 @@ __device__ __noinline__ V3 matrix_to_axis_angle(const M3& R) {
 
 // ---- residual-force QP (solve_rfc).  Dual Newton in float64 on the 6-D wrench multiplier (DESIGN.md "RFC QP").
 // Scratch (union region): QP_CF contact-geom frames [19][12], QP_TS [19], QP_G1 [19] ints, QP_C [380] penalties.
-#define QP_CF (S_UNION)
+#define QP_CF (QP_BASE)
 #define QP_TS (QP_CF + H_NHG * 12)
 #define QP_G1 (QP_TS + 32)
 #define QP_C (QP_G1 + 32)

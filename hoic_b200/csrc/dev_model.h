@@ -7,9 +7,15 @@
 #define HN 32          // lanes = max bodies / dofs / geoms / joints
 #define H_NQ 36
 #define H_MAXCAND 128
-#define H_NCON 32      // contact capacity per env (HOIC_MAX_CONTACTS)
-#define H_NBASIS 64    // contact Jacobian basis rows per env (condim 3: 3 per contact, condim 4: 4)
+#ifndef H_NCON
+#define H_NCON 24      // contact capacity per env (<= HOIC_MAX_CONTACTS)
+#endif
+#ifndef H_NBASIS
+#define H_NBASIS 56    // contact Jacobian basis rows per env (condim 3: 3 per contact, condim 4: 4)
+#endif
+#ifndef H_NEDGE
 #define H_NEDGE 96     // pyramid edge rows per env
+#endif
 #define H_RFR 0        // row index ranges: friction-loss rows [0,32)
 #define H_RLIM 32      //                   joint-limit rows   [32,64)
 #define H_RCON 64      //                   contact edge rows  [64,64+H_NEDGE)
@@ -77,11 +83,12 @@ struct DevModel {
   int geom_cladr[HN], geom_ncl[HN];
   float geom_aabb_c[HN][3], geom_aabb_h[HN][3];   // mesh geoms: local AABB centre / half sizes (conservative pair culling)
   float geom_dop[HN][H_NDOP][2];                  // mesh geoms: [min, max] of the vertices along the c_dop directions
-  // collision candidates in MuJoCo's signature order
-  DevCand cand[H_MAXCAND];
   // env
   int hand_body_idx[HN];
   float base_pose[HN], ctrl_scale[HN], jkp[HN], jkd[HN], torque_lim[HN];
+  int stage_bytes, pad1;         // k_step stages this many leading bytes of the model into shared memory (0: reads stay global)
+  // collision candidates in MuJoCo's signature order; LAST member: only the first ncand entries are staged
+  DevCand cand[H_MAXCAND];
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -110,14 +117,18 @@ struct DevModel {
 #define S_SEARCH (S_GRAD + HN)
 #define S_TMP (S_SEARCH + HN)          // 32
 #define S_FCON (S_TMP + HN)            // qfrc_constraint
+#define S_MISC (S_FCON + HN)           // 16 scalars: ncon, nlim, nbasis, nedge, flags, ...
 #define MS_STRIDE 12                   // row stride of S_MS (16-byte aligned rows; entries beyond the depth stay zero)
-#define S_MS (S_FCON + HN)             // 32*12: M by (dof, ancestor depth): entry d of row i = M[i, ancestor of i at depth d]
+#define S_MS (S_MISC + 16)             // 32*12: M by (dof, ancestor depth): entry d of row i = M[i, ancestor of i at depth d]
 #define S_H (S_MS + 384)               // 576: lower triangle of the Newton Hessian / its Cholesky factor in 4x4 blocks
                                        //      (dev_math.cuh: warp_chol_solve); scratch of tree_solve outside the Newton iterations
-#define S_CSUM (S_H + 576)             // 19*12 contact sums -> 240
-#define S_CCNT (S_CSUM + 240)          // 32 (as float counts)
-#define S_MISC (S_CCNT + HN)           // 16 scalars: ncon, nlim, nbasis, nedge, flags, ...
-#define S_UNION (S_MISC + 16)
+// S_MS and S_H sit right below the union: both are dead after the last substep, so the residual-force QP of the step
+// tail starts its scratch at S_MS (QP_BASE) and the union only has to hold the position and constraint stages.
+// The per-hand-geom contact sums of record_contact (19 x 12 + counts) live in global memory (BatchDev.csum): they are
+// touched once per recorded contact, and every float of shared memory per env counts towards the warps an SM can hold.
+#define S_UNION (S_H + 576)
+#define QP_BASE S_MS
+#define CSUM_STRIDE 272                // global: 19*12 contact sums (240) + 32 counts
 // position / velocity stage temporaries
 #define U_XMAT (S_UNION)               // 32*9
 #define U_XAXIS (U_XMAT + 288)         // 32*3 per joint
@@ -143,9 +154,9 @@ struct DevModel {
 #define U_BV (U_RINFO + H_NROW)        // H_NBASIS: basis . v products
 #define U_BMASK (U_BV + H_NBASIS)      // H_NBASIS: dof mask of each basis row (bit i: dof i has a column)
 #define U_CINFO (U_BMASK + H_NBASIS)      // H_NCON * 8: basis offset, nbasis, edge offset, nedge, mu0, mu1, D, pad
-#define U_MPRQ (U_CINFO + H_NCON * 8)  // H_MAXCAND ints: queued MPR candidates
-#define U_CON_END (U_MPRQ + H_MAXCAND)
-#define U_QP_END (S_UNION + 3168)      // residual-force QP scratch (dev_env.cuh: QP_*; static_assert there)
+#define U_MPRQ (U_CINFO + H_NCON * 8)  // H_MAXCAND 16-bit indices: queued MPR candidates (later H_NBASIS ints: U_BINFO)
+#define U_CON_END (U_MPRQ + (H_MAXCAND / 2 > H_NBASIS ? H_MAXCAND / 2 : H_NBASIS))
+#define U_QP_END (QP_BASE + 3168)      // residual-force QP scratch (dev_env.cuh: QP_*; static_assert there)
 #define U_TS_END (S_UNION + 32 * 21)   // tree_solve's branch products (dev_math.cuh: TS_P)
 #define S_MAX2(a, b) ((a) > (b) ? (a) : (b))
 #define S_TOTAL ((S_MAX2(S_MAX2(U_CON_END, U_POS_END), S_MAX2(U_QP_END, U_TS_END)) + 3) & ~3)

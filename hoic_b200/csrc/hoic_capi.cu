@@ -33,6 +33,8 @@ struct BatchDev {
   int mode_train;
   unsigned long long* counters;       // hoic_counters as 12 x u64
   const int* perm;                    // optional env order (load balancing), NULL = identity
+  int model_smem;                     // bytes of shared memory behind the env regions that k_step may stage a model into
+  float* csum;                        // [N][CSUM_STRIDE] per-hand-geom contact sums / counts of the step (record_contact)
   float* rec_frames;                  // test-mode recording (hoic_set_record), NULL = off
   float* rec_surface;
 };
@@ -41,7 +43,7 @@ struct StepOut {
   float* obs; float* reward; float* info; uint8_t* done; uint8_t* fail; uint8_t* end; float* percent;
 };
 
-struct Cnt { unsigned substeps, ncon, nefc, newton, ls, mpr_calls, mpr_iters, qp, fail_phys, fail_over; };
+struct Cnt { unsigned substeps, ncon, nefc, newton, ls, mpr_calls, mpr_iters, qp, fail_phys, fail_over, max_ncon, max_nbasis, max_nedge; };
 
 __device__ __forceinline__ bool bad(float v) { return !(fabsf(v) <= F_MAXVAL); }
 
@@ -76,6 +78,9 @@ __device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int lane, 
   cnt.substeps++;
   cnt.ncon += misc[MI_NCON];
   cnt.nefc += m.nv + misc[MI_NLIM] + misc[MI_NEDGE];
+  cnt.max_ncon = max(cnt.max_ncon, (unsigned)misc[MI_NCON]);
+  cnt.max_nbasis = max(cnt.max_nbasis, (unsigned)misc[MI_NBASIS]);
+  cnt.max_nedge = max(cnt.max_nedge, (unsigned)misc[MI_NEDGE]);
   if (lane == 0) misc[MI_ITER] = (int)it;
   fail = __any_sync(FULLMASK, fail || bad(s[S_QACC + lane]));
   if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
@@ -89,7 +94,7 @@ __device__ bool substep_core(float* s, const DevModel& m, int lane, bool record,
   vel_stage(s, m, lane);
   if (!phase_smooth(s, m, lane)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
-  if (record) record_contacts(s, m, lane);
+  (void)record;   // single-substep entry: no contact averaging
   build_rows(s, m, lane);
   if (!phase_solve(s, m, lane, cnt, true)) return false;
   if (!euler_step(s, m, lane, nullptr)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
@@ -116,6 +121,9 @@ __device__ void flush_counters(const BatchDev& B, const Cnt& c, int lane, unsign
   atomicAdd(g + 8, (unsigned long long)c.qp);
   if (c.fail_phys) atomicAdd(g + 9, (unsigned long long)c.fail_phys);
   if (c.fail_over) atomicAdd(g + 10, (unsigned long long)c.fail_over);
+  atomicMax(g + 12, (unsigned long long)c.max_ncon);
+  atomicMax(g + 13, (unsigned long long)c.max_nbasis);
+  atomicMax(g + 14, (unsigned long long)c.max_nedge);
 }
 
 __device__ __forceinline__ EnvCtx make_ctx(const BatchDev& B, const int* ints) {
@@ -130,7 +138,7 @@ __device__ __forceinline__ EnvCtx make_ctx(const BatchDev& B, const int* ints) {
 
 // ---- tail of env.step after the substeps: averages, contact classification, residual-force QP (ho_im4.py:553-565, 631)
 __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, const float* og, float old_obj_vel, V3 vf, V3 vt,
-                                        float* rest, int& ncg_out, unsigned& qp_iters, float* surf) {
+                                        float* rest, int& ncg_out, unsigned& qp_iters, float* surf, const float* csum) {
   float rfc_score = 0.f;
   const int nhg = m.hand_geom1 - m.hand_geom0 + 1;
   const float inv_dt = 1.0f / (m.sim_step * m.timestep);
@@ -139,11 +147,12 @@ __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, c
   const V3 obj_a = v3(__shfl_sync(FULLMASK, acc, m.nv - 6), __shfl_sync(FULLMASK, acc, m.nv - 5), __shfl_sync(FULLMASK, acc, m.nv - 4));
   const V3 obj_oa = v3(__shfl_sync(FULLMASK, acc, m.nv - 3), __shfl_sync(FULLMASK, acc, m.nv - 2), __shfl_sync(FULLMASK, acc, m.nv - 1));
   // classify_contact: lane = hand geom slot
-  const bool has = lane < nhg && s[S_CCNT + lane] > 0.f;
+  const float ccnt = lane < nhg ? csum[240 + lane] : 0.f;
+  const bool has = ccnt > 0.f;
   float fr[12];
   if (has) {
-    const float ic = 1.0f / s[S_CCNT + lane];
-    for (int k = 0; k < 12; k++) fr[k] = s[S_CSUM + 12 * lane + k] * ic;
+    const float ic = 1.0f / ccnt;
+    for (int k = 0; k < 12; k++) fr[k] = csum[12 * lane + k] * ic;
     V3 n = ld3(fr + 3);
     n = n * (1.0f / norm(n));
     V3 t = fabsf(n.x) >= 1e-5f ? cross(n, v3(1.f, 0.f, 0.f)) : cross(n, v3(0.f, 1.f, 0.f));
@@ -152,7 +161,7 @@ __device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, c
     b = b * (1.0f / norm(b));
     st3(fr + 3, n); st3(fr + 6, t); st3(fr + 9, b);
   }
-  const float ts = has ? s[S_CCNT + lane] / (float)m.sim_step : 0.f;
+  const float ts = has ? ccnt / (float)m.sim_step : 0.f;
   const unsigned bal = __ballot_sync(FULLMASK, has);
   const int ncg = __popc(bal);
   ncg_out = ncg;
@@ -232,7 +241,23 @@ __global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const fl
   const bool live = slot < B.n_envs;
   const int env = live ? (B.perm ? B.perm[slot] : slot) : B.n_envs - 1;
   const int envc = env;
-  const DevModel& m = *B.env_model[envc];
+  // When every env of the CTA uses the same model (always, except in mixed-object batches) the model constants are staged
+  // once into shared memory behind the env regions: the phases then read joint / geom / candidate tables through shared
+  // memory instead of an L1 that the ~200 KB carve-out leaves little room for (box 4096 envs: 5.93 -> 5.80 ms).  Models with
+  // large meshes keep the L1 for their vertices instead (stage_bytes = 0; banana measured faster that way).
+  const DevModel* gm = B.env_model[envc];
+  DevModel* sm_model = reinterpret_cast<DevModel*>(smem + (size_t)H_WPB * S_TOTAL);
+  const int first = min(blockIdx.x * H_WPB, B.n_envs - 1);
+  const int nstage = gm->stage_bytes;
+  const bool uniform = __syncthreads_and(nstage > 0 && nstage <= B.model_smem && gm == B.env_model[B.perm ? B.perm[first] : first]);
+  if (uniform) {
+    const float2* src = reinterpret_cast<const float2*>(gm);
+    float2* dst = reinterpret_cast<float2*>(sm_model);
+    for (int i = threadIdx.x; i < nstage / 8; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  const DevModel& m = uniform ? *sm_model : *gm;
+
   float* st = B.state + (size_t)envc * ST_STRIDE;
   int* ints = (int*)(st + ST_INTS);
   int* misc = (int*)(s + S_MISC);
@@ -247,8 +272,8 @@ __global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const fl
   // current state in registers while the previous forward is recomputed
   const float cq = st[ST_QPOS + lane], cq32 = st[ST_QPOS + 32], cv = st[ST_QVEL + lane], cw = st[ST_WARM + lane];
   load_state(s, st, lane, ST_PQPOS, ST_PQVEL);
-  for (int i = lane; i < 240; i += 32) s[S_CSUM + i] = 0.f;
-  s[S_CCNT + lane] = 0.f;
+  float* csum = B.csum + (size_t)envc * CSUM_STRIDE;
+  if (live) for (int i = lane; i < CSUM_STRIDE; i += 32) csum[i] = 0.f;
   __syncwarp();
   const float old_obj_vel = (lane >= m.nv - 6 && lane < m.nv) ? cv : 0.f;
   float* og = B.old_geom + (size_t)envc * (HN * 12 + 4);
@@ -295,7 +320,7 @@ __global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const fl
     HB(3);
     if (ok) {
       collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
-      if (k + 1 < nsub) record_contacts(s, m, lane);
+      if (k + 1 < nsub) record_contacts(s, m, lane, csum);
     }
     if (k < 0) {
       if (ok) {
@@ -334,7 +359,7 @@ __global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const fl
   if (flags & 2) cnt.fail_over++;
   float rfc_score = 0.f, rest[6] = {0, 0, 0, 0, 0, 0};
   int ncg = 0;
-  if (!fail) rfc_score = step_tail(s, m, lane, og, old_obj_vel, vf, vt, rest, ncg, cnt.qp, surf);
+  if (!fail) rfc_score = step_tail(s, m, lane, og, old_obj_vel, vf, vt, rest, ncg, cnt.qp, surf, csum);
   // ---- bookkeeping, termination, reward, observation (ho_im4.py:641-662)
   ctx.cur_t += 1;
   float reward = 0.f;
@@ -504,8 +529,6 @@ __global__ void __launch_bounds__(32) k_substep_debug(BatchDev B, const float* c
   s[S_WARM + lane] = st[ST_WARM + lane];
   s[S_CTRL + lane] = lane < m.nu ? ctrl[(size_t)env * m.nu + lane] : 0.f;
   s[S_QAPP + lane] = qfrc_applied[(size_t)env * 32 + lane];
-  for (int i = lane; i < 240; i += 32) s[S_CSUM + i] = 0.f;
-  s[S_CCNT + lane] = 0.f;
   const float pq = s[S_QPOS + lane], pv = s[S_QVEL + lane], pq32 = st[ST_QPOS + 32];
   __syncwarp();
   const bool ok = substep_core(s, m, lane, false, cnt);
@@ -629,7 +652,7 @@ struct hoic_batch {
   const DevModel** env_model_dev;
   float *frames, *reward_w;
   int *motion_offset, *motion_len;
-  size_t smem_bytes;
+  size_t smem_bytes, step_smem;
 };
 
 extern "C" const char* hoic_last_error(void) { return g_err.c_str(); }
@@ -997,6 +1020,8 @@ bool build_dev_model(const void* blob, size_t nbytes, DevModel& D, std::vector<f
   }
   if (too_many) return false;
   D.ncand = ncand;
+  // leading bytes k_step stages into shared memory: everything up to the used candidates; large meshes keep the L1 instead
+  D.stage_bytes = mv.size() / 3 <= 1024 ? (int)((offsetof(DevModel, cand) + (size_t)ncand * sizeof(DevCand) + 7) & ~(size_t)7) : 0;
   return true;
 }
 
@@ -1045,6 +1070,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   CUDA_OKP(cudaMalloc(&b->b.state, (size_t)n_envs * ST_STRIDE * sizeof(float)));
   CUDA_OKP(cudaMemset(b->b.state, 0, (size_t)n_envs * ST_STRIDE * sizeof(float)));
   CUDA_OKP(cudaMalloc(&b->b.old_geom, (size_t)n_envs * (HN * 12 + 4) * sizeof(float)));
+  CUDA_OKP(cudaMalloc(&b->b.csum, (size_t)n_envs * CSUM_STRIDE * sizeof(float)));
   CUDA_OKP(cudaMalloc(&b->b.counters, 16 * sizeof(unsigned long long)));
   CUDA_OKP(cudaMemset(b->b.counters, 0, 16 * sizeof(unsigned long long)));
   CUDA_OKP(cudaMalloc(&b->reward_w, 24 * sizeof(float)));
@@ -1054,7 +1080,18 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   b->b.reward_w = b->reward_w;
   b->b.mode_train = 1;
   b->smem_bytes = (size_t)S_TOTAL * sizeof(float);
-  CUDA_OKP(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(b->smem_bytes * H_WPB)));
+  b->step_smem = b->smem_bytes * H_WPB;
+  {
+    static_assert(sizeof(DevModel) % 8 == 0 && (S_TOTAL * 4) % 16 == 0 && offsetof(DevModel, cand) % 8 == 0, "model staging copies 8-byte words");
+    size_t want = 0;
+    // mixed-object batches: CTAs hold envs of different models (the env order groups by cost), staging would rarely apply and
+    // the larger carve-out would cost every CTA half of its L1: stage only in single-model batches
+    if (n_models == 1) want = (size_t)models[0]->host.stage_bytes;
+    const size_t room = 232448 - b->step_smem;      // 227 KB of dynamic shared memory per CTA on sm_100
+    b->b.model_smem = (int)std::min(want, room);      // models that need more than this keep reading global memory
+    b->step_smem += b->b.model_smem;
+  }
+  CUDA_OKP(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->step_smem));
   CUDA_OKP(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
   { cudaFuncAttributes fa; CUDA_OKP(cudaFuncGetAttributes(&fa, k_get_work)); }   // load now: launches may later be graph-captured
   CUDA_OKP(cudaFuncSetAttribute(k_forward_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
@@ -1065,7 +1102,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
 extern "C" void hoic_batch_destroy(hoic_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  cudaFree(b->env_model_dev); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters);
+  cudaFree(b->env_model_dev); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum);
   cudaFree(b->reward_w); cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
   delete b;
 }
@@ -1131,7 +1168,7 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
   if (!b->b.frames) return set_err("hoic_step: call hoic_set_motions first");
   CUDA_OK(cudaSetDevice(b->device));
   StepOut o = {obs, reward, reward_info, done, fail, end, percent};
-  k_step<<<(b->n_envs + H_WPB - 1) / H_WPB, 32 * H_WPB, b->smem_bytes * H_WPB, (cudaStream_t)stream>>>(b->b, actions, o);
+  k_step<<<(b->n_envs + H_WPB - 1) / H_WPB, 32 * H_WPB, b->step_smem, (cudaStream_t)stream>>>(b->b, actions, o);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1225,6 +1262,7 @@ extern "C" int hoic_get_counters(hoic_batch* b, hoic_counters* out_host) {
   out_host->env_steps = h[0]; out_host->substeps = h[1]; out_host->ncon = h[2]; out_host->nefc = h[3]; out_host->newton_iters = h[4];
   out_host->ls_evals = h[5]; out_host->mpr_calls = h[6]; out_host->mpr_iters = h[7]; out_host->qp_iters = h[8];
   out_host->fail_physics = h[9]; out_host->fail_overflow = h[10]; out_host->chol_calls = h[11];
+  out_host->max_ncon = h[12]; out_host->max_nbasis = h[13]; out_host->max_nedge = h[14];
 #ifdef H_PROF
   { unsigned long long pr[16][2]; cudaMemcpyFromSymbol(pr, g_prof, sizeof pr);
     static const char* nm[16] = {"0:pd+applyft", "1:smooth", "2:build_rows", "3:collide", "4:euler", "5:vel", "6:pos", "7:solve", "8:prologue/tail-k-1"};

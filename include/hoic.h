@@ -50,6 +50,7 @@ typedef struct hoic_batch hoic_batch;
 typedef struct hoic_counters {
   unsigned long long env_steps, substeps, ncon, nefc, newton_iters, ls_evals, mpr_calls, mpr_iters, qp_iters;
   unsigned long long fail_physics, fail_overflow, chol_calls;
+  unsigned long long max_ncon, max_nbasis, max_nedge;   /* high-water marks against the kernels' per-env capacities */
 } hoic_counters;
 
 const char* hoic_last_error(void);
