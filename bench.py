@@ -28,8 +28,8 @@ METRIC = "env-steps/sec at 1/2/4/8 B200 vs mujoco_py sampler on N host cores"
 UNIT = "env-steps/s"
 ALGO_BYTES_PER_ENV_STEP = 6000.0          # ~1500 float32 of state / action / obs traffic per env step
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch from the `ncu --set full` capture of this workload
-# (profiles/r01_v12_k_step_raw.csv: 16.76 MB read + 6.20 MB write at box / 4096 envs); other workloads: not captured -> null
-NCU_TRAFFIC_BYTES = {("box", 4096): 16.756480e6 + 6.199808e6}
+# (profiles/r01_v14_k_step_raw.csv: 16.49 MB read + 8.27 MB write at box / 4096 envs); other workloads: not captured -> null
+NCU_TRAFFIC_BYTES = {("box", 4096): 16.493312e6 + 8.271104e6}
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline
@@ -106,7 +106,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        """Keep the samples taken inside [t0, t1] (the sampler is started early: nvidia-smi needs ~0.1 s to produce its
+        first line, longer than a short timed region)."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
@@ -114,7 +119,9 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [r for t, r in self.rows if t0 <= t <= t1]
+        for r in (inside if inside else [r for _, r in self.rows[-3:]]):
             p = [x.strip() for x in r.split(",")]
             if len(p) < 6:
                 continue
@@ -180,21 +187,22 @@ def run_ours(args):
         stats.update(r, info["reward_info"], d)
         return o
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     obs = env.reset()
     for _ in range(max(args.warmup, 3)):
         obs = one_step(obs)
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, L2 flushed (untimed) between steps, CUDA events on the launching stream
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     c0 = env.counters()
     l0 = L.hoic_launch_count()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.time()
     for k in range(args.steps):
         flush.fill_(k & 0xff)
         e0, e1, e2 = ev[k]
@@ -206,6 +214,7 @@ def run_ours(args):
         e2.record()
         stats.update(r, info["reward_info"], d)
     torch.cuda.synchronize()
+    clocks.window(t_wall0, time.time())
     if world > 1:
         dist.barrier()
     launches = L.hoic_launch_count() - l0
@@ -273,7 +282,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get((args.obj, N)),
-                     "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * N, "traffic_source": "profiles/r01_v12_k_step_raw.csv (ncu --set full, per launch)",
+                     "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * N, "traffic_source": "profiles/r01_v14_k_step_raw.csv (ncu --set full, per launch)",
                      "peak_source": peak_src, "kernel": "k_step", "kernel_ms": kernel_ms,
                      "note": "neither HBM nor tensor cores bind this kernel: it is FP32-pipe / latency bound, see roofline_fp32"},
         "roofline_fp32": {"bound": "fp32", "achieved": fp32_ach, "peak": tf.value, "unit": "TFLOP/s", "frac": fp32_ach / max(tf.value, 1e-9),
