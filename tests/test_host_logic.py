@@ -137,6 +137,28 @@ def test_capi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     lib.hoic_version.restype = ctypes.c_int
     assert lib.hoic_version() == 1
+    # the Python mirror of the header's layout constants and of hoic_counters (values through the C compiler itself)
+    import subprocess, tempfile
+    names = ["HOIC_OBS_DIM", "HOIC_ACT_DIM", "HOIC_FRAME_DIM", "HOIC_INFO_DIM", "HOIC_NQ", "HOIC_NV", "HOIC_MAX_CONTACTS", "HOIC_NHG",
+             "HOIC_REC_MAXCON", "HOIC_REC_CON", "HOIC_REC_STRIDE", "HOIC_SURF_MAXPT", "HOIC_SURF_PT", "HOIC_SURF_STRIDE"]
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "c.c")
+        open(src, "w").write('#include <stdio.h>\n#include "hoic.h"\nint main(void){' + "".join('printf("%s %%d\\n", (int)(%s));' % (n, n) for n in names) +
+                             'printf("COUNTERS %d\\n", (int)(sizeof(hoic_counters) / sizeof(unsigned long long))); return 0;}')
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "c"), src])
+        out = dict(l.split() for l in subprocess.check_output([os.path.join(td, "c")]).decode().splitlines())
+    val = lambda n: int(out[n])
+    assert val("COUNTERS") == len(capi.Counters._fields_)
+    assert (val("HOIC_OBS_DIM"), val("HOIC_ACT_DIM"), val("HOIC_FRAME_DIM"), val("HOIC_INFO_DIM")) == (capi.OBS_DIM, capi.ACT_DIM, capi.FRAME_DIM, capi.INFO_DIM)
+    assert (val("HOIC_NQ"), val("HOIC_NV"), val("HOIC_MAX_CONTACTS"), val("HOIC_NHG")) == (capi.NQ, capi.NV, capi.MAX_CONTACTS, capi.NHG)
+    assert (val("HOIC_REC_MAXCON"), val("HOIC_REC_CON"), val("HOIC_REC_STRIDE")) == (capi.REC_MAXCON, capi.REC_CON, capi.REC_STRIDE)
+    assert (val("HOIC_SURF_MAXPT"), val("HOIC_SURF_PT"), val("HOIC_SURF_STRIDE")) == (capi.SURF_MAXPT, capi.SURF_PT, capi.SURF_STRIDE)
+    import oracle
+    assert (oracle.REC_STRIDE, oracle.SURF_STRIDE) == (capi.REC_STRIDE, capi.SURF_STRIDE)
+    body = re.search(r"typedef struct hoic_counters \{(.*?)\} hoic_counters;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [f.strip() for f in re.sub(r"unsigned long long", "", body).replace(";", ",").split(",") if f.strip()]
+    assert fields == [n for n, _ in capi.Counters._fields_], (fields, capi.Counters._fields_)
 
 
 def test_vecenv_refuses_without_gpu():
