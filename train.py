@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--epoch", type=int, default=0, help="first epoch (adaptive schedules start here)")
     ap.add_argument("--min-batch-size", type=int, default=0, help="override cfg.min_batch_size (total over all GPUs)")
+    ap.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core matmuls in the policy / value MLPs (default: fp32; the reference runs fp64)")
     ap.add_argument("--load", default="", help="checkpoint to start from (iter_XXXX.p layout of the reference)")
     ap.add_argument("--save", default="", help="write the final checkpoint here (rank 0)")
     ap.add_argument("--eval", action="store_true", help="run eval_policy (test mode, mean action) after training")
@@ -35,6 +36,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    if a.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
     if a.obj == "mixed":
         models = [load_model(o) for o in ("box", "bottle", "banana")]
         ids = hdist.mixed_model_ids(a.envs * world, 3, rank, world)
