@@ -652,7 +652,8 @@ struct hoic_batch {
   const DevModel** env_model_dev;
   float *frames, *reward_w;
   int *motion_offset, *motion_len;
-  size_t smem_bytes, step_smem;
+  size_t smem_bytes, step_smem, frames_cap = 0;
+  int motions_cap = 0;
 };
 
 extern "C" const char* hoic_last_error(void) { return g_err.c_str(); }
@@ -1119,10 +1120,15 @@ extern "C" int hoic_set_motions(hoic_batch* b, const float* frames_host, const i
   }
   CUDA_OK(cudaSetDevice(b->device));
   CUDA_OK(cudaDeviceSynchronize());
-  cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
-  CUDA_OK(cudaMalloc(&b->frames, total * H_FRAME * sizeof(float)));
-  CUDA_OK(cudaMalloc(&b->motion_offset, n_motions * sizeof(int)));
-  CUDA_OK(cudaMalloc(&b->motion_len, n_motions * sizeof(int)));
+  if (total != b->frames_cap || n_motions != b->motions_cap) {
+    // (a table of unchanged shape is refreshed in place: the sliding-window tracking env rewrites its frames every step)
+    cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
+    b->frames = nullptr; b->motion_offset = nullptr; b->motion_len = nullptr; b->frames_cap = 0; b->motions_cap = 0;
+    CUDA_OK(cudaMalloc(&b->frames, total * H_FRAME * sizeof(float)));
+    CUDA_OK(cudaMalloc(&b->motion_offset, n_motions * sizeof(int)));
+    CUDA_OK(cudaMalloc(&b->motion_len, n_motions * sizeof(int)));
+    b->frames_cap = total; b->motions_cap = n_motions;
+  }
   CUDA_OK(cudaMemcpy(b->frames, frames_host, total * H_FRAME * sizeof(float), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(b->motion_offset, motion_offset_host, n_motions * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(b->motion_len, motion_len_host, n_motions * sizeof(int), cudaMemcpyHostToDevice));

@@ -91,6 +91,16 @@ class HandMimicVecEnv:
         self._motion_count = torch.as_tensor([len(p) for p in per], device=self.device)
         self._env_model = torch.as_tensor(self.env_model_id.astype(np.int64), device=self.device)
 
+    def set_motion_frames(self, frames):
+        """Replace the frames of ALL motions in place: `frames` [n_motions, T, 212] with the same n_motions / T as the
+        current table (one host->device copy; used by the sliding-window tracking env, hoic_b200/track.py)."""
+        f = np.ascontiguousarray(frames, dtype=np.float32)
+        nm, T = f.shape[0], f.shape[1]
+        assert f.shape[2] == capi.FRAME_DIM and nm == int(self.motion_len.numel()) and bool((self.motion_len == T).all())
+        lens = np.full(nm, T, dtype=np.int32)
+        offs = (np.arange(nm, dtype=np.int32) * T).astype(np.int32)
+        capi.check(self.L.hoic_set_motions(self._hb, capi.ptr(f.reshape(nm * T, capi.FRAME_DIM)), capi.ptr(offs), capi.ptr(lens), nm), "hoic_set_motions")
+
     def set_reward_weights(self, w24):
         w = np.ascontiguousarray(w24, dtype=np.float32)
         assert w.size == 24

@@ -483,3 +483,38 @@ def test_phys_metrics_vs_oracle_contacts():
         assert stable[t] == float(rest_ft[t] > 0.01)
         n_checked += len(ho) > 0
     assert n_checked > 10 and n_ambiguous == 0 and np.isfinite(pene).all() and (pene >= 0).all() and hand_j > 0 and ang_j >= 0
+
+
+def test_tracking_env_sliding_window_vs_oracle():
+    """HandMimicTrackEnv (the HandObjMimicTest mirror, ho_im_test.py:26-91): reset on the window's first frame, steps with a
+    new expert frame inserted every step, against the oracle driven through the same window layouts (whose equivalence to
+    the reference's window-relative accessors is pinned on the CPU: test_tracking_window_layout_...)."""
+    from hoic_b200 import motion as hmotion
+    from hoic_b200.track import HandMimicTrackEnv
+    mdl = model("box")
+    frames = hmotion.pack_frames(mdl.motion(1))
+    t0 = 40
+    window = frames[t0:t0 + 6].copy()
+    trk = HandMimicTrackEnv(mdl, 2, np.stack([window, window]))
+    orc = oracle_env("box")
+    orc.set_motion(np.concatenate([window, window[-1:]]))
+    o = orc.reset()
+    g = trk.reset().cpu().numpy()
+    assert np.abs(g[0] - o).max() < 2e-6 and np.array_equal(g[0], g[1])
+    assert np.abs(trk.get_expert_attr("hand_dof_seq", 3) - window[3, :26]).max() < 1e-7
+    rng = np.random.RandomState(4)
+    for step in range(8):
+        a = np.clip(rng.randn(32) * 0.1, -1, 1)
+        orc.set_motion(np.concatenate([window[:1], window]))
+        orc.cur_t = 0
+        oo, orw, od, oi = orc.step(a)
+        go, grw, gfail, gi = trk.step(torch.as_tensor(np.tile(a, (2, 1)), dtype=torch.float32))
+        err = np.abs(go.cpu().numpy()[0] - oo).max()
+        assert err < 2e-4 * (step + 1), (step, err)
+        assert abs(float(grw[0]) - orw) < 1e-4 * abs(orw) + 1e-5 * (step + 1) and bool(gfail[0]) == oi["fail"]
+        new = frames[t0 + 6 + step]
+        window = np.concatenate([window[1:], new[None]])
+        trk.insert_new_frame(np.stack([new, new]))
+    q, _ = trk.get_state()
+    assert np.abs(q.cpu().numpy()[0] - orc.get("qpos")).max() < 2e-4
+    trk.close()

@@ -522,3 +522,37 @@ def test_oracle_wrench_qp_known_answers():
     r1, s1, _ = oracle.solve_wrench_qp(off, W, [0, 0, 0], mu=0.75, w_t=1.0, surface_contact=False)
     r2, s2, _ = oracle.solve_wrench_qp(off, W, [0, 0, 0], mu=0.75, w_t=1e4, surface_contact=False)
     assert np.linalg.norm(r2[3:]) < np.linalg.norm(r1[3:]) and np.linalg.norm(r2[:3]) > np.linalg.norm(r1[:3])
+
+
+def test_tracking_window_layout_matches_the_window_relative_accessors():
+    """HandObjMimicTest (ho_im_test.py:26-91) looks the expert up relative to a sliding window, whatever cur_t is.  The
+    7-frame layouts hoic_b200/track.py feeds the ordinary kernels must give exactly that: checked on the oracle against
+    the numpy transcription of get_full_obs_v5 / calc_ho_diff reading a 6-frame window at cur_t = 0."""
+    from hoic_b200.dataset import unpack_frames
+    mdl = model("box")
+    M, ex = mdl.compiled(), mdl.motion(1)
+    frames = hmotion.pack_frames(ex)                       # [300, 212]
+    env = oracle_env("box")
+    rng = np.random.RandomState(2)
+    t0 = 40
+    window = frames[t0:t0 + 6].copy()
+    view_of = lambda w: unpack_frames(np.asarray(w, dtype=np.float64))
+    # reset: layout [w0..w5, w5], cur_t = 0
+    env.set_motion(np.concatenate([window, window[-1:]]))
+    o = env.reset()
+    v = R.EnvView(env.get("qpos"), env.get("qvel"), env.get("xpos").reshape(-1, 3), env.get("xquat").reshape(-1, 4), view_of(window), 0,
+                  M["env"]["hand_body_idx"], M["env"]["palm_body"])
+    assert np.abs(env.get("qpos")[:26] - window[0, :26]).max() == 0 and np.abs(R.get_full_obs_v5(v) - o).max() < 1e-12
+    for step in range(5):
+        # step: layout [w0, w0..w5], cur_t = 0; afterwards cur_t = 1 and every lookup is relative to the SAME window
+        env.set_motion(np.concatenate([window[:1], window]))
+        env.cur_t = 0
+        o, r, done, info = env.step(rng.randn(32) * 0.1)
+        v = R.EnvView(env.get("qpos"), env.get("qvel"), env.get("xpos").reshape(-1, 3), env.get("xquat").reshape(-1, 4), view_of(window), 0,
+                      M["env"]["hand_body_idx"], M["env"]["palm_body"], rfc_score=info["rfc_score"])
+        # the transcription reads window[cur_t + 1 + idx] = window[1 + idx] for the targets and window[0] for the errors
+        v_obs = R.EnvView(v.qpos, v.qvel, v.body_xpos, v.body_xquat, view_of(window), 0, v.hand_body_idx, v.palm_body)
+        assert np.abs(R.get_full_obs_v5(v_obs) - o).max() < 1e-12
+        assert np.abs(R.calc_ho_diff(v) - env.ho_diff()).max() < 1e-12
+        # the tracker delivers the next frame: insert_new_frame (ho_im_test.py:34-38)
+        window = np.concatenate([window[1:], frames[t0 + 6 + step][None]])
