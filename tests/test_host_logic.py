@@ -556,3 +556,35 @@ def test_tracking_window_layout_matches_the_window_relative_accessors():
         assert np.abs(R.calc_ho_diff(v) - env.ho_diff()).max() < 1e-12
         # the tracker delivers the next frame: insert_new_frame (ho_im_test.py:34-38)
         window = np.concatenate([window[1:], frames[t0 + 6 + step][None]])
+
+
+def test_oracle_spinning_object_friction_loss_and_quaternion_integration():
+    """Object spinning about a principal axis in free fall: the free joint's 0.001 N m friction loss decelerates it at
+    fl / (I + armature); semi-implicit Euler with the quaternion exponential map gives the rotation angle in closed form."""
+    env = oracle_env("box")
+    env.reset()
+    A = model("box").arrays
+    h, I, arm, fl = A["opt_timestep"][0], A["body_inertia"][24][2], A["dof_armature"][31], A["dof_frictionloss"][31]
+    q = env.get("qpos"); q[0:3] = [0, 0, 1.5]; q[26:29] = [0.5, 0.5, 3.0]; q[29:33] = [1, 0, 0, 0]
+    v = np.zeros(32); v[31] = 20.0
+    env.set_state(q, v); env.set_ctrl_applied(np.zeros(26), np.zeros(32))
+    n = 50
+    for _ in range(n):
+        env.mj_step()
+    a = fl / (I + arm)
+    w = env.get("qvel")[26:32]
+    assert abs(w[5] - (20.0 - a * h * n)) < 1e-9 and np.abs(w[3:5]).max() < 1e-12          # no precession about a principal axis
+    theta = h * (n * 20.0 - a * h * n * (n + 1) / 2)                                       # sum of the updated velocities
+    quat = env.get("qpos")[29:33]
+    assert np.abs(quat - [np.cos(theta / 2), 0, 0, np.sin(theta / 2)]).max() < 1e-9 and abs(np.linalg.norm(quat) - 1) < 1e-12
+    # about a non-principal direction the gyroscopic term enters: angular momentum R I R^T w only changes by the friction torque
+    v[29:32] = [8.0, -5.0, 12.0]
+    env.set_state(q, v)
+    Ib = A["body_inertia"][24]
+    L0 = Ib * v[29:32]                                                                      # body frame = world frame at t = 0
+    env.mj_step()
+    w1, q1 = env.get("qvel")[29:32], env.get("qpos")[29:33]
+    Rm = mjcf.quat2mat(q1) if hasattr(mjcf, "quat2mat") else R.quat2mat(q1)
+    # free-joint angular velocity is expressed in the body frame (MuJoCo convention)
+    L1 = Rm @ (Ib * w1)
+    assert np.abs(L1 - L0).max() < (fl + arm * np.abs(w1 - v[29:32]).max() / h) * h * 3 + 1e-7
