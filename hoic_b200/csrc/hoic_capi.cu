@@ -1092,7 +1092,16 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     b->b.model_smem = (int)std::min(want, room);      // models that need more than this keep reading global memory
     b->step_smem += b->b.model_smem;
   }
-  CUDA_OKP(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->step_smem));
+  {
+    // the attribute belongs to the function, not to the batch: never lower it below what an earlier, still living batch
+    // of this process launches with (a box batch stages its model and needs more than a banana batch created after it)
+    static size_t step_smem_attr[64] = {0};
+    size_t& cur = step_smem_attr[device & 63];
+    if (b->step_smem > cur) {
+      CUDA_OKP(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->step_smem));
+      cur = b->step_smem;
+    }
+  }
   CUDA_OKP(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
   { cudaFuncAttributes fa; CUDA_OKP(cudaFuncGetAttributes(&fa, k_get_work)); }   // load now: launches may later be graph-captured
   CUDA_OKP(cudaFuncSetAttribute(k_forward_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));

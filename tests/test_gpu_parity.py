@@ -518,3 +518,18 @@ def test_tracking_env_sliding_window_vs_oracle():
     q, _ = trk.get_state()
     assert np.abs(q.cpu().numpy()[0] - orc.get("qpos")).max() < 2e-4
     trk.close()
+
+
+def test_two_live_batches_with_different_shared_memory_needs():
+    """A box batch (model staged into shared memory: larger launch) must keep stepping after a banana batch (smaller
+    launch) was created in the same process: the dynamic-shared-memory cap is a per-function attribute."""
+    a = make_env("box", 4)
+    a.reset(motion_id=[0] * 4, start_idx=[0] * 4)
+    o1 = a.step(torch.zeros(4, 32))[0].clone()
+    b = make_env("banana", 4)
+    b.reset(motion_id=[0] * 4, start_idx=[0] * 4)
+    ob = b.step(torch.zeros(4, 32))[0]
+    o2 = a.step(torch.zeros(4, 32))[0]
+    torch.cuda.synchronize()
+    assert torch.isfinite(o1).all() and torch.isfinite(o2).all() and torch.isfinite(ob).all() and not torch.equal(o1, o2)
+    a.close(); b.close()
