@@ -1,0 +1,17 @@
+"""Tiny workload for compute-sanitizer (memcheck / racecheck): python tools/sanitize_small.py [obj] [n_envs] [steps]"""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import model
+from hoic_b200.vecenv import HandMimicVecEnv
+obj = sys.argv[1] if len(sys.argv) > 1 else "box"
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+mdl = model(obj)
+env = HandMimicVecEnv(mdl, N, [mdl.motion(1)], seed=1, auto_reset=True, random_start=False)
+env.reset(motion_id=[0] * N, start_idx=[100] * N)
+env.set_record(True)
+for _ in range(K):
+    o, r, d, i = env.step(torch.zeros(N, 32, device="cuda"))
+torch.cuda.synchronize()
+print(obj, "ok", float(r.mean()), env.counters()["ncon"])
