@@ -588,3 +588,18 @@ def test_oracle_spinning_object_friction_loss_and_quaternion_integration():
     # free-joint angular velocity is expressed in the body frame (MuJoCo convention)
     L1 = Rm @ (Ib * w1)
     assert np.abs(L1 - L0).max() < (fl + arm * np.abs(w1 - v[29:32]).max() / h) * h * 3 + 1e-7
+
+
+def test_frame_table_roundtrip_and_window_packers():
+    """[T, 212] frame table <-> expert dict (hoic_b200/dataset.py, motion.py) and the tracking env's frame packers."""
+    from hoic_b200.dataset import unpack_frames
+    from hoic_b200.track import _pack
+    ex = model("box").motion(1)
+    fr = hmotion.pack_frames(ex)
+    back = unpack_frames(fr)
+    for k in hmotion.EXPERT_KEYS:
+        assert back[k].shape == ex[k].shape and np.array_equal(back[k], ex[k])
+    assert back["seq_len"] == ex["seq_len"] and np.array_equal(hmotion.pack_frames(back), fr)
+    one = {k: ex[k][7] for k in hmotion.EXPERT_KEYS}                 # a single frame as the reference's insert_new_frame gets it
+    assert np.allclose(_pack([one, one]), fr[7][None].repeat(2, 0)) and _pack(fr[3:9]).shape == (6, 212)
+    assert np.allclose(_pack({k: ex[k][3:9] for k in hmotion.EXPERT_KEYS}), fr[3:9])
