@@ -603,3 +603,31 @@ def test_frame_table_roundtrip_and_window_packers():
     one = {k: ex[k][7] for k in hmotion.EXPERT_KEYS}                 # a single frame as the reference's insert_new_frame gets it
     assert np.allclose(_pack([one, one]), fr[7][None].repeat(2, 0)) and _pack(fr[3:9]).shape == (6, 212)
     assert np.allclose(_pack({k: ex[k][3:9] for k in hmotion.EXPERT_KEYS}), fr[3:9])
+
+
+def test_oracle_joint_limit_row_follows_mujocos_impedance_formulas():
+    """A limited joint inside its margin: the row's D and aref against MuJoCo 2.1's published formulas (mj_makeImpedance:
+    K = 1 / (dmax^2 tc^2 dr^2), B = 2 / (dmax tc); getimpedance: power-p sigmoid between d0 and dmax over `width`;
+    R = (1 - imp) / imp * dof_invweight0; aref = -B vel - K imp (pos - margin)), on both sigmoid branches and saturated."""
+    env = oracle_env("box")
+    env.reset()
+    A = model("box").arrays
+    j = 10
+    lo, hi = A["jnt_range"][j]
+    margin, (tc, dr), (d0, dmax, width, mid, power) = A["jnt_margin"][j], A["jnt_solref"][j], A["jnt_solimp"][j]
+    iw = A["dof_invweight0"][j]
+    q0 = env.get("qpos"); q0[0:3] = [0, 0, 1.5]; q0[26:29] = [2, 2, 3]
+    for dist, vel in [(-0.004, 0.3), (margin - 0.0003, -0.2), (margin - 0.0007, 0.0), (margin - 0.00099, 0.1)]:
+        q = q0.copy(); q[j] = hi - dist                    # upper limit: pos = range_hi - q
+        v = np.zeros(32); v[j] = vel
+        env.set_state(q, v)
+        nefc = env.counters()["nefc"]
+        pos, D, aref, J = env.get("efc_pos")[32:nefc], env.get("efc_D")[32:nefc], env.get("efc_aref")[32:nefc], env.efc_J()[32:nefc]
+        r = int(np.argmin(np.abs(pos - dist)))
+        assert abs(pos[r] - dist) < 1e-12 and J[r, j] == -1.0 and np.count_nonzero(J[r]) == 1
+        x = min(abs(dist - margin) / width, 1.0)
+        y = x ** power / mid ** (power - 1) if x <= mid else 1 - (1 - x) ** power / (1 - mid) ** (power - 1)
+        imp = d0 + y * (dmax - d0)
+        K, B = 1.0 / (dmax * dmax * tc * tc * dr * dr), 2.0 / (dmax * tc)
+        assert abs(D[r] - imp / ((1 - imp) * iw)) < 1e-12 * D[r]
+        assert abs(aref[r] - (-B * (-vel) - K * imp * (dist - margin))) < 1e-10 * max(1.0, abs(aref[r]))
