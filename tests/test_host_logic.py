@@ -631,3 +631,62 @@ def test_oracle_joint_limit_row_follows_mujocos_impedance_formulas():
         K, B = 1.0 / (dmax * dmax * tc * tc * dr * dr), 2.0 / (dmax * tc)
         assert abs(D[r] - imp / ((1 - imp) * iw)) < 1e-12 * D[r]
         assert abs(aref[r] - (-B * (-vel) - K * imp * (dist - margin))) < 1e-10 * max(1.0, abs(aref[r]))
+
+
+def _seg_seg_closest(p1, d1, h1, p2, d2, h2):
+    """Closest points of two segments p_i + t d_i, |t| <= h_i (unit d_i), by brute force over the candidate set of the
+    standard clamped solution (independent of the oracle's implementation)."""
+    best = None
+    A = np.array([[1.0, -(d1 @ d2)], [-(d1 @ d2), 1.0]])
+    rhs = np.array([(p2 - p1) @ d1, (p1 - p2) @ d2])
+    cands = []
+    if abs(np.linalg.det(A)) > 1e-12:
+        t = np.linalg.solve(A, rhs)
+        cands.append((np.clip(t[0], -h1, h1), np.clip(t[1], -h2, h2)))
+    for s in (-h1, h1):
+        cands.append((s, np.clip((p1 + s * d1 - p2) @ d2, -h2, h2)))
+    for u in (-h2, h2):
+        cands.append((np.clip((p2 + u * d2 - p1) @ d1, -h1, h1), u))
+    for s, u in cands:
+        for _ in range(3):                                  # alternate projections: converges for segments
+            u = np.clip((p1 + s * d1 - p2) @ d2, -h2, h2)
+            s = np.clip((p2 + u * d2 - p1) @ d1, -h1, h1)
+        a, b = p1 + s * d1, p2 + u * d2
+        if best is None or np.linalg.norm(a - b) < best[0]:
+            best = (np.linalg.norm(a - b), a, b)
+    return best
+
+
+def test_oracle_capsule_capsule_pairs_vs_segment_distance():
+    """The explicit finger-finger <pair>s (condim 1, capsule-capsule): in random hand poses every reported contact has
+    dist = segment distance - r1 - r2, the normal from geom1 to geom2 and the position midway between the surfaces, and no
+    penetrating pair goes unreported (mjc_CapsuleCapsule restated; margin = gap = 0 so contact iff penetrating)."""
+    env = oracle_env("box")
+    env.reset()
+    A = model("box").arrays
+    rng = np.random.RandomState(7)
+    lo, hi = A["jnt_range"][:26, 0], A["jnt_range"][:26, 1]
+    pairs = [(int(a), int(b)) for a, b in zip(A["pair_geom1"], A["pair_geom2"]) if A["geom_type"][int(a)] == 3 and A["geom_type"][int(b)] == 3]
+    seen = 0
+    for trial in range(40):
+        q = env.get("qpos")
+        q[0:3] = [0, 0, 1.5]; q[3:6] = rng.randn(3) * 0.3; q[26:29] = [2, 2, 3]
+        q[6:26] = lo[6:] + rng.rand(20) * (hi[6:] - lo[6:])
+        env.set_state(q, np.zeros(32))
+        gp, gm = env.get("geom_xpos").reshape(-1, 3), env.get("geom_xmat").reshape(-1, 3, 3)
+        c = env.contacts()
+        reported = {(int(r[13]), int(r[14])): r for r in c if int(r[15]) == 1}
+        for g1, g2 in set(pairs):
+            r1, h1, r2, h2 = A["geom_size"][g1][0], A["geom_size"][g1][1], A["geom_size"][g2][0], A["geom_size"][g2][1]
+            d, a, b = _seg_seg_closest(gp[g1], gm[g1][:, 2], h1, gp[g2], gm[g2][:, 2], h2)
+            dist = d - r1 - r2
+            if (g1, g2) in reported:
+                row = reported[(g1, g2)]
+                n = (b - a) / d
+                assert abs(row[0] - dist) < 1e-9 and dist < 0, (g1, g2, row[0], dist)
+                assert np.abs(row[4:7] - n).max() < 1e-7
+                assert np.abs(row[1:4] - 0.5 * ((a + n * r1) + (b - n * r2))).max() < 1e-9
+                seen += 1
+            else:
+                assert dist > -1e-9, (g1, g2, dist)
+    assert seen > 15
