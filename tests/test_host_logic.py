@@ -690,3 +690,51 @@ def test_oracle_capsule_capsule_pairs_vs_segment_distance():
             else:
                 assert dist > -1e-9, (g1, g2, dist)
     assert seen > 15
+
+
+def test_oracle_apply_ft_is_the_transposed_point_jacobian():
+    """mj_applyFT (gravity compensation and the residual wrench enter the dynamics through it, ho_im4.py:488-501, 526-536):
+    qfrc = J_p^T f + J_r^T tau with the point Jacobian of a body-fixed point, checked against finite differences of the
+    forward kinematics for the 26 scalar hand joints and against virtual work for the object's free joint."""
+    import ctypes as C
+    import oracle
+    env = oracle_env("box")
+    env.reset()
+    L = oracle.lib()
+    L.orc_env_data.restype = C.c_void_p
+    L.orc_apply_ft.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    A = model("box").arrays
+    rng = np.random.RandomState(9)
+    q = env.get("qpos")
+    q[6:26] += rng.randn(20) * 0.1
+    q[3:6] = rng.randn(3) * 0.4
+    g = 12                                             # a finger capsule; its centre is a body-fixed point
+    body = int(A["geom_bodyid"][g])
+
+    def point(qq):
+        env.set_state(qq, np.zeros(32))
+        return env.get("geom_xpos").reshape(-1, 3)[g].copy()
+    eps = 1e-6
+    Jfd = np.zeros((3, 26))
+    for i in range(26):
+        dq = np.zeros(33); dq[i] = eps
+        Jfd[:, i] = (point(q + dq) - point(q - dq)) / (2 * eps)
+    p = point(q)
+    data = C.c_void_p(L.orc_env_data(env.env))
+    P = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.c_void_p)
+    for k in range(3):
+        f = np.zeros(3); f[k] = 1.0
+        qfrc = np.zeros(32)
+        L.orc_apply_ft(C.c_void_p(env.model), data, P(f), P(np.zeros(3)), P(p), body, qfrc.ctypes.data_as(C.c_void_p))
+        assert np.abs(qfrc[:26] - Jfd[k]).max() < 1e-7 and not qfrc[26:].any()      # the object's dofs do not move a finger
+    # object (free joint): force at an offset point -> translational dofs get f (world frame), rotational dofs r x f in the BODY frame
+    ob = 24
+    r_world = np.array([0.01, -0.02, 0.015])
+    f = np.array([0.3, -0.2, 0.5])
+    env.set_state(q, np.zeros(32))
+    op = q[26:29]
+    Rm = R.quat2mat(q[29:33] / np.linalg.norm(q[29:33]))
+    qfrc = np.zeros(32)
+    L.orc_apply_ft(C.c_void_p(env.model), data, P(f), P(np.zeros(3)), P(op + r_world), ob, qfrc.ctypes.data_as(C.c_void_p))
+    assert np.abs(qfrc[26:29] - f).max() < 1e-12 and np.abs(qfrc[29:32] - Rm.T @ np.cross(r_world, f)).max() < 1e-12
+    assert not qfrc[:26].any()
