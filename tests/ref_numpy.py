@@ -231,3 +231,32 @@ def solve_rfc_numpy(F, T, frames, ts_counts, geom_xpos_g1, gvel, gangvel, obj_p,
     x = res.x
     rest_f, rest_t = F - J_f @ x, T - J_t @ x
     return np.linalg.norm(rest_f) + math.sqrt(w_t) * np.linalg.norm(rest_t), 0.5 * x @ Q @ x + p @ x, Q, p
+
+
+def compute_torque_numpy(qpos, qvel, ref_qpos, ctrl, M, C, jkp, jkd, ctrl_scale, torque_lim, dt):
+    """Literal transcription of HandObjMimic4.compute_torque + compute_desired_accel + the clip of do_simulation
+    (uhc/envs/ho_im4.py:393-486, :521) for action_type 'position', pd_type 'rel', grot_type 'euler', no meta-PD:
+    qpos / qvel / ref_qpos are the 26 hand entries, M and C the hand block of mj_fullM(qM) and qfrc_bias."""
+    from scipy.linalg import cho_factor, cho_solve
+    qpos, qvel = qpos.copy(), qvel.copy()
+    target_pos = np.zeros_like(qpos)
+    ctrl_pos, ctrl_rot, ctrl_loco = ctrl[:3], ctrl[3:6], ctrl[6:26]
+    target_pos[0:3] = ref_qpos[0:3] + 0.1 * ctrl_pos
+    target_pos[6:] = ref_qpos[6:] + ctrl_scale[6:] * ctrl_loco
+    target_pos[3:6] = ref_qpos[3:6] + 0.3 * ctrl_rot
+    k_p, k_d = np.zeros(qvel.shape[0]), np.zeros(qvel.shape[0])
+    k_p[:], k_d[:] = jkp, jkd
+    qpos_err = qpos[:] + qvel[:] * dt - target_pos
+    qvel_err = qvel
+    rot_qpos_err = qpos_err[3:].copy()
+    while np.any(rot_qpos_err > np.pi):
+        rot_qpos_err[rot_qpos_err > np.pi] -= 2 * np.pi
+    while np.any(rot_qpos_err < -np.pi):
+        rot_qpos_err[rot_qpos_err < -np.pi] += 2 * np.pi
+    qpos_err[3:] = rot_qpos_err[:]
+    K_p, K_d = np.diag(k_p), np.diag(k_d)
+    q_accel = cho_solve(cho_factor(M + K_d * dt, overwrite_a=True, check_finite=False),
+                        -C[:, None] - K_p.dot(qpos_err[:, None]) - K_d.dot(qvel_err[:, None]), overwrite_b=True, check_finite=False).squeeze()
+    qvel_err += q_accel * dt
+    torque = -jkp * qpos_err - jkd * qvel_err
+    return np.clip(torque, -torque_lim, torque_lim)

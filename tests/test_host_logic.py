@@ -738,3 +738,27 @@ def test_oracle_apply_ft_is_the_transposed_point_jacobian():
     L.orc_apply_ft(C.c_void_p(env.model), data, P(f), P(np.zeros(3)), P(op + r_world), ob, qfrc.ctypes.data_as(C.c_void_p))
     assert np.abs(qfrc[26:29] - f).max() < 1e-12 and np.abs(qfrc[29:32] - Rm.T @ np.cross(r_world, f)).max() < 1e-12
     assert not qfrc[:26].any()
+
+
+@pytest.mark.parametrize("obj", ["box", "banana"])
+def test_oracle_stable_pd_vs_numpy_transcription(obj):
+    """compute_torque / compute_desired_accel (ho_im4.py:393-486) + torque clip (:521): the oracle's stable PD on the STALE
+    mass matrix and bias of the last forward against the literal transcription with scipy's Cholesky."""
+    env = oracle_env(obj)
+    mdl = model(obj)
+    A, ex = mdl.arrays, mdl.motion(1)
+    rng = np.random.RandomState(12)
+    env.reset()
+    dt = A["opt_timestep"][0]
+    clipped = 0
+    for t in range(1, 9):
+        env.step(rng.randn(32) * 0.2)
+        for scale in (0.3, 3.0):                            # the larger one drives some torques into the clip
+            a = np.clip(rng.randn(32) * scale, -1, 1)
+            got = env.compute_torque(a)
+            want = R.compute_torque_numpy(env.get("qpos")[:26], env.get("qvel")[:26], ex["hand_dof_seq"][t], a, env.qM()[:26, :26],
+                                          env.get("qfrc_bias")[:26], A["env_jkp"][:26], A["env_jkd"][:26], A["env_ctrl_scale"][:26],
+                                          A["env_torque_lim"][:26], dt)
+            assert np.abs(got - want).max() < 1e-9 * max(1.0, np.abs(want).max())
+            clipped += int((np.abs(want) == A["env_torque_lim"][:26]).sum())
+    assert clipped > 0
