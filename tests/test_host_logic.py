@@ -762,3 +762,24 @@ def test_oracle_stable_pd_vs_numpy_transcription(obj):
             assert np.abs(got - want).max() < 1e-9 * max(1.0, np.abs(want).max())
             clipped += int((np.abs(want) == A["env_torque_lim"][:26]).sum())
     assert clipped > 0
+
+
+def test_oracle_reproduces_extras_goldens():
+    """Regression fixtures of the widened rows (tools/make_golden.py extras_fixture): test-mode record, wrench QPs, preprocessing."""
+    import oracle
+    G = np.load(os.path.join(ROOT, "tests", "golden", "extras.npz"))
+    env = oracle_env("box", start_idx=100)
+    env.set_mode("test"); env.set_record(True); env.reset()
+    for t in range(len(G["rec_actions"])):
+        env.step(G["rec_actions"][t])
+        fr, su = env.record()
+        assert np.abs(fr - G["rec_frames"][t]).max() < 1e-7 and np.abs(su - G["rec_surface"][t]).max() < 1e-6
+    assert G["rec_frames"][:, :, 114].max() >= 1 and G["rec_surface"][:, 7].max() == 1      # the fixture does contain contacts
+    for k in range(len(G["qp_n"])):
+        nc = int(G["qp_n"][k])
+        rest, score, _ = oracle.solve_wrench_qp(G["qp_contacts"][k][:nc], G["qp_target"][k], G["qp_center"][k], mu=0.75, w_t=1e4)
+        assert np.abs(rest - G["qp_rest"][k]).max() < 1e-9 and abs(score - G["qp_score"][k]) < 1e-9
+    mdl = model("bottle")
+    ex = mdl.motion(2)
+    fr, cm, cp = oracle.preprocess_seq(mdl.blob, ex["hand_dof_seq"][::10], ex["obj_pose_seq"][::10], 3.0)
+    assert np.abs(fr - G["pre_frames"]).max() < 1e-10 and np.array_equal(cm, G["pre_cmask"]) and np.abs(cp - G["pre_cpos"]).max() < 1e-9

@@ -70,7 +70,47 @@ def substep_fixture(obj, n_states=48, seed=0):
     return out
 
 
+def extras_fixture():
+    """Fixtures of the widened rows: the test-mode record of box steps in the grasp, random wrench QPs, a contact pre-pass."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    out = {}
+    env = oracle_env("box", start_idx=100)
+    env.set_mode("test"); env.set_record(True); env.reset()
+    rng = np.random.RandomState(21)
+    acts, frames, surf = [], [], []
+    for t in range(4):
+        a = np.clip(rng.randn(32) * 0.1, -1, 1)
+        env.step(a)
+        fr, su = env.record()
+        acts.append(a); frames.append(fr); surf.append(su)
+    out.update(rec_actions=np.array(acts), rec_frames=np.array(frames), rec_surface=np.array(surf))
+    qc, qt, qce, qn, qrest, qscore = [], [], [], [], [], []
+    for nc in (1, 2, 5, 19):
+        c = np.zeros((19, 12)); center = rng.randn(3) * 0.1 + [0.4, 0.4, 0.6]
+        for k in range(nc):
+            n = rng.randn(3); n /= np.linalg.norm(n)
+            t = np.cross(n, [1.0, 0, 0]) if abs(n[0]) < 0.9 else np.cross(n, [0, 1.0, 0]); t /= np.linalg.norm(t)
+            c[k] = np.concatenate([center + rng.randn(3) * 0.03, n, t, np.cross(n, t)])
+        target = np.concatenate([rng.randn(3) * 0.5 + [0, 0, 0.6], rng.randn(3) * 0.005])
+        rest, score, _ = oracle.solve_wrench_qp(c[:nc], target, center, mu=0.75, w_t=1e4)
+        qc.append(c); qt.append(target); qce.append(center); qn.append(nc); qrest.append(rest); qscore.append(score)
+    out.update(qp_contacts=np.array(qc), qp_target=np.array(qt), qp_center=np.array(qce), qp_n=np.array(qn, dtype=np.int32),
+               qp_rest=np.array(qrest), qp_score=np.array(qscore))
+    mdl = model("bottle")
+    ex = mdl.motion(2)
+    fr, cm, cp = oracle.preprocess_seq(mdl.blob, ex["hand_dof_seq"][::10], ex["obj_pose_seq"][::10], 3.0)
+    out.update(pre_frames=fr, pre_cmask=cm, pre_cpos=cp)
+    return out
+
+
 if __name__ == "__main__":
+    d = extras_fixture()
+    p = os.path.join(ROOT, "tests", "golden", "extras.npz")
+    np.savez_compressed(p, **d)
+    print("extras", {k: v.shape for k, v in d.items()}, os.path.getsize(p), "bytes")
+    if "--extras-only" in sys.argv:
+        sys.exit(0)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for obj in OBJECTS:
         d = rollout_fixture(obj)
