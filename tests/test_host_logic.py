@@ -783,3 +783,54 @@ def test_oracle_reproduces_extras_goldens():
     ex = mdl.motion(2)
     fr, cm, cp = oracle.preprocess_seq(mdl.blob, ex["hand_dof_seq"][::10], ex["obj_pose_seq"][::10], 3.0)
     assert np.abs(fr - G["pre_frames"]).max() < 1e-10 and np.array_equal(cm, G["pre_cmask"]) and np.abs(cp - G["pre_cpos"]).max() < 1e-9
+
+
+def test_single_env_facade_attribute_surface_with_a_fake_engine():
+    """hoic_b200/env_facade.py: the HandObjMimic4 attribute surface the reference's callers read, exercised on
+    the CPU with a stand-in that has HandMimicVecEnv's method signatures (the façade only forwards to reset / step / get_state /
+    get_derived / get_rfc / set_motions / set_mode, each covered on the GPU by tests/test_gpu_parity.py)."""
+    import torch
+    from hoic_b200.env_facade import HandObjMimic4, ho_mimic_reward_9
+    mdl = model("box")
+    ex = mdl.motion(1)
+
+    class Fake:
+        def __init__(self):
+            self.mode, self.t, self.motions = None, 0, None
+        def set_mode(self, m): self.mode = m
+        def set_motions(self, ms): self.motions = ms
+        def reset(self, motion_id=None, start_idx=None):
+            self.t = 0
+            return torch.full((1, 617), 0.5)
+        def step(self, a):
+            assert a.shape == (1, 32) and a.dtype == torch.float32
+            self.t += 1
+            info = dict(fail=torch.tensor([0], dtype=torch.uint8), end=torch.tensor([1 if self.t >= 2 else 0], dtype=torch.uint8),
+                        percent=torch.tensor([self.t / 299.0]), reward_info=torch.arange(9, dtype=torch.float32)[None] * 0.1)
+            return torch.full((1, 617), float(self.t)), torch.tensor([0.25 * self.t]), info["end"].clone(), info
+        def get_state(self): return torch.arange(33, dtype=torch.float32)[None], torch.arange(32, dtype=torch.float32)[None] * 2
+        def get_derived(self): return torch.arange(75, dtype=torch.float32).reshape(1, 25, 3), torch.ones(1, 25, 4), None, None
+        def get_rfc(self): return torch.tensor([[0.75, 0, 0, 0, 0, 0, 0, 1.0]])
+        def close(self): pass
+    fake = Fake()
+    env = HandObjMimic4(mdl.cfg, ex, mdl, mode="test", _vecenv=fake)
+    assert fake.mode == "test" and env.observation_space.shape[0] == 617 and env.action_space.shape[0] == 32
+    assert (env.ndof, env.vf_dim, env.hand_qpos_dim, env.expert_len, env.start_ind, env.cur_t) == (26, 6, 26, 300, 0, 0)
+    o = env.reset()
+    assert o.dtype == np.float64 and o.shape == (617,)
+    o, r, done, info = env.step(np.zeros(32))
+    assert r == 1.0 and done is False and info["fail"] is False and info["end"] is False and abs(info["percent"] - 1 / 299.0) < 1e-7
+    rew, ri = ho_mimic_reward_9(env, o, np.zeros(32), info)
+    assert rew == 0.25 and np.allclose(ri, np.arange(9) * 0.1) and env.rfc_score == 0.75 and env.cur_t == 1
+    _, _, done, info = env.step(np.zeros(26))           # a caller without residual force entries: padded
+    assert done is True and info["end"] is True
+    assert np.array_equal(env.get_hand_qpos(), np.arange(26.0)) and np.array_equal(env.get_obj_qpos(), np.arange(26.0, 33.0))
+    assert np.array_equal(env.get_obj_qvel(), np.arange(26.0, 32.0) * 2) and env.data.qpos.shape == (33,)
+    assert env.get_wbody_pos().shape == (63,) and env.get_wbody_quat().shape == (84,)
+    assert np.array_equal(env.get_wbody_pos()[:3], np.arange(75.0).reshape(25, 3)[env.hand_body_idx[0]])
+    assert np.array_equal(env.get_expert_attr("hand_dof_seq", 10_000), ex["hand_dof_seq"][-1])          # clamp (ho_im4.py:740)
+    assert np.array_equal(env.get_expert_hand_qpos(delta_t=1), ex["hand_dof_seq"][3]) and env.get_expert_obj_vel().shape == (6,)
+    env.set_expert({k: (v[50:] if hasattr(v, "shape") else v) for k, v in ex.items()})
+    assert env.expert_len == 250 and env.cur_t == 0 and fake.motions is not None
+    env.set_mode("train")
+    assert fake.mode == "train" and env.seed(3) == [3]
