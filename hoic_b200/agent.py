@@ -48,18 +48,24 @@ class AgentHandMimic:
         self.world = torch.distributed.get_world_size() if hdist._on() else 1
         seed = cfg.seed if seed is None else seed
         if motions is None:
+            # the sampler never draws a data set's LAST sequence (randint(0, seq_num - 1), agent_handmimic.py:444): it is
+            # the held-out sequence eval_policy runs (:344).  Default data set per model: synthetic motions 1..9, of
+            # which 1..8 train and 9 evaluates.
             motions, motion_model = [], []
             for i, m in enumerate(models):
                 for s in range(1, 9):
                     motions.append(m.motion(s))
                     motion_model.append(i)
+            self.eval_motions = [[m.motion(9)] for m in models]
+        else:
+            self.eval_motions = None
         self.env = HandMimicVecEnv(models, n_envs, motions, motion_model=motion_model, env_model_id=env_model_id, device=device,
                                    seed=seed + 1000 * self.rank, auto_reset=True, random_start=True)
         self.n_envs = n_envs
         # identical initial weights on every rank (same seed), as a forked worker would inherit them
         self.policy_net, self.value_net = ppo.make_policy_value(cfg, self.env.obs_dim, self.env.act_dim, device=self.device,
                                                                 dtype=torch.float32, seed=seed)
-        self.running_state = ppo.ZFilter((self.env.obs_dim,), clip=5.0, device=self.device, dtype=torch.float32)
+        self.running_state = ppo.ZFilter((self.env.obs_dim,), clip=5.0, device=self.device)   # float64 accumulators
         self.optimizer_policy = torch.optim.Adam(self.policy_net.parameters(), lr=cfg.policy_lr, weight_decay=cfg.policy_weightdecay)
         self.optimizer_value = torch.optim.Adam(self.value_net.parameters(), lr=cfg.value_lr, weight_decay=cfg.value_weightdecay)
         self.policy_grad_clip = policy_grad_clip
@@ -67,6 +73,13 @@ class AgentHandMimic:
         self.noise_rate = 1.0
         self.epoch = 0
         self._obs = None
+        # env.end_reward of the reference (ho_im4.py:117; set per iteration in optimize_policy, agent_handmimic.py:317-319)
+        self.end_reward = 0.0
+        self._episode_reward = torch.zeros(n_envs, dtype=torch.float64, device=self.device)
+        # freq_dict of the reference (agent_handmimic.py:487-489, 523-533): per training motion the [percent, start] rows of
+        # its finished episodes, the newest `max_freq` kept
+        self.freq_dict = {k: [] for k in range(len(motions))}
+        self.max_freq = 50
 
     # ------------------------------------------------------------------ agent_handmimic.py:264-282
     def per_epoch_update(self, epoch):
@@ -87,10 +100,11 @@ class AgentHandMimic:
         env.set_mode("train")
         T = max(1, math.ceil(min_batch_size / (N * self.world)))
         batch = TrajBatch(T, N, env.obs_dim, env.act_dim, self.device)
-        stats = hdist.RolloutStats(self.device)
+        stats = hdist.RolloutStats(self.device, episode_reward=self._episode_reward)
         if self._obs is None:
             self._obs = env.reset()
         obs = self._obs
+        use_end = bool(self.cfg.end_reward) and self.end_reward != 0.0
         for t in range(T):
             x = self.running_state(obs)
             mean, log_std = self.policy_net(x)
@@ -104,13 +118,20 @@ class AgentHandMimic:
             batch.states[t] = x
             batch.actions[t] = act
             batch.exps[t] = exp
+            mid, start = env.motion_id.clone(), env.start_idx.clone()     # of the episode this step belongs to
             obs, r, done, info = env.step(act)
-            batch.rewards[t] = r
+            r = torch.nan_to_num(r, nan=0.0, posinf=0.0, neginf=0.0)      # (the library already reports a finite reward)
+            # `reward += env.end_reward` on info["end"] (agent_handmimic.py:478-480); the logger sees c_reward without it
+            batch.rewards[t] = r + self.end_reward * info["end"].to(r.dtype) if use_end else r
             batch.masks[t] = 1.0 - done.to(torch.float32)
-            stats.update(r, info["reward_info"], done)
+            stats.update(r, info["reward_info"], done, mid, start, info["percent"])
         self._obs = obs
         batch.last_state = self.running_state(obs, update=False)
         self.running_state.allreduce()
+        rows = stats.freq_rows()
+        for k, pc, st in rows:
+            self.freq_dict.setdefault(int(k), []).append([float(pc), int(st)])
+        self.freq_dict = {k: v[-self.max_freq:] for k, v in self.freq_dict.items()}
         return batch, stats
 
     # ------------------------------------------------------------------ agent_pg.py:40-56 + agent_ppo.py:16-64
@@ -141,7 +162,10 @@ class AgentHandMimic:
         torch.cuda.synchronize(self.device)
         t2 = time.perf_counter()
         log = stats.allreduce()
-        return dict(log=log, T_sample=t1 - t0, T_update=t2 - t1, T_total=t2 - t0, samples=batch.T * batch.N * self.world,
+        if self.cfg.end_reward:
+            # env.end_reward = avg_c_reward * gamma / (1 - gamma): used by the NEXT iteration's rollout (:317-319)
+            self.end_reward = log["avg_c_reward"] * self.cfg.gamma / (1.0 - self.cfg.gamma)
+        return dict(log=log, end_reward=self.end_reward, T_sample=t1 - t0, T_update=t2 - t1, T_total=t2 - t0, samples=batch.T * batch.N * self.world,
                     horizon=batch.T, **upd)
 
     # ------------------------------------------------------------------ agent_handmimic.py:339-403
@@ -154,7 +178,8 @@ class AgentHandMimic:
         import numpy as np
         mdl = self.env.models[model_index]
         if motions is None:
-            motions = [mdl.motion(1)]
+            # the held-out last sequence of the model's data set (seq_idx = seq_num - 1, agent_handmimic.py:344)
+            motions = self.eval_motions[model_index] if self.eval_motions else [mdl.motion(9)]
         n = len(motions)
         env = HandMimicVecEnv(mdl, n, motions, device=self.device.index, seed=0, auto_reset=False, random_start=False, balance=False)
         env.set_mode("test")
@@ -173,7 +198,7 @@ class AgentHandMimic:
         lens = torch.as_tensor([int(m["seq_len"]) for m in motions], device=self.device)
         obs = env.reset(motion_id=list(range(n)), start_idx=[0] * n)
         alive = torch.ones(n, dtype=torch.bool, device=self.device)
-        acc = {k: torch.zeros(n, device=self.device) for k in ("pose_err", "mpjpe", "reward", "steps")}
+        acc = {k: torch.zeros(n, device=self.device) for k in ("pose_err", "pose_steps", "mpjpe", "reward", "steps")}
         info_sum = torch.zeros(n, 9, device=self.device)
         percent = torch.zeros(n, device=self.device)
         frames = []
@@ -183,7 +208,11 @@ class AgentHandMimic:
             xpos = env.get_derived()[0]
             ti = torch.remainder(torch.full_like(lens, t), lens)
             w = alive.to(torch.float32)
-            acc["pose_err"] += w * torch.linalg.norm(gt[ar, ti, 6:] - q[:, 6:26], dim=-1)
+            # the reference's `res["gt"][6:] - res["pred"][6:]` slices the stacked [T, 26] arrays along TIME: frames 6.. of
+            # all 26 hand dofs (agent_handmimic.py:386)
+            if t >= 6:
+                acc["pose_err"] += w * torch.linalg.norm(gt[ar, ti] - q[:, :26], dim=-1)
+                acc["pose_steps"] += w
             acc["mpjpe"] += w * torch.linalg.norm(gtj[ar, ti] - xpos[:, hb], dim=-1).mean(-1)
             x = self.running_state(obs, update=False)
             act = self.policy_net(x)[0]                      # select_action(mean_action=True)
@@ -200,7 +229,7 @@ class AgentHandMimic:
         steps = acc["steps"].clamp(min=1)
         names = ("pose_reward", "wpose_reward", "jpos_reward", "vel_reward", "obj_pos_reward", "obj_rot_reward", "obj_vel_reward",
                  "obj_rfc_reward")
-        per = dict(pose_err=acc["pose_err"] / steps, mpjpe=acc["mpjpe"] / steps, avg_reward=acc["reward"] / steps,
+        per = dict(pose_err=acc["pose_err"] / acc["pose_steps"].clamp(min=1), mpjpe=acc["mpjpe"] / steps, avg_reward=acc["reward"] / steps,
                    total_reward=acc["reward"], percent=percent, **{k: info_sum[:, i] / steps for i, k in enumerate(names)})
         per = {k: v.cpu().numpy() for k, v in per.items()}
         metrics = {k: float(v.mean()) for k, v in per.items()}

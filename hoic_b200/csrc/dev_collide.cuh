@@ -25,7 +25,7 @@ __device__ __forceinline__ int plane_sphere(RawCon& c, float margin, V3 pp, V3 p
   c.dist = dist; c.n = pn; c.pos = sp - pn * (r + 0.5f * dist); c.t = v3(0, 0, 0);
   return 1;
 }
-__device__ int plane_capsule(RawCon* c, float margin, V3 pp, const M3& pm, V3 cp, const M3& cm, const float* size) {
+static __device__ int plane_capsule(RawCon* c, float margin, V3 pp, const M3& pm, V3 cp, const M3& cm, const float* size) {
   V3 pn = col(pm, 2), ax = col(cm, 2);
   int n = 0;
   n += plane_sphere(c[n], margin, pp, pn, cp + ax * size[1], size[0]);
@@ -33,7 +33,7 @@ __device__ int plane_capsule(RawCon* c, float margin, V3 pp, const M3& pm, V3 cp
   for (int i = 0; i < n; i++) c[i].t = ax;
   return n;
 }
-__device__ int plane_box(RawCon* c, float margin, V3 pp, const M3& pm, V3 bp, const M3& bm, const float* size) {
+static __device__ int plane_box(RawCon* c, float margin, V3 pp, const M3& pm, V3 bp, const M3& bm, const float* size) {
   V3 pn = col(pm, 2);
   float dist = dot(bp - pp, pn);
   int n = 0;
@@ -49,7 +49,7 @@ __device__ int plane_box(RawCon* c, float margin, V3 pp, const M3& pm, V3 bp, co
   }
   return n;
 }
-__device__ int capsule_capsule(RawCon* c, float margin, V3 p1, const M3& m1, const float* s1, V3 p2, const M3& m2, const float* s2) {
+static __device__ int capsule_capsule(RawCon* c, float margin, V3 p1, const M3& m1, const float* s1, V3 p2, const M3& m2, const float* s2) {
   V3 a1 = col(m1, 2), a2 = col(m2, 2), dif = p1 - p2;
   float ma = dot(a1, a1), mb = -dot(a1, a2), mc = dot(a2, a2), u = -dot(a1, dif), v = dot(a2, dif);
   float det = ma * mc - mb * mb, x1, x2;
@@ -80,7 +80,7 @@ __device__ int capsule_capsule(RawCon* c, float margin, V3 p1, const M3& m1, con
 }
 
 // sphere (centre p, box frame) against the solid box; normal points sphere -> box
-__device__ int sphere_box_local(RawCon& c, float margin, V3 p, float r, const float* s) {
+static __device__ int sphere_box_local(RawCon& c, float margin, V3 p, float r, const float* s) {
   V3 q = v3(fminf(fmaxf(p.x, -s[0]), s[0]), fminf(fmaxf(p.y, -s[1]), s[1]), fminf(fmaxf(p.z, -s[2]), s[2]));
   V3 d = q - p;
   float d2 = dot(d, d), dist;
@@ -108,7 +108,7 @@ __device__ int sphere_box_local(RawCon& c, float margin, V3 p, float r, const fl
 
 // capsule (geom1) vs box (geom2): exact minimiser of the segment-box distance, two contacts at the ends of the
 // portion above a face when the closest feature is a face (same construction as the oracle).
-__device__ __noinline__ int capsule_box(RawCon* c, float margin, V3 cp, const M3& cm, const float* cs, V3 bp, const M3& bm, const float* bs) {
+static __device__ __noinline__ int capsule_box(RawCon* c, float margin, V3 cp, const M3& cm, const float* cs, V3 bp, const M3& bm, const float* bs) {
   const float h = cs[1], r = cs[0];
   V3 p0 = mulTv(bm, cp - bp), a = mulTv(bm, col(cm, 2));
   float tb[8];
@@ -166,7 +166,7 @@ __device__ __noinline__ int capsule_box(RawCon* c, float margin, V3 cp, const M3
 }
 
 // box (geom1) vs box (geom2): 15-axis separating-axis test, reference/incident face clipping or edge-edge point
-__device__ __noinline__ int box_box(RawCon* c, float margin, V3 p1, const M3& R1, const float* A, V3 p2, const M3& R2, const float* B) {
+static __device__ __noinline__ int box_box(RawCon* c, float margin, V3 p1, const M3& R1, const float* A, V3 p2, const M3& R2, const float* B) {
   V3 p = p2 - p1, pp = mulTv(R1, p);
   float R[9], Q[9], s, best = -FLT_MAX;
   V3 nrm = v3(0, 0, 0);
@@ -292,7 +292,7 @@ __device__ __noinline__ int box_box(RawCon* c, float margin, V3 p1, const M3& R1
     {0.f, 0.70710678f, 0.70710678f}, {0.f, 0.70710678f, -0.70710678f}, \
     {0.57735027f, 0.57735027f, 0.57735027f}, {0.57735027f, 0.57735027f, -0.57735027f}, {0.57735027f, -0.57735027f, 0.57735027f}, \
     {0.57735027f, -0.57735027f, -0.57735027f}}
-__constant__ float c_dop[H_NDOP][3] = H_DOP_TABLE;
+static __constant__ float c_dop[H_NDOP][3] = H_DOP_TABLE;
 static const float h_dop[H_NDOP][3] = H_DOP_TABLE;   // host copy for the model build
 
 // ---------------------------------------------------------------------------------------------- MPR (libccd)
@@ -335,7 +335,7 @@ __device__ __forceinline__ MeshLane mesh_lane(const CObj& o, int lane) {
 // support, lower bound of the answer = the best projection of a few known vertices; only clusters
 // whose upper bound reaches it are scanned, lane-strided, and reduced with redux.sync.  The dot products and the tie
 // rule (lowest ORIGINAL index) are those of a serial scan over all vertices.
-__device__ __noinline__ SuppPt support_w(const CObj& o, V3 dirw, int lane, MeshLane ml) {
+static __device__ __noinline__ SuppPt support_w(const CObj& o, V3 dirw, int lane, MeshLane ml) {
   V3 d = mulTv(o.mat, dirw), l;
   if (o.type == G_CAPSULE) {
     float nn = norm(d);
@@ -402,7 +402,7 @@ __device__ __forceinline__ bool ccd_eq(float a, float b) {
   if (ab < CCDF_EPS) return true;
   return ab < CCDF_EPS * fmaxf(fabsf(a), fabsf(b));
 }
-__device__ float point_seg_dist2(V3 P, V3 x0, V3 b, V3& wit) {
+static __device__ float point_seg_dist2(V3 P, V3 x0, V3 b, V3& wit) {
   V3 d = b - x0, a = x0 - P;
   float t = -dot(a, d) / dot(d, d);
   if (t < 0.f || ccd_zero(t)) { wit = x0; V3 e = x0 - P; return dot(e, e); }
@@ -411,7 +411,7 @@ __device__ float point_seg_dist2(V3 P, V3 x0, V3 b, V3& wit) {
   V3 e = wit - P;
   return dot(e, e);
 }
-__device__ __noinline__ float point_tri_dist2(V3 P, V3 x0, V3 B, V3 C, V3& wit, bool& inside) {
+static __device__ __noinline__ float point_tri_dist2(V3 P, V3 x0, V3 B, V3 C, V3& wit, bool& inside) {
   V3 d1 = B - x0, d2 = C - x0, a = x0 - P;
   float v = dot(d1, d1), w = dot(d2, d2), p = dot(a, d1), q = dot(a, d2), r = dot(d1, d2);
   float s = (q * r - w * p) / (w * v - r * r), t = (-s * r - q) / w;
@@ -446,7 +446,7 @@ __device__ __forceinline__ void expand_portal(Supp* s, const Supp& v4) {
   else { if (dot(s[3].v, c) > 0.f) s[2] = v4; else s[1] = v4; }
 }
 // returns 0 when intersecting; all lanes run the same scalar logic (uniform), only support scans are split
-__device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, float tol, int max_iter, float& depth, V3& dir, V3& pos,
+static __device__ __noinline__ int mpr_penetration(const CObj& o1, const CObj& o2, float tol, int max_iter, float& depth, V3& dir, V3& pos,
                                int& iters, int lane, MeshLane ml2) {
   Supp s[4], v4;
   V3 d;
@@ -575,7 +575,7 @@ __device__ __forceinline__ void write_contact(float* s, int idx, const RawCon& r
 }
 
 // Fills U_CON / MI_NCON from S_GPOS / S_GMAT.  Counters: mpr calls / support iterations.
-__device__ __noinline__ void collide(float* s, const DevModel& m, int lane, unsigned& mpr_calls, unsigned& mpr_iters) {
+static __device__ __noinline__ void collide(float* s, const DevModel& m, int lane, unsigned& mpr_calls, unsigned& mpr_iters) {
   int ncon = 0, nq = 0;
   bool overflow = false;
   unsigned short* mprq = (unsigned short*)(s + U_MPRQ);   // candidate indices < H_MAXCAND = 128

@@ -11,10 +11,9 @@
 // Scratch aliases inside the union (dead before the constraint stage): per-joint local rotation / slide and per-body
 // local transform are computed lane-parallel first, so that the serial walk down the tree is one quaternion product
 // and one rotation per level.
-#define U_JQ (U_CVEL)          // 32*4: hinge rotation quaternion of each joint (slide: displacement in .w)
-#define U_DV (U_CVEL)          // 32*6: cdof * qvel            (velocity stage; U_JQ is dead by then)
-#define U_DA (U_CACC)          // 32*6: cdof_dot * qvel
-__device__ __noinline__ void pos_stage(float* s, const DevModel& m, int lane) {
+// `gpos` / `gmat`: where the geom poses go ([32][3], [32][9]); nothing in the position / velocity stage reads them back, so
+// the kernel that only produces them (k_p1) points these at the global working set instead of shared memory.
+static __device__ __noinline__ void pos_stage(float* s, const DevModel& m, int lane, float* gpos, float* gmat) {
   const float* q = s + S_QPOS;
   const int nbody = m.nbody;
   if (lane < 3) s[S_ORG + lane] = q[m.org_qadr + lane];
@@ -103,8 +102,8 @@ __device__ __noinline__ void pos_stage(float* s, const DevModel& m, int lane) {
   if (lane < m.ngeom) {
     const int gb = m.geom_body[lane];
     const M3 R = ldm(s + U_XMAT + 9 * gb);
-    st3(s + S_GPOS + 3 * lane, ld3(s + S_XPOS + 3 * gb) + mulv(R, ld3(m.geom_pos[lane])));
-    stm(s + S_GMAT + 9 * lane, mulm(R, ldm(m.geom_mat[lane])));
+    st3(gpos + 3 * lane, ld3(s + S_XPOS + 3 * gb) + mulv(R, ld3(m.geom_pos[lane])));
+    stm(gmat + 9 * lane, mulm(R, ldm(m.geom_mat[lane])));
   }
   // inertial frames, subtree CoM of each moving tree, cinert
   V3 xipos = v3(0, 0, 0);
@@ -189,7 +188,7 @@ __device__ __noinline__ void pos_stage(float* s, const DevModel& m, int lane) {
 // Bias forces by recursive Newton-Euler, written as lane-parallel sums over ancestor-dof masks instead of a serial walk:
 //   cvel_b = sum_{e in chain(b)} cdof_e qvel_e ;  cdof_dot_d = cvel(before d) x cdof_d ;  cacc_b = -g + sum cdof_dot_e qvel_e
 // (mj_comVel / mj_rne).  Needs U_CINERT from pos_stage (same substep).
-__device__ __noinline__ void vel_stage(float* s, const DevModel& m, int lane) {
+static __device__ __noinline__ void vel_stage(float* s, const DevModel& m, int lane) {
   const int b = lane;
   const int lvl = b < m.nbody ? m.body_level[b] : -1;
   const float qv = lane < m.nv ? s[S_QVEL + lane] : 0.f;
@@ -262,7 +261,7 @@ __device__ __forceinline__ float apply_ft(const float* s, const DevModel& m, int
 // ---------------------------------------------------------------------------------------------- Euler
 // mj_Euler with implicit joint damping: (M + h diag(damping)) qacc' = qfrc_smooth + qfrc_constraint.
 // Returns false on a failed factorisation.
-__device__ __noinline__ bool euler_step(float* s, const DevModel& m, int lane, unsigned long long* chol_calls) {
+static __device__ __noinline__ bool euler_step(float* s, const DevModel& m, int lane, unsigned long long* chol_calls) {
   const float h = m.timestep;
   float qa;
   const float rhs = lane < m.nv ? s[S_SMOOTH + lane] + s[S_FCON + lane] : 0.f;

@@ -25,7 +25,7 @@ __device__ __forceinline__ const float* expert_frame(const EnvCtx& e, int delta)
 }
 
 // ---- stable PD with the previous forward's M and bias.  Writes S_CTRL.
-__device__ __noinline__ bool pd_torque(float* s, const DevModel& m, int lane, const EnvCtx& e) {
+static __device__ __noinline__ bool pd_torque(float* s, const DevModel& m, int lane, const EnvCtx& e) {
   const int n = m.nhand_v;
   const float dt = m.timestep;
   const float* ref = expert_frame(e, 0) + F_DOF;
@@ -57,7 +57,7 @@ __device__ __noinline__ bool pd_torque(float* s, const DevModel& m, int lane, co
 }
 
 // ---- record_contact: add hand-object contacts of the last forward to the per-hand-geom sums (world positions)
-__device__ __noinline__ void record_contacts(float* s, const DevModel& m, int lane, float* csum) {
+static __device__ __noinline__ void record_contacts(float* s, const DevModel& m, int lane, float* csum) {
   const int ncon = ((const int*)(s + S_MISC))[MI_NCON];
   const V3 org = ld3(s + S_ORG);
   for (int c = 0; c < ncon; c++) {
@@ -79,7 +79,7 @@ __device__ __noinline__ void record_contacts(float* s, const DevModel& m, int la
 // reference, which records after sim.step(), body positions / contacts / contact forces / qacc are those of the forward
 // that produced the new state.  record_contact_frames runs before the solve (the Newton weights reuse the head of the
 // contact records), record_forward after it (U_FORCE / U_CINFO live), record_state after Euler.
-__device__ __noinline__ void record_contact_frames(const float* s, const DevModel& m, int lane, float* o) {
+static __device__ __noinline__ void record_contact_frames(const float* s, const DevModel& m, int lane, float* o) {
   const int ncon = ((const int*)(s + S_MISC))[MI_NCON];
   const V3 org = ld3(s + S_ORG);
   int n = 0;
@@ -96,7 +96,10 @@ __device__ __noinline__ void record_contact_frames(const float* s, const DevMode
   }
   if (lane == 0) o[114] = (float)(n < HOIC_REC_MAXCON ? n : HOIC_REC_MAXCON);
 }
-__device__ __noinline__ void record_forward(const float* s, const DevModel& m, int lane, float* o) {
+// `con` / `force` / `cinfo`: the U_CON / U_FORCE / U_CINFO arrays of the constraint stage that produced qacc (the pipeline's
+// kernels pass their copies in the global working set: the kernel that runs Euler does not hold the constraint stage).
+static __device__ __noinline__ void record_forward(const float* s, const DevModel& m, int lane, float* o, const float* con, const float* force,
+                                            const float* cinfo) {
   const int* misc = (const int*)(s + S_MISC);
   const V3 org = ld3(s + S_ORG);
   for (int i = lane; i < 3 * m.n_hand_body; i += 32) {
@@ -105,14 +108,14 @@ __device__ __noinline__ void record_forward(const float* s, const DevModel& m, i
   }
   if (lane < 6) o[108 + lane] = s[S_QACC + m.nv - 6 + lane];
   const int ncon = misc[MI_NCON];
-  const float* F = s + U_FORCE + H_RCON;
+  const float* F = force + H_RCON;
   int n = 0;
   for (int c = 0; c < ncon; c++) {
-    const DevCand& cd = m.cand[__float_as_int(s[U_CON + 16 * c + 13])];
+    const DevCand& cd = m.cand[__float_as_int(con[16 * c + 13])];
     if (cd.hand_slot < 0) continue;
     if (n < HOIC_REC_MAXCON && lane < 6) {
       // mj_contactForce: mju_decodePyramid of the edge forces (frictionless contacts: the single row's force)
-      const float* ci = s + U_CINFO + 8 * c;
+      const float* ci = cinfo + 8 * c;
       const int eoff = ((const int*)ci)[2], ne = ((const int*)ci)[3], k = lane;
       float f = 0.f;
       if (ne == 1) f = k == 0 ? F[eoff] : 0.f;
@@ -123,7 +126,7 @@ __device__ __noinline__ void record_forward(const float* s, const DevModel& m, i
     n++;
   }
 }
-__device__ __noinline__ void record_state(const float* s, const DevModel& m, int lane, V3 vf, V3 vt, float* o) {
+static __device__ __noinline__ void record_state(const float* s, const DevModel& m, int lane, V3 vf, V3 vt, float* o) {
   if (lane < m.nhand_q) o[63 + lane] = s[S_QPOS + lane];
   if (lane < 7) o[95 + lane] = s[S_QPOS + m.nhand_q + lane];
   if (lane < 6) {
@@ -134,7 +137,7 @@ __device__ __noinline__ void record_state(const float* s, const DevModel& m, int
 }
 
 // pytorch3d-style matrix -> axis-angle (uhc/utils/transforms.py:99-158, 414-490)
-__device__ __noinline__ V3 matrix_to_axis_angle(const M3& R) {
+static __device__ __noinline__ V3 matrix_to_axis_angle(const M3& R) {
   const float* r = R.m;
   float qa[4] = {1 + r[0] + r[4] + r[8], 1 + r[0] - r[4] - r[8], 1 - r[0] + r[4] - r[8], 1 - r[0] - r[4] + r[8]};
   float cand[4][4] = {{0, r[7] - r[5], r[2] - r[6], r[3] - r[1]}, {r[7] - r[5], 0, r[3] + r[1], r[2] + r[6]},
@@ -161,7 +164,7 @@ __device__ __noinline__ V3 matrix_to_axis_angle(const M3& R) {
 #define QP_END (QP_GV + H_NHG * 6)
 
 struct QpVar { double g[6]; };
-__device__ __noinline__ void qp_var(const float* s, int i, int ec, V3 obj_p, float sqw, float mu, QpVar& out, V3* pos_out) {
+static __device__ __noinline__ void qp_var(const float* s, int i, int ec, V3 obj_p, float sqw, float mu, QpVar& out, V3* pos_out) {
   const float dx = 0.0025f;
   const int pt = i >> 2, e = i & 3, k = pt / ec, j = pt % ec;
   const float* cf = s + QP_CF + 12 * k;
@@ -225,7 +228,7 @@ static_assert(((QP_RED + 1) & ~1) + 64 <= U_QP_END, "QP scratch exceeds the unio
 // per lane: the loops over a lane's variables are unrolled (their values live in registers), so small problems (most
 // grasps touch 2-5 hand geoms = 40-100 variables) run a 3- or 6-wide instance instead of the 12-wide one.
 template <int NPER>
-__device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T, float* rest, unsigned& qp_iters, float* surf, double sqw) {
+static __device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T, float* rest, unsigned& qp_iters, float* surf, double sqw) {
   const double eps = 1e-7, inv_eps = 1.0 / eps;
   double* red = reinterpret_cast<double*>(s + ((QP_RED + 1) & ~1));
   const double b6[6] = {F.x, F.y, F.z, sqw * T.x, sqw * T.y, sqw * T.z};
@@ -344,7 +347,7 @@ __device__ __noinline__ float rfc_qp_core(float* s, int lane, int n, V3 F, V3 T,
 
 // Standalone wrench QP on caller-supplied contacts (PhysMetrics.solve_force, scripts/metrics.py:156-196, and the QP of
 // solve_rfc with explicit inputs): contact frames in QP_CF, weights in QP_TS, optional penalties c (NULL = 0).
-__device__ __noinline__ float wrench_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 center, float mu, float sqw, const float* pen,
+static __device__ __noinline__ float wrench_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 center, float mu, float sqw, const float* pen,
                                         float* rest, unsigned& qp_iters, float* surf) {
   const int n = 4 * ec * ncg;
   for (int i = lane; i < n; i += 32) {
@@ -369,7 +372,7 @@ __device__ __noinline__ float wrench_qp(float* s, int lane, int ncg, int ec, V3 
 }
 
 // returns rfc_score; fills rest[6]
-__device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,
+static __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, V3 T, V3 obj_p, V3 obj_v, V3 obj_w, const float* gpos_now,
                         V3 org_now, float* rest, unsigned& qp_iters, float* surf) {
   const double sqw = 100.0;
   const int n = 4 * ec * ncg;
@@ -414,7 +417,7 @@ __device__ __noinline__ float rfc_qp(float* s, int lane, int ncg, int ec, V3 F, 
 __device__ __forceinline__ void put_rot2(float* o, const M3& R) {
   o[0] = R.m[0]; o[1] = R.m[1]; o[2] = R.m[3]; o[3] = R.m[4]; o[4] = R.m[6]; o[5] = R.m[7];
 }
-__device__ __noinline__ void write_obs(const float* s, const DevModel& m, int lane, const EnvCtx& e, float* obs) {
+static __device__ __noinline__ void write_obs(const float* s, const DevModel& m, int lane, const EnvCtx& e, float* obs) {
   const float* qpos = s + S_QPOS;
   const float* qvel = s + S_QVEL;
   const V3 org = ld3(s + S_ORG);
@@ -486,7 +489,7 @@ __device__ __noinline__ void write_obs(const float* s, const DevModel& m, int la
 }
 
 // ---- calc_ho_diff + reward 9.  Returns body_fail; reward / info written by lane 0.
-__device__ __noinline__ bool diff_and_reward(const float* s, const DevModel& m, int lane, const EnvCtx& e, const float* rw, float rfc_score,
+static __device__ __noinline__ bool diff_and_reward(const float* s, const DevModel& m, int lane, const EnvCtx& e, const float* rw, float rfc_score,
                                 float* reward, float* info9) {
   const float* f = expert_frame(e, 0);
   const float* qpos = s + S_QPOS;

@@ -169,7 +169,7 @@ __device__ __forceinline__ float rsqrt_nr(float x) {
   float y = rsqrtf(x);
   return y * fmaf(-0.5f * x * y, y, 1.5f);   // one Newton step on the MUFU estimate
 }
-__device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int lane) {
+static __device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int lane) {
   // Branch-free on purpose: lanes outside the active part of a panel read clamped (valid, irrelevant) addresses and
   // only their stores are predicated, so the warp never diverges and nothing waits on a reconvergence barrier.
   const int I = lane >> 2, r = lane & 3;
@@ -258,10 +258,14 @@ __device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xout, int
 // Scratch (in S_H): scaled rows L[k][d] = M'[k, a_k(d)] / D_k, pivots D, published solution entries, trunk block.
 #define T_MAXD 10
 #define T_HUBD 5     // depth of the hub dof when there is one (compile-time so that the block step is emitted once)
+#if H_KERNEL == HK_P1
+#define TS_LS (S_UNION + UN_TS)     // k_p1 holds no Hessian: the factor scratch follows the branch products in the union
+#else
 #define TS_LS (S_H)                 // 32 x MS_STRIDE scaled rows
+#endif
 #define TS_D (TS_LS + 32 * MS_STRIDE)
 #define TS_X (TS_D + 32)
-#define TS_T (TS_X + 32)            // 21 trunk-block sums (TS_T + 21 <= S_H + H_FLOATS)
+#define TS_T (TS_X + 32)            // 21 trunk-block sums (TS_T + 21 <= TS_LS + 480)
 #define TS_P (S_UNION)              // 32 x 21 products of the branch dofs (default scratch: callers run while the union region is free)
 __device__ __forceinline__ float rcp_nr(float x) {
   const float y = 1.0f / x;
@@ -278,7 +282,7 @@ __device__ __forceinline__ void ld_row12(float (&r)[12], const float* p) {
 }
 // `rows` = row storage to factorise (S_MS layout; may alias TS_LS: every lane reads only its own row before anything is
 // written), `tsp` = 32 x 21 floats of scratch for the hub block.
-__device__ __noinline__ bool tree_solve_at(float* s, const DevModel& m, int lane, const float* rows, float* tsp, float diag_add, float b,
+static __device__ __noinline__ bool tree_solve_at(float* s, const DevModel& m, int lane, const float* rows, float* tsp, float diag_add, float b,
                                            float* xout) {
   const int dep = lane < m.nv ? m.dof_depth[lane] : -1;
   const int hd = m.hub_depth, maxd = m.tree_maxdepth;

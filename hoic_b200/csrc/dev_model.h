@@ -16,6 +16,11 @@
 #ifndef H_NEDGE
 #define H_NEDGE 96     // pyramid edge rows per env
 #endif
+// capacities of the GLOBAL working set (BatchDev.scratch): what k_p2 produces.  A kernel compiled with smaller H_NCON /
+// H_NBASIS / H_NEDGE (k_p3's small tier) holds a smaller constraint stage in shared memory and only takes envs that fit.
+#define HG_NCON 24
+#define HG_NBASIS 56
+#define HG_NEDGE 96
 #define H_RFR 0        // row index ranges: friction-loss rows [0,32)
 #define H_RLIM 32      //                   joint-limit rows   [32,64)
 #define H_RCON 64      //                   contact edge rows  [64,64+H_NEDGE)
@@ -92,41 +97,129 @@ struct DevModel {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// per-environment shared-memory layout (float offsets).  Persistent part survives a substep boundary (the env logic
-// reads the PREVIOUS forward's M / bias / cdof / poses: SURVEY.md S1); the union part is reused inside a substep.
-#define S_QPOS 0
-#define S_QVEL (S_QPOS + H_NQ)
-#define S_WARM (S_QVEL + HN)
-#define S_QACC (S_WARM + HN)
-#define S_CTRL (S_QACC + HN)
-#define S_QAPP (S_CTRL + HN)
-#define S_ACT (S_QAPP + HN)
-#define S_ORG (S_ACT + HN)             // 4
-#define S_XPOS (S_ORG + 4)             // 32*3, relative to S_ORG
-#define S_XQUAT (S_XPOS + 96)          // 32*4
-#define S_GPOS (S_XQUAT + 128)         // 32*3
-#define S_GMAT (S_GPOS + 96)           // 32*9
-#define S_COM (S_GMAT + 288)           // 4 roots * 3 -> 12
-#define S_CDOF (S_COM + 12)            // 32*6
-#define S_BIAS (S_CDOF + 192)
-#define S_SMOOTH (S_BIAS + HN)         // qfrc_smooth
-#define S_ASMOOTH (S_SMOOTH + HN)      // qacc_smooth
-#define S_MA (S_ASMOOTH + HN)
-#define S_MV (S_MA + HN)
-#define S_GRAD (S_MV + HN)
-#define S_SEARCH (S_GRAD + HN)
-#define S_TMP (S_SEARCH + HN)          // 32
-#define S_FCON (S_TMP + HN)            // qfrc_constraint
-#define S_MISC (S_FCON + HN)           // 16 scalars: ncon, nlim, nbasis, nedge, flags, ...
+// Per-environment working-set layout (float offsets).  One table describes every field once; each kernel of the step
+// pipeline (k_p1 / k_p2 / k_p3 / k_tail, see hoic_step.cuh) is compiled in its own translation unit with H_KERNEL set to
+// its bit, and gets a COMPACT shared-memory layout holding only the fields it touches (offsets S_*: a constexpr prefix
+// sum over the fields whose `use` mask contains the kernel).  Between kernels the working set lives in global memory
+// (BatchDev.scratch, L2-resident) in the FULL layout (offsets G_*).  The single-warp kernels of hoic_capi.cu (reset,
+// debug entries, preprocessing, standalone QP) use the full layout in shared memory as well.
+// "Persistent" fields survive a substep boundary (the env logic reads the PREVIOUS forward's M / bias / cdof / poses:
+// SURVEY.md S1); the union region at the end is reused inside a substep.
+#define HK_P1 1u        // Euler of the previous substep, stable PD, J^T wrenches, position + velocity stage, qacc_smooth
+#define HK_P2 2u        // collision, contact recording, constraint rows
+#define HK_P3 4u        // Newton solve
+#define HK_TAIL 8u      // last Euler, averages, residual-force QP, termination, reward, observation
+#define HK_FULL 0xffu
+#ifndef H_KERNEL
+#define H_KERNEL HK_FULL
+#endif
 #define MS_STRIDE 12                   // row stride of S_MS (16-byte aligned rows; entries beyond the depth stay zero)
-#define S_MS (S_MISC + 16)             // 32*12: M by (dof, ancestor depth): entry d of row i = M[i, ancestor of i at depth d]
-#define S_H (S_MS + 384)               // 576: lower triangle of the Newton Hessian / its Cholesky factor in 4x4 blocks
-                                       //      (dev_math.cuh: warp_chol_solve); scratch of tree_solve outside the Newton iterations
+#define B_STRIDE 17                    // a contact Jacobian row touches <= 16 dofs (one hand chain + the object, or two
+                                       // finger chains): columns are stored compacted in dof order, see build_rows
+// sizes of the three users of the union region (floats)
+#define UN_POS (288 + 96 + 96 + 320 + 320)                                             /* position / velocity stage */
+#define UN_CON_OF(nc, nb, ne) ((nc) * 16 + (nb) * B_STRIDE + 6 * (H_RCON + (ne)) + 2 * (nb) + (nc) * 8 + (H_MAXCAND / 2 > (nb) ? H_MAXCAND / 2 : (nb)))
+#define UN_CON UN_CON_OF(H_NCON, H_NBASIS, H_NEDGE)
+#define UN_CON_G UN_CON_OF(HG_NCON, HG_NBASIS, HG_NEDGE)
+#define UN_QP (3168 - 384 - 576)       /* residual-force QP scratch starts at S_MS (QP_BASE) and runs over S_H into the union */
+#define UN_TS (32 * 21)                /* tree_solve's branch products (dev_math.cuh: TS_P) */
+#define UN_TSF 480                     /* tree_solve's factor scratch (TS_LS .. TS_T) when it lives in the union (k_p1) */
+#define S_MAX2(a, b) ((a) > (b) ? (a) : (b))
+#define UN_SIZE ((H_KERNEL) == HK_P1 ? S_MAX2(UN_POS, UN_TS + UN_TSF) : ((H_KERNEL) == HK_P2 || (H_KERNEL) == HK_P3) ? UN_CON : \
+                 (H_KERNEL) == HK_TAIL ? S_MAX2(UN_QP, UN_TS) : S_MAX2(S_MAX2(UN_POS, UN_CON), S_MAX2(UN_QP, UN_TS)))
+#define UN_FULL S_MAX2(S_MAX2(UN_POS, UN_CON_G), S_MAX2(UN_QP, UN_TS))
+
+#define H_FIELDS(X)                                                                                                      \
+  X(QPOS, H_NQ, HK_P1 | HK_P2 | HK_TAIL)                                                                                   \
+  X(QVEL, HN, HK_P1 | HK_P2 | HK_TAIL)                                                                                     \
+  X(WARM, HN, HK_P1 | HK_P3 | HK_TAIL)                                                                                     \
+  X(QACC, HN, HK_P1 | HK_P3 | HK_TAIL)                                                                                     \
+  X(CTRL, HN, HK_P1)                                                                                                       \
+  X(QAPP, HN, HK_P1)                                                                                                       \
+  X(ACT, HN, HK_P1)                                                                                                        \
+  X(ORG, 4, HK_P1 | HK_P2 | HK_TAIL)                  /* hand-root translation the stored positions are relative to */     \
+  X(XPOS, 96, HK_P1 | HK_TAIL)                                                                                             \
+  X(XQUAT, 128, HK_P1 | HK_TAIL)                                                                                           \
+  X(GPOS, 96, HK_P2 | HK_TAIL)                                                                                             \
+  X(GMAT, 288, HK_P2 | HK_TAIL)                                                                                            \
+  X(COM, 12, HK_P1 | HK_P2)                           /* 4 roots * 3 */                                                    \
+  X(CDOF, 192, HK_P1 | HK_P2)                                                                                              \
+  X(BIAS, HN, HK_P1)                                                                                                       \
+  X(SMOOTH, HN, HK_P1 | HK_P3 | HK_TAIL)              /* qfrc_smooth */                                                    \
+  X(ASMOOTH, HN, HK_P1 | HK_P3)                       /* qacc_smooth */                                                    \
+  X(MA, HN, HK_P3)                                                                                                         \
+  X(MV, HN, HK_P3)                                                                                                         \
+  X(GRAD, HN, HK_P3)                                                                                                       \
+  X(SEARCH, HN, HK_P3)                                                                                                     \
+  X(FCON, HN, HK_P1 | HK_P3 | HK_TAIL)                /* qfrc_constraint */                                                \
+  X(MISC, 32, HK_FULL)                                /* int scalars: counts, flags, per-step counters (MI_*) */           \
+  X(MS, 384, HK_P1 | HK_P3 | HK_TAIL)                 /* M by (dof, ancestor depth): entry d of row i = M[i, anc_d(i)] */   \
+  X(H, 576, HK_P3 | HK_TAIL)                          /* Newton Hessian / Cholesky factor in 4x4 blocks; tree_solve scratch */ \
+  X(UNION, UN_SIZE, HK_FULL)
+
+enum {
+#define X(name, size, use) FI_##name,
+  H_FIELDS(X)
+#undef X
+  FI_COUNT
+};
+struct HField { int size; unsigned use; };
+#define H_POISON (1 << 24)     // offset of a field the kernel's layout does not hold: any access faults
+__host__ __device__ constexpr int h_field_off(int f, unsigned kernel, int union_size) {
+  const HField tab[FI_COUNT] = {
+#define X(name, size, use) {FI_##name == FI_UNION ? union_size : (size), (use)},
+      H_FIELDS(X)
+#undef X
+  };
+  int o = 0;
+  for (int i = 0; i < f && i < FI_COUNT; i++)
+    if (tab[i].use & kernel) o += tab[i].size;
+  if (f < FI_COUNT && !(tab[f].use & kernel)) return H_POISON;
+  return o;
+}
+__host__ __device__ constexpr int h_field_size(int f) {
+  const HField tab[FI_COUNT] = {
+#define X(name, size, use) {(size), (use)},
+      H_FIELDS(X)
+#undef X
+  };
+  return tab[f].size;
+}
+#define S_OFF(name) h_field_off(FI_##name, H_KERNEL, UN_SIZE)
+#define G_OFF(name) h_field_off(FI_##name, HK_FULL, UN_FULL)
+#define F_SIZE(name) h_field_size(FI_##name)
+#define S_TOTAL ((h_field_off(FI_COUNT, H_KERNEL, UN_SIZE) + 3) & ~3)
+#define G_TOTAL ((h_field_off(FI_COUNT, HK_FULL, UN_FULL) + 3) & ~3)
+
+#define S_QPOS S_OFF(QPOS)
+#define S_QVEL S_OFF(QVEL)
+#define S_WARM S_OFF(WARM)
+#define S_QACC S_OFF(QACC)
+#define S_CTRL S_OFF(CTRL)
+#define S_QAPP S_OFF(QAPP)
+#define S_ACT S_OFF(ACT)
+#define S_ORG S_OFF(ORG)
+#define S_XPOS S_OFF(XPOS)             // 32*3, relative to S_ORG
+#define S_XQUAT S_OFF(XQUAT)           // 32*4
+#define S_GPOS S_OFF(GPOS)             // 32*3
+#define S_GMAT S_OFF(GMAT)             // 32*9
+#define S_COM S_OFF(COM)
+#define S_CDOF S_OFF(CDOF)             // 32*6
+#define S_BIAS S_OFF(BIAS)
+#define S_SMOOTH S_OFF(SMOOTH)
+#define S_ASMOOTH S_OFF(ASMOOTH)
+#define S_MA S_OFF(MA)
+#define S_MV S_OFF(MV)
+#define S_GRAD S_OFF(GRAD)
+#define S_SEARCH S_OFF(SEARCH)
+#define S_FCON S_OFF(FCON)
+#define S_MISC S_OFF(MISC)
+#define S_MS S_OFF(MS)
+#define S_H S_OFF(H)
 // S_MS and S_H sit right below the union: both are dead after the last substep, so the residual-force QP of the step
-// tail starts its scratch at S_MS (QP_BASE) and the union only has to hold the position and constraint stages.
-// The per-hand-geom contact sums of record_contact (19 x 12 + counts) live in global memory (BatchDev.csum): they are
-// touched once per recorded contact, and every float of shared memory per env counts towards the warps an SM can hold.
-#define S_UNION (S_H + 576)
+// tail starts its scratch at S_MS (QP_BASE) and the union only has to hold what the kernel's own stages need.
+// The per-hand-geom contact sums of record_contact (19 x 12 + counts) live in global memory (BatchDev.csum).
+#define S_UNION S_OFF(UNION)
 #define QP_BASE S_MS
 #define CSUM_STRIDE 272                // global: 19*12 contact sums (240) + 32 counts
 // position / velocity stage temporaries
@@ -135,31 +228,44 @@ struct DevModel {
 #define U_XANCH (U_XAXIS + 96)
 #define U_CINERT (U_XANCH + 96)        // 32*10
 #define U_CRB (U_CINERT + 320)
-#define U_CDOFDOT (U_CRB + 320)        // 32*6
-#define U_CVEL (U_CDOFDOT + 192)
-#define U_CACC (U_CVEL + 192)
-#define U_CFRC (U_CACC + 192)
-#define U_POS_END (U_CFRC + 192)
-// constraint stage (aliases the above; built after the velocity stage)
-#define U_CON (S_UNION)                // H_NCON * 16: pos3 frame9 dist cand(int) 2 pad
-#define B_STRIDE 17                    // a contact Jacobian row touches <= 16 dofs (one hand chain + the object, or two
-                                       // finger chains): columns are stored compacted in dof order, see build_rows
-#define U_B (U_CON + H_NCON * 16)      // H_NBASIS * B_STRIDE basis rows
-#define U_AREF (U_B + H_NBASIS * B_STRIDE)   // H_NROW each:
-#define U_D (U_AREF + H_NROW)
-#define U_JAR (U_D + H_NROW)
-#define U_JV (U_JAR + H_NROW)
-#define U_FORCE (U_JV + H_NROW)
-#define U_RINFO (U_FORCE + H_NROW)     // int per row: limit rows dof | sign<<8 ; edge rows contact | edge<<8
-#define U_BV (U_RINFO + H_NROW)        // H_NBASIS: basis . v products
-#define U_BMASK (U_BV + H_NBASIS)      // H_NBASIS: dof mask of each basis row (bit i: dof i has a column)
-#define U_CINFO (U_BMASK + H_NBASIS)      // H_NCON * 8: basis offset, nbasis, edge offset, nedge, mu0, mu1, D, pad
-#define U_MPRQ (U_CINFO + H_NCON * 8)  // H_MAXCAND 16-bit indices: queued MPR candidates (later H_NBASIS ints: U_BINFO)
-#define U_CON_END (U_MPRQ + (H_MAXCAND / 2 > H_NBASIS ? H_MAXCAND / 2 : H_NBASIS))
+#define U_POS_END (U_CRB + 320)
+// velocity-stage temporaries lie over position-stage ones that are dead by then (U_XMAT / U_XAXIS / U_XANCH, U_CRB)
+#define U_DV (U_XMAT)                  // 32*6: cdof * qvel
+#define U_DA (U_XMAT + 192)            // 32*6: cdof_dot * qvel
+#define U_CFRC (U_CRB)                 // 32*6
+#define U_JQ (U_CRB)                   // 32*4: hinge rotation quaternion of each joint (first half of pos_stage only)
+// constraint stage (aliases the above; built after the velocity stage); offsets relative to the union start
+#define UL_CON(nc, nb, ne) 0                                     // nc * 16: pos3 frame9 dist cand(int) 2 pad
+#define UL_B(nc, nb, ne) ((nc) * 16)                             // nb * B_STRIDE basis rows
+#define UL_AREF(nc, nb, ne) (UL_B(nc, nb, ne) + (nb) * B_STRIDE) // (H_RCON + ne) each:
+#define UL_D(nc, nb, ne) (UL_AREF(nc, nb, ne) + H_RCON + (ne))
+#define UL_JAR(nc, nb, ne) (UL_D(nc, nb, ne) + H_RCON + (ne))
+#define UL_JV(nc, nb, ne) (UL_JAR(nc, nb, ne) + H_RCON + (ne))
+#define UL_FORCE(nc, nb, ne) (UL_JV(nc, nb, ne) + H_RCON + (ne))
+#define UL_RINFO(nc, nb, ne) (UL_FORCE(nc, nb, ne) + H_RCON + (ne))   // int per row: limit rows dof | sign<<8 ; edge rows contact | edge<<8
+#define UL_BV(nc, nb, ne) (UL_RINFO(nc, nb, ne) + H_RCON + (ne))  // nb: basis . v products
+#define UL_BMASK(nc, nb, ne) (UL_BV(nc, nb, ne) + (nb))          // nb: dof mask of each basis row (bit i: dof i has a column)
+#define UL_CINFO(nc, nb, ne) (UL_BMASK(nc, nb, ne) + (nb))       // nc * 8: basis offset, nbasis, edge offset, nedge, mu0, mu1, D, pad
+#define UL_MPRQ(nc, nb, ne) (UL_CINFO(nc, nb, ne) + (nc) * 8)    // H_MAXCAND 16-bit indices: queued MPR candidates (later nb ints: U_BINFO)
+#define U_S(f) (S_UNION + UL_##f(H_NCON, H_NBASIS, H_NEDGE))     // in this kernel's shared memory
+#define U_G(f) (G_OFF(UNION) + UL_##f(HG_NCON, HG_NBASIS, HG_NEDGE))   // in the global working set
+#define U_CON U_S(CON)
+#define U_B U_S(B)
+#define U_AREF U_S(AREF)
+#define U_D U_S(D)
+#define U_JAR U_S(JAR)
+#define U_JV U_S(JV)
+#define U_FORCE U_S(FORCE)
+#define U_RINFO U_S(RINFO)
+#define U_BV U_S(BV)
+#define U_BMASK U_S(BMASK)
+#define U_CINFO U_S(CINFO)
+#define U_MPRQ U_S(MPRQ)
+#define U_CON_END (S_UNION + UN_CON)
 #define U_QP_END (QP_BASE + 3168)      // residual-force QP scratch (dev_env.cuh: QP_*; static_assert there)
-#define U_TS_END (S_UNION + 32 * 21)   // tree_solve's branch products (dev_math.cuh: TS_P)
-#define S_MAX2(a, b) ((a) > (b) ? (a) : (b))
-#define S_TOTAL ((S_MAX2(S_MAX2(U_CON_END, U_POS_END), S_MAX2(U_QP_END, U_TS_END)) + 3) & ~3)
+#define U_TS_END (S_UNION + UN_TS)
+static_assert(UN_POS == 1120 && (UN_CON % 4) == 0 && (H_NBASIS * B_STRIDE) % 4 == 0 && H_NROW % 4 == 0 && H_NCON % 4 == 0 &&
+              H_NBASIS % 4 == 0 && H_NCON <= HG_NCON && H_NBASIS <= HG_NBASIS && H_NEDGE <= HG_NEDGE, "union sub-layouts");
 
 // misc slots
 #define MI_NCON 0
@@ -168,6 +274,19 @@ struct DevModel {
 #define MI_NEDGE 3
 #define MI_FLAGS 4      // bit0 physics failure (NaN / huge), bit1 capacity overflow
 #define MI_ITER 5
+// per-env counters of the running step (summed into hoic_counters by the step tail)
+#define MI_C_SUBSTEPS 8
+#define MI_C_NCON 9
+#define MI_C_NEFC 10
+#define MI_C_NEWTON 11
+#define MI_C_LS 12
+#define MI_C_MPRCALLS 13
+#define MI_C_MPRITERS 14
+#define MI_C_MAXNCON 15
+#define MI_C_MAXNBASIS 16
+#define MI_C_MAXNEDGE 17
+#define MI_C_FAILPHYS 18
+#define MI_C_FAILOVER 19
 
 // per-env persistent state in global memory (floats), AoS so that a warp reads it coalesced
 #define ST_QPOS 0

@@ -7,8 +7,8 @@
 #include "dev_math.cuh"
 
 #ifdef H_STATS
-__device__ unsigned long long g_stats[8];
-__device__ unsigned long long g_nst[64];   // [0..7] solves by iteration count, [8..15] their cycles, [16..] cycles by part
+static __device__ unsigned long long g_stats[8];
+static __device__ unsigned long long g_nst[64];   // [0..7] solves by iteration count, [8..15] their cycles, [16..] cycles by part
 #define NST_T(i) do { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_nst[16 + (i)], (unsigned long long)(t_ - nst_t)); nst_t = t_; } while (0)
 #else
 #define NST_T(i) do { } while (0)
@@ -17,7 +17,7 @@ __device__ unsigned long long g_nst[64];   // [0..7] solves by iteration count, 
 #define U_CW (U_CON)       // per-contact Hessian weights reuse the contact records' slots 14..15 + CINFO pad
 
 // general power-law sigmoid of mj_makeImpedance; out of line: powf is large and the models here all use power 2
-__device__ __noinline__ float impedance_pow(float x, float s3, float s4) {
+static __device__ __noinline__ float impedance_pow(float x, float s3, float s4) {
   if (x <= s3) return powf(x, s4) / powf(s3, s4 - 1.f);
   return 1.f - powf(1.f - x, s4) / powf(1.f - s3, s4 - 1.f);
 }
@@ -45,7 +45,7 @@ __device__ __forceinline__ void kb_from_solref(const float* sr, const float* si,
 }
 
 // Builds all rows from the contacts in U_CON and the current qpos / qvel.  Sets MI_NLIM / MI_NBASIS / MI_NEDGE.
-__device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
+static __device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
   int* misc = (int*)(s + S_MISC);
   int* rinfo = (int*)(s + U_RINFO);
   int* binfo = (int*)(s + U_BINFO);
@@ -171,7 +171,7 @@ __device__ __noinline__ void build_rows(float* s, const DevModel& m, int lane) {
 
 // ---- row-wise products ----------------------------------------------------------------------------------------
 // out[r] = (J v)[r] for all rows; v in shared (32 floats).  Uses U_BV as scratch.
-__device__ __noinline__ void mul_J(float* s, int lane, int nbasis, int nedge, const float* v, float* out) {
+static __device__ __noinline__ void mul_J(float* s, int lane, int nbasis, int nedge, const float* v, float* out) {
   const int* rinfo = (const int*)(s + U_RINFO);
 #pragma unroll 1
   for (int a = lane; a < nbasis; a += 32) {
@@ -229,7 +229,7 @@ __device__ __forceinline__ void row_eval(const float* s, const DevModel& m, int 
 }
 
 // constraint cost at jar (shared array), optionally writing forces; all lanes get the total
-__device__ __noinline__ float rows_update(float* s, const DevModel& m, int lane, int nedge, const float* jar, bool write) {
+static __device__ __noinline__ float rows_update(float* s, const DevModel& m, int lane, int nedge, const float* jar, bool write) {
   float cost = 0.f;
   const int nrow = H_RCON + nedge;
 #pragma unroll 1
@@ -248,7 +248,7 @@ __device__ __noinline__ float rows_update(float* s, const DevModel& m, int lane,
 // descendant per level inside the lane's chain, and for the trunk (hub) dofs the sum over all branch dofs by warp sums.
 // The helpers of the Newton iteration below use rolled loops (code bytes cost instruction fetches, profiles/README.md);
 // mul_M is the exception: its unrolled form measured 4 % faster on the whole step than a rolled one.
-__device__ __noinline__ float mul_M(const float* s, const DevModel& m, int lane, const float* v) {
+static __device__ __noinline__ float mul_M(const float* s, const DevModel& m, int lane, const float* v) {
   const bool on = lane < m.nv;
   const int dep = on ? m.dof_depth[lane] : 0;
   const bool trunk = on && m.dof_is_trunk[lane];
@@ -284,7 +284,7 @@ __device__ __noinline__ float mul_M(const float* s, const DevModel& m, int lane,
 
 // gradient: grad = Ma - qfrc_smooth - J^T f (forces from the last rows_update).  Writes S_GRAD and S_FCON = J^T f,
 // and the per-basis-row force coefficients in U_BV.  Returns |grad|^2 (all lanes).
-__device__ __noinline__ float newton_gradient(float* s, const DevModel& m, int lane, int nlim, int nbasis) {
+static __device__ __noinline__ float newton_gradient(float* s, const DevModel& m, int lane, int nlim, int nbasis) {
   const int* rinfo = (const int*)(s + U_RINFO);
   const int* binfo = (const int*)(s + U_BINFO);
   (void)m;
@@ -323,7 +323,7 @@ __device__ __noinline__ float newton_gradient(float* s, const DevModel& m, int l
 
 // Per-contact Hessian weights of the currently quadratic edge rows (written over contact record slots 0..6) and the
 // diagonal contribution of the friction-loss / limit rows (returned, lane = dof).
-__device__ __noinline__ float newton_weights(float* s, const DevModel& m, int lane, int nlim, int ncon) {
+static __device__ __noinline__ float newton_weights(float* s, const DevModel& m, int lane, int nlim, int ncon) {
   const int* rinfo = (const int*)(s + U_RINFO);
   const float* jar = s + U_JAR;
 #pragma unroll 1
@@ -363,7 +363,7 @@ __device__ __noinline__ float newton_weights(float* s, const DevModel& m, int la
 
 // Newton direction: H = M + J^T D_active J assembled in shared memory (lane i owns row i, columns j <= i, blocked
 // layout of warp_chol_solve), Cholesky, search = -H^-1 grad.  All loops are rolled: see warp_chol_solve.
-__device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int lane, int ncon, float diag) {
+static __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int lane, int ncon, float diag) {
   float* A = s + S_H;
 #ifdef H_STATS
   long long nst_t = clock64();
@@ -427,7 +427,7 @@ __device__ __noinline__ bool newton_direction(float* s, const DevModel& m, int l
 }
 
 // derivative and curvature of the total cost along the search direction at step alpha
-__device__ __noinline__ void ls_eval(const float* s, const DevModel& m, int lane, int nedge, float alpha, float qg1,
+static __device__ __noinline__ void ls_eval(const float* s, const DevModel& m, int lane, int nedge, float alpha, float qg1,
                                         float qg2, float& d1, float& d2) {
   float a1 = 0.f, a2 = 0.f;
   const int nrow = H_RCON + nedge;
@@ -444,7 +444,7 @@ __device__ __noinline__ void ls_eval(const float* s, const DevModel& m, int lane
 }
 
 // exact minimiser of the piecewise-quadratic cost along `search` by safeguarded Newton on its derivative
-__device__ __noinline__ float line_search(float* s, const DevModel& m, int lane, int nbasis, int nedge, unsigned& evals) {
+static __device__ __noinline__ float line_search(float* s, const DevModel& m, int lane, int nbasis, int nedge, unsigned& evals) {
   const float sv = s[S_SEARCH + lane];
   const float mv = mul_M(s, m, lane, s + S_SEARCH);
   s[S_MV + lane] = mv;
@@ -478,7 +478,7 @@ __device__ __noinline__ float line_search(float* s, const DevModel& m, int lane,
 // ---- mj_fwdConstraint with the Newton solver, split into sub-phases that every warp of a CTA runs in lockstep.
 // Inputs: S_SMOOTH, S_ASMOOTH, S_WARM, rows.  Outputs: S_QACC, S_FCON.
 // warm start selection and initial cost; leaves S_QACC, S_MA, U_JAR, U_FORCE consistent
-__device__ __noinline__ float newton_init(float* s, const DevModel& m, int lane, int nbasis, int nedge) {
+static __device__ __noinline__ float newton_init(float* s, const DevModel& m, int lane, int nbasis, int nedge) {
   const float asm_ = s[S_ASMOOTH + lane], fsm = s[S_SMOOTH + lane];
   float qacc = s[S_WARM + lane];
   s[S_QACC + lane] = qacc;
@@ -506,7 +506,7 @@ __device__ __noinline__ float newton_init(float* s, const DevModel& m, int lane,
 
 // line search along S_SEARCH, move, new cost.  Returns 0: zero step (nothing moved), 1: moved and some row changed
 // state (active set / friction branch), 2: moved and no row changed state.
-__device__ __noinline__ int newton_move(float* s, const DevModel& m, int lane, int nbasis, int nedge, float& cost, unsigned& ls_evals) {
+static __device__ __noinline__ int newton_move(float* s, const DevModel& m, int lane, int nbasis, int nedge, float& cost, unsigned& ls_evals) {
   const float alpha = line_search(s, m, lane, nbasis, nedge, ls_evals);
   if (alpha == 0.f) return 0;
   const float qacc = s[S_QACC + lane] + alpha * s[S_SEARCH + lane];

@@ -1,6 +1,6 @@
-// hoic_capi.cu -- kernels and the C ABI of libhoic_b200.so (include/hoic.h).
-// One warp per environment, one 32-thread CTA per warp: an env's whole step (15 substeps of control + physics, the
-// residual-force QP, termination, reward and observation) runs in one kernel with its working set in shared memory.
+// hoic_capi.cu -- the C ABI of libhoic_b200.so (include/hoic.h) and its single-warp kernels (reset, state access, the
+// single-mj_step parity entries, dataset preprocessing, standalone wrench QP).  env.step itself is the kernel pipeline
+// of hoic_step.cuh (k_p1.cu / k_p2.cu / k_p3.cu / k_tail.cu), one warp per environment throughout.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -12,385 +12,25 @@
 
 #include "../../include/hoic.h"
 #include "../../include/hoic_blob.h"
-#include "dev_collide.cuh"
-#include "dev_dynamics.cuh"
-#include "dev_env.cuh"
-#include "dev_model.h"
-#include "dev_solver.cuh"
+#include "dev_batch.cuh"
+#include "hoic_step.h"
 
 // ================================================================================================ device side
 
-struct BatchDev {
-  int n_envs;
-  const DevModel* const* env_model;   // [N]
-  float* state;                       // [N][ST_STRIDE]
-  float* old_geom;                    // [N][HN*12 + 4] geom poses (+origin) of the forward that preceded the step
-  const float* frames;                // all motions
-  const int* motion_offset;
-  const int* motion_len;
-  int n_motions;
-  const float* reward_w;              // [24]
-  int mode_train;
-  unsigned long long* counters;       // hoic_counters as 12 x u64
-  const int* perm;                    // optional env order (load balancing), NULL = identity
-  int model_smem;                     // bytes of shared memory behind the env regions that k_step may stage a model into
-  float* csum;                        // [N][CSUM_STRIDE] per-hand-geom contact sums / counts of the step (record_contact)
-  float* rec_frames;                  // test-mode recording (hoic_set_record), NULL = off
-  float* rec_surface;
-};
-
-struct StepOut {
-  float* obs; float* reward; float* info; uint8_t* done; uint8_t* fail; uint8_t* end; float* percent;
-};
-
-struct Cnt { unsigned substeps, ncon, nefc, newton, ls, mpr_calls, mpr_iters, qp, fail_phys, fail_over, max_ncon, max_nbasis, max_nedge; };
-
-__device__ __forceinline__ bool bad(float v) { return !(fabsf(v) <= F_MAXVAL); }
-
-// Phases of one substep.  Kept as separate noinline calls so that every warp of a CTA runs the same (large) piece of
-// code between two CTA barriers: the step kernel is instruction-fetch bound otherwise (profiles/r01_v1_*).
-__device__ __noinline__ bool phase_forward(float* s, const DevModel& m, int lane) {
-  int* misc = (int*)(s + S_MISC);
-  const bool fail = __any_sync(FULLMASK, bad(s[S_QPOS + lane]) || bad(s[S_QVEL + lane]) || (lane == 0 && bad(s[S_QPOS + 32])));
-  if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
-  pos_stage(s, m, lane);
-  return true;
-}
-__device__ __noinline__ bool phase_smooth(float* s, const DevModel& m, int lane) {
-  const bool on = lane < m.nv;
-  const float passive = on ? -m.dof_damping[lane] * s[S_QVEL + lane] : 0.f;
-  const float act = lane < m.nu ? s[S_CTRL + lane] : 0.f;   // motors on dofs 0..nu-1, gear 1
-  const float fs = on ? passive - s[S_BIAS + lane] + s[S_QAPP + lane] + act : 0.f;
-  s[S_SMOOTH + lane] = fs;
-  float as;
-  const bool ok = tree_solve(s, m, lane, 0.f, fs, &as);
-  s[S_ASMOOTH + lane] = as;
-  __syncwarp();
-  return ok;
-}
-// Every warp of the CTA calls this (active = false: only the CTA barriers inside the solver are taken).
-__device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int lane, Cnt& cnt, bool active) {
-  int* misc = (int*)(s + S_MISC);
-  unsigned it = 0;
-  bool fail = !solve_newton(s, m, lane, active, it, cnt.ls);
-  if (!active) return false;
-  cnt.newton += it;
-  cnt.substeps++;
-  cnt.ncon += misc[MI_NCON];
-  cnt.nefc += m.nv + misc[MI_NLIM] + misc[MI_NEDGE];
-  cnt.max_ncon = max(cnt.max_ncon, (unsigned)misc[MI_NCON]);
-  cnt.max_nbasis = max(cnt.max_nbasis, (unsigned)misc[MI_NBASIS]);
-  cnt.max_nedge = max(cnt.max_nedge, (unsigned)misc[MI_NEDGE]);
-  if (lane == 0) misc[MI_ITER] = (int)it;
-  fail = __any_sync(FULLMASK, fail || bad(s[S_QACC + lane]));
-  if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
-  return !(misc[MI_FLAGS] & 2);   // capacity overflow: treated like MuJoCo's nconmax / njmax warnings
-}
-
-// forward dynamics of the state in S_QPOS/S_QVEL with S_CTRL/S_QAPP/S_WARM, then Euler (single-warp callers)
-__device__ bool substep_core(float* s, const DevModel& m, int lane, bool record, Cnt& cnt) {
-  int* misc = (int*)(s + S_MISC);
-  if (!phase_forward(s, m, lane)) return false;
-  vel_stage(s, m, lane);
-  if (!phase_smooth(s, m, lane)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
-  collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
-  (void)record;   // single-substep entry: no contact averaging
-  build_rows(s, m, lane);
-  if (!phase_solve(s, m, lane, cnt, true)) return false;
-  if (!euler_step(s, m, lane, nullptr)) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
-  return true;
-}
-
-__device__ __forceinline__ void load_state(float* s, const float* st, int lane, int qoff, int voff) {
-  s[S_QPOS + lane] = st[qoff + lane];
-  if (lane < 4) s[S_QPOS + 32 + lane] = lane == 0 ? st[qoff + 32] : 0.f;
-  s[S_QVEL + lane] = st[voff + lane];
-}
-
-__device__ void flush_counters(const BatchDev& B, const Cnt& c, int lane, unsigned env_steps) {
-  if (lane != 0) return;
-  unsigned long long* g = B.counters;
-  if (env_steps) atomicAdd(g + 0, (unsigned long long)env_steps);
-  atomicAdd(g + 1, (unsigned long long)c.substeps);
-  atomicAdd(g + 2, (unsigned long long)c.ncon);
-  atomicAdd(g + 3, (unsigned long long)c.nefc);
-  atomicAdd(g + 4, (unsigned long long)c.newton);
-  atomicAdd(g + 5, (unsigned long long)c.ls);
-  atomicAdd(g + 6, (unsigned long long)c.mpr_calls);
-  atomicAdd(g + 7, (unsigned long long)c.mpr_iters);
-  atomicAdd(g + 8, (unsigned long long)c.qp);
-  if (c.fail_phys) atomicAdd(g + 9, (unsigned long long)c.fail_phys);
-  if (c.fail_over) atomicAdd(g + 10, (unsigned long long)c.fail_over);
-  atomicMax(g + 12, (unsigned long long)c.max_ncon);
-  atomicMax(g + 13, (unsigned long long)c.max_nbasis);
-  atomicMax(g + 14, (unsigned long long)c.max_nedge);
-}
-
-__device__ __forceinline__ EnvCtx make_ctx(const BatchDev& B, const int* ints) {
-  EnvCtx e;
-  const int mid = ints[1], sidx = ints[2];
-  e.motion = B.frames + (size_t)(B.motion_offset[mid] + sidx) * H_FRAME;
-  e.expert_len = ints[3];
-  e.cur_t = ints[0];
-  e.start_ind = 0;
-  return e;
-}
-
-// ---- tail of env.step after the substeps: averages, contact classification, residual-force QP (ho_im4.py:553-565, 631)
-__device__ __noinline__ float step_tail(float* s, const DevModel& m, int lane, const float* og, float old_obj_vel, V3 vf, V3 vt,
-                                        float* rest, int& ncg_out, unsigned& qp_iters, float* surf, const float* csum) {
-  float rfc_score = 0.f;
-  const int nhg = m.hand_geom1 - m.hand_geom0 + 1;
-  const float inv_dt = 1.0f / (m.sim_step * m.timestep);
-  const V3 org = ld3(s + S_ORG), oorg = ld3(og + HN * 12);
-  const float acc = (s[S_QVEL + lane] - old_obj_vel) * inv_dt;   // lanes nv-6..nv-1: obj_avg_acc
-  const V3 obj_a = v3(__shfl_sync(FULLMASK, acc, m.nv - 6), __shfl_sync(FULLMASK, acc, m.nv - 5), __shfl_sync(FULLMASK, acc, m.nv - 4));
-  const V3 obj_oa = v3(__shfl_sync(FULLMASK, acc, m.nv - 3), __shfl_sync(FULLMASK, acc, m.nv - 2), __shfl_sync(FULLMASK, acc, m.nv - 1));
-  // classify_contact: lane = hand geom slot
-  const float ccnt = lane < nhg ? csum[240 + lane] : 0.f;
-  const bool has = ccnt > 0.f;
-  float fr[12];
-  if (has) {
-    const float ic = 1.0f / ccnt;
-    for (int k = 0; k < 12; k++) fr[k] = csum[12 * lane + k] * ic;
-    V3 n = ld3(fr + 3);
-    n = n * (1.0f / norm(n));
-    V3 t = fabsf(n.x) >= 1e-5f ? cross(n, v3(1.f, 0.f, 0.f)) : cross(n, v3(0.f, 1.f, 0.f));
-    t = t * (1.0f / norm(t));
-    V3 b = cross(n, t);
-    b = b * (1.0f / norm(b));
-    st3(fr + 3, n); st3(fr + 6, t); st3(fr + 9, b);
-  }
-  const float ts = has ? ccnt / (float)m.sim_step : 0.f;
-  const unsigned bal = __ballot_sync(FULLMASK, has);
-  const int ncg = __popc(bal);
-  ncg_out = ncg;
-  __syncwarp();
-  // geom average velocities: contact geoms (lane = slot) and the last geom (object visual mesh)
-  auto geom_vel = [&](int g, V3& lin, V3& ang) {
-    const V3 pn = ld3(s + S_GPOS + 3 * g), po = ld3(og + 3 * g);
-    lin = ((pn - po) + (org - oorg)) * inv_dt;
-    const M3 Rd = mulmT(ldm(s + S_GMAT + 9 * g), ldm(og + HN * 3 + 9 * g));
-    ang = matrix_to_axis_angle(Rd) * inv_dt;
-  };
-  V3 obj_v, obj_w;
-  geom_vel(m.last_geom, obj_v, obj_w);
-  if (has) {
-    const int idx = __popc(bal & ((1u << lane) - 1u));
-    for (int k = 0; k < 12; k++) s[QP_CF + 12 * idx + k] = fr[k];
-    s[QP_TS + idx] = ts;
-    ((int*)(s + QP_G1))[idx] = m.hand_geom0 + lane;
-    V3 gl, ga;
-    geom_vel(m.hand_geom0 + lane, gl, ga);
-    st3(s + QP_GV + 6 * idx, gl); st3(s + QP_GV + 6 * idx + 3, ga);
-  }
-  __syncwarp();
-  if (m.residual_force) {
-    if (!m.explain_force) {
-      rfc_score = norm(vf) + 1e4f * norm(vt);
-    } else {
-      const V3 obj_p = ld3(s + S_QPOS + m.nhand_q);
-      const M3 R = q2m(qnormalize(ldq(s + S_QPOS + m.nhand_q + 3)));
-      M3 RI;
-      for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) RI.m[3 * i + j] = R.m[3 * i + j] * m.obj_inertia[j];
-      const M3 I = mulmT(RI, R);
-      const V3 F = (obj_a + v3(0.f, 0.f, 9.8f)) * m.obj_mass;
-      const V3 T = mulv(I, obj_oa) + cross(obj_w, mulv(I, obj_w));
-      if (ncg == 0) {
-        rfc_score = norm(F) + 1e4f * norm(T);
-        rest[0] = F.x; rest[1] = F.y; rest[2] = F.z; rest[3] = T.x; rest[4] = T.y; rest[5] = T.z;
-      } else {
-#ifdef H_NOQP   // timing experiment only (tools/ab.sh): what the residual-force QP costs in kernel wall time
-        if (qp_iters > 1000000u)
-#endif
-        rfc_score = rfc_qp(s, lane, ncg, m.surface_contact ? 5 : 1, F, T, obj_p, obj_v, obj_w, s + S_GPOS, org, rest, qp_iters, surf);
-      }
-    }
-  }
-  return rfc_score;
-}
-
-// ------------------------------------------------------------------------------------------------ step kernel
-// H_WPB warps (= environments) per CTA.  The substep loop runs sim_step+1 times: pass -1 recomputes the forward of the
-// state that preceded the step (the "stale" quantities the env logic reads) with the same code as the
-// real substeps.  CTA barriers keep the warps of a CTA inside the same code region (instruction-cache locality).
-#ifndef H_WPB
-#define H_WPB 10
-#endif
-#ifndef H_CPS
-#define H_CPS 1         // resident CTAs per SM the register budget is sized for
-#endif
-#ifndef H_BARRIERS
-#define H_BARRIERS 0xff
-#endif
-#ifdef H_PROF
-// per-phase cycle accounting: own work (phase start -> arrival at the next barrier) and wait (arrival -> release)
-__device__ unsigned long long g_prof[16][2];
-#define HB(n) do { const long long t_arr = clock64(); if (H_BARRIERS & (1 << (n))) __syncthreads(); const long long t_rel = clock64(); \
-    if (lane == 0 && ok) { atomicAdd(&g_prof[prof_phase][0], (unsigned long long)(t_arr - prof_t0)); atomicAdd(&g_prof[prof_phase][1], (unsigned long long)(t_rel - t_arr)); } \
-    prof_phase = (n); prof_t0 = t_rel; } while (0)
-#else
-#define HB(n) do { if (H_BARRIERS & (1 << (n))) __syncthreads(); } while (0)
-#endif
-__global__ void __launch_bounds__(32 * H_WPB, H_CPS) k_step(BatchDev B, const float* __restrict__ actions, StepOut out) {
-  extern __shared__ float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * H_WPB + warp;
-  float* s = smem + (size_t)warp * S_TOTAL;
-  const bool live = slot < B.n_envs;
-  const int env = live ? (B.perm ? B.perm[slot] : slot) : B.n_envs - 1;
-  const int envc = env;
-  // When every env of the CTA uses the same model (always, except in mixed-object batches) the model constants are staged
-  // once into shared memory behind the env regions: the phases then read joint / geom / candidate tables through shared
-  // memory instead of an L1 that the ~200 KB carve-out leaves little room for (box 4096 envs: 5.93 -> 5.80 ms).  Models with
-  // large meshes keep the L1 for their vertices instead (stage_bytes = 0; banana measured faster that way).
-  const DevModel* gm = B.env_model[envc];
-  DevModel* sm_model = reinterpret_cast<DevModel*>(smem + (size_t)H_WPB * S_TOTAL);
-  const int first = min(blockIdx.x * H_WPB, B.n_envs - 1);
-  const int nstage = gm->stage_bytes;
-  const bool uniform = __syncthreads_and(nstage > 0 && nstage <= B.model_smem && gm == B.env_model[B.perm ? B.perm[first] : first]);
-  if (uniform) {
-    const float2* src = reinterpret_cast<const float2*>(gm);
-    float2* dst = reinterpret_cast<float2*>(sm_model);
-    for (int i = threadIdx.x; i < nstage / 8; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-  }
-  const DevModel& m = uniform ? *sm_model : *gm;
-
-  float* st = B.state + (size_t)envc * ST_STRIDE;
-  int* ints = (int*)(st + ST_INTS);
-  int* misc = (int*)(s + S_MISC);
-  Cnt cnt;
-  memset(&cnt, 0, sizeof cnt);
-  if (lane < 16) misc[lane] = 0;
-  EnvCtx ctx = make_ctx(B, ints);
-  {
-    float a = lane < m.nu + (m.residual_force ? 6 : 0) ? actions[(size_t)envc * HOIC_ACT_DIM + lane] : 0.f;
-    s[S_ACT + lane] = fminf(fmaxf(a, -1.f), 1.f);
-  }
-  // current state in registers while the previous forward is recomputed
-  const float cq = st[ST_QPOS + lane], cq32 = st[ST_QPOS + 32], cv = st[ST_QVEL + lane], cw = st[ST_WARM + lane];
-  load_state(s, st, lane, ST_PQPOS, ST_PQVEL);
-  float* csum = B.csum + (size_t)envc * CSUM_STRIDE;
-  if (live) for (int i = lane; i < CSUM_STRIDE; i += 32) csum[i] = 0.f;
-  __syncwarp();
-  const float old_obj_vel = (lane >= m.nv - 6 && lane < m.nv) ? cv : 0.f;
-  float* og = B.old_geom + (size_t)envc * (HN * 12 + 4);
-  V3 vf = v3(0, 0, 0), vt = v3(0, 0, 0);
-  float pq = cq, pq32 = cq32, pv = cv;
-  bool ok = live;      // false once this env failed (or the slot is padding): skips work, keeps hitting the barriers
-  float* recf = (B.rec_frames && live) ? B.rec_frames + (size_t)envc * m.sim_step * HOIC_REC_STRIDE : nullptr;
-  float* surf = (B.rec_surface && live) ? B.rec_surface + (size_t)envc * HOIC_SURF_STRIDE : nullptr;
-  if (recf) for (int i = lane; i < m.sim_step * HOIC_REC_STRIDE; i += 32) recf[i] = 0.f;
-  if (surf) for (int i = lane; i < HOIC_SURF_STRIDE; i += 32) surf[i] = 0.f;
-#ifdef H_PROF
-  int prof_phase = 8;
-  long long prof_t0 = clock64();
-#endif
-  const int nsub = m.sim_step;
-  for (int k = -1; k < nsub; k++) {
-    HB(0);
-    if (ok && k >= 0) {
-      if (k == 0) {
-        vf = m.residual_force ? ld3(s + S_ACT + m.nu) * m.rf_scale : v3(0, 0, 0);
-        vt = m.residual_force ? ld3(s + S_ACT + m.nu + 3) * m.rt_scale : v3(0, 0, 0);
-      }
-      ok = pd_torque(s, m, lane, ctx);
-      // J^T wrenches with the previous forward's Jacobians (stale cdof / com / geom_xpos)
-      const V3 org = ld3(s + S_ORG);
-      float qf = apply_ft(s, m, lane, v3(0.f, 0.f, m.hand_mass * 9.8f), v3(0, 0, 0), ld3(s + S_GPOS + 3 * m.hand_geom0), m.palm_body);
-      if (m.residual_force) qf += apply_ft(s, m, lane, vf, vt, ld3(s + S_QPOS + m.nhand_q) - org, m.obj_body);
-      __syncwarp();
-      s[S_QAPP + lane] = qf;
-      pq = s[S_QPOS + lane]; pq32 = s[S_QPOS + 32]; pv = s[S_QVEL + lane];
-      __syncwarp();
-      if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
-    }
-    HB(6);
-    if (ok) ok = phase_forward(s, m, lane) || k < 0;   // a bad stale state is reported by the previous step already
-    HB(5);
-    if (ok) vel_stage(s, m, lane);
-    HB(1);
-    if (ok && k >= 0) {
-      // qacc_smooth first: tree_solve borrows the union region, which the contacts occupy from collide() on
-      ok = phase_smooth(s, m, lane);
-      if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
-    }
-    HB(3);
-    if (ok) {
-      collide(s, m, lane, cnt.mpr_calls, cnt.mpr_iters);
-      if (k + 1 < nsub) record_contacts(s, m, lane, csum);
-    }
-    if (k < 0) {
-      if (ok) {
-        // snapshot of geom poses for the averaged velocities (ho_im4.py:508-511), then restore the current state
-        for (int i = lane; i < m.ngeom * 3; i += 32) og[i] = s[S_GPOS + i];
-        for (int i = lane; i < m.ngeom * 9; i += 32) og[HN * 3 + i] = s[S_GMAT + i];
-        if (lane < 3) og[HN * 12 + lane] = s[S_ORG + lane];
-        s[S_QPOS + lane] = cq;
-        if (lane == 0) { s[S_QPOS + 32] = cq32; misc[MI_FLAGS] = 0; }
-        s[S_QVEL + lane] = cv;
-        s[S_WARM + lane] = cw;
-        __syncwarp();
-      }
-      continue;
-    }
-    HB(2);
-    if (ok) {
-      build_rows(s, m, lane);
-      if (recf) record_contact_frames(s, m, lane, recf + (size_t)k * HOIC_REC_STRIDE);
-    }
-    HB(7);
-    ok = phase_solve(s, m, lane, cnt, ok);
-    HB(4);
-    if (ok) {
-      if (recf) record_forward(s, m, lane, recf + (size_t)k * HOIC_REC_STRIDE);
-      ok = euler_step(s, m, lane, nullptr);
-      if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
-      if (recf && ok) record_state(s, m, lane, vf, vt, recf + (size_t)k * HOIC_REC_STRIDE);
-    }
-  }
-  __syncthreads();
-  if (!live) return;
-  bool fail = !ok;
-  const int flags = misc[MI_FLAGS];
-  if (flags & 1) cnt.fail_phys++;
-  if (flags & 2) cnt.fail_over++;
-  float rfc_score = 0.f, rest[6] = {0, 0, 0, 0, 0, 0};
-  int ncg = 0;
-  if (!fail) rfc_score = step_tail(s, m, lane, og, old_obj_vel, vf, vt, rest, ncg, cnt.qp, surf, csum);
-  // ---- bookkeeping, termination, reward, observation (ho_im4.py:641-662)
-  ctx.cur_t += 1;
-  float reward = 0.f;
-  const bool body_fail = diff_and_reward(s, m, lane, ctx, B.reward_w, rfc_score, &reward, out.info ? out.info + (size_t)env * HOIC_INFO_DIM : nullptr);
-  if (B.mode_train) fail = fail || body_fail;
-  const bool end = ctx.cur_t + ctx.start_ind >= ctx.expert_len - m.w_size - 1;
-  if (out.obs) write_obs(s, m, lane, ctx, out.obs + (size_t)env * HOIC_OBS_DIM);
-  if (lane == 0) {
-    if (out.reward) out.reward[env] = reward;
-    if (out.done) out.done[env] = fail || end;
-    if (out.fail) out.fail[env] = fail;
-    if (out.end) out.end[env] = end;
-    if (out.percent) out.percent[env] = (float)ctx.cur_t / (float)(ctx.expert_len - 1);
-    ints[0] = ctx.cur_t;
-    ints[5] = (int)(cnt.newton * 8 + cnt.ncon * 2 + cnt.mpr_iters + (ncg ? 40 + 8 * ncg : 0));
-    st[ST_RFC] = rfc_score;
-    for (int k = 0; k < 6; k++) st[ST_RFC + 1 + k] = rest[k];
-    st[ST_RFC + 7] = (float)ncg;
-  }
-  st[ST_QPOS + lane] = s[S_QPOS + lane];
-  st[ST_QVEL + lane] = s[S_QVEL + lane];
-  st[ST_WARM + lane] = s[S_WARM + lane];
-  st[ST_PQPOS + lane] = pq;
-  st[ST_PQVEL + lane] = pv;
-  if (lane == 0) { st[ST_QPOS + 32] = s[S_QPOS + 32]; st[ST_PQPOS + 32] = pq32; }
-  flush_counters(B, cnt, lane, 1);
-}
-
 // ------------------------------------------------------------------------------------------------ reset kernel
+// counter-based uniform in [0, 1): splitmix64 of (seed, env, episode counter, draw)
+__device__ __forceinline__ float hoic_uniform(unsigned long long seed, unsigned env, unsigned episode, unsigned draw) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (((unsigned long long)env << 32 | episode) * 4ull + draw + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// `sample` != 0: draw (motion, start_idx) on the device as the sampler does between episodes (agent_handmimic.py:437-448):
+// a uniform motion of the env's model, start ~ U{0 .. len - min_episode - 1} (0 without random_start).
 __global__ void __launch_bounds__(32) k_reset(BatchDev B, const uint8_t* __restrict__ mask, const int* __restrict__ motion_id,
-                                              const int* __restrict__ start_idx, float* obs_out) {
+                                              const int* __restrict__ start_idx, float* obs_out, int sample) {
   extern __shared__ float s[];
   const int env = blockIdx.x, lane = threadIdx.x;
   if (env >= B.n_envs) return;
@@ -399,14 +39,25 @@ __global__ void __launch_bounds__(32) k_reset(BatchDev B, const uint8_t* __restr
   float* st = B.state + (size_t)env * ST_STRIDE;
   int* ints = (int*)(st + ST_INTS);
   int* misc = (int*)(s + S_MISC);
-  if (lane < 16) misc[lane] = 0;
+  misc[lane] = 0;
   int mid = ints[1], sidx = ints[2];
-  if (motion_id) mid = min(max(motion_id[env], 0), B.n_motions - 1);
-  if (start_idx) sidx = start_idx[env];
+  const int episode = ints[6];
+  if (sample) {
+    const int mi = B.env_model_idx[env], lo = B.samp_off[mi], cnt = B.samp_off[mi + 1] - lo;
+    mid = B.samp_ids[lo + min((int)(hoic_uniform(B.samp_seed, env, episode, 0) * cnt), cnt - 1)];
+    sidx = 0;
+    if (B.samp_random_start) {
+      const int span = max(B.motion_len[mid] - B.samp_min_episode, 1);
+      sidx = min((int)(hoic_uniform(B.samp_seed, env, episode, 1) * span), span - 1);
+    }
+  } else {
+    if (motion_id) mid = min(max(motion_id[env], 0), B.n_motions - 1);
+    if (start_idx) sidx = start_idx[env];
+  }
   const int mlen = B.motion_len[mid];
   sidx = min(max(sidx, 0), mlen - 1);
   __syncwarp();
-  if (lane == 0) { ints[0] = 0; ints[1] = mid; ints[2] = sidx; ints[3] = mlen - sidx; }
+  if (lane == 0) { ints[0] = 0; ints[1] = mid; ints[2] = sidx; ints[3] = mlen - sidx; ints[6] = episode + 1; }
   EnvCtx ctx;
   ctx.motion = B.frames + (size_t)(B.motion_offset[mid] + sidx) * H_FRAME;
   ctx.expert_len = mlen - sidx; ctx.cur_t = 0; ctx.start_ind = 0;
@@ -420,7 +71,7 @@ __global__ void __launch_bounds__(32) k_reset(BatchDev B, const uint8_t* __restr
   else if (lane < nhv + 3) s[S_QVEL + lane] = f[F_OBJVEL + lane - nhv];
   else s[S_QVEL + lane] = f[F_OBJANGVEL + lane - nhv - 3];
   __syncwarp();
-  pos_stage(s, m, lane);   // sim.forward() of set_state: poses for the observation (and normalised quaternion)
+  pos_stage(s, m, lane, s + S_GPOS, s + S_GMAT);   // sim.forward() of set_state: poses for the observation (and normalised quaternion)
   if (obs_out) write_obs(s, m, lane, ctx, obs_out + (size_t)env * HOIC_OBS_DIM);
   st[ST_QPOS + lane] = s[S_QPOS + lane];
   st[ST_QVEL + lane] = s[S_QVEL + lane];
@@ -429,6 +80,33 @@ __global__ void __launch_bounds__(32) k_reset(BatchDev B, const uint8_t* __restr
   st[ST_PQVEL + lane] = s[S_QVEL + lane];
   if (lane == 0) { st[ST_QPOS + 32] = s[S_QPOS + 32]; st[ST_PQPOS + 32] = s[S_QPOS + 32]; }
   if (lane < 8) st[ST_RFC + lane] = 0.f;
+}
+
+// Longest-processing-time env order for the step pipeline: a counting sort of the envs by the cost proxy of their last
+// step (ints[5]: solver iterations, contacts, MPR iterations, QP size), most expensive first, so that the last CTAs of
+// every kernel are the cheap ones.  One CTA; the order inside a bucket is irrelevant (results do not depend on the order).
+#define ORDER_BUCKETS 512
+__global__ void __launch_bounds__(1024) k_order(BatchDev B, int* order) {
+  __shared__ int hist[ORDER_BUCKETS];
+  for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  auto bucket = [&](int env) {
+    const int w = ((const int*)(B.state + (size_t)env * ST_STRIDE + ST_INTS))[5];
+    return ORDER_BUCKETS - 1 - min(max(w, 0) >> 2, ORDER_BUCKETS - 1);
+  };
+  for (int i = threadIdx.x; i < B.n_envs; i += blockDim.x) atomicAdd(&hist[bucket(i)], 1);
+  __syncthreads();
+  if (threadIdx.x < 32) {      // exclusive scan of the histogram by one warp
+    int carry = 0;
+    for (int base = 0; base < ORDER_BUCKETS; base += 32) {
+      const int v = hist[base + threadIdx.x];
+      const int ex = wexscan(v, threadIdx.x);
+      hist[base + threadIdx.x] = carry + ex;
+      carry += __shfl_sync(FULLMASK, ex + v, 31);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B.n_envs; i += blockDim.x) order[atomicAdd(&hist[bucket(i)], 1)] = i;
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
@@ -470,10 +148,10 @@ __global__ void __launch_bounds__(32) k_forward_debug(BatchDev B, float* xpos, f
   const DevModel& m = *B.env_model[env];
   const float* st = B.state + (size_t)env * ST_STRIDE;
   int* misc = (int*)(s + S_MISC);
-  if (lane < 16) misc[lane] = 0;
+  misc[lane] = 0;
   load_state(s, st, lane, ST_PQPOS, ST_PQVEL);
   __syncwarp();
-  pos_stage(s, m, lane);
+  pos_stage(s, m, lane, s + S_GPOS, s + S_GMAT);
   vel_stage(s, m, lane);
   const V3 org = ld3(s + S_ORG);
   if (xpos) for (int i = lane; i < m.nbody * 3; i += 32) xpos[(size_t)env * m.nbody * 3 + i] = s[S_XPOS + i] + comp(org, i % 3);
@@ -522,7 +200,7 @@ __global__ void __launch_bounds__(32) k_substep_debug(BatchDev B, const float* c
   const DevModel& m = *B.env_model[env];
   float* st = B.state + (size_t)env * ST_STRIDE;
   int* misc = (int*)(s + S_MISC);
-  if (lane < 16) misc[lane] = 0;
+  misc[lane] = 0;
   Cnt cnt;
   memset(&cnt, 0, sizeof cnt);
   load_state(s, st, lane, ST_QPOS, ST_QVEL);
@@ -584,7 +262,7 @@ __global__ void __launch_bounds__(32) k_preprocess(const DevModel* mp, const flo
   if (t >= T) return;
   const DevModel& m = *mp;
   int* misc = (int*)(s + S_MISC);
-  if (lane < 16) misc[lane] = 0;
+  misc[lane] = 0;
   const int nh = m.nhand_q;
   const int a = t == 0 ? 1 : t, b = a - 1;           // vel[0] = vel[1] (:157-158)
   float* f = frames + (size_t)t * H_FRAME;
@@ -610,7 +288,7 @@ __global__ void __launch_bounds__(32) k_preprocess(const DevModel* mp, const flo
   if (lane == 0) s[S_QPOS + 32] = obj[(size_t)7 * t + 32 - nh];
   s[S_QVEL + lane] = 0.f;
   __syncwarp();
-  pos_stage(s, m, lane);
+  pos_stage(s, m, lane, s + S_GPOS, s + S_GMAT);
   const V3 org = ld3(s + S_ORG);
   for (int i = lane; i < 3 * m.n_hand_body; i += 32) f[F_BPOS + i] = s[S_XPOS + 3 * m.hand_body_idx[i / 3] + i % 3] + comp(org, i % 3);
   for (int i = lane; i < 4 * m.n_hand_body; i += 32) f[F_BQUAT + i] = s[S_XQUAT + 4 * m.hand_body_idx[i / 4] + i % 4];
@@ -645,6 +323,7 @@ struct hoic_model {
   DevModel host;
 };
 
+#define HOIC_MAX_PARTS 8
 struct hoic_batch {
   int device, n_envs;
   BatchDev b;
@@ -652,8 +331,15 @@ struct hoic_batch {
   const DevModel** env_model_dev;
   float *frames, *reward_w;
   int *motion_offset, *motion_len;
-  size_t smem_bytes, step_smem, frames_cap = 0;
-  int motions_cap = 0;
+  int *env_model_idx = nullptr, *samp_off = nullptr, *samp_ids = nullptr, *order = nullptr;
+  int balance = 0, n_models = 0, n_samp_ids = 0;
+  const int* user_perm = nullptr;
+  size_t smem_bytes, frames_cap = 0;
+  int motions_cap = 0, nsub = 0;
+  // hoic_step runs the batch as `nparts` interleaved parts on internal streams (fork / join around the caller's stream)
+  int nparts = 1;
+  cudaStream_t part_stream[HOIC_MAX_PARTS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[HOIC_MAX_PARTS] = {};
 };
 
 extern "C" const char* hoic_last_error(void) { return g_err.c_str(); }
@@ -1068,6 +754,17 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   CUDA_OKP(cudaSetDevice(device));
   CUDA_OKP(cudaMalloc(&b->env_model_dev, n_envs * sizeof(DevModel*)));
   CUDA_OKP(cudaMemcpy(b->env_model_dev, b->env_model_host.data(), n_envs * sizeof(DevModel*), cudaMemcpyHostToDevice));
+  {
+    std::vector<int> idx(n_envs);
+    for (int i = 0; i < n_envs; i++) idx[i] = env_model_id_host ? env_model_id_host[i] : 0;
+    CUDA_OKP(cudaMalloc(&b->env_model_idx, n_envs * sizeof(int)));
+    CUDA_OKP(cudaMemcpy(b->env_model_idx, idx.data(), n_envs * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OKP(cudaMalloc(&b->order, n_envs * sizeof(int)));
+    b->b.env_model_idx = b->env_model_idx;
+    b->b.order = b->order;
+    b->n_models = n_models;
+    b->balance = n_envs > 7;
+  }
   CUDA_OKP(cudaMalloc(&b->b.state, (size_t)n_envs * ST_STRIDE * sizeof(float)));
   CUDA_OKP(cudaMemset(b->b.state, 0, (size_t)n_envs * ST_STRIDE * sizeof(float)));
   CUDA_OKP(cudaMalloc(&b->b.old_geom, (size_t)n_envs * (HN * 12 + 4) * sizeof(float)));
@@ -1081,25 +778,28 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   b->b.reward_w = b->reward_w;
   b->b.mode_train = 1;
   b->smem_bytes = (size_t)S_TOTAL * sizeof(float);
-  b->step_smem = b->smem_bytes * H_WPB;
+  CUDA_OKP(cudaMalloc(&b->b.scratch, (size_t)n_envs * G_TOTAL * sizeof(float)));
+  CUDA_OKP(cudaMemset(b->b.scratch, 0, (size_t)n_envs * G_TOTAL * sizeof(float)));
+  for (int i = 0; i < n_models; i++) b->nsub = std::max(b->nsub, models[i]->host.sim_step);
+  b->b.model_smem = 0;
   {
-    static_assert(sizeof(DevModel) % 8 == 0 && (S_TOTAL * 4) % 16 == 0 && offsetof(DevModel, cand) % 8 == 0, "model staging copies 8-byte words");
-    size_t want = 0;
-    // mixed-object batches: CTAs hold envs of different models (the env order groups by cost), staging would rarely apply and
-    // the larger carve-out would cost every CTA half of its L1: stage only in single-model batches
-    if (n_models == 1) want = (size_t)models[0]->host.stage_bytes;
-    const size_t room = 232448 - b->step_smem;      // 227 KB of dynamic shared memory per CTA on sm_100
-    b->b.model_smem = (int)std::min(want, room);      // models that need more than this keep reading global memory
-    b->step_smem += b->b.model_smem;
+    // parts only pay off while a part still fills the GPU about once; HOIC_STEP_PARTS overrides
+    int want = n_envs >= 1024 ? 2 : 1;
+    if (const char* e = getenv("HOIC_STEP_PARTS")) want = atoi(e);
+    b->nparts = std::min(std::max(want, 1), HOIC_MAX_PARTS);
+    if (b->nparts > 1) {
+      CUDA_OKP(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+      for (int j = 0; j < b->nparts; j++) {
+        CUDA_OKP(cudaStreamCreateWithFlags(&b->part_stream[j], cudaStreamNonBlocking));
+        CUDA_OKP(cudaEventCreateWithFlags(&b->ev_join[j], cudaEventDisableTiming));
+      }
+    }
   }
   {
-    // the attribute belongs to the function, not to the batch: never lower it below what an earlier, still living batch
-    // of this process launches with (a box batch stages its model and needs more than a banana batch created after it)
-    static size_t step_smem_attr[64] = {0};
-    size_t& cur = step_smem_attr[device & 63];
-    if (b->step_smem > cur) {
-      CUDA_OKP(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->step_smem));
-      cur = b->step_smem;
+    static bool configured[64] = {false};
+    if (!configured[device & 63]) {
+      CUDA_OKP(hoic_configure_p1()); CUDA_OKP(hoic_configure_p2()); CUDA_OKP(hoic_configure_p3()); CUDA_OKP(hoic_configure_p3s()); CUDA_OKP(hoic_configure_tail());
+      configured[device & 63] = true;
     }
   }
   CUDA_OKP(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
@@ -1112,7 +812,11 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
 extern "C" void hoic_batch_destroy(hoic_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  cudaFree(b->env_model_dev); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum);
+  cudaDeviceSynchronize();
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  for (int j = 0; j < HOIC_MAX_PARTS; j++) { if (b->ev_join[j]) cudaEventDestroy(b->ev_join[j]); if (b->part_stream[j]) cudaStreamDestroy(b->part_stream[j]); }
+  cudaFree(b->env_model_dev); cudaFree(b->b.scratch); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum);
+  cudaFree(b->env_model_idx); cudaFree(b->samp_off); cudaFree(b->samp_ids); cudaFree(b->order);
   cudaFree(b->reward_w); cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
   delete b;
 }
@@ -1168,23 +872,106 @@ extern "C" int hoic_set_mode(hoic_batch* b, int train) {
 
 #define LAUNCH_CHECK() do { g_launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return set_err(std::string("kernel launch: ") + cudaGetErrorString(e_)); } while (0)
 
+extern "C" int hoic_set_sampler(hoic_batch* b, const int* model_motion_offset_host, const int* motion_ids_host, int random_start,
+                                int min_episode, unsigned long long seed) {
+  if (!b || !model_motion_offset_host || !motion_ids_host) return set_err("hoic_set_sampler: bad arguments");
+  if (!b->b.frames) return set_err("hoic_set_sampler: call hoic_set_motions first");
+  const int total = model_motion_offset_host[b->n_models];
+  if (model_motion_offset_host[0] != 0 || total < 1) return set_err("hoic_set_sampler: bad motion table");
+  for (int i = 0; i < b->n_models; i++)
+    if (model_motion_offset_host[i + 1] <= model_motion_offset_host[i]) return set_err("hoic_set_sampler: every model needs at least one motion");
+  for (int i = 0; i < total; i++)
+    if (motion_ids_host[i] < 0 || motion_ids_host[i] >= b->b.n_motions) return set_err("hoic_set_sampler: motion id out of range");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  cudaFree(b->samp_off); cudaFree(b->samp_ids);
+  b->samp_off = b->samp_ids = nullptr;
+  CUDA_OK(cudaMalloc(&b->samp_off, (b->n_models + 1) * sizeof(int)));
+  CUDA_OK(cudaMalloc(&b->samp_ids, total * sizeof(int)));
+  CUDA_OK(cudaMemcpy(b->samp_off, model_motion_offset_host, (b->n_models + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(b->samp_ids, motion_ids_host, total * sizeof(int), cudaMemcpyHostToDevice));
+  b->b.samp_off = b->samp_off; b->b.samp_ids = b->samp_ids;
+  b->b.samp_random_start = random_start ? 1 : 0;
+  b->b.samp_min_episode = min_episode;
+  b->b.samp_seed = seed;
+  return 0;
+}
+
 extern "C" int hoic_reset(hoic_batch* b, const uint8_t* mask, const int* motion_id, const int* start_idx, float* obs_out, void* stream) {
   if (!b) return set_err("hoic_reset: null batch");
   if (!b->b.frames) return set_err("hoic_reset: call hoic_set_motions first");
   CUDA_OK(cudaSetDevice(b->device));
-  k_reset<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, mask, motion_id, start_idx, obs_out);
+  k_reset<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, mask, motion_id, start_idx, obs_out, 0);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int hoic_reset_sampled(hoic_batch* b, const uint8_t* mask, float* obs_out, void* stream) {
+  if (!b) return set_err("hoic_reset_sampled: null batch");
+  if (!b->b.samp_off) return set_err("hoic_reset_sampled: call hoic_set_sampler first");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_reset<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, mask, nullptr, nullptr, obs_out, 1);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_get_episode(BatchDev B, int* motion_id, int* start_idx, int* cur_t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n_envs) return;
+  const int* ints = (const int*)(B.state + (size_t)i * ST_STRIDE + ST_INTS);
+  if (cur_t) cur_t[i] = ints[0];
+  if (motion_id) motion_id[i] = ints[1];
+  if (start_idx) start_idx[i] = ints[2];
+}
+extern "C" int hoic_get_episode(hoic_batch* b, int* motion_id, int* start_idx, int* cur_t, void* stream) {
+  if (!b) return set_err("hoic_get_episode: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_get_episode<<<(b->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, motion_id, start_idx, cur_t);
   LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float* reward, float* reward_info, uint8_t* done,
-                         uint8_t* fail, uint8_t* end, float* percent, void* stream) {
+                         uint8_t* fail, uint8_t* end, float* percent, int auto_reset, void* stream) {
   if (!b || !actions) return set_err("hoic_step: bad arguments");
   if (!b->b.frames) return set_err("hoic_step: call hoic_set_motions first");
+  if (auto_reset && (!done || !b->b.samp_off)) return set_err("hoic_step: auto_reset needs the done output and hoic_set_sampler");
   CUDA_OK(cudaSetDevice(b->device));
+  if (b->user_perm) b->b.perm = b->user_perm;
+  else if (b->balance) {
+    k_order<<<1, 1024, 0, (cudaStream_t)stream>>>(b->b, b->order);
+    LAUNCH_CHECK();
+    b->b.perm = b->order;
+  } else b->b.perm = nullptr;
   StepOut o = {obs, reward, reward_info, done, fail, end, percent};
-  k_step<<<(b->n_envs + H_WPB - 1) / H_WPB, 32 * H_WPB, b->step_smem, (cudaStream_t)stream>>>(b->b, actions, o);
-  LAUNCH_CHECK();
+  cudaStream_t user = (cudaStream_t)stream;
+  const int np = b->nparts;
+#define STEP_LAUNCH(call) do { cudaError_t e_ = (call); g_launches++; if (e_ != cudaSuccess) return set_err(std::string("kernel launch (" #call "): ") + cudaGetErrorString(e_)); } while (0)
+#define STEP_PARTS(call) do { for (int j = 0; j < np; j++) { const StepPart sp = {j, np}; cudaStream_t sm = np > 1 ? b->part_stream[j] : user; STEP_LAUNCH(call); } } while (0)
+  if (np > 1) {
+    CUDA_OK(cudaEventRecord(b->ev_fork, user));
+    for (int j = 0; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_fork, 0));
+  }
+  STEP_PARTS(hoic_launch_p1(b->b, sp, actions, -1, sm));
+  STEP_PARTS(hoic_launch_p2(b->b, sp, -1, sm));
+  for (int k = 0; k < b->nsub; k++) {
+    STEP_PARTS(hoic_launch_p1(b->b, sp, actions, k, sm));
+    STEP_PARTS(hoic_launch_p2(b->b, sp, k, sm));
+    STEP_PARTS(hoic_launch_p3s(b->b, sp, k, sm));
+    STEP_PARTS(hoic_launch_p3(b->b, sp, k, sm));
+  }
+  STEP_PARTS(hoic_launch_tail(b->b, sp, actions, o, sm));
+  if (np > 1) {
+    for (int j = 0; j < np; j++) { CUDA_OK(cudaEventRecord(b->ev_join[j], b->part_stream[j])); CUDA_OK(cudaStreamWaitEvent(user, b->ev_join[j], 0)); }
+  }
+#undef STEP_PARTS
+  if (auto_reset) {
+    // the sampler's episode loop (agent_handmimic.py:437-454): a finished env restarts on a freshly drawn (motion, start)
+    // and its returned observation is the reset observation
+    k_reset<<<b->n_envs, 32, b->smem_bytes, user>>>(b->b, done, nullptr, nullptr, obs, 1);
+    LAUNCH_CHECK();
+  }
+#undef STEP_LAUNCH
   return 0;
 }
 
@@ -1265,7 +1052,12 @@ extern "C" int hoic_get_work(hoic_batch* b, int* work, void* stream) {
 }
 extern "C" int hoic_set_env_order(hoic_batch* b, const int* perm) {
   if (!b) return set_err("hoic_set_env_order: null batch");
-  b->b.perm = perm;
+  b->user_perm = perm;
+  return 0;
+}
+extern "C" int hoic_set_balance(hoic_batch* b, int on) {
+  if (!b) return set_err("hoic_set_balance: null batch");
+  b->balance = on ? 1 : 0;
   return 0;
 }
 extern "C" int hoic_get_counters(hoic_batch* b, hoic_counters* out_host) {
@@ -1278,22 +1070,6 @@ extern "C" int hoic_get_counters(hoic_batch* b, hoic_counters* out_host) {
   out_host->ls_evals = h[5]; out_host->mpr_calls = h[6]; out_host->mpr_iters = h[7]; out_host->qp_iters = h[8];
   out_host->fail_physics = h[9]; out_host->fail_overflow = h[10]; out_host->chol_calls = h[11];
   out_host->max_ncon = h[12]; out_host->max_nbasis = h[13]; out_host->max_nedge = h[14];
-#ifdef H_PROF
-  { unsigned long long pr[16][2]; cudaMemcpyFromSymbol(pr, g_prof, sizeof pr);
-    static const char* nm[16] = {"0:pd+applyft", "1:smooth", "2:build_rows", "3:collide", "4:euler", "5:vel", "6:pos", "7:solve", "8:prologue/tail-k-1"};
-    double tot = 0; for (int i = 0; i < 9; i++) tot += (double)pr[i][0] + (double)pr[i][1];
-    for (int i = 0; i < 9; i++) fprintf(stderr, "H_PROF after-barrier %-20s work %5.1f%%  wait %5.1f%%\n", nm[i], 100.0 * pr[i][0] / tot, 100.0 * pr[i][1] / tot); }
-#endif
-#ifdef H_STATS
-  { unsigned long long ns[64]; cudaMemcpyFromSymbol(ns, g_nst, sizeof ns);
-    for (int i = 0; i < 8; i++) fprintf(stderr, "H_STATS solves with %d iters: %llu  avg cycles %.0f\n", i, ns[i], ns[i] ? (double)ns[8 + i] / ns[i] : 0.0);
-    static const char* pn[6] = {"init", "gradient", "incremental", "full direction", "line search", "move+cost"};
-    double tot = 0; for (int i = 0; i < 6; i++) tot += (double)ns[16 + i];
-    for (int i = 0; i < 6; i++) fprintf(stderr, "H_STATS newton part %-16s %5.1f%%\n", pn[i], 100.0 * ns[16 + i] / tot);
-    unsigned long long nsolve = 0, niter = 0; for (int i = 0; i < 8; i++) { nsolve += ns[i]; niter += ns[i] * i; }
-    fprintf(stderr, "H_STATS per direction call: assembly %.0f cycles, cholesky %.0f cycles (%llu calls)\n", (double)ns[24] / niter, (double)ns[25] / niter, niter); }
-  { unsigned long long st[8]; cudaMemcpyFromSymbol(st, g_stats, sizeof st); fprintf(stderr, "H_STATS iters_with_change=%llu changed_fric=%llu changed_con=%llu le4=%llu only_fric=%llu dir_tree=%llu dir_dense=%llu dir_incremental=%llu\n", st[0], st[1], st[2], st[3], st[4], st[5], st[6], st[7]); }
-#endif
   return 0;
 }
 

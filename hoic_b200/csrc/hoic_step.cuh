@@ -1,0 +1,46 @@
+// hoic_step.cuh -- helpers shared by the kernels of the env-step pipeline.
+// One env.step = k_p1(-1) k_p2(-1) [k_p1(k) k_p2(k) k_p3(k)] x sim_step  k_tail, one warp per environment in every kernel.
+// The working set of an env travels between the kernels through BatchDev.scratch (global memory, L2-resident at the
+// batch sizes of the benchmark) in the FULL layout; each kernel copies the fields it needs into its own compact
+// shared-memory layout, so that every kernel runs at its own occupancy, holds only its own code in the instruction cache
+// and is load-balanced by the CTA scheduler (the Newton solve and collision take a data-dependent time per env).
+#pragma once
+#include "dev_batch.cuh"
+#include "hoic_step.h"
+
+// n floats, n % 4 == 0, both sides 16-byte aligned
+__device__ __forceinline__ void cpf(float* dst, const float* src, int n, int lane) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = lane; i < (n >> 2); i += 32) d4[i] = s4[i];
+}
+#define LD_FIELD(name) cpf(s + S_OFF(name), g + G_OFF(name), F_SIZE(name), lane)
+#define ST_FIELD(name) cpf(g + G_OFF(name), s + S_OFF(name), F_SIZE(name), lane)
+// first n floats of a constraint-stage array (name as in UL_*: B, AREF, D, ...)
+#define LD_U(f, n) cpf(s + U_S(f), g + U_G(f), ((n) + 3) & ~3, lane)
+#define ST_U(f, n) cpf(g + U_G(f), s + U_S(f), ((n) + 3) & ~3, lane)
+
+struct EnvSlot {
+  int env;
+  bool live;
+};
+__device__ __forceinline__ EnvSlot env_of_slot(const BatchDev& B, StepPart sp, int idx) {
+  const int slot = idx * sp.nparts + sp.part;
+  EnvSlot e;
+  e.live = slot < B.n_envs;
+  e.env = e.live ? (B.perm ? B.perm[slot] : slot) : B.n_envs - 1;
+  return e;
+}
+// env failed earlier in this step (physics failure or capacity overflow): the remaining kernels skip it
+__device__ __forceinline__ bool env_dead(const int* misc) { return (misc[MI_FLAGS] & 3) != 0; }
+
+// dynamic shared memory per CTA: `pad` extra bytes lower the number of resident CTAs (leaves more L1)
+inline int hoic_step_grid(const BatchDev& B, StepPart sp, int warps) {
+  const int n = (B.n_envs - sp.part + sp.nparts - 1) / sp.nparts;     // slots of this part
+  return (n + warps - 1) / warps;
+}
+inline size_t hoic_step_smem(int warps, int pad_bytes) { return (size_t)warps * S_TOTAL * sizeof(float) + (size_t)pad_bytes; }
+inline int hoic_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}

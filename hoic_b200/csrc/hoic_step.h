@@ -1,0 +1,22 @@
+// hoic_step.h -- host-side launchers of the env-step pipeline (one translation unit per kernel: k_p1.cu, k_p2.cu, k_p3.cu,
+// k_tail.cu; each is compiled with its own compact shared-memory layout, see dev_model.h).
+#pragma once
+#include <cuda_runtime.h>
+struct BatchDev;
+struct StepOut;
+// A launch covers one interleaved part of the batch: slots part, part + nparts, part + 2 nparts, ...  hoic_step runs the
+// parts on parallel streams so that the tail of one part's kernel (a few long Newton solves) overlaps the next kernel of
+// another part instead of leaving SMs idle.
+struct StepPart { int part, nparts; };
+// k = substep index; -1 = the pass that recomputes the forward of the state that preceded the step
+cudaError_t hoic_launch_p1(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream);
+cudaError_t hoic_launch_p2(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);
+cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);    // full-capacity tier
+cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);   // small tier (most envs)
+cudaError_t hoic_launch_tail(const BatchDev& B, StepPart sp, const float* actions, const StepOut& out, cudaStream_t stream);
+// shared-memory attributes of the four kernels on the current device (once per device)
+cudaError_t hoic_configure_p1();
+cudaError_t hoic_configure_p2();
+cudaError_t hoic_configure_p3();
+cudaError_t hoic_configure_p3s();
+cudaError_t hoic_configure_tail();

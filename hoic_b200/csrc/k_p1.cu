@@ -1,0 +1,116 @@
+// k_p1.cu -- pipeline kernel 1 of env.step: everything of a substep that costs the same for every environment.
+//   k >= 1 : mj_Euler of substep k-1 (ho_im4.py:545, the tail of sim.step())
+//   k >= 0 : stable-PD torque + gravity compensation / residual wrench through J^T with the PREVIOUS forward's M, bias and
+//            Jacobians (ho_im4.py:412-501, 526-536), then mj_kinematics / comPos / crb, comVel / rne and
+//            qacc_smooth of the new state (MuJoCo mj_fwdPosition / mj_fwdVelocity / mj_fwdAcceleration)
+//   k = -1 : forward of the state that preceded the step (the "stale" quantities of S1 are recomputed, not stored)
+// One warp per env; all warps do the same work, so the warps of a CTA stay in step without barriers.
+#define H_KERNEL HK_P1
+#include "hoic_step.cuh"
+
+#ifndef P1_W
+#define P1_W 1          // warps (= envs) per CTA
+#endif
+#ifndef P1_WPS
+#define P1_WPS 23       // resident warps per SM the register budget is sized for
+#endif
+
+__global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) k_p1(BatchDev B, StepPart sp, const float* __restrict__ actions, int k) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P1_W + warp);
+  const int env = es.env;
+  float* s = smem + (size_t)warp * S_TOTAL;
+  float* g = B.scratch + (size_t)env * G_TOTAL;
+  float* st = B.state + (size_t)env * ST_STRIDE;
+  const DevModel& m = *B.env_model[env];
+  int* misc = (int*)(s + S_MISC);
+  if (k >= m.sim_step) return;
+  bool ok = es.live;
+  float* recf = (B.rec_frames && es.live) ? B.rec_frames + (size_t)env * m.sim_step * HOIC_REC_STRIDE : nullptr;
+  if (k < 0) {
+    misc[lane] = 0;
+    load_state(s, st, lane, ST_PQPOS, ST_PQVEL);
+    if (es.live) {
+      float* csum = B.csum + (size_t)env * CSUM_STRIDE;
+      for (int i = lane; i < CSUM_STRIDE; i += 32) csum[i] = 0.f;
+      if (recf) for (int i = lane; i < m.sim_step * HOIC_REC_STRIDE; i += 32) recf[i] = 0.f;
+      if (B.rec_surface) {
+        float* surf = B.rec_surface + (size_t)env * HOIC_SURF_STRIDE;
+        for (int i = lane; i < HOIC_SURF_STRIDE; i += 32) surf[i] = 0.f;
+      }
+    }
+    __syncwarp();
+  } else {
+    LD_FIELD(MISC); LD_FIELD(QPOS); LD_FIELD(QVEL); LD_FIELD(BIAS); LD_FIELD(COM); LD_FIELD(CDOF); LD_FIELD(ORG);
+    LD_FIELD(MS);
+    if (k > 0) {
+      LD_FIELD(QACC); LD_FIELD(SMOOTH); LD_FIELD(FCON);   // Euler of substep k-1 (sets S_WARM)
+      if (recf) LD_FIELD(XPOS);
+    } else {
+      LD_FIELD(WARM);
+    }
+    {
+      const float a = lane < m.nu + (m.residual_force ? 6 : 0) ? actions[(size_t)env * HOIC_ACT_DIM + lane] : 0.f;
+      s[S_ACT + lane] = fminf(fmaxf(a, -1.f), 1.f);
+    }
+    __syncwarp();
+    if (!ok || env_dead(misc)) return;    // failed earlier in this step: the working set stays as it was
+  }
+  const V3 vf = (k >= 0 && m.residual_force) ? ld3(s + S_ACT + m.nu) * m.rf_scale : v3(0, 0, 0);
+  const V3 vt = (k >= 0 && m.residual_force) ? ld3(s + S_ACT + m.nu + 3) * m.rt_scale : v3(0, 0, 0);
+  if (ok && k > 0) {
+    // integrate substep k-1 with the M of its forward
+    float* rf = recf ? recf + (size_t)(k - 1) * HOIC_REC_STRIDE : nullptr;
+    if (rf) record_forward(s, m, lane, rf, g + U_G(CON), g + U_G(FORCE), g + U_G(CINFO));
+    ok = euler_step(s, m, lane, nullptr);
+    if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
+    if (rf && ok) record_state(s, m, lane, vf, vt, rf);
+  }
+  if (ok && k >= 0) {
+    const EnvCtx ctx = make_ctx(B, (const int*)(st + ST_INTS));
+    ok = pd_torque(s, m, lane, ctx);
+    // J^T wrenches with the previous forward's Jacobians (stale cdof / com / geom_xpos)
+    const V3 org = ld3(s + S_ORG);
+    float qf = apply_ft(s, m, lane, v3(0.f, 0.f, m.hand_mass * 9.8f), v3(0, 0, 0), ld3(g + G_OFF(GPOS) + 3 * m.hand_geom0), m.palm_body);
+    if (m.residual_force) qf += apply_ft(s, m, lane, vf, vt, ld3(s + S_QPOS + m.nhand_q) - org, m.obj_body);
+    __syncwarp();
+    s[S_QAPP + lane] = qf;
+    // the state this forward is computed from: what the next env.step recomputes its stale quantities from
+    st[ST_PQPOS + lane] = s[S_QPOS + lane];
+    st[ST_PQVEL + lane] = s[S_QVEL + lane];
+    if (lane == 0) st[ST_PQPOS + 32] = s[S_QPOS + 32];
+    __syncwarp();
+    if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
+  }
+  if (ok) ok = phase_forward(s, m, lane, g + G_OFF(GPOS), g + G_OFF(GMAT)) || k < 0;   // a bad stale state was reported by the previous step already
+  if (ok) vel_stage(s, m, lane);
+  if (ok && k >= 0) {
+    ok = phase_smooth(s, m, lane);
+    if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
+  }
+  __syncwarp();
+  if (!es.live) return;
+  ST_FIELD(MISC);
+  if (k < 0) {
+    // scratch carries the CURRENT state into substep 0; the stale forward's derived quantities stay
+    for (int i = lane; i < H_NQ; i += 32) g[G_OFF(QPOS) + i] = i < 33 ? st[ST_QPOS + i] : 0.f;
+    g[G_OFF(QVEL) + lane] = st[ST_QVEL + lane];
+    g[G_OFF(WARM) + lane] = st[ST_WARM + lane];
+  } else {
+    ST_FIELD(QPOS); ST_FIELD(QVEL); ST_FIELD(WARM); ST_FIELD(SMOOTH); ST_FIELD(ASMOOTH);
+  }
+  ST_FIELD(ORG); ST_FIELD(COM); ST_FIELD(CDOF); ST_FIELD(BIAS); ST_FIELD(MS);
+  ST_FIELD(XPOS); ST_FIELD(XQUAT);   // read by the step tail (poses of the last forward) and by the test-mode record
+}
+
+static int g_p1_pad = -1;
+cudaError_t hoic_configure_p1() {
+  g_p1_pad = hoic_env_int("HOIC_P1_PAD", 0);
+  const size_t smem = hoic_step_smem(P1_W, g_p1_pad);
+  return cudaFuncSetAttribute(k_p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+cudaError_t hoic_launch_p1(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream) {
+  k_p1<<<hoic_step_grid(B, sp, P1_W), 32 * P1_W, hoic_step_smem(P1_W, g_p1_pad < 0 ? 0 : g_p1_pad), stream>>>(B, sp, actions, k);
+  return cudaGetLastError();
+}

@@ -1,0 +1,81 @@
+// k_p2.cu -- pipeline kernel 2 of env.step: mj_collision (analytic narrow phase + warp-cooperative MPR for meshes),
+// record_contact (ho_im4.py:883-889; the contacts of the forward BEFORE sim.step()) and mj_makeConstraint.
+// k = -1: contacts of the forward that preceded the step + the geom-pose snapshot of ho_im4.py:508-511.
+// The work per env depends on its contacts, so every env is its own CTA: the CTA scheduler balances the load.
+#define H_KERNEL HK_P2
+#include "hoic_step.cuh"
+
+#ifndef P2_W
+#define P2_W 8
+#endif
+#ifndef P2_WPS
+#define P2_WPS 16
+#endif
+
+// P2_W > 1: the warps of a CTA start collision together and meet again before the constraint rows, so that they fetch the
+// same (large) code at the same time; the kernel is instruction-fetch bound otherwise (profiles/README.md, r02).
+#if P2_W > 1
+#define P2_SYNC() __syncthreads()
+#else
+#define P2_SYNC() do { } while (0)
+#endif
+__global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, StepPart sp, int k) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P2_W + warp);
+  const int env = es.env;
+  float* s = smem + (size_t)warp * S_TOTAL;
+  float* g = B.scratch + (size_t)env * G_TOTAL;
+  const DevModel& m = *B.env_model[env];
+  int* misc = (int*)(s + S_MISC);
+  LD_FIELD(MISC); LD_FIELD(ORG); LD_FIELD(GPOS); LD_FIELD(GMAT);
+  if (k >= 0) { LD_FIELD(QPOS); LD_FIELD(QVEL); LD_FIELD(COM); LD_FIELD(CDOF); }
+  __syncwarp();
+  // work = this slot holds an env that is still running this step (k = -1: whose previous state had a forward)
+  const bool work = es.live && k < m.sim_step && (k < 0 ? !(misc[MI_FLAGS] & 1) : !env_dead(misc));
+  float* csum = B.csum + (size_t)env * CSUM_STRIDE;
+  unsigned c0 = 0, c1 = 0;
+  P2_SYNC();
+  if (work) {
+    collide(s, m, lane, c0, c1);
+    if (k + 1 < m.sim_step) record_contacts(s, m, lane, csum);
+    if (lane == 0) { misc[MI_C_MPRCALLS] += (int)c0; misc[MI_C_MPRITERS] += (int)c1; }
+  }
+  if (k < 0) {
+    if (!es.live || k >= m.sim_step) return;
+    if (work) {
+      // snapshot of the geom poses for the averaged velocities (ho_im4.py:508-511)
+      float* og = B.old_geom + (size_t)env * (HN * 12 + 4);
+      for (int i = lane; i < m.ngeom * 3; i += 32) og[i] = s[S_GPOS + i];
+      for (int i = lane; i < m.ngeom * 9; i += 32) og[HN * 3 + i] = s[S_GMAT + i];
+      if (lane < 3) og[HN * 12 + lane] = s[S_ORG + lane];
+    }
+    __syncwarp();
+    if (lane == 0) misc[MI_FLAGS] = 0;     // a bad stale state was reported by the previous step already
+    __syncwarp();
+    ST_FIELD(MISC);
+    return;
+  }
+  P2_SYNC();
+  if (!work) return;
+  build_rows(s, m, lane);
+  if (B.rec_frames) record_contact_frames(s, m, lane, B.rec_frames + ((size_t)env * m.sim_step + k) * HOIC_REC_STRIDE);
+  __syncwarp();
+  // the used part of the constraint stage -> global working set (input of the Newton solve)
+  const int nc = misc[MI_NCON], nb = misc[MI_NBASIS], nrow = H_RCON + ((misc[MI_NEDGE] + 31) & ~31);
+  ST_FIELD(MISC);
+  ST_U(B, nb * B_STRIDE);
+  ST_U(AREF, nrow); ST_U(D, nrow); ST_U(RINFO, nrow);
+  ST_U(BMASK, nb); ST_U(MPRQ, nb); ST_U(CINFO, nc * 8);      // (U_BINFO lives in the MPR queue's slots)
+  if (B.rec_frames) ST_U(CON, nc * 16);
+}
+
+static int g_p2_pad = -1;
+cudaError_t hoic_configure_p2() {
+  g_p2_pad = hoic_env_int("HOIC_P2_PAD", 0);
+  return cudaFuncSetAttribute(k_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hoic_step_smem(P2_W, g_p2_pad));
+}
+cudaError_t hoic_launch_p2(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
+  k_p2<<<hoic_step_grid(B, sp, P2_W), 32 * P2_W, hoic_step_smem(P2_W, g_p2_pad < 0 ? 0 : g_p2_pad), stream>>>(B, sp, k);
+  return cudaGetLastError();
+}

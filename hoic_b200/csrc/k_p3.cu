@@ -1,0 +1,88 @@
+// k_p3.cu -- pipeline kernel 3 of env.step: mj_fwdConstraint, the Newton solver of MuJoCo 2.1's soft-constraint model
+// (dev_solver.cuh; reference call site ho_im4.py:545).  The number of Newton iterations differs from env to env
+// (1: 54 %, 2: 18 %, 3: 18 %, 4+: 10 % of the solves), so every env is its own CTA and the CTA scheduler keeps the SMs
+// full while long solves finish.
+// Compiled twice: the SMALL tier (-DP3_SMALL) holds a constraint stage of 8 contacts / 24 basis rows / 32 pyramid edges
+// in shared memory (10 KB per env: 21 resident warps per SM) and solves the envs that fit, which is most of them; the
+// full tier (24 / 56 / 96, 16 KB per env) takes the rest.  Each env is solved by exactly one of the two launches.
+#define H_KERNEL HK_P3
+#ifdef P3_SMALL
+#define H_NCON 8
+#define H_NBASIS 24
+#define H_NEDGE 32
+#define K_P3 k_p3s
+#define P3_TIER 0
+#else
+#define K_P3 k_p3
+#define P3_TIER 1
+#endif
+#include "hoic_step.cuh"
+
+#define P3S_NCON 8
+#define P3S_NBASIS 24
+#define P3S_NEDGE 32
+#ifndef P3_W
+#define P3_W 1
+#endif
+#ifndef P3_WPS
+#ifdef P3_SMALL
+#define P3_WPS 21
+#else
+#define P3_WPS 14
+#endif
+#endif
+
+__global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, StepPart sp, int k) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P3_W + warp);
+  const int env = es.env;
+  if (!es.live) return;
+  float* s = smem + (size_t)warp * S_TOTAL;
+  float* g = B.scratch + (size_t)env * G_TOTAL;
+  const DevModel& m = *B.env_model[env];
+  int* misc = (int*)(s + S_MISC);
+  if (k >= m.sim_step) return;
+  LD_FIELD(MISC);
+  __syncwarp();
+  if (env_dead(misc)) return;
+  const int nc = misc[MI_NCON], nb = misc[MI_NBASIS], ne = misc[MI_NEDGE], nrow = H_RCON + ((ne + 31) & ~31);
+  if ((nc <= P3S_NCON && nb <= P3S_NBASIS && ne <= P3S_NEDGE) != (P3_TIER == 0)) return;    // the other tier's env
+  LD_FIELD(WARM); LD_FIELD(SMOOTH); LD_FIELD(ASMOOTH); LD_FIELD(MS);
+  LD_U(B, nb * B_STRIDE);
+  LD_U(AREF, nrow); LD_U(D, nrow); LD_U(RINFO, nrow);
+  LD_U(BMASK, nb); LD_U(MPRQ, nb); LD_U(CINFO, nc * 8);
+  __syncwarp();
+  Cnt cnt;
+  memset(&cnt, 0, sizeof cnt);
+  phase_solve(s, m, lane, cnt, true);
+  if (lane == 0) {
+    misc[MI_C_SUBSTEPS] += (int)cnt.substeps; misc[MI_C_NCON] += (int)cnt.ncon; misc[MI_C_NEFC] += (int)cnt.nefc;
+    misc[MI_C_NEWTON] += (int)cnt.newton; misc[MI_C_LS] += (int)cnt.ls;
+    misc[MI_C_MAXNCON] = max(misc[MI_C_MAXNCON], (int)cnt.max_ncon);
+    misc[MI_C_MAXNBASIS] = max(misc[MI_C_MAXNBASIS], (int)cnt.max_nbasis);
+    misc[MI_C_MAXNEDGE] = max(misc[MI_C_MAXNEDGE], (int)cnt.max_nedge);
+  }
+  __syncwarp();
+  ST_FIELD(MISC); ST_FIELD(QACC); ST_FIELD(FCON);
+  if (B.rec_frames) ST_U(FORCE, nrow);
+}
+
+static int g_p3_pad = -1;
+#ifdef P3_SMALL
+cudaError_t hoic_configure_p3s() {
+  g_p3_pad = hoic_env_int("HOIC_P3S_PAD", 0);
+#else
+cudaError_t hoic_configure_p3() {
+  g_p3_pad = hoic_env_int("HOIC_P3_PAD", 0);
+#endif
+  return cudaFuncSetAttribute(K_P3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hoic_step_smem(P3_W, g_p3_pad));
+}
+#ifdef P3_SMALL
+cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
+#else
+cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
+#endif
+  K_P3<<<hoic_step_grid(B, sp, P3_W), 32 * P3_W, hoic_step_smem(P3_W, g_p3_pad < 0 ? 0 : g_p3_pad), stream>>>(B, sp, k);
+  return cudaGetLastError();
+}

@@ -23,32 +23,61 @@ def _on() -> bool:
 
 
 class RolloutStats:
-    """Device-side sums of LoggerRL (logger_rl.py:28-67): steps, episodes, reward sum / min / max, 9-vector info sum."""
+    """Device-side LoggerRL (uhc/khrylib/rl/core/logger_rl.py:28-67) for a batch of envs stepping together: step / episode
+    counts, c_reward sum / min / max and the 9-vector info sum per step, and per EPISODE the reward sum with its min / max
+    (`episode_reward`, kept per env across rollouts so that an episode spanning two iterations is counted whole).
+    `finished` collects (motion_id, start_idx, percent) of the episodes that ended, the reference's `freq_dict` rows
+    (agent_handmimic.py:487-489)."""
 
-    def __init__(self, device):
+    def __init__(self, device, episode_reward=None):
         self.device = device
-        self.sums = torch.zeros(2 + 1 + 9, dtype=torch.float64, device=device)   # steps, episodes, reward, info[9]
-        self.minmax = torch.tensor([float("inf"), float("-inf")], dtype=torch.float64, device=device)
+        self.sums = torch.zeros(2 + 1 + 9 + 1, dtype=torch.float64, device=device)   # steps, episodes, reward, info[9], episode reward
+        self.minmax = torch.tensor([float("inf"), float("-inf"), float("inf"), float("-inf")], dtype=torch.float64, device=device)
+        self.episode_reward = episode_reward      # [N] running sums (float64), owned by the caller
+        self.finished = []
 
-    def update(self, reward, info, done):
+    def update(self, reward, info, done, motion_id=None, start_idx=None, percent=None):
         r = reward.to(torch.float64)
+        d = done.to(torch.bool)
         self.sums[0] += r.numel()
-        self.sums[1] += done.to(torch.float64).sum()
+        self.sums[1] += d.to(torch.float64).sum()
         self.sums[2] += r.sum()
-        self.sums[3:] += info.to(torch.float64).sum(0)
+        self.sums[3:12] += info.to(torch.float64).sum(0)
         self.minmax[0] = torch.minimum(self.minmax[0], r.min())
         self.minmax[1] = torch.maximum(self.minmax[1], r.max())
+        if self.episode_reward is not None:
+            self.episode_reward += r
+            ep = self.episode_reward
+            self.sums[12] += torch.where(d, ep, torch.zeros_like(ep)).sum()
+            self.minmax[2] = torch.minimum(self.minmax[2], torch.where(d, ep, torch.full_like(ep, float("inf"))).min())
+            self.minmax[3] = torch.maximum(self.minmax[3], torch.where(d, ep, torch.full_like(ep, float("-inf"))).max())
+            self.episode_reward.masked_fill_(d, 0.0)
+        if motion_id is not None:
+            self.finished.append((d.clone(), motion_id.clone(), start_idx.clone(), percent.clone()))
+
+    def freq_rows(self):
+        """[(motion_id, percent, start_idx)] of the finished episodes of this rank, on the host."""
+        rows = []
+        for d, mid, st, pc in self.finished:
+            idx = d.nonzero().squeeze(1)
+            if idx.numel():
+                rows.append(torch.stack([mid[idx].double(), pc[idx].double(), st[idx].double()], 1).cpu().numpy())
+        return np.concatenate(rows, 0) if rows else np.zeros((0, 3))
 
     def allreduce(self) -> dict:
-        s, mn, mx = self.sums.clone(), self.minmax[0:1].clone(), self.minmax[1:2].clone()
+        s, mn, mx = self.sums.clone(), self.minmax[0::2].clone(), self.minmax[1::2].clone()
         if _on():
             dist.all_reduce(s, op=dist.ReduceOp.SUM)
             dist.all_reduce(mn, op=dist.ReduceOp.MIN)
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        s = s.cpu().numpy()
-        return dict(num_steps=int(s[0]), num_episodes=int(s[1]), reward_sum=float(s[2]), info_sum=s[3:],
-                    reward_min=float(mn.item()), reward_max=float(mx.item()),
-                    avg_reward=float(s[2] / max(s[0], 1)))
+        s, mn, mx = s.cpu().numpy(), mn.cpu().numpy(), mx.cpu().numpy()
+        steps, eps = max(s[0], 1), max(s[1], 1)
+        return dict(num_steps=int(s[0]), num_episodes=int(s[1]), reward_sum=float(s[2]), info_sum=s[3:12],
+                    reward_min=float(mn[0]), reward_max=float(mx[0]), avg_reward=float(s[2] / steps),
+                    # LoggerRL names
+                    avg_c_reward=float(s[2] / steps), avg_c_info=s[3:12] / steps, avg_episode_len=float(s[0] / eps),
+                    total_reward=float(s[12]), avg_episode_reward=float(s[12] / eps), avg_episode_c_reward=float(s[2] / eps),
+                    min_episode_reward=float(mn[1]), max_episode_reward=float(mx[1]))
 
 
 def global_mean_std(x: torch.Tensor):
@@ -63,16 +92,30 @@ def global_mean_std(x: torch.Tensor):
     return float(mean), float(torch.sqrt(torch.clamp(var, min=0)))
 
 
+_flat_cache = {}
+
+
 def allreduce_grads(params):
-    """Average gradients across ranks (one flat buffer, one collective)."""
-    params = [p for p in params if p.grad is not None]
+    """Average gradients across ranks with ONE collective per network: the gradients of a network live as views into one
+    flat buffer (set up on first use, `p.grad` is re-pointed into it), so there is no gather / scatter copy around the
+    all-reduce."""
+    params = [p for p in params if p.requires_grad]
     if not _on() or not params:
         return
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    key = tuple(id(p) for p in params)
+    ent = _flat_cache.get(key)
+    if ent is None or any(p.grad is None or p.grad.data_ptr() != v.data_ptr() for p, v in zip(params, ent[1])):
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+        views, o = [], 0
+        for p in params:
+            v = flat[o:o + p.numel()].view_as(p)
+            if p.grad is not None:
+                v.copy_(p.grad)
+            p.grad = v
+            views.append(v)
+            o += p.numel()
+        ent = (flat, views)
+        _flat_cache[key] = ent
+    flat = ent[0]
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat /= dist.get_world_size()
-    o = 0
-    for p in params:
-        n = p.grad.numel()
-        p.grad.copy_(flat[o:o + n].view_as(p.grad))
-        o += n

@@ -74,73 +74,97 @@ class Value(nn.Module):
 
 
 class ZFilter:
-    """y = clip((x - mean) / (std + 1e-8), -clip, clip) with running statistics over every env (the reference only
-    keeps worker 0's statistics, SURVEY.md section 5 -- documented difference).  Batched Welford merge."""
+    """y = clip((x - mean) / (std + 1e-8), -clip, clip) with running statistics (uhc/khrylib/utils/zfilter.py:7-73), batched:
+    a [N, dim] batch is merged with Chan's parallel Welford update.  The accumulators are float64 like the reference's
+    numpy RunningStat, whatever dtype the observations have.  The statistics see every env (the reference keeps worker
+    0's, SURVEY.md section 5 -- documented difference).
+
+    Multi-rank: each rank also accumulates what it saw SINCE the last `allreduce()` in a separate (n, mean, M2) triple;
+    `allreduce()` pools those per-rank deltas and merges them into the pooled state of the previous sync.  (Pooling the
+    ranks' full statistics again and again would count the shared history `world` times per iteration.)"""
 
     def __init__(self, shape, clip=5.0, device="cpu", dtype=torch.float64):
-        self.n = torch.zeros((), dtype=dtype, device=device)
-        self.mean = torch.zeros(shape, dtype=dtype, device=device)
-        self.m2 = torch.zeros(shape, dtype=dtype, device=device)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=device)
+        self.n, self.mean, self.m2 = z(()), z(shape), z(shape)
+        self._dn, self._dmean, self._dm2 = z(()), z(shape), z(shape)     # since the last allreduce
+        self._bn, self._bmean, self._bm2 = z(()), z(shape), z(shape)     # pooled state at the last allreduce
         self.clip = clip
+        self.out_dtype = dtype
 
     @property
     def std(self):
         var = torch.where(self.n > 1, self.m2 / torch.clamp(self.n - 1, min=1), self.mean ** 2)
         return torch.sqrt(torch.clamp(var, min=0))
 
+    @staticmethod
+    def _merge(n, mean, m2, nb, bmean, bm2):
+        tot = n + nb
+        delta = bmean - mean
+        w = nb / torch.clamp(tot, min=1)
+        return tot, mean + delta * w, m2 + bm2 + delta ** 2 * (n * w)
+
     def update(self, x):
-        x = x.to(self.mean.dtype)
-        nb = x.shape[0]
+        x = x.to(torch.float64)
+        nb = torch.tensor(float(x.shape[0]), dtype=torch.float64, device=x.device)
         bmean = x.mean(0)
         bm2 = ((x - bmean) ** 2).sum(0)
-        tot = self.n + nb
-        delta = bmean - self.mean
-        self.mean = self.mean + delta * (nb / tot)
-        self.m2 = self.m2 + bm2 + delta ** 2 * (self.n * nb / tot)
-        self.n = tot
+        self.n, self.mean, self.m2 = self._merge(self.n, self.mean, self.m2, nb, bmean, bm2)
+        self._dn, self._dmean, self._dm2 = self._merge(self._dn, self._dmean, self._dm2, nb, bmean, bm2)
 
     def __call__(self, x, update=True):
         if update:
             self.update(x)
-        y = (x.to(self.mean.dtype) - self.mean) / (self.std + 1e-8)
+        y = (x.to(torch.float64) - self.mean) / (self.std + 1e-8)
         return torch.clamp(y, -self.clip, self.clip).to(x.dtype)
+
+    def set_state(self, n, mean, m2):
+        """Adopt pooled statistics (checkpoint load): they become the synced base, nothing is pending."""
+        dev = self.mean.device
+        self.n = torch.as_tensor(float(n), dtype=torch.float64, device=dev)
+        self.mean = torch.as_tensor(mean, dtype=torch.float64, device=dev).clone()
+        self.m2 = torch.as_tensor(m2, dtype=torch.float64, device=dev).clone()
+        self._bn, self._bmean, self._bm2 = self.n.clone(), self.mean.clone(), self.m2.clone()
+        self._dn, self._dmean, self._dm2 = torch.zeros_like(self.n), torch.zeros_like(self.mean), torch.zeros_like(self.m2)
 
     @staticmethod
     def merge_moments(parts):
-        """Pooled (n, mean, M2) of per-rank (n, mean, M2) triples: the arithmetic `allreduce` performs with collectives."""
+        """Pooled (n, mean, M2) of (n, mean, M2) triples: the arithmetic `allreduce` performs with collectives."""
         n = sum(p[0].double() for p in parts)
         mean = sum(p[1].double() * p[0].double() for p in parts) / torch.clamp(n, min=1)
         m2 = sum(p[2].double() + p[0].double() * (p[1].double() - mean) ** 2 for p in parts)
         return n, mean, torch.clamp(m2, min=0)
 
     def allreduce(self):
-        """Merge statistics across ranks: counts add, means pool, and the centred second moments combine as
-        M2 = sum_r [M2_r + n_r (mean_r - mean)^2] (Chan et al.), in float64.  Raw moments (sum of squares minus n mean^2)
-        cancel catastrophically in float32 and turned the std of (near-)constant observation entries into NaN."""
+        """Pool what the ranks saw since the last call (counts add, means pool, centred second moments combine as
+        M2 = sum_r [M2_r + n_r (mean_r - mean)^2], Chan et al.) and merge it into the previously pooled state."""
         if not hdist._on():
             return
         import torch.distributed as dist
-        dt = self.mean.dtype
-        n_r, mean_r, m2_r = self.n.double(), self.mean.double(), self.m2.double()
+        n_r, mean_r, m2_r = self._dn, self._dmean, self._dm2
         head = torch.cat([n_r.reshape(1), (mean_r * n_r).reshape(-1)])
         dist.all_reduce(head)
-        n = head[0]
-        mean = head[1:].reshape(mean_r.shape) / torch.clamp(n, min=1)
-        m2 = m2_r + n_r * (mean_r - mean) ** 2
-        dist.all_reduce(m2)
-        self.n, self.mean, self.m2 = n.to(dt), mean.to(dt), torch.clamp(m2, min=0).to(dt)
+        dn = head[0]
+        dmean = head[1:].reshape(mean_r.shape) / torch.clamp(dn, min=1)
+        dm2 = m2_r + n_r * (mean_r - dmean) ** 2
+        dist.all_reduce(dm2)
+        self.n, self.mean, self.m2 = self._merge(self._bn, self._bmean, self._bm2, dn, dmean, torch.clamp(dm2, min=0))
+        self._bn, self._bmean, self._bm2 = self.n.clone(), self.mean.clone(), self.m2.clone()
+        self._dn, self._dmean, self._dm2 = torch.zeros_like(self.n), torch.zeros_like(self.mean), torch.zeros_like(self.m2)
 
 
 def estimate_advantages(rewards, masks, values, gamma, tau):
     """GAE over time-major [T, N] tensors (common.py:5-25 applied per environment column).  `values` has T+1 rows: the
     last row bootstraps envs whose episode is still running when the fixed-horizon rollout stops (the reference only
-    stores complete episodes; SURVEY.md R21 documents this)."""
+    stores complete episodes; SURVEY.md R21 documents this).  A terminal transition (mask 0) SELECTS zero for the tail
+    terms instead of multiplying by the mask, so a non-finite value behind an episode boundary cannot cross it."""
     T = rewards.shape[0]
     adv = torch.zeros_like(rewards)
     last = torch.zeros_like(rewards[0])
+    zero = torch.zeros_like(last)
     for t in range(T - 1, -1, -1):
-        delta = rewards[t] + gamma * values[t + 1] * masks[t] - values[t]
-        last = delta + gamma * tau * last * masks[t]
+        live = masks[t] > 0
+        delta = rewards[t] + torch.where(live, gamma * values[t + 1], zero) - values[t]
+        last = delta + torch.where(live, gamma * tau * last, zero)
         adv[t] = last
     returns = values[:-1] + adv
     mean, std = hdist.global_mean_std(adv.reshape(-1))
@@ -157,7 +181,7 @@ def ppo_update(policy, value, opt_policy, opt_value, states, actions, returns, a
         ind = None
     for _ in range(num_epoch):
         vloss = (value(states) - returns).pow(2).mean()
-        opt_value.zero_grad(set_to_none=True)
+        opt_value.zero_grad(set_to_none=False)
         vloss.backward()
         hdist.allreduce_grads(value.parameters())
         opt_value.step()
@@ -170,7 +194,7 @@ def ppo_update(policy, value, opt_policy, opt_value, states, actions, returns, a
             ratio = torch.exp(log_probs - fixed_log_probs[ind])
             adv = advantages[ind]
         surr = -torch.min(ratio * adv, torch.clamp(ratio, 1.0 - clip_epsilon, 1.0 + clip_epsilon) * adv).mean()
-        opt_policy.zero_grad(set_to_none=True)
+        opt_policy.zero_grad(set_to_none=False)
         surr.backward()
         hdist.allreduce_grads(policy.parameters())
         torch.nn.utils.clip_grad_norm_(policy.parameters(), grad_clip)
@@ -261,10 +285,7 @@ def load_checkpoint(path, policy_net, value_net, running_state):
     policy_net.load_state_dict({k: torch.as_tensor(v).to(next(policy_net.parameters())) for k, v in cp["policy_dict"].items()})
     value_net.load_state_dict({k: torch.as_tensor(v).to(next(value_net.parameters())) for k, v in cp["value_dict"].items()})
     z = cp["running_state"]
-    dev, dt = running_state.mean.device, running_state.mean.dtype
-    running_state.n = torch.as_tensor(float(z.rs._n), dtype=dt, device=dev)
-    running_state.mean = torch.as_tensor(z.rs._M, dtype=dt, device=dev).clone()
-    running_state.m2 = torch.as_tensor(z.rs._S, dtype=dt, device=dev).clone()
+    running_state.set_state(z.rs._n, z.rs._M, z.rs._S)
     if z.clip:
         running_state.clip = float(z.clip)
     return cp

@@ -61,11 +61,14 @@ class HandMimicVecEnv:
         self.done = torch.zeros(N, dtype=torch.uint8, device=self.device)
         self.fail = torch.zeros(N, dtype=torch.uint8, device=self.device)
         self.end = torch.zeros(N, dtype=torch.uint8, device=self.device)
+        self._seed = int(seed)
+        self._hs = None
+        self._ep_mid = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self._ep_start = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self._ep_t = torch.zeros(N, dtype=torch.int32, device=self.device)
         self.set_motions(motions, motion_model)
         self.set_reward_weights(models[0].cfg.reward_vector())
         self.balance = balance
-        self._work = torch.zeros(N, dtype=torch.int32, device=self.device)
-        self._perm = None
 
     # ------------------------------------------------------------------ configuration
     def set_motions(self, motions, motion_model=None):
@@ -90,6 +93,12 @@ class HandMimicVecEnv:
         self._motion_table = torch.as_tensor(table, device=self.device)
         self._motion_count = torch.as_tensor([len(p) for p in per], device=self.device)
         self._env_model = torch.as_tensor(self.env_model_id.astype(np.int64), device=self.device)
+        # the same tables for the library's on-device sampler (auto-reset inside hoic_step, hoic_reset_sampled)
+        offs_m = np.concatenate([[0], np.cumsum([len(p) for p in per])]).astype(np.int32)
+        ids = np.ascontiguousarray(np.concatenate(per), dtype=np.int32)
+        capi.check(self.L.hoic_set_sampler(self._hb, capi.ptr(offs_m), capi.ptr(ids), 1 if self.random_start else 0,
+                                           int(self.min_episode), self._seed), "hoic_set_sampler")
+        self._hs = None     # the table may have been reallocated: a captured host-step graph holds stale pointers
 
     def set_motion_frames(self, frames):
         """Replace the frames of ALL motions in place: `frames` [n_motions, T, 212] with the same n_motions / T as the
@@ -108,6 +117,17 @@ class HandMimicVecEnv:
 
     def set_mode(self, mode):
         capi.check(self.L.hoic_set_mode(self._hb, 1 if mode == "train" else 0), "hoic_set_mode")
+        self._hs = None     # kernel arguments are baked into a captured graph: recapture
+
+    @property
+    def balance(self):
+        return self._balance
+
+    @balance.setter
+    def balance(self, on):
+        self._balance = bool(on)
+        capi.check(self.L.hoic_set_balance(self._hb, 1 if on else 0), "hoic_set_balance")
+        self._hs = None
 
     def set_record(self, on=True):
         """Test-mode recording of `MotionData` (ho_im4.py:27-41): with it on, every `step` also fills the per-substep
@@ -119,6 +139,7 @@ class HandMimicVecEnv:
         else:
             self._rec_frames = self._rec_surface = None
         capi.check(self.L.hoic_set_record(self._hb, capi.ptr(self._rec_frames), capi.ptr(self._rec_surface)), "hoic_set_record")
+        self._hs = None
 
     def motion_data(self):
         """Record of the last `step` as a dict of device tensors named like the reference's `MotionData` lists; the
@@ -141,7 +162,8 @@ class HandMimicVecEnv:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def sample_assignments(self):
-        """Random (motion_id, start_idx) per env, as agent_handmimic.py:439-448."""
+        """Random (motion_id, start_idx) per env, as agent_handmimic.py:439-448, drawn with torch's generator (explicit
+        resets; the auto-reset inside `step` and `reset()` without arguments use the library's on-device sampler)."""
         N = self.n_envs
         cnt = self._motion_count[self._env_model]
         u = torch.rand(N, device=self.device, generator=self.gen)
@@ -155,35 +177,48 @@ class HandMimicVecEnv:
             start = torch.zeros(N, dtype=torch.long, device=self.device)
         return mid.to(torch.int32).contiguous(), start.to(torch.int32).contiguous()
 
+    def _episode(self):
+        capi.check(self.L.hoic_get_episode(self._hb, capi.ptr(self._ep_mid), capi.ptr(self._ep_start), capi.ptr(self._ep_t),
+                                           self._stream()), "hoic_get_episode")
+
+    @property
+    def motion_id(self):
+        """Motion index of every env's current episode ([N] int32, device)."""
+        self._episode()
+        return self._ep_mid
+
+    @property
+    def start_idx(self):
+        self._episode()
+        return self._ep_start
+
+    @property
+    def cur_t(self):
+        self._episode()
+        return self._ep_t
+
     def reset(self, mask=None, motion_id=None, start_idx=None):
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
         if motion_id is None and start_idx is None:
-            motion_id, start_idx = self.sample_assignments()
+            capi.check(self.L.hoic_reset_sampled(self._hb, capi.ptr(mask), capi.ptr(self.obs), self._stream()), "hoic_reset_sampled")
+            return self.obs
         if motion_id is not None:
             motion_id = torch.as_tensor(motion_id, dtype=torch.int32, device=self.device).contiguous()
         if start_idx is not None:
             start_idx = torch.as_tensor(start_idx, dtype=torch.int32, device=self.device).contiguous()
-        if mask is not None:
-            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
         capi.check(self.L.hoic_reset(self._hb, capi.ptr(mask), capi.ptr(motion_id), capi.ptr(start_idx), capi.ptr(self.obs),
                                      self._stream()), "hoic_reset")
         return self.obs
 
     def step(self, actions):
+        """`env.step` for the whole batch: ONE library call (env ordering, the step pipeline and, with `auto_reset`, the
+        restart of finished envs on a freshly drawn episode all happen inside hoic_step)."""
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         assert a.shape == (self.n_envs, capi.ACT_DIM)
-        if self.balance and self.n_envs > 7:
-            # group envs of similar cost (last step's solver iterations / contacts) into the same CTA, most expensive
-            # CTAs first (longest-processing-time order: the last wave of the grid is the cheapest one)
-            capi.check(self.L.hoic_get_work(self._hb, capi.ptr(self._work), self._stream()), "hoic_get_work")
-            self._perm = torch.argsort(self._work, stable=True, descending=True).to(torch.int32)
-            capi.check(self.L.hoic_set_env_order(self._hb, capi.ptr(self._perm)), "hoic_set_env_order")
         capi.check(self.L.hoic_step(self._hb, capi.ptr(a), capi.ptr(self.obs), capi.ptr(self.reward), capi.ptr(self.reward_info),
                                     capi.ptr(self.done), capi.ptr(self.fail), capi.ptr(self.end), capi.ptr(self.percent),
-                                    self._stream()), "hoic_step")
-        if self.auto_reset:
-            mid, start = self.sample_assignments()
-            capi.check(self.L.hoic_reset(self._hb, capi.ptr(self.done), capi.ptr(mid), capi.ptr(start), capi.ptr(self.obs),
-                                         self._stream()), "hoic_reset")
+                                    1 if self.auto_reset else 0, self._stream()), "hoic_step")
         info = {"fail": self.fail, "end": self.end, "percent": self.percent, "reward_info": self.reward_info}
         return self.obs, self.reward, self.done, info
 
@@ -193,7 +228,7 @@ class HandMimicVecEnv:
         array / CPU tensor; returns (obs, reward, done, info) as pinned CPU tensors that stay valid until the next call.
         The H2D copy of the actions, env ordering, the step kernel, the in-place auto-reset and the D2H copies of the
         results are captured once into a CUDA graph and replayed as ONE launch per step."""
-        if getattr(self, "_hs", None) is None:
+        if self._hs is None:
             self._build_host_step()
         hs = self._hs
         src = torch.as_tensor(actions_host, dtype=torch.float32)
@@ -229,30 +264,22 @@ class HandMimicVecEnv:
         self.h2d_bytes = N * capi.ACT_DIM * 4
         self.d2h_bytes = N * (capi.OBS_DIM * 4 + 4 + 4 + capi.INFO_DIM * 4 + 3)
         try:
-            # warm up the torch ops of the body on a side stream without touching the environments, then capture
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
-            rng = self.gen.get_state()
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    self.sample_assignments()
-                    torch.argsort(self._work, stable=True, descending=True).to(torch.int32)
-                    self._hs["d_act"].copy_(self._hs["act"], non_blocking=True)
-                    self._hs["obs"].copy_(self.obs, non_blocking=True)
+            with torch.cuda.stream(side):      # warm up the copies of the body without touching the environments
+                self._hs["d_act"].copy_(self._hs["act"], non_blocking=True)
+                self._hs["obs"].copy_(self.obs, non_blocking=True)
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
-            self.gen.set_state(rng)
             g = torch.cuda.CUDAGraph()
-            g.register_generator_state(self.gen)
             with torch.cuda.graph(g, stream=side):
                 self._host_step_body()
             torch.cuda.synchronize(self.device)
             self._hs["graph"] = g
-        except Exception as e:                     # no graph support for this generator / torch build: plain launches
+        except Exception as e:                     # no graph support in this torch build: plain launches
             import warnings
             warnings.warn(f"step_host: CUDA graph capture unavailable ({e}); using eager launches")
             self._hs["graph"] = None
-
 
     def get_state(self):
         q = torch.empty(self.n_envs, capi.NQ, dtype=torch.float32, device=self.device)
@@ -318,6 +345,7 @@ class HandMimicVecEnv:
         return c.as_dict()
 
     def close(self):
+        self._hs = None
         if getattr(self, "_hb", None):
             self.L.hoic_batch_destroy(self._hb)
             self._hb = None

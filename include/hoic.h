@@ -117,12 +117,32 @@ int hoic_set_record(hoic_batch* b, float* frames, float* surface);
 int hoic_reset(hoic_batch* b, const uint8_t* mask, const int* motion_id, const int* start_idx, float* obs_out,
                void* stream);
 
+/* replaces the sampler's draw of the next episode (uhc/agents/agent_handmimic.py:437-452: seq_idx = randint(0, seq_num - 1),
+ * start_idx = randint(0, len - 200), env.set_expert(load_seq(...))) with an on-device draw: env i picks a uniform motion
+ * among those of its model, motion_ids_host[model_motion_offset_host[m] .. model_motion_offset_host[m + 1]) for model m
+ * (n_models + 1 offsets), and start_idx ~ U{0 .. len - min_episode - 1} (0 when random_start == 0).  The draws are a
+ * counter-based hash of (seed, env, episode number of the env): reproducible and independent of the batch order. */
+int hoic_set_sampler(hoic_batch* b, const int* model_motion_offset_host, const int* motion_ids_host, int random_start,
+                     int min_episode, unsigned long long seed);
+/* hoic_reset with (motion, start_idx) drawn by the sampler for every env with mask[i] != 0 (mask NULL = all) */
+int hoic_reset_sampled(hoic_batch* b, const uint8_t* mask, float* obs_out, void* stream);
+/* env.cur_t / the current expert assignment of every env (any pointer may be NULL) */
+int hoic_get_episode(hoic_batch* b, int* motion_id /*[N]*/, int* start_idx /*[N]*/, int* cur_t /*[N]*/, void* stream);
+
 /* replaces env.step(a) + custom_reward (ho_im4.py:611-662, ho_reward.py:943-1046, agent_handmimic.py:467-473):
  * 15 x [stable PD, gravity compensation + residual wrench, contact recording, mj_step], residual-force QP,
- * termination, reward 9, observation.  Any output pointer may be NULL. */
+ * termination, reward 9, observation.  Any output pointer may be NULL.
+ * auto_reset != 0 also runs the sampler's episode loop (agent_handmimic.py:437-454) for the envs that finished: they are
+ * reset to a (motion, start_idx) drawn by hoic_set_sampler and obs[i] is the reset observation (reward / done / fail /
+ * end / percent still describe the finished transition).  Needs `done`.
+ * A simulation that blows up (non-finite state, failed factorisation: MuJoCo's mjWARN_BADQACC -> MujocoException ->
+ * fail, ho_im4.py:635-637) is reported as fail with reward 0 and zero info / observation, and the env keeps the state it
+ * had before the step.
+ * The call launches a pipeline of kernels (per physics substep: smooth dynamics, collision + constraint rows, Newton
+ * solve) on internal streams forked from / joined to `stream`; it is capturable into a CUDA graph. */
 int hoic_step(hoic_batch* b, const float* actions /*[N][32]*/, float* obs /*[N][617]*/, float* reward /*[N]*/,
               float* reward_info /*[N][9]*/, uint8_t* done /*[N]*/, uint8_t* fail /*[N]*/, uint8_t* end /*[N]*/,
-              float* percent /*[N]*/, void* stream);
+              float* percent /*[N]*/, int auto_reset, void* stream);
 
 /* replaces sim.get_state() / data.qpos, data.qvel reads (mujoco_env.py:109, ho_im4.py:794-804) */
 int hoic_get_state(hoic_batch* b, float* qpos /*[N][33]*/, float* qvel /*[N][32]*/, void* stream);
@@ -148,11 +168,14 @@ int hoic_get_derived(hoic_batch* b, float* xpos, float* xquat, float* qM, float*
 /* per-step scalars of the last hoic_step: [N][8] = rfc_score, rest_force[3], rest_torque[3], n contact geoms */
 int hoic_get_rfc(hoic_batch* b, float* out, void* stream);
 
-/* load balancing across CTAs: work[N] = cost proxy of each env's last step (solver iterations, contacts, QP size);
- * hoic_set_env_order installs a device permutation (NULL = identity) so that a CTA steps envs of similar cost.
- * Results do not depend on the order. */
+/* load balancing: every kernel of the step pipeline schedules one env per CTA in `order`; by default (batches of 8+
+ * envs) hoic_step sorts the envs by the cost proxy of their last step, most expensive first (longest-processing-time
+ * order), in a small kernel of its own.  hoic_set_balance(0) switches that off (identity order); hoic_set_env_order
+ * installs a caller-owned device permutation instead (NULL = back to the library's choice); hoic_get_work exports the
+ * cost proxy work[N] (solver iterations, contacts, MPR iterations, QP size).  Results do not depend on the order. */
 int hoic_get_work(hoic_batch* b, int* work /*[N]*/, void* stream);
 int hoic_set_env_order(hoic_batch* b, const int* perm /*[N] device, kept by reference*/);
+int hoic_set_balance(hoic_batch* b, int on);
 
 /* integer work counters accumulated by the kernels since creation (synchronises the device) */
 int hoic_get_counters(hoic_batch* b, hoic_counters* out_host);

@@ -61,6 +61,30 @@ assert torch.allclose(zf.std.double()[3:], one.std[3:], rtol=1e-4) and float(zf.
 assert abs(float(zf.std[1]) - float(one.std[1])) < 1e-3
 y = zf(torch.as_tensor(x[:8]), update=False)
 assert torch.isfinite(y).all()
+# repeated rollouts: update / allreduce every iteration (agent.sample).  Each rank must end up with the statistics of
+# ALL samples seen so far counted ONCE (pooling full per-rank statistics again would count the shared history `world`
+# times per iteration and freeze the normaliser).
+zr = ppo.ZFilter((6,), clip=5.0)
+single = ppo.ZFilter((6,), clip=5.0)
+seen = 0
+for it in range(5):
+    xi = (rng.randn(300, 6) * (1 + it) + it).astype(np.float32)
+    for chunk in np.array_split(xi[rank::2], 3):
+        zr(torch.as_tensor(chunk))
+    zr.allreduce()
+    single(torch.as_tensor(xi))
+    seen += 300
+    assert float(zr.n) == seen, (float(zr.n), seen)
+    assert torch.allclose(zr.mean, single.mean, rtol=1e-10, atol=1e-10) and torch.allclose(zr.std, single.std, rtol=1e-10)
+# flat-buffer gradient averaging survives a second backward pass (the grads stay views of the flat buffer)
+lin = torch.nn.Linear(3, 2)
+torch.manual_seed(7)
+for q in lin.parameters(): torch.nn.init.constant_(q, 0.5)
+for rep in range(2):
+    lin.zero_grad(set_to_none=False)
+    (lin(torch.full((1, 3), float(rank + 1 + rep))).sum()).backward()
+    hd.allreduce_grads(lin.parameters())
+    assert torch.allclose(lin.weight.grad, torch.full((2, 3), 1.5 + rep)), lin.weight.grad
 dist.destroy_process_group()
 print("OK", rank)
 '''

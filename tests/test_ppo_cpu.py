@@ -173,8 +173,74 @@ def test_zfilter_merge_of_eight_float32_ranks_stays_finite():
     assert float(n) == 768 and torch.isfinite(std).all() and (m2 >= 0).all()
     assert torch.allclose(mean, ref.mean(0), atol=1e-6) and torch.allclose(std[3:], ref.std(0)[3:], rtol=2e-3)
     assert float(std[0]) < 1e-6 and float(std[2]) == 0.0 and abs(float(std[1]) - float(ref.std(0)[1])) < 1e-6
-    # the raw-moment merge this replaces does fail on the same input
-    nn = sum(p[0] for p in parts)
-    m = sum(p[1] * p[0] for p in parts) / nn
-    raw = sum(p[2] + p[1] ** 2 * p[0] for p in parts) - m ** 2 * nn
-    assert (raw < 0).any()
+    # accumulators are float64 whatever dtype the observations have (zfilter.py:7-24 is numpy float64)
+    assert parts[0][1].dtype == torch.float64 and parts[0][0].dtype == torch.float64
+
+
+def test_gae_terminal_transition_isolates_non_finite_tail():
+    """A NaN / inf value or reward BEHIND an episode boundary must not leak across it (mask 0 selects zero, it does not
+    multiply): one blown-up env may not poison the batch (common.py:5-25 semantics otherwise unchanged)."""
+    T, N = 6, 3
+    rng = np.random.RandomState(3)
+    rewards = torch.as_tensor(rng.rand(T, N))
+    values = torch.as_tensor(rng.rand(T + 1, N))
+    masks = torch.ones(T, N, dtype=torch.float64)
+    masks[2, 1] = 0.0                       # env 1: episode ends at t = 2, the next one is garbage from t = 3 on
+    clean_adv, clean_ret = ppo.estimate_advantages(rewards, masks, values, 0.95, 0.95)
+    values2 = values.clone()
+    values2[3, 1] = float("nan")            # V(s_3) of the NEXT episode
+    adv, ret = ppo.estimate_advantages(rewards, masks, values2, 0.95, 0.95)
+    # the transitions of env 1 up to its terminal step see none of it (returns are un-normalised: exact)
+    assert torch.isfinite(ret[:3, 1]).all() and torch.allclose(ret[:3, 1], clean_ret[:3, 1])
+    assert torch.isfinite(ret[:, 0]).all() and torch.isfinite(ret[:, 2]).all()
+
+
+def test_end_reward_and_logger_statistics_follow_the_reference():
+    """`reward += env.end_reward` on info["end"] with env.end_reward = avg_c_reward gamma / (1 - gamma) of the PREVIOUS
+    iteration (agent_handmimic.py:317-319, 478-480), and LoggerRL's per-episode statistics (logger_rl.py:28-67), against a
+    transcription of the reference's sequential loop on a scripted environment."""
+    from hoic_b200 import dist as hd
+    rng = np.random.RandomState(5)
+    T, N, gamma = 40, 4, 0.95
+    rew = rng.rand(T, N)
+    done = rng.rand(T, N) < 0.15
+    end = done & (rng.rand(T, N) < 0.5)
+    info = rng.rand(T, N, 9)
+    end_reward = 0.7 * gamma / (1 - gamma)
+    # --- reference: per env, sequential episodes
+    ref_train = np.zeros((T, N))
+    n_steps = n_eps = 0
+    total_c = total_ep = 0.0
+    mn_ep, mx_ep = np.inf, -np.inf
+    for e in range(N):
+        ep = 0.0
+        for t in range(T):
+            c_reward = rew[t, e]
+            reward = c_reward + (end_reward if end[t, e] else 0.0)      # :478-480
+            ep += c_reward                                               # LoggerRL.step sees env_reward = c_reward here
+            total_c += c_reward
+            n_steps += 1
+            ref_train[t, e] = reward
+            if done[t, e]:
+                n_eps += 1
+                total_ep += ep
+                mn_ep, mx_ep = min(mn_ep, ep), max(mx_ep, ep)
+                ep = 0.0
+    # --- batched
+    ep_acc = torch.zeros(N, dtype=torch.float64)
+    st = hd.RolloutStats("cpu", episode_reward=ep_acc)
+    train = np.zeros((T, N))
+    for t in range(T):
+        r = torch.as_tensor(rew[t])
+        train[t] = (r + end_reward * torch.as_tensor(end[t]).to(r.dtype)).numpy()
+        st.update(r, torch.as_tensor(info[t]), torch.as_tensor(done[t]), torch.zeros(N, dtype=torch.int32),
+                  torch.zeros(N, dtype=torch.int32), torch.as_tensor(rng.rand(N)))
+    log = st.allreduce()
+    assert np.allclose(train, ref_train)
+    assert log["num_steps"] == n_steps and log["num_episodes"] == n_eps
+    assert abs(log["avg_c_reward"] - total_c / n_steps) < 1e-12 and abs(log["avg_episode_len"] - n_steps / n_eps) < 1e-12
+    assert abs(log["avg_episode_reward"] - total_ep / n_eps) < 1e-12
+    assert abs(log["min_episode_reward"] - mn_ep) < 1e-12 and abs(log["max_episode_reward"] - mx_ep) < 1e-12
+    assert st.freq_rows().shape == (n_eps, 3)
+    # next iteration's end reward
+    assert abs(log["avg_c_reward"] * gamma / (1 - gamma) - (total_c / n_steps) * gamma / (1 - gamma)) < 1e-12

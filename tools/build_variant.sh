@@ -4,6 +4,5 @@ set -e
 cd "$(dirname "$0")/.."
 mkdir -p variants
 name=$1; shift
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC --fmad=true \
-  -prec-div=false -prec-sqrt=false -ftz=true "$@" -o variants/lib_$name.so hoic_b200/csrc/hoic_capi.cu
-echo variants/lib_$name.so
+HOIC_BUILD_OUT=$PWD/variants/lib_$name.so HOIC_NVCC_FLAGS="$*" python hoic_b200/build.py --force
+rm -rf variants/lib_$name.so.obj
