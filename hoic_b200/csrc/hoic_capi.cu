@@ -338,8 +338,8 @@ struct hoic_batch {
   int motions_cap = 0, nsub = 0;
   // hoic_step runs the batch as `nparts` interleaved parts on internal streams (fork / join around the caller's stream)
   int nparts = 1;
-  cudaStream_t part_stream[HOIC_MAX_PARTS] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[HOIC_MAX_PARTS] = {};
+  cudaStream_t part_stream[HOIC_MAX_PARTS] = {}, aux_stream[HOIC_MAX_PARTS] = {};   // aux: the solver's full-capacity tier
+  cudaEvent_t ev_fork = nullptr, ev_join[HOIC_MAX_PARTS] = {}, ev_rows[HOIC_MAX_PARTS] = {}, ev_aux[HOIC_MAX_PARTS] = {};
 };
 
 extern "C" const char* hoic_last_error(void) { return g_err.c_str(); }
@@ -787,12 +787,13 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     int want = n_envs >= 1024 ? 2 : 1;
     if (const char* e = getenv("HOIC_STEP_PARTS")) want = atoi(e);
     b->nparts = std::min(std::max(want, 1), HOIC_MAX_PARTS);
-    if (b->nparts > 1) {
-      CUDA_OKP(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
-      for (int j = 0; j < b->nparts; j++) {
-        CUDA_OKP(cudaStreamCreateWithFlags(&b->part_stream[j], cudaStreamNonBlocking));
-        CUDA_OKP(cudaEventCreateWithFlags(&b->ev_join[j], cudaEventDisableTiming));
-      }
+    CUDA_OKP(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    for (int j = 0; j < b->nparts; j++) {
+      CUDA_OKP(cudaStreamCreateWithFlags(&b->part_stream[j], cudaStreamNonBlocking));
+      CUDA_OKP(cudaStreamCreateWithFlags(&b->aux_stream[j], cudaStreamNonBlocking));
+      CUDA_OKP(cudaEventCreateWithFlags(&b->ev_join[j], cudaEventDisableTiming));
+      CUDA_OKP(cudaEventCreateWithFlags(&b->ev_rows[j], cudaEventDisableTiming));
+      CUDA_OKP(cudaEventCreateWithFlags(&b->ev_aux[j], cudaEventDisableTiming));
     }
   }
   {
@@ -814,7 +815,13 @@ extern "C" void hoic_batch_destroy(hoic_batch* b) {
   cudaSetDevice(b->device);
   cudaDeviceSynchronize();
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
-  for (int j = 0; j < HOIC_MAX_PARTS; j++) { if (b->ev_join[j]) cudaEventDestroy(b->ev_join[j]); if (b->part_stream[j]) cudaStreamDestroy(b->part_stream[j]); }
+  for (int j = 0; j < HOIC_MAX_PARTS; j++) {
+    if (b->ev_join[j]) cudaEventDestroy(b->ev_join[j]);
+    if (b->ev_rows[j]) cudaEventDestroy(b->ev_rows[j]);
+    if (b->ev_aux[j]) cudaEventDestroy(b->ev_aux[j]);
+    if (b->part_stream[j]) cudaStreamDestroy(b->part_stream[j]);
+    if (b->aux_stream[j]) cudaStreamDestroy(b->aux_stream[j]);
+  }
   cudaFree(b->env_model_dev); cudaFree(b->b.scratch); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum);
   cudaFree(b->env_model_idx); cudaFree(b->samp_off); cudaFree(b->samp_ids); cudaFree(b->order);
   cudaFree(b->reward_w); cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
@@ -947,23 +954,29 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
   cudaStream_t user = (cudaStream_t)stream;
   const int np = b->nparts;
 #define STEP_LAUNCH(call) do { cudaError_t e_ = (call); g_launches++; if (e_ != cudaSuccess) return set_err(std::string("kernel launch (" #call "): ") + cudaGetErrorString(e_)); } while (0)
-#define STEP_PARTS(call) do { for (int j = 0; j < np; j++) { const StepPart sp = {j, np}; cudaStream_t sm = np > 1 ? b->part_stream[j] : user; STEP_LAUNCH(call); } } while (0)
-  if (np > 1) {
-    CUDA_OK(cudaEventRecord(b->ev_fork, user));
-    for (int j = 0; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_fork, 0));
-  }
+#define STEP_PARTS(call) do { for (int j = 0; j < np; j++) { const StepPart sp = {j, np}; cudaStream_t sm = b->part_stream[j]; STEP_LAUNCH(call); } } while (0)
+  // fork: every part runs on its own stream; the caller's stream waits for all of them at the end
+  CUDA_OK(cudaEventRecord(b->ev_fork, user));
+  for (int j = 0; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_fork, 0));
   STEP_PARTS(hoic_launch_p1(b->b, sp, actions, -1, sm));
   STEP_PARTS(hoic_launch_p2(b->b, sp, -1, sm));
   for (int k = 0; k < b->nsub; k++) {
     STEP_PARTS(hoic_launch_p1(b->b, sp, actions, k, sm));
     STEP_PARTS(hoic_launch_p2(b->b, sp, k, sm));
-    STEP_PARTS(hoic_launch_p3s(b->b, sp, k, sm));
-    STEP_PARTS(hoic_launch_p3(b->b, sp, k, sm));
+    // the two capacity tiers of the solver take disjoint envs: side by side (the few long solves of the full tier would
+    // otherwise sit on every substep's critical path)
+    for (int j = 0; j < np; j++) {
+      const StepPart sp = {j, np};
+      CUDA_OK(cudaEventRecord(b->ev_rows[j], b->part_stream[j]));
+      CUDA_OK(cudaStreamWaitEvent(b->aux_stream[j], b->ev_rows[j], 0));
+      STEP_LAUNCH(hoic_launch_p3(b->b, sp, k, b->aux_stream[j]));
+      CUDA_OK(cudaEventRecord(b->ev_aux[j], b->aux_stream[j]));
+      STEP_LAUNCH(hoic_launch_p3s(b->b, sp, k, b->part_stream[j]));
+      CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_aux[j], 0));
+    }
   }
   STEP_PARTS(hoic_launch_tail(b->b, sp, actions, o, sm));
-  if (np > 1) {
-    for (int j = 0; j < np; j++) { CUDA_OK(cudaEventRecord(b->ev_join[j], b->part_stream[j])); CUDA_OK(cudaStreamWaitEvent(user, b->ev_join[j], 0)); }
-  }
+  for (int j = 0; j < np; j++) { CUDA_OK(cudaEventRecord(b->ev_join[j], b->part_stream[j])); CUDA_OK(cudaStreamWaitEvent(user, b->ev_join[j], 0)); }
 #undef STEP_PARTS
   if (auto_reset) {
     // the sampler's episode loop (agent_handmimic.py:437-454): a finished env restarts on a freshly drawn (motion, start)

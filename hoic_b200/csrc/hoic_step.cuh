@@ -14,10 +14,22 @@ __device__ __forceinline__ void cpf(float* dst, const float* src, int n, int lan
   float4* d4 = reinterpret_cast<float4*>(dst);
   for (int i = lane; i < (n >> 2); i += 32) d4[i] = s4[i];
 }
-#define LD_FIELD(name) cpf(s + S_OFF(name), g + G_OFF(name), F_SIZE(name), lane)
+// global -> shared without a round trip through registers (LDGSTS): every copy of a kernel's load phase is in flight at
+// once; ld_wait() before the first read.  The working set was written by an earlier kernel, so bypassing L1 (.cg) is safe
+// and keeps L1 for the model constants.
+__device__ __forceinline__ void ldf(float* dst_smem, const float* src, int n, int lane) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  for (int i = lane; i < (n >> 2); i += 32)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * i), "l"(src + 4 * i) : "memory");
+}
+__device__ __forceinline__ void ld_wait() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+#define LD_FIELD(name) ldf(s + S_OFF(name), g + G_OFF(name), F_SIZE(name), lane)
 #define ST_FIELD(name) cpf(g + G_OFF(name), s + S_OFF(name), F_SIZE(name), lane)
 // first n floats of a constraint-stage array (name as in UL_*: B, AREF, D, ...)
-#define LD_U(f, n) cpf(s + U_S(f), g + U_G(f), ((n) + 3) & ~3, lane)
+#define LD_U(f, n) ldf(s + U_S(f), g + U_G(f), ((n) + 3) & ~3, lane)
 #define ST_U(f, n) cpf(g + U_G(f), s + U_S(f), ((n) + 3) & ~3, lane)
 
 struct EnvSlot {

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) k_p1(BatchDev B, Ste
       const float a = lane < m.nu + (m.residual_force ? 6 : 0) ? actions[(size_t)env * HOIC_ACT_DIM + lane] : 0.f;
       s[S_ACT + lane] = fminf(fmaxf(a, -1.f), 1.f);
     }
-    __syncwarp();
+    ld_wait();
     if (!ok || env_dead(misc)) return;    // failed earlier in this step: the working set stays as it was
   }
   const V3 vf = (k >= 0 && m.residual_force) ? ld3(s + S_ACT + m.nu) * m.rf_scale : v3(0, 0, 0);

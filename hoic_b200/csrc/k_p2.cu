@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, Ste
   int* misc = (int*)(s + S_MISC);
   LD_FIELD(MISC); LD_FIELD(ORG); LD_FIELD(GPOS); LD_FIELD(GMAT);
   if (k >= 0) { LD_FIELD(QPOS); LD_FIELD(QVEL); LD_FIELD(COM); LD_FIELD(CDOF); }
-  __syncwarp();
+  ld_wait();
   // work = this slot holds an env that is still running this step (k = -1: whose previous state had a forward)
   const bool work = es.live && k < m.sim_step && (k < 0 ? !(misc[MI_FLAGS] & 1) : !env_dead(misc));
   float* csum = B.csum + (size_t)env * CSUM_STRIDE;

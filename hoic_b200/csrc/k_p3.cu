@@ -43,16 +43,23 @@ __global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, Ste
   const DevModel& m = *B.env_model[env];
   int* misc = (int*)(s + S_MISC);
   if (k >= m.sim_step) return;
-  LD_FIELD(MISC);
-  __syncwarp();
+  LD_FIELD(MISC); LD_FIELD(WARM); LD_FIELD(SMOOTH); LD_FIELD(ASMOOTH); LD_FIELD(MS);
+#ifdef P3_SMALL
+  // the small tier's whole constraint stage is 3 KB: fetch it at capacity in the same round trip as the counts
+  LD_U(B, H_NBASIS * B_STRIDE);
+  LD_U(AREF, H_NROW); LD_U(D, H_NROW); LD_U(RINFO, H_NROW);
+  LD_U(BMASK, H_NBASIS); LD_U(MPRQ, H_NBASIS); LD_U(CINFO, H_NCON * 8);
+#endif
+  ld_wait();
   if (env_dead(misc)) return;
   const int nc = misc[MI_NCON], nb = misc[MI_NBASIS], ne = misc[MI_NEDGE], nrow = H_RCON + ((ne + 31) & ~31);
   if ((nc <= P3S_NCON && nb <= P3S_NBASIS && ne <= P3S_NEDGE) != (P3_TIER == 0)) return;    // the other tier's env
-  LD_FIELD(WARM); LD_FIELD(SMOOTH); LD_FIELD(ASMOOTH); LD_FIELD(MS);
+#ifndef P3_SMALL
   LD_U(B, nb * B_STRIDE);
   LD_U(AREF, nrow); LD_U(D, nrow); LD_U(RINFO, nrow);
   LD_U(BMASK, nb); LD_U(MPRQ, nb); LD_U(CINFO, nc * 8);
-  __syncwarp();
+  ld_wait();
+#endif
   Cnt cnt;
   memset(&cnt, 0, sizeof cnt);
   phase_solve(s, m, lane, cnt, true);

@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(32 * PT_W, PT_WPS / PT_W) k_tail(BatchDev B, S
   const DevModel& m = *B.env_model[env];
   int* misc = (int*)(s + S_MISC);
   LD_FIELD(MISC); LD_FIELD(QPOS); LD_FIELD(QVEL); LD_FIELD(WARM); LD_FIELD(ORG); LD_FIELD(XPOS); LD_FIELD(XQUAT); LD_FIELD(GPOS);
-  LD_FIELD(GMAT);
-  __syncwarp();
+  LD_FIELD(GMAT); LD_FIELD(QACC); LD_FIELD(SMOOTH); LD_FIELD(FCON); LD_FIELD(MS);
+  ld_wait();
   bool ok = !env_dead(misc);
   float* recf = B.rec_frames ? B.rec_frames + ((size_t)env * m.sim_step + (m.sim_step - 1)) * HOIC_REC_STRIDE : nullptr;
   float* surf = B.rec_surface ? B.rec_surface + (size_t)env * HOIC_SURF_STRIDE : nullptr;
@@ -39,8 +39,6 @@ __global__ void __launch_bounds__(32 * PT_W, PT_WPS / PT_W) k_tail(BatchDev B, S
   }
   const float old_obj_vel = (lane >= m.nv - 6 && lane < m.nv) ? st[ST_QVEL + lane] : 0.f;   // state at the start of the step
   if (ok) {
-    LD_FIELD(QACC); LD_FIELD(SMOOTH); LD_FIELD(FCON); LD_FIELD(MS);
-    __syncwarp();
     if (recf) record_forward(s, m, lane, recf, g + U_G(CON), g + U_G(FORCE), g + U_G(CINFO));
     ok = euler_step(s, m, lane, nullptr);
     if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
