@@ -20,6 +20,7 @@ import torch
 
 from . import dist as hdist
 from . import ppo
+from .sampler import SamplerStep, matmul_context
 from .vecenv import HandMimicVecEnv
 
 
@@ -39,7 +40,7 @@ class TrajBatch:
 
 class AgentHandMimic:
     def __init__(self, models, n_envs, motions=None, motion_model=None, env_model_id=None, device=0, seed=None, cfg=None,
-                 policy_grad_clip=40.0):
+                 policy_grad_clip=40.0, policy_dtype="bf16", graph=True):
         models = [models] if not isinstance(models, (list, tuple)) else list(models)
         self.cfg = cfg or models[0].cfg
         cfg = self.cfg
@@ -80,6 +81,11 @@ class AgentHandMimic:
         # its finished episodes, the newest `max_freq` kept
         self.freq_dict = {k: [] for k in range(len(motions))}
         self.max_freq = 50
+        # the sampler's inner loop as one CUDA graph; MLPs on the tensor cores (bf16 operands, fp32 accumulate and master weights)
+        self.policy_dtype = policy_dtype
+        self.stats = hdist.RolloutStats(self.device, episode_reward=self._episode_reward)
+        self.sampler = SamplerStep(self.env, self.policy_net, self.running_state, self.gen, stats=self.stats,
+                                   policy_dtype=policy_dtype, graph=graph)
 
     # ------------------------------------------------------------------ agent_handmimic.py:264-282
     def per_epoch_update(self, epoch):
@@ -100,36 +106,30 @@ class AgentHandMimic:
         env.set_mode("train")
         T = max(1, math.ceil(min_batch_size / (N * self.world)))
         batch = TrajBatch(T, N, env.obs_dim, env.act_dim, self.device)
-        stats = hdist.RolloutStats(self.device, episode_reward=self._episode_reward)
+        s = self.sampler
         if self._obs is None:
             self._obs = env.reset()
-        obs = self._obs
+            s.warmup()                     # (three policy steps whose transitions are dropped, then the graph exists)
+        s.set_noise_rate(self.noise_rate)
+        stats = self.stats
+        stats.reset()
         use_end = bool(self.cfg.end_reward) and self.end_reward != 0.0
+        ep = dict(done=torch.empty(T, N, dtype=torch.uint8, device=self.device), mid=torch.empty(T, N, dtype=torch.int32, device=self.device),
+                  start=torch.empty(T, N, dtype=torch.int32, device=self.device), percent=torch.empty(T, N, device=self.device))
         for t in range(T):
-            x = self.running_state(obs)
-            mean, log_std = self.policy_net(x)
-            noise = torch.randn(mean.shape, device=self.device, dtype=mean.dtype, generator=self.gen)
-            if self.noise_rate < 1.0:
-                # mean_action = binomial(1, 1 - noise_rate) per (env, step); exp = 1 - mean_action (:464-465, :484)
-                exp = (torch.rand(N, device=self.device, generator=self.gen) < self.noise_rate).to(torch.float32)
-            else:
-                exp = torch.ones(N, device=self.device)
-            act = mean + torch.exp(log_std) * noise * exp[:, None]
-            batch.states[t] = x
-            batch.actions[t] = act
-            batch.exps[t] = exp
-            mid, start = env.motion_id.clone(), env.start_idx.clone()     # of the episode this step belongs to
-            obs, r, done, info = env.step(act)
-            r = torch.nan_to_num(r, nan=0.0, posinf=0.0, neginf=0.0)      # (the library already reports a finite reward)
+            s.step()
+            batch.states[t].copy_(s.x)
+            batch.actions[t].copy_(s.act)
+            batch.exps[t].copy_(s.exp)
             # `reward += env.end_reward` on info["end"] (agent_handmimic.py:478-480); the logger sees c_reward without it
-            batch.rewards[t] = r + self.end_reward * info["end"].to(r.dtype) if use_end else r
-            batch.masks[t] = 1.0 - done.to(torch.float32)
-            stats.update(r, info["reward_info"], done, mid, start, info["percent"])
-        self._obs = obs
-        batch.last_state = self.running_state(obs, update=False)
+            batch.rewards[t] = env.reward + self.end_reward * env.end.to(torch.float32) if use_end else env.reward
+            batch.masks[t] = 1.0 - env.done.to(torch.float32)
+            ep["done"][t].copy_(env.done); ep["mid"][t].copy_(s.motion_id); ep["start"][t].copy_(s.start_idx)
+            ep["percent"][t].copy_(env.percent)
+        self._obs = env.obs
+        batch.last_state = self.running_state(env.obs, update=False).to(torch.float32)
         self.running_state.allreduce()
-        rows = stats.freq_rows()
-        for k, pc, st in rows:
+        for k, pc, st in stats.freq_rows([(ep["done"], ep["mid"], ep["start"], ep["percent"])]):
             self.freq_dict.setdefault(int(k), []).append([float(pc), int(st)])
         self.freq_dict = {k: v[-self.max_freq:] for k, v in self.freq_dict.items()}
         return batch, stats
@@ -140,11 +140,16 @@ class AgentHandMimic:
         T, N = batch.T, batch.N
         states = batch.states.reshape(T * N, -1)
         actions = batch.actions.reshape(T * N, -1)
-        with torch.no_grad():
-            values = self.value_net(torch.cat([states, batch.last_state], 0)).reshape(T + 1, N)
+        with torch.no_grad(), matmul_context(self.policy_dtype):
+            values = self.value_net(torch.cat([states, batch.last_state], 0)).float().reshape(T + 1, N)
             adv, ret = ppo.estimate_advantages(batch.rewards, batch.masks, values, cfg.gamma, cfg.tau)
-            fixed_log_probs = self.policy_net.get_log_prob(states, actions)
+            fixed_log_probs = self.policy_net.get_log_prob(states, actions).float()
         ind = batch.exps.reshape(-1).nonzero().squeeze(1)
+        with matmul_context(self.policy_dtype):
+            return self._ppo_update(states, actions, ret, adv, fixed_log_probs, ind)
+
+    def _ppo_update(self, states, actions, ret, adv, fixed_log_probs, ind):
+        cfg = self.cfg
         return ppo.ppo_update(self.policy_net, self.value_net, self.optimizer_policy, self.optimizer_value, states, actions,
                               ret.reshape(-1, 1), adv.reshape(-1, 1), fixed_log_probs, clip_epsilon=cfg.clip_epsilon,
                               num_epoch=cfg.num_optim_epoch, grad_clip=self.policy_grad_clip, ind=ind)

@@ -324,6 +324,7 @@ struct hoic_model {
 };
 
 #define HOIC_MAX_PARTS 8
+#define HOIC_TIMING_CLASSES 8          // k_p1, k_p2, k_p3s, k_p3, k_tail, k_reset, k_order, whole call
 struct hoic_batch {
   int device, n_envs;
   BatchDev b;
@@ -332,6 +333,13 @@ struct hoic_batch {
   float *frames, *reward_w;
   int *motion_offset, *motion_len;
   int *env_model_idx = nullptr, *samp_off = nullptr, *samp_ids = nullptr, *order = nullptr;
+  // optional per-kernel timing of hoic_step (hoic_set_timing): event pairs around every launch, summed per kernel class
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;          // pairs (before, after)
+  std::vector<int> tev_class;
+  size_t tev_used = 0;
+  double tacc[HOIC_TIMING_CLASSES] = {};
+  int tsteps = 0;
   int balance = 0, n_models = 0, n_samp_ids = 0;
   const int* user_perm = nullptr;
   size_t smem_bytes, frames_cap = 0;
@@ -938,53 +946,109 @@ extern "C" int hoic_get_episode(hoic_batch* b, int* motion_id, int* start_idx, i
   return 0;
 }
 
+namespace {
+// event pair around a launch of kernel class `cls` on `sm` (no-ops unless hoic_set_timing is on)
+struct TimedLaunch {
+  hoic_batch* b; cudaStream_t sm; bool on; size_t idx = 0;
+  TimedLaunch(hoic_batch* b_, int cls, cudaStream_t sm_) : b(b_), sm(sm_), on(b_->timing) {
+    if (!on) return;
+    idx = b->tev_used;
+    b->tev_used += 2;
+    while (b->tev.size() < b->tev_used) { cudaEvent_t e; cudaEventCreate(&e); b->tev.push_back(e); }
+    if (b->tev_class.size() < b->tev_used / 2) b->tev_class.resize(b->tev_used / 2);
+    b->tev_class[idx / 2] = cls;
+    cudaEventRecord(b->tev[idx], sm);
+  }
+  ~TimedLaunch() { if (on) cudaEventRecord(b->tev[idx + 1], sm); }
+};
+void timing_collect(hoic_batch* b) {
+  if (!b->tev_used) return;
+  cudaDeviceSynchronize();
+  for (size_t i = 0; i + 1 < b->tev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, b->tev[i], b->tev[i + 1]) == cudaSuccess) b->tacc[b->tev_class[i / 2]] += ms;
+  }
+  b->tev_used = 0;
+}
+}  // namespace
+
+extern "C" int hoic_set_timing(hoic_batch* b, int on) {
+  if (!b) return set_err("hoic_set_timing: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  timing_collect(b);
+  b->timing = on != 0;
+  for (int i = 0; i < HOIC_TIMING_CLASSES; i++) b->tacc[i] = 0;
+  b->tsteps = 0;
+  return 0;
+}
+extern "C" int hoic_get_timing(hoic_batch* b, double* ms_host, int* steps_host) {
+  if (!b || !ms_host) return set_err("hoic_get_timing: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  timing_collect(b);
+  for (int i = 0; i < HOIC_TIMING_CLASSES; i++) ms_host[i] = b->tacc[i];
+  if (steps_host) *steps_host = b->tsteps;
+  return 0;
+}
+
 extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float* reward, float* reward_info, uint8_t* done,
                          uint8_t* fail, uint8_t* end, float* percent, int auto_reset, void* stream) {
   if (!b || !actions) return set_err("hoic_step: bad arguments");
   if (!b->b.frames) return set_err("hoic_step: call hoic_set_motions first");
   if (auto_reset && (!done || !b->b.samp_off)) return set_err("hoic_step: auto_reset needs the done output and hoic_set_sampler");
   CUDA_OK(cudaSetDevice(b->device));
-  if (b->user_perm) b->b.perm = b->user_perm;
-  else if (b->balance) {
-    k_order<<<1, 1024, 0, (cudaStream_t)stream>>>(b->b, b->order);
-    LAUNCH_CHECK();
-    b->b.perm = b->order;
-  } else b->b.perm = nullptr;
-  StepOut o = {obs, reward, reward_info, done, fail, end, percent};
   cudaStream_t user = (cudaStream_t)stream;
+  if (b->timing) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(user, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return set_err("hoic_step: per-kernel timing cannot run under stream capture");
+    timing_collect(b);      // the previous call's events
+  }
+  StepOut o = {obs, reward, reward_info, done, fail, end, percent};
   const int np = b->nparts;
-#define STEP_LAUNCH(call) do { cudaError_t e_ = (call); g_launches++; if (e_ != cudaSuccess) return set_err(std::string("kernel launch (" #call "): ") + cudaGetErrorString(e_)); } while (0)
-#define STEP_PARTS(call) do { for (int j = 0; j < np; j++) { const StepPart sp = {j, np}; cudaStream_t sm = b->part_stream[j]; STEP_LAUNCH(call); } } while (0)
-  // fork: every part runs on its own stream; the caller's stream waits for all of them at the end
-  CUDA_OK(cudaEventRecord(b->ev_fork, user));
-  for (int j = 0; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_fork, 0));
-  STEP_PARTS(hoic_launch_p1(b->b, sp, actions, -1, sm));
-  STEP_PARTS(hoic_launch_p2(b->b, sp, -1, sm));
-  for (int k = 0; k < b->nsub; k++) {
-    STEP_PARTS(hoic_launch_p1(b->b, sp, actions, k, sm));
-    STEP_PARTS(hoic_launch_p2(b->b, sp, k, sm));
-    // the two capacity tiers of the solver take disjoint envs: side by side (the few long solves of the full tier would
-    // otherwise sit on every substep's critical path)
-    for (int j = 0; j < np; j++) {
-      const StepPart sp = {j, np};
-      CUDA_OK(cudaEventRecord(b->ev_rows[j], b->part_stream[j]));
-      CUDA_OK(cudaStreamWaitEvent(b->aux_stream[j], b->ev_rows[j], 0));
-      STEP_LAUNCH(hoic_launch_p3(b->b, sp, k, b->aux_stream[j]));
-      CUDA_OK(cudaEventRecord(b->ev_aux[j], b->aux_stream[j]));
-      STEP_LAUNCH(hoic_launch_p3s(b->b, sp, k, b->part_stream[j]));
-      CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_aux[j], 0));
+#define STEP_LAUNCH(cls, sm_, call) do { TimedLaunch tl_(b, cls, sm_); cudaError_t e_ = (call); g_launches++; if (e_ != cudaSuccess) return set_err(std::string("kernel launch (" #call "): ") + cudaGetErrorString(e_)); } while (0)
+#define STEP_PARTS(cls, call) do { for (int j = 0; j < np; j++) { const StepPart sp = {j, np}; cudaStream_t sm = b->part_stream[j]; STEP_LAUNCH(cls, sm, call); } } while (0)
+  {
+    TimedLaunch whole(b, 7, user);
+    if (b->user_perm) b->b.perm = b->user_perm;
+    else if (b->balance) {
+      TimedLaunch tl(b, 6, user);
+      k_order<<<1, 1024, 0, user>>>(b->b, b->order);
+      LAUNCH_CHECK();
+      b->b.perm = b->order;
+    } else b->b.perm = nullptr;
+    // fork: every part runs on its own stream; the caller's stream waits for all of them at the end
+    CUDA_OK(cudaEventRecord(b->ev_fork, user));
+    for (int j = 0; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_fork, 0));
+    STEP_PARTS(0, hoic_launch_p1(b->b, sp, actions, -1, sm));
+    STEP_PARTS(1, hoic_launch_p2(b->b, sp, -1, sm));
+    for (int k = 0; k < b->nsub; k++) {
+      STEP_PARTS(0, hoic_launch_p1(b->b, sp, actions, k, sm));
+      STEP_PARTS(1, hoic_launch_p2(b->b, sp, k, sm));
+      // the two capacity tiers of the solver take disjoint envs: side by side (the few long solves of the full tier would
+      // otherwise sit on every substep's critical path)
+      for (int j = 0; j < np; j++) {
+        const StepPart sp = {j, np};
+        CUDA_OK(cudaEventRecord(b->ev_rows[j], b->part_stream[j]));
+        CUDA_OK(cudaStreamWaitEvent(b->aux_stream[j], b->ev_rows[j], 0));
+        STEP_LAUNCH(3, b->aux_stream[j], hoic_launch_p3(b->b, sp, k, b->aux_stream[j]));
+        CUDA_OK(cudaEventRecord(b->ev_aux[j], b->aux_stream[j]));
+        STEP_LAUNCH(2, b->part_stream[j], hoic_launch_p3s(b->b, sp, k, b->part_stream[j]));
+        CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_aux[j], 0));
+      }
+    }
+    STEP_PARTS(4, hoic_launch_tail(b->b, sp, actions, o, sm));
+    for (int j = 0; j < np; j++) { CUDA_OK(cudaEventRecord(b->ev_join[j], b->part_stream[j])); CUDA_OK(cudaStreamWaitEvent(user, b->ev_join[j], 0)); }
+    if (auto_reset) {
+      // the sampler's episode loop (agent_handmimic.py:437-454): a finished env restarts on a freshly drawn (motion, start)
+      // and its returned observation is the reset observation
+      TimedLaunch tl(b, 5, user);
+      k_reset<<<b->n_envs, 32, b->smem_bytes, user>>>(b->b, done, nullptr, nullptr, obs, 1);
+      LAUNCH_CHECK();
     }
   }
-  STEP_PARTS(hoic_launch_tail(b->b, sp, actions, o, sm));
-  for (int j = 0; j < np; j++) { CUDA_OK(cudaEventRecord(b->ev_join[j], b->part_stream[j])); CUDA_OK(cudaStreamWaitEvent(user, b->ev_join[j], 0)); }
 #undef STEP_PARTS
-  if (auto_reset) {
-    // the sampler's episode loop (agent_handmimic.py:437-454): a finished env restarts on a freshly drawn (motion, start)
-    // and its returned observation is the reset observation
-    k_reset<<<b->n_envs, 32, b->smem_bytes, user>>>(b->b, done, nullptr, nullptr, obs, 1);
-    LAUNCH_CHECK();
-  }
 #undef STEP_LAUNCH
+  if (b->timing) b->tsteps++;
   return 0;
 }
 

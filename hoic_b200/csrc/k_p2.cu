@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, Ste
     ST_FIELD(MISC);
     return;
   }
+#ifndef P2_NO_MIDSYNC
   P2_SYNC();
+#endif
   if (!work) return;
   build_rows(s, m, lane);
   if (B.rec_frames) record_contact_frames(s, m, lane, B.rec_frames + ((size_t)env * m.sim_step + k) * HOIC_REC_STRIDE);

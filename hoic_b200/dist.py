@@ -36,6 +36,12 @@ class RolloutStats:
         self.episode_reward = episode_reward      # [N] running sums (float64), owned by the caller
         self.finished = []
 
+    def reset(self):
+        """Zero in place (the tensors may be baked into a captured CUDA graph)."""
+        self.sums.zero_()
+        self.minmax.copy_(torch.tensor([float("inf"), float("-inf"), float("inf"), float("-inf")], dtype=torch.float64))
+        self.finished = []
+
     def update(self, reward, info, done, motion_id=None, start_idx=None, percent=None):
         r = reward.to(torch.float64)
         d = done.to(torch.bool)
@@ -55,10 +61,12 @@ class RolloutStats:
         if motion_id is not None:
             self.finished.append((d.clone(), motion_id.clone(), start_idx.clone(), percent.clone()))
 
-    def freq_rows(self):
-        """[(motion_id, percent, start_idx)] of the finished episodes of this rank, on the host."""
+    def freq_rows(self, extra=()):
+        """[(motion_id, percent, start_idx)] of the finished episodes of this rank, on the host.  `extra`: more
+        (done, motion_id, start_idx, percent) tuples, e.g. whole [T, N] rollout arrays."""
         rows = []
-        for d, mid, st, pc in self.finished:
+        for d, mid, st, pc in list(self.finished) + list(extra):
+            d, mid, st, pc = d.reshape(-1).to(torch.bool), mid.reshape(-1), st.reshape(-1), pc.reshape(-1)
             idx = d.nonzero().squeeze(1)
             if idx.numel():
                 rows.append(torch.stack([mid[idx].double(), pc[idx].double(), st[idx].double()], 1).cpu().numpy())

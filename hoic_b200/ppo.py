@@ -103,13 +103,18 @@ class ZFilter:
         w = nb / torch.clamp(tot, min=1)
         return tot, mean + delta * w, m2 + bm2 + delta ** 2 * (n * w)
 
+    def _assign(self, names, values):
+        # in place: the tensors keep their addresses, so an update may be captured in a CUDA graph and replayed
+        for name, v in zip(names, values):
+            getattr(self, name).copy_(v)
+
     def update(self, x):
         x = x.to(torch.float64)
-        nb = torch.tensor(float(x.shape[0]), dtype=torch.float64, device=x.device)
+        nb = float(x.shape[0])
         bmean = x.mean(0)
         bm2 = ((x - bmean) ** 2).sum(0)
-        self.n, self.mean, self.m2 = self._merge(self.n, self.mean, self.m2, nb, bmean, bm2)
-        self._dn, self._dmean, self._dm2 = self._merge(self._dn, self._dmean, self._dm2, nb, bmean, bm2)
+        self._assign(("n", "mean", "m2"), self._merge(self.n, self.mean, self.m2, nb, bmean, bm2))
+        self._assign(("_dn", "_dmean", "_dm2"), self._merge(self._dn, self._dmean, self._dm2, nb, bmean, bm2))
 
     def __call__(self, x, update=True):
         if update:
@@ -120,11 +125,12 @@ class ZFilter:
     def set_state(self, n, mean, m2):
         """Adopt pooled statistics (checkpoint load): they become the synced base, nothing is pending."""
         dev = self.mean.device
-        self.n = torch.as_tensor(float(n), dtype=torch.float64, device=dev)
-        self.mean = torch.as_tensor(mean, dtype=torch.float64, device=dev).clone()
-        self.m2 = torch.as_tensor(m2, dtype=torch.float64, device=dev).clone()
-        self._bn, self._bmean, self._bm2 = self.n.clone(), self.mean.clone(), self.m2.clone()
-        self._dn, self._dmean, self._dm2 = torch.zeros_like(self.n), torch.zeros_like(self.mean), torch.zeros_like(self.m2)
+        self._assign(("n", "mean", "m2"), (torch.as_tensor(float(n), dtype=torch.float64, device=dev),
+                                            torch.as_tensor(mean, dtype=torch.float64, device=dev),
+                                            torch.as_tensor(m2, dtype=torch.float64, device=dev)))
+        self._assign(("_bn", "_bmean", "_bm2"), (self.n, self.mean, self.m2))
+        for name in ("_dn", "_dmean", "_dm2"):
+            getattr(self, name).zero_()
 
     @staticmethod
     def merge_moments(parts):
@@ -147,9 +153,10 @@ class ZFilter:
         dmean = head[1:].reshape(mean_r.shape) / torch.clamp(dn, min=1)
         dm2 = m2_r + n_r * (mean_r - dmean) ** 2
         dist.all_reduce(dm2)
-        self.n, self.mean, self.m2 = self._merge(self._bn, self._bmean, self._bm2, dn, dmean, torch.clamp(dm2, min=0))
-        self._bn, self._bmean, self._bm2 = self.n.clone(), self.mean.clone(), self.m2.clone()
-        self._dn, self._dmean, self._dm2 = torch.zeros_like(self.n), torch.zeros_like(self.mean), torch.zeros_like(self.m2)
+        self._assign(("n", "mean", "m2"), self._merge(self._bn, self._bmean, self._bm2, dn, dmean, torch.clamp(dm2, min=0)))
+        self._assign(("_bn", "_bmean", "_bm2"), (self.n, self.mean, self.m2))
+        for name in ("_dn", "_dmean", "_dm2"):
+            getattr(self, name).zero_()
 
 
 def estimate_advantages(rewards, masks, values, gamma, tau):

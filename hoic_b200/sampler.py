@@ -1,0 +1,166 @@
+"""One step of the sampler's inner loop for the whole batch (uhc/agents/agent_handmimic.py:460-490):
+observation normaliser -> policy MLP -> exploration noise -> env.step (+ custom reward, auto-reset) -> logger,
+captured once into ONE CUDA graph and replayed per step.
+
+The MLP runs on the tensor cores: bfloat16 operands with float32 accumulation under `torch.autocast`, float32 master
+weights (`policy_dtype="tf32"` / `"fp32"` select TF32 tensor cores / the plain float32 pipe; the reference runs float64
+on the CPU).  Everything else of the step is libhoic_b200.so (`HandMimicVecEnv.step` = one `hoic_step` call).
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+
+from . import capi
+
+
+def matmul_context(policy_dtype):
+    """Context in which the policy / value MLPs run: bf16 autocast, TF32 tensor cores, or strict float32."""
+    if policy_dtype == "bf16":
+        return torch.autocast(device_type="cuda", dtype=torch.bfloat16)
+    if policy_dtype == "tf32":
+        return _tf32(True)
+    if policy_dtype == "fp32":
+        return _tf32(False)
+    raise ValueError(policy_dtype)
+
+
+@contextlib.contextmanager
+def _tf32(on):
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = on
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+class SamplerStep:
+    """`step()` advances every env by one policy step and leaves the transition in fixed device buffers:
+    `x` (normalised state the action was computed from), `act`, `exp`, `reward` (c_reward), `done`, `end`, `fail`,
+    `percent`, `reward_info`, `motion_id` / `start_idx` (the episode the transition belongs to), `obs` (next state, raw;
+    the reset observation where the episode ended).  `stats` (dist.RolloutStats) and `running_state` (ppo.ZFilter) are
+    updated in place inside the graph."""
+
+    def __init__(self, env, policy, running_state, gen, stats=None, noise_rate=1.0, policy_dtype="bf16", graph=True,
+                 update_filter=True, host_noise=False):
+        self.env, self.policy, self.zf, self.gen, self.stats = env, policy, running_state, gen, stats
+        self.policy_dtype, self.update_filter = policy_dtype, update_filter
+        N, dev = env.n_envs, env.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.noise_rate = torch.full((), float(noise_rate), **f32)      # device scalar: changing it needs no recapture
+        self.x = torch.zeros(N, env.obs_dim, **f32)
+        self.act = torch.zeros(N, env.act_dim, **f32)
+        self.exp = torch.ones(N, **f32)
+        self.motion_id = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.start_idx = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.noise = torch.zeros(N, env.act_dim, **f32) if host_noise else None   # filled by the caller (step_host)
+        self.obs = env.obs
+        self._graph = None
+        self._use_graph = graph
+        self._host = None
+
+    def set_noise_rate(self, r):
+        self.noise_rate.fill_(float(r))
+
+    # ------------------------------------------------------------------ the step body (eager or under capture)
+    def _body(self):
+        env = self.env
+        x = self.zf(env.obs, update=self.update_filter)
+        with matmul_context(self.policy_dtype):
+            mean, log_std = self.policy(x)
+        mean, log_std = mean.float(), log_std.float()
+        if self.noise is None:
+            noise = torch.randn(mean.shape, device=mean.device, dtype=torch.float32, generator=self.gen)
+        else:
+            noise = self.noise
+        # mean_action = binomial(1, 1 - noise_rate) per (env, step); exp = 1 - mean_action (agent_handmimic.py:464-465, :484)
+        u = torch.rand(mean.shape[0], device=mean.device, generator=self.gen)
+        self.exp.copy_((u < self.noise_rate).to(torch.float32))
+        self.x.copy_(x)
+        self.act.copy_(mean + torch.exp(log_std) * noise * self.exp[:, None])
+        capi.check(env.L.hoic_get_episode(env._hb, capi.ptr(self.motion_id), capi.ptr(self.start_idx), None, env._stream()),
+                   "hoic_get_episode")
+        obs, r, done, info = env.step(self.act)
+        if self.stats is not None:
+            self.stats.update(r, info["reward_info"], done)
+
+    def warmup(self):
+        """Two eager steps (cuBLAS handles, autocast caches, lazily loaded kernels), then the capture.  The eager steps are
+        ordinary rollout steps whose transitions are dropped: call this before the rollouts that count (and reset `stats`)."""
+        if not self._use_graph or self._graph is not None:
+            return
+        dev = self.env.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        g.register_generator_state(self.gen)
+        with torch.cuda.graph(g, stream=side):
+            self._body()
+        torch.cuda.synchronize(dev)
+        self._graph = g
+
+    def step(self):
+        if self._use_graph:
+            if self._graph is None:
+                self.warmup()
+            self._graph.replay()
+        else:
+            self._body()
+
+    # ------------------------------------------------------------------ host-resident rollout storage (Memory.push on the host)
+    def step_host(self, noise_host):
+        """The same step for a sampler whose RNG and rollout storage live on the HOST, like the reference's
+        (agent_handmimic.py:463-485, khrylib/rl/core/memory.py): `noise_host` [N, 32] pinned float32 standard-normal draws
+        go H2D, the transition (normalised state, action, exp, reward, mask, info, percent) comes back D2H into pinned
+        buffers.  One graph launch + one stream synchronise per step.  Returns the dict of pinned host tensors."""
+        if self.noise is None:
+            raise capi.HoicError("construct SamplerStep(host_noise=True) for step_host")
+        if self._host is None:
+            self._build_host()
+        h = self._host
+        if noise_host.data_ptr() != h["noise"].data_ptr():
+            h["noise"].copy_(noise_host)
+        h["graph"].replay()
+        torch.cuda.current_stream(self.env.device).synchronize()
+        return h["out"]
+
+    def _host_body(self):
+        h = self._host
+        self.noise.copy_(h["noise"], non_blocking=True)
+        self._body()
+        env = self.env
+        for k, src in (("state", self.x), ("action", self.act), ("exp", self.exp), ("reward", env.reward), ("done", env.done),
+                       ("end", env.end), ("fail", env.fail), ("percent", env.percent), ("reward_info", env.reward_info)):
+            h["out"][k].copy_(src, non_blocking=True)
+
+    def _build_host(self):
+        env, N = self.env, self.env.n_envs
+        pin = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype).pin_memory()
+        out = dict(state=pin(N, env.obs_dim), action=pin(N, env.act_dim), exp=pin(N), reward=pin(N), percent=pin(N),
+                   reward_info=pin(N, capi.INFO_DIM), done=pin(N, dtype=torch.uint8), end=pin(N, dtype=torch.uint8),
+                   fail=pin(N, dtype=torch.uint8))
+        self._host = dict(noise=pin(N, env.act_dim), out=out, graph=None)
+        self._host["noise"].zero_()
+        self.h2d_bytes = N * env.act_dim * 4
+        self.d2h_bytes = sum(v.numel() * v.element_size() for v in out.values())
+        dev = env.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._host_body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        g.register_generator_state(self.gen)
+        with torch.cuda.graph(g, stream=side):
+            self._host_body()
+        torch.cuda.synchronize(dev)
+        self._host["graph"] = g

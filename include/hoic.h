@@ -177,6 +177,14 @@ int hoic_get_work(hoic_batch* b, int* work /*[N]*/, void* stream);
 int hoic_set_env_order(hoic_batch* b, const int* perm /*[N] device, kept by reference*/);
 int hoic_set_balance(hoic_batch* b, int on);
 
+/* per-kernel timing of hoic_step for bench.py's roofline (off by default; not under stream capture): with it on, every
+ * launch of the step pipeline is bracketed by CUDA events on the stream it runs on.  hoic_get_timing returns the summed
+ * durations since hoic_set_timing(b, 1) in ms_host[8] = k_p1, k_p2, k_p3s (solver, small tier), k_p3 (full tier), k_tail,
+ * k_reset, k_order, the whole call on the caller's stream (fork to join), and the number of hoic_step calls.  The batch
+ * runs as interleaved parts on parallel streams, so the per-kernel sums count concurrent time more than once. */
+int hoic_set_timing(hoic_batch* b, int on);
+int hoic_get_timing(hoic_batch* b, double* ms_host /*[8]*/, int* steps_host);
+
 /* integer work counters accumulated by the kernels since creation (synchronises the device) */
 int hoic_get_counters(hoic_batch* b, hoic_counters* out_host);
 /* FP32 FMA micro-benchmark on `device` (roofline denominator for the non-tensor pipe): 2*FMAs/s in TFLOP/s */

@@ -34,7 +34,10 @@ def test_ppo_iteration_end_to_end(obj):
     agent.per_epoch_update(500)
     assert not np.allclose(w1, cfg.reward_vector())
     c = agent.env.counters()
-    assert c["env_steps"] == 2 * 512 * 6 and c["fail_overflow"] == 0
+    assert c["env_steps"] == (2 * 6 + 2) * 512 and c["fail_overflow"] == 0     # + the 2 warm-up steps of the sampler graph
+    # end_reward of the next iteration = avg_c_reward gamma / (1 - gamma) (agent_handmimic.py:317-319)
+    assert abs(infos[1]["end_reward"] - infos[1]["log"]["avg_c_reward"] * cfg.gamma / (1 - cfg.gamma)) < 1e-9
+    assert infos[1]["log"]["num_episodes"] >= 0 and len(agent.freq_dict) >= 8
     agent.close()
 
 
@@ -43,7 +46,7 @@ def test_noise_rate_masks_exploration():
     mdl = model("box")
     cfg = copy.deepcopy(mdl.cfg)
     cfg.min_batch_size = 256 * 3
-    agent = AgentHandMimic(mdl, 256, cfg=cfg)
+    agent = AgentHandMimic(mdl, 256, cfg=cfg, policy_dtype="fp32")
     agent.per_epoch_update(0)
     agent.noise_rate = 0.5
     batch, _ = agent.sample(cfg.min_batch_size)
@@ -95,3 +98,43 @@ def test_eval_policy_batched_test_mode():
     assert abs(per["pose_err"][0] - pe / 6) < 1e-3 and abs(per["mpjpe"][0] - mp / 12) < 1e-4
     assert abs(per["avg_reward"][0] - rw / 12) < 2e-3
     agent.close()
+
+
+def test_bf16_policy_matches_fp32_within_a_thousandth_of_sigma_and_graph_equals_eager():
+    """Rollout inference runs on the tensor cores (bf16 operands, fp32 accumulate, fp32 master weights): the action mean must
+    stay within 1e-3 sigma of the float32 network's; and the CUDA-graph sampler step must produce exactly what the eager
+    step produces from the same state and RNG stream."""
+    from hoic_b200 import ppo, dist as hdist
+    from hoic_b200.sampler import SamplerStep, matmul_context
+    from hoic_b200.vecenv import HandMimicVecEnv
+    mdl = model("box")
+    dev = torch.device("cuda", 0)
+    pol, _ = ppo.make_policy_value(mdl.cfg, device=dev, dtype=torch.float32, seed=1)
+    x = torch.clamp(torch.randn(2048, 617, device=dev), -5, 5)
+    with torch.no_grad():
+        ref = pol(x)[0]
+        with matmul_context("bf16"):
+            lo = pol(x)[0].float()
+    sigma = float(torch.exp(pol.action_log_std).mean())
+    assert float((lo - ref).abs().max()) < 1e-3 * sigma, float((lo - ref).abs().max()) / sigma
+    outs = []
+    for graph in (False, True):
+        env = HandMimicVecEnv(mdl, 64, [mdl.motion(s) for s in range(1, 9)], device=0, seed=3, auto_reset=True)
+        zf = ppo.ZFilter((617,), clip=5.0, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(11)
+        st = hdist.RolloutStats(dev)
+        s = SamplerStep(env, pol, zf, gen, stats=st, policy_dtype="bf16", graph=graph)
+        env.reset()
+        if graph:
+            s.warmup()
+        else:
+            for _ in range(2):
+                s.step()        # the graph's two eager warm-up steps
+        st.reset()
+        for _ in range(4):
+            s.step()
+        torch.cuda.synchronize()
+        outs.append((s.act.clone(), env.reward.clone(), env.done.clone(), zf.mean.clone(), st.sums.clone()))
+        env.close()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
