@@ -430,7 +430,7 @@ def run_ours(args):
                          "note": "does not bind; the working set of the pipeline travels between kernels through L2"},
         "counters_per_substep": {k: dc[k] / max(dc["substeps"], 1) for k in ("ncon", "nefc", "newton_iters", "ls_evals", "mpr_iters")},
         "capacity_high_water": {"max_ncon": c1["max_ncon"], "max_nbasis": c1["max_nbasis"], "max_nedge": c1["max_nedge"],
-                                "capacity": [24, 56, 96]},
+                                "capacity": [32, 80, 128]},
         "rollout": {"avg_reward": tot["avg_reward"], "episodes": tot["num_episodes"], "avg_episode_len": tot["avg_episode_len"],
                     "fail_overflow": dc["fail_overflow"], "fail_physics": dc["fail_physics"]},
     }

@@ -37,8 +37,12 @@ static __device__ __noinline__ bool pd_torque(float* s, const DevModel& m, int l
     qv = s[S_QVEL + lane];
     err = s[S_QPOS + lane] + qv * dt - target;
     if (lane >= 3) {
-      while (err > F_PI) err -= 2.f * F_PI;
-      while (err < -F_PI) err += 2.f * F_PI;
+      // the reference's `while err > pi: err -= 2 pi` (ho_im4.py:455-460), bounded: a state whose error is beyond a few turns
+      // has blown up and is failed by the state check of the forward that follows
+#pragma unroll 1
+      for (int it = 0; it < 8 && err > F_PI; it++) err -= 2.f * F_PI;
+#pragma unroll 1
+      for (int it = 0; it < 8 && err < -F_PI; it++) err += 2.f * F_PI;
     }
     kp = m.jkp[lane]; kd = m.jkd[lane];
     rhs = -s[S_BIAS + lane] - kp * err - kd * qv;

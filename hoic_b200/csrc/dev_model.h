@@ -8,19 +8,19 @@
 #define H_NQ 36
 #define H_MAXCAND 128
 #ifndef H_NCON
-#define H_NCON 24      // contact capacity per env (<= HOIC_MAX_CONTACTS)
+#define H_NCON 32      // contact capacity per env (<= HOIC_MAX_CONTACTS)
 #endif
 #ifndef H_NBASIS
-#define H_NBASIS 56    // contact Jacobian basis rows per env (condim 3: 3 per contact, condim 4: 4)
+#define H_NBASIS 80    // contact Jacobian basis rows per env (condim 3: 3 per contact, condim 4: 4)
 #endif
 #ifndef H_NEDGE
-#define H_NEDGE 96     // pyramid edge rows per env
+#define H_NEDGE 128    // pyramid edge rows per env
 #endif
 // capacities of the GLOBAL working set (BatchDev.scratch): what k_p2 produces.  A kernel compiled with smaller H_NCON /
 // H_NBASIS / H_NEDGE (k_p3's small tier) holds a smaller constraint stage in shared memory and only takes envs that fit.
-#define HG_NCON 24
-#define HG_NBASIS 56
-#define HG_NEDGE 96
+#define HG_NCON 32
+#define HG_NBASIS 80
+#define HG_NEDGE 128
 #define H_RFR 0        // row index ranges: friction-loss rows [0,32)
 #define H_RLIM 32      //                   joint-limit rows   [32,64)
 #define H_RCON 64      //                   contact edge rows  [64,64+H_NEDGE)
@@ -119,7 +119,9 @@ struct DevModel {
 // sizes of the three users of the union region (floats)
 #define UN_POS (288 + 96 + 96 + 320 + 320)                                             /* position / velocity stage */
 #define UN_CON_OF(nc, nb, ne) ((nc) * 16 + (nb) * B_STRIDE + 6 * (H_RCON + (ne)) + 2 * (nb) + (nc) * 8 + (H_MAXCAND / 2 > (nb) ? H_MAXCAND / 2 : (nb)))
-#define UN_CON UN_CON_OF(H_NCON, H_NBASIS, H_NEDGE)
+// k_p2 builds the rows but never touches the solver's per-row work arrays (JAR, JV, FORCE, BV), which lie at the end
+#define UN_CON_BUILD_OF(nc, nb, ne) (UN_CON_OF(nc, nb, ne) - 3 * (H_RCON + (ne)) - (nb))
+#define UN_CON ((H_KERNEL) == HK_P2 ? UN_CON_BUILD_OF(H_NCON, H_NBASIS, H_NEDGE) : UN_CON_OF(H_NCON, H_NBASIS, H_NEDGE))
 #define UN_CON_G UN_CON_OF(HG_NCON, HG_NBASIS, HG_NEDGE)
 #define UN_QP (3168 - 384 - 576)       /* residual-force QP scratch starts at S_MS (QP_BASE) and runs over S_H into the union */
 #define UN_TS (32 * 21)                /* tree_solve's branch products (dev_math.cuh: TS_P) */
@@ -239,14 +241,15 @@ __host__ __device__ constexpr int h_field_size(int f) {
 #define UL_B(nc, nb, ne) ((nc) * 16)                             // nb * B_STRIDE basis rows
 #define UL_AREF(nc, nb, ne) (UL_B(nc, nb, ne) + (nb) * B_STRIDE) // (H_RCON + ne) each:
 #define UL_D(nc, nb, ne) (UL_AREF(nc, nb, ne) + H_RCON + (ne))
-#define UL_JAR(nc, nb, ne) (UL_D(nc, nb, ne) + H_RCON + (ne))
-#define UL_JV(nc, nb, ne) (UL_JAR(nc, nb, ne) + H_RCON + (ne))
-#define UL_FORCE(nc, nb, ne) (UL_JV(nc, nb, ne) + H_RCON + (ne))
-#define UL_RINFO(nc, nb, ne) (UL_FORCE(nc, nb, ne) + H_RCON + (ne))   // int per row: limit rows dof | sign<<8 ; edge rows contact | edge<<8
-#define UL_BV(nc, nb, ne) (UL_RINFO(nc, nb, ne) + H_RCON + (ne))  // nb: basis . v products
-#define UL_BMASK(nc, nb, ne) (UL_BV(nc, nb, ne) + (nb))          // nb: dof mask of each basis row (bit i: dof i has a column)
+#define UL_RINFO(nc, nb, ne) (UL_D(nc, nb, ne) + H_RCON + (ne))  // int per row: limit rows dof | sign<<8 ; edge rows contact | edge<<8
+#define UL_BMASK(nc, nb, ne) (UL_RINFO(nc, nb, ne) + H_RCON + (ne))   // nb: dof mask of each basis row (bit i: dof i has a column)
 #define UL_CINFO(nc, nb, ne) (UL_BMASK(nc, nb, ne) + (nb))       // nc * 8: basis offset, nbasis, edge offset, nedge, mu0, mu1, D, pad
 #define UL_MPRQ(nc, nb, ne) (UL_CINFO(nc, nb, ne) + (nc) * 8)    // H_MAXCAND 16-bit indices: queued MPR candidates (later nb ints: U_BINFO)
+// ... the solver's work arrays (absent from k_p2's layout)
+#define UL_JAR(nc, nb, ne) (UL_MPRQ(nc, nb, ne) + (H_MAXCAND / 2 > (nb) ? H_MAXCAND / 2 : (nb)))
+#define UL_JV(nc, nb, ne) (UL_JAR(nc, nb, ne) + H_RCON + (ne))
+#define UL_FORCE(nc, nb, ne) (UL_JV(nc, nb, ne) + H_RCON + (ne))
+#define UL_BV(nc, nb, ne) (UL_FORCE(nc, nb, ne) + H_RCON + (ne)) // nb: basis . v products
 #define U_S(f) (S_UNION + UL_##f(H_NCON, H_NBASIS, H_NEDGE))     // in this kernel's shared memory
 #define U_G(f) (G_OFF(UNION) + UL_##f(HG_NCON, HG_NBASIS, HG_NEDGE))   // in the global working set
 #define U_CON U_S(CON)
@@ -262,6 +265,7 @@ __host__ __device__ constexpr int h_field_size(int f) {
 #define U_CINFO U_S(CINFO)
 #define U_MPRQ U_S(MPRQ)
 #define U_CON_END (S_UNION + UN_CON)
+static_assert(UL_BV(H_NCON, H_NBASIS, H_NEDGE) + H_NBASIS == UN_CON_OF(H_NCON, H_NBASIS, H_NEDGE), "constraint stage layout");
 #define U_QP_END (QP_BASE + 3168)      // residual-force QP scratch (dev_env.cuh: QP_*; static_assert there)
 #define U_TS_END (S_UNION + UN_TS)
 static_assert(UN_POS == 1120 && (UN_CON % 4) == 0 && (H_NBASIS * B_STRIDE) % 4 == 0 && H_NROW % 4 == 0 && H_NCON % 4 == 0 &&

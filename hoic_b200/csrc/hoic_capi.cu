@@ -272,7 +272,10 @@ __global__ void __launch_bounds__(32) k_preprocess(const DevModel* mp, const flo
     const float lo = clip ? m.jnt_range[lane][0] : -F_MAXVAL, hi = clip ? m.jnt_range[lane][1] : F_MAXVAL;
     q = fminf(fmaxf(hand[(size_t)t * nh + lane], lo), hi);
     float v = fminf(fmaxf(hand[(size_t)a * nh + lane], lo), hi) - fminf(fmaxf(hand[(size_t)b * nh + lane], lo), hi);
-    if (lane >= 3 && lane < 6) { while (v > F_PI) v -= 2.f * F_PI; while (v < -F_PI) v += 2.f * F_PI; }
+    if (lane >= 3 && lane < 6) {
+      for (int it = 0; it < 8 && v > F_PI; it++) v -= 2.f * F_PI;
+      for (int it = 0; it < 8 && v < -F_PI; it++) v += 2.f * F_PI;
+    }
     f[F_DOF + lane] = q;
     f[F_DOFVEL + lane] = v * freq;
   }

@@ -68,6 +68,14 @@ __global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) k_p1(BatchDev B, Ste
     if (rf && ok) record_state(s, m, lane, vf, vt, rf);
   }
   if (ok && k >= 0) {
+    // mj_checkPos / mj_checkVel at the head of mj_step: a non-finite or exploding state fails the env before anything reads it
+    if (__any_sync(FULLMASK, bad(s[S_QPOS + lane]) || bad(s[S_QVEL + lane]) || (lane == 0 && bad(s[S_QPOS + 32])))) {
+      ok = false;
+      if (lane == 0) misc[MI_FLAGS] |= 1;
+      __syncwarp();
+    }
+  }
+  if (ok && k >= 0) {
     const EnvCtx ctx = make_ctx(B, (const int*)(st + ST_INTS));
     ok = pd_torque(s, m, lane, ctx);
     // J^T wrenches with the previous forward's Jacobians (stale cdof / com / geom_xpos)

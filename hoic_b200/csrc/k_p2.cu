@@ -6,10 +6,10 @@
 #include "hoic_step.cuh"
 
 #ifndef P2_W
-#define P2_W 8
+#define P2_W 5
 #endif
 #ifndef P2_WPS
-#define P2_WPS 16
+#define P2_WPS 15
 #endif
 
 // P2_W > 1: the warps of a CTA start collision together and meet again before the constraint rows, so that they fetch the

@@ -29,9 +29,10 @@ extern "C" {
 #define HOIC_NQ 33
 #define HOIC_NV 32
 #define HOIC_NHG 19          /* hand collision geoms (hand_geom_range, ho_im4.py:80-87) */
-#define HOIC_MAX_CONTACTS 32 /* contact slots per env in hoic_get_contacts buffers; the kernels hold 24 contacts, 56 contact
-                              * basis rows and 96 pyramid edges per env (the MJCF's nconmax / njmax are 100 / 500): an env that
-                              * needs more is failed like MuJoCo's full-buffer warning does, see hoic_counters */
+#define HOIC_MAX_CONTACTS 32 /* contact slots per env in hoic_get_contacts buffers = the kernels' contact capacity; they hold 32
+                              * contacts, 80 contact basis rows and 128 pyramid edges per env (the MJCF's nconmax / njmax are
+                              * 100 / 500): an env that needs more is failed like MuJoCo's full-buffer warning does, see
+                              * hoic_counters.max_* (high-water marks) and fail_overflow */
 /* test-mode recording (MotionData, ho_im4.py:27-41).  One frame per physics substep (compute_data_frame :599-609):
  *   [0,63) hand_kps = body_xpos of the 21 hand bodies   [63,89) hand_qpos   [89,95) compensate_ft (obj_vf, obj_vt)
  *   [95,102) obj_pose   [102,108) obj_vel   [108,114) obj_acc = qacc[-6:]   [114] number of hand-object contacts

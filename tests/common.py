@@ -16,15 +16,15 @@ OBJECTS = ("box", "bottle", "banana")
 _CACHE = {}
 
 
-def model(obj):
-    if obj not in _CACHE:
-        _CACHE[obj] = load_model(obj)
-    return _CACHE[obj]
+def model(obj, cfg_id=None):
+    if (obj, cfg_id) not in _CACHE:
+        _CACHE[(obj, cfg_id)] = load_model(obj, cfg_id=cfg_id)
+    return _CACHE[(obj, cfg_id)]
 
 
-def oracle_env(obj, seed=1, start_idx=0):
+def oracle_env(obj, seed=1, start_idx=0, cfg_id=None):
     from oracle import OracleEnv
-    mdl = model(obj)
+    mdl = model(obj, cfg_id)
     env = OracleEnv(mdl.blob)
     ex = mdl.motion(seed)
     env.set_motion(hmotion.pack_frames(hmotion.load_seq(ex, start_idx)))

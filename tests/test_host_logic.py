@@ -834,3 +834,26 @@ def test_single_env_facade_attribute_surface_with_a_fake_engine():
     assert env.expert_len == 250 and env.cur_t == 0 and fake.motions is not None
     env.set_mode("train")
     assert fake.mode == "train" and env.seed(3) == [3]
+
+
+def test_oracle_reproduces_the_large_state_sets():
+    """tests/golden/<obj>_states.npz (tools/make_golden_states.py): 1280 single-mj_step vectors per object.  Oracle regression
+    on every 16th state (the CPU suite stays short): contact pairs, nefc, next qpos / qvel."""
+    import os
+    for obj in ("box", "bottle", "banana"):
+        G = np.load(os.path.join(ROOT, "tests", "golden", f"{obj}_states.npz"))
+        assert len(G["sub_q0"]) >= 1280 and int((G["sub_kind"] == 1).sum()) >= 256
+        assert int((G["sub_ncon"] >= 12).sum()) >= 100 and int(G["sub_nefc"].max()) >= 100
+        env = oracle_env(obj)
+        env.reset()
+        for i in range(0, len(G["sub_q0"]), 16):
+            env.clear_warnings()
+            env.set_state(G["sub_q0"][i], G["sub_v0"][i])
+            env.set_ctrl_applied(G["sub_ctrl"][i], G["sub_qapp"][i])
+            env.set_warmstart(G["sub_w0"][i])
+            env.mj_step()
+            con = env.contacts()
+            assert len(con) == G["sub_ncon"][i] and env.counters()["nefc"] == G["sub_nefc"][i]
+            assert np.array_equal(con[:, 13:15].astype(int), G["sub_pairs"][i][:len(con)].astype(int))
+            assert np.abs(env.get("qpos") - G["sub_q1"][i]).max() < 1e-12 and np.abs(env.get("qvel") - G["sub_v1"][i]).max() < 1e-10
+        env.close()
