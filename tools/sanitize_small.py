@@ -10,7 +10,8 @@ K = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 mdl = model(obj)
 env = HandMimicVecEnv(mdl, N, [mdl.motion(1)], seed=1, auto_reset=True, random_start=False)
 env.reset(motion_id=[0] * N, start_idx=[100] * N)
-env.set_record(True)
+if os.environ.get("HOIC_SAN_RECORD", "1") == "1":
+    env.set_record(True)
 for _ in range(K):
     o, r, d, i = env.step(torch.zeros(N, 32, device="cuda"))
 torch.cuda.synchronize()
