@@ -26,6 +26,7 @@ struct BatchDev {
   const int* perm;                    // optional env order (load balancing), NULL = identity
   int model_smem;                     // bytes of shared memory behind the env regions that k_step may stage a model into
   float* csum;                        // [N][CSUM_STRIDE] per-hand-geom contact sums / counts of the step (record_contact)
+  float* csum_carry;                  // [N][CSUM_STRIDE] record of the LAST forward's contacts: the first recording of the next step (S2)
   float* rec_frames;                  // test-mode recording (hoic_set_record), NULL = off
   float* rec_surface;
   float* scratch;                     // [N][G_TOTAL] working set of the running step between the kernels of the pipeline

@@ -628,6 +628,30 @@ static __device__ __noinline__ void collide(float* s, const DevModel& m, int lan
       }
       if (active && kind != K_CONVEX && kind != K_PLANE_MESH) {
         const M3 m1 = ldm(s + S_GMAT + 9 * g1), m2 = ldm(s + S_GMAT + 9 * g2);
+        // conservative separating-axis culls in front of the two large out-of-line routines (whose code runs for the whole
+        // warp as soon as one lane needs it): a pair separated by more than the margin along a face axis of the box(es) has
+        // no contact, so the routine would return 0 as well.
+        const float tol = cd.margin + 1e-6f;
+        if (kind == K_CAP_BOX) {
+          const float* cs = m.geom_size[g1];
+          const float* bs = m.geom_size[g2];
+          const V3 c = mulTv(m2, p1 - p2), a = mulTv(m2, col(m1, 2)) * cs[1];      // capsule centre / half axis in the box frame
+          if (fabsf(c.x) - fabsf(a.x) > bs[0] + cs[0] + tol || fabsf(c.y) - fabsf(a.y) > bs[1] + cs[0] + tol ||
+              fabsf(c.z) - fabsf(a.z) > bs[2] + cs[0] + tol) kind = -1;
+        } else if (kind == K_BOX_BOX) {
+          const float* A = m.geom_size[g1];
+          const float* Bz = m.geom_size[g2];
+          const V3 d = p2 - p1;
+          bool sep = false;
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            const V3 u = col(m1, i), w = col(m2, i);
+            const float e1 = comp(v3(A[0], A[1], A[2]), i) + fabsf(dot(u, col(m2, 0))) * Bz[0] + fabsf(dot(u, col(m2, 1))) * Bz[1] + fabsf(dot(u, col(m2, 2))) * Bz[2];
+            const float e2 = comp(v3(Bz[0], Bz[1], Bz[2]), i) + fabsf(dot(w, col(m1, 0))) * A[0] + fabsf(dot(w, col(m1, 1))) * A[1] + fabsf(dot(w, col(m1, 2))) * A[2];
+            sep = sep || fabsf(dot(d, u)) > e1 + tol || fabsf(dot(d, w)) > e2 + tol;
+          }
+          if (sep) kind = -1;
+        }
         switch (kind) {
           case K_PLANE_CAPSULE: n = plane_capsule(rc, cd.margin, p1, m1, p2, m2, m.geom_size[g2]); break;
           case K_PLANE_BOX: n = plane_box(rc, cd.margin, p1, m1, p2, m2, m.geom_size[g2]); break;

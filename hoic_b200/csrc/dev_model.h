@@ -291,6 +291,7 @@ static_assert(UN_POS == 1120 && (UN_CON % 4) == 0 && (H_NBASIS * B_STRIDE) % 4 =
 #define MI_C_MAXNEDGE 17
 #define MI_C_FAILPHYS 18
 #define MI_C_FAILOVER 19
+#define MI_CARRIED 20    // this step started from the working set the previous step left (no pass -1 recomputation)
 
 // per-env persistent state in global memory (floats), AoS so that a warp reads it coalesced
 #define ST_QPOS 0
@@ -298,6 +299,6 @@ static_assert(UN_POS == 1120 && (UN_CON % 4) == 0 && (H_NBASIS * B_STRIDE) % 4 =
 #define ST_WARM 68
 #define ST_PQPOS 100     // state of the previous forward (stale derived quantities are recomputed from it)
 #define ST_PQVEL 136
-#define ST_INTS 168      // cur_t, motion_id, start_idx, expert_len, flags
+#define ST_INTS 168      // cur_t, motion_id, start_idx, expert_len, flags, work, episode counter, working set valid
 #define ST_RFC 176       // rfc_score, rest_force3, rest_torque3, n contact geoms
 #define ST_STRIDE 192

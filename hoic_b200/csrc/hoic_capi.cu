@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(32) k_reset(BatchDev B, const uint8_t* __restr
   const int mlen = B.motion_len[mid];
   sidx = min(max(sidx, 0), mlen - 1);
   __syncwarp();
-  if (lane == 0) { ints[0] = 0; ints[1] = mid; ints[2] = sidx; ints[3] = mlen - sidx; ints[6] = episode + 1; }
+  if (lane == 0) { ints[0] = 0; ints[1] = mid; ints[2] = sidx; ints[3] = mlen - sidx; ints[6] = episode + 1; ints[7] = 0; }
   EnvCtx ctx;
   ctx.motion = B.frames + (size_t)(B.motion_offset[mid] + sidx) * H_FRAME;
   ctx.expert_len = mlen - sidx; ctx.cur_t = 0; ctx.start_ind = 0;
@@ -132,6 +132,7 @@ __global__ void k_set_state(BatchDev B, const float* qpos, const float* qvel, co
     if (warm) st[ST_WARM + k] = warm[env * 32 + k];
   }
   if (cur_t && k == 0) ((int*)(st + ST_INTS))[0] = cur_t[env];
+  if ((qpos || qvel) && k == 0) ((int*)(st + ST_INTS))[7] = 0;      // the step pipeline's working set no longer matches the state
 }
 __global__ void k_get_rfc(BatchDev B, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(32) k_substep_debug(BatchDev B, const float* c
   st[ST_WARM + lane] = s[S_WARM + lane];
   st[ST_PQPOS + lane] = pq;
   st[ST_PQVEL + lane] = pv;
-  if (lane == 0) { st[ST_QPOS + 32] = s[S_QPOS + 32]; st[ST_PQPOS + 32] = pq32; }
+  if (lane == 0) { st[ST_QPOS + 32] = s[S_QPOS + 32]; st[ST_PQPOS + 32] = pq32; ((int*)(st + ST_INTS))[7] = 0; }
   flush_counters(B, cnt, lane, 0);
 }
 
@@ -780,6 +781,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   CUDA_OKP(cudaMemset(b->b.state, 0, (size_t)n_envs * ST_STRIDE * sizeof(float)));
   CUDA_OKP(cudaMalloc(&b->b.old_geom, (size_t)n_envs * (HN * 12 + 4) * sizeof(float)));
   CUDA_OKP(cudaMalloc(&b->b.csum, (size_t)n_envs * CSUM_STRIDE * sizeof(float)));
+  CUDA_OKP(cudaMalloc(&b->b.csum_carry, (size_t)n_envs * CSUM_STRIDE * sizeof(float)));
   CUDA_OKP(cudaMalloc(&b->b.counters, 16 * sizeof(unsigned long long)));
   CUDA_OKP(cudaMemset(b->b.counters, 0, 16 * sizeof(unsigned long long)));
   CUDA_OKP(cudaMalloc(&b->reward_w, 24 * sizeof(float)));
@@ -833,7 +835,7 @@ extern "C" void hoic_batch_destroy(hoic_batch* b) {
     if (b->part_stream[j]) cudaStreamDestroy(b->part_stream[j]);
     if (b->aux_stream[j]) cudaStreamDestroy(b->aux_stream[j]);
   }
-  cudaFree(b->env_model_dev); cudaFree(b->b.scratch); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum);
+  cudaFree(b->env_model_dev); cudaFree(b->b.scratch); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum); cudaFree(b->b.csum_carry);
   cudaFree(b->env_model_idx); cudaFree(b->samp_off); cudaFree(b->samp_ids); cudaFree(b->order);
   cudaFree(b->reward_w); cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
   delete b;

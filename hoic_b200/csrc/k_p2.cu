@@ -32,17 +32,25 @@ __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, Ste
   if (k >= 0) { LD_FIELD(QPOS); LD_FIELD(QVEL); LD_FIELD(COM); LD_FIELD(CDOF); }
   ld_wait();
   // work = this slot holds an env that is still running this step (k = -1: whose previous state had a forward)
-  const bool work = es.live && k < m.sim_step && (k < 0 ? !(misc[MI_FLAGS] & 1) : !env_dead(misc));
+  // (k = -1 is skipped for an env whose working set was carried over from the previous step, see k_p1)
+  const bool work = es.live && k < m.sim_step && (k < 0 ? !(misc[MI_FLAGS] & 1) && !misc[MI_CARRIED] : !env_dead(misc));
   float* csum = B.csum + (size_t)env * CSUM_STRIDE;
   unsigned c0 = 0, c1 = 0;
   P2_SYNC();
   if (work) {
     collide(s, m, lane, c0, c1);
     if (k + 1 < m.sim_step) record_contacts(s, m, lane, csum);
+    else {
+      // the last forward's contacts are what the NEXT env.step records first (record_contact runs before sim.step(), S2)
+      float* carry = B.csum_carry + (size_t)env * CSUM_STRIDE;
+      for (int i = lane; i < CSUM_STRIDE; i += 32) carry[i] = 0.f;
+      __syncwarp();
+      record_contacts(s, m, lane, carry);
+    }
     if (lane == 0) { misc[MI_C_MPRCALLS] += (int)c0; misc[MI_C_MPRITERS] += (int)c1; }
   }
   if (k < 0) {
-    if (!es.live || k >= m.sim_step) return;
+    if (!es.live || k >= m.sim_step || misc[MI_CARRIED]) return;
     if (work) {
       // snapshot of the geom poses for the averaged velocities (ho_im4.py:508-511)
       float* og = B.old_geom + (size_t)env * (HN * 12 + 4);

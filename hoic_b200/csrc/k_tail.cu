@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(32 * PT_W, PT_WPS / PT_W) k_tail(BatchDev B, S
     if (out.end) out.end[env] = end;
     if (out.percent) out.percent[env] = (float)ctx.cur_t / (float)(ctx.expert_len - 1);
     ints[0] = ctx.cur_t;
+    ints[7] = (flags & 3) || !ok ? 0 : 1;      // the working set holds this step's last forward: the next step starts from it
     ints[5] = (int)(cnt.newton * 8 + cnt.ncon * 2 + cnt.mpr_iters + (ncg ? 40 + 8 * ncg : 0));
     st[ST_RFC] = rfc_score;
     for (int k = 0; k < 6; k++) st[ST_RFC + 1 + k] = rest[k];
