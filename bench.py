@@ -282,7 +282,7 @@ def ppo_iteration(local, rank, world, dev, iters=3):
     infos = [agent.optimize_policy(i) for i in range(iters)]
     last = infos[-1]
     out = dict(workload=f"banana, {n_envs} envs per GPU x {last['horizon']} steps = {last['samples']} samples per iteration, GAE + "
-                        f"{cfg.num_optim_epoch} epochs (bf16 tensor cores, fp32 master weights)",
+                        f"{cfg.num_optim_epoch} epochs (rollout MLP bf16, GAE + update TF32 tensor cores, fp32 master weights)",
                T_sample=last["T_sample"], T_update=last["T_update"], T_total=last["T_total"], samples=last["samples"],
                samples_per_s=last["samples"] / last["T_total"], avg_reward=last["log"]["avg_reward"],
                value_loss=last["value_loss"], iterations_timed=iters)

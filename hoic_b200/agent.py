@@ -40,7 +40,7 @@ class TrajBatch:
 
 class AgentHandMimic:
     def __init__(self, models, n_envs, motions=None, motion_model=None, env_model_id=None, device=0, seed=None, cfg=None,
-                 policy_grad_clip=40.0, policy_dtype="bf16", graph=True):
+                 policy_grad_clip=40.0, policy_dtype="bf16", update_dtype="tf32", graph=True):
         models = [models] if not isinstance(models, (list, tuple)) else list(models)
         self.cfg = cfg or models[0].cfg
         cfg = self.cfg
@@ -82,7 +82,11 @@ class AgentHandMimic:
         self.freq_dict = {k: [] for k in range(len(motions))}
         self.max_freq = 50
         # the sampler's inner loop as one CUDA graph; MLPs on the tensor cores (bf16 operands, fp32 accumulate and master weights)
-        self.policy_dtype = policy_dtype
+        # rollout inference: bf16 operands (the action-mean error, < 1e-3 sigma at init, only perturbs the exploration noise);
+        # GAE values, log-probabilities and the PPO update: TF32 tensor cores -- with bf16 there the rounding noise of the mean
+        # enters the importance ratio exp(logp - logp_old) through (a - mu) dmu / sigma^2 with sigma = 0.1 and training
+        # became unstable (profiles/r02_train_box_2048x25_*.jsonl)
+        self.policy_dtype, self.update_dtype = policy_dtype, update_dtype
         self.stats = hdist.RolloutStats(self.device, episode_reward=self._episode_reward)
         self.sampler = SamplerStep(self.env, self.policy_net, self.running_state, self.gen, stats=self.stats,
                                    policy_dtype=policy_dtype, graph=graph)
@@ -140,12 +144,12 @@ class AgentHandMimic:
         T, N = batch.T, batch.N
         states = batch.states.reshape(T * N, -1)
         actions = batch.actions.reshape(T * N, -1)
-        with torch.no_grad(), matmul_context(self.policy_dtype):
+        with torch.no_grad(), matmul_context(self.update_dtype):
             values = self.value_net(torch.cat([states, batch.last_state], 0)).float().reshape(T + 1, N)
             adv, ret = ppo.estimate_advantages(batch.rewards, batch.masks, values, cfg.gamma, cfg.tau)
             fixed_log_probs = self.policy_net.get_log_prob(states, actions).float()
         ind = batch.exps.reshape(-1).nonzero().squeeze(1)
-        with matmul_context(self.policy_dtype):
+        with matmul_context(self.update_dtype):
             return self._ppo_update(states, actions, ret, adv, fixed_log_probs, ind)
 
     def _ppo_update(self, states, actions, ret, adv, fixed_log_probs, ind):

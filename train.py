@@ -23,7 +23,10 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--epoch", type=int, default=0, help="first epoch (adaptive schedules start here)")
     ap.add_argument("--min-batch-size", type=int, default=0, help="override cfg.min_batch_size (total over all GPUs)")
-    ap.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core matmuls in the policy / value MLPs (default: fp32; the reference runs fp64)")
+    ap.add_argument("--policy-dtype", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="arithmetic of the policy / value MLPs in rollout and update: bf16 tensor cores with fp32 accumulation and "
+                         "fp32 master weights (default), TF32 tensor cores, or the plain fp32 pipe (the reference runs fp64)")
+    ap.add_argument("--update-dtype", default="tf32", choices=["bf16", "tf32", "fp32"], help="arithmetic of GAE values / log-probabilities / the PPO update")
     ap.add_argument("--load", default="", help="checkpoint to start from (iter_XXXX.p layout of the reference)")
     ap.add_argument("--save", default="", help="write the final checkpoint here (rank 0)")
     ap.add_argument("--eval", action="store_true", help="run eval_policy (test mode, mean action) after training")
@@ -36,15 +39,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    if a.tf32:
-        torch.backends.cuda.matmul.allow_tf32 = True
-        torch.backends.cudnn.allow_tf32 = True
     if a.obj == "mixed":
         models = [load_model(o) for o in ("box", "bottle", "banana")]
         ids = hdist.mixed_model_ids(a.envs * world, 3, rank, world)
     else:
         models, ids = [load_model(a.obj)], None
-    agent = AgentHandMimic(models, a.envs, env_model_id=ids, device=local)
+    agent = AgentHandMimic(models, a.envs, env_model_id=ids, device=local, policy_dtype=a.policy_dtype, update_dtype=a.update_dtype)
     if a.min_batch_size:
         agent.cfg.min_batch_size = a.min_batch_size
     if a.load:
@@ -53,8 +53,9 @@ def main():
         info = agent.optimize_policy(i)
         if rank == 0:
             log = info.pop("log")
-            print(json.dumps(dict(iter=i, avg_reward=log["avg_reward"], episodes=log["num_episodes"],
-                                  samples_per_s=info["samples"] / info["T_total"], **{k: v for k, v in info.items()})))
+            print(json.dumps(dict(iter=i, policy_dtype=a.policy_dtype, update_dtype=a.update_dtype, avg_reward=log["avg_reward"], episodes=log["num_episodes"],
+                                  avg_episode_len=log["avg_episode_len"], avg_episode_reward=log["avg_episode_reward"],
+                                  samples_per_s=info["samples"] / info["T_total"], **{k: v for k, v in info.items()})), flush=True)
     if rank == 0 and a.save:
         agent.save_checkpoint(a.save)
     if rank == 0 and a.eval:
