@@ -117,10 +117,33 @@ class ZFilter:
         self._assign(("_dn", "_dmean", "_dm2"), self._merge(self._dn, self._dmean, self._dm2, nb, bmean, bm2))
 
     def __call__(self, x, update=True):
+        if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous():
+            return self._call_library(x, update)
         if update:
             self.update(x)
         y = (x.to(torch.float64) - self.mean) / (self.std + 1e-8)
         return torch.clamp(y, -self.clip, self.clip).to(x.dtype)
+
+    def _call_library(self, x, update):
+        """Device batches go through libhoic_b200.so (hoic_zfilter: one pass for the batch moments, one to normalise) instead
+        of a dozen torch kernels; same arithmetic (double accumulation, Chan merge)."""
+        from . import capi
+        import ctypes as C
+        L = capi.lib()
+        if getattr(self, "_lib_buf", None) is None or self._lib_buf[0].device != x.device:
+            dim = self.mean.numel()
+            self._lib_buf = (torch.zeros(16 * dim + 1, dtype=torch.float64, device=x.device),
+                             torch.zeros(2 * dim, dtype=torch.float32, device=x.device), {})
+        scratch, shift_scale, outs = self._lib_buf
+        key = (x.shape[0], torch.cuda.is_current_stream_capturing())
+        y = outs.get(key)
+        if y is None:
+            y = outs[key] = torch.empty_like(x)
+        capi.check(L.hoic_zfilter(capi.ptr(x), x.shape[0], x.shape[1], capi.ptr(self.n), capi.ptr(self.mean), capi.ptr(self.m2),
+                                  capi.ptr(self._dn), capi.ptr(self._dmean), capi.ptr(self._dm2), capi.ptr(scratch),
+                                  capi.ptr(shift_scale), float(self.clip), 1 if update else 0, capi.ptr(y),
+                                  C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "hoic_zfilter")
+        return y
 
     def set_state(self, n, mean, m2):
         """Adopt pooled statistics (checkpoint load): they become the synced base, nothing is pending."""

@@ -178,6 +178,22 @@ int hoic_get_work(hoic_batch* b, int* work /*[N]*/, void* stream);
 int hoic_set_env_order(hoic_batch* b, const int* perm /*[N] device, kept by reference*/);
 int hoic_set_balance(hoic_batch* b, int on);
 
+/* replaces running_state(state) = ZFilter.__call__ / RunningStat.push of the sampler (uhc/khrylib/utils/zfilter.py:14-24, 59-68;
+ * agent_handmimic.py:455-457, 469-470) for the whole batch obs[n][dim]: with update != 0 the batch is merged into the running
+ * statistics n / mean[dim] / M2[dim] (double, device; Chan's parallel Welford merge = what n successive push calls give) and,
+ * if given, into a second since-last-sync triple dn / dmean / dM2 (multi-rank pooling); then
+ * x_out = clip((obs - mean) / (std + 1e-8), -clip, clip) with std = sqrt(M2 / (n - 1)) (|mean| while n <= 1).
+ * scratch: double[16 dim + 1], zero-initialised once by the caller; shift_scale: float[2 dim] work buffer.  Results are bitwise
+ * reproducible (fixed summation order). */
+int hoic_zfilter(const float* obs, int n, int dim, double* st_n, double* mean, double* m2, double* dn, double* dmean, double* dm2,
+                 double* scratch, float* shift_scale, float clip, int update, float* x_out, void* stream);
+/* replaces LoggerRL.step / end_episode (uhc/khrylib/rl/core/logger_rl.py:28-44) for one batched step: sums[13] += steps,
+ * finished episodes, c_reward, reward_info[9], reward of the episodes that finished; minmax[4] = c_reward min / max, episode
+ * reward min / max; episode_reward[n] (may be NULL) = per-env running sums, cleared where done. */
+int hoic_logger_step(const float* reward, const float* reward_info, const uint8_t* done, int n, double* sums, double* minmax,
+                     double* episode_reward, void* stream);
+const char* hoic_glue_last_error(void);
+
 /* per-kernel timing of hoic_step for bench.py's roofline (off by default; not under stream capture): with it on, every
  * launch of the step pipeline is bracketed by CUDA events on the stream it runs on.  hoic_get_timing returns the summed
  * durations since hoic_set_timing(b, 1) in ms_host[8] = k_p1, k_p2, k_p3s (solver, small tier), k_p3 (full tier), k_tail,

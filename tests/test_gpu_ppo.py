@@ -138,3 +138,35 @@ def test_bf16_policy_matches_fp32_within_a_thousandth_of_sigma_and_graph_equals_
         env.close()
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_library_normaliser_and_logger_match_the_reference_arithmetic():
+    """hoic_zfilter / hoic_logger_step (device batches) against the float64 torch implementation that the CPU tests pin to
+    zfilter.py / logger_rl.py: statistics, normalised output, since-last-sync accumulators, per-episode statistics."""
+    from hoic_b200 import ppo, dist as hdist
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(2)
+    gz, cz = ppo.ZFilter((617,), clip=5.0, device=dev), ppo.ZFilter((617,), clip=5.0, device="cpu")
+    for it in range(4):
+        x = (rng.randn(1000 + 37 * it, 617) * (1 + it) + 3 * it).astype(np.float32)
+        x[:, 5] = 0.25                      # a constant observation entry
+        x[:, 7] = 1000.0 + 1e-3 * x[:, 7]   # large mean, tiny spread
+        yg = gz(torch.as_tensor(x, device=dev), update=it != 2)
+        yc = cz(torch.as_tensor(x), update=it != 2)
+        assert float(gz.n) == float(cz.n)
+        assert torch.allclose(gz.mean.cpu(), cz.mean, rtol=1e-12, atol=1e-12) and torch.allclose(gz.m2.cpu(), cz.m2, rtol=1e-9, atol=1e-9)
+        assert torch.allclose(gz._dmean.cpu(), cz._dmean, rtol=1e-12, atol=1e-12) and float(gz._dn) == float(cz._dn)
+        assert torch.allclose(yg.cpu(), yc, rtol=1e-5, atol=2e-6)
+    N = 300
+    gs = hdist.RolloutStats(dev, episode_reward=torch.zeros(N, dtype=torch.float64, device=dev))
+    cs = hdist.RolloutStats("cpu", episode_reward=torch.zeros(N, dtype=torch.float64))
+    for t in range(12):
+        r = rng.rand(N).astype(np.float32); info = rng.rand(N, 9).astype(np.float32); d = (rng.rand(N) < 0.2).astype(np.uint8)
+        gs.update(torch.as_tensor(r, device=dev), torch.as_tensor(info, device=dev), torch.as_tensor(d, device=dev))
+        cs.update(torch.as_tensor(r).double(), torch.as_tensor(info).double(), torch.as_tensor(d))
+    a, b = gs.allreduce(), cs.allreduce()
+    for k in ("num_steps", "num_episodes"):
+        assert a[k] == b[k]
+    for k in ("avg_c_reward", "avg_episode_len", "avg_episode_reward", "min_episode_reward", "max_episode_reward", "reward_min", "reward_max"):
+        assert abs(a[k] - b[k]) < 1e-9, k
+    assert np.allclose(a["info_sum"], b["info_sum"]) and torch.allclose(gs.episode_reward.cpu(), cs.episode_reward)
