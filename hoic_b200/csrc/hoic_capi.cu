@@ -134,6 +134,38 @@ __global__ void k_set_state(BatchDev B, const float* qpos, const float* qvel, co
   if (cur_t && k == 0) ((int*)(st + ST_INTS))[0] = cur_t[env];
   if ((qpos || qvel) && k == 0) ((int*)(st + ST_INTS))[7] = 0;      // the step pipeline's working set no longer matches the state
 }
+// env.cur_t / the expert assignment without touching the physics state (the tracking env re-bases its window every step)
+__global__ void k_set_episode(BatchDev B, const int* motion_id, const int* start_idx, const int* cur_t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n_envs) return;
+  int* ints = (int*)(B.state + (size_t)i * ST_STRIDE + ST_INTS);
+  int mid = ints[1], sidx = ints[2];
+  if (motion_id) mid = min(max(motion_id[i], 0), B.n_motions - 1);
+  if (start_idx) sidx = start_idx[i];
+  const int mlen = B.motion_len[mid];
+  sidx = min(max(sidx, 0), mlen - 1);
+  ints[1] = mid; ints[2] = sidx; ints[3] = mlen - sidx;
+  if (cur_t) ints[0] = cur_t[i];
+}
+// Sliding expert window of the online tracking env (HandObjMimicTest.insert_new_frame, ho_im_test.py:34-38), on the device:
+// every motion is a window kept as [w0, w0, w1, ..., wK, wK] (first and last frame duplicated); pushing a frame drops w0 and
+// appends the new frame: [w1, w1, w2, ..., wK, f, f].  One warp per motion.
+__global__ void __launch_bounds__(32) k_push_frame(float* frames, const int* __restrict__ motion_offset, const int* __restrict__ motion_len,
+                                                   int n_motions, const float* __restrict__ frame, int per_motion) {
+  const int mtn = blockIdx.x, lane = threadIdx.x;
+  if (mtn >= n_motions) return;
+  const int len = motion_len[mtn];
+  float* f = frames + (size_t)motion_offset[mtn] * H_FRAME;
+  const float* nf = frame + (size_t)(per_motion ? mtn : 0) * H_FRAME;
+  // frames 2 .. len-2 move one slot down; a lane owns the same float columns in every frame, so the in-place shift is safe
+  for (int c = lane; c < H_FRAME; c += 32) {
+    for (int k = 1; k + 2 < len; k++) f[(size_t)k * H_FRAME + c] = f[(size_t)(k + 1) * H_FRAME + c];
+    f[c] = f[H_FRAME + c];
+    const float v = nf[c];
+    f[(size_t)(len - 2) * H_FRAME + c] = v;
+    f[(size_t)(len - 1) * H_FRAME + c] = v;
+  }
+}
 __global__ void k_get_rfc(BatchDev B, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B.n_envs * 8) return;
@@ -344,7 +376,7 @@ struct hoic_batch {
   size_t tev_used = 0;
   double tacc[HOIC_TIMING_CLASSES] = {};
   int tsteps = 0;
-  int balance = 0, n_models = 0, n_samp_ids = 0;
+  int balance = 0, n_models = 0, n_samp_ids = 0, min_motion_len = 0;
   const int* user_perm = nullptr;
   size_t smem_bytes, frames_cap = 0;
   int motions_cap = 0, nsub = 0;
@@ -846,8 +878,10 @@ extern "C" int hoic_batch_size(const hoic_batch* b) { return b ? b->n_envs : -1;
 extern "C" int hoic_set_motions(hoic_batch* b, const float* frames_host, const int* motion_offset_host, const int* motion_len_host, int n_motions) {
   if (!b || !frames_host || n_motions < 1) return set_err("hoic_set_motions: bad arguments");
   size_t total = 0;
+  b->min_motion_len = motion_len_host[0];
   for (int i = 0; i < n_motions; i++) {
     if (motion_len_host[i] < 2) return set_err("hoic_set_motions: motion shorter than 2 frames");
+    b->min_motion_len = std::min(b->min_motion_len, motion_len_host[i]);
     size_t e = (size_t)motion_offset_host[i] + motion_len_host[i];
     if (e > total) total = e;
   }
@@ -1075,6 +1109,23 @@ extern "C" int hoic_set_cur_t(hoic_batch* b, const int* cur_t, void* stream) {
   if (!b || !cur_t) return set_err("hoic_set_cur_t: bad arguments");
   CUDA_OK(cudaSetDevice(b->device));
   k_set_state<<<(b->n_envs * 33 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, nullptr, nullptr, nullptr, cur_t);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_set_episode(hoic_batch* b, const int* motion_id, const int* start_idx, const int* cur_t, void* stream) {
+  if (!b) return set_err("hoic_set_episode: null batch");
+  if (!b->b.frames) return set_err("hoic_set_episode: call hoic_set_motions first");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_set_episode<<<(b->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(b->b, motion_id, start_idx, cur_t);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int hoic_push_frame(hoic_batch* b, const float* frame, int per_motion, void* stream) {
+  if (!b || !frame) return set_err("hoic_push_frame: bad arguments");
+  if (!b->b.frames) return set_err("hoic_push_frame: call hoic_set_motions first");
+  if (b->min_motion_len < 4) return set_err("hoic_push_frame: every motion must hold a window of at least 4 frames [w0, w0, .., wK, wK]");
+  CUDA_OK(cudaSetDevice(b->device));
+  k_push_frame<<<b->b.n_motions, 32, 0, (cudaStream_t)stream>>>(b->frames, b->motion_offset, b->motion_len, b->b.n_motions, frame, per_motion);
   LAUNCH_CHECK();
   return 0;
 }

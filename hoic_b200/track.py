@@ -3,16 +3,19 @@ reference's inference server drives (InferenceServer/RLTest.py): the expert is n
 of `future_w_size + 1` frames that the tracker refills one frame per step (`insert_new_frame`), and every expert lookup is
 relative to the window (`get_expert_attr(attr, delta_t)`), whatever `cur_t` is.
 
-It runs on the same kernels as training.  The kernels index the expert as `cur_t + delta_t` (ho_im4.py:739-792), use
-`cur_t` for the PD target during the substeps and `cur_t + 1` for termination / reward / observation after them, so the
-window `w0 .. w5` is laid out per env as a 7-frame motion
+It runs on the same kernels as training.  The kernels index the expert as `start_idx + cur_t + delta_t` (ho_im4.py:739-792),
+use `cur_t` for the PD target during the substeps and `cur_t + 1` for termination / reward / observation after them.  The
+window `w0 .. w5` lives ON THE DEVICE as one 8-frame motion per env, `[w0, w0, w1, w2, w3, w4, w5, w5]`:
 
-    after reset  (cur_t = 0):  [w0, w1, w2, w3, w4, w5, w5]   state <- w0, observation targets w1 .. w5
-    for a step   (cur_t = 0):  [w0, w0, w1, w2, w3, w4, w5]   PD tracks w0; afterwards (cur_t = 1) the tracking error and the
-                                                             reward are against w0, the observation targets are w1 .. w5
+    reset        (start_idx 1, cur_t 0):  sees [w0, w1, w2, w3, w4, w5, w5]   state <- w0, observation targets w1 .. w5
+    step         (start_idx 0, cur_t 0):  sees [w0, w0, w1, w2, w3, w4, w5]   PD tracks w0; afterwards (cur_t = 1) the tracking
+                                                                             error and the reward are against w0, the
+                                                                             observation targets are w1 .. w5
 
-which is exactly what the window-relative accessors of ho_im_test.py:40-75 return.  `end` is meaningless here (the window
-never ends) and is not reported; `fail` keeps the tracking-error thresholds (the reference builds this env in mode 'train').
+which is exactly what the window-relative accessors of ho_im_test.py:40-75 return.  `insert_new_frame` is `hoic_push_frame`
+(a device-side shift of every window: only the new frame crosses the PCIe bus), `step(actions, values=...)` adds the inference
+server's value-threshold reset (InferenceServer/RLTest.py:283-299).  `end` is meaningless here (the window never ends) and is
+not reported; `fail` keeps the tracking-error thresholds (the reference builds this env in mode 'train').
 """
 from __future__ import annotations
 
@@ -43,24 +46,32 @@ class HandMimicTrackEnv:
         if w.ndim == 2:
             w = np.broadcast_to(w[None], (self.n_envs,) + w.shape)
         assert w.shape == (self.n_envs, W, capi.FRAME_DIM), w.shape
-        self.expert_window = np.array(w, dtype=np.float32)          # [N, W, 212], slot order = age (index 0 = current frame)
-        motions = [self._as_expert(self._reset_layout()[i]) for i in range(self.n_envs)]
+        table = np.concatenate([w[:, :1], w, w[:, -1:]], axis=1)        # [w0, w0, w1 .. w5, w5] per env
+        motions = [self._as_expert(table[i]) for i in range(self.n_envs)]
         self.env = HandMimicVecEnv(model, self.n_envs, motions, motion_model=[0] * self.n_envs, device=device, seed=seed,
                                    auto_reset=False, random_start=False, balance=False)
-        self._ids = list(range(self.n_envs))
+        dev = self.env.device
+        self.expert_window = torch.as_tensor(np.ascontiguousarray(w), dtype=torch.float32, device=dev)   # [N, W, 212], index 0 = current frame
+        self._ids = torch.arange(self.n_envs, dtype=torch.int32, device=dev)
+        self._zero = torch.zeros(self.n_envs, dtype=torch.int32, device=dev)
+        self._one = torch.ones(self.n_envs, dtype=torch.int32, device=dev)
         self.obs_dim, self.act_dim = self.env.obs_dim, self.env.act_dim
 
     # ---- window bookkeeping (ho_im_test.py:34-43)
     def insert_new_frame(self, frame):
-        """Drop the oldest frame of every env's window and append `frame` ([n_envs, 212], [212], or a frame dict)."""
-        f = _pack(frame)
-        if f.ndim == 1:
-            f = np.broadcast_to(f[None], (self.n_envs, capi.FRAME_DIM))
-        self.expert_window = np.concatenate([self.expert_window[:, 1:], f[:, None]], axis=1)
+        """Drop the oldest frame of every env's window and append `frame` ([n_envs, 212], [212], a frame dict, or a device tensor)."""
+        dev = self.env.device
+        f = frame if isinstance(frame, torch.Tensor) else torch.as_tensor(_pack(frame))
+        f = f.to(device=dev, dtype=torch.float32)
+        per = f.dim() == 2
+        f = f.contiguous()
+        assert f.shape[-1] == capi.FRAME_DIM and (not per or f.shape[0] == self.n_envs)
+        capi.check(self.env.L.hoic_push_frame(self.env._hb, capi.ptr(f), 1 if per else 0, self.env._stream()), "hoic_push_frame")
+        self.expert_window = torch.cat([self.expert_window[:, 1:], (f if per else f.expand(self.n_envs, -1))[:, None]], dim=1)
 
     def get_expert_attr(self, attr, ind, env=0):
         assert ind <= self.w_size
-        ex = self._as_expert(self.expert_window[env])
+        ex = self._as_expert(self.expert_window[env].cpu().numpy())
         return ex[attr][ind].copy()
 
     @staticmethod
@@ -68,25 +79,29 @@ class HandMimicTrackEnv:
         from .dataset import unpack_frames
         return unpack_frames(np.asarray(frames, dtype=np.float64))
 
-    def _reset_layout(self):
-        w = self.expert_window
-        return np.concatenate([w, w[:, -1:]], axis=1)            # [w0 .. w5, w5]
-
-    def _step_layout(self):
-        w = self.expert_window
-        return np.concatenate([w[:, :1], w], axis=1)             # [w0, w0 .. w5]
-
     # ---- env surface
-    def reset(self):
-        """ho_im_test.py:77-91: state <- the window's current frame, observation against the rest of the window."""
-        self.env.set_motion_frames(self._reset_layout())
-        return self.env.reset(motion_id=self._ids, start_idx=[0] * self.n_envs)
+    def reset(self, mask=None):
+        """ho_im_test.py:77-91 (`env.reset(True)`): state <- the window's current frame, observation against the rest of the
+        window; `mask` restricts it to some envs (the others keep their state and their row of the returned observation)."""
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=self.env.device).to(torch.uint8).contiguous()
+        e = self.env
+        capi.check(e.L.hoic_reset(e._hb, capi.ptr(mask), capi.ptr(self._ids), capi.ptr(self._one), capi.ptr(e.obs), e._stream()), "hoic_reset")
+        return e.obs
 
-    def step(self, actions):
-        self.env.set_motion_frames(self._step_layout())
-        self.env.set_cur_t([0] * self.n_envs)
-        obs, reward, done, info = self.env.step(actions)
-        return obs, reward, info["fail"], {"fail": info["fail"], "reward_info": info["reward_info"]}
+    def step(self, actions, values=None, reset_threshold=12.0):
+        """One tracking step.  `values`: V(s) of the observation the actions were computed from; envs whose value is below
+        `reset_threshold` are re-initialised on the window's current frame after the step (RLTest.py:283-299) and
+        `info["reset"]` marks them."""
+        e = self.env
+        capi.check(e.L.hoic_set_episode(e._hb, None, capi.ptr(self._zero), capi.ptr(self._zero), e._stream()), "hoic_set_episode")
+        obs, reward, done, info = e.step(actions)
+        out = {"fail": info["fail"], "reward_info": info["reward_info"]}
+        if values is not None:
+            lost = torch.as_tensor(values, device=e.device).reshape(-1) < reset_threshold
+            out["reset"] = lost
+            obs = self.reset(mask=lost)
+        return obs, reward, info["fail"], out
 
     def set_mode(self, mode):
         self.env.set_mode(mode)

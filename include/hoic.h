@@ -151,6 +151,14 @@ int hoic_get_state(hoic_batch* b, float* qpos /*[N][33]*/, float* qvel /*[N][32]
 int hoic_set_state(hoic_batch* b, const float* qpos, const float* qvel, void* stream);
 /* sets env.cur_t (parity tests start from arbitrary expert frames) */
 int hoic_set_cur_t(hoic_batch* b, const int* cur_t, void* stream);
+/* env.cur_t and the expert assignment (motion, start_idx) of every env without touching its physics state; any pointer NULL */
+int hoic_set_episode(hoic_batch* b, const int* motion_id, const int* start_idx, const int* cur_t, void* stream);
+/* replaces HandObjMimicTest.insert_new_frame (uhc/envs/ho_im_test.py:34-38; driven by InferenceServer/RLTest.py:254-303) on the
+ * device: every motion of the batch is a sliding expert window stored as [w0, w0, w1, ..., wK, wK]; the call drops w0 and
+ * appends the new frame -> [w1, w1, w2, ..., wK, f, f].  frame: [n_motions][212] (per_motion != 0) or one [212] frame for all,
+ * device memory.  With that layout `hoic_reset(start_idx = 1)` sees [w0 .. wK, wK] and a step from (start_idx 0, cur_t 0) sees
+ * [w0, w0 .. wK]: exactly the window-relative accessors of ho_im_test.py:40-75 (hoic_b200/track.py). */
+int hoic_push_frame(hoic_batch* b, const float* frame, int per_motion, void* stream);
 /* qacc_warmstart in/out (data.qacc_warmstart); parity entry */
 int hoic_get_warmstart(hoic_batch* b, float* warm /*[N][32]*/, void* stream);
 int hoic_set_warmstart(hoic_batch* b, const float* warm, void* stream);

@@ -251,3 +251,37 @@ def test_blown_up_env_reports_fail_with_finite_outputs():
     assert np.array_equal(obs[0], obs[1]) and np.array_equal(obs[0], obs[7]) and r[0] > 0
     assert env.counters()["fail_physics"] == 2
     env.close()
+
+
+def test_tracking_env_value_threshold_reset_and_device_window():
+    """The inference server's loop (InferenceServer/RLTest.py:283-299): insert_new_frame -> env.step -> `if value <
+    reset_threshold: obs = env.reset(True)`.  The window lives on the device (hoic_push_frame); an env whose value is below the
+    threshold restarts on the window's current frame, the other keeps tracking."""
+    from hoic_b200 import motion as hmotion
+    from hoic_b200.track import HandMimicTrackEnv
+    mdl = model("box")
+    frames = hmotion.pack_frames(mdl.motion(1)).astype(np.float32)
+    t0 = 60
+    window = frames[t0:t0 + 6].copy()
+    trk = HandMimicTrackEnv(mdl, 2, np.stack([window, window]))
+    trk.reset()
+    a = torch.zeros(2, 32)
+    for step in range(3):
+        new = frames[t0 + 6 + step]
+        trk.insert_new_frame(new)                       # one [212] frame for all envs, H2D of 848 bytes
+        window = np.concatenate([window[1:], new[None]])
+        values = torch.tensor([20.0, 5.0 if step == 2 else 20.0])
+        obs, r, fail, info = trk.step(a, values=values, reset_threshold=12.0)
+        assert info["reset"].cpu().tolist() == [False, step == 2]
+        assert np.allclose(trk.expert_window.cpu().numpy()[1], window) and np.allclose(trk.get_expert_attr("hand_dof_seq", 0), window[0, :26])
+    q, v = [x.cpu().numpy() for x in trk.get_state()]
+    # env 1 was re-initialised on the current frame of the window (hand dofs + object pose, expert velocities) ...
+    assert np.abs(q[1, :26] - window[0, 0:26]).max() < 1e-6 and np.abs(q[1, 26:29] - window[0, 52:55]).max() < 1e-6
+    assert np.abs(v[1, :26] - window[0, 26:52]).max() < 1e-6
+    # ... env 0 kept tracking (it lags the expert by its control error)
+    assert np.abs(q[0, :26] - window[0, 0:26]).max() > 1e-5
+    # and env 1's observation is the reset observation of that window
+    ref = HandMimicTrackEnv(mdl, 1, window[None])
+    assert np.abs(ref.reset().cpu().numpy()[0] - obs.cpu().numpy()[1]).max() < 1e-6
+    ref.close()
+    trk.close()
