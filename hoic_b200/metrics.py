@@ -3,7 +3,7 @@
 The reference loops over the frames on the CPU (`sim.forward()` per frame, one `qpsolvers` call per frame); here every
 frame is one environment of a `HandMimicVecEnv`, the hand-object contacts of all frames come from one forward pass and the
 per-frame stability QPs (`solve_force`, :156-196) are solved by `hoic_solve_wrench_qp`, one warp per frame.
-`eval_penetration` (pysdf signed distances to the visual mesh) is not rebuilt; `eval_penetration2` (the box-specific
+`eval_penetration` evaluates the mesh's signed distance with `mesh_sdf` below (pysdf is not available); `eval_penetration2` (the box-specific
 analytic depth) is.  There is no CPU path.
 """
 from __future__ import annotations
@@ -83,6 +83,47 @@ def _matrix_to_axis_angle(R):
     return q[..., 1:] / s[..., None]
 
 
+def mesh_sdf(points, tri, chunk=512):
+    """Signed distance of `points` [P, 3] to the closed triangle mesh `tri` [F, 3, 3], POSITIVE INSIDE (pysdf's convention,
+    scripts/metrics.py:49-50, 68-70): exact point-triangle distance (Ericson's closest point on triangle), sign from the
+    generalised winding number (sum of the triangles' signed solid angles / 4 pi > 1/2).  Batched torch ops, any device."""
+    tri = tri.to(points.dtype)
+    a, b, c = tri[:, 0], tri[:, 1], tri[:, 2]
+    out = torch.empty(points.shape[0], dtype=points.dtype, device=points.device)
+    for s in range(0, points.shape[0], chunk):
+        p = points[s:s + chunk, None, :]                                   # [p, 1, 3]
+        ab, ac, ap = b - a, c - a, p - a
+        d1, d2 = (ab * ap).sum(-1), (ac * ap).sum(-1)
+        bp = p - b
+        d3, d4 = (ab * bp).sum(-1), (ac * bp).sum(-1)
+        cp = p - c
+        d5, d6 = (ab * cp).sum(-1), (ac * cp).sum(-1)
+        va, vb, vc = d3 * d6 - d5 * d4, d5 * d2 - d1 * d6, d1 * d4 - d3 * d2
+        eps = torch.finfo(points.dtype).tiny
+        # interior of the face by default, then the edge / vertex regions override (Ericson, Real-Time Collision Detection 5.1.5)
+        denom = 1.0 / (va + vb + vc).clamp_min(eps)
+        v, w = vb * denom, vc * denom
+        q = a + ab * v[..., None] + ac * w[..., None]
+        wbc = ((d4 - d3) / ((d4 - d3) + (d5 - d6)).clamp_min(eps))[..., None]
+        q = torch.where(((va <= 0) & (d4 - d3 >= 0) & (d5 - d6 >= 0))[..., None], b + (c - b) * wbc, q)
+        wac = (d2 / (d2 - d6).clamp_min(eps))[..., None]
+        q = torch.where(((vb <= 0) & (d2 >= 0) & (d6 <= 0))[..., None], a + ac * wac, q)
+        wab = (d1 / (d1 - d3).clamp_min(eps))[..., None]
+        q = torch.where(((vc <= 0) & (d1 >= 0) & (d3 <= 0))[..., None], a + ab * wab, q)
+        q = torch.where(((d6 >= 0) & (d5 <= d6))[..., None], c.expand_as(q), q)
+        q = torch.where(((d3 >= 0) & (d4 <= d3))[..., None], b.expand_as(q), q)
+        q = torch.where(((d1 <= 0) & (d2 <= 0))[..., None], a.expand_as(q), q)
+        dist = (p - q).norm(dim=-1).min(dim=1).values
+        # winding number: solid angle of every triangle seen from p (Van Oosterom & Strackee)
+        ra, rb, rc = a - p, b - p, c - p
+        la, lb, lc = ra.norm(dim=-1), rb.norm(dim=-1), rc.norm(dim=-1)
+        num = (ra * torch.cross(rb, rc, dim=-1)).sum(-1)
+        den = la * lb * lc + (ra * rb).sum(-1) * lc + (rb * rc).sum(-1) * la + (rc * ra).sum(-1) * lb
+        wind = (2.0 * torch.atan2(num, den)).sum(1) / (4.0 * np.pi)
+        out[s:s + chunk] = torch.where(wind.abs() > 0.5, dist, -dist)
+    return out
+
+
 class PhysMetrics:
     """`PhysMetrics(model, qpos_seq, obj_mesh_fn)` of the reference with the model given as a compiled `Model`;
     `qpos_seq` [T, 33] at 30 Hz."""
@@ -115,6 +156,22 @@ class PhysMetrics:
     # ---- scripts/metrics.py:141-153
     def eval_contact_point(self):
         return self.ho_mask.sum(1)
+
+    # ---- scripts/metrics.py:52-75: signed distance (positive inside) of the object's mesh at every hand-object contact position,
+    # negative values clamped to 0, mean over the frame's contacts, in mm.  `obj_mesh`: path of a binary STL (read raw like
+    # trimesh.load_mesh does: no MJCF scale) or a [F, 3, 3] triangle array.
+    def eval_penetration(self, obj_mesh):
+        from . import mjcf
+        tri = mjcf.load_stl(obj_mesh, 1.0) if isinstance(obj_mesh, str) else np.asarray(obj_mesh, dtype=np.float64)
+        tri = torch.as_tensor(tri, dtype=torch.float32, device=self.device)
+        obj_pos, R = self.qpos_seq[:, -7:-4], _quat_to_mat(self.qpos_seq[:, -4:])
+        local = torch.einsum("tji,tcj->tci", R, self.contact_pos - obj_pos[:, None, :])        # R^-1 (p - obj_pos)
+        idx = self.ho_mask.nonzero()
+        pene = torch.zeros(self.qpos_seq.shape[0], device=self.device)
+        if idx.numel():
+            sdf = mesh_sdf(local[idx[:, 0], idx[:, 1]], tri).clamp_min(0.0)
+            pene.index_add_(0, idx[:, 0], sdf)
+        return pene * 1000 / torch.clamp(self.ho_mask.sum(1), min=1)
 
     # ---- scripts/metrics.py:76-101 (box only: depth of each hand-object contact point inside the box, x2, in mm, / ncon)
     def eval_penetration2(self):

@@ -285,3 +285,25 @@ def test_tracking_env_value_threshold_reset_and_device_window():
     assert np.abs(ref.reset().cpu().numpy()[0] - obs.cpu().numpy()[1]).max() < 1e-6
     ref.close()
     trk.close()
+
+
+def test_sdf_penetration_metric():
+    """PhysMetrics.eval_penetration (scripts/metrics.py:52-75, pysdf on the object's mesh): on the box the mesh SDF at a contact
+    point inside the box equals the analytic depth of eval_penetration2 (:76-101, which doubles it and divides by ALL
+    contacts); on the banana it runs on the collision hull triangles and stays within the contact depths."""
+    from hoic_b200.metrics import PhysMetrics
+    mdl = model("box")
+    ex = mdl.motion(1)
+    qpos = np.concatenate([ex["hand_dof_seq"], ex["obj_pose_seq"]], 1)[80:200]
+    pm = PhysMetrics(mdl, qpos)
+    h = np.array([0.0165, 0.0265, 0.049])
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64) * h
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    tri = np.array([[corners[q[0]], corners[q[1]], corners[q[2]]] for q in quads] + [[corners[q[0]], corners[q[2]], corners[q[3]]] for q in quads])
+    p1 = pm.eval_penetration(tri).cpu().numpy()
+    p2 = pm.eval_penetration2().cpu().numpy()
+    nho, ncon = pm.eval_contact_point().cpu().numpy(), pm.ncon.cpu().numpy()
+    assert nho.max() >= 2 and p1.max() > 0
+    assert np.abs(p1 * np.maximum(nho, 1) * 2 - p2 * np.maximum(ncon, 1)).max() < 1e-3
+    pm2 = PhysMetrics(model("banana"), np.concatenate([model("banana").motion(1)["hand_dof_seq"], model("banana").motion(1)["obj_pose_seq"]], 1)[100:160])
+    assert pm2.eval_contact_point().max() >= 1

@@ -857,3 +857,33 @@ def test_oracle_reproduces_the_large_state_sets():
             assert np.array_equal(con[:, 13:15].astype(int), G["sub_pairs"][i][:len(con)].astype(int))
             assert np.abs(env.get("qpos") - G["sub_q1"][i]).max() < 1e-12 and np.abs(env.get("qvel") - G["sub_v1"][i]).max() < 1e-10
         env.close()
+
+
+def test_mesh_sdf_positive_inside_against_closed_forms():
+    """hoic_b200.metrics.mesh_sdf (stands in for pysdf in PhysMetrics.eval_penetration, scripts/metrics.py:49-75): signed distance
+    to a closed triangle mesh, positive inside.  Checked on a box (closed form) and on a finely tessellated sphere."""
+    import torch
+    from hoic_b200.metrics import mesh_sdf
+    h = np.array([0.3, 0.2, 0.5])
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64) * h
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    tri = np.array([[corners[q[0]], corners[q[1]], corners[q[2]]] for q in quads] + [[corners[q[0]], corners[q[2]], corners[q[3]]] for q in quads])
+    rng = np.random.RandomState(0)
+    p = rng.uniform(-0.8, 0.8, (400, 3))
+    d = np.abs(p) - h
+    exact = -(np.linalg.norm(np.maximum(d, 0), axis=1) + np.minimum(d.max(1), 0))      # box SDF, positive inside
+    got = mesh_sdf(torch.as_tensor(p), torch.as_tensor(tri)).numpy()
+    assert np.abs(got - exact).max() < 1e-12 and (got > 0).sum() > 20 and (got < 0).sum() > 20
+    # icosphere-like tessellation: |sdf - (r - |p|)| bounded by the sagitta of the facets
+    n, r = 40, 0.4
+    th, ph = np.linspace(0, np.pi, n + 1), np.linspace(0, 2 * np.pi, 2 * n + 1)
+    P = lambda i, j: r * np.array([np.sin(th[i]) * np.cos(ph[j]), np.sin(th[i]) * np.sin(ph[j]), np.cos(th[i])])
+    tris = []
+    for i in range(n):
+        for j in range(2 * n):
+            a, b, c, e = P(i, j), P(i + 1, j), P(i + 1, j + 1), P(i, j + 1)
+            if i > 0: tris.append([a, b, e])
+            if i < n - 1: tris.append([b, c, e])
+    q = rng.uniform(-0.6, 0.6, (200, 3))
+    got = mesh_sdf(torch.as_tensor(q), torch.as_tensor(np.array(tris))).numpy()
+    assert np.abs(got - (r - np.linalg.norm(q, axis=1))).max() < 2e-3 and ((got > 0) == (np.linalg.norm(q, axis=1) < r)).mean() > 0.98
