@@ -887,3 +887,67 @@ def test_mesh_sdf_positive_inside_against_closed_forms():
     q = rng.uniform(-0.6, 0.6, (200, 3))
     got = mesh_sdf(torch.as_tensor(q), torch.as_tensor(np.array(tris))).numpy()
     assert np.abs(got - (r - np.linalg.norm(q, axis=1))).max() < 2e-3 and ((got > 0) == (np.linalg.norm(q, axis=1) < r)).mean() > 0.98
+
+
+@pytest.mark.parametrize("obj", ["box", "banana"])
+def test_compiled_constants_vs_an_independent_route(obj):
+    """mj_setConst constants of the model blob (`stat_meaninertia`, `dof_invweight0`, `body_invweight0`: they set R of every
+    constraint row) recomputed WITHOUT hoic_b200.mjcf's mass_matrix / Jacobians: M at qpos0 from the oracle's C
+    composite-rigid-body pass, body-CoM Jacobians by central finite differences of the oracle's forward kinematics."""
+    mdl = model(obj)
+    A = mdl.arrays
+    nv, nb = 32, int(A["nbody"][0])
+    env = oracle_env(obj)
+    q0 = np.asarray(A["qpos0"], dtype=np.float64).copy()
+    env.set_state(q0, np.zeros(nv))
+    H = env.qM().reshape(nv, nv)
+    Hinv = np.linalg.inv(H)
+    assert abs(float(A["stat_meaninertia"][0]) - np.trace(H) / nv) < 1e-12
+    dw = np.diag(Hinv).copy()
+    dw[26:29] = dw[26:29].mean(); dw[29:32] = dw[29:32].mean()        # the object's free joint: translation / rotation averages
+    assert np.abs(np.asarray(A["dof_invweight0"]) - dw).max() < 1e-9 * np.abs(dw).max()
+    ipos = np.asarray(A["body_ipos"]).reshape(nb, 3)
+
+    def quat2mat(q):
+        w, x, y, z = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+    def com_and_rot(q):
+        env.set_state(q, np.zeros(nv))
+        xp, xq = env.get("xpos").reshape(-1, 3)[:nb], env.get("xquat").reshape(-1, 4)[:nb]
+        R = np.array([quat2mat(xq[b]) for b in range(nb)])
+        return xp + np.einsum("bij,bj->bi", R, ipos), R
+
+    def perturb(q, d, eps):
+        q = q.copy()
+        if d < 26:
+            q[d] += eps
+        elif d < 29:
+            q[d] += eps
+        else:                                   # rotation about the object's body axis d - 29
+            ax = np.zeros(3); ax[d - 29] = 1.0
+            dq = np.concatenate([[np.cos(eps / 2)], np.sin(eps / 2) * ax])
+            w0, x0, y0, z0 = q[29:33]; w1, x1, y1, z1 = dq
+            q[29:33] = [w0 * w1 - x0 * x1 - y0 * y1 - z0 * z1, w0 * x1 + x0 * w1 + y0 * z1 - z0 * y1,
+                        w0 * y1 - x0 * z1 + y0 * w1 + z0 * x1, w0 * z1 + x0 * y1 - y0 * x1 + z0 * w1]
+        return q
+
+    eps = 1e-6
+    Jp, Jr = np.zeros((nb, 3, nv)), np.zeros((nb, 3, nv))
+    for d in range(nv):
+        cp, Rp = com_and_rot(perturb(q0, d, eps))
+        cm, Rm = com_and_rot(perturb(q0, d, -eps))
+        Jp[:, :, d] = (cp - cm) / (2 * eps)
+        dR = np.einsum("bij,bkj->bik", Rp, Rm)                        # R+ R-^T ~ I + [w]x * 2 eps
+        Jr[:, :, d] = np.stack([dR[:, 2, 1] - dR[:, 1, 2], dR[:, 0, 2] - dR[:, 2, 0], dR[:, 1, 0] - dR[:, 0, 1]], 1) / (4 * eps)
+    bw = np.asarray(A["body_invweight0"]).reshape(nb, 2)
+    weld = np.asarray(A["body_weldid"])
+    for b in range(1, nb):
+        if weld[b] == 0:
+            continue
+        t = np.trace(Jp[b] @ Hinv @ Jp[b].T) / 3
+        r = np.trace(Jr[b] @ Hinv @ Jr[b].T) / 3
+        assert abs(bw[b, 0] - t) < 1e-5 * max(t, 1e-12) and abs(bw[b, 1] - r) < 1e-5 * max(r, 1e-12), (b, bw[b], t, r)
+    env.close()
