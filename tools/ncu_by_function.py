@@ -32,6 +32,11 @@ for r in rows[2:]:
 ti = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values())
 print(f"{'function':45s} {'inst %':>7s} {'samples %':>9s} {'lanes':>6s}  top stall reasons (% of the function's samples)")
 for k, v in sorted(agg.items(), key=lambda x: -x[1][0]):
-    print(f"{re.sub(r'^_Z[0-9]+', '', k)[:45]:45s} {100*v[0]/ti:7.2f} {100*v[1]/max(ts,1):9.2f} {v[2]/max(v[0],1):6.1f}  " +
+    nm = re.sub(r'^_ZN\d+_INTERNAL_[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]+', '', k)
+    nm = re.sub(r'^_Z[0-9]+', '', nm)
+    m2 = re.match(r'^(\d+)(.*)$', nm)
+    if m2:
+        nm = m2.group(2)[:int(m2.group(1))]
+    print(f"{nm[:45]:45s} {100*v[0]/ti:7.2f} {100*v[1]/max(ts,1):9.2f} {v[2]/max(v[0],1):6.1f}  " +
           " ".join(f"{n}:{100*c/max(sum(stalls[k].values()),1):.0f}" for n, c in stalls[k].most_common(5)))
 print("total inst", ti, "samples", ts)

@@ -1,0 +1,79 @@
+"""Turn the captures of tools/profile_r02.sh (gpurun_out/r02_final_*) into the tracked summaries under profiles/:
+launch-list summary, DRAM traffic per hoic_step (profiles/r02_dram_traffic.json, read by bench.py), raw ncu pages and
+per-function tables of the pipeline kernels.   python tools/summarise_profiles.py"""
+import collections, csv, json, os, shutil, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+
+def rows_of(path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    return rows[hi], rows[hi + 2:]
+
+
+def launch_summary(src, dst, title):
+    h, rows = rows_of(src)
+    ik, iv, im = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Name")
+    agg = collections.defaultdict(list)
+    for r in rows:
+        if len(r) > iv and r[im] == "gpu__time_duration.sum":
+            agg[r[ik].split("(")[0][:60]].append(float(r[iv].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(title + "\n")
+        for k, v in sorted(agg.items(), key=lambda x: -sum(x[1])):
+            f.write(f"{k:62s} n={len(v):5d} mean={sum(v)/len(v)/1e3:9.1f} us  total={sum(v)/1e6:9.3f} ms {100*sum(v)/tot:5.1f}%\n")
+    return agg
+
+
+if os.path.exists(os.path.join(G, "r02_final_bench_launches.csv")):
+    shutil.copy(os.path.join(G, "r02_final_bench_launches.csv"), os.path.join(P, "r02_final_bench_launches.csv"))
+    launch_summary(os.path.join(G, "r02_final_bench_launches.csv"), os.path.join(P, "r02_final_bench_launch_summary.txt"),
+                   "ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 2 --warmup 1 --preroll 2 --no-extras --no-cpu "
+                   "(box, 4096 envs; kernels of the replayed CUDA graphs are profiled one by one: cold, serialised)")
+
+tp = os.path.join(G, "r02_final_step_traffic.csv")
+if os.path.exists(tp):
+    h, rows = rows_of(tp)
+    ik, iv, im = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Name")
+    per = collections.defaultdict(lambda: collections.defaultdict(float))
+    n_tail = 0
+    for r in rows:
+        if len(r) <= iv:
+            continue
+        k = r[ik].split("(")[0]
+        per[k][r[im]] += float(r[iv].replace(",", ""))
+        if k == "k_tail" and r[im] == "gpu__time_duration.sum":
+            n_tail += 1
+    steps = n_tail / 2.0                       # two batch parts per hoic_step
+    tot = sum(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for k, v in per.items() if k.startswith("k_"))
+    unit = h[h.index("Metric Unit")] if "Metric Unit" in h else "byte"
+    iu = h.index("Metric Unit")
+    units = {r[im]: r[iu] for r in rows if len(r) > iu}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units.get("dram__bytes_read.sum", "byte"), 1.0)
+    out = {"box:4096": tot * scale / max(steps, 1)}
+    json.dump(out, open(os.path.join(P, "r02_dram_traffic.json"), "w"))
+    with open(os.path.join(P, "r02_final_step_traffic.txt"), "w") as f:
+        f.write(f"ncu dram__bytes_read.sum + dram__bytes_write.sum and durations of the launches of {steps:.1f} hoic_step calls (box, 4096 envs, 2 parts), per step:\n")
+        for k, v in sorted(per.items(), key=lambda x: -x[1]["gpu__time_duration.sum"]):
+            if k.startswith("k_"):
+                f.write(f"{k:10s} read {v['dram__bytes_read.sum']*scale/steps/1e6:9.2f} MB  write {v['dram__bytes_write.sum']*scale/steps/1e6:9.2f} MB  "
+                        f"time {v['gpu__time_duration.sum']/steps/1e6:8.3f} ms (serialised)\n")
+        f.write(f"total {out['box:4096']/1e6:.1f} MB per hoic_step = {out['box:4096']/4096/1e3:.1f} KB per env-step\n")
+    print(out)
+
+cub = "/tmp/cub_final"
+os.makedirs(cub, exist_ok=True)
+for kn, obj in (("k_p1", "k_p1"), ("k_p2", "k_p2"), ("k_p3s", "k_p3s"), ("k_tail", "k_tail"), ("banana_k_p2", "k_p2")):
+    rep = os.path.join(G, f"r02_final_{kn}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    raw = os.path.join(P, f"r02_final_{kn}_raw.csv")
+    subprocess.run(f"ncu -i {rep} --page raw --csv > {raw} 2>/dev/null", shell=True)
+    src = f"/tmp/r02_final_{kn}_src.csv"
+    subprocess.run(f"ncu -i {rep} --page source --csv > {src} 2>/dev/null", shell=True)
+    subprocess.run(f"cd {cub} && cuobjdump -xelf all {ROOT}/hoic_b200/build/{obj}.o > /dev/null 2>&1", shell=True)
+    kernel = "_Z5k_p3s" if obj == "k_p3s" else ("_Z6k_tail" if obj == "k_tail" else "_Z4" + obj)
+    subprocess.run(f"python {ROOT}/tools/ncu_by_function.py {src} {cub}/{obj}.sm_100a.cubin {kernel} > {P}/r02_final_{kn}_by_function.txt 2>/dev/null", shell=True)
+    print(kn, "done")
