@@ -16,6 +16,11 @@ from . import dist as hdist
 
 
 class MLP(nn.Module):
+    """uhc/khrylib/models/mlp.py:5-27.  The first layer's input width (617 observation entries) is not a multiple of 8, which
+    sends its GEMM to a legacy tensor-op kernel five times slower than the native one (profiles/README.md, r02): input and
+    weight are zero-padded to a multiple of 64 columns on the fly (exact: the padded products are zeros; parameters keep their
+    checkpoint shapes)."""
+
     def __init__(self, input_dim, hidden_dims=(2048, 1024, 512), activation="gelu"):
         super().__init__()
         self.activation = {"tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid, "gelu": nn.GELU()}[activation]
@@ -25,10 +30,15 @@ class MLP(nn.Module):
         for nh in hidden_dims:
             self.affine_layers.append(nn.Linear(last, nh))
             last = nh
+        self.in_pad = (-input_dim) % 64 if input_dim % 8 else 0
 
     def forward(self, x):
-        for affine in self.affine_layers:
-            x = self.activation(affine(x))
+        for i, affine in enumerate(self.affine_layers):
+            if i == 0 and self.in_pad and x.is_cuda:
+                x = nn.functional.linear(nn.functional.pad(x, (0, self.in_pad)), nn.functional.pad(affine.weight, (0, self.in_pad)), affine.bias)
+            else:
+                x = affine(x)
+            x = self.activation(x)
         return x
 
 

@@ -33,35 +33,45 @@ if os.path.exists(os.path.join(G, "r02_final_bench_launches.csv")):
                    "ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 2 --warmup 1 --preroll 2 --no-extras --no-cpu "
                    "(box, 4096 envs; kernels of the replayed CUDA graphs are profiled one by one: cold, serialised)")
 
-tp = os.path.join(G, "r02_final_step_traffic.csv")
-if os.path.exists(tp):
+def traffic(tp, tag, note):
     h, rows = rows_of(tp)
-    ik, iv, im = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Name")
+    ik, iv, im, iu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Name"), h.index("Metric Unit")
     per = collections.defaultdict(lambda: collections.defaultdict(float))
-    n_tail = 0
+    units, n_tail = {}, 0
     for r in rows:
         if len(r) <= iv:
             continue
         k = r[ik].split("(")[0]
         per[k][r[im]] += float(r[iv].replace(",", ""))
+        units[r[im]] = r[iu]
         if k == "k_tail" and r[im] == "gpu__time_duration.sum":
             n_tail += 1
-    steps = n_tail / 2.0                       # two batch parts per hoic_step
-    tot = sum(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for k, v in per.items() if k.startswith("k_"))
-    unit = h[h.index("Metric Unit")] if "Metric Unit" in h else "byte"
-    iu = h.index("Metric Unit")
-    units = {r[im]: r[iu] for r in rows if len(r) > iu}
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units.get("dram__bytes_read.sum", "byte"), 1.0)
-    out = {"box:4096": tot * scale / max(steps, 1)}
-    json.dump(out, open(os.path.join(P, "r02_dram_traffic.json"), "w"))
-    with open(os.path.join(P, "r02_final_step_traffic.txt"), "w") as f:
-        f.write(f"ncu dram__bytes_read.sum + dram__bytes_write.sum and durations of the launches of {steps:.1f} hoic_step calls (box, 4096 envs, 2 parts), per step:\n")
+    steps = max(n_tail / 2.0, 1.0)             # two batch parts per hoic_step
+    sc = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rs, ws = sc[units["dram__bytes_read.sum"]], sc[units["dram__bytes_write.sum"]]
+    tot = sum(v["dram__bytes_read.sum"] * rs + v["dram__bytes_write.sum"] * ws for k, v in per.items() if k.startswith("k_")) / steps
+    with open(os.path.join(P, f"r02_final_step_traffic_{tag}.txt"), "w") as f:
+        f.write(f"ncu dram__bytes_read.sum + dram__bytes_write.sum and durations of the launches of {steps:.1f} hoic_step calls (box, 4096 envs, "
+                f"2 parts), per step; {note}:\n")
         for k, v in sorted(per.items(), key=lambda x: -x[1]["gpu__time_duration.sum"]):
             if k.startswith("k_"):
-                f.write(f"{k:10s} read {v['dram__bytes_read.sum']*scale/steps/1e6:9.2f} MB  write {v['dram__bytes_write.sum']*scale/steps/1e6:9.2f} MB  "
+                f.write(f"{k:10s} read {v['dram__bytes_read.sum']*rs/steps/1e6:9.2f} MB  write {v['dram__bytes_write.sum']*ws/steps/1e6:9.2f} MB  "
                         f"time {v['gpu__time_duration.sum']/steps/1e6:8.3f} ms (serialised)\n")
-        f.write(f"total {out['box:4096']/1e6:.1f} MB per hoic_step = {out['box:4096']/4096/1e3:.1f} KB per env-step\n")
-    print(out)
+        f.write(f"total {tot/1e6:.1f} MB per hoic_step = {tot/4096/1e3:.1f} KB per env-step\n")
+    return tot
+
+
+cold, warm = os.path.join(G, "r02_final_step_traffic.csv"), os.path.join(G, "r02_final_step_traffic_warm.csv")
+res = {}
+if os.path.exists(cold):
+    res["box:4096:cold_caches"] = traffic(cold, "cold", "ncu's default cache control: L2 flushed before every kernel, so every kernel re-reads its part "
+                                                        "of the working set from DRAM -- an upper bound, not what a run does")
+if os.path.exists(warm):
+    res["box:4096"] = traffic(warm, "warm", "--cache-control none: caches as the preceding kernels left them, i.e. what a run does; this is the figure "
+                                            "bench.py reports as roofline.traffic")
+if res:
+    json.dump(res, open(os.path.join(P, "r02_dram_traffic.json"), "w"))
+    print(res)
 
 cub = "/tmp/cub_final"
 os.makedirs(cub, exist_ok=True)
