@@ -208,11 +208,13 @@ def kernel_timing(env, actions, steps):
     import torch
     L = env.L
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    l0 = L.hoic_launch_count()
     for a, b in ev:
         a.record()
         env.step(actions)
         b.record()
     torch.cuda.synchronize()
+    launches = (L.hoic_launch_count() - l0) // steps
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     L.hoic_set_timing(env._hb, 1)
     for _ in range(steps):
@@ -224,6 +226,7 @@ def kernel_timing(env, actions, steps):
     kt = {k: ms[i] / max(n.value, 1) for i, k in enumerate(TIMING_CLASSES)}
     kt["hoic_step_with_event_pairs"] = kt["hoic_step"]
     kt["hoic_step"] = step_ms
+    kt["launches_per_hoic_step"] = int(launches)
     return kt
 
 
@@ -339,9 +342,8 @@ def run_ours(args):
     tot = stats.allreduce()
 
     # ---- per-kernel durations and the launch count of one step (eager launches with the library's event timing)
-    l0 = L.hoic_launch_count()
     kt = kernel_timing(env, sampler.act, 5)
-    launches_per_step = (L.hoic_launch_count() - l0) // 5
+    launches_per_step = kt["launches_per_hoic_step"] + 3       # + k_zf_moments, k_zf_apply, k_logger of the sampler step
 
     # ---- e2e: host-resident sampler (noise H2D, transition D2H, one graph launch + stream sync per step)
     h_noise = torch.randn(N, 32).pin_memory()
