@@ -343,18 +343,21 @@ def run_ours(args):
 
     # ---- per-kernel durations and the launch count of one step (eager launches with the library's event timing)
     kt = kernel_timing(env, sampler.act, 5)
-    launches_per_step = kt["launches_per_hoic_step"] + 3       # + k_zf_moments, k_zf_apply, k_logger of the sampler step
+    launches_per_step = kt["launches_per_hoic_step"] + 5       # + k_zf_moments, k_zf_apply16, k_sample_action, k_get_episode, k_logger
 
     # ---- e2e: host-resident sampler (noise H2D, transition D2H, one graph launch + stream sync per step)
-    h_noise = torch.randn(N, 32).pin_memory()
+    h_noise = [torch.randn(N, 32).pin_memory(), torch.randn(N, 32).pin_memory()]
     for _ in range(3):
-        host_sampler.step_host(h_noise)
+        host_sampler.step_host(h_noise[0])
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        h_noise.normal_()                      # the host's RNG draw is part of the step, as in the reference's sampler
-        host_sampler.step_host(h_noise)
+    for k in range(args.steps):
+        # the host's RNG draw is part of the step, as in the reference's sampler; the draw for step k + 1 runs on the host
+        # while the device works on step k (two pinned buffers), then the host waits for step k's transition
+        host_sampler.step_host_begin(h_noise[k & 1])
+        h_noise[(k + 1) & 1].normal_()
+        host_sampler.step_host_end()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -410,8 +413,10 @@ def run_ours(args):
                    "envs_per_gpu": N, "sim_step": 15, "preroll_steps": args.preroll,
                    "l2": "flushed between steps (256 MiB write, untimed)", "parallelism": f"env-sharded x{world}"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_sampler_bytes[0]), "d2h_bytes_per_step": int(host_sampler_bytes[1]),
-                "api": "SamplerStep.step_host: exploration noise from pinned HOST memory in, normalised state / action / reward / mask / "
-                       "info of the transition into pinned HOST memory out; normaliser + policy + hoic_step + auto-reset in between"},
+                "api": "SamplerStep.step_host_begin / step_host_end: exploration noise drawn by the host RNG (the draw for the next step "
+                       "overlaps the device's work on this one) from pinned HOST memory in, normalised state / action / reward / mask / info "
+                       "of the transition into pinned HOST memory out (state / action copies run underneath hoic_step), one stream "
+                       "synchronise per step; normaliser + policy + hoic_step + auto-reset in between"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clk,

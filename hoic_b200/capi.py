@@ -17,7 +17,7 @@ EXPORTS = [
     "hoic_batch_destroy", "hoic_batch_size", "hoic_set_motions", "hoic_set_reward_weights", "hoic_set_mode",
     "hoic_reset", "hoic_step", "hoic_get_state", "hoic_set_state", "hoic_set_cur_t", "hoic_get_warmstart",
     "hoic_set_warmstart", "hoic_get_contacts", "hoic_substep_debug", "hoic_get_derived", "hoic_get_rfc",
-    "hoic_get_counters", "hoic_launch_count", "hoic_measure_fp32_peak", "hoic_get_work", "hoic_set_env_order", "hoic_set_balance", "hoic_set_sampler", "hoic_reset_sampled", "hoic_get_episode", "hoic_set_timing", "hoic_get_timing", "hoic_zfilter", "hoic_logger_step", "hoic_set_episode", "hoic_push_frame", "hoic_glue_last_error", "hoic_set_record", "hoic_preprocess_seq", "hoic_solve_wrench_qp",
+    "hoic_get_counters", "hoic_launch_count", "hoic_measure_fp32_peak", "hoic_get_work", "hoic_set_env_order", "hoic_set_balance", "hoic_set_sampler", "hoic_reset_sampled", "hoic_get_episode", "hoic_set_timing", "hoic_get_timing", "hoic_zfilter", "hoic_zfilter16", "hoic_sample_action", "hoic_logger_step", "hoic_set_episode", "hoic_push_frame", "hoic_glue_last_error", "hoic_set_record", "hoic_preprocess_seq", "hoic_solve_wrench_qp",
 ]
 
 
@@ -68,6 +68,8 @@ def lib():
         L.hoic_push_frame.argtypes = [vp, vp, C.c_int, vp]
         L.hoic_zfilter.argtypes = [vp, ip, ip] + [vp] * 8 + [C.c_float, ip, vp, vp]
         L.hoic_logger_step.argtypes = [vp, vp, vp, ip, vp, vp, vp, vp]
+        L.hoic_zfilter16.argtypes = [vp, ip, ip] + [vp] * 8 + [C.c_float, ip, vp, vp, ip, vp]
+        L.hoic_sample_action.argtypes = [vp, ip, vp, vp, vp, vp, ip, ip, vp, vp, vp]
         L.hoic_glue_last_error.restype = C.c_char_p
         L.hoic_get_timing.argtypes = [vp, vp, vp]
         L.hoic_get_state.argtypes = [vp, vp, vp, vp]

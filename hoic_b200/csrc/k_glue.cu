@@ -2,6 +2,7 @@
 // the observation normaliser (ZFilter / RunningStat, uhc/khrylib/utils/zfilter.py:7-73) and the sample logger
 // (LoggerRL.step / end_episode, uhc/khrylib/rl/core/logger_rl.py:28-44).  HBM-bound streaming kernels: one pass over the
 // [N, dim] observations for the batch moments, one pass to normalise.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -89,6 +90,36 @@ __global__ void k_zf_apply(const float* __restrict__ x, size_t total, int dim, c
     y[i] = fminf(fmaxf(v, -clip), clip);
   }
 }
+// the same pass with a second output for the policy MLP's first GEMM: y16[n][ld16] = bfloat16(y) (round to nearest even, what
+// torch.autocast's cast does), columns dim..ld16-1 zero (the MLP pads its 617 inputs to a multiple of 64, ppo.MLP)
+__global__ void k_zf_apply16(const float* __restrict__ x, int n, int dim, int ld16, const double* __restrict__ mean,
+                             const float* __restrict__ shift_scale, float clip, float* __restrict__ y, __nv_bfloat16* __restrict__ y16) {
+  const size_t total = (size_t)n * ld16;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ld16);
+    const size_t r = i / ld16;
+    float v = 0.f;
+    if (c < dim) {
+      v = (float)(((double)x[r * dim + c] - mean[c]) * (double)shift_scale[dim + c]);
+      v = fminf(fmaxf(v, -clip), clip);
+      y[r * dim + c] = v;
+    }
+    y16[i] = __float2bfloat16_rn(v);
+  }
+}
+// PolicyGaussian.select_action for the batch with the sampler's mean_action switch (agent_handmimic.py:463-466, 484):
+// explore[i] = u[i] < noise_rate (1 - mean_action), action = mean + exp(log_std) * noise * explore
+__global__ void k_sample_action(const __nv_bfloat16* __restrict__ mean16, const float* __restrict__ mean32, const float* __restrict__ log_std,
+                                const float* __restrict__ noise, const float* __restrict__ u, const float* __restrict__ noise_rate, int n,
+                                int act_dim, float* __restrict__ action, float* __restrict__ explore) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * act_dim) return;
+  const int r = i / act_dim, c = i - r * act_dim;
+  const float e = u[r] < *noise_rate ? 1.f : 0.f;
+  const float mu = mean16 ? __bfloat162float(mean16[i]) : mean32[i];
+  action[i] = mu + expf(log_std[c]) * noise[i] * e;
+  if (c == 0) explore[r] = e;
+}
 
 // LoggerRL for a batch: sums[0..12] = steps, episodes, c_reward, info[9], finished-episode reward; minmax = c_reward min / max,
 // episode reward min / max; episode_reward[N] running sums (reset where an episode ended).  One CTA.
@@ -139,19 +170,38 @@ __global__ void __launch_bounds__(1024) k_logger(const float* __restrict__ rewar
 
 extern "C" const char* hoic_glue_last_error(void) { return g_glue_err.c_str(); }
 
-extern "C" int hoic_zfilter(const float* obs, int n, int dim, double* st_n, double* mean, double* m2, double* dn, double* dmean, double* dm2,
-                            double* scratch, float* shift_scale, float clip, int update, float* x_out, void* stream) {
-  if (!obs || n < 1 || dim < 1 || !st_n || !mean || !m2 || !scratch || !shift_scale || !x_out) { g_glue_err = "hoic_zfilter: bad arguments"; return -1; }
+extern "C" int hoic_zfilter16(const float* obs, int n, int dim, double* st_n, double* mean, double* m2, double* dn, double* dmean, double* dm2,
+                              double* scratch, float* shift_scale, float clip, int update, float* x_out, void* x16_out, int ld16, void* stream) {
+  if (!obs || n < 1 || dim < 1 || !st_n || !mean || !m2 || !scratch || !shift_scale || !x_out || (x16_out && ld16 < dim)) {
+    g_glue_err = "hoic_zfilter: bad arguments";
+    return -1;
+  }
   cudaStream_t sm = (cudaStream_t)stream;
   const int chunks = update ? ZF_CHUNKS : 1;
   k_zf_moments<<<dim3((dim + ZF_COLS - 1) / ZF_COLS, chunks), ZF_COLS * ZF_ROWS, 0, sm>>>(obs, n, dim, chunks, st_n, mean, m2, dn, dmean, dm2, scratch,
                                                                                        shift_scale, update);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return glue_err("k_zf_moments", e);
-  const size_t total = (size_t)n * dim;
-  k_zf_apply<<<(int)((total + 1023) / 1024 < 1184 ? (total + 1023) / 1024 : 1184), 256, 0, sm>>>(obs, total, dim, mean, shift_scale, clip, x_out);
+  const size_t total = (size_t)n * (x16_out ? ld16 : dim);
+  const int grid = (int)((total + 1023) / 1024 < 1184 ? (total + 1023) / 1024 : 1184);
+  if (x16_out) k_zf_apply16<<<grid, 256, 0, sm>>>(obs, n, dim, ld16, mean, shift_scale, clip, x_out, (__nv_bfloat16*)x16_out);
+  else k_zf_apply<<<grid, 256, 0, sm>>>(obs, total, dim, mean, shift_scale, clip, x_out);
   e = cudaGetLastError();
   if (e != cudaSuccess) return glue_err("k_zf_apply", e);
+  return 0;
+}
+extern "C" int hoic_zfilter(const float* obs, int n, int dim, double* st_n, double* mean, double* m2, double* dn, double* dmean, double* dm2,
+                            double* scratch, float* shift_scale, float clip, int update, float* x_out, void* stream) {
+  return hoic_zfilter16(obs, n, dim, st_n, mean, m2, dn, dmean, dm2, scratch, shift_scale, clip, update, x_out, nullptr, 0, stream);
+}
+extern "C" int hoic_sample_action(const void* mean, int mean_is_bf16, const float* log_std, const float* noise, const float* u,
+                                  const float* noise_rate, int n, int act_dim, float* action, float* explore, void* stream) {
+  if (!mean || !log_std || !noise || !u || !noise_rate || n < 1 || act_dim < 1 || !action || !explore) { g_glue_err = "hoic_sample_action: bad arguments"; return -1; }
+  k_sample_action<<<(n * act_dim + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mean_is_bf16 ? (const __nv_bfloat16*)mean : nullptr,
+                                                                            mean_is_bf16 ? nullptr : (const float*)mean, log_std, noise, u,
+                                                                            noise_rate, n, act_dim, action, explore);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return glue_err("k_sample_action", e);
   return 0;
 }
 

@@ -126,15 +126,17 @@ class ZFilter:
         self._assign(("n", "mean", "m2"), self._merge(self.n, self.mean, self.m2, nb, bmean, bm2))
         self._assign(("_dn", "_dmean", "_dm2"), self._merge(self._dn, self._dmean, self._dm2, nb, bmean, bm2))
 
-    def __call__(self, x, update=True):
+    def __call__(self, x, update=True, out=None, out16=None):
+        """`out` (float32 [N, dim]) / `out16` (bfloat16 [N, ld >= dim], padding columns zeroed): device buffers the library
+        path writes the normalised batch into (the sampler step keeps both at fixed addresses for its CUDA graph)."""
         if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous():
-            return self._call_library(x, update)
+            return self._call_library(x, update, out, out16)
         if update:
             self.update(x)
         y = (x.to(torch.float64) - self.mean) / (self.std + 1e-8)
         return torch.clamp(y, -self.clip, self.clip).to(x.dtype)
 
-    def _call_library(self, x, update):
+    def _call_library(self, x, update, out=None, out16=None):
         """Device batches go through libhoic_b200.so (hoic_zfilter: one pass for the batch moments, one to normalise) instead
         of a dozen torch kernels; same arithmetic (double accumulation, Chan merge)."""
         from . import capi
@@ -146,13 +148,17 @@ class ZFilter:
                              torch.zeros(2 * dim, dtype=torch.float32, device=x.device), {})
         scratch, shift_scale, outs = self._lib_buf
         key = (x.shape[0], torch.cuda.is_current_stream_capturing())
-        y = outs.get(key)
+        y = out if out is not None else outs.get(key)
         if y is None:
             y = outs[key] = torch.empty_like(x)
-        capi.check(L.hoic_zfilter(capi.ptr(x), x.shape[0], x.shape[1], capi.ptr(self.n), capi.ptr(self.mean), capi.ptr(self.m2),
-                                  capi.ptr(self._dn), capi.ptr(self._dmean), capi.ptr(self._dm2), capi.ptr(scratch),
-                                  capi.ptr(shift_scale), float(self.clip), 1 if update else 0, capi.ptr(y),
-                                  C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "hoic_zfilter")
+        if out16 is not None and not (out16.dtype == torch.bfloat16 and out16.is_contiguous() and out16.shape[0] == x.shape[0]
+                                      and out16.shape[1] >= x.shape[1]):
+            raise ValueError("ZFilter: out16 must be a contiguous bfloat16 [N, ld >= dim] tensor")
+        capi.check(L.hoic_zfilter16(capi.ptr(x), x.shape[0], x.shape[1], capi.ptr(self.n), capi.ptr(self.mean), capi.ptr(self.m2),
+                                    capi.ptr(self._dn), capi.ptr(self._dmean), capi.ptr(self._dm2), capi.ptr(scratch),
+                                    capi.ptr(shift_scale), float(self.clip), 1 if update else 0, capi.ptr(y),
+                                    capi.ptr(out16) if out16 is not None else None, out16.shape[1] if out16 is not None else 0,
+                                    C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "hoic_zfilter")
         return y
 
     def set_state(self, n, mean, m2):

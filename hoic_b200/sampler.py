@@ -60,12 +60,67 @@ class SamplerStep:
         self._graph = None
         self._use_graph = graph
         self._host = None
+        # bf16 fast path: the normaliser writes a bfloat16 copy of the state (padded to the first layer's GEMM width) next to
+        # the float32 one, the MLP runs on bfloat16 copies of the weights that are refreshed only when the parameters change
+        # (torch.autocast re-casts every weight on every call: 9 cast / pad kernels per step), and the draw of the action is
+        # one library kernel.  Same arithmetic as the autocast path (bf16 operands, fp32 accumulation, bf16 activations).
+        self._fast = policy_dtype == "bf16" and hasattr(policy, "net") and hasattr(policy.net, "affine_layers") and env.device.type == "cuda"
+        if self._fast:
+            in_dim = policy.net.affine_layers[0].in_features
+            self._ld16 = in_dim + ((-in_dim) % 64 if in_dim % 8 else 0)
+            self.x16 = torch.zeros(N, self._ld16, dtype=torch.bfloat16, device=dev)
+            self._u = torch.zeros(N, **f32)
+            self._rnd = torch.zeros(N, env.act_dim, **f32)
+            self._w16, self._w16_version = None, None
+            self._refresh_weights()
+
+    # ------------------------------------------------------------------ bf16 copies of the policy's parameters
+    def _params(self):
+        ps = []
+        for a in self.policy.net.affine_layers:
+            ps += [a.weight, a.bias]
+        return ps + [self.policy.action_mean.weight, self.policy.action_mean.bias]
+
+    def _refresh_weights(self):
+        """In-place refresh of the bfloat16 weight copies when a parameter changed (optimizer step, checkpoint load): the
+        buffers keep their addresses, so a captured graph keeps reading the right memory."""
+        ps = self._params()
+        version = tuple((p.data_ptr(), p._version) for p in ps)
+        if version == self._w16_version:
+            return
+        with torch.no_grad():
+            if self._w16 is None:
+                self._w16 = [torch.zeros(p.shape[0], self._ld16, dtype=torch.bfloat16, device=p.device) if i == 0
+                             else torch.empty_like(p, dtype=torch.bfloat16) for i, p in enumerate(ps)]
+            for i, (w, p) in enumerate(zip(self._w16, ps)):
+                if i == 0:
+                    w[:, :p.shape[1]].copy_(p)
+                else:
+                    w.copy_(p)
+        self._w16_version = version
 
     def set_noise_rate(self, r):
         self.noise_rate.fill_(float(r))
 
     # ------------------------------------------------------------------ the step body (eager or under capture)
-    def _body(self):
+    def _act_fast(self):
+        env = self.env
+        self.zf(env.obs, update=self.update_filter, out=self.x, out16=self.x16)
+        h = self.x16
+        w = self._w16
+        for i in range(len(self.policy.net.affine_layers)):
+            h = self.policy.net.activation(torch.nn.functional.linear(h, w[2 * i], w[2 * i + 1]))
+        mean = torch.nn.functional.linear(h, w[-2], w[-1])
+        if self.noise is None:
+            noise = self._rnd.normal_(generator=self.gen)
+        else:
+            noise = self.noise
+        self._u.uniform_(generator=self.gen)
+        capi.check(env.L.hoic_sample_action(capi.ptr(mean), 1, capi.ptr(self.policy.action_log_std), capi.ptr(noise), capi.ptr(self._u),
+                                            capi.ptr(self.noise_rate), mean.shape[0], mean.shape[1], capi.ptr(self.act), capi.ptr(self.exp),
+                                            env._stream()), "hoic_sample_action")
+
+    def _act_torch(self):
         env = self.env
         x = self.zf(env.obs, update=self.update_filter)
         with matmul_context(self.policy_dtype):
@@ -80,6 +135,16 @@ class SamplerStep:
         self.exp.copy_((u < self.noise_rate).to(torch.float32))
         self.x.copy_(x)
         self.act.copy_(mean + torch.exp(log_std) * noise * self.exp[:, None])
+
+    def _body(self, after_action=None):
+        env = self.env
+        with torch.no_grad():
+            if self._fast:
+                self._act_fast()
+            else:
+                self._act_torch()
+        if after_action is not None:
+            after_action()      # step_host: the state / action of the transition start their way to the host here
         capi.check(env.L.hoic_get_episode(env._hb, capi.ptr(self.motion_id), capi.ptr(self.start_idx), None, env._stream()),
                    "hoic_get_episode")
         obs, r, done, info = env.step(self.act)
@@ -107,6 +172,8 @@ class SamplerStep:
         self._graph = g
 
     def step(self):
+        if self._fast:
+            self._refresh_weights()
         if self._use_graph:
             if self._graph is None:
                 self.warmup()
@@ -120,25 +187,50 @@ class SamplerStep:
         (agent_handmimic.py:463-485, khrylib/rl/core/memory.py): `noise_host` [N, 32] pinned float32 standard-normal draws
         go H2D, the transition (normalised state, action, exp, reward, mask, info, percent) comes back D2H into pinned
         buffers.  One graph launch + one stream synchronise per step.  Returns the dict of pinned host tensors."""
+        self.step_host_begin(noise_host)
+        return self.step_host_end()
+
+    def step_host_begin(self, noise_host):
+        """Launch the host-resident step and return at once: the caller may draw the next step's noise (into ANOTHER pinned
+        buffer) while the device works; `step_host_end()` waits for the transition."""
         if self.noise is None:
             raise capi.HoicError("construct SamplerStep(host_noise=True) for step_host")
+        if self._fast:
+            self._refresh_weights()
         if self._host is None:
             self._build_host()
         h = self._host
         if noise_host.data_ptr() != h["noise"].data_ptr():
             h["noise"].copy_(noise_host)
         h["graph"].replay()
+
+    def step_host_end(self):
         torch.cuda.current_stream(self.env.device).synchronize()
-        return h["out"]
+        return self._host["out"]
 
     def _host_body(self):
         h = self._host
-        self.noise.copy_(h["noise"], non_blocking=True)
-        self._body()
         env = self.env
-        for k, src in (("state", self.x), ("action", self.act), ("exp", self.exp), ("reward", env.reward), ("done", env.done),
-                       ("end", env.end), ("fail", env.fail), ("percent", env.percent), ("reward_info", env.reward_info)):
+        dev = env.device
+        self.noise.copy_(h["noise"], non_blocking=True)
+        main = torch.cuda.current_stream(dev)
+
+        def early():
+            # the normalised state (95 % of the transition's bytes) and the action are final before the physics starts:
+            # their D2H copies run on a side stream underneath hoic_step
+            h["ev0"].record(main)
+            h["side"].wait_event(h["ev0"])
+            with torch.cuda.stream(h["side"]):
+                h["out"]["state"].copy_(self.x, non_blocking=True)
+                h["out"]["action"].copy_(self.act, non_blocking=True)
+                h["out"]["exp"].copy_(self.exp, non_blocking=True)
+                h["ev1"].record(h["side"])
+
+        self._body(after_action=early)
+        for k, src in (("reward", env.reward), ("done", env.done), ("end", env.end), ("fail", env.fail), ("percent", env.percent),
+                       ("reward_info", env.reward_info)):
             h["out"][k].copy_(src, non_blocking=True)
+        main.wait_event(h["ev1"])
 
     def _build_host(self):
         env, N = self.env, self.env.n_envs
@@ -146,7 +238,8 @@ class SamplerStep:
         out = dict(state=pin(N, env.obs_dim), action=pin(N, env.act_dim), exp=pin(N), reward=pin(N), percent=pin(N),
                    reward_info=pin(N, capi.INFO_DIM), done=pin(N, dtype=torch.uint8), end=pin(N, dtype=torch.uint8),
                    fail=pin(N, dtype=torch.uint8))
-        self._host = dict(noise=pin(N, env.act_dim), out=out, graph=None)
+        self._host = dict(noise=pin(N, env.act_dim), out=out, graph=None, side=torch.cuda.Stream(env.device),
+                          ev0=torch.cuda.Event(), ev1=torch.cuda.Event())
         self._host["noise"].zero_()
         self.h2d_bytes = N * env.act_dim * 4
         self.d2h_bytes = sum(v.numel() * v.element_size() for v in out.values())

@@ -195,6 +195,16 @@ int hoic_set_balance(hoic_batch* b, int on);
  * reproducible (fixed summation order). */
 int hoic_zfilter(const float* obs, int n, int dim, double* st_n, double* mean, double* m2, double* dn, double* dmean, double* dm2,
                  double* scratch, float* shift_scale, float clip, int update, float* x_out, void* stream);
+/* hoic_zfilter with a second output for the policy MLP's first GEMM on the tensor cores: x16_out[n][ld16] = bfloat16(x_out)
+ * (round to nearest even), columns dim..ld16-1 zero (ld16 >= dim).  x16_out NULL = hoic_zfilter. */
+int hoic_zfilter16(const float* obs, int n, int dim, double* st_n, double* mean, double* m2, double* dn, double* dmean, double* dm2,
+                   double* scratch, float* shift_scale, float clip, int update, float* x_out, void* x16_out, int ld16, void* stream);
+/* replaces PolicyGaussian.select_action + the sampler's mean_action switch (uhc/khrylib/rl/core/policy_gaussian.py:35-37,
+ * agent_handmimic.py:463-466, 484) for the batch: explore[i] = u[i] < *noise_rate ? 1 : 0 (u uniform in [0,1): mean_action =
+ * binomial(1, 1 - noise_rate)), action[i][:] = mean[i][:] + exp(log_std[:]) * noise[i][:] * explore[i].  mean: [n][act_dim]
+ * bfloat16 (mean_is_bf16 != 0, the MLP's tensor-core output) or float32; noise: standard-normal draws of the caller's RNG. */
+int hoic_sample_action(const void* mean, int mean_is_bf16, const float* log_std, const float* noise, const float* u,
+                       const float* noise_rate, int n, int act_dim, float* action, float* explore, void* stream);
 /* replaces LoggerRL.step / end_episode (uhc/khrylib/rl/core/logger_rl.py:28-44) for one batched step: sums[13] += steps,
  * finished episodes, c_reward, reward_info[9], reward of the episodes that finished; minmax[4] = c_reward min / max, episode
  * reward min / max; episode_reward[n] (may be NULL) = per-env running sums, cleared where done. */

@@ -597,6 +597,7 @@ void orc_env_step(orc_env* e, const double* action_in, double* obs, double* scal
   }
   for (int i = 0; i < m->sim_step && !fail; i++) {
     fail = orc_env_substep(e, a);
+    e->sub_iters[i & 31] = d->solver_iter; e->sub_ncon[i & 31] = d->ncon;
     if (!fail && e->record) record_frame(e, i);   /* a MujocoException leaves do_simulation before compute_data_frame */
   }
   if (!fail) {
@@ -671,6 +672,9 @@ int orc_get_contacts(orc_env* e, double* out) {
     o[13] = k->geom1; o[14] = k->geom2; o[15] = k->dim;
   }
   return e->d.ncon;
+}
+int orc_get_substep_log(const orc_env* e, int* iters, int* ncon) {
+  memcpy(iters, e->sub_iters, sizeof e->sub_iters); memcpy(ncon, e->sub_ncon, sizeof e->sub_ncon); return e->m->sim_step;
 }
 /* ints: [ncon, nefc, solver_iter, warn_bad, warn_contactfull, warn_cnstrfull, mpr_calls, mpr_iters, qp_n, qp_iters, n_avg_cp] */
 void orc_get_counters(orc_env* e, int* out) {

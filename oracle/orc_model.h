@@ -109,6 +109,7 @@ typedef struct {
   double end_reward;
   /* per-step scratch kept for inspection */
   double obj_vf[3], obj_vt[3], rfc_score;
+  int sub_iters[32], sub_ncon[32];   /* per-substep solver iterations / contacts of the last step (analysis accessor) */
   double obj_avg_acc[6], geom_avg_vel[ORC_NG][3], geom_avg_ang_vel[ORC_NG][3];
   double contact_sum[ORC_NHG][12];
   int contact_count[ORC_NHG];

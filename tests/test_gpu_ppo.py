@@ -170,3 +170,58 @@ def test_library_normaliser_and_logger_match_the_reference_arithmetic():
     for k in ("avg_c_reward", "avg_episode_len", "avg_episode_reward", "min_episode_reward", "max_episode_reward", "reward_min", "reward_max"):
         assert abs(a[k] - b[k]) < 1e-9, k
     assert np.allclose(a["info_sum"], b["info_sum"]) and torch.allclose(gs.episode_reward.cpu(), cs.episode_reward)
+
+
+def test_sampler_fast_path_equals_the_autocast_path_and_host_step_returns_the_transition():
+    """The sampler step's bf16 fast path (hoic_zfilter16 -> MLP on cached bfloat16 weights -> hoic_sample_action) against
+    the torch.autocast path it replaces, from the same observations / noise / parameters; the weight copies follow an
+    in-place parameter update; step_host (early D2H copies on a side stream) returns the device transition."""
+    from hoic_b200 import ppo
+    from hoic_b200.sampler import SamplerStep
+    from hoic_b200.vecenv import HandMimicVecEnv
+    mdl = model("box")
+    dev = torch.device("cuda", 0)
+    pol, _ = ppo.make_policy_value(mdl.cfg, device=dev, dtype=torch.float32, seed=1)
+    acts, xs = [], []
+    for fast in (True, False):
+        env = HandMimicVecEnv(mdl, 96, [mdl.motion(s) for s in range(1, 9)], device=0, seed=3, auto_reset=True)
+        zf = ppo.ZFilter((617,), clip=5.0, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(11)
+        s = SamplerStep(env, pol, zf, gen, policy_dtype="bf16", graph=False, host_noise=True)
+        assert s._fast
+        s._fast = fast
+        env.reset()
+        s.noise.copy_(torch.randn(96, 32, generator=torch.Generator().manual_seed(5)).to(dev))
+        with torch.no_grad():
+            (s._act_fast if fast else s._act_torch)()
+        torch.cuda.synchronize()
+        acts.append(s.act.clone()); xs.append(s.x.clone())
+        if fast:
+            assert torch.equal(s.x16[:, :617].float(), s.x.to(torch.bfloat16).float()) and float(s.x16[:, 617:].abs().max()) == 0.0
+            # parameters change in place -> the bf16 copies follow at the next step
+            with torch.no_grad():
+                pol.action_mean.bias.add_(0.25)
+            s._refresh_weights()
+            assert torch.equal(s._w16[-1].float(), pol.action_mean.bias.to(torch.bfloat16).float())
+            with torch.no_grad():
+                pol.action_mean.bias.sub_(0.25)
+            s._refresh_weights()
+        env.close()
+    assert torch.equal(xs[0], xs[1])
+    sigma = float(torch.exp(pol.action_log_std).mean())
+    assert float((acts[0] - acts[1]).abs().max()) < 2e-3 * sigma, float((acts[0] - acts[1]).abs().max())
+    # host-resident step: pinned buffers hold exactly the device transition
+    env = HandMimicVecEnv(mdl, 96, [mdl.motion(s) for s in range(1, 9)], device=0, seed=3, auto_reset=True)
+    zf = ppo.ZFilter((617,), clip=5.0, device=dev)
+    s = SamplerStep(env, pol, zf, torch.Generator(device=dev).manual_seed(11), policy_dtype="bf16", graph=True, host_noise=True)
+    env.reset()
+    noise = [torch.randn(96, 32).pin_memory(), torch.randn(96, 32).pin_memory()]
+    for k in range(3):
+        s.step_host_begin(noise[k & 1])
+        noise[(k + 1) & 1].normal_()
+        out = s.step_host_end()
+        assert torch.equal(out["state"], s.x.cpu()) and torch.equal(out["action"], s.act.cpu()) and torch.equal(out["exp"], s.exp.cpu())
+        assert torch.equal(out["reward"], env.reward.cpu()) and torch.equal(out["done"], env.done.cpu())
+        assert torch.equal(out["reward_info"], env.reward_info.cpu())
+        assert torch.allclose(s.noise.cpu(), noise[k & 1])
+    env.close()
