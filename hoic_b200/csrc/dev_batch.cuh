@@ -37,7 +37,12 @@ struct BatchDev {
   int samp_random_start, samp_min_episode;
   unsigned long long samp_seed;
   int* order;                         // [N] library-owned env order (hoic_set_balance), what `perm` points to when it is on
+  // envs of the running substep whose constraint stage exceeds the solver's small tier, appended by k_p2 and consumed by
+  // k_p3 (full tier): the full-tier launch then covers only those envs instead of starting one 19 KB CTA per env of the batch
+  int* full_list;                     // [nparts][N]
+  int* full_count;                    // [nparts][FULL_COUNT_STRIDE], entry k = substep, zeroed at the start of a step
 };
+#define FULL_COUNT_STRIDE 32
 
 struct StepOut {
   float* obs; float* reward; float* info; uint8_t* done; uint8_t* fail; uint8_t* end; float* percent;

@@ -166,6 +166,8 @@ __device__ __forceinline__ void cross_force(float* res, const float* vel, const 
 #ifndef CHOL_TRAIL_UNROLL
 #define CHOL_TRAIL_UNROLL 2    // A/B knob (tools/build_variant.sh): unroll factor of the rank-4 trailing update
 #endif
+#define H_PRAGMA_(x) _Pragma(#x)
+#define H_UNROLL(n) H_PRAGMA_(unroll n)
 #define H_FLOATS 576
 __device__ __forceinline__ int hidx(int i, int j) { return HB_OFF(i >> 2, j >> 2) + 4 * (i & 3) + (j & 3); }
 __device__ __forceinline__ float rsqrt_nr(float x) {
@@ -215,7 +217,7 @@ static __device__ __noinline__ bool warp_chol_solve(float* A, float b, float* xo
     if (I >= p) *own = make_float4(x0, s1, s2, s3);
     __syncwarp();
     // rank-4 update of the row segments right of the panel: A[i][4 Jb + c] -= sum_k L[i][4p + k] L[4 Jb + c][4p + k]
-#pragma unroll CHOL_TRAIL_UNROLL
+H_UNROLL(CHOL_TRAIL_UNROLL)
     for (int Jb = p + 1; Jb < 8; Jb++) {
       const float4* Lr = reinterpret_cast<const float4*>(A + HB_OFF(Jb, p));
       float4* o = reinterpret_cast<float4*>(A + HB_OFF(I, min(Jb, I)) + 4 * r);

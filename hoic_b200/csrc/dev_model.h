@@ -21,6 +21,10 @@
 #define HG_NCON 32
 #define HG_NBASIS 80
 #define HG_NEDGE 128
+// capacity of the solver's SMALL tier (k_p3s / k_as): envs whose constraint stage fits are solved there, the rest by k_p3 / k_a
+#define P3S_NCON 8
+#define P3S_NBASIS 24
+#define P3S_NEDGE 32
 #define H_RFR 0        // row index ranges: friction-loss rows [0,32)
 #define H_RLIM 32      //                   joint-limit rows   [32,64)
 #define H_RCON 64      //                   contact edge rows  [64,64+H_NEDGE)
@@ -127,7 +131,9 @@ struct DevModel {
 #define UN_TS (32 * 21)                /* tree_solve's branch products (dev_math.cuh: TS_P) */
 #define UN_TSF 480                     /* tree_solve's factor scratch (TS_LS .. TS_T) when it lives in the union (k_p1) */
 #define S_MAX2(a, b) ((a) > (b) ? (a) : (b))
+#define HK_A (HK_P1 | HK_P3)   // fused kernel k_a (k_a.cu): Newton solve of substep k, then k_p1's work for substep k + 1
 #define UN_SIZE ((H_KERNEL) == HK_P1 ? S_MAX2(UN_POS, UN_TS + UN_TSF) : ((H_KERNEL) == HK_P2 || (H_KERNEL) == HK_P3) ? UN_CON : \
+                 (H_KERNEL) == HK_A ? S_MAX2(S_MAX2(UN_POS, UN_TS), UN_CON) : \
                  (H_KERNEL) == HK_TAIL ? S_MAX2(UN_QP, UN_TS) : S_MAX2(S_MAX2(UN_POS, UN_CON), S_MAX2(UN_QP, UN_TS)))
 #define UN_FULL S_MAX2(S_MAX2(UN_POS, UN_CON_G), S_MAX2(UN_QP, UN_TS))
 

@@ -259,6 +259,23 @@ static __device__ __noinline__ float mul_M(const float* s, const DevModel& m, in
   ld_row12(r, s + S_MS + lane * MS_STRIDE);
   const float vl = v[lane];
   float acc0 = on ? s[S_MS + lane * MS_STRIDE + dep] * vl : vl, acc1 = 0.f;
+#ifdef MULM_ROLLED
+  {
+    const float* Mr = s + S_MS + lane * MS_STRIDE;
+#pragma unroll 1
+    for (int d = 0; d < T_MAXD - 1; d++) {
+      const unsigned w = d < 4 ? a0 : (d < 8 ? a1 : a2);
+      const int j = (int)((w >> (8 * (d & 3))) & 0xffu);
+      if (j != 0xff) acc0 = fmaf(Mr[d], v[j], acc0);
+    }
+#pragma unroll 1
+    for (int l = 1; l < T_MAXD; l++) {
+      const unsigned w = l < 4 ? c0 : (l < 8 ? c1 : c2);
+      const int k = (int)((w >> (8 * (l & 3))) & 0xffu);
+      if (k != 0xff) acc1 = fmaf(s[S_MS + k * MS_STRIDE + dep], v[k], acc1);
+    }
+  }
+#else
 #pragma unroll
   for (int d = 0; d < T_MAXD - 1; d++) {
     const int j = tbyte(a0, a1, a2, d);
@@ -269,6 +286,7 @@ static __device__ __noinline__ float mul_M(const float* s, const DevModel& m, in
     const int k = tbyte(c0, c1, c2, l);
     if (k != 0xff) acc1 = fmaf(s[S_MS + k * MS_STRIDE + dep], v[k], acc1);
   }
+#endif
   {
     // unconditional (uniform control flow keeps the shuffles free of convergence barriers); no hub -> no branch lanes
     float corr = 0.f;

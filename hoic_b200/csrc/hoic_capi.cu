@@ -361,6 +361,7 @@ struct hoic_model {
 
 #define HOIC_MAX_PARTS 8
 #define HOIC_TIMING_CLASSES 8          // k_p1, k_p2, k_p3s, k_p3, k_tail, k_reset, k_order, whole call
+static int capi_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 struct hoic_batch {
   int device, n_envs;
   BatchDev b;
@@ -382,6 +383,8 @@ struct hoic_batch {
   int motions_cap = 0, nsub = 0;
   // hoic_step runs the batch as `nparts` interleaved parts on internal streams (fork / join around the caller's stream)
   int nparts = 1;
+  bool fuse = false;                     // solve + next substep's k_p1 in one launch (k_a.cu)
+  int part_delay_ns = 0;                 // experiment: part 1 starts this much later than part 0 (HOIC_PART_DELAY_US)
   cudaStream_t part_stream[HOIC_MAX_PARTS] = {}, aux_stream[HOIC_MAX_PARTS] = {};   // aux: the solver's full-capacity tier
   cudaEvent_t ev_fork = nullptr, ev_join[HOIC_MAX_PARTS] = {}, ev_rows[HOIC_MAX_PARTS] = {}, ev_aux[HOIC_MAX_PARTS] = {};
 };
@@ -814,6 +817,11 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   CUDA_OKP(cudaMalloc(&b->b.old_geom, (size_t)n_envs * (HN * 12 + 4) * sizeof(float)));
   CUDA_OKP(cudaMalloc(&b->b.csum, (size_t)n_envs * CSUM_STRIDE * sizeof(float)));
   CUDA_OKP(cudaMalloc(&b->b.csum_carry, (size_t)n_envs * CSUM_STRIDE * sizeof(float)));
+  if (capi_env_int("HOIC_FULL_LIST", 1)) {
+    CUDA_OKP(cudaMalloc(&b->b.full_list, (size_t)HOIC_MAX_PARTS * n_envs * sizeof(int)));
+    CUDA_OKP(cudaMalloc(&b->b.full_count, (size_t)HOIC_MAX_PARTS * FULL_COUNT_STRIDE * sizeof(int)));
+    CUDA_OKP(cudaMemset(b->b.full_count, 0, (size_t)HOIC_MAX_PARTS * FULL_COUNT_STRIDE * sizeof(int)));
+  }
   CUDA_OKP(cudaMalloc(&b->b.counters, 16 * sizeof(unsigned long long)));
   CUDA_OKP(cudaMemset(b->b.counters, 0, 16 * sizeof(unsigned long long)));
   CUDA_OKP(cudaMalloc(&b->reward_w, 24 * sizeof(float)));
@@ -832,10 +840,20 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     int want = n_envs >= 1024 ? 2 : 1;
     if (const char* e = getenv("HOIC_STEP_PARTS")) want = atoi(e);
     b->nparts = std::min(std::max(want, 1), HOIC_MAX_PARTS);
+    // fused solve + k_p1 launches (k_a.cu) are an opt-in experiment (HOIC_FUSE=1): measured SLOWER than the separate kernels
+    // (box, 4096 envs: 5.37 vs 4.32 ms per step; 16 384 envs: 18.0 vs 13.6 ms) -- warps of one SM then run the solver's and
+    // k_p1's code at the same time and the instruction cache hit rate falls from 93 % / 91 % to 73 % (profiles/README.md)
+    b->fuse = false;
+    b->part_delay_ns = 1000 * capi_env_int("HOIC_PART_DELAY_US", 0);
+    if (const char* e = getenv("HOIC_FUSE")) b->fuse = atoi(e) != 0;
     CUDA_OKP(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     for (int j = 0; j < b->nparts; j++) {
-      CUDA_OKP(cudaStreamCreateWithFlags(&b->part_stream[j], cudaStreamNonBlocking));
-      CUDA_OKP(cudaStreamCreateWithFlags(&b->aux_stream[j], cudaStreamNonBlocking));
+      // experiment knobs (tools/ab_r2b.sh): HOIC_PRIO_PART1 / HOIC_PRIO_AUX = CUDA stream priority (lower = more urgent)
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      const int pp = j == 1 ? capi_env_int("HOIC_PRIO_PART1", 0) : 0, pa = capi_env_int("HOIC_PRIO_AUX", 0);
+      CUDA_OKP(cudaStreamCreateWithPriority(&b->part_stream[j], cudaStreamNonBlocking, std::max(hi, std::min(lo, pp))));
+      CUDA_OKP(cudaStreamCreateWithPriority(&b->aux_stream[j], cudaStreamNonBlocking, std::max(hi, std::min(lo, pa))));
       CUDA_OKP(cudaEventCreateWithFlags(&b->ev_join[j], cudaEventDisableTiming));
       CUDA_OKP(cudaEventCreateWithFlags(&b->ev_rows[j], cudaEventDisableTiming));
       CUDA_OKP(cudaEventCreateWithFlags(&b->ev_aux[j], cudaEventDisableTiming));
@@ -845,6 +863,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     static bool configured[64] = {false};
     if (!configured[device & 63]) {
       CUDA_OKP(hoic_configure_p1()); CUDA_OKP(hoic_configure_p2()); CUDA_OKP(hoic_configure_p3()); CUDA_OKP(hoic_configure_p3s()); CUDA_OKP(hoic_configure_tail());
+      CUDA_OKP(hoic_configure_a()); CUDA_OKP(hoic_configure_as());
       configured[device & 63] = true;
     }
   }
@@ -868,6 +887,7 @@ extern "C" void hoic_batch_destroy(hoic_batch* b) {
     if (b->aux_stream[j]) cudaStreamDestroy(b->aux_stream[j]);
   }
   cudaFree(b->env_model_dev); cudaFree(b->b.scratch); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum); cudaFree(b->b.csum_carry);
+  cudaFree(b->b.full_list); cudaFree(b->b.full_count);
   cudaFree(b->env_model_idx); cudaFree(b->samp_off); cudaFree(b->samp_ids); cudaFree(b->order);
   cudaFree(b->reward_w); cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
   delete b;
@@ -1029,6 +1049,11 @@ extern "C" int hoic_get_timing(hoic_batch* b, double* ms_host, int* steps_host) 
   return 0;
 }
 
+__global__ void k_delay(int ns) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < (long long)ns * 2) __nanosleep(200);     // ~2 cycles per ns at 1.9 GHz
+}
+
 extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float* reward, float* reward_info, uint8_t* done,
                          uint8_t* fail, uint8_t* end, float* percent, int auto_reset, void* stream) {
   if (!b || !actions) return set_err("hoic_step: bad arguments");
@@ -1055,13 +1080,16 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
       LAUNCH_CHECK();
       b->b.perm = b->order;
     } else b->b.perm = nullptr;
+    if (b->b.full_count) CUDA_OK(cudaMemsetAsync(b->b.full_count, 0, (size_t)HOIC_MAX_PARTS * FULL_COUNT_STRIDE * sizeof(int), user));
     // fork: every part runs on its own stream; the caller's stream waits for all of them at the end
     CUDA_OK(cudaEventRecord(b->ev_fork, user));
     for (int j = 0; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_fork, 0));
+    if (b->part_delay_ns > 0 && np > 1) { k_delay<<<1, 1, 0, b->part_stream[1]>>>(b->part_delay_ns); LAUNCH_CHECK(); }
     STEP_PARTS(0, hoic_launch_p1(b->b, sp, actions, -1, sm));
     STEP_PARTS(1, hoic_launch_p2(b->b, sp, -1, sm));
     for (int k = 0; k < b->nsub; k++) {
-      STEP_PARTS(0, hoic_launch_p1(b->b, sp, actions, k, sm));
+      // fused mode: k_p1 of substep k >= 1 ran inside the previous substep's solve launch (k_a.cu)
+      if (!(b->fuse && k > 0)) STEP_PARTS(0, hoic_launch_p1(b->b, sp, actions, k, sm));
       STEP_PARTS(1, hoic_launch_p2(b->b, sp, k, sm));
       // the two capacity tiers of the solver take disjoint envs: side by side (the few long solves of the full tier would
       // otherwise sit on every substep's critical path)
@@ -1069,9 +1097,11 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
         const StepPart sp = {j, np};
         CUDA_OK(cudaEventRecord(b->ev_rows[j], b->part_stream[j]));
         CUDA_OK(cudaStreamWaitEvent(b->aux_stream[j], b->ev_rows[j], 0));
-        STEP_LAUNCH(3, b->aux_stream[j], hoic_launch_p3(b->b, sp, k, b->aux_stream[j]));
+        if (b->fuse) STEP_LAUNCH(3, b->aux_stream[j], hoic_launch_a(b->b, sp, actions, k, b->aux_stream[j]));
+        else STEP_LAUNCH(3, b->aux_stream[j], hoic_launch_p3(b->b, sp, k, b->aux_stream[j]));
         CUDA_OK(cudaEventRecord(b->ev_aux[j], b->aux_stream[j]));
-        STEP_LAUNCH(2, b->part_stream[j], hoic_launch_p3s(b->b, sp, k, b->part_stream[j]));
+        if (b->fuse) STEP_LAUNCH(2, b->part_stream[j], hoic_launch_as(b->b, sp, actions, k, b->part_stream[j]));
+        else STEP_LAUNCH(2, b->part_stream[j], hoic_launch_p3s(b->b, sp, k, b->part_stream[j]));
         CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_aux[j], 0));
       }
     }

@@ -13,6 +13,9 @@ cudaError_t hoic_launch_p1(const BatchDev& B, StepPart sp, const float* actions,
 cudaError_t hoic_launch_p2(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);
 cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);    // full-capacity tier
 cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);   // small tier (most envs)
+// fused kernels (k_a.cu): Newton solve of substep k + k_p1's work of substep k + 1 in one launch, per capacity tier
+cudaError_t hoic_launch_a(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream);
+cudaError_t hoic_launch_as(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream);
 cudaError_t hoic_launch_tail(const BatchDev& B, StepPart sp, const float* actions, const StepOut& out, cudaStream_t stream);
 // shared-memory attributes of the four kernels on the current device (once per device)
 cudaError_t hoic_configure_p1();
@@ -20,3 +23,5 @@ cudaError_t hoic_configure_p2();
 cudaError_t hoic_configure_p3();
 cudaError_t hoic_configure_p3s();
 cudaError_t hoic_configure_tail();
+cudaError_t hoic_configure_a();
+cudaError_t hoic_configure_as();

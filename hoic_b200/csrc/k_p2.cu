@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, Ste
   __syncwarp();
   // the used part of the constraint stage -> global working set (input of the Newton solve)
   const int nc = misc[MI_NCON], nb = misc[MI_NBASIS], nrow = H_RCON + ((misc[MI_NEDGE] + 31) & ~31);
+  if (lane == 0 && B.full_list && !(nc <= P3S_NCON && nb <= P3S_NBASIS && misc[MI_NEDGE] <= P3S_NEDGE) && !env_dead(misc))
+    B.full_list[(size_t)sp.part * B.n_envs + atomicAdd(B.full_count + sp.part * FULL_COUNT_STRIDE + k, 1)] = env;
   ST_FIELD(MISC);
   ST_U(B, nb * B_STRIDE);
   ST_U(AREF, nrow); ST_U(D, nrow); ST_U(RINFO, nrow);

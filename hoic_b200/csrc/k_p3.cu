@@ -18,11 +18,11 @@
 #endif
 #include "hoic_step.cuh"
 
-#define P3S_NCON 8
-#define P3S_NBASIS 24
-#define P3S_NEDGE 32
 #ifndef P3_W
 #define P3_W 1
+#endif
+#ifndef P3_LIST_GRID
+#define P3_LIST_GRID 592     // CTAs of a full-tier launch over k_p2's env list (4 per SM; more envs than that are grid-strided)
 #endif
 #ifndef P3_WPS
 #ifdef P3_SMALL
@@ -32,13 +32,8 @@
 #endif
 #endif
 
-__global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, StepPart sp, int k) {
-  extern __shared__ __align__(16) float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P3_W + warp);
-  const int env = es.env;
-  if (!es.live) return;
-  float* s = smem + (size_t)warp * S_TOTAL;
+// the solve of one env (one warp); s = the warp's shared-memory region
+__device__ __forceinline__ void p3_env(const BatchDev& B, const int env, const int k, float* s, const int lane) {
   float* g = B.scratch + (size_t)env * G_TOTAL;
   const DevModel& m = *B.env_model[env];
   int* misc = (int*)(s + S_MISC);
@@ -75,6 +70,27 @@ __global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, Ste
   if (B.rec_frames) ST_U(FORCE, nrow);
 }
 
+__global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, StepPart sp, int k) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s = smem + (size_t)warp * S_TOTAL;
+#ifndef P3_SMALL
+  if (B.full_list) {
+    // full tier: only the envs k_p2 listed for this substep (a few per cent of the batch), grid-strided
+    const int n = B.full_count[sp.part * FULL_COUNT_STRIDE + k];
+    const int* list = B.full_list + (size_t)sp.part * B.n_envs;
+    for (int i = blockIdx.x * P3_W + warp; i < n; i += gridDim.x * P3_W) {
+      p3_env(B, list[i], k, s, lane);
+      __syncwarp();
+    }
+    return;
+  }
+#endif
+  const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P3_W + warp);
+  if (!es.live) return;
+  p3_env(B, es.env, k, s, lane);
+}
+
 static int g_p3_pad = -1;
 #ifdef P3_SMALL
 cudaError_t hoic_configure_p3s() {
@@ -90,6 +106,10 @@ cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t 
 #else
 cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
 #endif
-  K_P3<<<hoic_step_grid(B, sp, P3_W), 32 * P3_W, hoic_step_smem(P3_W, g_p3_pad < 0 ? 0 : g_p3_pad), stream>>>(B, sp, k);
+  int grid = hoic_step_grid(B, sp, P3_W);
+#ifndef P3_SMALL
+  if (B.full_list) grid = grid < P3_LIST_GRID ? grid : P3_LIST_GRID;
+#endif
+  K_P3<<<grid, 32 * P3_W, hoic_step_smem(P3_W, g_p3_pad < 0 ? 0 : g_p3_pad), stream>>>(B, sp, k);
   return cudaGetLastError();
 }

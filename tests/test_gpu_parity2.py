@@ -307,3 +307,37 @@ def test_sdf_penetration_metric():
     assert np.abs(p1 * np.maximum(nho, 1) * 2 - p2 * np.maximum(ncon, 1)).max() < 1e-3
     pm2 = PhysMetrics(model("banana"), np.concatenate([model("banana").motion(1)["hand_dof_seq"], model("banana").motion(1)["obj_pose_seq"]], 1)[100:160])
     assert pm2.eval_contact_point().max() >= 1
+
+
+def test_fused_solve_and_smooth_dynamics_kernel_equals_the_separate_kernels():
+    """HOIC_FUSE=1 (k_a.cu: Newton solve of substep k + k_p1's work of substep k + 1 in one launch; opt-in, measured slower)
+    must reproduce the default pipeline bit for bit: box and banana, auto-reset on, test-mode recording on."""
+    import os
+    import torch
+    from hoic_b200.vecenv import HandMimicVecEnv
+    for obj in ("box", "banana"):
+        mdl = model(obj)
+        outs = []
+        for fuse in ("0", "1"):
+            os.environ["HOIC_FUSE"] = fuse
+            try:
+                env = HandMimicVecEnv(mdl, 160, [mdl.motion(s) for s in range(1, 9)], device=0, seed=5, auto_reset=True)
+            finally:
+                os.environ.pop("HOIC_FUSE", None)
+            env.set_record(True)
+            env.reset()
+            g = torch.Generator(device="cuda").manual_seed(3)
+            acc = []
+            for _ in range(6):
+                a = torch.randn(160, 32, device="cuda", generator=g) * 0.3
+                obs, r, done, info = env.step(a)
+                qpos, qvel = env.get_state()
+                acc.append((obs.clone(), r.clone(), done.clone(), info["reward_info"].clone(), qpos.clone(), qvel.clone(),
+                            env._rec_frames.clone(), env._rec_surface.clone()))
+            torch.cuda.synchronize()
+            outs.append((acc, env.counters()))
+            env.close()
+        for sa, sb in zip(outs[0][0], outs[1][0]):
+            for x, y in zip(sa, sb):
+                assert torch.equal(x, y), obj
+        assert outs[0][1] == outs[1][1]
