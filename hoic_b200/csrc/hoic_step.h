@@ -10,6 +10,7 @@ struct StepOut;
 struct StepPart { int part, nparts; };
 // k = substep index; -1 = the pass that recomputes the forward of the state that preceded the step
 cudaError_t hoic_launch_p1(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream);
+cudaError_t hoic_launch_p1w(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream);   // four envs per CTA
 cudaError_t hoic_launch_p2(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);
 cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);    // full-capacity tier
 cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);   // small tier (most envs)
@@ -19,6 +20,7 @@ cudaError_t hoic_launch_as(const BatchDev& B, StepPart sp, const float* actions,
 cudaError_t hoic_launch_tail(const BatchDev& B, StepPart sp, const float* actions, const StepOut& out, cudaStream_t stream);
 // shared-memory attributes of the four kernels on the current device (once per device)
 cudaError_t hoic_configure_p1();
+cudaError_t hoic_configure_p1w();
 cudaError_t hoic_configure_p2();
 cudaError_t hoic_configure_p3();
 cudaError_t hoic_configure_p3s();

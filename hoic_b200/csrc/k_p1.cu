@@ -8,6 +8,17 @@
 #define H_KERNEL HK_P1
 #include "p1_body.cuh"
 
+// Compiled twice: one env per CTA (k_p1) and, with -DP1_WIDE, four envs per CTA (k_p1w).  Every CTA pays 1 KB of reserved
+// shared memory, so the wide form holds 24 instead of 22 envs per SM: faster where the batch keeps every SM full (box,
+// 16 384 envs: 13.33 -> 12.88 ms per step), slower at 4 096 envs (4.26 -> 4.36 ms: a part's kernel is about one wave there
+// and a four-env CTA starts only when 38 KB are free at once).  hoic_step picks by the batch size.
+#ifdef P1_WIDE
+#define P1_W 4
+#define P1_WPS 24
+#define K_P1 k_p1w
+#else
+#define K_P1 k_p1
+#endif
 #ifndef P1_W
 #define P1_W 1          // warps (= envs) per CTA
 #endif
@@ -15,7 +26,7 @@
 #define P1_WPS 23       // resident warps per SM the register budget is sized for
 #endif
 
-__global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) k_p1(BatchDev B, StepPart sp, const float* __restrict__ actions, int k) {
+__global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) K_P1(BatchDev B, StepPart sp, const float* __restrict__ actions, int k) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P1_W + warp);
@@ -30,12 +41,20 @@ __global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) k_p1(BatchDev B, Ste
 }
 
 static int g_p1_pad = -1;
+#ifdef P1_WIDE
+cudaError_t hoic_configure_p1w() {
+#else
 cudaError_t hoic_configure_p1() {
+#endif
   g_p1_pad = hoic_env_int("HOIC_P1_PAD", 0);
   const size_t smem = hoic_step_smem(P1_W, g_p1_pad);
-  return cudaFuncSetAttribute(k_p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaFuncSetAttribute(K_P1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
+#ifdef P1_WIDE
+cudaError_t hoic_launch_p1w(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream) {
+#else
 cudaError_t hoic_launch_p1(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream) {
-  k_p1<<<hoic_step_grid(B, sp, P1_W), 32 * P1_W, hoic_step_smem(P1_W, g_p1_pad < 0 ? 0 : g_p1_pad), stream>>>(B, sp, actions, k);
+#endif
+  K_P1<<<hoic_step_grid(B, sp, P1_W), 32 * P1_W, hoic_step_smem(P1_W, g_p1_pad < 0 ? 0 : g_p1_pad), stream>>>(B, sp, actions, k);
   return cudaGetLastError();
 }

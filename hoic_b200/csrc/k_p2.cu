@@ -3,6 +3,11 @@
 // k = -1: contacts of the forward that preceded the step + the geom-pose snapshot of ho_im4.py:508-511.
 // The work per env depends on its contacts, so every env is its own CTA: the CTA scheduler balances the load.
 #define H_KERNEL HK_P2
+#ifdef P2_CAP_NCON      // experiment (tools/build_variant.sh): constraint stage of k_p2 at a smaller capacity than the working set's
+#define H_NCON P2_CAP_NCON
+#define H_NBASIS P2_CAP_NBASIS
+#define H_NEDGE P2_CAP_NEDGE
+#endif
 #include "hoic_step.cuh"
 
 #ifndef P2_W
