@@ -202,20 +202,33 @@ def timed_rollout(sampler, steps, flush, world, dist, dev):
 
 
 def kernel_timing(env, actions, steps):
-    """Duration of hoic_step (CUDA events on the launching stream around eager calls, not part of the timed region) and,
-    from a second pass with the library's per-launch event timing, how the stream time splits over the pipeline's kernels."""
+    """Duration of hoic_step (CUDA events on the launching stream around replays of a graph that holds only that call, the
+    way the sampler step runs it; a few extra rollout steps, not part of the timed region) and, from a second pass of eager
+    calls with the library's per-launch event timing, how the stream time splits over the pipeline's kernels."""
     import ctypes as C
     import torch
     L = env.L
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     l0 = L.hoic_launch_count()
+    for _ in range(2):
+        env.step(actions)
+    torch.cuda.synchronize()
+    launches = (L.hoic_launch_count() - l0) // 2
+    # hoic_step alone as the sampler runs it: captured into a CUDA graph, replayed, CUDA events around every replay
+    dev = actions.device
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        env.step(actions)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b in ev:
         a.record()
-        env.step(actions)
+        g.replay()
         b.record()
     torch.cuda.synchronize()
-    launches = (L.hoic_launch_count() - l0) // steps
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    del g
     L.hoic_set_timing(env._hb, 1)
     for _ in range(steps):
         env.step(actions)
@@ -342,7 +355,7 @@ def run_ours(args):
     tot = stats.allreduce()
 
     # ---- per-kernel durations and the launch count of one step (eager launches with the library's event timing)
-    kt = kernel_timing(env, sampler.act, 5)
+    kt = kernel_timing(env, sampler.act, 10)
     launches_per_step = kt["launches_per_hoic_step"] + 5       # + k_zf_moments, k_zf_apply16, k_sample_action, k_get_episode, k_logger
 
     # ---- e2e: host-resident sampler (noise H2D, transition D2H, one graph launch + stream sync per step)

@@ -22,9 +22,11 @@
 #define HG_NBASIS 80
 #define HG_NEDGE 128
 // capacity of the solver's SMALL tier (k_p3s / k_as): envs whose constraint stage fits are solved there, the rest by k_p3 / k_a
+#ifndef P3S_NCON
 #define P3S_NCON 8
 #define P3S_NBASIS 24
 #define P3S_NEDGE 32
+#endif
 #define H_RFR 0        // row index ranges: friction-loss rows [0,32)
 #define H_RLIM 32      //                   joint-limit rows   [32,64)
 #define H_RCON 64      //                   contact edge rows  [64,64+H_NEDGE)

@@ -16,9 +16,14 @@
 // The last substep's solve has no k_p1 after it (k_tail integrates it): for k + 1 >= sim_step the kernel ends like k_p3.
 #define H_KERNEL HK_A
 #ifdef P3_SMALL
-#define H_NCON 8
-#define H_NBASIS 24
-#define H_NEDGE 32
+#ifndef P3S_NCON      // (A/B builds pass -DP3S_NCON=.. -DP3S_NBASIS=.. -DP3S_NEDGE=..; the default lives in dev_model.h)
+#define P3S_NCON 8
+#define P3S_NBASIS 24
+#define P3S_NEDGE 32
+#endif
+#define H_NCON P3S_NCON
+#define H_NBASIS P3S_NBASIS
+#define H_NEDGE P3S_NEDGE
 #define K_A k_as
 #define P3_TIER 0
 #else

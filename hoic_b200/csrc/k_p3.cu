@@ -7,9 +7,14 @@
 // full tier (24 / 56 / 96, 16 KB per env) takes the rest.  Each env is solved by exactly one of the two launches.
 #define H_KERNEL HK_P3
 #ifdef P3_SMALL
-#define H_NCON 8
-#define H_NBASIS 24
-#define H_NEDGE 32
+#ifndef P3S_NCON      // (A/B builds pass -DP3S_NCON=.. -DP3S_NBASIS=.. -DP3S_NEDGE=..; the default lives in dev_model.h)
+#define P3S_NCON 8
+#define P3S_NBASIS 24
+#define P3S_NEDGE 32
+#endif
+#define H_NCON P3S_NCON
+#define H_NBASIS P3S_NBASIS
+#define H_NEDGE P3S_NEDGE
 #define K_P3 k_p3s
 #define P3_TIER 0
 #else

@@ -4,6 +4,7 @@ per-function tables of the pipeline kernels.   python tools/summarise_profiles.p
 import collections, csv, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+TAG = os.environ.get("TAG", "r02_final")      # capture set (tools/profile_r02.sh)
 
 
 def rows_of(path):
@@ -27,9 +28,9 @@ def launch_summary(src, dst, title):
     return agg
 
 
-if os.path.exists(os.path.join(G, "r02_final_bench_launches.csv")):
-    shutil.copy(os.path.join(G, "r02_final_bench_launches.csv"), os.path.join(P, "r02_final_bench_launches.csv"))
-    launch_summary(os.path.join(G, "r02_final_bench_launches.csv"), os.path.join(P, "r02_final_bench_launch_summary.txt"),
+if os.path.exists(os.path.join(G, TAG + "_bench_launches.csv")):
+    shutil.copy(os.path.join(G, TAG + "_bench_launches.csv"), os.path.join(P, TAG + "_bench_launches.csv"))
+    launch_summary(os.path.join(G, TAG + "_bench_launches.csv"), os.path.join(P, TAG + "_bench_launch_summary.txt"),
                    "ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 2 --warmup 1 --preroll 2 --no-extras --no-cpu "
                    "(box, 4096 envs; kernels of the replayed CUDA graphs are profiled one by one: cold, serialised)")
 
@@ -50,7 +51,7 @@ def traffic(tp, tag, note):
     sc = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     rs, ws = sc[units["dram__bytes_read.sum"]], sc[units["dram__bytes_write.sum"]]
     tot = sum(v["dram__bytes_read.sum"] * rs + v["dram__bytes_write.sum"] * ws for k, v in per.items() if k.startswith("k_")) / steps
-    with open(os.path.join(P, f"r02_final_step_traffic_{tag}.txt"), "w") as f:
+    with open(os.path.join(P, f"{TAG}_step_traffic_{tag}.txt"), "w") as f:
         f.write(f"ncu dram__bytes_read.sum + dram__bytes_write.sum and durations of the launches of {steps:.1f} hoic_step calls (box, 4096 envs, "
                 f"2 parts), per step; {note}:\n")
         for k, v in sorted(per.items(), key=lambda x: -x[1]["gpu__time_duration.sum"]):
@@ -61,7 +62,7 @@ def traffic(tp, tag, note):
     return tot
 
 
-cold, warm = os.path.join(G, "r02_final_step_traffic.csv"), os.path.join(G, "r02_final_step_traffic_warm.csv")
+cold, warm = os.path.join(G, TAG + "_step_traffic.csv"), os.path.join(G, TAG + "_step_traffic_warm.csv")
 res = {}
 if os.path.exists(cold):
     res["box:4096:cold_caches"] = traffic(cold, "cold", "ncu's default cache control: L2 flushed before every kernel, so every kernel re-reads its part "
@@ -76,14 +77,14 @@ if res:
 cub = "/tmp/cub_final"
 os.makedirs(cub, exist_ok=True)
 for kn, obj in (("k_p1", "k_p1"), ("k_p2", "k_p2"), ("k_p3s", "k_p3s"), ("k_tail", "k_tail"), ("banana_k_p2", "k_p2")):
-    rep = os.path.join(G, f"r02_final_{kn}.ncu-rep")
+    rep = os.path.join(G, f"{TAG}_{kn}.ncu-rep")
     if not os.path.exists(rep):
         continue
-    raw = os.path.join(P, f"r02_final_{kn}_raw.csv")
+    raw = os.path.join(P, f"{TAG}_{kn}_raw.csv")
     subprocess.run(f"ncu -i {rep} --page raw --csv > {raw} 2>/dev/null", shell=True)
-    src = f"/tmp/r02_final_{kn}_src.csv"
+    src = f"/tmp/{TAG}_{kn}_src.csv"
     subprocess.run(f"ncu -i {rep} --page source --csv > {src} 2>/dev/null", shell=True)
     subprocess.run(f"cd {cub} && cuobjdump -xelf all {ROOT}/hoic_b200/build/{obj}.o > /dev/null 2>&1", shell=True)
     kernel = "_Z5k_p3s" if obj == "k_p3s" else ("_Z6k_tail" if obj == "k_tail" else "_Z4" + obj)
-    subprocess.run(f"python {ROOT}/tools/ncu_by_function.py {src} {cub}/{obj}.sm_100a.cubin {kernel} > {P}/r02_final_{kn}_by_function.txt 2>/dev/null", shell=True)
+    subprocess.run(f"python {ROOT}/tools/ncu_by_function.py {src} {cub}/{obj}.sm_100a.cubin {kernel} > {P}/{TAG}_{kn}_by_function.txt 2>/dev/null", shell=True)
     print(kn, "done")
