@@ -201,15 +201,17 @@ def timed_rollout(sampler, steps, flush, world, dist, dev):
     return float(tmax.item()), t0, t1
 
 
-def kernel_timing(env, actions, steps):
+def kernel_timing(env, sampler, steps):
     """Duration of hoic_step (CUDA events on the launching stream around replays of a graph that holds only that call, the
     way the sampler step runs it; a few extra rollout steps, not part of the timed region) and, from a second pass of eager
     calls with the library's per-launch event timing, how the stream time splits over the pipeline's kernels."""
     import ctypes as C
     import torch
     L = env.L
+    actions = sampler.act
     l0 = L.hoic_launch_count()
     for _ in range(2):
+        sampler.compute_action()
         env.step(actions)
     torch.cuda.synchronize()
     launches = (L.hoic_launch_count() - l0) // 2
@@ -223,6 +225,7 @@ def kernel_timing(env, actions, steps):
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b in ev:
+        sampler.compute_action()        # untimed: the rollout goes on under the policy, so the states stay those of the timed region
         a.record()
         g.replay()
         b.record()
@@ -231,6 +234,7 @@ def kernel_timing(env, actions, steps):
     del g
     L.hoic_set_timing(env._hb, 1)
     for _ in range(steps):
+        sampler.compute_action()
         env.step(actions)
     ms = (C.c_double * 8)()
     n = C.c_int(0)
@@ -270,7 +274,7 @@ def short_config(obj, N, local, rank, world, dist, dev, policy_seed=1, steps=8, 
     total_ms, _, _ = timed_rollout(sampler, steps, None, world, dist, dev)
     c1 = env.counters()
     flops, per, dc = flop_model(c0, c1)
-    kt = kernel_timing(env, sampler.act, 3)
+    kt = kernel_timing(env, sampler, 3)
     out = dict(workload=f"{obj}, {N} envs per GPU" + (", episodes started in frames 100-179 (grasp / lift)" if grasp else ""),
                value=world * N * steps / (total_ms * 1e-3), unit=UNIT, ms_per_step=total_ms / steps, kernel_ms=kt["hoic_step"],
                flops_per_env_step=flops / max(dc["env_steps"], 1),
@@ -355,7 +359,7 @@ def run_ours(args):
     tot = stats.allreduce()
 
     # ---- per-kernel durations and the launch count of one step (eager launches with the library's event timing)
-    kt = kernel_timing(env, sampler.act, 10)
+    kt = kernel_timing(env, sampler, 10)
     launches_per_step = kt["launches_per_hoic_step"] + 5       # + k_zf_moments, k_zf_apply16, k_sample_action, k_get_episode, k_logger
 
     # ---- e2e: host-resident sampler (noise H2D, transition D2H, one graph launch + stream sync per step)

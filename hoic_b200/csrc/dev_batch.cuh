@@ -41,6 +41,9 @@ struct BatchDev {
   // k_p3 (full tier): the full-tier launch then covers only those envs instead of starting one 19 KB CTA per env of the batch
   int* full_list;                     // [nparts][N]
   int* full_count;                    // [nparts][FULL_COUNT_STRIDE], entry k = substep, zeroed at the start of a step
+  // envs whose episode ended in the running step (appended by k_tail): the auto-reset launch covers only those
+  int* reset_list;                    // [N]
+  int* reset_count;                   // one counter behind full_count's block (same memset)
 };
 #define FULL_COUNT_STRIDE 32
 

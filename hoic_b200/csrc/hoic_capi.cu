@@ -29,12 +29,8 @@ __device__ __forceinline__ float hoic_uniform(unsigned long long seed, unsigned 
 
 // `sample` != 0: draw (motion, start_idx) on the device as the sampler does between episodes (agent_handmimic.py:437-448):
 // a uniform motion of the env's model, start ~ U{0 .. len - min_episode - 1} (0 without random_start).
-__global__ void __launch_bounds__(32) k_reset(BatchDev B, const uint8_t* __restrict__ mask, const int* __restrict__ motion_id,
-                                              const int* __restrict__ start_idx, float* obs_out, int sample) {
-  extern __shared__ float s[];
-  const int env = blockIdx.x, lane = threadIdx.x;
-  if (env >= B.n_envs) return;
-  if (mask && !mask[env]) return;
+static __device__ void reset_env(const BatchDev& B, const int env, const int* __restrict__ motion_id, const int* __restrict__ start_idx,
+                                 float* obs_out, const int sample, float* s, const int lane) {
   const DevModel& m = *B.env_model[env];
   float* st = B.state + (size_t)env * ST_STRIDE;
   int* ints = (int*)(st + ST_INTS);
@@ -80,6 +76,24 @@ __global__ void __launch_bounds__(32) k_reset(BatchDev B, const uint8_t* __restr
   st[ST_PQVEL + lane] = s[S_QVEL + lane];
   if (lane == 0) { st[ST_QPOS + 32] = s[S_QPOS + 32]; st[ST_PQPOS + 32] = s[S_QPOS + 32]; }
   if (lane < 8) st[ST_RFC + lane] = 0.f;
+}
+// use_list != 0: the envs k_tail listed as finished (B.reset_list / reset_count), grid-strided; otherwise env = blockIdx.x under `mask`
+__global__ void __launch_bounds__(32) k_reset(BatchDev B, const uint8_t* __restrict__ mask, const int* __restrict__ motion_id,
+                                              const int* __restrict__ start_idx, float* obs_out, int sample, int use_list) {
+  extern __shared__ float s[];
+  const int lane = threadIdx.x;
+  if (use_list) {
+    const int n = *B.reset_count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+      reset_env(B, B.reset_list[i], motion_id, start_idx, obs_out, sample, s, lane);
+      __syncwarp();
+    }
+    return;
+  }
+  const int env = blockIdx.x;
+  if (env >= B.n_envs) return;
+  if (mask && !mask[env]) return;
+  reset_env(B, env, motion_id, start_idx, obs_out, sample, s, lane);
 }
 
 // Longest-processing-time env order for the step pipeline: a counting sort of the envs by the cost proxy of their last
@@ -360,6 +374,7 @@ struct hoic_model {
 };
 
 #define HOIC_MAX_PARTS 8
+#define HOIC_COUNT_INTS (HOIC_MAX_PARTS * FULL_COUNT_STRIDE + 32)   // full-tier counters per (part, substep) + the reset counter
 #define HOIC_TIMING_CLASSES 8          // k_p1, k_p2, k_p3s, k_p3, k_tail, k_reset, k_order, whole call
 static int capi_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 struct hoic_batch {
@@ -387,6 +402,8 @@ struct hoic_batch {
   bool p1_wide = false;                  // k_p1 with four envs per CTA (large batches)
   int part_delay_ns = 0;                 // experiment: part 1 starts this much later than part 0 (HOIC_PART_DELAY_US)
   cudaStream_t part_stream[HOIC_MAX_PARTS] = {}, aux_stream[HOIC_MAX_PARTS] = {};   // aux: the solver's full-capacity tier
+  bool order_valid = false;              // b->order holds the env order the previous hoic_step computed for this one
+  cudaEvent_t ev_tail = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join[HOIC_MAX_PARTS] = {}, ev_rows[HOIC_MAX_PARTS] = {}, ev_aux[HOIC_MAX_PARTS] = {};
 };
 
@@ -820,8 +837,10 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   CUDA_OKP(cudaMalloc(&b->b.csum_carry, (size_t)n_envs * CSUM_STRIDE * sizeof(float)));
   if (capi_env_int("HOIC_FULL_LIST", 1)) {
     CUDA_OKP(cudaMalloc(&b->b.full_list, (size_t)HOIC_MAX_PARTS * n_envs * sizeof(int)));
-    CUDA_OKP(cudaMalloc(&b->b.full_count, (size_t)HOIC_MAX_PARTS * FULL_COUNT_STRIDE * sizeof(int)));
-    CUDA_OKP(cudaMemset(b->b.full_count, 0, (size_t)HOIC_MAX_PARTS * FULL_COUNT_STRIDE * sizeof(int)));
+    CUDA_OKP(cudaMalloc(&b->b.full_count, (size_t)HOIC_COUNT_INTS * sizeof(int)));
+    CUDA_OKP(cudaMemset(b->b.full_count, 0, (size_t)HOIC_COUNT_INTS * sizeof(int)));
+    CUDA_OKP(cudaMalloc(&b->b.reset_list, (size_t)n_envs * sizeof(int)));
+    b->b.reset_count = b->b.full_count + HOIC_MAX_PARTS * FULL_COUNT_STRIDE;
   }
   CUDA_OKP(cudaMalloc(&b->b.counters, 16 * sizeof(unsigned long long)));
   CUDA_OKP(cudaMemset(b->b.counters, 0, 16 * sizeof(unsigned long long)));
@@ -849,6 +868,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     b->p1_wide = capi_env_int("HOIC_P1_WIDE", n_envs >= 8192 ? 1 : 0) != 0;
     if (const char* e = getenv("HOIC_FUSE")) b->fuse = atoi(e) != 0;
     CUDA_OKP(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    CUDA_OKP(cudaEventCreateWithFlags(&b->ev_tail, cudaEventDisableTiming));
     for (int j = 0; j < b->nparts; j++) {
       // experiment knobs (tools/ab_r2b.sh): HOIC_PRIO_PART1 / HOIC_PRIO_AUX = CUDA stream priority (lower = more urgent)
       int lo = 0, hi = 0;
@@ -881,6 +901,7 @@ extern "C" void hoic_batch_destroy(hoic_batch* b) {
   cudaSetDevice(b->device);
   cudaDeviceSynchronize();
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_tail) cudaEventDestroy(b->ev_tail);
   for (int j = 0; j < HOIC_MAX_PARTS; j++) {
     if (b->ev_join[j]) cudaEventDestroy(b->ev_join[j]);
     if (b->ev_rows[j]) cudaEventDestroy(b->ev_rows[j]);
@@ -889,7 +910,7 @@ extern "C" void hoic_batch_destroy(hoic_batch* b) {
     if (b->aux_stream[j]) cudaStreamDestroy(b->aux_stream[j]);
   }
   cudaFree(b->env_model_dev); cudaFree(b->b.scratch); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum); cudaFree(b->b.csum_carry);
-  cudaFree(b->b.full_list); cudaFree(b->b.full_count);
+  cudaFree(b->b.full_list); cudaFree(b->b.full_count); cudaFree(b->b.reset_list);
   cudaFree(b->env_model_idx); cudaFree(b->samp_off); cudaFree(b->samp_ids); cudaFree(b->order);
   cudaFree(b->reward_w); cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
   delete b;
@@ -977,7 +998,7 @@ extern "C" int hoic_reset(hoic_batch* b, const uint8_t* mask, const int* motion_
   if (!b) return set_err("hoic_reset: null batch");
   if (!b->b.frames) return set_err("hoic_reset: call hoic_set_motions first");
   CUDA_OK(cudaSetDevice(b->device));
-  k_reset<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, mask, motion_id, start_idx, obs_out, 0);
+  k_reset<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, mask, motion_id, start_idx, obs_out, 0, 0);
   LAUNCH_CHECK();
   return 0;
 }
@@ -986,7 +1007,7 @@ extern "C" int hoic_reset_sampled(hoic_batch* b, const uint8_t* mask, float* obs
   if (!b) return set_err("hoic_reset_sampled: null batch");
   if (!b->b.samp_off) return set_err("hoic_reset_sampled: call hoic_set_sampler first");
   CUDA_OK(cudaSetDevice(b->device));
-  k_reset<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, mask, nullptr, nullptr, obs_out, 1);
+  k_reset<<<b->n_envs, 32, b->smem_bytes, (cudaStream_t)stream>>>(b->b, mask, nullptr, nullptr, obs_out, 1, 0);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1077,12 +1098,16 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
     TimedLaunch whole(b, 7, user);
     if (b->user_perm) b->b.perm = b->user_perm;
     else if (b->balance) {
-      TimedLaunch tl(b, 6, user);
-      k_order<<<1, 1024, 0, user>>>(b->b, b->order);
-      LAUNCH_CHECK();
+      // the order of THIS step was computed at the end of the previous one (below), beside the auto-reset; only a batch's
+      // first step sorts at its head
+      if (!b->order_valid) {
+        TimedLaunch tl(b, 6, user);
+        k_order<<<1, 1024, 0, user>>>(b->b, b->order);
+        LAUNCH_CHECK();
+      }
       b->b.perm = b->order;
     } else b->b.perm = nullptr;
-    if (b->b.full_count) CUDA_OK(cudaMemsetAsync(b->b.full_count, 0, (size_t)HOIC_MAX_PARTS * FULL_COUNT_STRIDE * sizeof(int), user));
+    if (b->b.full_count) CUDA_OK(cudaMemsetAsync(b->b.full_count, 0, (size_t)HOIC_COUNT_INTS * sizeof(int), user));
     // fork: every part runs on its own stream; the caller's stream waits for all of them at the end
     CUDA_OK(cudaEventRecord(b->ev_fork, user));
     for (int j = 0; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_fork, 0));
@@ -1109,13 +1134,28 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
     }
     STEP_PARTS(4, hoic_launch_tail(b->b, sp, actions, o, sm));
     for (int j = 0; j < np; j++) { CUDA_OK(cudaEventRecord(b->ev_join[j], b->part_stream[j])); CUDA_OK(cudaStreamWaitEvent(user, b->ev_join[j], 0)); }
+    const bool order_next = !b->user_perm && b->balance;
+    if (order_next) {
+      // env order of the NEXT step from this step's cost proxies (k_tail wrote them), on a side stream beside the auto-reset
+      CUDA_OK(cudaEventRecord(b->ev_tail, user));
+      CUDA_OK(cudaStreamWaitEvent(b->aux_stream[0], b->ev_tail, 0));
+      {
+        TimedLaunch tl(b, 6, b->aux_stream[0]);
+        k_order<<<1, 1024, 0, b->aux_stream[0]>>>(b->b, b->order);
+        LAUNCH_CHECK();
+      }
+      CUDA_OK(cudaEventRecord(b->ev_aux[0], b->aux_stream[0]));
+      b->order_valid = true;
+    }
     if (auto_reset) {
       // the sampler's episode loop (agent_handmimic.py:437-454): a finished env restarts on a freshly drawn (motion, start)
-      // and its returned observation is the reset observation
+      // and its returned observation is the reset observation; only the envs k_tail listed as finished get a CTA
       TimedLaunch tl(b, 5, user);
-      k_reset<<<b->n_envs, 32, b->smem_bytes, user>>>(b->b, done, nullptr, nullptr, obs, 1);
+      if (b->b.reset_list) k_reset<<<std::min(b->n_envs, 296), 32, b->smem_bytes, user>>>(b->b, nullptr, nullptr, nullptr, obs, 1, 1);
+      else k_reset<<<b->n_envs, 32, b->smem_bytes, user>>>(b->b, done, nullptr, nullptr, obs, 1, 0);
       LAUNCH_CHECK();
     }
+    if (order_next) CUDA_OK(cudaStreamWaitEvent(user, b->ev_aux[0], 0));
   }
 #undef STEP_PARTS
 #undef STEP_LAUNCH

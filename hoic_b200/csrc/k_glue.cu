@@ -15,7 +15,7 @@ int glue_err(const char* what, cudaError_t e) { g_glue_err = std::string(what) +
 
 #define ZF_COLS 32       // columns per CTA (one warp-wide coalesced row segment)
 #define ZF_ROWS 8        // row lanes per CTA
-#define ZF_CHUNKS 8      // row chunks (grid.y) of the moments pass
+#define ZF_CHUNKS 32     // row chunks (grid.y) of the moments pass: 20 x 32 CTAs for 617 columns (8 chunks: 20.5 us at 4096 rows)
 // Batch moments about the batch's first row c (a sample of the distribution is a good shift: sums of (x - c) and (x - c)^2
 // add across CTAs without cancellation, whatever the running mean is), double accumulation.  The last CTA to finish merges the batch into the running statistics (Chan et al.,
 // exactly what a sequence of RunningStat.push calls converges to) and into the since-last-sync accumulators, publishes

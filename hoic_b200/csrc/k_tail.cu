@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(32 * PT_W, PT_WPS / PT_W) k_tail(BatchDev B, S
   if (lane == 0) {
     if (out.reward) out.reward[env] = reward;
     if (out.done) out.done[env] = fail || end;
+    if (B.reset_list && (fail || end)) B.reset_list[atomicAdd(B.reset_count, 1)] = env;
     if (out.fail) out.fail[env] = fail;
     if (out.end) out.end[env] = end;
     if (out.percent) out.percent[env] = (float)ctx.cur_t / (float)(ctx.expert_len - 1);

@@ -144,7 +144,7 @@ class ZFilter:
         L = capi.lib()
         if getattr(self, "_lib_buf", None) is None or self._lib_buf[0].device != x.device:
             dim = self.mean.numel()
-            self._lib_buf = (torch.zeros(16 * dim + 1, dtype=torch.float64, device=x.device),
+            self._lib_buf = (torch.zeros(64 * dim + 1, dtype=torch.float64, device=x.device),
                              torch.zeros(2 * dim, dtype=torch.float32, device=x.device), {})
         scratch, shift_scale, outs = self._lib_buf
         key = (x.shape[0], torch.cuda.is_current_stream_capturing())

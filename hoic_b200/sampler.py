@@ -136,6 +136,17 @@ class SamplerStep:
         self.x.copy_(x)
         self.act.copy_(mean + torch.exp(log_std) * noise * self.exp[:, None])
 
+    def compute_action(self):
+        """The first half of the step alone, eagerly: normalise `env.obs`, run the policy, draw `self.act` (bench.py times
+        `hoic_step` by itself on the actions the sampler would feed it)."""
+        if self._fast:
+            self._refresh_weights()
+        with torch.no_grad():
+            if self._fast:
+                self._act_fast()
+            else:
+                self._act_torch()
+
     def _body(self, after_action=None):
         env = self.env
         with torch.no_grad():

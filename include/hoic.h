@@ -191,7 +191,7 @@ int hoic_set_balance(hoic_batch* b, int on);
  * statistics n / mean[dim] / M2[dim] (double, device; Chan's parallel Welford merge = what n successive push calls give) and,
  * if given, into a second since-last-sync triple dn / dmean / dM2 (multi-rank pooling); then
  * x_out = clip((obs - mean) / (std + 1e-8), -clip, clip) with std = sqrt(M2 / (n - 1)) (|mean| while n <= 1).
- * scratch: double[16 dim + 1], zero-initialised once by the caller; shift_scale: float[2 dim] work buffer.  Results are bitwise
+ * scratch: double[64 dim + 1], zero-initialised once by the caller; shift_scale: float[2 dim] work buffer.  Results are bitwise
  * reproducible (fixed summation order). */
 int hoic_zfilter(const float* obs, int n, int dim, double* st_n, double* mean, double* m2, double* dn, double* dmean, double* dm2,
                  double* scratch, float* shift_scale, float clip, int update, float* x_out, void* stream);
