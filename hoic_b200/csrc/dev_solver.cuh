@@ -6,6 +6,12 @@
 #pragma once
 #include "dev_math.cuh"
 
+#ifdef H_SOLVE_STATS
+static __device__ unsigned long long g_solve_stats[64];   // [0..15] solves by iterations, [16..31] cycles, [32..47] ls evals, [48..] cycles by part
+#define SST(i) do { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_solve_stats[48 + (i)], (unsigned long long)(t_ - sst_t)); sst_t = t_; } while (0)
+#else
+#define SST(i) do { } while (0)
+#endif
 #ifdef H_STATS
 static __device__ unsigned long long g_stats[8];
 static __device__ unsigned long long g_nst[64];   // [0..7] solves by iteration count, [8..15] their cycles, [16..] cycles by part
@@ -386,6 +392,9 @@ static __device__ __noinline__ bool newton_direction(float* s, const DevModel& m
 #ifdef H_STATS
   long long nst_t = clock64();
 #endif
+#ifdef H_SOLVE_STATS
+  const long long sst_a = clock64();
+#endif
   {
     const int I = lane >> 2, r = lane & 3;
 #pragma unroll 1
@@ -436,6 +445,9 @@ static __device__ __noinline__ bool newton_direction(float* s, const DevModel& m
   }
   __syncwarp();
   NST_T(8);    // Hessian assembly
+#ifdef H_SOLVE_STATS
+  { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_solve_stats[48 + 5], (unsigned long long)(t_ - sst_a)); }
+#endif
   float dir;
   const bool ok = warp_chol_solve(A, -s[S_GRAD + lane], &dir, lane);
   s[S_SEARCH + lane] = dir;
@@ -464,9 +476,15 @@ static __device__ __noinline__ void ls_eval(const float* s, const DevModel& m, i
 // exact minimiser of the piecewise-quadratic cost along `search` by safeguarded Newton on its derivative
 static __device__ __noinline__ float line_search(float* s, const DevModel& m, int lane, int nbasis, int nedge, unsigned& evals) {
   const float sv = s[S_SEARCH + lane];
+#ifdef H_SOLVE_STATS
+  const long long sst_l = clock64();
+#endif
   const float mv = mul_M(s, m, lane, s + S_SEARCH);
   s[S_MV + lane] = mv;
   mul_J(s, lane, nbasis, nedge, s + S_SEARCH, s + U_JV);
+#ifdef H_SOLVE_STATS
+  { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_solve_stats[48 + 6], (unsigned long long)(t_ - sst_l)); }
+#endif
   const float qg1 = wsum(sv * (s[S_MA + lane] - s[S_SMOOTH + lane]));
   const float qg2 = 0.5f * wsum(sv * mv);
   float d1, d2, lo = 0.f, hi = -1.f, alpha = 1.f;
@@ -505,11 +523,20 @@ static __device__ __noinline__ float newton_init(float* s, const DevModel& m, in
   mul_J(s, lane, nbasis, nedge, s + S_QACC, s + U_JAR);
   for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JAR + r] -= s[U_AREF + r];
   __syncwarp();
-  const float cost_warm = rows_update(s, m, lane, nedge, s + U_JAR, false) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
-  mul_J(s, lane, nbasis, nedge, s + S_ASMOOTH, s + U_JV);
-  for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JV + r] -= s[U_AREF + r];
-  __syncwarp();
-  const float cost_smooth = rows_update(s, m, lane, nedge, s + U_JV, false);
+#ifdef NEWTON_WARM_ONLY
+  // A/B: take the warm start whenever it is not the zero vector of a fresh reset (the optimum does not depend on the start)
+  const bool cmp = !__any_sync(FULLMASK, qacc != 0.f);
+#else
+  const bool cmp = true;
+#endif
+  float cost_warm = 0.f, cost_smooth = 0.f;
+  if (cmp) {
+    cost_warm = rows_update(s, m, lane, nedge, s + U_JAR, false) + wsum(0.5f * (ma - fsm) * (qacc - asm_));
+    mul_J(s, lane, nbasis, nedge, s + S_ASMOOTH, s + U_JV);
+    for (int r = lane; r < H_RCON + nedge; r += 32) s[U_JV + r] -= s[U_AREF + r];
+    __syncwarp();
+    cost_smooth = rows_update(s, m, lane, nedge, s + U_JV, false);
+  }
   if (cost_warm > cost_smooth) {
     qacc = asm_;
     s[S_QACC + lane] = qacc;
@@ -564,10 +591,15 @@ __device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int la
   bool run = active, ok = true;
   unsigned iter = 0;
   float cost = 0.f, oldcost = 0.f;
+#ifdef H_SOLVE_STATS
+  long long sst_t = clock64();
+#endif
   if (run) { cost = newton_init(s, m, lane, nbasis, nedge); oldcost = cost; }
+  SST(0);   // init
   for (;;) {
     if (run) {
       const float g2 = newton_gradient(s, m, lane, nlim, nbasis);
+      SST(1);   // gradient
       if (iter > 0) {
         const float improvement = scale * (oldcost - cost), gradn = scale * sqrtf(g2);
         // float32 noise floor on the cost difference replaces MuJoCo's absolute 1e-8 (see DESIGN.md "precision")
@@ -575,18 +607,24 @@ __device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int la
         if (improvement < tol || gradn < m.tolerance) run = false;
       }
       if (iter >= (unsigned)m.iterations) run = false;
+#ifdef NEWTON_CAP      // timing experiment only (what the long solves cost): stop after NEWTON_CAP iterations, converged or not
+      if (iter >= NEWTON_CAP) run = false;
+#endif
     }
     if (!NEWTON_ANY(run)) break;
     if (run) {
       // full refactorisation every iteration: the blocked Cholesky is cheaper than tracking rank-one changes
       const float diag = newton_weights(s, m, lane, nlim, ncon);
+      SST(2);   // weights
       ok = newton_direction(s, m, lane, ncon, diag);
+      SST(3);   // Hessian assembly + Cholesky + substitutions
       if (!ok) run = false;
     }
     NEWTON_SYNC();
     if (run) {
       oldcost = cost;
       const int mv = newton_move(s, m, lane, nbasis, nedge, cost, ls_evals);
+      SST(4);   // line search + move + cost
       if (mv == 0) run = false;
       else {
         iter++;

@@ -62,7 +62,18 @@ __device__ __forceinline__ void p3_env(const BatchDev& B, const int env, const i
 #endif
   Cnt cnt;
   memset(&cnt, 0, sizeof cnt);
+#ifdef H_SOLVE_STATS
+  const long long t_solve = clock64();
+#endif
   phase_solve(s, m, lane, cnt, true);
+#ifdef H_SOLVE_STATS
+  if (lane == 0) {     // analysis build (tools/solve_stats.py): solves, cycles and line-search evaluations by iteration count
+    const int it = min((int)cnt.newton, 15);
+    atomicAdd(&g_solve_stats[it], 1ull);
+    atomicAdd(&g_solve_stats[16 + it], (unsigned long long)(clock64() - t_solve));
+    atomicAdd(&g_solve_stats[32 + it], (unsigned long long)cnt.ls);
+  }
+#endif
   if (lane == 0) {
     misc[MI_C_SUBSTEPS] += (int)cnt.substeps; misc[MI_C_NCON] += (int)cnt.ncon; misc[MI_C_NEFC] += (int)cnt.nefc;
     misc[MI_C_NEWTON] += (int)cnt.newton; misc[MI_C_LS] += (int)cnt.ls;
@@ -118,3 +129,15 @@ cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t s
   K_P3<<<grid, 32 * P3_W, hoic_step_smem(P3_W, g_p3_pad < 0 ? 0 : g_p3_pad), stream>>>(B, sp, k);
   return cudaGetLastError();
 }
+
+#ifdef H_SOLVE_STATS
+#ifdef P3_SMALL
+extern "C" int hoic_debug_solve_stats_small(unsigned long long* out64, int reset) {
+#else
+extern "C" int hoic_debug_solve_stats_full(unsigned long long* out64, int reset) {
+#endif
+  if (cudaMemcpyFromSymbol(out64, g_solve_stats, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_solve_stats, z, sizeof z); }
+  return 0;
+}
+#endif
