@@ -60,6 +60,7 @@ class SamplerStep:
         self._graph = None
         self._use_graph = graph
         self._host = None
+        self._warm_done = self._host_warm_done = False
         # bf16 fast path: the normaliser writes a bfloat16 copy of the state (padded to the first layer's GEMM width) next to
         # the float32 one, the MLP runs on bfloat16 copies of the weights that are refreshed only when the parameters change
         # (torch.autocast re-casts every weight on every call: 9 cast / pad kernels per step), and the draw of the action is
@@ -171,8 +172,9 @@ class SamplerStep:
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(2):
+            for _ in range(0 if self._warm_done else 2):     # a recapture (env.graph_epoch changed) needs no warm-up steps
                 self._body()
+        self._warm_done = True
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
@@ -182,7 +184,18 @@ class SamplerStep:
         torch.cuda.synchronize(dev)
         self._graph = g
 
+    def _check_epoch(self):
+        """The env's mode / recording buffers / motion tables are kernel arguments baked into a captured graph: drop the
+        graphs when the env says one of them changed (HandMimicVecEnv.graph_epoch) and capture again on the next step."""
+        ep = getattr(self.env, "graph_epoch", 0)
+        if ep != getattr(self, "_epoch", ep):
+            self._graph = None
+            if self._host is not None:
+                self._host["graph"] = None
+        self._epoch = ep
+
     def step(self):
+        self._check_epoch()
         if self._fast:
             self._refresh_weights()
         if self._use_graph:
@@ -206,9 +219,10 @@ class SamplerStep:
         buffer) while the device works; `step_host_end()` waits for the transition."""
         if self.noise is None:
             raise capi.HoicError("construct SamplerStep(host_noise=True) for step_host")
+        self._check_epoch()
         if self._fast:
             self._refresh_weights()
-        if self._host is None:
+        if self._host is None or self._host["graph"] is None:
             self._build_host()
         h = self._host
         if noise_host.data_ptr() != h["noise"].data_ptr():
@@ -258,8 +272,9 @@ class SamplerStep:
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(2):
+            for _ in range(0 if self._host_warm_done else 2):
                 self._host_body()
+        self._host_warm_done = True
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()

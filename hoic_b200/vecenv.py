@@ -63,6 +63,7 @@ class HandMimicVecEnv:
         self.end = torch.zeros(N, dtype=torch.uint8, device=self.device)
         self._seed = int(seed)
         self._hs = None
+        self.graph_epoch = 0     # bumped whenever something a captured CUDA graph bakes in changes (mode, recording, tables)
         self._ep_mid = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._ep_start = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._ep_t = torch.zeros(N, dtype=torch.int32, device=self.device)
@@ -99,6 +100,7 @@ class HandMimicVecEnv:
         capi.check(self.L.hoic_set_sampler(self._hb, capi.ptr(offs_m), capi.ptr(ids), 1 if self.random_start else 0,
                                            int(self.min_episode), self._seed), "hoic_set_sampler")
         self._hs = None     # the table may have been reallocated: a captured host-step graph holds stale pointers
+        self.graph_epoch += 1
 
     def set_motion_frames(self, frames):
         """Replace the frames of ALL motions in place: `frames` [n_motions, T, 212] with the same n_motions / T as the
@@ -118,6 +120,7 @@ class HandMimicVecEnv:
     def set_mode(self, mode):
         capi.check(self.L.hoic_set_mode(self._hb, 1 if mode == "train" else 0), "hoic_set_mode")
         self._hs = None     # kernel arguments are baked into a captured graph: recapture
+        self.graph_epoch += 1
 
     @property
     def balance(self):
@@ -128,6 +131,7 @@ class HandMimicVecEnv:
         self._balance = bool(on)
         capi.check(self.L.hoic_set_balance(self._hb, 1 if on else 0), "hoic_set_balance")
         self._hs = None
+        self.graph_epoch += 1
 
     def set_record(self, on=True):
         """Test-mode recording of `MotionData` (ho_im4.py:27-41): with it on, every `step` also fills the per-substep
@@ -140,6 +144,7 @@ class HandMimicVecEnv:
             self._rec_frames = self._rec_surface = None
         capi.check(self.L.hoic_set_record(self._hb, capi.ptr(self._rec_frames), capi.ptr(self._rec_surface)), "hoic_set_record")
         self._hs = None
+        self.graph_epoch += 1
 
     def motion_data(self):
         """Record of the last `step` as a dict of device tensors named like the reference's `MotionData` lists; the

@@ -225,3 +225,38 @@ def test_sampler_fast_path_equals_the_autocast_path_and_host_step_returns_the_tr
         assert torch.equal(out["reward_info"], env.reward_info.cpu())
         assert torch.allclose(s.noise.cpu(), noise[k & 1])
     env.close()
+
+
+def test_sampler_graph_is_recaptured_when_the_env_changes_what_the_graph_bakes_in():
+    """set_mode / set_record / set_motions change kernel arguments (and may reallocate tables) that a captured sampler graph
+    holds by value: the sampler must drop its graph (HandMimicVecEnv.graph_epoch) instead of replaying stale arguments.
+    Train mode fails an env whose hand drifts from the expert (body_fail), test mode does not: after set_mode("test") the
+    replayed step must follow the test-mode rule."""
+    from hoic_b200 import ppo
+    from hoic_b200.sampler import SamplerStep
+    from hoic_b200.vecenv import HandMimicVecEnv
+    mdl = model("box")
+    dev = torch.device("cuda", 0)
+    pol, _ = ppo.make_policy_value(mdl.cfg, device=dev, dtype=torch.float32, seed=1)
+    with torch.no_grad():
+        pol.action_log_std.fill_(1.5)            # wild actions: body_fail fires within a few steps in train mode
+    env = HandMimicVecEnv(mdl, 64, [mdl.motion(s) for s in range(1, 9)], device=0, seed=3, auto_reset=True)
+    s = SamplerStep(env, pol, ppo.ZFilter((617,), clip=5.0, device=dev), torch.Generator(device=dev).manual_seed(1), policy_dtype="bf16", graph=True)
+    env.reset()
+    fails = 0
+    for _ in range(12):
+        s.step()
+        fails += int((env.fail & ~env.end.bool()).sum())
+    assert fails > 0
+    g0 = s._graph
+    env.set_mode("test")
+    env.set_record(True)
+    env.reset()
+    fails = 0
+    for _ in range(12):
+        s.step()
+        fails += int(env.fail.sum())
+    assert s._graph is not g0
+    assert fails == 0 or int(env.counters()["fail_physics"]) + int(env.counters()["fail_overflow"]) > 0
+    assert float(env._rec_frames.abs().sum()) > 0          # the recapture wrote into the new recording buffers
+    env.close()
