@@ -326,7 +326,7 @@ H_UNROLL(CHOL_TRAIL_UNROLL)
 // Scratch (in S_H): scaled rows L[k][d] = M'[k, a_k(d)] / D_k, pivots D, published solution entries, trunk block.
 #define T_MAXD 10
 #define T_HUBD 5     // depth of the hub dof when there is one (compile-time so that the block step is emitted once)
-#if H_KERNEL == HK_P1
+#if H_KERNEL == HK_P1 || H_KERNEL == HK_P12
 #define TS_LS (S_UNION + UN_TS)     // k_p1 holds no Hessian: the factor scratch follows the branch products in the union
 #else
 #define TS_LS (S_H)                 // 32 x MS_STRIDE scaled rows

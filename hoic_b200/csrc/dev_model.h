@@ -127,14 +127,15 @@ struct DevModel {
 #define UN_CON_OF(nc, nb, ne) ((nc) * 16 + (nb) * B_STRIDE + 6 * (H_RCON + (ne)) + 2 * (nb) + (nc) * 8 + (H_MAXCAND / 2 > (nb) ? H_MAXCAND / 2 : (nb)))
 // k_p2 builds the rows but never touches the solver's per-row work arrays (JAR, JV, FORCE, BV), which lie at the end
 #define UN_CON_BUILD_OF(nc, nb, ne) (UN_CON_OF(nc, nb, ne) - 3 * (H_RCON + (ne)) - (nb))
-#define UN_CON ((H_KERNEL) == HK_P2 ? UN_CON_BUILD_OF(H_NCON, H_NBASIS, H_NEDGE) : UN_CON_OF(H_NCON, H_NBASIS, H_NEDGE))
+#define HK_P12 (HK_P1 | HK_P2)  // fused kernel k_p12 (k_p12.cu): k_p1's and k_p2's work of a substep in one launch
+#define UN_CON ((H_KERNEL) == HK_P2 || (H_KERNEL) == HK_P12 ? UN_CON_BUILD_OF(H_NCON, H_NBASIS, H_NEDGE) : UN_CON_OF(H_NCON, H_NBASIS, H_NEDGE))
 #define UN_CON_G UN_CON_OF(HG_NCON, HG_NBASIS, HG_NEDGE)
 #define UN_QP (3168 - 384 - 576)       /* residual-force QP scratch starts at S_MS (QP_BASE) and runs over S_H into the union */
 #define UN_TS (32 * 21)                /* tree_solve's branch products (dev_math.cuh: TS_P) */
 #define UN_TSF 480                     /* tree_solve's factor scratch (TS_LS .. TS_T) when it lives in the union (k_p1) */
 #define S_MAX2(a, b) ((a) > (b) ? (a) : (b))
 #define HK_A (HK_P1 | HK_P3)   // fused kernel k_a (k_a.cu): Newton solve of substep k, then k_p1's work for substep k + 1
-#define UN_SIZE ((H_KERNEL) == HK_P1 ? S_MAX2(UN_POS, UN_TS + UN_TSF) : ((H_KERNEL) == HK_P2 || (H_KERNEL) == HK_P3) ? UN_CON : \
+#define UN_SIZE ((H_KERNEL) == HK_P1 ? S_MAX2(UN_POS, UN_TS + UN_TSF) : ((H_KERNEL) == HK_P2 || (H_KERNEL) == HK_P3 || (H_KERNEL) == HK_P12) ? UN_CON : \
                  (H_KERNEL) == HK_A ? S_MAX2(S_MAX2(UN_POS, UN_TS), UN_CON) : \
                  (H_KERNEL) == HK_TAIL ? S_MAX2(UN_QP, UN_TS) : S_MAX2(S_MAX2(UN_POS, UN_CON), S_MAX2(UN_QP, UN_TS)))
 #define UN_FULL S_MAX2(S_MAX2(UN_POS, UN_CON_G), S_MAX2(UN_QP, UN_TS))
@@ -175,12 +176,30 @@ enum {
 };
 struct HField { int size; unsigned use; };
 #define H_POISON (1 << 24)     // offset of a field the kernel's layout does not hold: any access faults
+#define P12_P1_FIELDS 1152     // k_p12: union floats of k_p1's own stages (max(UN_POS, UN_TS + UN_TSF)); its private fields follow
 __host__ __device__ constexpr int h_field_off(int f, unsigned kernel, int union_size) {
   const HField tab[FI_COUNT] = {
 #define X(name, size, use) {FI_##name == FI_UNION ? union_size : (size), (use)},
       H_FIELDS(X)
 #undef X
   };
+  if (kernel == HK_P12) {
+    // k_p12: the fields k_p2 reads are laid out first, then the union at k_p2's size; the fields only k_p1's half touches
+    // (dead once that half has stored its results) live INSIDE the union, behind the 1152 floats k_p1's own stages use
+    int common = 0, p1only = 0, off_common = 0, off_p1 = 0;
+    for (int i = 0; i < FI_COUNT; i++) {
+      if (i == FI_UNION) continue;
+      const bool c = (tab[i].use & HK_P2) != 0, q = !c && (tab[i].use & HK_P1) != 0;
+      if (i == f) { off_common = common; off_p1 = p1only; }
+      if (c) common += tab[i].size;
+      if (q) p1only += tab[i].size;
+    }
+    if (f >= FI_COUNT) return common + union_size;
+    if (f == FI_UNION) return common;
+    if (tab[f].use & HK_P2) return off_common;
+    if (tab[f].use & HK_P1) return common + P12_P1_FIELDS + off_p1;
+    return H_POISON;
+  }
   int o = 0;
   for (int i = 0; i < f && i < FI_COUNT; i++)
     if (tab[i].use & kernel) o += tab[i].size;

@@ -399,6 +399,7 @@ struct hoic_batch {
   // hoic_step runs the batch as `nparts` interleaved parts on internal streams (fork / join around the caller's stream)
   int nparts = 1;
   bool fuse = false;                     // solve + next substep's k_p1 in one launch (k_a.cu)
+  bool fuse12 = false;                   // k_p1 + k_p2 of a substep in one launch (k_p12.cu, HOIC_FUSE12=1)
   bool p1_wide = false;                  // k_p1 with four envs per CTA (large batches)
   int part_delay_ns = 0;                 // experiment: part 1 starts this much later than part 0 (HOIC_PART_DELAY_US)
   cudaStream_t part_stream[HOIC_MAX_PARTS] = {}, aux_stream[HOIC_MAX_PARTS] = {};   // aux: the solver's full-capacity tier
@@ -866,6 +867,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     b->fuse = false;
     b->part_delay_ns = 1000 * capi_env_int("HOIC_PART_DELAY_US", 0);
     b->p1_wide = capi_env_int("HOIC_P1_WIDE", n_envs >= 8192 ? 1 : 0) != 0;
+    b->fuse12 = capi_env_int("HOIC_FUSE12", 0) != 0 && !b->fuse;
     if (const char* e = getenv("HOIC_FUSE")) b->fuse = atoi(e) != 0;
     CUDA_OKP(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     CUDA_OKP(cudaEventCreateWithFlags(&b->ev_tail, cudaEventDisableTiming));
@@ -885,7 +887,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     static bool configured[64] = {false};
     if (!configured[device & 63]) {
       CUDA_OKP(hoic_configure_p1()); CUDA_OKP(hoic_configure_p2()); CUDA_OKP(hoic_configure_p3()); CUDA_OKP(hoic_configure_p3s()); CUDA_OKP(hoic_configure_tail());
-      CUDA_OKP(hoic_configure_a()); CUDA_OKP(hoic_configure_as()); CUDA_OKP(hoic_configure_p1w());
+      CUDA_OKP(hoic_configure_a()); CUDA_OKP(hoic_configure_as()); CUDA_OKP(hoic_configure_p1w()); CUDA_OKP(hoic_configure_p12());
       configured[device & 63] = true;
     }
   }
@@ -1112,12 +1114,18 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
     CUDA_OK(cudaEventRecord(b->ev_fork, user));
     for (int j = 0; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_fork, 0));
     if (b->part_delay_ns > 0 && np > 1) { k_delay<<<1, 1, 0, b->part_stream[1]>>>(b->part_delay_ns); LAUNCH_CHECK(); }
-    STEP_PARTS(0, b->p1_wide ? hoic_launch_p1w(b->b, sp, actions, -1, sm) : hoic_launch_p1(b->b, sp, actions, -1, sm));
-    STEP_PARTS(1, hoic_launch_p2(b->b, sp, -1, sm));
+    if (b->fuse12) STEP_PARTS(0, hoic_launch_p12(b->b, sp, actions, -1, sm));
+    else {
+      STEP_PARTS(0, b->p1_wide ? hoic_launch_p1w(b->b, sp, actions, -1, sm) : hoic_launch_p1(b->b, sp, actions, -1, sm));
+      STEP_PARTS(1, hoic_launch_p2(b->b, sp, -1, sm));
+    }
     for (int k = 0; k < b->nsub; k++) {
       // fused mode: k_p1 of substep k >= 1 ran inside the previous substep's solve launch (k_a.cu)
-      if (!(b->fuse && k > 0)) STEP_PARTS(0, b->p1_wide ? hoic_launch_p1w(b->b, sp, actions, k, sm) : hoic_launch_p1(b->b, sp, actions, k, sm));
-      STEP_PARTS(1, hoic_launch_p2(b->b, sp, k, sm));
+      if (b->fuse12) STEP_PARTS(0, hoic_launch_p12(b->b, sp, actions, k, sm));
+      else {
+        if (!(b->fuse && k > 0)) STEP_PARTS(0, b->p1_wide ? hoic_launch_p1w(b->b, sp, actions, k, sm) : hoic_launch_p1(b->b, sp, actions, k, sm));
+        STEP_PARTS(1, hoic_launch_p2(b->b, sp, k, sm));
+      }
       // the two capacity tiers of the solver take disjoint envs: side by side (the few long solves of the full tier would
       // otherwise sit on every substep's critical path)
       for (int j = 0; j < np; j++) {

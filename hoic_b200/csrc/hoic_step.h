@@ -17,6 +17,8 @@ cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t 
 // fused kernels (k_a.cu): Newton solve of substep k + k_p1's work of substep k + 1 in one launch, per capacity tier
 cudaError_t hoic_launch_a(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream);
 cudaError_t hoic_launch_as(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream);
+// fused k_p1 + k_p2 (k_p12.cu, opt-in experiment)
+cudaError_t hoic_launch_p12(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream);
 cudaError_t hoic_launch_tail(const BatchDev& B, StepPart sp, const float* actions, const StepOut& out, cudaStream_t stream);
 // shared-memory attributes of the four kernels on the current device (once per device)
 cudaError_t hoic_configure_p1();
@@ -25,5 +27,6 @@ cudaError_t hoic_configure_p2();
 cudaError_t hoic_configure_p3();
 cudaError_t hoic_configure_p3s();
 cudaError_t hoic_configure_tail();
+cudaError_t hoic_configure_p12();
 cudaError_t hoic_configure_a();
 cudaError_t hoic_configure_as();

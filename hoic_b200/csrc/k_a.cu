@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(32, KA_WPS) K_A(BatchDev B, StepPart sp, const
     ST_FIELD(MISC); ST_FIELD(QACC); ST_FIELD(FCON);
     return;
   }
-  p1_body<true>(B, es, env, s, g, st, m, misc, actions, k + 1, lane);
+  p1_body<true>(B, es, env, s, g, st, m, misc, actions, k + 1, lane, g + G_OFF(GPOS), g + G_OFF(GMAT));
 }
 
 static int g_ka_pad = -1;

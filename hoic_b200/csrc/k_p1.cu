@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) K_P1(BatchDev B, Ste
   const DevModel& m = *B.env_model[env];
   int* misc = (int*)(s + S_MISC);
   if (k >= m.sim_step) return;
-  p1_body<false>(B, es, env, s, g, st, m, misc, actions, k, lane);
+  p1_body<false>(B, es, env, s, g, st, m, misc, actions, k, lane, g + G_OFF(GPOS), g + G_OFF(GMAT));
 }
 
 static int g_p1_pad = -1;

@@ -8,22 +8,8 @@
 #define H_NBASIS P2_CAP_NBASIS
 #define H_NEDGE P2_CAP_NEDGE
 #endif
-#include "hoic_step.cuh"
+#include "p2_body.cuh"
 
-#ifndef P2_W
-#define P2_W 5
-#endif
-#ifndef P2_WPS
-#define P2_WPS 15
-#endif
-
-// P2_W > 1: the warps of a CTA start collision together and meet again before the constraint rows, so that they fetch the
-// same (large) code at the same time; the kernel is instruction-fetch bound otherwise (profiles/README.md, r02).
-#if P2_W > 1
-#define P2_SYNC() __syncthreads()
-#else
-#define P2_SYNC() do { } while (0)
-#endif
 __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, StepPart sp, int k) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -33,58 +19,7 @@ __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, Ste
   float* g = B.scratch + (size_t)env * G_TOTAL;
   const DevModel& m = *B.env_model[env];
   int* misc = (int*)(s + S_MISC);
-  LD_FIELD(MISC); LD_FIELD(ORG); LD_FIELD(GPOS); LD_FIELD(GMAT);
-  if (k >= 0) { LD_FIELD(QPOS); LD_FIELD(QVEL); LD_FIELD(COM); LD_FIELD(CDOF); }
-  ld_wait();
-  // work = this slot holds an env that is still running this step (k = -1: whose previous state had a forward)
-  // (k = -1 is skipped for an env whose working set was carried over from the previous step, see k_p1)
-  const bool work = es.live && k < m.sim_step && (k < 0 ? !(misc[MI_FLAGS] & 1) && !misc[MI_CARRIED] : !env_dead(misc));
-  float* csum = B.csum + (size_t)env * CSUM_STRIDE;
-  unsigned c0 = 0, c1 = 0;
-  P2_SYNC();
-  if (work) {
-    collide(s, m, lane, c0, c1);
-    if (k + 1 < m.sim_step) record_contacts(s, m, lane, csum);
-    else {
-      // the last forward's contacts are what the NEXT env.step records first (record_contact runs before sim.step(), S2)
-      float* carry = B.csum_carry + (size_t)env * CSUM_STRIDE;
-      for (int i = lane; i < CSUM_STRIDE; i += 32) carry[i] = 0.f;
-      __syncwarp();
-      record_contacts(s, m, lane, carry);
-    }
-    if (lane == 0) { misc[MI_C_MPRCALLS] += (int)c0; misc[MI_C_MPRITERS] += (int)c1; }
-  }
-  if (k < 0) {
-    if (!es.live || k >= m.sim_step || misc[MI_CARRIED]) return;
-    if (work) {
-      // snapshot of the geom poses for the averaged velocities (ho_im4.py:508-511)
-      float* og = B.old_geom + (size_t)env * (HN * 12 + 4);
-      for (int i = lane; i < m.ngeom * 3; i += 32) og[i] = s[S_GPOS + i];
-      for (int i = lane; i < m.ngeom * 9; i += 32) og[HN * 3 + i] = s[S_GMAT + i];
-      if (lane < 3) og[HN * 12 + lane] = s[S_ORG + lane];
-    }
-    __syncwarp();
-    if (lane == 0) misc[MI_FLAGS] = 0;     // a bad stale state was reported by the previous step already
-    __syncwarp();
-    ST_FIELD(MISC);
-    return;
-  }
-#ifndef P2_NO_MIDSYNC
-  P2_SYNC();
-#endif
-  if (!work) return;
-  build_rows(s, m, lane);
-  if (B.rec_frames) record_contact_frames(s, m, lane, B.rec_frames + ((size_t)env * m.sim_step + k) * HOIC_REC_STRIDE);
-  __syncwarp();
-  // the used part of the constraint stage -> global working set (input of the Newton solve)
-  const int nc = misc[MI_NCON], nb = misc[MI_NBASIS], nrow = H_RCON + ((misc[MI_NEDGE] + 31) & ~31);
-  if (lane == 0 && B.full_list && !(nc <= P3S_NCON && nb <= P3S_NBASIS && misc[MI_NEDGE] <= P3S_NEDGE) && !env_dead(misc))
-    B.full_list[(size_t)sp.part * B.n_envs + atomicAdd(B.full_count + sp.part * FULL_COUNT_STRIDE + k, 1)] = env;
-  ST_FIELD(MISC);
-  ST_U(B, nb * B_STRIDE);
-  ST_U(AREF, nrow); ST_U(D, nrow); ST_U(RINFO, nrow);
-  ST_U(BMASK, nb); ST_U(MPRQ, nb); ST_U(CINFO, nc * 8);      // (U_BINFO lives in the MPR queue's slots)
-  if (B.rec_frames) ST_U(CON, nc * 16);
+  p2_body<false>(B, sp, es, env, s, g, m, misc, k, lane);
 }
 
 static int g_p2_pad = -1;

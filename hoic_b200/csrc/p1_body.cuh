@@ -6,9 +6,13 @@
 #pragma once
 #include "hoic_step.cuh"
 
+// gpos_out / gmat_out: where mj_kinematics writes the geom poses (k_p1 / k_a: straight into the global working set; k_p12: its
+// shared-memory fields, which k_p2's half reads).  Returns true when the forward of this launch ran (the poses are valid).
 template <bool FUSED>
-__device__ __forceinline__ void p1_body(const BatchDev& B, const EnvSlot es, const int env, float* s, float* g, float* st, const DevModel& m,
-                                        int* misc, const float* __restrict__ actions, const int k, const int lane) {
+__device__ __forceinline__ bool p1_body(const BatchDev& B, const EnvSlot es, const int env, float* s, float* g, float* st, const DevModel& m,
+                                        int* misc, const float* __restrict__ actions, const int k, const int lane, float* gpos_out,
+                                        float* gmat_out) {
+  bool fwd = false;
   bool ok = es.live;
   float* recf = (B.rec_frames && es.live) ? B.rec_frames + (size_t)env * m.sim_step * HOIC_REC_STRIDE : nullptr;
   if (!FUSED && k < 0) {
@@ -39,7 +43,7 @@ __device__ __forceinline__ void p1_body(const BatchDev& B, const EnvSlot es, con
       for (int i = lane; i < H_NQ; i += 32) g[G_OFF(QPOS) + i] = i < 33 ? st[ST_QPOS + i] : 0.f;
       g[G_OFF(QVEL) + lane] = st[ST_QVEL + lane];
       g[G_OFF(WARM) + lane] = st[ST_WARM + lane];
-      return;
+      return false;
     }
     load_state(s, st, lane, ST_PQPOS, ST_PQVEL);
     __syncwarp();
@@ -57,7 +61,7 @@ __device__ __forceinline__ void p1_body(const BatchDev& B, const EnvSlot es, con
       s[S_ACT + lane] = fminf(fmaxf(a, -1.f), 1.f);
     }
     ld_wait();
-    if (!ok || env_dead(misc)) return;    // failed earlier in this step: the working set stays as it was
+    if (!ok || env_dead(misc)) return false;    // failed earlier in this step: the working set stays as it was
   }
   const V3 vf = (k >= 0 && m.residual_force) ? ld3(s + S_ACT + m.nu) * m.rf_scale : v3(0, 0, 0);
   const V3 vt = (k >= 0 && m.residual_force) ? ld3(s + S_ACT + m.nu + 3) * m.rt_scale : v3(0, 0, 0);
@@ -93,14 +97,14 @@ __device__ __forceinline__ void p1_body(const BatchDev& B, const EnvSlot es, con
     __syncwarp();
     if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
   }
-  if (ok) ok = phase_forward(s, m, lane, g + G_OFF(GPOS), g + G_OFF(GMAT)) || k < 0;   // a bad stale state was reported by the previous step already
+  if (ok) { fwd = phase_forward(s, m, lane, gpos_out, gmat_out); ok = fwd || k < 0; }   // a bad stale state was reported by the previous step already
   if (ok) vel_stage(s, m, lane);
   if (ok && k >= 0) {
     ok = phase_smooth(s, m, lane);
     if (!ok && lane == 0) misc[MI_FLAGS] |= 1;
   }
   __syncwarp();
-  if (!es.live) return;
+  if (!es.live) return false;
   ST_FIELD(MISC);
   if (k < 0) {
     // scratch carries the CURRENT state into substep 0; the stale forward's derived quantities stay
@@ -112,4 +116,5 @@ __device__ __forceinline__ void p1_body(const BatchDev& B, const EnvSlot es, con
   }
   ST_FIELD(ORG); ST_FIELD(COM); ST_FIELD(CDOF); ST_FIELD(BIAS); ST_FIELD(MS);
   ST_FIELD(XPOS); ST_FIELD(XQUAT);   // read by the step tail (poses of the last forward) and by the test-mode record
+  return fwd;
 }

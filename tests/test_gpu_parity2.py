@@ -309,9 +309,11 @@ def test_sdf_penetration_metric():
     assert pm2.eval_contact_point().max() >= 1
 
 
-def test_fused_solve_and_smooth_dynamics_kernel_equals_the_separate_kernels():
-    """HOIC_FUSE=1 (k_a.cu: Newton solve of substep k + k_p1's work of substep k + 1 in one launch; opt-in, measured slower)
-    must reproduce the default pipeline bit for bit: box and banana, auto-reset on, test-mode recording on."""
+@pytest.mark.parametrize("knob", ["HOIC_FUSE", "HOIC_FUSE12"])
+def test_fused_kernels_equal_the_separate_kernels(knob):
+    """The opt-in fused kernels -- HOIC_FUSE=1 (k_a.cu: Newton solve of substep k + k_p1's work of substep k + 1 in one launch)
+    and HOIC_FUSE12=1 (k_p12.cu: k_p1 + k_p2 of a substep in one launch) -- must reproduce the default pipeline bit for bit:
+    box and banana, auto-reset on, test-mode recording on."""
     import os
     import torch
     from hoic_b200.vecenv import HandMimicVecEnv
@@ -319,11 +321,11 @@ def test_fused_solve_and_smooth_dynamics_kernel_equals_the_separate_kernels():
         mdl = model(obj)
         outs = []
         for fuse in ("0", "1"):
-            os.environ["HOIC_FUSE"] = fuse
+            os.environ[knob] = fuse
             try:
                 env = HandMimicVecEnv(mdl, 160, [mdl.motion(s) for s in range(1, 9)], device=0, seed=5, auto_reset=True)
             finally:
-                os.environ.pop("HOIC_FUSE", None)
+                os.environ.pop(knob, None)
             env.set_record(True)
             env.reset()
             g = torch.Generator(device="cuda").manual_seed(3)
