@@ -363,7 +363,9 @@ def run_ours(args):
     launches_per_step = kt["launches_per_hoic_step"] + 5       # + k_zf_moments, k_zf_apply16, k_sample_action, k_get_episode, k_logger
 
     # ---- e2e: host-resident sampler (noise H2D, transition D2H, one graph launch + stream sync per step)
-    h_noise = [torch.randn(N, 32).pin_memory(), torch.randn(N, 32).pin_memory()]
+    h_noise = host_sampler.host_noise_buffers()       # the sampler's two pinned staging buffers: the host RNG draws straight into them
+    for b in h_noise:
+        b.normal_()
     for _ in range(3):
         host_sampler.step_host(h_noise[0])
     if world > 1:

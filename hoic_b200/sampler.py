@@ -225,19 +225,33 @@ class SamplerStep:
         if self._host is None or self._host["graph"] is None:
             self._build_host()
         h = self._host
-        if noise_host.data_ptr() != h["noise"].data_ptr():
-            h["noise"].copy_(noise_host)
-        h["graph"].replay()
+        ptrs = [b.data_ptr() for b in h["noise"]]
+        if noise_host.data_ptr() in ptrs:
+            idx = ptrs.index(noise_host.data_ptr())      # one of the sampler's own staging buffers: no host copy
+        else:
+            idx = 0
+            h["noise"][0].copy_(noise_host)
+        h["graph"][idx].replay()
+
+    def host_noise_buffers(self):
+        """The two pinned [N, act_dim] staging buffers of the host-resident step (each has its own captured graph): a caller
+        that draws its noise straight into them, alternating, saves the host-side copy of `step_host_begin`."""
+        if self.noise is None:
+            raise capi.HoicError("construct SamplerStep(host_noise=True) for step_host")
+        if self._host is None or self._host["graph"] is None:
+            self._check_epoch()
+            self._build_host()
+        return self._host["noise"]
 
     def step_host_end(self):
         torch.cuda.current_stream(self.env.device).synchronize()
         return self._host["out"]
 
-    def _host_body(self):
+    def _host_body(self, idx=0):
         h = self._host
         env = self.env
         dev = env.device
-        self.noise.copy_(h["noise"], non_blocking=True)
+        self.noise.copy_(h["noise"][idx], non_blocking=True)
         main = torch.cuda.current_stream(dev)
 
         def early():
@@ -263,9 +277,12 @@ class SamplerStep:
         out = dict(state=pin(N, env.obs_dim), action=pin(N, env.act_dim), exp=pin(N), reward=pin(N), percent=pin(N),
                    reward_info=pin(N, capi.INFO_DIM), done=pin(N, dtype=torch.uint8), end=pin(N, dtype=torch.uint8),
                    fail=pin(N, dtype=torch.uint8))
-        self._host = dict(noise=pin(N, env.act_dim), out=out, graph=None, side=torch.cuda.Stream(env.device),
-                          ev0=torch.cuda.Event(), ev1=torch.cuda.Event())
-        self._host["noise"].zero_()
+        keep = self._host["noise"] if self._host is not None else None      # a recapture keeps the buffers callers may hold
+        self._host = dict(noise=keep or [pin(N, env.act_dim), pin(N, env.act_dim)], out=out, graph=None,
+                          side=torch.cuda.Stream(env.device), ev0=torch.cuda.Event(), ev1=torch.cuda.Event())
+        if keep is None:
+            for b in self._host["noise"]:
+                b.zero_()
         self.h2d_bytes = N * env.act_dim * 4
         self.d2h_bytes = sum(v.numel() * v.element_size() for v in out.values())
         dev = env.device
@@ -277,9 +294,12 @@ class SamplerStep:
         self._host_warm_done = True
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        g.register_generator_state(self.gen)
-        with torch.cuda.graph(g, stream=side):
-            self._host_body()
-        torch.cuda.synchronize(dev)
-        self._host["graph"] = g
+        graphs = []
+        for idx in range(2):       # one graph per staging buffer (the H2D copy node reads a fixed host address)
+            g = torch.cuda.CUDAGraph()
+            g.register_generator_state(self.gen)
+            with torch.cuda.graph(g, stream=side):
+                self._host_body(idx)
+            torch.cuda.synchronize(dev)
+            graphs.append(g)
+        self._host["graph"] = graphs

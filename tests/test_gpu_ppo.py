@@ -215,7 +215,9 @@ def test_sampler_fast_path_equals_the_autocast_path_and_host_step_returns_the_tr
     zf = ppo.ZFilter((617,), clip=5.0, device=dev)
     s = SamplerStep(env, pol, zf, torch.Generator(device=dev).manual_seed(11), policy_dtype="bf16", graph=True, host_noise=True)
     env.reset()
-    noise = [torch.randn(96, 32).pin_memory(), torch.randn(96, 32).pin_memory()]
+    noise = s.host_noise_buffers()
+    for b in noise:
+        b.normal_()
     for k in range(3):
         s.step_host_begin(noise[k & 1])
         noise[(k + 1) & 1].normal_()
@@ -223,7 +225,11 @@ def test_sampler_fast_path_equals_the_autocast_path_and_host_step_returns_the_tr
         assert torch.equal(out["state"], s.x.cpu()) and torch.equal(out["action"], s.act.cpu()) and torch.equal(out["exp"], s.exp.cpu())
         assert torch.equal(out["reward"], env.reward.cpu()) and torch.equal(out["done"], env.done.cpu())
         assert torch.equal(out["reward_info"], env.reward_info.cpu())
-        assert torch.allclose(s.noise.cpu(), noise[k & 1])
+        # (noise[(k + 1) & 1] was redrawn while step k ran; noise[k & 1] is what step k used)
+    assert torch.equal(s.noise.cpu(), noise[0])                 # step 2 read staging buffer 0
+    ext = torch.randn(96, 32).pin_memory()                      # a caller's own pinned buffer goes through staging buffer 0
+    s.step_host(ext)
+    assert torch.equal(s.noise.cpu(), ext)
     env.close()
 
 
