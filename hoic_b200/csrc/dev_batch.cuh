@@ -42,10 +42,17 @@ struct BatchDev {
   int* full_list;                     // [nparts][N]
   int* full_count;                    // [nparts][FULL_COUNT_STRIDE], entry k = substep, zeroed at the start of a step
   // envs whose episode ended in the running step (appended by k_tail): the auto-reset launch covers only those
+  // "carry" mode of hoic_step: a capped k_p3s leaves the few long solves open; k_p3c finishes them on another stream while k_p1 /
+  // k_p2 of the next substep already run for everybody else, then k_p1 / k_p2 run for the carried envs alone (short launches)
+  int* carry_list;                    // [nparts][N] envs whose solve of the running substep is open (appended by k_p3s)
+  int* carry_count;                   // [nparts][FULL_COUNT_STRIDE], behind reset_count's block
+  int* late_stamp;                    // [N] substep + 1 of the last solve this env was carried / full-tier in (0 after the step's memset)
+  int solve_budget;                   // Newton iterations of the capped launch (0: carry mode off)
   int* reset_list;                    // [N]
   int* reset_count;                   // one counter behind full_count's block (same memset)
 };
 #define FULL_COUNT_STRIDE 32
+#define HOIC_LIST_PARTS 8            // = HOIC_MAX_PARTS of hoic_capi.cu
 
 struct StepOut {
   float* obs; float* reward; float* info; uint8_t* done; uint8_t* fail; uint8_t* end; float* percent;
@@ -77,19 +84,24 @@ static __device__ __noinline__ bool phase_smooth(float* s, const DevModel& m, in
   return ok;
 }
 // Every warp of the CTA calls this (active = false: only the CTA barriers inside the solver are taken).
-static __device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int lane, Cnt& cnt, bool active) {
+// budget / resume / open_out: see solve_newton (a solve split over a capped launch and its continuation); the per-substep counters
+// are taken by the launch that STARTS the solve.
+static __device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int lane, Cnt& cnt, bool active, int budget = 0, bool resume = false,
+                                                bool* open_out = nullptr) {
   int* misc = (int*)(s + S_MISC);
   unsigned it = 0;
-  bool fail = !solve_newton(s, m, lane, active, it, cnt.ls);
+  bool fail = !solve_newton(s, m, lane, active, it, cnt.ls, budget, resume, open_out);
   if (!active) return false;
   cnt.newton += it;
-  cnt.substeps++;
-  cnt.ncon += misc[MI_NCON];
-  cnt.nefc += m.nv + misc[MI_NLIM] + misc[MI_NEDGE];
-  cnt.max_ncon = max(cnt.max_ncon, (unsigned)misc[MI_NCON]);
-  cnt.max_nbasis = max(cnt.max_nbasis, (unsigned)misc[MI_NBASIS]);
-  cnt.max_nedge = max(cnt.max_nedge, (unsigned)misc[MI_NEDGE]);
-  if (lane == 0) misc[MI_ITER] = (int)it;
+  if (!resume) {
+    cnt.substeps++;
+    cnt.ncon += misc[MI_NCON];
+    cnt.nefc += m.nv + misc[MI_NLIM] + misc[MI_NEDGE];
+    cnt.max_ncon = max(cnt.max_ncon, (unsigned)misc[MI_NCON]);
+    cnt.max_nbasis = max(cnt.max_nbasis, (unsigned)misc[MI_NBASIS]);
+    cnt.max_nedge = max(cnt.max_nedge, (unsigned)misc[MI_NEDGE]);
+  }
+  if (lane == 0) misc[MI_ITER] = (int)it + (resume ? misc[MI_ITER] : 0);
   fail = __any_sync(FULLMASK, fail || bad(s[S_QACC + lane]));
   if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   return !(misc[MI_FLAGS] & 2);   // capacity overflow: treated like MuJoCo's nconmax / njmax warnings

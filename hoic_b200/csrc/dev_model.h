@@ -319,6 +319,11 @@ static_assert(UN_POS == 1120 && (UN_CON % 4) == 0 && (H_NBASIS * B_STRIDE) % 4 =
 #define MI_C_FAILPHYS 18
 #define MI_C_FAILOVER 19
 #define MI_CARRIED 20    // this step started from the working set the previous step left (no pass -1 recomputation)
+// a Newton solve that a capped launch left open (k_p3s with an iteration budget, continued by k_p3c; hoic_step "carry" mode)
+#define MI_SV_OPEN 21    // 1: the solve of this substep is open, QACC / MA / JAR in the working set hold its state
+#define MI_SV_ITER 22    // iterations done so far
+#define MI_SV_COST 23    // float bits: cost, cost before the last move
+#define MI_SV_OLDCOST 24
 
 // per-env persistent state in global memory (floats), AoS so that a warp reads it coalesced
 #define ST_QPOS 0

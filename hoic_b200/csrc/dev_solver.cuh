@@ -584,8 +584,13 @@ static __device__ __noinline__ int newton_move(float* s, const DevModel& m, int 
 #define NEWTON_ANY(run) (run)
 #define NEWTON_SYNC() do { } while (0)
 #endif
-__device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int lane, bool active, unsigned& iters_out, unsigned& ls_evals) {
-  const int* misc = (const int*)(s + S_MISC);
+// `budget` > 0: at most that many iterations in this call; a solve that is still running then is left OPEN: S_QACC, S_MA, U_JAR and
+// MISC[MI_SV_*] hold its state (the caller stores them) and `open_out` is set.  `resume`: continue such a solve (the caller loaded
+// S_QACC, S_MA, U_JAR; the row forces are recomputed from U_JAR, which reproduces them bit for bit), so that a solve split over two
+// launches performs exactly the arithmetic of an unsplit one.
+__device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int lane, bool active, unsigned& iters_out, unsigned& ls_evals,
+                                             int budget = 0, bool resume = false, bool* open_out = nullptr) {
+  int* misc = (int*)(s + S_MISC);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON], nbasis = misc[MI_NBASIS], nedge = misc[MI_NEDGE];
   const float scale = 1.0f / (m.meaninertia * (float)(m.nv > 1 ? m.nv : 1));
   bool run = active, ok = true;
@@ -594,7 +599,13 @@ __device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int la
 #ifdef H_SOLVE_STATS
   long long sst_t = clock64();
 #endif
-  if (run) { cost = newton_init(s, m, lane, nbasis, nedge); oldcost = cost; }
+  if (run && resume) {
+    iter = (unsigned)misc[MI_SV_ITER];
+    cost = __int_as_float(misc[MI_SV_COST]);
+    oldcost = __int_as_float(misc[MI_SV_OLDCOST]);
+    rows_update(s, m, lane, nedge, s + U_JAR, true);      // U_FORCE of the saved point
+  } else if (run) { cost = newton_init(s, m, lane, nbasis, nedge); oldcost = cost; }
+  const unsigned iter0 = iter;
   SST(0);   // init
   for (;;) {
     if (run) {
@@ -607,6 +618,17 @@ __device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int la
         if (improvement < tol || gradn < m.tolerance) run = false;
       }
       if (iter >= (unsigned)m.iterations) run = false;
+      if (run && budget > 0 && iter - iter0 >= (unsigned)budget) {
+        // out of budget with the solve still running: leave it open at the top of an iteration (gradient of this point is cheap
+        // to redo; cost / oldcost / iter are what the termination test of the continuation needs)
+        if (lane == 0) {
+          misc[MI_SV_OPEN] = 1; misc[MI_SV_ITER] = (int)iter;
+          misc[MI_SV_COST] = __float_as_int(cost); misc[MI_SV_OLDCOST] = __float_as_int(oldcost);
+        }
+        __syncwarp();
+        if (open_out) *open_out = true;
+        run = false;
+      }
 #ifdef NEWTON_CAP      // timing experiment only (what the long solves cost): stop after NEWTON_CAP iterations, converged or not
       if (iter >= NEWTON_CAP) run = false;
 #endif
@@ -637,7 +659,7 @@ __device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int la
       }
     }
   }
-  iters_out += iter;
+  iters_out += iter - iter0;
   // S_FCON holds J^T f of the final forces (written by newton_gradient)
   return ok;
 }

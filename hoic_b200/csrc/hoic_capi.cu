@@ -374,7 +374,8 @@ struct hoic_model {
 };
 
 #define HOIC_MAX_PARTS 8
-#define HOIC_COUNT_INTS (HOIC_MAX_PARTS * FULL_COUNT_STRIDE + 32)   // full-tier counters per (part, substep) + the reset counter
+static_assert(HOIC_MAX_PARTS == HOIC_LIST_PARTS, "dev_batch.cuh: HOIC_LIST_PARTS");
+#define HOIC_COUNT_INTS (2 * HOIC_MAX_PARTS * FULL_COUNT_STRIDE + 32)   // full-tier and carry counters per (part, substep) + the reset counter
 #define HOIC_TIMING_CLASSES 8          // k_p1, k_p2, k_p3s, k_p3, k_tail, k_reset, k_order, whole call
 static int capi_env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 struct hoic_batch {
@@ -403,6 +404,8 @@ struct hoic_batch {
   bool p1_wide = false;                  // k_p1 with four envs per CTA (large batches)
   int part_delay_ns = 0;                 // experiment: part 1 starts this much later than part 0 (HOIC_PART_DELAY_US)
   cudaStream_t part_stream[HOIC_MAX_PARTS] = {}, aux_stream[HOIC_MAX_PARTS] = {};   // aux: the solver's full-capacity tier
+  cudaStream_t carry_stream[HOIC_MAX_PARTS] = {};                                    // carry mode: the late group of every substep
+  cudaEvent_t ev_p3s[HOIC_MAX_PARTS] = {}, ev_carry[HOIC_MAX_PARTS] = {};
   bool order_valid = false;              // b->order holds the env order the previous hoic_step computed for this one
   cudaEvent_t ev_tail = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join[HOIC_MAX_PARTS] = {}, ev_rows[HOIC_MAX_PARTS] = {}, ev_aux[HOIC_MAX_PARTS] = {};
@@ -837,11 +840,16 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   CUDA_OKP(cudaMalloc(&b->b.csum, (size_t)n_envs * CSUM_STRIDE * sizeof(float)));
   CUDA_OKP(cudaMalloc(&b->b.csum_carry, (size_t)n_envs * CSUM_STRIDE * sizeof(float)));
   if (capi_env_int("HOIC_FULL_LIST", 1)) {
-    CUDA_OKP(cudaMalloc(&b->b.full_list, (size_t)HOIC_MAX_PARTS * n_envs * sizeof(int)));
+    CUDA_OKP(cudaMalloc(&b->b.full_list, (size_t)2 * HOIC_MAX_PARTS * n_envs * sizeof(int)));
+    CUDA_OKP(cudaMalloc(&b->b.carry_list, (size_t)HOIC_MAX_PARTS * n_envs * sizeof(int)));
+    CUDA_OKP(cudaMalloc(&b->b.late_stamp, (size_t)n_envs * sizeof(int)));
+    CUDA_OKP(cudaMemset(b->b.late_stamp, 0, (size_t)n_envs * sizeof(int)));
+    b->b.solve_budget = capi_env_int("HOIC_SOLVE_BUDGET", 0);
     CUDA_OKP(cudaMalloc(&b->b.full_count, (size_t)HOIC_COUNT_INTS * sizeof(int)));
     CUDA_OKP(cudaMemset(b->b.full_count, 0, (size_t)HOIC_COUNT_INTS * sizeof(int)));
     CUDA_OKP(cudaMalloc(&b->b.reset_list, (size_t)n_envs * sizeof(int)));
-    b->b.reset_count = b->b.full_count + HOIC_MAX_PARTS * FULL_COUNT_STRIDE;
+    b->b.carry_count = b->b.full_count + HOIC_MAX_PARTS * FULL_COUNT_STRIDE;
+    b->b.reset_count = b->b.full_count + 2 * HOIC_MAX_PARTS * FULL_COUNT_STRIDE;
   }
   CUDA_OKP(cudaMalloc(&b->b.counters, 16 * sizeof(unsigned long long)));
   CUDA_OKP(cudaMemset(b->b.counters, 0, 16 * sizeof(unsigned long long)));
@@ -867,8 +875,9 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     b->fuse = false;
     b->part_delay_ns = 1000 * capi_env_int("HOIC_PART_DELAY_US", 0);
     b->p1_wide = capi_env_int("HOIC_P1_WIDE", n_envs >= 8192 ? 1 : 0) != 0;
-    b->fuse12 = capi_env_int("HOIC_FUSE12", 0) != 0 && !b->fuse;
     if (const char* e = getenv("HOIC_FUSE")) b->fuse = atoi(e) != 0;
+    b->fuse12 = capi_env_int("HOIC_FUSE12", 0) != 0 && !b->fuse;
+    if (b->fuse || b->fuse12 || !b->b.full_list) b->b.solve_budget = 0;      // carry mode needs the separate kernels and the env lists
     CUDA_OKP(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     CUDA_OKP(cudaEventCreateWithFlags(&b->ev_tail, cudaEventDisableTiming));
     for (int j = 0; j < b->nparts; j++) {
@@ -878,6 +887,11 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
       const int pp = j == 1 ? capi_env_int("HOIC_PRIO_PART1", 0) : 0, pa = capi_env_int("HOIC_PRIO_AUX", 0);
       CUDA_OKP(cudaStreamCreateWithPriority(&b->part_stream[j], cudaStreamNonBlocking, std::max(hi, std::min(lo, pp))));
       CUDA_OKP(cudaStreamCreateWithPriority(&b->aux_stream[j], cudaStreamNonBlocking, std::max(hi, std::min(lo, pa))));
+      // the carry stream runs the few late envs' short launches, which sit on the critical path: most urgent priority by default
+      const int pc = capi_env_int("HOIC_PRIO_CARRY", -100);
+      CUDA_OKP(cudaStreamCreateWithPriority(&b->carry_stream[j], cudaStreamNonBlocking, std::max(hi, std::min(lo, pc))));
+      CUDA_OKP(cudaEventCreateWithFlags(&b->ev_p3s[j], cudaEventDisableTiming));
+      CUDA_OKP(cudaEventCreateWithFlags(&b->ev_carry[j], cudaEventDisableTiming));
       CUDA_OKP(cudaEventCreateWithFlags(&b->ev_join[j], cudaEventDisableTiming));
       CUDA_OKP(cudaEventCreateWithFlags(&b->ev_rows[j], cudaEventDisableTiming));
       CUDA_OKP(cudaEventCreateWithFlags(&b->ev_aux[j], cudaEventDisableTiming));
@@ -886,7 +900,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   {
     static bool configured[64] = {false};
     if (!configured[device & 63]) {
-      CUDA_OKP(hoic_configure_p1()); CUDA_OKP(hoic_configure_p2()); CUDA_OKP(hoic_configure_p3()); CUDA_OKP(hoic_configure_p3s()); CUDA_OKP(hoic_configure_tail());
+      CUDA_OKP(hoic_configure_p1()); CUDA_OKP(hoic_configure_p2()); CUDA_OKP(hoic_configure_p3()); CUDA_OKP(hoic_configure_p3s()); CUDA_OKP(hoic_configure_p3c()); CUDA_OKP(hoic_configure_tail());
       CUDA_OKP(hoic_configure_a()); CUDA_OKP(hoic_configure_as()); CUDA_OKP(hoic_configure_p1w()); CUDA_OKP(hoic_configure_p12());
       configured[device & 63] = true;
     }
@@ -906,13 +920,16 @@ extern "C" void hoic_batch_destroy(hoic_batch* b) {
   if (b->ev_tail) cudaEventDestroy(b->ev_tail);
   for (int j = 0; j < HOIC_MAX_PARTS; j++) {
     if (b->ev_join[j]) cudaEventDestroy(b->ev_join[j]);
+    if (b->ev_p3s[j]) cudaEventDestroy(b->ev_p3s[j]);
+    if (b->ev_carry[j]) cudaEventDestroy(b->ev_carry[j]);
+    if (b->carry_stream[j]) cudaStreamDestroy(b->carry_stream[j]);
     if (b->ev_rows[j]) cudaEventDestroy(b->ev_rows[j]);
     if (b->ev_aux[j]) cudaEventDestroy(b->ev_aux[j]);
     if (b->part_stream[j]) cudaStreamDestroy(b->part_stream[j]);
     if (b->aux_stream[j]) cudaStreamDestroy(b->aux_stream[j]);
   }
   cudaFree(b->env_model_dev); cudaFree(b->b.scratch); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum); cudaFree(b->b.csum_carry);
-  cudaFree(b->b.full_list); cudaFree(b->b.full_count); cudaFree(b->b.reset_list);
+  cudaFree(b->b.full_list); cudaFree(b->b.full_count); cudaFree(b->b.reset_list); cudaFree(b->b.carry_list); cudaFree(b->b.late_stamp);
   cudaFree(b->env_model_idx); cudaFree(b->samp_off); cudaFree(b->samp_ids); cudaFree(b->order);
   cudaFree(b->reward_w); cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
   delete b;
@@ -1110,6 +1127,7 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
       b->b.perm = b->order;
     } else b->b.perm = nullptr;
     if (b->b.full_count) CUDA_OK(cudaMemsetAsync(b->b.full_count, 0, (size_t)HOIC_COUNT_INTS * sizeof(int), user));
+    if (b->b.solve_budget > 0) CUDA_OK(cudaMemsetAsync(b->b.late_stamp, 0, (size_t)b->n_envs * sizeof(int), user));
     // fork: every part runs on its own stream; the caller's stream waits for all of them at the end
     CUDA_OK(cudaEventRecord(b->ev_fork, user));
     for (int j = 0; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_fork, 0));
@@ -1119,7 +1137,46 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
       STEP_PARTS(0, b->p1_wide ? hoic_launch_p1w(b->b, sp, actions, -1, sm) : hoic_launch_p1(b->b, sp, actions, -1, sm));
       STEP_PARTS(1, hoic_launch_p2(b->b, sp, -1, sm));
     }
-    for (int k = 0; k < b->nsub; k++) {
+    const bool carry = b->b.solve_budget > 0 && !b->fuse && !b->fuse12;
+    for (int k = 0; carry && k < b->nsub; k++) {
+      // Carry mode (opt-in experiment, HOIC_SOLVE_BUDGET=n; bit-identical results).  A launch of the solver lasts as long as its
+      // slowest solve (7-8 Newton iterations in SOME env of the part, every substep), and k_p1 / k_p2 of the next substep wait for
+      // it.  Here k_p3s stops after `solve_budget` iterations; the few solves that are still open (and the full tier's envs) are
+      // finished on the carry stream while k_p1 / k_p2 of substep k + 1 already run for everybody else (group 1), followed by
+      // k_p1 / k_p2 for those few (group 2).  MEASURED SLOWER (box, 4 096 envs, budget 3 / 4 / 6: 4.88 / 4.67 / 4.48 vs 4.29 ms per
+      // step): the late group's chain -- the straggler's own solve, now split, + its own k_p1 + k_p2 + three more launches -- is as
+      // long as the lock-step chain it replaces, because the same env is rarely the straggler twice in a row and every substep
+      // still joins.  What the split solver and the list-mode kernels are for is a schedule without that join.
+      auto p1 = [&](const StepPart& sp, int kk, cudaStream_t sm) {
+        return b->p1_wide ? hoic_launch_p1w(b->b, sp, actions, kk, sm) : hoic_launch_p1(b->b, sp, actions, kk, sm);
+      };
+      for (int j = 0; j < np; j++) {
+        const StepPart all = {j, np, 0}, early = {j, np, 1}, late = {j, np, 2};
+        cudaStream_t S = b->part_stream[j], X = b->aux_stream[j], Y = b->carry_stream[j];
+        if (k == 0) {
+          STEP_LAUNCH(0, S, p1(all, 0, S));
+          STEP_LAUNCH(1, S, hoic_launch_p2(b->b, all, 0, S));
+        } else CUDA_OK(cudaStreamWaitEvent(S, b->ev_carry[j], 0));          // the late group's rows of substep k
+        CUDA_OK(cudaEventRecord(b->ev_rows[j], S));
+        CUDA_OK(cudaStreamWaitEvent(X, b->ev_rows[j], 0));
+        STEP_LAUNCH(3, X, hoic_launch_p3(b->b, all, k, X));
+        CUDA_OK(cudaEventRecord(b->ev_aux[j], X));
+        STEP_LAUNCH(2, S, hoic_launch_p3s(b->b, all, k, S));
+        CUDA_OK(cudaEventRecord(b->ev_p3s[j], S));
+        CUDA_OK(cudaStreamWaitEvent(Y, b->ev_p3s[j], 0));
+        CUDA_OK(cudaStreamWaitEvent(Y, b->ev_aux[j], 0));
+        STEP_LAUNCH(2, Y, hoic_launch_p3c(b->b, all, k, Y));
+        if (k + 1 < b->nsub) {
+          STEP_LAUNCH(0, Y, p1(late, k + 1, Y));
+          STEP_LAUNCH(1, Y, hoic_launch_p2(b->b, late, k + 1, Y));
+          STEP_LAUNCH(0, S, p1(early, k + 1, S));
+          STEP_LAUNCH(1, S, hoic_launch_p2(b->b, early, k + 1, S));
+        }
+        CUDA_OK(cudaEventRecord(b->ev_carry[j], Y));
+        if (k + 1 == b->nsub) CUDA_OK(cudaStreamWaitEvent(S, b->ev_carry[j], 0));
+      }
+    }
+    for (int k = 0; !carry && k < b->nsub; k++) {
       // fused mode: k_p1 of substep k >= 1 ran inside the previous substep's solve launch (k_a.cu)
       if (b->fuse12) STEP_PARTS(0, hoic_launch_p12(b->b, sp, actions, k, sm));
       else {

@@ -43,6 +43,22 @@ __device__ __forceinline__ EnvSlot env_of_slot(const BatchDev& B, StepPart sp, i
   e.env = e.live ? (B.perm ? B.perm[slot] : slot) : B.n_envs - 1;
   return e;
 }
+// full-tier list of (part, substep k): double-buffered by the parity of k (carry mode reads substep k - 1's list while k_p2 of
+// substep k appends to the other one)
+__device__ __forceinline__ int* full_list_of(const BatchDev& B, int part, int k) {
+  return B.full_list + ((size_t)(k & 1) * HOIC_LIST_PARTS + part) * B.n_envs;
+}
+// the envs of group 2 at substep k (see StepPart): carried solves first, then the full tier's envs, both of substep k - 1
+struct LateList { const int* carry; const int* full; int n1, n; };
+__device__ __forceinline__ LateList late_list(const BatchDev& B, StepPart sp, int k) {
+  LateList l;
+  l.carry = B.carry_list + (size_t)sp.part * B.n_envs;
+  l.full = full_list_of(B, sp.part, k - 1);
+  l.n1 = B.carry_count[sp.part * FULL_COUNT_STRIDE + k - 1];
+  l.n = l.n1 + B.full_count[sp.part * FULL_COUNT_STRIDE + k - 1];
+  return l;
+}
+__device__ __forceinline__ int late_env(const LateList& l, int i) { return i < l.n1 ? l.carry[i] : l.full[i - l.n1]; }
 // env failed earlier in this step (physics failure or capacity overflow): the remaining kernels skip it
 __device__ __forceinline__ bool env_dead(const int* misc) { return (misc[MI_FLAGS] & 3) != 0; }
 

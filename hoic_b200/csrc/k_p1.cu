@@ -29,13 +29,29 @@
 __global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) K_P1(BatchDev B, StepPart sp, const float* __restrict__ actions, int k) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s = smem + (size_t)warp * S_TOTAL;
+  int* misc = (int*)(s + S_MISC);
+  if (sp.group == 2) {
+    // carry mode: the late envs of substep k (their solve of substep k - 1 was finished by k_p3c / the full tier), warp-strided
+    const LateList l = late_list(B, sp, k);
+    for (int i = blockIdx.x * P1_W + warp; i < l.n; i += gridDim.x * P1_W) {
+      EnvSlot es;
+      es.live = true;
+      es.env = late_env(l, i);
+      float* g = B.scratch + (size_t)es.env * G_TOTAL;
+      const DevModel& m = *B.env_model[es.env];
+      if (k < m.sim_step)
+        p1_body<false>(B, es, es.env, s, g, B.state + (size_t)es.env * ST_STRIDE, m, misc, actions, k, lane, g + G_OFF(GPOS), g + G_OFF(GMAT));
+      __syncwarp();
+    }
+    return;
+  }
   const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P1_W + warp);
   const int env = es.env;
-  float* s = smem + (size_t)warp * S_TOTAL;
+  if (sp.group == 1 && k > 0 && es.live && B.late_stamp[env] == k) return;     // carry mode: this env comes with group 2
   float* g = B.scratch + (size_t)env * G_TOTAL;
   float* st = B.state + (size_t)env * ST_STRIDE;
   const DevModel& m = *B.env_model[env];
-  int* misc = (int*)(s + S_MISC);
   if (k >= m.sim_step) return;
   p1_body<false>(B, es, env, s, g, st, m, misc, actions, k, lane, g + G_OFF(GPOS), g + G_OFF(GMAT));
 }
@@ -55,6 +71,8 @@ cudaError_t hoic_launch_p1w(const BatchDev& B, StepPart sp, const float* actions
 #else
 cudaError_t hoic_launch_p1(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream) {
 #endif
-  K_P1<<<hoic_step_grid(B, sp, P1_W), 32 * P1_W, hoic_step_smem(P1_W, g_p1_pad < 0 ? 0 : g_p1_pad), stream>>>(B, sp, actions, k);
+  int grid = hoic_step_grid(B, sp, P1_W);
+  if (sp.group == 2) grid = grid < 592 ? grid : 592;
+  K_P1<<<grid, 32 * P1_W, hoic_step_smem(P1_W, g_p1_pad < 0 ? 0 : g_p1_pad), stream>>>(B, sp, actions, k);
   return cudaGetLastError();
 }

@@ -13,12 +13,24 @@
 __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, StepPart sp, int k) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s = smem + (size_t)warp * S_TOTAL;
+  int* misc = (int*)(s + S_MISC);
+  if (sp.group == 2) {
+    // carry mode: the late envs of substep k, CTA-strided so that the warps of a CTA keep meeting at p2_body's barriers
+    const LateList l = late_list(B, sp, k);
+    for (int base = blockIdx.x * P2_W; base < l.n; base += gridDim.x * P2_W) {
+      EnvSlot es;
+      es.live = base + warp < l.n;
+      es.env = late_env(l, es.live ? base + warp : base);
+      p2_body<false>(B, sp, es, es.env, s, B.scratch + (size_t)es.env * G_TOTAL, *B.env_model[es.env], misc, k, lane);
+      __syncthreads();
+    }
+    return;
+  }
   const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P2_W + warp);
   const int env = es.env;
-  float* s = smem + (size_t)warp * S_TOTAL;
   float* g = B.scratch + (size_t)env * G_TOTAL;
   const DevModel& m = *B.env_model[env];
-  int* misc = (int*)(s + S_MISC);
   p2_body<false>(B, sp, es, env, s, g, m, misc, k, lane);
 }
 
@@ -28,6 +40,8 @@ cudaError_t hoic_configure_p2() {
   return cudaFuncSetAttribute(k_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hoic_step_smem(P2_W, g_p2_pad));
 }
 cudaError_t hoic_launch_p2(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
-  k_p2<<<hoic_step_grid(B, sp, P2_W), 32 * P2_W, hoic_step_smem(P2_W, g_p2_pad < 0 ? 0 : g_p2_pad), stream>>>(B, sp, k);
+  int grid = hoic_step_grid(B, sp, P2_W);
+  if (sp.group == 2) grid = grid < 148 ? grid : 148;     // a few per cent of the part: one 5-env CTA per SM, strided beyond that
+  k_p2<<<grid, 32 * P2_W, hoic_step_smem(P2_W, g_p2_pad < 0 ? 0 : g_p2_pad), stream>>>(B, sp, k);
   return cudaGetLastError();
 }

@@ -15,7 +15,11 @@
 #define H_NCON P3S_NCON
 #define H_NBASIS P3S_NBASIS
 #define H_NEDGE P3S_NEDGE
+#ifdef P3_CONT         // third build: k_p3c continues the solves a capped k_p3s left open (hoic_step "carry" mode)
+#define K_P3 k_p3c
+#else
 #define K_P3 k_p3s
+#endif
 #define P3_TIER 0
 #else
 #define K_P3 k_p3
@@ -38,7 +42,7 @@
 #endif
 
 // the solve of one env (one warp); s = the warp's shared-memory region
-__device__ __forceinline__ void p3_env(const BatchDev& B, const int env, const int k, float* s, const int lane) {
+__device__ __forceinline__ void p3_env(const BatchDev& B, const StepPart sp, const int env, const int k, float* s, const int lane) {
   float* g = B.scratch + (size_t)env * G_TOTAL;
   const DevModel& m = *B.env_model[env];
   int* misc = (int*)(s + S_MISC);
@@ -50,10 +54,18 @@ __device__ __forceinline__ void p3_env(const BatchDev& B, const int env, const i
   LD_U(AREF, H_NROW); LD_U(D, H_NROW); LD_U(RINFO, H_NROW);
   LD_U(BMASK, H_NBASIS); LD_U(MPRQ, H_NBASIS); LD_U(CINFO, H_NCON * 8);
 #endif
+#ifdef P3_CONT
+  LD_FIELD(QACC); LD_FIELD(MA); LD_U(JAR, H_NROW);      // the open solve's point
+#endif
   ld_wait();
   if (env_dead(misc)) return;
   const int nc = misc[MI_NCON], nb = misc[MI_NBASIS], ne = misc[MI_NEDGE], nrow = H_RCON + ((ne + 31) & ~31);
   if ((nc <= P3S_NCON && nb <= P3S_NBASIS && ne <= P3S_NEDGE) != (P3_TIER == 0)) return;    // the other tier's env
+#ifdef P3_CONT
+  if (!misc[MI_SV_OPEN]) return;
+  if (lane == 0) misc[MI_SV_OPEN] = 0;
+  __syncwarp();
+#endif
 #ifndef P3_SMALL
   LD_U(B, nb * B_STRIDE);
   LD_U(AREF, nrow); LD_U(D, nrow); LD_U(RINFO, nrow);
@@ -65,7 +77,14 @@ __device__ __forceinline__ void p3_env(const BatchDev& B, const int env, const i
 #ifdef H_SOLVE_STATS
   const long long t_solve = clock64();
 #endif
+  bool open = false;
+#if defined(P3_CONT)
+  phase_solve(s, m, lane, cnt, true, 0, true, nullptr);
+#elif defined(P3_SMALL)
+  phase_solve(s, m, lane, cnt, true, B.solve_budget, false, &open);
+#else
   phase_solve(s, m, lane, cnt, true);
+#endif
 #ifdef H_SOLVE_STATS
   if (lane == 0) {     // analysis build (tools/solve_stats.py): solves, cycles and line-search evaluations by iteration count
     const int it = min((int)cnt.newton, 15);
@@ -82,6 +101,18 @@ __device__ __forceinline__ void p3_env(const BatchDev& B, const int env, const i
     misc[MI_C_MAXNEDGE] = max(misc[MI_C_MAXNEDGE], (int)cnt.max_nedge);
   }
   __syncwarp();
+#if defined(P3_SMALL) && !defined(P3_CONT)
+  if (open && !env_dead(misc)) {
+    // out of budget: the solve's point goes to the working set, the env to the carry list of this (part, substep); k_p1 / k_p2 of
+    // the next substep skip it (late_stamp) until k_p3c has finished the solve
+    ST_FIELD(MISC); ST_FIELD(QACC); ST_FIELD(MA); ST_U(JAR, nrow);
+    if (lane == 0) {
+      B.late_stamp[env] = k + 1;
+      B.carry_list[(size_t)sp.part * B.n_envs + atomicAdd(B.carry_count + sp.part * FULL_COUNT_STRIDE + k, 1)] = env;
+    }
+    return;
+  }
+#endif
   ST_FIELD(MISC); ST_FIELD(QACC); ST_FIELD(FCON);
   if (B.rec_frames) ST_U(FORCE, nrow);
 }
@@ -94,9 +125,20 @@ __global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, Ste
   if (B.full_list) {
     // full tier: only the envs k_p2 listed for this substep (a few per cent of the batch), grid-strided
     const int n = B.full_count[sp.part * FULL_COUNT_STRIDE + k];
-    const int* list = B.full_list + (size_t)sp.part * B.n_envs;
+    const int* list = full_list_of(B, sp.part, k);
     for (int i = blockIdx.x * P3_W + warp; i < n; i += gridDim.x * P3_W) {
-      p3_env(B, list[i], k, s, lane);
+      p3_env(B, sp, list[i], k, s, lane);
+      __syncwarp();
+    }
+    return;
+  }
+#endif
+#ifdef P3_CONT
+  {
+    const int n = B.carry_count[sp.part * FULL_COUNT_STRIDE + k];
+    const int* list = B.carry_list + (size_t)sp.part * B.n_envs;
+    for (int i = blockIdx.x * P3_W + warp; i < n; i += gridDim.x * P3_W) {
+      p3_env(B, sp, list[i], k, s, lane);
       __syncwarp();
     }
     return;
@@ -104,11 +146,14 @@ __global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, Ste
 #endif
   const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P3_W + warp);
   if (!es.live) return;
-  p3_env(B, es.env, k, s, lane);
+  p3_env(B, sp, es.env, k, s, lane);
 }
 
 static int g_p3_pad = -1;
-#ifdef P3_SMALL
+#if defined(P3_CONT)
+cudaError_t hoic_configure_p3c() {
+  g_p3_pad = hoic_env_int("HOIC_P3S_PAD", 0);
+#elif defined(P3_SMALL)
 cudaError_t hoic_configure_p3s() {
   g_p3_pad = hoic_env_int("HOIC_P3S_PAD", 0);
 #else
@@ -117,7 +162,9 @@ cudaError_t hoic_configure_p3() {
 #endif
   return cudaFuncSetAttribute(K_P3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hoic_step_smem(P3_W, g_p3_pad));
 }
-#ifdef P3_SMALL
+#if defined(P3_CONT)
+cudaError_t hoic_launch_p3c(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
+#elif defined(P3_SMALL)
 cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
 #else
 cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
@@ -126,11 +173,14 @@ cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t s
 #ifndef P3_SMALL
   if (B.full_list) grid = grid < P3_LIST_GRID ? grid : P3_LIST_GRID;
 #endif
+#ifdef P3_CONT
+  grid = grid < P3_LIST_GRID ? grid : P3_LIST_GRID;
+#endif
   K_P3<<<grid, 32 * P3_W, hoic_step_smem(P3_W, g_p3_pad < 0 ? 0 : g_p3_pad), stream>>>(B, sp, k);
   return cudaGetLastError();
 }
 
-#ifdef H_SOLVE_STATS
+#if defined(H_SOLVE_STATS) && !defined(P3_CONT)
 #ifdef P3_SMALL
 extern "C" int hoic_debug_solve_stats_small(unsigned long long* out64, int reset) {
 #else

@@ -28,7 +28,8 @@ __device__ __forceinline__ void p2_body(const BatchDev& B, const StepPart sp, co
   }
   // work = this slot holds an env that is still running this step (k = -1: whose previous state had a forward)
   // (k = -1 is skipped for an env whose working set was carried over from the previous step, see k_p1)
-  const bool work = es.live && k < m.sim_step && (k < 0 ? !(misc[MI_FLAGS] & 1) && !misc[MI_CARRIED] : !env_dead(misc));
+  const bool late = sp.group == 1 && k > 0 && es.live && B.late_stamp[env] == k;     // carry mode: this env comes with group 2
+  const bool work = es.live && !late && k < m.sim_step && (k < 0 ? !(misc[MI_FLAGS] & 1) && !misc[MI_CARRIED] : !env_dead(misc));
   float* csum = B.csum + (size_t)env * CSUM_STRIDE;
   unsigned c0 = 0, c1 = 0;
   P2_SYNC();
@@ -68,8 +69,10 @@ __device__ __forceinline__ void p2_body(const BatchDev& B, const StepPart sp, co
   __syncwarp();
   // the used part of the constraint stage -> global working set (input of the Newton solve)
   const int nc = misc[MI_NCON], nb = misc[MI_NBASIS], nrow = H_RCON + ((misc[MI_NEDGE] + 31) & ~31);
-  if (lane == 0 && B.full_list && !(nc <= P3S_NCON && nb <= P3S_NBASIS && misc[MI_NEDGE] <= P3S_NEDGE) && !env_dead(misc))
-    B.full_list[(size_t)sp.part * B.n_envs + atomicAdd(B.full_count + sp.part * FULL_COUNT_STRIDE + k, 1)] = env;
+  if (lane == 0 && B.full_list && !(nc <= P3S_NCON && nb <= P3S_NBASIS && misc[MI_NEDGE] <= P3S_NEDGE) && !env_dead(misc)) {
+    full_list_of(B, sp.part, k)[atomicAdd(B.full_count + sp.part * FULL_COUNT_STRIDE + k, 1)] = env;
+    if (B.solve_budget > 0) B.late_stamp[env] = k + 1;      // carry mode: the full tier's envs take k_p1 / k_p2 of the next substep late, too
+  }
   ST_FIELD(MISC);
   ST_U(B, nb * B_STRIDE);
   ST_U(AREF, nrow); ST_U(D, nrow); ST_U(RINFO, nrow);
