@@ -48,11 +48,20 @@ struct BatchDev {
   int* carry_count;                   // [nparts][FULL_COUNT_STRIDE], behind reset_count's block
   int* late_stamp;                    // [N] substep + 1 of the last solve this env was carried / full-tier in (0 after the step's memset)
   int solve_budget;                   // Newton iterations of the capped launch (0: carry mode off)
+  // "tick" mode of hoic_step (env-asynchronous schedule): every env carries its own substep index; a tick runs k_p12 for the envs
+  // that are due for their smooth dynamics + collision and a BUDGETED solver launch for the envs that are in their solve (fresh or
+  // continued); the kernels of tick t read the lists of tick t and append to those of tick t + 1
+  int* tk_k;                          // [N] substep index of each env
+  int* tk_list;                       // [3][2][N]: 0 = k_p12, 1 = small solver tier, 2 = full tier; [parity of the tick]
+  int* tk_count;                      // [ticks + 2][4]
+  int tk_budget;                      // Newton iterations per tick
   int* reset_list;                    // [N]
   int* reset_count;                   // one counter behind full_count's block (same memset)
 };
 #define FULL_COUNT_STRIDE 32
 #define HOIC_LIST_PARTS 8            // = HOIC_MAX_PARTS of hoic_capi.cu
+#define TK_LIST(B, which, t) ((B).tk_list + ((size_t)(which) * 2 + ((t) & 1)) * (B).n_envs)
+#define TK_COUNT(B, which, t) ((B).tk_count + (size_t)(t) * 4 + (which))
 
 struct StepOut {
   float* obs; float* reward; float* info; uint8_t* done; uint8_t* fail; uint8_t* end; float* percent;

@@ -400,6 +400,7 @@ struct hoic_batch {
   // hoic_step runs the batch as `nparts` interleaved parts on internal streams (fork / join around the caller's stream)
   int nparts = 1;
   bool fuse = false;                     // solve + next substep's k_p1 in one launch (k_a.cu)
+  int ticks = 0;                         // tick mode: number of ticks per step (HOIC_TICKS), 0 = off
   bool fuse12 = false;                   // k_p1 + k_p2 of a substep in one launch (k_p12.cu, HOIC_FUSE12=1)
   bool p1_wide = false;                  // k_p1 with four envs per CTA (large batches)
   int part_delay_ns = 0;                 // experiment: part 1 starts this much later than part 0 (HOIC_PART_DELAY_US)
@@ -845,6 +846,13 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     CUDA_OKP(cudaMalloc(&b->b.late_stamp, (size_t)n_envs * sizeof(int)));
     CUDA_OKP(cudaMemset(b->b.late_stamp, 0, (size_t)n_envs * sizeof(int)));
     b->b.solve_budget = capi_env_int("HOIC_SOLVE_BUDGET", 0);
+    b->ticks = std::min(std::max(capi_env_int("HOIC_TICKS", 0), 0), 256);
+    b->b.tk_budget = std::max(capi_env_int("HOIC_TICK_BUDGET", 4), 1);
+    if (b->ticks > 0) {
+      CUDA_OKP(cudaMalloc(&b->b.tk_k, (size_t)n_envs * sizeof(int)));
+      CUDA_OKP(cudaMalloc(&b->b.tk_list, (size_t)6 * n_envs * sizeof(int)));
+      CUDA_OKP(cudaMalloc(&b->b.tk_count, (size_t)(b->ticks + 2) * 4 * sizeof(int)));
+    }
     CUDA_OKP(cudaMalloc(&b->b.full_count, (size_t)HOIC_COUNT_INTS * sizeof(int)));
     CUDA_OKP(cudaMemset(b->b.full_count, 0, (size_t)HOIC_COUNT_INTS * sizeof(int)));
     CUDA_OKP(cudaMalloc(&b->b.reset_list, (size_t)n_envs * sizeof(int)));
@@ -878,6 +886,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
     if (const char* e = getenv("HOIC_FUSE")) b->fuse = atoi(e) != 0;
     b->fuse12 = capi_env_int("HOIC_FUSE12", 0) != 0 && !b->fuse;
     if (b->fuse || b->fuse12 || !b->b.full_list) b->b.solve_budget = 0;      // carry mode needs the separate kernels and the env lists
+    if (b->fuse || b->fuse12 || b->b.solve_budget > 0 || !b->b.full_list) b->ticks = 0;
     CUDA_OKP(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     CUDA_OKP(cudaEventCreateWithFlags(&b->ev_tail, cudaEventDisableTiming));
     for (int j = 0; j < b->nparts; j++) {
@@ -900,7 +909,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   {
     static bool configured[64] = {false};
     if (!configured[device & 63]) {
-      CUDA_OKP(hoic_configure_p1()); CUDA_OKP(hoic_configure_p2()); CUDA_OKP(hoic_configure_p3()); CUDA_OKP(hoic_configure_p3s()); CUDA_OKP(hoic_configure_p3c()); CUDA_OKP(hoic_configure_tail());
+      CUDA_OKP(hoic_configure_p1()); CUDA_OKP(hoic_configure_p2()); CUDA_OKP(hoic_configure_p3()); CUDA_OKP(hoic_configure_p3s()); CUDA_OKP(hoic_configure_p3c()); CUDA_OKP(hoic_configure_p3fc()); CUDA_OKP(hoic_configure_tail());
       CUDA_OKP(hoic_configure_a()); CUDA_OKP(hoic_configure_as()); CUDA_OKP(hoic_configure_p1w()); CUDA_OKP(hoic_configure_p12());
       configured[device & 63] = true;
     }
@@ -930,6 +939,7 @@ extern "C" void hoic_batch_destroy(hoic_batch* b) {
   }
   cudaFree(b->env_model_dev); cudaFree(b->b.scratch); cudaFree(b->b.state); cudaFree(b->b.old_geom); cudaFree(b->b.counters); cudaFree(b->b.csum); cudaFree(b->b.csum_carry);
   cudaFree(b->b.full_list); cudaFree(b->b.full_count); cudaFree(b->b.reset_list); cudaFree(b->b.carry_list); cudaFree(b->b.late_stamp);
+  cudaFree(b->b.tk_k); cudaFree(b->b.tk_list); cudaFree(b->b.tk_count);
   cudaFree(b->env_model_idx); cudaFree(b->samp_off); cudaFree(b->samp_ids); cudaFree(b->order);
   cudaFree(b->reward_w); cudaFree(b->frames); cudaFree(b->motion_offset); cudaFree(b->motion_len);
   delete b;
@@ -1091,6 +1101,22 @@ extern "C" int hoic_get_timing(hoic_batch* b, double* ms_host, int* steps_host) 
   return 0;
 }
 
+// tick mode: every env starts substep 0 in the k_p12 list of tick 0 (in the step's env order)
+__global__ void k_tick_init(BatchDev B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n_envs) return;
+  const int env = B.perm ? B.perm[i] : i;
+  B.tk_k[env] = 0;
+  TK_LIST(B, 0, 0)[i] = env;
+  if (i == 0) *TK_COUNT(B, 0, 0) = B.n_envs;
+}
+// tick mode: an env that is not through its substeps when the ticks are used up fails like a diverged simulation
+__global__ void k_tick_finish(BatchDev B) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= B.n_envs) return;
+  int* misc = (int*)(B.scratch + (size_t)env * G_TOTAL + G_OFF(MISC));
+  if (B.tk_k[env] < B.env_model[env]->sim_step && !(misc[MI_FLAGS] & 3)) misc[MI_FLAGS] |= 1;
+}
 __global__ void k_delay(int ns) {
   const long long t0 = clock64();
   while (clock64() - t0 < (long long)ns * 2) __nanosleep(200);     // ~2 cycles per ns at 1.9 GHz
@@ -1137,7 +1163,39 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
       STEP_PARTS(0, b->p1_wide ? hoic_launch_p1w(b->b, sp, actions, -1, sm) : hoic_launch_p1(b->b, sp, actions, -1, sm));
       STEP_PARTS(1, hoic_launch_p2(b->b, sp, -1, sm));
     }
-    const bool carry = b->b.solve_budget > 0 && !b->fuse && !b->fuse12;
+    const bool tick = b->ticks > 0 && b->b.tk_k;
+    if (tick) {
+      // Tick mode (opt-in experiment, HOIC_TICKS=T HOIC_TICK_BUDGET=M): an env-asynchronous schedule out of plain launches.
+      // The parts' pass -1 launches above have run; from here ONE chain: every tick runs k_p12 (smooth dynamics + collision +
+      // rows of an env's own next substep) for the envs that are due and a solver launch of at most M Newton iterations for the
+      // envs that are in a solve, side by side; an env moves to the other list when it is through.  Bit-identical results;
+      // MEASURED SLOWER (box, 4 096 envs: 5.9 ms with T = 64, M = 3 against 4.3 ms): a tick's k_p12 over the ~2 000 envs that are due
+      // is a throughput-bound 110 us launch, not one env's 60 us chain (profiles/README.md).
+      cudaStream_t M0 = b->part_stream[0], A = b->aux_stream[0], C = b->carry_stream[0];
+      for (int j = 1; j < np; j++) { CUDA_OK(cudaEventRecord(b->ev_join[j], b->part_stream[j])); CUDA_OK(cudaStreamWaitEvent(M0, b->ev_join[j], 0)); }
+      CUDA_OK(cudaMemsetAsync(b->b.tk_count, 0, (size_t)(b->ticks + 2) * 4 * sizeof(int), M0));
+      k_tick_init<<<(b->n_envs + 255) / 256, 256, 0, M0>>>(b->b);
+      LAUNCH_CHECK();
+      const StepPart tk = {0, 1, 3};
+      for (int t = 0; t < b->ticks; t++) {
+        CUDA_OK(cudaEventRecord(b->ev_rows[0], M0));
+        CUDA_OK(cudaStreamWaitEvent(A, b->ev_rows[0], 0));
+        CUDA_OK(cudaStreamWaitEvent(C, b->ev_rows[0], 0));
+        STEP_LAUNCH(0, M0, hoic_launch_p12(b->b, tk, actions, t, M0));
+        STEP_LAUNCH(2, A, hoic_launch_p3c(b->b, tk, t, A));
+        STEP_LAUNCH(3, C, hoic_launch_p3fc(b->b, tk, t, C));
+        CUDA_OK(cudaEventRecord(b->ev_aux[0], A));
+        CUDA_OK(cudaEventRecord(b->ev_carry[0], C));
+        CUDA_OK(cudaStreamWaitEvent(M0, b->ev_aux[0], 0));
+        CUDA_OK(cudaStreamWaitEvent(M0, b->ev_carry[0], 0));
+      }
+      k_tick_finish<<<(b->n_envs + 255) / 256, 256, 0, M0>>>(b->b);
+      LAUNCH_CHECK();
+      // the other parts' streams continue after the ticks (their k_tail launches below)
+      CUDA_OK(cudaEventRecord(b->ev_rows[0], M0));
+      for (int j = 1; j < np; j++) CUDA_OK(cudaStreamWaitEvent(b->part_stream[j], b->ev_rows[0], 0));
+    }
+    const bool carry = !tick && b->b.solve_budget > 0 && !b->fuse && !b->fuse12;
     for (int k = 0; carry && k < b->nsub; k++) {
       // Carry mode (opt-in experiment, HOIC_SOLVE_BUDGET=n; bit-identical results).  A launch of the solver lasts as long as its
       // slowest solve (7-8 Newton iterations in SOME env of the part, every substep), and k_p1 / k_p2 of the next substep wait for
@@ -1176,7 +1234,7 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
         if (k + 1 == b->nsub) CUDA_OK(cudaStreamWaitEvent(S, b->ev_carry[j], 0));
       }
     }
-    for (int k = 0; !carry && k < b->nsub; k++) {
+    for (int k = 0; !carry && !tick && k < b->nsub; k++) {
       // fused mode: k_p1 of substep k >= 1 ran inside the previous substep's solve launch (k_a.cu)
       if (b->fuse12) STEP_PARTS(0, hoic_launch_p12(b->b, sp, actions, k, sm));
       else {

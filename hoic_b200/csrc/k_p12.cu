@@ -19,6 +19,36 @@ static_assert(S_OFF(MS) + 384 <= S_OFF(UNION) + UN_SIZE && S_OFF(WARM) >= S_OFF(
 __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p12(BatchDev B, StepPart sp, const float* __restrict__ actions, int k) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (sp.group == 3) {
+    // tick mode: `k` is the tick; the envs that are due come from the tick's list, each with its own substep index
+    const int t = k, n = *TK_COUNT(B, 0, t);
+    const int* list = TK_LIST(B, 0, t);
+    float* s = smem + (size_t)warp * S_TOTAL;
+    int* misc = (int*)(s + S_MISC);
+    for (int base = blockIdx.x * P2_W; base < n; base += gridDim.x * P2_W) {
+      EnvSlot es;
+      es.live = base + warp < n;
+      es.env = list[es.live ? base + warp : base];
+      const int env = es.env, kk = B.tk_k[env];
+      float* g = B.scratch + (size_t)env * G_TOTAL;
+      const DevModel& m = *B.env_model[env];
+      bool fwd = false;
+      if (kk < m.sim_step) fwd = p1_body<false>(B, es, env, s, g, B.state + (size_t)env * ST_STRIDE, m, misc, actions, kk, lane, s + S_GPOS, s + S_GMAT);
+      __syncwarp();
+      if (fwd && es.live) { ST_FIELD(GPOS); ST_FIELD(GMAT); }
+      if (kk >= m.sim_step) misc[lane] = 0;
+      __syncwarp();
+      p2_body<true>(B, sp, es, env, s, g, m, misc, kk, lane);
+      __syncwarp();
+      if (es.live && lane == 0 && fwd && kk < m.sim_step && !env_dead(misc)) {
+        // into the solver's list of the next tick, by capacity tier
+        const int tier = (misc[MI_NCON] <= P3S_NCON && misc[MI_NBASIS] <= P3S_NBASIS && misc[MI_NEDGE] <= P3S_NEDGE) ? 1 : 2;
+        TK_LIST(B, tier, t + 1)[atomicAdd(TK_COUNT(B, tier, t + 1), 1)] = env;
+      }
+      __syncthreads();
+    }
+    return;
+  }
   const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P2_W + warp);
   const int env = es.env;
   float* s = smem + (size_t)warp * S_TOTAL;
@@ -43,6 +73,8 @@ cudaError_t hoic_configure_p12() {
   return cudaFuncSetAttribute(k_p12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hoic_step_smem(P2_W, g_p12_pad));
 }
 cudaError_t hoic_launch_p12(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream) {
-  k_p12<<<hoic_step_grid(B, sp, P2_W), 32 * P2_W, hoic_step_smem(P2_W, g_p12_pad < 0 ? 0 : g_p12_pad), stream>>>(B, sp, actions, k);
+  int grid = hoic_step_grid(B, sp, P2_W);
+  if (sp.group == 3) grid = grid < 444 ? grid : 444;      // tick mode: one resident wave, CTA-strided over the tick's list
+  k_p12<<<grid, 32 * P2_W, hoic_step_smem(P2_W, g_p12_pad < 0 ? 0 : g_p12_pad), stream>>>(B, sp, actions, k);
   return cudaGetLastError();
 }

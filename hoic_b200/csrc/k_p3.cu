@@ -15,14 +15,18 @@
 #define H_NCON P3S_NCON
 #define H_NBASIS P3S_NBASIS
 #define H_NEDGE P3S_NEDGE
-#ifdef P3_CONT         // third build: k_p3c continues the solves a capped k_p3s left open (hoic_step "carry" mode)
-#define K_P3 k_p3c
+#ifdef P3_CONT         // third build: k_p3c continues the solves a capped k_p3s left open (hoic_step "carry" mode) and is the
+#define K_P3 k_p3c    // small tier's budgeted solver of the "tick" mode
 #else
 #define K_P3 k_p3s
 #endif
 #define P3_TIER 0
 #else
+#ifdef P3_CONT         // fourth build: the full tier's budgeted solver of the tick mode
+#define K_P3 k_p3fc
+#else
 #define K_P3 k_p3
+#endif
 #define P3_TIER 1
 #endif
 #include "hoic_step.cuh"
@@ -117,10 +121,75 @@ __device__ __forceinline__ void p3_env(const BatchDev& B, const StepPart sp, con
   if (B.rec_frames) ST_U(FORCE, nrow);
 }
 
+#ifdef P3_CONT
+// tick mode: one budgeted round of the solve of env `env` (fresh, or the continuation of a solve an earlier tick left open);
+// afterwards the env goes to the next tick's list of whoever comes next: this solver tier again, or k_p12 of the next substep
+__device__ __forceinline__ void p3_env_tick(const BatchDev& B, const int env, const int t, float* s, const int lane) {
+  float* g = B.scratch + (size_t)env * G_TOTAL;
+  const DevModel& m = *B.env_model[env];
+  int* misc = (int*)(s + S_MISC);
+  const int k = B.tk_k[env];
+  if (k >= m.sim_step) return;
+  LD_FIELD(MISC); LD_FIELD(WARM); LD_FIELD(SMOOTH); LD_FIELD(ASMOOTH); LD_FIELD(MS); LD_FIELD(QACC); LD_FIELD(MA);
+#ifdef P3_SMALL
+  LD_U(B, H_NBASIS * B_STRIDE);
+  LD_U(AREF, H_NROW); LD_U(D, H_NROW); LD_U(RINFO, H_NROW);
+  LD_U(BMASK, H_NBASIS); LD_U(MPRQ, H_NBASIS); LD_U(CINFO, H_NCON * 8); LD_U(JAR, H_NROW);
+#endif
+  ld_wait();
+  if (env_dead(misc)) return;
+  const int nc = misc[MI_NCON], nb = misc[MI_NBASIS], ne = misc[MI_NEDGE], nrow = H_RCON + ((ne + 31) & ~31);
+#ifndef P3_SMALL
+  LD_U(B, nb * B_STRIDE);
+  LD_U(AREF, nrow); LD_U(D, nrow); LD_U(RINFO, nrow);
+  LD_U(BMASK, nb); LD_U(MPRQ, nb); LD_U(CINFO, nc * 8); LD_U(JAR, nrow);
+  ld_wait();
+#endif
+  const bool resume = misc[MI_SV_OPEN] != 0;
+  __syncwarp();
+  if (lane == 0) misc[MI_SV_OPEN] = 0;
+  __syncwarp();
+  Cnt cnt;
+  memset(&cnt, 0, sizeof cnt);
+  bool open = false;
+  phase_solve(s, m, lane, cnt, true, B.tk_budget, resume, &open);
+  if (lane == 0) {
+    misc[MI_C_SUBSTEPS] += (int)cnt.substeps; misc[MI_C_NCON] += (int)cnt.ncon; misc[MI_C_NEFC] += (int)cnt.nefc;
+    misc[MI_C_NEWTON] += (int)cnt.newton; misc[MI_C_LS] += (int)cnt.ls;
+    misc[MI_C_MAXNCON] = max(misc[MI_C_MAXNCON], (int)cnt.max_ncon);
+    misc[MI_C_MAXNBASIS] = max(misc[MI_C_MAXNBASIS], (int)cnt.max_nbasis);
+    misc[MI_C_MAXNEDGE] = max(misc[MI_C_MAXNEDGE], (int)cnt.max_nedge);
+  }
+  __syncwarp();
+  if (open && !env_dead(misc)) {
+    ST_FIELD(MISC); ST_FIELD(QACC); ST_FIELD(MA); ST_U(JAR, nrow);
+    if (lane == 0) TK_LIST(B, 1 + P3_TIER, t + 1)[atomicAdd(TK_COUNT(B, 1 + P3_TIER, t + 1), 1)] = env;
+    return;
+  }
+  ST_FIELD(MISC); ST_FIELD(QACC); ST_FIELD(FCON);
+  if (B.rec_frames) ST_U(FORCE, nrow);
+  if (lane == 0) {
+    B.tk_k[env] = k + 1;
+    if (k + 1 < m.sim_step && !env_dead(misc)) TK_LIST(B, 0, t + 1)[atomicAdd(TK_COUNT(B, 0, t + 1), 1)] = env;
+  }
+}
+#endif
+
 __global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, StepPart sp, int k) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s = smem + (size_t)warp * S_TOTAL;
+#ifdef P3_CONT
+  if (sp.group == 3) {
+    const int t = k, n = *TK_COUNT(B, 1 + P3_TIER, t);
+    const int* list = TK_LIST(B, 1 + P3_TIER, t);
+    for (int i = blockIdx.x * P3_W + warp; i < n; i += gridDim.x * P3_W) {
+      p3_env_tick(B, list[i], t, s, lane);
+      __syncwarp();
+    }
+    return;
+  }
+#endif
 #ifndef P3_SMALL
   if (B.full_list) {
     // full tier: only the envs k_p2 listed for this substep (a few per cent of the batch), grid-strided
@@ -133,7 +202,7 @@ __global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, Ste
     return;
   }
 #endif
-#ifdef P3_CONT
+#if defined(P3_CONT) && defined(P3_SMALL)
   {
     const int n = B.carry_count[sp.part * FULL_COUNT_STRIDE + k];
     const int* list = B.carry_list + (size_t)sp.part * B.n_envs;
@@ -150,7 +219,10 @@ __global__ void __launch_bounds__(32 * P3_W, P3_WPS / P3_W) K_P3(BatchDev B, Ste
 }
 
 static int g_p3_pad = -1;
-#if defined(P3_CONT)
+#if defined(P3_CONT) && !defined(P3_SMALL)
+cudaError_t hoic_configure_p3fc() {
+  g_p3_pad = hoic_env_int("HOIC_P3_PAD", 0);
+#elif defined(P3_CONT)
 cudaError_t hoic_configure_p3c() {
   g_p3_pad = hoic_env_int("HOIC_P3S_PAD", 0);
 #elif defined(P3_SMALL)
@@ -162,7 +234,9 @@ cudaError_t hoic_configure_p3() {
 #endif
   return cudaFuncSetAttribute(K_P3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hoic_step_smem(P3_W, g_p3_pad));
 }
-#if defined(P3_CONT)
+#if defined(P3_CONT) && !defined(P3_SMALL)
+cudaError_t hoic_launch_p3fc(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
+#elif defined(P3_CONT)
 cudaError_t hoic_launch_p3c(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
 #elif defined(P3_SMALL)
 cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
@@ -174,7 +248,12 @@ cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t s
   if (B.full_list) grid = grid < P3_LIST_GRID ? grid : P3_LIST_GRID;
 #endif
 #ifdef P3_CONT
-  grid = grid < P3_LIST_GRID ? grid : P3_LIST_GRID;
+#ifdef P3_SMALL
+  if (sp.group == 3) grid = grid < 2960 ? grid : 2960;      // tick mode: up to one resident wave, warp-strided over the tick's list
+#else
+  if (sp.group == 3) grid = grid < 148 ? grid : 148;        // (the full tier's list is a handful of envs)
+#endif
+  else grid = grid < P3_LIST_GRID ? grid : P3_LIST_GRID;
 #endif
   K_P3<<<grid, 32 * P3_W, hoic_step_smem(P3_W, g_p3_pad < 0 ? 0 : g_p3_pad), stream>>>(B, sp, k);
   return cudaGetLastError();

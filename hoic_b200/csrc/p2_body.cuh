@@ -69,7 +69,7 @@ __device__ __forceinline__ void p2_body(const BatchDev& B, const StepPart sp, co
   __syncwarp();
   // the used part of the constraint stage -> global working set (input of the Newton solve)
   const int nc = misc[MI_NCON], nb = misc[MI_NBASIS], nrow = H_RCON + ((misc[MI_NEDGE] + 31) & ~31);
-  if (lane == 0 && B.full_list && !(nc <= P3S_NCON && nb <= P3S_NBASIS && misc[MI_NEDGE] <= P3S_NEDGE) && !env_dead(misc)) {
+  if (lane == 0 && sp.group != 3 && B.full_list && !(nc <= P3S_NCON && nb <= P3S_NBASIS && misc[MI_NEDGE] <= P3S_NEDGE) && !env_dead(misc)) {
     full_list_of(B, sp.part, k)[atomicAdd(B.full_count + sp.part * FULL_COUNT_STRIDE + k, 1)] = env;
     if (B.solve_budget > 0) B.late_stamp[env] = k + 1;      // carry mode: the full tier's envs take k_p1 / k_p2 of the next substep late, too
   }

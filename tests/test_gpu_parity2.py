@@ -309,7 +309,7 @@ def test_sdf_penetration_metric():
     assert pm2.eval_contact_point().max() >= 1
 
 
-@pytest.mark.parametrize("knob", ["HOIC_FUSE", "HOIC_FUSE12", "HOIC_SOLVE_BUDGET"])
+@pytest.mark.parametrize("knob", ["HOIC_FUSE", "HOIC_FUSE12", "HOIC_SOLVE_BUDGET", "HOIC_TICKS"])
 def test_fused_kernels_equal_the_separate_kernels(knob):
     """The opt-in fused kernels -- HOIC_FUSE=1 (k_a.cu: Newton solve of substep k + k_p1's work of substep k + 1 in one launch)
     and HOIC_FUSE12=1 (k_p12.cu: k_p1 + k_p2 of a substep in one launch) -- must reproduce the default pipeline bit for bit:
@@ -321,7 +321,7 @@ def test_fused_kernels_equal_the_separate_kernels(knob):
         mdl = model(obj)
         outs = []
         for fuse in ("0", "1"):     # (HOIC_SOLVE_BUDGET=1: carry mode with one Newton iteration per capped launch, the hardest split)
-            os.environ[knob] = fuse
+            os.environ[knob] = "96" if (knob == "HOIC_TICKS" and fuse == "1") else fuse
             try:
                 env = HandMimicVecEnv(mdl, 160, [mdl.motion(s) for s in range(1, 9)], device=0, seed=5, auto_reset=True)
             finally:
