@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # (source, object, extra flags): k_p3.cu and k_a.cu are compiled twice, once per capacity tier
 UNITS = [("hoic_capi.cu", "hoic_capi.o", []), ("k_p1.cu", "k_p1.o", []), ("k_p1.cu", "k_p1w.o", ["-DP1_WIDE"]), ("k_p2.cu", "k_p2.o", []), ("k_p3.cu", "k_p3.o", []),
-         ("k_p3.cu", "k_p3s.o", ["-DP3_SMALL"]), ("k_p3.cu", "k_p3c.o", ["-DP3_SMALL", "-DP3_CONT"]), ("k_p3.cu", "k_p3fc.o", ["-DP3_CONT"]), ("k_tail.cu", "k_tail.o", []), ("k_glue.cu", "k_glue.o", []),
+         ("k_p3.cu", "k_p3s.o", ["-DP3_SMALL"]), ("k_p3.cu", "k_p3sb.o", ["-DP3_SMALL", "-DP3_BUDGET"]), ("k_p3.cu", "k_p3c.o", ["-DP3_SMALL", "-DP3_CONT"]), ("k_p3.cu", "k_p3fc.o", ["-DP3_CONT"]), ("k_tail.cu", "k_tail.o", []), ("k_glue.cu", "k_glue.o", []),
          ("k_p12.cu", "k_p12.o", []), ("k_a.cu", "k_a.o", []), ("k_a.cu", "k_as.o", ["-DP3_SMALL"])]
 OUT = os.environ.get("HOIC_BUILD_OUT", os.path.join(HERE, "libhoic_b200.so"))      # HOIC_BUILD_OUT: A/B variant builds
 OBJDIR = os.path.join(HERE, "build") if "HOIC_BUILD_OUT" not in os.environ else OUT + ".obj"

@@ -95,14 +95,15 @@ static __device__ __noinline__ bool phase_smooth(float* s, const DevModel& m, in
 // Every warp of the CTA calls this (active = false: only the CTA barriers inside the solver are taken).
 // budget / resume / open_out: see solve_newton (a solve split over a capped launch and its continuation); the per-substep counters
 // are taken by the launch that STARTS the solve.
+template <bool SPLIT = false>
 static __device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int lane, Cnt& cnt, bool active, int budget = 0, bool resume = false,
                                                 bool* open_out = nullptr) {
   int* misc = (int*)(s + S_MISC);
   unsigned it = 0;
-  bool fail = !solve_newton(s, m, lane, active, it, cnt.ls, budget, resume, open_out);
+  bool fail = !solve_newton<SPLIT>(s, m, lane, active, it, cnt.ls, budget, resume, open_out);
   if (!active) return false;
   cnt.newton += it;
-  if (!resume) {
+  if (!(SPLIT && resume)) {
     cnt.substeps++;
     cnt.ncon += misc[MI_NCON];
     cnt.nefc += m.nv + misc[MI_NLIM] + misc[MI_NEDGE];
@@ -110,7 +111,7 @@ static __device__ __noinline__ bool phase_solve(float* s, const DevModel& m, int
     cnt.max_nbasis = max(cnt.max_nbasis, (unsigned)misc[MI_NBASIS]);
     cnt.max_nedge = max(cnt.max_nedge, (unsigned)misc[MI_NEDGE]);
   }
-  if (lane == 0) misc[MI_ITER] = (int)it + (resume ? misc[MI_ITER] : 0);
+  if (lane == 0) misc[MI_ITER] = (int)it + (SPLIT && resume ? misc[MI_ITER] : 0);
   fail = __any_sync(FULLMASK, fail || bad(s[S_QACC + lane]));
   if (fail) { if (lane == 0) misc[MI_FLAGS] |= 1; __syncwarp(); return false; }
   return !(misc[MI_FLAGS] & 2);   // capacity overflow: treated like MuJoCo's nconmax / njmax warnings

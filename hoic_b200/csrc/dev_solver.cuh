@@ -588,6 +588,8 @@ static __device__ __noinline__ int newton_move(float* s, const DevModel& m, int 
 // MISC[MI_SV_*] hold its state (the caller stores them) and `open_out` is set.  `resume`: continue such a solve (the caller loaded
 // S_QACC, S_MA, U_JAR; the row forces are recomputed from U_JAR, which reproduces them bit for bit), so that a solve split over two
 // launches performs exactly the arithmetic of an unsplit one.
+// SPLIT = false compiles all of that out (the default kernels).
+template <bool SPLIT = false>
 __device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int lane, bool active, unsigned& iters_out, unsigned& ls_evals,
                                              int budget = 0, bool resume = false, bool* open_out = nullptr) {
   int* misc = (int*)(s + S_MISC);
@@ -599,7 +601,7 @@ __device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int la
 #ifdef H_SOLVE_STATS
   long long sst_t = clock64();
 #endif
-  if (run && resume) {
+  if (SPLIT && run && resume) {
     iter = (unsigned)misc[MI_SV_ITER];
     cost = __int_as_float(misc[MI_SV_COST]);
     oldcost = __int_as_float(misc[MI_SV_OLDCOST]);
@@ -618,7 +620,7 @@ __device__ __forceinline__ bool solve_newton(float* s, const DevModel& m, int la
         if (improvement < tol || gradn < m.tolerance) run = false;
       }
       if (iter >= (unsigned)m.iterations) run = false;
-      if (run && budget > 0 && iter - iter0 >= (unsigned)budget) {
+      if (SPLIT && run && budget > 0 && iter - iter0 >= (unsigned)budget) {
         // out of budget with the solve still running: leave it open at the top of an iteration (gradient of this point is cheap
         // to redo; cost / oldcost / iter are what the termination test of the continuation needs)
         if (lane == 0) {

@@ -909,7 +909,7 @@ extern "C" hoic_batch* hoic_batch_create(const hoic_model* const* models, int n_
   {
     static bool configured[64] = {false};
     if (!configured[device & 63]) {
-      CUDA_OKP(hoic_configure_p1()); CUDA_OKP(hoic_configure_p2()); CUDA_OKP(hoic_configure_p3()); CUDA_OKP(hoic_configure_p3s()); CUDA_OKP(hoic_configure_p3c()); CUDA_OKP(hoic_configure_p3fc()); CUDA_OKP(hoic_configure_tail());
+      CUDA_OKP(hoic_configure_p1()); CUDA_OKP(hoic_configure_p2()); CUDA_OKP(hoic_configure_p3()); CUDA_OKP(hoic_configure_p3s()); CUDA_OKP(hoic_configure_p3sb()); CUDA_OKP(hoic_configure_p3c()); CUDA_OKP(hoic_configure_p3fc()); CUDA_OKP(hoic_configure_tail());
       CUDA_OKP(hoic_configure_a()); CUDA_OKP(hoic_configure_as()); CUDA_OKP(hoic_configure_p1w()); CUDA_OKP(hoic_configure_p12());
       configured[device & 63] = true;
     }
@@ -1219,7 +1219,7 @@ extern "C" int hoic_step(hoic_batch* b, const float* actions, float* obs, float*
         CUDA_OK(cudaStreamWaitEvent(X, b->ev_rows[j], 0));
         STEP_LAUNCH(3, X, hoic_launch_p3(b->b, all, k, X));
         CUDA_OK(cudaEventRecord(b->ev_aux[j], X));
-        STEP_LAUNCH(2, S, hoic_launch_p3s(b->b, all, k, S));
+        STEP_LAUNCH(2, S, hoic_launch_p3sb(b->b, all, k, S));
         CUDA_OK(cudaEventRecord(b->ev_p3s[j], S));
         CUDA_OK(cudaStreamWaitEvent(Y, b->ev_p3s[j], 0));
         CUDA_OK(cudaStreamWaitEvent(Y, b->ev_aux[j], 0));

@@ -17,6 +17,7 @@ cudaError_t hoic_launch_p1w(const BatchDev& B, StepPart sp, const float* actions
 cudaError_t hoic_launch_p2(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);
 cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);    // full-capacity tier
 cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);   // small tier (most envs)
+cudaError_t hoic_launch_p3sb(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);  // small tier with an iteration budget (carry mode)
 cudaError_t hoic_launch_p3c(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);   // continuation of the solves a capped k_p3s left open
 cudaError_t hoic_launch_p3fc(const BatchDev& B, StepPart sp, int k, cudaStream_t stream);  // full tier, budgeted (tick mode)
 // fused kernels (k_a.cu): Newton solve of substep k + k_p1's work of substep k + 1 in one launch, per capacity tier
@@ -31,6 +32,7 @@ cudaError_t hoic_configure_p1w();
 cudaError_t hoic_configure_p2();
 cudaError_t hoic_configure_p3();
 cudaError_t hoic_configure_p3s();
+cudaError_t hoic_configure_p3sb();
 cudaError_t hoic_configure_p3c();
 cudaError_t hoic_configure_p3fc();
 cudaError_t hoic_configure_tail();

@@ -26,12 +26,15 @@
 #define P1_WPS 23       // resident warps per SM the register budget is sized for
 #endif
 
+// GROUP (StepPart::group, a template parameter so that the default kernel carries none of the list-mode code): 0 = every env of the
+// part; 1 / 2 = hoic_step's carry mode (everybody but the late envs / the late envs from their lists)
+template <int GROUP>
 __global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) K_P1(BatchDev B, StepPart sp, const float* __restrict__ actions, int k) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s = smem + (size_t)warp * S_TOTAL;
   int* misc = (int*)(s + S_MISC);
-  if (sp.group == 2) {
+  if (GROUP == 2) {
     // carry mode: the late envs of substep k (their solve of substep k - 1 was finished by k_p3c / the full tier), warp-strided
     const LateList l = late_list(B, sp, k);
     for (int i = blockIdx.x * P1_W + warp; i < l.n; i += gridDim.x * P1_W) {
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(32 * P1_W, P1_WPS / P1_W) K_P1(BatchDev B, Ste
   }
   const EnvSlot es = env_of_slot(B, sp, blockIdx.x * P1_W + warp);
   const int env = es.env;
-  if (sp.group == 1 && k > 0 && es.live && B.late_stamp[env] == k) return;     // carry mode: this env comes with group 2
+  if (GROUP == 1 && k > 0 && es.live && B.late_stamp[env] == k) return;     // carry mode: this env comes with group 2
   float* g = B.scratch + (size_t)env * G_TOTAL;
   float* st = B.state + (size_t)env * ST_STRIDE;
   const DevModel& m = *B.env_model[env];
@@ -64,15 +67,20 @@ cudaError_t hoic_configure_p1() {
 #endif
   g_p1_pad = hoic_env_int("HOIC_P1_PAD", 0);
   const size_t smem = hoic_step_smem(P1_W, g_p1_pad);
-  return cudaFuncSetAttribute(K_P1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(K_P1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(K_P1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(K_P1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return e;
 }
 #ifdef P1_WIDE
 cudaError_t hoic_launch_p1w(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream) {
 #else
 cudaError_t hoic_launch_p1(const BatchDev& B, StepPart sp, const float* actions, int k, cudaStream_t stream) {
 #endif
-  int grid = hoic_step_grid(B, sp, P1_W);
-  if (sp.group == 2) grid = grid < 592 ? grid : 592;
-  K_P1<<<grid, 32 * P1_W, hoic_step_smem(P1_W, g_p1_pad < 0 ? 0 : g_p1_pad), stream>>>(B, sp, actions, k);
+  const int grid = hoic_step_grid(B, sp, P1_W);
+  const size_t smem = hoic_step_smem(P1_W, g_p1_pad < 0 ? 0 : g_p1_pad);
+  if (sp.group == 2) K_P1<2><<<grid < 592 ? grid : 592, 32 * P1_W, smem, stream>>>(B, sp, actions, k);
+  else if (sp.group == 1) K_P1<1><<<grid, 32 * P1_W, smem, stream>>>(B, sp, actions, k);
+  else K_P1<0><<<grid, 32 * P1_W, smem, stream>>>(B, sp, actions, k);
   return cudaGetLastError();
 }

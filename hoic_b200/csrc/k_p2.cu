@@ -10,13 +10,15 @@
 #endif
 #include "p2_body.cuh"
 
+// LIST (a template parameter so that the default kernel carries none of the list-mode code): hoic_step's carry mode, the late
+// envs of substep k, CTA-strided so that the warps of a CTA keep meeting at p2_body's barriers
+template <bool LIST>
 __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, StepPart sp, int k) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s = smem + (size_t)warp * S_TOTAL;
   int* misc = (int*)(s + S_MISC);
-  if (sp.group == 2) {
-    // carry mode: the late envs of substep k, CTA-strided so that the warps of a CTA keep meeting at p2_body's barriers
+  if (LIST) {
     const LateList l = late_list(B, sp, k);
     for (int base = blockIdx.x * P2_W; base < l.n; base += gridDim.x * P2_W) {
       EnvSlot es;
@@ -37,11 +39,15 @@ __global__ void __launch_bounds__(32 * P2_W, P2_WPS / P2_W) k_p2(BatchDev B, Ste
 static int g_p2_pad = -1;
 cudaError_t hoic_configure_p2() {
   g_p2_pad = hoic_env_int("HOIC_P2_PAD", 0);
-  return cudaFuncSetAttribute(k_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hoic_step_smem(P2_W, g_p2_pad));
+  cudaError_t e = cudaFuncSetAttribute(k_p2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hoic_step_smem(P2_W, g_p2_pad));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_p2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hoic_step_smem(P2_W, g_p2_pad));
+  return e;
 }
 cudaError_t hoic_launch_p2(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
-  int grid = hoic_step_grid(B, sp, P2_W);
-  if (sp.group == 2) grid = grid < 148 ? grid : 148;     // a few per cent of the part: one 5-env CTA per SM, strided beyond that
-  k_p2<<<grid, 32 * P2_W, hoic_step_smem(P2_W, g_p2_pad < 0 ? 0 : g_p2_pad), stream>>>(B, sp, k);
+  const int grid = hoic_step_grid(B, sp, P2_W);
+  const size_t smem = hoic_step_smem(P2_W, g_p2_pad < 0 ? 0 : g_p2_pad);
+  // (list mode: a few per cent of the part, one 5-env CTA per SM, strided beyond that)
+  if (sp.group == 2) k_p2<true><<<grid < 148 ? grid : 148, 32 * P2_W, smem, stream>>>(B, sp, k);
+  else k_p2<false><<<grid, 32 * P2_W, smem, stream>>>(B, sp, k);
   return cudaGetLastError();
 }

@@ -15,8 +15,10 @@
 #define H_NCON P3S_NCON
 #define H_NBASIS P3S_NBASIS
 #define H_NEDGE P3S_NEDGE
-#ifdef P3_CONT         // third build: k_p3c continues the solves a capped k_p3s left open (hoic_step "carry" mode) and is the
+#if defined(P3_CONT)   // third build: k_p3c continues the solves a capped launch left open (hoic_step "carry" mode) and is the
 #define K_P3 k_p3c    // small tier's budgeted solver of the "tick" mode
+#elif defined(P3_BUDGET)   // fifth build: k_p3sb, the capped launch of the carry mode (k_p3s itself carries no budget code)
+#define K_P3 k_p3sb
 #else
 #define K_P3 k_p3s
 #endif
@@ -83,9 +85,9 @@ __device__ __forceinline__ void p3_env(const BatchDev& B, const StepPart sp, con
 #endif
   bool open = false;
 #if defined(P3_CONT)
-  phase_solve(s, m, lane, cnt, true, 0, true, nullptr);
-#elif defined(P3_SMALL)
-  phase_solve(s, m, lane, cnt, true, B.solve_budget, false, &open);
+  phase_solve<true>(s, m, lane, cnt, true, 0, true, nullptr);
+#elif defined(P3_BUDGET)
+  phase_solve<true>(s, m, lane, cnt, true, B.solve_budget, false, &open);
 #else
   phase_solve(s, m, lane, cnt, true);
 #endif
@@ -105,7 +107,7 @@ __device__ __forceinline__ void p3_env(const BatchDev& B, const StepPart sp, con
     misc[MI_C_MAXNEDGE] = max(misc[MI_C_MAXNEDGE], (int)cnt.max_nedge);
   }
   __syncwarp();
-#if defined(P3_SMALL) && !defined(P3_CONT)
+#if defined(P3_BUDGET) && !defined(P3_CONT)
   if (open && !env_dead(misc)) {
     // out of budget: the solve's point goes to the working set, the env to the carry list of this (part, substep); k_p1 / k_p2 of
     // the next substep skip it (late_stamp) until k_p3c has finished the solve
@@ -152,7 +154,7 @@ __device__ __forceinline__ void p3_env_tick(const BatchDev& B, const int env, co
   Cnt cnt;
   memset(&cnt, 0, sizeof cnt);
   bool open = false;
-  phase_solve(s, m, lane, cnt, true, B.tk_budget, resume, &open);
+  phase_solve<true>(s, m, lane, cnt, true, B.tk_budget, resume, &open);
   if (lane == 0) {
     misc[MI_C_SUBSTEPS] += (int)cnt.substeps; misc[MI_C_NCON] += (int)cnt.ncon; misc[MI_C_NEFC] += (int)cnt.nefc;
     misc[MI_C_NEWTON] += (int)cnt.newton; misc[MI_C_LS] += (int)cnt.ls;
@@ -225,6 +227,9 @@ cudaError_t hoic_configure_p3fc() {
 #elif defined(P3_CONT)
 cudaError_t hoic_configure_p3c() {
   g_p3_pad = hoic_env_int("HOIC_P3S_PAD", 0);
+#elif defined(P3_BUDGET)
+cudaError_t hoic_configure_p3sb() {
+  g_p3_pad = hoic_env_int("HOIC_P3S_PAD", 0);
 #elif defined(P3_SMALL)
 cudaError_t hoic_configure_p3s() {
   g_p3_pad = hoic_env_int("HOIC_P3S_PAD", 0);
@@ -238,6 +243,8 @@ cudaError_t hoic_configure_p3() {
 cudaError_t hoic_launch_p3fc(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
 #elif defined(P3_CONT)
 cudaError_t hoic_launch_p3c(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
+#elif defined(P3_BUDGET)
+cudaError_t hoic_launch_p3sb(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
 #elif defined(P3_SMALL)
 cudaError_t hoic_launch_p3s(const BatchDev& B, StepPart sp, int k, cudaStream_t stream) {
 #else
@@ -259,7 +266,7 @@ cudaError_t hoic_launch_p3(const BatchDev& B, StepPart sp, int k, cudaStream_t s
   return cudaGetLastError();
 }
 
-#if defined(H_SOLVE_STATS) && !defined(P3_CONT)
+#if defined(H_SOLVE_STATS) && !defined(P3_CONT) && !defined(P3_BUDGET)
 #ifdef P3_SMALL
 extern "C" int hoic_debug_solve_stats_small(unsigned long long* out64, int reset) {
 #else
