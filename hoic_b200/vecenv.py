@@ -63,6 +63,7 @@ class HandMimicVecEnv:
         self.end = torch.zeros(N, dtype=torch.uint8, device=self.device)
         self._seed = int(seed)
         self._hs = None
+        self._mode = "train"     # the library's default (hoic_batch_create)
         self.graph_epoch = 0     # bumped whenever something a captured CUDA graph bakes in changes (mode, recording, tables)
         self._ep_mid = torch.zeros(N, dtype=torch.int32, device=self.device)
         self._ep_start = torch.zeros(N, dtype=torch.int32, device=self.device)
@@ -119,8 +120,10 @@ class HandMimicVecEnv:
 
     def set_mode(self, mode):
         capi.check(self.L.hoic_set_mode(self._hb, 1 if mode == "train" else 0), "hoic_set_mode")
-        self._hs = None     # kernel arguments are baked into a captured graph: recapture
-        self.graph_epoch += 1
+        if getattr(self, "_mode", None) != mode:      # (the sampler sets the mode at the start of every rollout: no change, no recapture)
+            self._mode = mode
+            self._hs = None     # kernel arguments are baked into a captured graph: recapture
+            self.graph_epoch += 1
 
     @property
     def balance(self):
