@@ -17,6 +17,7 @@ __device__ __forceinline__ bool p1_body(const BatchDev& B, const EnvSlot es, con
   float* recf = (B.rec_frames && es.live) ? B.rec_frames + (size_t)env * m.sim_step * HOIC_REC_STRIDE : nullptr;
   if (!FUSED && k < 0) {
     misc[lane] = 0;
+    __syncwarp();      // lane 0 sets MI_CARRIED (lane 20's slot) below: racecheck, profiles/r02b_sanitizer.txt
     int* ints = (int*)(st + ST_INTS);
     // The stale quantities of SURVEY S1 / S2 are the last forward of the previous env.step.  If this env's working set still
     // holds that forward (ints[7]: no reset / set_state since, no failure), nothing has to be recomputed: take the geom-pose
