@@ -19,6 +19,12 @@ static __device__ unsigned long long g_nst[64];   // [0..7] solves by iteration 
 #else
 #define NST_T(i) do { } while (0)
 #endif
+#ifndef NEWTON_ASM_UNROLL
+#define NEWTON_ASM_UNROLL 1     // A/B knobs (tools/build_variant.sh): unroll factors of the Hessian-assembly column loop ...
+#endif
+#ifndef NEWTON_AUX_UNROLL
+#define NEWTON_AUX_UNROLL 1     // ... and of the per-edge / per-row helper loops of newton_weights / newton_gradient
+#endif
 #define U_BINFO (U_MPRQ)   // basis row -> contact | k<<8 (the MPR queue is dead once contacts exist)
 #define U_CW (U_CON)       // per-contact Hessian weights reuse the contact records' slots 14..15 + CINFO pad
 
@@ -333,7 +339,7 @@ static __device__ __noinline__ float newton_gradient(float* s, const DevModel& m
     const int ri = rinfo[H_RLIM + r];
     if ((ri & 255) == lane) jtf += ((ri >> 8) & 1 ? 1.f : -1.f) * s[U_FORCE + H_RLIM + r];
   }
-#pragma unroll 1
+H_UNROLL(NEWTON_AUX_UNROLL)
   for (int a = 0; a < nbasis; a++) {
     const unsigned mk = ((const unsigned*)(s + U_BMASK))[a];
     if ((mk >> lane) & 1u) jtf = fmaf(s[U_B + a * B_STRIDE + __popc(mk & ((1u << lane) - 1u))], s[U_BV + a], jtf);
@@ -358,7 +364,7 @@ static __device__ __noinline__ float newton_weights(float* s, const DevModel& m,
     const float D = ci[6];
     float* w = s + U_CON + 16 * c;
     w[0] = 0.f; w[1] = 0.f; w[2] = 0.f; w[3] = 0.f; w[4] = 0.f; w[5] = 0.f; w[6] = 0.f;
-#pragma unroll 1
+H_UNROLL(NEWTON_AUX_UNROLL)
     for (int e = 0; e < ne; e++) {
       const float act = jar[eo + e] < 0.f ? D : 0.f;
       w[0] += act;
@@ -404,7 +410,7 @@ static __device__ __noinline__ bool newton_direction(float* s, const DevModel& m
   if (lane < m.nv) {
     const float* Mr = s + S_MS + lane * MS_STRIDE;
     int d = 0;
-#pragma unroll 1
+H_UNROLL(NEWTON_ASM_UNROLL)
     for (unsigned mk = m.dof_anc[lane]; mk; mk &= mk - 1, d++) A[hidx(lane, __ffs(mk) - 1)] = Mr[d];
     A[hidx(lane, lane)] = Mr[d] + diag;
   } else {
@@ -435,7 +441,7 @@ static __device__ __noinline__ bool newton_direction(float* s, const DevModel& m
     }
     // columns j <= lane of the contact's dofs; the compact column index runs with the set bits
     int tj = 0;
-#pragma unroll 1
+H_UNROLL(NEWTON_ASM_UNROLL)
     for (unsigned mk = mask & (0xffffffffu >> (31 - lane)); mk; mk &= mk - 1, tj++) {
       float acc = al0 * B0[tj];
       if (nb > 1) { acc = fmaf(al1, B0[B_STRIDE + tj], acc); acc = fmaf(al2, B0[2 * B_STRIDE + tj], acc); }
